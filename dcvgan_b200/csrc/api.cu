@@ -1,0 +1,125 @@
+// C-ABI glue: error reporting and the convolution-family dispatchers.
+#include "common.cuh"
+#include "conv_geom.cuh"
+#include <string.h>
+
+namespace dcv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
+}
+
+// implemented in simt_conv.cu / tc_conv.cu
+int conv_simt(const dcv_geom*, int, int, const void*, int64_t, const void*, void*, int64_t, int, float, cudaStream_t);
+int wgrad_simt(const dcv_geom*, int, const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int64_t, int,
+               void*, int64_t, cudaStream_t);
+int64_t wgrad_simt_ws_bytes(const dcv_geom*);
+int pack_weight_simt(const dcv_geom*, int, const float*, int64_t, int64_t, int64_t, float*, cudaStream_t);
+int conv_tc_supported(const dcv_geom*, int);
+int64_t packed_weight_tc_bytes(const dcv_geom*, int);
+int pack_weight_tc(const dcv_geom*, int, const float*, int64_t, int64_t, int64_t, void*, cudaStream_t);
+int conv_tc(const dcv_geom*, int, const void*, int64_t, const void*, void*, int64_t, int, float, cudaStream_t);
+int wgrad_tc_supported(const dcv_geom*);
+int64_t wgrad_tc_ws_bytes(const dcv_geom*);
+int wgrad_tc(const dcv_geom*, const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int64_t, int, void*,
+             int64_t, cudaStream_t);
+
+static int check_geom(const dcv_geom* g) {
+  DCV_REQUIRE(g, "null geometry");
+  DCV_REQUIRE(g->N >= 0 && g->Cl > 0 && g->Cs > 0, "bad geometry: N=%d Cl=%d Cs=%d", g->N, g->Cl, g->Cs);
+  DCV_REQUIRE(g->kt > 0 && g->kh > 0 && g->kw > 0 && g->st > 0 && g->sh > 0 && g->sw > 0, "bad kernel/stride");
+  DCV_REQUIRE(g->Tl > 0 && g->Hl > 0 && g->Wl > 0 && g->Ts > 0 && g->Hs > 0 && g->Ws > 0, "bad extents");
+  // S extent must be what a convolution of L produces: floor((L + 2p - k)/s) + 1
+  DCV_REQUIRE(g->Ts == (g->Tl + 2 * g->pt - g->kt) / g->st + 1 && g->Hs == (g->Hl + 2 * g->ph - g->kh) / g->sh + 1 &&
+              g->Ws == (g->Wl + 2 * g->pw - g->kw) / g->sw + 1, "inconsistent L/S extents");
+  return 0;
+}
+
+}  // namespace dcv
+
+using namespace dcv;
+
+extern "C" {
+
+int dcv_abi_version(void) { return DCV_ABI_VERSION; }
+const char* dcv_last_error(void) { return g_err; }
+
+int dcv_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device"); return 0; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return 0; }
+  if (prop.major != 10) { set_error("device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor); return 0; }
+  return 1;
+}
+
+int64_t dcv_packed_weight_bytes(const dcv_geom* g, int dir, int impl) {
+  if (check_geom(g)) return -1;
+  if (impl == DCV_IMPL_TC) return packed_weight_tc_bytes(g, dir);
+  return (int64_t)g->kt * g->kh * g->kw * g->Cl * g->Cs * sizeof(float);
+}
+
+int dcv_pack_weight(const dcv_geom* g, int dir, int impl, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
+                    void* out, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DCV_REQUIRE(w && out, "pack_weight: null pointer");
+  if (impl == DCV_IMPL_TC) return pack_weight_tc(g, dir, w, s_l, s_s, s_tap, out, as_stream(stream));
+  return pack_weight_simt(g, dir, w, s_l, s_s, s_tap, (float*)out, as_stream(stream));
+}
+
+int dcv_conv_tc_supported(const dcv_geom* g, int dir) {
+  if (check_geom(g)) return 0;
+  return conv_tc_supported(g, dir);
+}
+
+int dcv_conv(const dcv_geom* g, int dir, int impl, int dtype, const void* x, int64_t ldx, const void* wp, void* y,
+             int64_t ldy, int act, float slope, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DCV_REQUIRE(x && wp && y, "conv: null pointer");
+  DCV_REQUIRE(dtype == DCV_F32 || dtype == DCV_BF16, "conv: bad dtype %d", dtype);
+  if (g->N == 0) return 0;
+  if (impl == DCV_IMPL_TC) {
+    DCV_REQUIRE(dtype == DCV_BF16, "conv: the tcgen05 kernel computes in bf16");
+    return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, as_stream(stream));
+  }
+  return conv_simt(g, dir, dtype, x, ldx, wp, y, ldy, act, slope, as_stream(stream));
+}
+
+int64_t dcv_wgrad_workspace_bytes(const dcv_geom* g, int impl) {
+  if (check_geom(g)) return -1;
+  return impl == DCV_IMPL_TC ? wgrad_tc_ws_bytes(g) : wgrad_simt_ws_bytes(g);
+}
+
+int dcv_wgrad_tc_supported(const dcv_geom* g) {
+  if (check_geom(g)) return 0;
+  return wgrad_tc_supported(g);
+}
+
+int dcv_wgrad(const dcv_geom* g, int impl, int dtype, const void* xl, int64_t ldl, const void* xs, int64_t lds, float* dw,
+              int64_t s_l, int64_t s_s, int64_t s_tap, int accumulate, void* ws, int64_t ws_bytes, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DCV_REQUIRE(xl && xs && dw && ws, "wgrad: null pointer");
+  DCV_REQUIRE(g->N > 0, "wgrad: empty batch");
+  if (impl == DCV_IMPL_TC) {
+    DCV_REQUIRE(dtype == DCV_BF16, "wgrad: the tcgen05 kernel computes in bf16");
+    return wgrad_tc(g, xl, ldl, xs, lds, dw, s_l, s_s, s_tap, accumulate, ws, ws_bytes, as_stream(stream));
+  }
+  return wgrad_simt(g, dtype, xl, ldl, xs, lds, dw, s_l, s_s, s_tap, accumulate, ws, ws_bytes, as_stream(stream));
+}
+
+}  // extern "C"

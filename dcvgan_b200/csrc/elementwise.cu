@@ -1,0 +1,469 @@
+// HBM-bound layers of the DCVGAN step: BatchNorm statistics / apply / backward, activations,
+// Dropout2d scaling, Noise, softmax, layout conversion, temporal difference.
+// Everything is channels-last with an explicit pixel stride, fp32 math, fp32 or bf16 storage.
+#include "common.cuh"
+
+namespace dcv {
+
+static inline int ew_blocks(int64_t total, int per_thread = 1) {
+  int64_t b = (total + 256 * per_thread - 1) / (256 * per_thread);
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-channel reductions.  Block b reduces rows [b*rpb, (b+1)*rpb) into partials[b][k][C].
+// F(row, c, &v0, &v1) yields the two addends.
+template <typename F>
+__device__ __forceinline__ void channel_reduce2(int64_t rows, int C, float* __restrict__ partials, F f) {
+  __shared__ float s0[256];
+  __shared__ float s1[256];
+  const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t rb = (int64_t)blockIdx.x * rpb;
+  int64_t re = rb + rpb; if (re > rows) re = rows;
+  float* out = partials + (int64_t)blockIdx.x * 2 * C;
+  const int tid = threadIdx.x;
+  if (C <= 256) {
+    const int lanes = 256 / C;
+    const int c = tid % C, r = tid / C;
+    float a0 = 0.f, a1 = 0.f;
+    if (r < lanes) {
+      for (int64_t row = rb + r; row < re; row += lanes) {
+        float v0, v1; f(row, c, v0, v1); a0 += v0; a1 += v1;
+      }
+    }
+    s0[tid] = a0; s1[tid] = a1;
+    __syncthreads();
+    if (r == 0) {
+      for (int rr = 1; rr < lanes; ++rr) { a0 += s0[rr * C + c]; a1 += s1[rr * C + c]; }
+      out[c] = a0; out[C + c] = a1;
+    }
+  } else {
+    for (int c = tid; c < C; c += 256) {
+      float a0 = 0.f, a1 = 0.f;
+      for (int64_t row = rb; row < re; ++row) { float v0, v1; f(row, c, v0, v1); a0 += v0; a1 += v1; }
+      out[c] = a0; out[C + c] = a1;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C,
+                                                        float* __restrict__ partials) {
+  channel_reduce2(rows, C, partials, [&](int64_t row, int c, float& v0, float& v1) {
+    const float v = ldf(z + row * ldz + c); v0 = v; v1 = v * v;
+  });
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblk, int C, double count, float eps,
+                                   float momentum, float* running_mean, float* running_var,
+                                   float* __restrict__ mean, float* __restrict__ invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = 0; b < nblk; ++b) { s0 += partials[(int64_t)b * 2 * C + c]; s1 += partials[(int64_t)b * 2 * C + C + c]; }
+  const double m = s0 / count;
+  double var = s1 / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, float eps,
+                                     float* __restrict__ mean, float* __restrict__ invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = rm[c];
+  invstd[c] = 1.0f / sqrtf(rv[c] + eps);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
+              const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+              const float* __restrict__ drop, int64_t rows_per_n, int act, float slope, T* __restrict__ a, int64_t lda) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C; const int c = (int)(i - row * C);
+    float v = ldf(z + row * ldz + c);
+    if (mean) {
+      v = (v - mean[c]) * invstd[c];
+      if (gamma) v = v * gamma[c] + beta[c];
+    }
+    if (drop) v *= drop[(row / rows_per_n) * C + c];
+    stf(a + row * lda + c, apply_act(v, act, slope));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, int64_t lda,
+                         const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ drop, int64_t rows_per_n,
+                         int act, float slope, float* __restrict__ partials) {
+  channel_reduce2(rows, C, partials, [&](int64_t row, int c, float& v0, float& v1) {
+    float du = ldf(da + row * ldda + c) * act_grad_from_out(ldf(a + row * lda + c), act, slope);
+    if (drop) du *= drop[(row / rows_per_n) * C + c];
+    const float xhat = (ldf(z + row * ldz + c) - mean[c]) * invstd[c];
+    v0 = du; v1 = du * xhat;
+  });
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int C, float* __restrict__ sums,
+                                       float* dgamma, float* dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = 0; b < nblk; ++b) { s0 += partials[(int64_t)b * 2 * C + c]; s1 += partials[(int64_t)b * 2 * C + C + c]; }
+  sums[c] = (float)s0; sums[C + c] = (float)s1;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s0 : (float)s0;
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)s1 : (float)s1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, int64_t lda,
+                        const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                        const float* __restrict__ drop, int64_t rows_per_n, int act, float slope,
+                        const float* __restrict__ sums, float inv_count, T* __restrict__ dz, int64_t lddz) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C; const int c = (int)(i - row * C);
+    float du = ldf(da + row * ldda + c) * act_grad_from_out(ldf(a + row * lda + c), act, slope);
+    if (drop) du *= drop[(row / rows_per_n) * C + c];
+    const float is = invstd[c];
+    const float xhat = (ldf(z + row * ldz + c) - mean[c]) * is;
+    const float g = gamma ? gamma[c] : 1.f;
+    const float v = g * is * (du - sums[c] * inv_count - xhat * sums[C + c] * inv_count);
+    stf(dz + row * lddz + c, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, int64_t lda, int64_t rows, int C,
+               int act, float slope, T* __restrict__ dz, int64_t lddz) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C; const int c = (int)(i - row * C);
+    stf(dz + row * lddz + c, ldf(da + row * ldda + c) * act_grad_from_out(ldf(a + row * lda + c), act, slope));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_noise_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ noise, float sigma, int64_t rows,
+                 int C, T* __restrict__ out, int64_t ldo) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C; const int c = (int)(i - row * C);
+    stf(out + row * ldo + c, ldf(x + row * ldx + c) + sigma * noise[i]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+axpy_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __restrict__ out, int64_t ldo, int accumulate) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C; const int c = (int)(i - row * C);
+    float v = ldf(x + row * ldx + c);
+    if (accumulate) v += ldf(out + row * ldo + c);
+    stf(out + row * ldo + c, v);
+  }
+}
+
+// out[n, t, p, c] = x[n, t+1, p, c] - x[n, t, p, c], t in [0, T-1)
+template <typename T>
+__global__ void __launch_bounds__(256)
+tdiff_kernel(const T* __restrict__ x, int64_t ldx, int N, int Tn, int64_t hw, int C, T* __restrict__ out, int64_t ldo) {
+  const int64_t total = (int64_t)N * (Tn - 1) * hw * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); int64_t r = i / C;
+    const int64_t p = r % hw; r /= hw;
+    const int t = (int)(r % (Tn - 1)); const int n = (int)(r / (Tn - 1));
+    const int64_t src = ((int64_t)n * Tn + t) * hw + p;
+    const float v = ldf(x + (src + hw) * ldx + c) - ldf(x + src * ldx + c);
+    stf(out + (((int64_t)n * (Tn - 1) + t) * hw + p) * ldo + c, v);
+  }
+}
+
+// dx[n,t] (+)= dy[n,t-1] - dy[n,t]  (terms dropped where out of range)
+template <typename T>
+__global__ void __launch_bounds__(256)
+tdiff_bwd_kernel(const T* __restrict__ dy, int64_t lddy, int N, int Tn, int64_t hw, int C, T* __restrict__ dx,
+                 int64_t lddx, int accumulate) {
+  const int64_t total = (int64_t)N * Tn * hw * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); int64_t r = i / C;
+    const int64_t p = r % hw; r /= hw;
+    const int t = (int)(r % Tn); const int n = (int)(r / Tn);
+    float v = 0.f;
+    if (t >= 1) v += ldf(dy + (((int64_t)n * (Tn - 1) + (t - 1)) * hw + p) * lddy + c);
+    if (t < Tn - 1) v -= ldf(dy + (((int64_t)n * (Tn - 1) + t) * hw + p) * lddy + c);
+    T* d = dx + (((int64_t)n * Tn + t) * hw + p) * lddx + c;
+    if (accumulate) v += ldf(d);
+    stf(d, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C, T* __restrict__ y, int64_t ldy) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
+    const T* zr = z + row * ldz; T* yr = y + row * ldy;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, ldf(zr + c));
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += expf(ldf(zr + c) - mx);
+    const float inv = 1.f / s;
+    for (int c = 0; c < C; ++c) stf(yr + c, expf(ldf(zr + c) - mx) * inv);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ y, int64_t ldy, int64_t rows, int C,
+                   T* __restrict__ dz, int64_t lddz) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
+    const T* dyr = dy + row * lddy; const T* yr = y + row * ldy; T* dzr = dz + row * lddz;
+    float dot = 0.f;
+    for (int c = 0; c < C; ++c) dot += ldf(dyr + c) * ldf(yr + c);
+    for (int c = 0; c < C; ++c) stf(dzr + c, ldf(yr + c) * (ldf(dyr + c) - dot));
+  }
+}
+
+// torch.argmax returns the first maximal index; scatter +1 there, -1 elsewhere
+template <typename T>
+__global__ void __launch_bounds__(256)
+segm_remap_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __restrict__ y, int64_t ldy) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
+    const T* xr = x + row * ldx; T* yr = y + row * ldy;
+    int best = 0; float bv = ldf(xr);
+    for (int c = 1; c < C; ++c) { const float v = ldf(xr + c); if (v > bv) { bv = v; best = c; } }
+    for (int c = 0; c < C; ++c) stf(yr + c, c == best ? 1.f : -1.f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+to_cl_kernel(const float* __restrict__ src, int64_t sn, int64_t sc, int64_t st, int64_t sh, int64_t sw, int N, int C,
+             int Tn, int H, int W, T* __restrict__ dst, int64_t ld) {
+  const int64_t total = (int64_t)N * Tn * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); int64_t r = i / C;
+    const int w = (int)(r % W); int64_t q = r / W;
+    const int h = (int)(q % H); q /= H;
+    const int t = (int)(q % Tn); const int n = (int)(q / Tn);
+    stf(dst + r * ld + c, src[n * sn + c * sc + t * st + h * sh + w * sw]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+from_cl_kernel(const T* __restrict__ src, int64_t ld, int N, int C, int Tn, int H, int W, float* __restrict__ dst,
+               int64_t sn, int64_t sc, int64_t st, int64_t sh, int64_t sw, int accumulate) {
+  const int64_t total = (int64_t)N * Tn * H * W * C;
+  // iterate with w fastest, then h, t, c, n: the usual dense NC(T)HW destination is then written coalesced
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W); int64_t q = i / W;
+    const int h = (int)(q % H); q /= H;
+    const int t = (int)(q % Tn); q /= Tn;
+    const int c = (int)(q % C); const int n = (int)(q / C);
+    const int64_t row = (((int64_t)n * Tn + t) * H + h) * W + w;
+    float v = ldf(src + row * ld + c);
+    float* d = dst + n * sn + c * sc + t * st + h * sh + w * sw;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256)
+copy_cl_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst, int64_t ldd, int64_t rows, int C) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C; const int c = (int)(i - row * C);
+    stf(dst + row * ldd + c, ldf(src + row * lds + c));
+  }
+}
+
+}  // namespace dcv
+
+using namespace dcv;
+
+#define DISPATCH_T(dtype, ...)                                 \
+  do {                                                         \
+    if ((dtype) == DCV_F32) { using T = float; __VA_ARGS__; }  \
+    else { using T = __nv_bfloat16; __VA_ARGS__; }             \
+  } while (0)
+
+extern "C" {
+
+int dcv_bn_stats_blocks(int64_t rows, int C) {
+  (void)C;
+  int64_t b = rows / 64;
+  if (b > 148 * 4) b = 148 * 4;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int dcv_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float* partials, void* stream) {
+  const int nblk = dcv_bn_stats_blocks(rows, C);
+  DISPATCH_T(dtype, bn_stats_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials));
+  return check_launch("bn_stats");
+}
+
+int dcv_bn_finalize(const float* partials, int nblk, int C, int64_t count, float eps, float momentum,
+                    float* running_mean, float* running_var, float* mean, float* invstd, void* stream) {
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partials, nblk, C, (double)count, eps, momentum,
+                                                                    running_mean, running_var, mean, invstd);
+  return check_launch("bn_finalize");
+}
+
+int dcv_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean,
+                      float* invstd, void* stream) {
+  bn_eval_stats_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(running_mean, running_var, C, eps, mean, invstd);
+  return check_launch("bn_eval_stats");
+}
+
+int dcv_bn_act(int dtype, const void* z, int64_t ldz, int64_t rows, int C, const float* mean, const float* invstd,
+               const float* gamma, const float* beta, const float* drop, int64_t rows_per_n, int act, float slope,
+               void* a, int64_t lda, void* stream) {
+  if (rows * C == 0) return 0;
+  DISPATCH_T(dtype, bn_act_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
+                        (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope, (T*)a, lda));
+  return check_launch("bn_act");
+}
+
+int dcv_bn_act_bwd_reduce(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, const void* z,
+                          int64_t ldz, int64_t rows, int C, const float* mean, const float* invstd, const float* drop,
+                          int64_t rows_per_n, int act, float slope, float* partials, void* stream) {
+  const int nblk = dcv_bn_stats_blocks(rows, C);
+  DISPATCH_T(dtype, bn_act_bwd_reduce_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>(
+                        (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, drop, rows_per_n,
+                        act, slope, partials));
+  return check_launch("bn_act_bwd_reduce");
+}
+
+int dcv_bn_bwd_finalize(const float* partials, int nblk, int C, float* sums, float* dgamma, float* dbeta,
+                        int accumulate, void* stream) {
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partials, nblk, C, sums, dgamma, dbeta, accumulate);
+  return check_launch("bn_bwd_finalize");
+}
+
+int dcv_bn_act_bwd_apply(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, const void* z,
+                         int64_t ldz, int64_t rows, int C, const float* mean, const float* invstd, const float* gamma,
+                         const float* drop, int64_t rows_per_n, int act, float slope, const float* sums, int64_t count,
+                         void* dz, int64_t lddz, void* stream) {
+  if (rows * C == 0) return 0;
+  DISPATCH_T(dtype, bn_act_bwd_apply_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
+                        (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, gamma, drop,
+                        rows_per_n, act, slope, sums, 1.0f / (float)count, (T*)dz, lddz));
+  return check_launch("bn_act_bwd_apply");
+}
+
+int dcv_act_bwd(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, int64_t rows, int C, int act,
+                float slope, void* dz, int64_t lddz, void* stream) {
+  if (rows * C == 0) return 0;
+  DISPATCH_T(dtype, act_bwd_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
+                        (const T*)da, ldda, (const T*)a, lda, rows, C, act, slope, (T*)dz, lddz));
+  return check_launch("act_bwd");
+}
+
+int dcv_add_noise(int dtype, const void* x, int64_t ldx, const float* noise, float sigma, int64_t rows, int C,
+                  void* out, int64_t ldo, void* stream) {
+  if (rows * C == 0) return 0;
+  DISPATCH_T(dtype, add_noise_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
+                        (const T*)x, ldx, noise, sigma, rows, C, (T*)out, ldo));
+  return check_launch("add_noise");
+}
+
+int dcv_axpy(int dtype, const void* x, int64_t ldx, int64_t rows, int C, void* out, int64_t ldo, int accumulate,
+             void* stream) {
+  if (rows * C == 0) return 0;
+  DISPATCH_T(dtype, axpy_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>((const T*)x, ldx, rows, C,
+                                                                                          (T*)out, ldo, accumulate));
+  return check_launch("axpy");
+}
+
+int dcv_tdiff(int dtype, const void* x, int64_t ldx, int N, int T_, int64_t hw, int C, void* out, int64_t ldo,
+              void* stream) {
+  const int64_t total = (int64_t)N * (T_ - 1) * hw * C;
+  if (total <= 0) return 0;
+  DISPATCH_T(dtype, tdiff_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>((const T*)x, ldx, N, T_, hw, C,
+                                                                                        (T*)out, ldo));
+  return check_launch("tdiff");
+}
+
+int dcv_tdiff_bwd(int dtype, const void* dy, int64_t lddy, int N, int T_, int64_t hw, int C, void* dx, int64_t lddx,
+                  int accumulate, void* stream) {
+  const int64_t total = (int64_t)N * T_ * hw * C;
+  if (total <= 0) return 0;
+  DISPATCH_T(dtype, tdiff_bwd_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(
+                        (const T*)dy, lddy, N, T_, hw, C, (T*)dx, lddx, accumulate));
+  return check_launch("tdiff_bwd");
+}
+
+int dcv_softmax(int dtype, const void* z, int64_t ldz, int64_t rows, int C, void* y, int64_t ldy, void* stream) {
+  if (rows == 0) return 0;
+  DISPATCH_T(dtype, softmax_kernel<T><<<ew_blocks(rows), 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, (T*)y, ldy));
+  return check_launch("softmax");
+}
+
+int dcv_softmax_bwd(int dtype, const void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t rows, int C, void* dz,
+                    int64_t lddz, void* stream) {
+  if (rows == 0) return 0;
+  DISPATCH_T(dtype, softmax_bwd_kernel<T><<<ew_blocks(rows), 256, 0, as_stream(stream)>>>((const T*)dy, lddy, (const T*)y,
+                                                                                          ldy, rows, C, (T*)dz, lddz));
+  return check_launch("softmax_bwd");
+}
+
+int dcv_segm_remap(int dtype, const void* x, int64_t ldx, int64_t rows, int C, void* y, int64_t ldy, void* stream) {
+  if (rows == 0) return 0;
+  DISPATCH_T(dtype, segm_remap_kernel<T><<<ew_blocks(rows), 256, 0, as_stream(stream)>>>((const T*)x, ldx, rows, C, (T*)y, ldy));
+  return check_launch("segm_remap");
+}
+
+int dcv_to_channels_last(int dtype, const float* src, int64_t sn, int64_t sc, int64_t st, int64_t sh, int64_t sw, int N,
+                         int C, int T_, int H, int W, void* dst, int64_t ld, void* stream) {
+  const int64_t total = (int64_t)N * T_ * H * W * C;
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, to_cl_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(src, sn, sc, st, sh, sw, N, C, T_,
+                                                                                        H, W, (T*)dst, ld));
+  return check_launch("to_channels_last");
+}
+
+int dcv_from_channels_last(int dtype, const void* src, int64_t ld, int N, int C, int T_, int H, int W, float* dst,
+                           int64_t sn, int64_t sc, int64_t st, int64_t sh, int64_t sw, int accumulate, void* stream) {
+  const int64_t total = (int64_t)N * T_ * H * W * C;
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, from_cl_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(
+                        (const T*)src, ld, N, C, T_, H, W, dst, sn, sc, st, sh, sw, accumulate));
+  return check_launch("from_channels_last");
+}
+
+int dcv_copy_cl(int src_dtype, const void* src, int64_t lds, int dst_dtype, void* dst, int64_t ldd, int64_t rows, int C,
+                void* stream) {
+  const int64_t total = rows * C;
+  if (total == 0) return 0;
+  const int nb = ew_blocks(total, 4);
+  cudaStream_t s = as_stream(stream);
+  if (src_dtype == DCV_F32 && dst_dtype == DCV_F32)
+    copy_cl_kernel<float, float><<<nb, 256, 0, s>>>((const float*)src, lds, (float*)dst, ldd, rows, C);
+  else if (src_dtype == DCV_F32)
+    copy_cl_kernel<float, __nv_bfloat16><<<nb, 256, 0, s>>>((const float*)src, lds, (__nv_bfloat16*)dst, ldd, rows, C);
+  else if (dst_dtype == DCV_F32)
+    copy_cl_kernel<__nv_bfloat16, float><<<nb, 256, 0, s>>>((const __nv_bfloat16*)src, lds, (float*)dst, ldd, rows, C);
+  else
+    copy_cl_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, 256, 0, s>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, rows, C);
+  return check_launch("copy_cl");
+}
+
+}  // extern "C"

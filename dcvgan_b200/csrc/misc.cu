@@ -1,0 +1,292 @@
+// GRU latent trajectory, adversarial/hinge loss heads and fused multi-tensor Adam.
+#include "common.cuh"
+
+namespace dcv {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float softplusf_(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+
+// ------------------------------------------------------------------------------------------
+// GRU trajectory (generator.py:84-101): h_t = GRUCell(eps_t, h_{t-1}), t = 1..T, gate order r,z,n.
+// One warp walks one batch row through all T steps; lanes own gate rows j = lane, lane+32, ...
+// Shared memory per warp: h[D] e[D] gi[3D] gh[3D] (+ backward: dgi[3D] dgh[3D] dh[D] dW_ih[3D*D] dW_hh[3D*D] db[6D])
+__global__ void gru_fwd_kernel(const float* __restrict__ h0, const float* __restrict__ eps, const float* __restrict__ w_ih,
+                               const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+                               const float* __restrict__ b_hh, int B, int T, int D, float* __restrict__ hs) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  float* h = sm + warp * (8 * D);
+  float* e = h + D; float* gi = e + D; float* gh = gi + 3 * D;
+  for (int b = blockIdx.x * nw + warp; b < B; b += gridDim.x * nw) {
+    for (int d = lane; d < D; d += 32) h[d] = h0[b * D + d];
+    __syncwarp();
+    for (int t = 0; t < T; ++t) {
+      for (int d = lane; d < D; d += 32) e[d] = eps[((int64_t)t * B + b) * D + d];
+      __syncwarp();
+      for (int j = lane; j < 3 * D; j += 32) {
+        float a = b_ih[j], c = b_hh[j];
+        for (int k = 0; k < D; ++k) { a = fmaf(w_ih[j * D + k], e[k], a); c = fmaf(w_hh[j * D + k], h[k], c); }
+        gi[j] = a; gh[j] = c;
+      }
+      __syncwarp();
+      for (int d = lane; d < D; d += 32) {
+        const float r = sigmoidf_(gi[d] + gh[d]);
+        const float z = sigmoidf_(gi[D + d] + gh[D + d]);
+        const float n = tanhf(gi[2 * D + d] + r * gh[2 * D + d]);
+        const float hn = (1.f - z) * n + z * h[d];
+        hs[((int64_t)b * T + t) * D + d] = hn;
+        gi[d] = hn;  // stash; h[] is still read by other lanes' nothing at this point, but keep it simple
+      }
+      __syncwarp();
+      for (int d = lane; d < D; d += 32) h[d] = gi[d];
+      __syncwarp();
+    }
+  }
+}
+
+// Backward through time.  A single block (nw warps); warp w handles rows w, w+nw, ... and keeps its
+// weight-gradient accumulators in shared memory; the block then sums the warps in a fixed order, so
+// the result is deterministic.
+__global__ void gru_bwd_kernel(const float* __restrict__ h0, const float* __restrict__ eps, const float* __restrict__ hs,
+                               const float* __restrict__ dhs, const float* __restrict__ w_ih,
+                               const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+                               const float* __restrict__ b_hh, int B, int T, int D, float* __restrict__ dw_ih,
+                               float* __restrict__ dw_hh, float* __restrict__ db_ih, float* __restrict__ db_hh,
+                               int accumulate) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  const int G = 3 * D;
+  const int per_warp = 3 * D /*h,e,dh*/ + 4 * G /*gi,gh,dgi,dgh*/ + 2 * G * D + 2 * G;
+  float* base = sm + warp * per_warp;
+  float* h = base; float* e = h + D; float* dh = e + D;
+  float* gi = dh + D; float* gh = gi + G; float* dgi = gh + G; float* dgh = dgi + G;
+  float* aWi = dgh + G; float* aWh = aWi + G * D; float* abi = aWh + G * D; float* abh = abi + G;
+  for (int i = lane; i < 2 * G * D + 2 * G; i += 32) aWi[i] = 0.f;
+  __syncwarp();
+  for (int b = warp; b < B; b += nw) {
+    for (int d = lane; d < D; d += 32) dh[d] = 0.f;
+    __syncwarp();
+    for (int t = T - 1; t >= 0; --t) {
+      for (int d = lane; d < D; d += 32) {
+        h[d] = t == 0 ? h0[b * D + d] : hs[((int64_t)b * T + (t - 1)) * D + d];
+        e[d] = eps[((int64_t)t * B + b) * D + d];
+        dh[d] += dhs[((int64_t)b * T + t) * D + d];
+      }
+      __syncwarp();
+      for (int j = lane; j < G; j += 32) {
+        float a = b_ih[j], c = b_hh[j];
+        for (int k = 0; k < D; ++k) { a = fmaf(w_ih[j * D + k], e[k], a); c = fmaf(w_hh[j * D + k], h[k], c); }
+        gi[j] = a; gh[j] = c;
+      }
+      __syncwarp();
+      for (int d = lane; d < D; d += 32) {
+        const float r = sigmoidf_(gi[d] + gh[d]);
+        const float z = sigmoidf_(gi[D + d] + gh[D + d]);
+        const float n = tanhf(gi[2 * D + d] + r * gh[2 * D + d]);
+        const float g = dh[d];
+        const float dn_pre = g * (1.f - z) * (1.f - n * n);
+        const float dz_pre = g * (h[d] - n) * z * (1.f - z);
+        const float dr_pre = dn_pre * gh[2 * D + d] * r * (1.f - r);
+        dgi[d] = dr_pre; dgi[D + d] = dz_pre; dgi[2 * D + d] = dn_pre;
+        dgh[d] = dr_pre; dgh[D + d] = dz_pre; dgh[2 * D + d] = dn_pre * r;
+        dh[d] = g * z;  // direct path to h_{t-1}
+      }
+      __syncwarp();
+      for (int j = lane; j < G; j += 32) {
+        const float a = dgi[j], c = dgh[j];
+        for (int k = 0; k < D; ++k) { aWi[j * D + k] = fmaf(a, e[k], aWi[j * D + k]); aWh[j * D + k] = fmaf(c, h[k], aWh[j * D + k]); }
+        abi[j] += a; abh[j] += c;
+      }
+      for (int k = lane; k < D; k += 32) {
+        float s = 0.f;
+        for (int j = 0; j < G; ++j) s = fmaf(dgh[j], w_hh[j * D + k], s);
+        dh[k] += s;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  const int nacc = 2 * G * D + 2 * G;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += sm[w * per_warp + 3 * D + 4 * G + i];
+    float* dst;
+    if (i < G * D) dst = dw_ih + i;
+    else if (i < 2 * G * D) dst = dw_hh + (i - G * D);
+    else if (i < 2 * G * D + G) dst = db_ih + (i - 2 * G * D);
+    else dst = db_hh + (i - 2 * G * D - G);
+    *dst = accumulate ? *dst + s : s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+loss_kernel(const T* __restrict__ y, int64_t n, int kind, float* __restrict__ loss_out, int accumulate,
+            T* __restrict__ dy, float grad_scale) {
+  __shared__ float red[256];
+  float acc = 0.f;
+  const float inv_n = 1.f / (float)n;
+  for (int64_t i = threadIdx.x; i < n; i += 256) {
+    const float v = ldf(y + i);
+    float l, g;
+    switch (kind) {
+      case DCV_LOSS_BCE_ONES:
+      case DCV_LOSS_SOFTPLUS_NEG: l = softplusf_(-v); g = sigmoidf_(v) - 1.f; break;
+      case DCV_LOSS_BCE_ZEROS: l = softplusf_(v); g = sigmoidf_(v); break;
+      case DCV_LOSS_HINGE_REAL: l = fmaxf(1.f - v, 0.f); g = (1.f - v > 0.f) ? -1.f : 0.f; break;
+      default: l = fmaxf(1.f + v, 0.f); g = (1.f + v > 0.f) ? 1.f : 0.f; break;
+    }
+    acc += l;
+    if (dy) stf(dy + i, g * inv_n * grad_scale);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float l = red[0] * inv_n;
+    loss_out[0] = accumulate ? loss_out[0] + l : l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam, one launch for many tensors.  Arithmetic follows torch.optim.Adam (single-tensor path):
+//   g += wd*p ; m = m + (g-m)(1-b1) ; v = b2*v + (1-b2) g^2 ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+constexpr int ADAM_MAXT = 40;
+constexpr int ADAM_CHUNK = 4096;  // elements per block
+struct AdamArgs {
+  float* p[ADAM_MAXT];
+  const float* g[ADAM_MAXT];
+  float* m[ADAM_MAXT];
+  float* v[ADAM_MAXT];
+  int64_t numel[ADAM_MAXT];
+  int block_start[ADAM_MAXT + 1];
+  int ntensors;
+};
+
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float b1, float b2, float eps,
+                                            float wd, float step_size, float inv_bc2_sqrt, float gscale) {
+  g = g * gscale + wd * p;
+  m = m + (g - m) * (1.f - b1);
+  v = v * b2 + (1.f - b2) * g * g;
+  const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
+  p = p - step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(AdamArgs a, float b1, float b2, float eps, float wd, float step_size, float inv_bc2_sqrt, float gscale) {
+  int t = 0;
+  while (t + 1 < a.ntensors && (int)blockIdx.x >= a.block_start[t + 1]) ++t;
+  const int64_t off = (int64_t)(blockIdx.x - a.block_start[t]) * ADAM_CHUNK;
+  const int64_t n = a.numel[t];
+  float* p = a.p[t] + off; const float* g = a.g[t] + off; float* m = a.m[t] + off; float* v = a.v[t] + off;
+  const int64_t len = (n - off) < ADAM_CHUNK ? (n - off) : ADAM_CHUNK;
+  const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
+  if (aligned && len == ADAM_CHUNK) {
+#pragma unroll
+    for (int it = 0; it < ADAM_CHUNK / (256 * 4); ++it) {
+      const int i = (it * 256 + threadIdx.x) * 4;
+      float4 pp = *reinterpret_cast<float4*>(p + i);
+      const float4 gg = *reinterpret_cast<const float4*>(g + i);
+      float4 mm = *reinterpret_cast<float4*>(m + i);
+      float4 vv = *reinterpret_cast<float4*>(v + i);
+      adam_update(pp.x, gg.x, mm.x, vv.x, b1, b2, eps, wd, step_size, inv_bc2_sqrt, gscale);
+      adam_update(pp.y, gg.y, mm.y, vv.y, b1, b2, eps, wd, step_size, inv_bc2_sqrt, gscale);
+      adam_update(pp.z, gg.z, mm.z, vv.z, b1, b2, eps, wd, step_size, inv_bc2_sqrt, gscale);
+      adam_update(pp.w, gg.w, mm.w, vv.w, b1, b2, eps, wd, step_size, inv_bc2_sqrt, gscale);
+      *reinterpret_cast<float4*>(p + i) = pp;
+      *reinterpret_cast<float4*>(m + i) = mm;
+      *reinterpret_cast<float4*>(v + i) = vv;
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < len; i += 256) {
+      float pp = p[i], mm = m[i], vv = v[i];
+      adam_update(pp, g[i], mm, vv, b1, b2, eps, wd, step_size, inv_bc2_sqrt, gscale);
+      p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+  }
+}
+
+}  // namespace dcv
+
+using namespace dcv;
+
+extern "C" {
+
+int dcv_gru_traj_fwd(const float* h0, const float* eps, const float* w_ih, const float* w_hh, const float* b_ih,
+                     const float* b_hh, int B, int T, int D, float* hs, void* stream) {
+  DCV_REQUIRE(D >= 1 && D <= 64, "gru: dim_z_motion %d out of range [1,64]", D);
+  if (B == 0) return 0;
+  const int nw = 4;
+  const int blocks = ceil_div(B, nw);
+  gru_fwd_kernel<<<blocks, nw * 32, nw * 8 * D * sizeof(float), as_stream(stream)>>>(h0, eps, w_ih, w_hh, b_ih, b_hh, B, T, D, hs);
+  return check_launch("gru_fwd");
+}
+
+int dcv_gru_traj_bwd(const float* h0, const float* eps, const float* hs, const float* dhs, const float* w_ih,
+                     const float* w_hh, const float* b_ih, const float* b_hh, int B, int T, int D, float* dw_ih,
+                     float* dw_hh, float* db_ih, float* db_hh, int accumulate, void* stream) {
+  DCV_REQUIRE(D >= 1 && D <= 64, "gru: dim_z_motion %d out of range [1,64]", D);
+  const int G = 3 * D;
+  const int per_warp = 3 * D + 4 * G + 2 * G * D + 2 * G;
+  int nw = 8;
+  while (nw > 1 && (size_t)nw * per_warp * sizeof(float) > 48 * 1024) nw /= 2;
+  DCV_REQUIRE((size_t)nw * per_warp * sizeof(float) <= 48 * 1024, "gru: dim_z_motion %d too large for BPTT kernel", D);
+  gru_bwd_kernel<<<1, nw * 32, nw * per_warp * sizeof(float), as_stream(stream)>>>(
+      h0, eps, hs, dhs, w_ih, w_hh, b_ih, b_hh, B, T, D, dw_ih, dw_hh, db_ih, db_hh, accumulate);
+  return check_launch("gru_bwd");
+}
+
+int dcv_loss_fwd_bwd(int dtype, const void* y, int64_t n, int kind, float* loss_out, int accumulate, void* dy,
+                     float grad_scale, void* stream) {
+  DCV_REQUIRE(n > 0, "loss: empty logits");
+  DCV_REQUIRE(kind >= 0 && kind <= 4, "loss: unknown kind %d", kind);
+  if (dtype == DCV_F32)
+    loss_kernel<float><<<1, 256, 0, as_stream(stream)>>>((const float*)y, n, kind, loss_out, accumulate, (float*)dy, grad_scale);
+  else
+    loss_kernel<__nv_bfloat16><<<1, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)y, n, kind, loss_out, accumulate,
+                                                                 (__nv_bfloat16*)dy, grad_scale);
+  return check_launch("loss");
+}
+
+int dcv_adam_multi(int ntensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                   const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                   float grad_scale, void* stream) {
+  DCV_REQUIRE(step >= 1, "adam: step must be >= 1");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  int i = 0;
+  while (i < ntensors) {
+    AdamArgs a;
+    int k = 0, blocks = 0;
+    while (i < ntensors && k < ADAM_MAXT) {
+      if (numel[i] > 0) {
+        a.p[k] = p[i]; a.g[k] = g[i]; a.m[k] = m[i]; a.v[k] = v[i]; a.numel[k] = numel[i];
+        a.block_start[k] = blocks;
+        blocks += (int)((numel[i] + ADAM_CHUNK - 1) / ADAM_CHUNK);
+        ++k;
+      }
+      ++i;
+    }
+    if (k == 0) break;
+    a.block_start[k] = blocks;
+    a.ntensors = k;
+    adam_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, grad_scale);
+    int rc = check_launch("adam_multi");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int dcv_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int64_t step, float grad_scale, void* stream) {
+  float* pp[1] = {p}; const float* gg[1] = {g}; float* mm[1] = {m}; float* vv[1] = {v}; int64_t nn[1] = {n};
+  return dcv_adam_multi(1, pp, gg, mm, vv, nn, lr, beta1, beta2, eps, weight_decay, step, grad_scale, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,643 @@
+// tcgen05 / TMEM / TMA implicit-GEMM correlation kernels for sm_100a (bf16 in, fp32 accumulate).
+//
+//   conv_tc   : forward / data-gradient of every Conv2d, ConvTranspose2d and Conv3d on the path whose
+//               reduction channel count is a multiple of 16.  A-operand tiles (128 output positions x CBLK
+//               channels) are fetched straight from the channels-last activation by one 5-D TMA box per
+//               (tap, channel block) - traversal strides implement the (1,2,2) convolution stride, out-of-
+//               bounds coordinates implement zero padding - so no im2col matrix ever exists in HBM.
+//               Transposed (scatter) correlations run as stride^d sub-pixel phases (blockIdx.z).
+//   wgrad_tc  : weight gradient.  Both operands are MN-major (channels contiguous, pixels = GEMM K), again
+//               straight from the activations by TMA; split over pixel ranges, fp32 partials reduced in a
+//               fixed order by wgrad_reduce (simt_conv.cu).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> registers -> global).
+#include "common.cuh"
+#include "conv_geom.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace dcv {
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (sm_100 "version 1"); see DESIGN.md for the field map
+//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle mode
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// instruction descriptor for kind::f16, bf16 x bf16 -> f32
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int TC_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+
+// ------------------------------------------------------------------------------------------ conv_tc
+struct TcConvP {
+  ConvP c;
+  int bw, bh, bt, bn;                    // box of 128 output index positions
+  int tiles_w, tiles_h, tiles_t, tiles_n;
+  int cblk, kchunks, bnt, stages;
+  int swz_layout;                        // UMMA layout code (2 = SW128, 4 = SW64, 6 = SW32)
+  int a_bytes, b_bytes, tx_bytes;
+  int64_t ldy;
+  int act; float slope;
+  int vec_ok;
+  int tmem_cols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcConvP p,
+               __nv_bfloat16* __restrict__ y) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[MAX_STAGES];
+  __shared__ uint64_t empty_bar[MAX_STAGES];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const PhaseInfo f = make_phase(p.c, blockIdx.z);
+
+  int tile = blockIdx.x;
+  const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+  const int th = tile % p.tiles_h; tile /= p.tiles_h;
+  const int tt = tile % p.tiles_t; const int tn = tile / p.tiles_t;
+  const int w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt, n0 = tn * p.bn;
+  if (w0 >= f.Qw || h0 >= f.Qh || t0 >= f.Qt) return;  // tile outside this phase (uniform per CTA)
+
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  const int ntaps = f.nt * f.nh * f.nw;
+
+  if (warp == 0 && lane == 0) { tmap_prefetch(&mapA); tmap_prefetch(&mapB); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      mbar_init(&tmem_full_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0;
+      for (int jt = 0; jt < f.nt; ++jt) {
+        const int ct = t0 * f.mult + f.offt + f.sgn * jt;
+        const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
+        for (int jh = 0; jh < f.nh; ++jh) {
+          const int ch = h0 * f.mulh + f.offh + f.sgn * jh;
+          const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
+          for (int jw = 0; jw < f.nw; ++jw, ++j) {
+            const int cw = w0 * f.mulw + f.offw + f.sgn * jw;
+            const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
+            if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_expect_tx(&full_bar[stage], (uint32_t)p.tx_bytes);
+              const uint32_t a_dst = sbase + stage * stage_bytes;
+              tma_load_5d(a_dst, &mapA, &full_bar[stage], kc * p.cblk, cw, ch, ct, n0);
+              tma_load_3d(a_dst + p.a_bytes, &mapB, &full_bar[stage], j * p.c.Kc + kc * p.cblk, blockIdx.y * p.bnt, blockIdx.z);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            ++executed;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
+      const uint32_t sbo = 8u * (uint32_t)p.cblk * 2u;
+      int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0; uint32_t accum = 0;
+      for (int jt = 0; jt < f.nt; ++jt) {
+        const int ct = t0 * f.mult + f.offt + f.sgn * jt;
+        const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
+        for (int jh = 0; jh < f.nh; ++jh) {
+          const int ch = h0 * f.mulh + f.offh + f.sgn * jh;
+          const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
+          for (int jw = 0; jw < f.nw; ++jw, ++j) {
+            const int cw = w0 * f.mulw + f.offw + f.sgn * jw;
+            const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
+            if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t a_src = sbase + stage * stage_bytes;
+              const uint32_t b_src = a_src + p.a_bytes;
+              for (int k = 0; k < p.cblk / 16; ++k) {
+                const uint64_t ad = make_sdesc(a_src + k * 32, 16, sbo, p.swz_layout);
+                const uint64_t bd = make_sdesc(b_src + k * 32, 16, sbo, p.swz_layout);
+                umma_bf16(tmem_base, ad, bd, idesc, accum);
+                accum = 1;
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            ++executed;
+          }
+        }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    // epilogue: TMEM lane quarter = warp % 4 (hardware restriction), row = quarter*32 + lane
+    const int quarter = warp % 4;
+    const int row = quarter * 32 + lane;
+    int r = row;
+    const int dw = r % p.bw; r /= p.bw;
+    const int dh = r % p.bh; r /= p.bh;
+    const int dt = r % p.bt; const int dn = r / p.bt;
+    const int qw = w0 + dw, qh = h0 + dh, qt = t0 + dt, n = n0 + dn;
+    const bool valid = qw < f.Qw && qh < f.Qh && qt < f.Qt && n < p.c.N;
+    const int64_t pos = (((int64_t)n * p.c.Ot + (qt * f.ost + f.rt)) * p.c.Oh + (qh * f.osh + f.rh)) * p.c.Ow + (qw * f.osw + f.rw);
+    __nv_bfloat16* yrow = y + pos * p.ldy;
+    const int nbase = blockIdx.y * p.bnt;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    for (int cb = 0; cb < p.bnt; cb += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb, v);
+      if (!valid) continue;
+      const int c0 = nbase + cb;
+      if (c0 >= p.c.Nc) continue;
+      if (p.vec_ok && c0 + 16 <= p.c.Nc) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = apply_act(__uint_as_float(v[2 * i]), p.act, p.slope);
+          const float b = apply_act(__uint_as_float(v[2 * i + 1]), p.act, p.slope);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < p.c.Nc) yrow[c0 + i] = __float2bfloat16_rn(apply_act(__uint_as_float(v[i]), p.act, p.slope));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ wgrad_tc
+struct TcWgradP {
+  dcv_geom g;
+  int pix;                               // pixels (GEMM K) per stage
+  int bw, bh, bt, bn;
+  int tiles_w, tiles_h, tiles_t, tiles_n;
+  int64_t ptiles_total, ptiles_per_split;
+  int G, Ns, clchunks, pairs_total, stages, tmem_cols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapS, const TcWgradP p,
+                float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[MAX_STAGES];
+  __shared__ uint64_t empty_bar[MAX_STAGES];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const dcv_geom& g = p.g;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int pair0 = blockIdx.x * p.G;
+  int Gcur = p.pairs_total - pair0; if (Gcur > p.G) Gcur = p.G;
+  const int cs0 = blockIdx.y * p.Ns;
+  const int64_t pt_begin = (int64_t)blockIdx.z * p.ptiles_per_split;
+  int64_t pt_end = pt_begin + p.ptiles_per_split; if (pt_end > p.ptiles_total) pt_end = p.ptiles_total;
+
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int blk_bytes = p.pix * 128;                       // one 64-channel block of `pix` pixels
+  const int nsb = p.Ns / 64;                               // S blocks
+  const int stage_bytes = blk_bytes * (nsb + 2 * p.G);
+
+  if (warp == 0 && lane == 0) { tmap_prefetch(&mapL); tmap_prefetch(&mapS); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      mbar_init(&tmem_full_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t pt = pt_begin; pt < pt_end; ++pt) {
+        int64_t q = pt;
+        const int w0 = (int)(q % p.tiles_w) * p.bw; q /= p.tiles_w;
+        const int h0 = (int)(q % p.tiles_h) * p.bh; q /= p.tiles_h;
+        const int t0 = (int)(q % p.tiles_t) * p.bt; const int n0 = (int)(q / p.tiles_t) * p.bn;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(blk_bytes * (nsb + 2 * Gcur)));
+        const uint32_t s_dst = sbase + stage * stage_bytes;
+        for (int b = 0; b < nsb; ++b)
+          tma_load_5d(s_dst + b * blk_bytes, &mapS, &full_bar[stage], cs0 + 64 * b, w0, h0, t0, n0);
+        const uint32_t a_dst = s_dst + nsb * blk_bytes;
+        for (int b = 0; b < 2 * Gcur; ++b) {
+          const int blk = pair0 * 2 + b;
+          const int tap = blk / p.clchunks, clc = blk % p.clchunks;
+          const int tc = tap % g.kw, tb = (tap / g.kw) % g.kh, ta = tap / (g.kw * g.kh);
+          tma_load_5d(a_dst + b * blk_bytes, &mapL, &full_bar[stage], clc * 64, w0 * g.sw - g.pw + tc,
+                      h0 * g.sh - g.ph + tb, t0 * g.st - g.pt + ta, n0);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, p.Ns, 1, 1);
+      int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
+      for (int64_t pt = pt_begin; pt < pt_end; ++pt) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t s_src = sbase + stage * stage_bytes;
+        const uint32_t a_src = s_src + nsb * blk_bytes;
+        for (int gi = 0; gi < Gcur; ++gi) {
+          uint32_t acc = accum;
+          for (int k = 0; k < p.pix / 16; ++k) {
+            const uint64_t ad = make_sdesc(a_src + (2 * gi) * blk_bytes + k * 2048, (uint32_t)blk_bytes, 1024, 2);
+            const uint64_t bd = make_sdesc(s_src + k * 2048, (uint32_t)blk_bytes, 1024, 2);
+            umma_bf16(tmem_base + gi * p.Ns, ad, bd, idesc, acc);
+            acc = 1;
+          }
+        }
+        accum = 1;
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp % 4;
+    const int row = quarter * 32 + lane;
+    const int taps = g.kt * g.kh * g.kw;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const bool has_work = pt_end > pt_begin;
+    for (int gi = 0; gi < Gcur; ++gi) {
+      const int blk = (pair0 + gi) * 2 + row / 64;
+      const int tap = blk / p.clchunks, clc = blk % p.clchunks;
+      const int cl = clc * 64 + row % 64;
+      float* out = partial + (((int64_t)blockIdx.z * taps + tap) * g.Cl + cl) * g.Cs + cs0;
+      for (int cb = 0; cb < p.Ns; cb += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(gi * p.Ns + cb), v);
+        float4* dst = reinterpret_cast<float4*>(out + cb);
+        if (has_work) {
+          dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+          dst[2] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+          dst[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
+        } else {
+          dst[0] = dst[1] = dst[2] = dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ packing
+// gather : out[n][tap][k]                 (n < npad, k < Kc)
+// scatter: out[phase][n][j][k]            (j = tap-in-phase index in the kernel's loop order)
+__global__ void pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap,
+                                      int npad, int phases, __nv_bfloat16* __restrict__ out) {
+  for (int ph = 0; ph < phases; ++ph) {
+    const PhaseInfo f = make_phase(c, ph);
+    const int ntaps = f.nt * f.nh * f.nw;
+    const int64_t per_phase = (int64_t)npad * ntaps * c.Kc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_phase; i += (int64_t)gridDim.x * blockDim.x) {
+      const int k = (int)(i % c.Kc); int64_t r = i / c.Kc;
+      const int j = (int)(r % ntaps); const int n = (int)(r / ntaps);
+      const int jw = j % f.nw, jh = (j / f.nw) % f.nh, jt = j / (f.nw * f.nh);
+      const int tap = ((f.a0t + f.ast * jt) * c.kh + (f.a0h + f.ash * jh)) * c.kw + (f.a0w + f.asw * jw);
+      float v = 0.f;
+      if (n < c.Nc) {
+        // gather: reduction channel k is an L channel, produced channel n is an S channel; scatter: swapped
+        const int cl = c.scatter ? n : k, cs = c.scatter ? k : n;
+        v = w[cl * s_l + cs * s_s + tap * s_tap];
+      }
+      out[ph * per_phase + i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// activation map: dims {C, W, H, T, N}, box {cbox, bw*ew, bh*eh, bt*et, bn}, traversal strides {1, ew, eh, et, 1}
+static int make_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int N, int64_t ld, int cbox,
+                        int bw, int bh, int bt, int bn, int ew, int eh, int et, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  DCV_REQUIRE(enc, "cuTensorMapEncodeTiled entry point unavailable");
+  DCV_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld % 8) == 0, "TMA operand must be 16-byte aligned (ptr %p, ld %lld)", ptr, (long long)ld);
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2, (cuuint64_t)T * H * W * ld * 2};
+  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)(bw * ew), (cuuint32_t)(bh * eh), (cuuint32_t)(bt * et), (cuuint32_t)bn};
+  cuuint32_t estr[5] = {1, (cuuint32_t)ew, (cuuint32_t)eh, (cuuint32_t)et, 1};
+  for (int i = 0; i < 5; ++i) DCV_REQUIRE(box[i] >= 1 && box[i] <= 256, "TMA box dim %d = %u out of range", i, box[i]);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed with %d", (int)r);
+  return 0;
+}
+
+static int make_weight_map(CUtensorMap* m, const void* ptr, int64_t K, int npad, int phases, int cbox, int nbox,
+                           CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  DCV_REQUIRE(enc, "cuTensorMapEncodeTiled entry point unavailable");
+  DCV_REQUIRE(((uintptr_t)ptr & 15) == 0, "packed weight must be 16-byte aligned");
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)npad, (cuuint64_t)phases};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * npad * 2};
+  cuuint32_t box[3] = {(cuuint32_t)cbox, (cuuint32_t)nbox, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed with %d", (int)r);
+  return 0;
+}
+
+static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+
+// choose a box (bw,bh,bt,bn) with product `target` over an index space (Qw,Qh,Qt,N)
+static void choose_box(int target, int Qw, int Qh, int Qt, int N, int* bw, int* bh, int* bt, int* bn) {
+  int rem = target;
+  *bw = pow2_floor(Qw < rem ? Qw : rem); rem /= *bw;
+  *bh = pow2_floor(Qh < rem ? Qh : rem); rem /= *bh;
+  int t = 1;
+  while (t * 2 <= rem && Qt % (t * 2) == 0) t *= 2;
+  *bt = t; rem /= t;
+  *bn = rem;
+  (void)N;
+}
+
+int tc_npad(int Nc) { return (Nc + 15) / 16 * 16; }
+static int tc_bnt(int npad) {
+  for (int b = 256; b >= 16; b -= 16) if (npad % b == 0) return b;
+  return 16;
+}
+
+int conv_tc_supported(const dcv_geom* g, int dir) {
+  const ConvP c = make_convp(g, dir);
+  if (c.Kc % 16 != 0) return 0;
+  if (c.scatter) {
+    if (g->kt % g->st || g->kh % g->sh || g->kw % g->sw) return 0;
+  } else {
+    if (g->st > 8 || g->sh > 8 || g->sw > 8) return 0;
+  }
+  return 1;
+}
+
+int64_t packed_weight_tc_bytes(const dcv_geom* g, int dir) {
+  const ConvP c = make_convp(g, dir);
+  const int taps = g->kt * g->kh * g->kw;   // sum over phases of taps-in-phase == taps when k % s == 0
+  return (int64_t)tc_npad(c.Nc) * taps * c.Kc * 2;
+}
+
+int pack_weight_tc(const dcv_geom* g, int dir, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, void* out,
+                   cudaStream_t s) {
+  DCV_REQUIRE(conv_tc_supported(g, dir), "pack_weight_tc: geometry not supported by the tcgen05 kernel");
+  const ConvP c = make_convp(g, dir);
+  const int phases = c.scatter ? g->st * g->sh * g->sw : 1;
+  const int64_t total = packed_weight_tc_bytes(g, dir) / 2 / phases;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_weight_tc_kernel<<<blocks, 256, 0, s>>>(c, w, s_l, s_s, s_tap, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
+  return check_launch("pack_weight_tc");
+}
+
+int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, int act,
+            float slope, cudaStream_t s) {
+  DCV_REQUIRE(conv_tc_supported(g, dir), "conv_tc: geometry not supported by the tcgen05 kernel");
+  TcConvP p;
+  p.c = make_convp(g, dir);
+  const ConvP& c = p.c;
+  const int phases = c.scatter ? g->st * g->sh * g->sw : 1;
+  const PhaseInfo f0 = make_phase(c, 0);
+  choose_box(128, f0.Qw, f0.Qh, f0.Qt, c.N, &p.bw, &p.bh, &p.bt, &p.bn);
+  p.tiles_w = ceil_div(f0.Qw, p.bw); p.tiles_h = ceil_div(f0.Qh, p.bh); p.tiles_t = ceil_div(f0.Qt, p.bt);
+  p.tiles_n = ceil_div(c.N, p.bn);
+  p.cblk = c.Kc % 64 == 0 ? 64 : (c.Kc % 32 == 0 ? 32 : 16);
+  p.kchunks = c.Kc / p.cblk;
+  const int npad = tc_npad(c.Nc);
+  p.bnt = tc_bnt(npad);
+  p.swz_layout = p.cblk == 64 ? 2 : (p.cblk == 32 ? 4 : 6);
+  const CUtensorMapSwizzle swz = p.cblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                              : (p.cblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  p.a_bytes = 128 * p.cblk * 2;
+  p.b_bytes = (p.bnt * p.cblk * 2 + 1023) / 1024 * 1024;
+  p.tx_bytes = p.a_bytes + p.bnt * p.cblk * 2;
+  int stages = (200 * 1024) / (p.a_bytes + p.b_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  const int ntaps0 = f0.nt * f0.nh * f0.nw;
+  if (stages > ntaps0 * p.kchunks) stages = ntaps0 * p.kchunks;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  p.ldy = ldy; p.act = act; p.slope = slope;
+  p.vec_ok = (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0);
+  p.tmem_cols = pow2_ceil(p.bnt < 32 ? 32 : p.bnt);
+
+  CUtensorMap mapA, mapB;
+  int rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn, f0.mulw, f0.mulh,
+                        f0.mult, swz);
+  if (rc) return rc;
+  const int64_t Kph = (int64_t)ntaps0 * c.Kc;
+  rc = make_weight_map(&mapB, wp, Kph, npad, phases, p.cblk, p.bnt, swz);
+  if (rc) return rc;
+
+  const int smem = stages * (p.a_bytes + p.b_bytes) + 1024;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    DCV_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n, npad / p.bnt, phases);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mapA, mapB, p, (__nv_bfloat16*)y);
+  return check_launch("conv_tc");
+}
+
+// ---- wgrad
+int wgrad_tc_supported(const dcv_geom* g) {
+  if (g->Cl % 64 || g->Cs % 64) return 0;
+  const int taps = g->kt * g->kh * g->kw;
+  if ((taps * (g->Cl / 64)) % 2) return 0;
+  if (g->st > 8 || g->sh > 8 || g->sw > 8) return 0;
+  return 1;
+}
+
+static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
+  p->g = *g;
+  p->Ns = g->Cs % 256 == 0 ? 256 : (g->Cs % 192 == 0 ? 192 : (g->Cs % 128 == 0 ? 128 : 64));
+  p->clchunks = g->Cl / 64;
+  const int taps = g->kt * g->kh * g->kw;
+  p->pairs_total = taps * p->clchunks / 2;
+  p->G = 512 / pow2_ceil(p->Ns);
+  if (p->G > 4) p->G = 4;
+  if (p->G > p->pairs_total) p->G = p->pairs_total;
+  p->tmem_cols = pow2_ceil(p->G * p->Ns < 32 ? 32 : p->G * p->Ns);
+  p->pix = 32;
+  choose_box(p->pix, g->Ws, g->Hs, g->Ts, g->N, &p->bw, &p->bh, &p->bt, &p->bn);
+  p->tiles_w = ceil_div(g->Ws, p->bw); p->tiles_h = ceil_div(g->Hs, p->bh); p->tiles_t = ceil_div(g->Ts, p->bt);
+  p->tiles_n = ceil_div(g->N, p->bn);
+  p->ptiles_total = (int64_t)p->tiles_w * p->tiles_h * p->tiles_t * p->tiles_n;
+  const int stage_bytes = p->pix * 128 * (p->Ns / 64 + 2 * p->G);
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 1) stages = 1;
+  p->stages = stages;
+  const int64_t tiles = (int64_t)ceil_div(p->pairs_total, p->G) * (g->Cs / p->Ns);
+  int64_t sp = (148 * 2 + tiles - 1) / tiles;
+  const int64_t maxs = (p->ptiles_total + 7) / 8;
+  if (sp > maxs) sp = maxs;
+  if (sp > 64) sp = 64;
+  if (sp < 1) sp = 1;
+  p->ptiles_per_split = (p->ptiles_total + sp - 1) / sp;
+  *splits = (int)((p->ptiles_total + p->ptiles_per_split - 1) / p->ptiles_per_split);
+}
+
+int64_t wgrad_tc_ws_bytes(const dcv_geom* g) {
+  TcWgradP p; int splits;
+  wgrad_tc_plan(g, &p, &splits);
+  return (int64_t)splits * g->kt * g->kh * g->kw * g->Cl * g->Cs * sizeof(float);
+}
+
+int wgrad_reduce(const float* partial, int splits, const dcv_geom* g, float* dw, int64_t s_l, int64_t s_s,
+                 int64_t s_tap, int accumulate, cudaStream_t s);
+
+int wgrad_tc(const dcv_geom* g, const void* xl, int64_t ldl, const void* xs, int64_t lds, float* dw, int64_t s_l,
+             int64_t s_s, int64_t s_tap, int accumulate, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  DCV_REQUIRE(wgrad_tc_supported(g), "wgrad_tc: geometry not supported by the tcgen05 kernel");
+  TcWgradP p; int splits;
+  wgrad_tc_plan(g, &p, &splits);
+  DCV_REQUIRE(ws_bytes >= wgrad_tc_ws_bytes(g), "wgrad_tc workspace too small");
+  CUtensorMap mapL, mapS;
+  int rc = make_act_map(&mapL, xl, g->Cl, g->Wl, g->Hl, g->Tl, g->N, ldl, 64, p.bw, p.bh, p.bt, p.bn, g->sw, g->sh, g->st,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_act_map(&mapS, xs, g->Cs, g->Ws, g->Hs, g->Ts, g->N, lds, 64, p.bw, p.bh, p.bt, p.bn, 1, 1, 1,
+                    CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  const int smem = p.stages * p.pix * 128 * (p.Ns / 64 + 2 * p.G) + 1024;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    DCV_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  dim3 grid(ceil_div(p.pairs_total, p.G), g->Cs / p.Ns, splits);
+  wgrad_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mapL, mapS, p, (float*)ws);
+  rc = check_launch("wgrad_tc");
+  if (rc) return rc;
+  return wgrad_reduce((const float*)ws, splits, g, dw, s_l, s_s, s_tap, accumulate, s);
+}
+
+}  // namespace dcv

@@ -1,0 +1,198 @@
+/*
+ * dcvgan_b200.h — C ABI of libdcvgan_b200.so
+ *
+ * Drop-in boundary for the DCVGAN training step (reference: raahii/dcvgan).
+ * The reference has no FFI of its own: its hot path is the PyTorch module surface
+ * src/generator.py, src/discriminator.py, src/loss.py, src/trainer.py:271-363 and the
+ * torch.optim.Adam steps built at src/train.py:167-176.  Every entry point below names the
+ * reference call site whose arithmetic it replaces.  The Python host side
+ * (dcvgan_b200/*.py) binds these through ctypes; see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless marked host
+ *   - the library never allocates or frees device memory: the caller owns every buffer
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*)
+ *   - return 0 on success, negative on error; dcv_last_error() gives the text
+ *   - activations are channels-last: (N, [T,] H, W, C) with an explicit pixel stride `ld`
+ *     (elements between consecutive pixels) so a tensor may be a channel slice of a wider
+ *     concat buffer (replaces torch.cat at generator.py:114,393,398,400,
+ *     discriminator.py:124,228)
+ *   - dtype: DCV_F32 (exact mode, CUDA-core fp32) or DCV_BF16 (fast mode; tcgen05 where the
+ *     shape allows, fp32 accumulate everywhere)
+ */
+#ifndef DCVGAN_B200_H
+#define DCVGAN_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCV_ABI_VERSION 1
+
+enum { DCV_F32 = 0, DCV_BF16 = 1 };
+/* activation selectors (generator.py:63,76,78,175,206,243,276; discriminator.py:82-99) */
+enum { DCV_ACT_NONE = 0, DCV_ACT_LEAKY = 1, DCV_ACT_TANH = 2 };
+/* implementation selector for the convolution entry points */
+enum { DCV_IMPL_SIMT = 0, DCV_IMPL_TC = 1 };
+/* direction of a correlation w.r.t. the geometry below */
+enum { DCV_DIR_GATHER = 0, DCV_DIR_SCATTER = 1 };
+/* loss kinds (loss.py:93-99,123-131,163-166,190-193) */
+enum {
+  DCV_LOSS_BCE_ONES = 0,   /* mean BCEWithLogits(y, 1) = mean softplus(-y)      */
+  DCV_LOSS_BCE_ZEROS = 1,  /* mean BCEWithLogits(y, 0) = mean softplus(+y)      */
+  DCV_LOSS_HINGE_REAL = 2, /* mean relu(1 - y)                                  */
+  DCV_LOSS_HINGE_FAKE = 3, /* mean relu(1 + y)                                  */
+  DCV_LOSS_SOFTPLUS_NEG = 4/* mean softplus(-y)  (HingeLoss.compute_gen_loss)   */
+};
+
+/*
+ * Geometry of one strided correlation between a "large" side L and a "small" side S:
+ *   S[n, ts, hs, ws]  <->  L[n, ts*st - pt + a, hs*sh - ph + b, ws*sw - pw + c]   for taps (a,b,c)
+ * nn.Conv2d / nn.Conv3d forward reads L and writes S (DCV_DIR_GATHER); their data gradient is
+ * DCV_DIR_SCATTER.  nn.ConvTranspose2d forward reads S and writes L (DCV_DIR_SCATTER); its data
+ * gradient is DCV_DIR_GATHER.  2-D layers use T=1, kt=1, st=1, pt=0.
+ */
+typedef struct dcv_geom {
+  int32_t N;
+  int32_t Tl, Hl, Wl, Cl;
+  int32_t Ts, Hs, Ws, Cs;
+  int32_t kt, kh, kw;
+  int32_t st, sh, sw;
+  int32_t pt, ph, pw;
+} dcv_geom;
+
+int dcv_abi_version(void);
+const char* dcv_last_error(void);
+/* 1 if the device behind the current context is sm_100 (B200); the host side refuses to run otherwise */
+int dcv_device_ok(void);
+
+/* ---- weight packing -------------------------------------------------------------------------
+ * Re-lays a PyTorch fp32 master weight for one direction of a layer.  `w` is addressed as
+ * w[cl*s_l + cs*s_s + tap*s_tap] (tap = (a*kh + b)*kw + c), which covers both
+ * nn.Conv*d (Cout,Cin,k..) and nn.ConvTranspose2d (Cin,Cout,kh,kw) layouts.
+ *   impl SIMT : out is fp32 [tap][K][Nout]           (K = reduction channels, Nout = produced channels)
+ *   impl TC   : out is bf16, GATHER : [Nout_pad][tap][K]
+ *                            SCATTER: [phase][Nout_pad][tap_in_phase][K]   (sub-pixel phases)
+ * dcv_packed_weight_bytes returns the size the caller must provide.
+ */
+int64_t dcv_packed_weight_bytes(const dcv_geom* g, int dir, int impl);
+int dcv_pack_weight(const dcv_geom* g, int dir, int impl, const float* w, int64_t s_l, int64_t s_s,
+                    int64_t s_tap, void* out, void* stream);
+
+/* ---- convolution family ---------------------------------------------------------------------
+ * dcv_conv: y = act(correlate(x, wp)); replaces every nn.Conv2d / nn.ConvTranspose2d / nn.Conv3d
+ * forward on the path (generator.py:61-73,174,204,240,274; discriminator.py:81-101,182-206,288-305)
+ * and, with the opposite `dir`, the data-gradient half of their autograd backward.
+ * dcv_conv_tc_supported tells whether the tcgen05 kernel covers (geom, dir).
+ */
+int dcv_conv_tc_supported(const dcv_geom* g, int dir);
+int dcv_conv(const dcv_geom* g, int dir, int impl, int dtype, const void* x, int64_t ldx,
+             const void* wp, void* y, int64_t ldy, int act, float slope, void* stream);
+
+/* Weight gradient: dw[cl*s_l + cs*s_s + tap*s_tap] (+)= sum_m S[m,cs] * L[gather(m,tap),cl].
+ * `ws` is scratch of dcv_wgrad_workspace_bytes(); split partial sums are reduced deterministically. */
+int64_t dcv_wgrad_workspace_bytes(const dcv_geom* g, int impl);
+int dcv_wgrad_tc_supported(const dcv_geom* g);
+int dcv_wgrad(const dcv_geom* g, int impl, int dtype, const void* xl, int64_t ldl, const void* xs,
+              int64_t lds, float* dw, int64_t s_l, int64_t s_s, int64_t s_tap, int accumulate,
+              void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- BatchNorm (training + eval), activation, dropout, noise --------------------------------
+ * Replaces nn.BatchNorm2d/3d (+ReLU/LeakyReLU, +Dropout2d between them, +Noise before the next
+ * conv): generator.py:62-71,205-211,242-248; discriminator.py:30-39,94-99,197-204,289-302.
+ * rows = N*T*H*W pixels.  partials is fp32 [nblk][2][C]; nblk = dcv_bn_stats_blocks(rows, C).
+ */
+int dcv_bn_stats_blocks(int64_t rows, int C);
+int dcv_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float* partials, void* stream);
+/* mean/invstd from partials (biased var), running stats updated with unbiased var, momentum. */
+int dcv_bn_finalize(const float* partials, int nblk, int C, int64_t count, float eps, float momentum,
+                    float* running_mean, float* running_var, float* mean, float* invstd, void* stream);
+/* eval mode: mean = running_mean, invstd = rsqrt(running_var + eps) */
+int dcv_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
+                      float* mean, float* invstd, void* stream);
+/* a = act( ((z-mean)*invstd*gamma+beta) * drop[n,c] ) ; any of mean/gamma/drop may be NULL (identity).
+ * rows_per_n = pixels per sample (dropout scale index n = row / rows_per_n). */
+int dcv_bn_act(int dtype, const void* z, int64_t ldz, int64_t rows, int C, const float* mean,
+               const float* invstd, const float* gamma, const float* beta, const float* drop,
+               int64_t rows_per_n, int act, float slope, void* a, int64_t lda, void* stream);
+/* backward: pass 1 reduces sum(du), sum(du*xhat) into partials [nblk][2][C]; pass 2 writes dz and,
+ * from the reduced sums, dgamma/dbeta (fp32, (+)= if accumulate). du = da*act'(a)*drop. */
+int dcv_bn_act_bwd_reduce(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda,
+                          const void* z, int64_t ldz, int64_t rows, int C, const float* mean,
+                          const float* invstd, const float* drop, int64_t rows_per_n, int act,
+                          float slope, float* partials, void* stream);
+int dcv_bn_bwd_finalize(const float* partials, int nblk, int C, float* sums /*[2][C]*/, float* dgamma,
+                        float* dbeta, int accumulate, void* stream);
+int dcv_bn_act_bwd_apply(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda,
+                         const void* z, int64_t ldz, int64_t rows, int C, const float* mean,
+                         const float* invstd, const float* gamma, const float* drop, int64_t rows_per_n,
+                         int act, float slope, const float* sums, int64_t count, void* dz, int64_t lddz,
+                         void* stream);
+/* plain activation backward (no BN): dz = da * act'(a) ; a is the activated output */
+int dcv_act_bwd(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, int64_t rows, int C,
+                int act, float slope, void* dz, int64_t lddz, void* stream);
+/* Noise layer (discriminator.py:30-39): out = x + sigma*noise (noise fp32, dense [rows][C]) */
+int dcv_add_noise(int dtype, const void* x, int64_t ldx, const float* noise, float sigma, int64_t rows,
+                  int C, void* out, int64_t ldo, void* stream);
+/* out (+)= x over a channel slice (gradient fan-in at U-Net skips and D inputs) */
+int dcv_axpy(int dtype, const void* x, int64_t ldx, int64_t rows, int C, void* out, int64_t ldo,
+             int accumulate, void* stream);
+/* temporal finite difference of the gradient discriminator (discriminator.py:330-331) and its adjoint */
+int dcv_tdiff(int dtype, const void* x, int64_t ldx, int N, int T, int64_t hw, int C, void* out,
+              int64_t ldo, void* stream);
+int dcv_tdiff_bwd(int dtype, const void* dy, int64_t lddy, int N, int T, int64_t hw, int C, void* dx,
+                  int64_t lddx, int accumulate, void* stream);
+/* Softmax(dim=channel) forward/backward (generator.py:75-76) */
+int dcv_softmax(int dtype, const void* z, int64_t ldz, int64_t rows, int C, void* y, int64_t ldy, void* stream);
+int dcv_softmax_bwd(int dtype, const void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t rows,
+                    int C, void* dz, int64_t lddz, void* stream);
+/* segmentation remap argmax -> {-1,+1} one-hot (generator.py:378-385) */
+int dcv_segm_remap(int dtype, const void* x, int64_t ldx, int64_t rows, int C, void* y, int64_t ldy, void* stream);
+
+/* ---- layout conversion at the module boundary -----------------------------------------------
+ * src fp32 with arbitrary element strides (n, c, t, h, w) <-> channels-last (N,T,H,W,ld) of `dtype`.
+ * Replaces the permute/view/contiguous copies at generator.py:136-139,425-433 and the frame slice
+ * x[:, :, t] at trainer.py:299,307,347 (pass T=1 and a pointer to frame t).
+ */
+int dcv_to_channels_last(int dtype, const float* src, int64_t sn, int64_t sc, int64_t st, int64_t sh,
+                         int64_t sw, int N, int C, int T, int H, int W, void* dst, int64_t ld, void* stream);
+int dcv_from_channels_last(int dtype, const void* src, int64_t ld, int N, int C, int T, int H, int W,
+                           float* dst, int64_t sn, int64_t sc, int64_t st, int64_t sh, int64_t sw,
+                           int accumulate, void* stream);
+/* dtype cast/copy of a channels-last block, optionally selecting frame t of (N,T,HW,C) */
+int dcv_copy_cl(int src_dtype, const void* src, int64_t lds, int dst_dtype, void* dst, int64_t ldd,
+                int64_t rows, int C, void* stream);
+
+/* ---- GRU latent trajectory (generator.py:58,84-101) -----------------------------------------
+ * h0 [B][D], eps [T][B][D] fp32; weights in nn.GRUCell layout (3D x D, gate order r,z,n).
+ * hs out [B][T][D].  Backward = BPTT producing fp32 weight/bias grads ((+)= if accumulate).
+ */
+int dcv_gru_traj_fwd(const float* h0, const float* eps, const float* w_ih, const float* w_hh,
+                     const float* b_ih, const float* b_hh, int B, int T, int D, float* hs, void* stream);
+int dcv_gru_traj_bwd(const float* h0, const float* eps, const float* hs, const float* dhs,
+                     const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B,
+                     int T, int D, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                     int accumulate, void* stream);
+
+/* ---- losses (loss.py) ------------------------------------------------------------------------
+ * loss_out[0] (+)= mean_i l(y_i); dy_i = grad_scale * dl/dy_i / n   (y dense, `dtype`) */
+int dcv_loss_fwd_bwd(int dtype, const void* y, int64_t n, int kind, float* loss_out, int accumulate,
+                     void* dy, float grad_scale, void* stream);
+
+/* ---- Adam (train.py:167-176, trainer.py:320-322,357-359) ---------------------------------------
+ * One launch over `ntensors` tensors.  ptrs are HOST arrays of device pointers; numel host array.
+ * L2-style weight decay (grad += wd*p), bias correction from `step` (1-based, already incremented). */
+int dcv_adam_multi(int ntensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                   const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   int64_t step, float grad_scale, void* stream);
+/* same over one flat buffer (the data-parallel path keeps params/grads/state flat per network) */
+int dcv_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCVGAN_B200_H */
