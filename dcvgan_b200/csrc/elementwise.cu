@@ -294,6 +294,21 @@ copy_cl_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst, in
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256)
+frame_copy_kernel(T* __restrict__ clips, int64_t ldc, int N, int Tn, int64_t hw, int C, int t, T* __restrict__ frames,
+                  int64_t ldfr, int reverse, int accumulate) {
+  const int64_t total = (int64_t)N * hw * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); int64_t r = i / C;
+    const int64_t p = r % hw; const int n = (int)(r / hw);
+    T* cp = clips + (((int64_t)n * Tn + t) * hw + p) * ldc + c;
+    T* fp = frames + r * ldfr + c;
+    if (!reverse) stf(fp, ldf(cp));
+    else stf(cp, accumulate ? ldf(cp) + ldf(fp) : ldf(fp));
+  }
+}
+
 }  // namespace dcv
 
 using namespace dcv;
@@ -447,6 +462,16 @@ int dcv_from_channels_last(int dtype, const void* src, int64_t ld, int N, int C,
   DISPATCH_T(dtype, from_cl_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(
                         (const T*)src, ld, N, C, T_, H, W, dst, sn, sc, st, sh, sw, accumulate));
   return check_launch("from_channels_last");
+}
+
+int dcv_frame_copy(int dtype, void* clips, int64_t ldc, int N, int T_, int64_t hw, int C, int t, void* frames, int64_t ldf,
+                   int reverse, int accumulate, void* stream) {
+  const int64_t total = (int64_t)N * hw * C;
+  if (total == 0) return 0;
+  DCV_REQUIRE(t >= 0 && t < T_, "frame_copy: frame %d out of range [0,%d)", t, T_);
+  DISPATCH_T(dtype, frame_copy_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(
+                        (T*)clips, ldc, N, T_, hw, C, t, (T*)frames, ldf, reverse, accumulate));
+  return check_launch("frame_copy");
 }
 
 int dcv_copy_cl(int src_dtype, const void* src, int64_t lds, int dst_dtype, void* dst, int64_t ldd, int64_t rows, int C,

@@ -1,0 +1,385 @@
+"""Thin torch-tensor wrappers over the C ABI (one function per dcv_* entry point family).
+
+Activations are torch tensors of shape (N, T, H, W, C), channels innermost, T == 1 for the
+2-D networks.  A tensor may be a channel-slice view of a wider buffer (that is how the
+torch.cat calls of the reference disappear); `ld` is then the pixel stride of the parent.
+PyTorch only provides memory and streams here - every arithmetic op is a libdcvgan_b200 kernel.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_TANH, DCV_BF16, DCV_F32, DIR_GATHER, DIR_SCATTER, IMPL_SIMT, IMPL_TC, Geom,
+                   check, lib)
+
+__all__ = ["ConvSpec", "Act"]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dcv_dtype(t):
+    if t.dtype == torch.float32:
+        return DCV_F32
+    if t.dtype == torch.bfloat16:
+        return DCV_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def torch_dtype(precision):
+    return torch.float32 if precision == "fp32" else torch.bfloat16
+
+
+class Act:
+    """Channels-last activation (N, T, H, W, C) with an explicit pixel stride `ld` (elements).
+
+    `base` is a flat torch tensor that owns the memory, `off` the element offset of channel 0 of
+    pixel 0.  `ch(c0, c1)` gives a channel slice that shares the parent's memory and stride.
+    """
+
+    __slots__ = ("base", "off", "n", "t", "h", "w", "c", "ld")
+
+    def __init__(self, base, off, n, t, h, w, c, ld):
+        self.base, self.off, self.n, self.t, self.h, self.w, self.c, self.ld = base, off, n, t, h, w, c, ld
+
+    @staticmethod
+    def empty(n, t, h, w, c, dtype, ld=None, zero=False):
+        ld = c if ld is None else ld
+        numel = max(n * t * h * w * ld, 1)
+        base = (torch.zeros if zero else torch.empty)(numel, dtype=dtype, device="cuda")
+        return Act(base, 0, n, t, h, w, c, ld)
+
+    @staticmethod
+    def from_dense(x):
+        """wrap a contiguous torch tensor already shaped (N,T,H,W,C)"""
+        assert x.is_contiguous() and x.dim() == 5
+        n, t, h, w, c = x.shape
+        return Act(x.view(-1), 0, n, t, h, w, c, c)
+
+    def ch(self, c0, c1):
+        assert 0 <= c0 < c1 <= self.c
+        return Act(self.base, self.off + c0, self.n, self.t, self.h, self.w, c1 - c0, self.ld)
+
+    @property
+    def ptr(self):
+        return self.base.data_ptr() + self.off * self.base.element_size()
+
+    @property
+    def dtype(self):
+        return self.base.dtype
+
+    @property
+    def device(self):
+        return self.base.device
+
+    @property
+    def shape(self):
+        return (self.n, self.t, self.h, self.w, self.c)
+
+    @property
+    def rows(self):
+        return self.n * self.t * self.h * self.w
+
+    @property
+    def spatial(self):
+        return (self.t, self.h, self.w)
+
+    def reshape_nt(self, n, t):
+        """reinterpret (N*T, 1, H, W) frames as (N, T, H, W) clips or back (same memory)"""
+        assert n * t == self.n * self.t
+        return Act(self.base, self.off, n, t, self.h, self.w, self.c, self.ld)
+
+    def torch(self):
+        """strided torch view (N,T,H,W,C) of the same memory (tests / debugging)"""
+        ld = self.ld
+        return self.base.as_strided(self.shape, (self.t * self.h * self.w * ld, self.h * self.w * ld, self.w * ld, ld, 1),
+                                    self.off)
+
+    def like(self, c=None, dtype=None):
+        return Act.empty(self.n, self.t, self.h, self.w, self.c if c is None else c, self.dtype if dtype is None else dtype)
+
+
+def cl_view(a):
+    """(ptr, ld, rows, C)"""
+    return a.ptr, a.ld, a.rows, a.c
+
+
+class ConvSpec:
+    """Static description of one convolution layer of the reference networks.
+
+    kind 'conv'  : nn.Conv2d / nn.Conv3d, weight (cout, cin, *k)      - forward = GATHER  (L = input)
+    kind 'convT' : nn.ConvTranspose2d,    weight (cin, cout, kh, kw)  - forward = SCATTER (L = output)
+    """
+
+    def __init__(self, kind, cin, cout, k, s, p):
+        assert kind in ("conv", "convT")
+        self.kind, self.cin, self.cout = kind, cin, cout
+        self.k, self.s, self.p = tuple(k), tuple(s), tuple(p)  # (t, h, w)
+        self.taps = self.k[0] * self.k[1] * self.k[2]
+
+    def out_spatial(self, in_spatial):
+        if self.kind == "conv":
+            return tuple((i + 2 * p - k) // s + 1 for i, k, s, p in zip(in_spatial, self.k, self.s, self.p))
+        return tuple((i - 1) * s - 2 * p + k for i, k, s, p in zip(in_spatial, self.k, self.s, self.p))
+
+    def geom(self, n, in_spatial):
+        out = self.out_spatial(in_spatial)
+        if self.kind == "conv":
+            l, s_, cl, cs = in_spatial, out, self.cin, self.cout
+        else:
+            l, s_, cl, cs = out, in_spatial, self.cout, self.cin
+        return Geom(n, l[0], l[1], l[2], cl, s_[0], s_[1], s_[2], cs, *self.k, *self.s, *self.p)
+
+    # element strides of the PyTorch master weight seen as w[cl, cs, tap]
+    def weight_strides(self):
+        if self.kind == "conv":      # (cout=cs, cin=cl, taps)
+            return self.taps, self.cin * self.taps, 1
+        return self.taps, self.cout * self.taps, 1  # convT: (cin=cs, cout=cl, taps)
+
+    @property
+    def fwd_dir(self):
+        return DIR_GATHER if self.kind == "conv" else DIR_SCATTER
+
+    @property
+    def bwd_dir(self):
+        return DIR_SCATTER if self.kind == "conv" else DIR_GATHER
+
+
+def _tc_ok(t):
+    ptr, ld, _, _ = cl_view(t)
+    return t.dtype == torch.bfloat16 and ptr % 16 == 0 and ld % 8 == 0
+
+
+def choose_conv_impl(g, direction, x):
+    if x.dtype == torch.bfloat16 and _tc_ok(x) and lib().dcv_conv_tc_supported(C.byref(g), direction):
+        return IMPL_TC
+    return IMPL_SIMT
+
+
+def pack_weight(spec, g, direction, impl, weight):
+    nbytes = lib().dcv_packed_weight_bytes(C.byref(g), direction, impl)
+    if nbytes < 0:
+        check(-1)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    s_l, s_s, s_tap = spec.weight_strides()
+    w = weight.detach()
+    assert w.is_contiguous() and w.dtype == torch.float32
+    check(lib().dcv_pack_weight(C.byref(g), direction, impl, w.data_ptr(), s_l, s_s, s_tap, out.data_ptr(), _stream()))
+    return out
+
+
+def conv(g, direction, impl, x, wp, y, act=ACT_NONE, slope=0.0):
+    xp, ldx, _, _ = cl_view(x)
+    yp, ldy, _, _ = cl_view(y)
+    assert x.dtype == y.dtype
+    check(lib().dcv_conv(C.byref(g), direction, impl, dcv_dtype(x), xp, ldx, wp.data_ptr(), yp, ldy, act, slope, _stream()))
+
+
+def choose_wgrad_impl(g, xl, xs):
+    if xl.dtype == torch.bfloat16 and _tc_ok(xl) and _tc_ok(xs) and lib().dcv_wgrad_tc_supported(C.byref(g)):
+        return IMPL_TC
+    return IMPL_SIMT
+
+
+def wgrad(spec, g, xl, xs, dw, accumulate=False, impl=None):
+    impl = choose_wgrad_impl(g, xl, xs) if impl is None else impl
+    nbytes = lib().dcv_wgrad_workspace_bytes(C.byref(g), impl)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=xl.device)
+    lp, ldl, _, _ = cl_view(xl)
+    sp, lds, _, _ = cl_view(xs)
+    s_l, s_s, s_tap = spec.weight_strides()
+    assert dw.is_contiguous() and dw.dtype == torch.float32
+    check(lib().dcv_wgrad(C.byref(g), impl, dcv_dtype(xl), lp, ldl, sp, lds, dw.data_ptr(), s_l, s_s, s_tap,
+                          int(accumulate), ws.data_ptr(), nbytes, _stream()))
+
+
+# ------------------------------------------------------------------------------------ BatchNorm & friends
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def bn_batch_stats(z, eps, momentum, running_mean, running_var):
+    zp, ldz, rows, c = cl_view(z)
+    nblk = lib().dcv_bn_stats_blocks(rows, c)
+    partials = torch.empty((nblk, 2, c), dtype=torch.float32, device=z.device)
+    mean = torch.empty(c, dtype=torch.float32, device=z.device)
+    invstd = torch.empty_like(mean)
+    check(lib().dcv_bn_stats(dcv_dtype(z), zp, ldz, rows, c, partials.data_ptr(), _stream()))
+    check(lib().dcv_bn_finalize(partials.data_ptr(), nblk, c, rows, eps, momentum, _p(running_mean), _p(running_var),
+                                mean.data_ptr(), invstd.data_ptr(), _stream()))
+    return mean, invstd
+
+
+def bn_eval_stats(running_mean, running_var, eps):
+    c = running_mean.numel()
+    mean = torch.empty(c, dtype=torch.float32, device=running_mean.device)
+    invstd = torch.empty_like(mean)
+    check(lib().dcv_bn_eval_stats(running_mean.data_ptr(), running_var.data_ptr(), c, eps, mean.data_ptr(),
+                                  invstd.data_ptr(), _stream()))
+    return mean, invstd
+
+
+def bn_act(z, mean, invstd, gamma, beta, drop, act, slope, out):
+    zp, ldz, rows, c = cl_view(z)
+    op, ldo, _, _ = cl_view(out)
+    rows_per_n = rows // z.n
+    check(lib().dcv_bn_act(dcv_dtype(z), zp, ldz, rows, c, _p(mean), _p(invstd), _p(gamma), _p(beta), _p(drop),
+                           rows_per_n, act, slope, op, ldo, _stream()))
+
+
+def bn_act_bwd(da, a, z, mean, invstd, gamma, drop, act, slope, dz, dgamma, dbeta, accumulate=False):
+    dap, ldda, rows, c = cl_view(da)
+    ap, lda, _, _ = cl_view(a)
+    zp, ldz, _, _ = cl_view(z)
+    dzp, lddz, _, _ = cl_view(dz)
+    rows_per_n = rows // z.n
+    nblk = lib().dcv_bn_stats_blocks(rows, c)
+    partials = torch.empty((nblk, 2, c), dtype=torch.float32, device=z.device)
+    sums = torch.empty((2, c), dtype=torch.float32, device=z.device)
+    dt = dcv_dtype(z)
+    check(lib().dcv_bn_act_bwd_reduce(dt, dap, ldda, ap, lda, zp, ldz, rows, c, mean.data_ptr(), invstd.data_ptr(),
+                                      _p(drop), rows_per_n, act, slope, partials.data_ptr(), _stream()))
+    check(lib().dcv_bn_bwd_finalize(partials.data_ptr(), nblk, c, sums.data_ptr(), _p(dgamma), _p(dbeta),
+                                    int(accumulate), _stream()))
+    check(lib().dcv_bn_act_bwd_apply(dt, dap, ldda, ap, lda, zp, ldz, rows, c, mean.data_ptr(), invstd.data_ptr(),
+                                     _p(gamma), _p(drop), rows_per_n, act, slope, sums.data_ptr(), rows, dzp, lddz,
+                                     _stream()))
+
+
+def act_bwd(da, a, act, slope, dz):
+    dap, ldda, rows, c = cl_view(da)
+    ap, lda, _, _ = cl_view(a)
+    dzp, lddz, _, _ = cl_view(dz)
+    check(lib().dcv_act_bwd(dcv_dtype(a), dap, ldda, ap, lda, rows, c, act, slope, dzp, lddz, _stream()))
+
+
+def add_noise(x, noise, sigma, out):
+    xp, ldx, rows, c = cl_view(x)
+    op, ldo, _, _ = cl_view(out)
+    assert noise.dtype == torch.float32 and noise.is_contiguous() and noise.numel() == rows * c
+    check(lib().dcv_add_noise(dcv_dtype(x), xp, ldx, noise.data_ptr(), sigma, rows, c, op, ldo, _stream()))
+
+
+def axpy(x, out, accumulate):
+    xp, ldx, rows, c = cl_view(x)
+    op, ldo, _, _ = cl_view(out)
+    check(lib().dcv_axpy(dcv_dtype(x), xp, ldx, rows, c, op, ldo, int(accumulate), _stream()))
+
+
+def tdiff(x, out):
+    xp, ldx, _, c = cl_view(x)
+    op, ldo, _, _ = cl_view(out)
+    n, t, h, w, _ = x.shape
+    check(lib().dcv_tdiff(dcv_dtype(x), xp, ldx, n, t, h * w, c, op, ldo, _stream()))
+
+
+def tdiff_bwd(dy, dx, accumulate):
+    dyp, lddy, _, c = cl_view(dy)
+    dxp, lddx, _, _ = cl_view(dx)
+    n, t, h, w, _ = dx.shape
+    check(lib().dcv_tdiff_bwd(dcv_dtype(dx), dyp, lddy, n, t, h * w, c, dxp, lddx, int(accumulate), _stream()))
+
+
+def softmax(z, y):
+    zp, ldz, rows, c = cl_view(z)
+    yp, ldy, _, _ = cl_view(y)
+    check(lib().dcv_softmax(dcv_dtype(z), zp, ldz, rows, c, yp, ldy, _stream()))
+
+
+def softmax_bwd(dy, y, dz):
+    dyp, lddy, rows, c = cl_view(dy)
+    yp, ldy, _, _ = cl_view(y)
+    dzp, lddz, _, _ = cl_view(dz)
+    check(lib().dcv_softmax_bwd(dcv_dtype(y), dyp, lddy, yp, ldy, rows, c, dzp, lddz, _stream()))
+
+
+def segm_remap(x, y):
+    xp, ldx, rows, c = cl_view(x)
+    yp, ldy, _, _ = cl_view(y)
+    check(lib().dcv_segm_remap(dcv_dtype(x), xp, ldx, rows, c, yp, ldy, _stream()))
+
+
+def to_channels_last(src, dst):
+    """src: fp32 (N,C,H,W) or (N,C,T,H,W) with arbitrary strides -> dst (N,T,H,W,C) channels-last."""
+    assert src.dtype == torch.float32 and src.is_cuda
+    if src.dim() == 4:
+        src = src.unsqueeze(2)
+    n, c, t, h, w = src.shape
+    assert tuple(dst.shape) == (n, t, h, w, c), (src.shape, dst.shape)
+    dp, ld, _, _ = cl_view(dst)
+    sn, sc, st, sh, sw = src.stride()
+    check(lib().dcv_to_channels_last(dcv_dtype(dst), src.data_ptr(), sn, sc, st, sh, sw, n, c, t, h, w, dp, ld, _stream()))
+
+
+def from_channels_last(src, dst, accumulate=False):
+    """src channels-last (N,T,H,W,C) -> dst fp32 (N,C,T,H,W) or (N,C,H,W) with arbitrary strides."""
+    assert dst.dtype == torch.float32 and dst.is_cuda
+    if dst.dim() == 4:
+        dst = dst.unsqueeze(2)
+    n, c, t, h, w = dst.shape
+    assert tuple(src.shape) == (n, t, h, w, c), (src.shape, dst.shape)
+    sp, ld, _, _ = cl_view(src)
+    sn, sc, st, sh, sw = dst.stride()
+    check(lib().dcv_from_channels_last(dcv_dtype(src), sp, ld, n, c, t, h, w, dst.data_ptr(), sn, sc, st, sh, sw,
+                                       int(accumulate), _stream()))
+
+
+def frame_extract(src, t, dst):
+    """dst (N,1,H,W,C) = frame t of src (N,T,H,W,C)   (the x[:, :, t] slice at trainer.py:299,307,347)"""
+    sp, lds, _, c = cl_view(src)
+    dp, ldd, _, _ = cl_view(dst)
+    check(lib().dcv_frame_copy(dcv_dtype(src), sp, lds, src.n, src.t, src.h * src.w, c, t, dp, ldd, 0, 0, _stream()))
+
+
+def frame_scatter(dsrc, t, dframe, accumulate=True):
+    """adjoint of frame_extract: dsrc[:, t] (+)= dframe"""
+    sp, lds, _, c = cl_view(dsrc)
+    dp, ldd, _, _ = cl_view(dframe)
+    check(lib().dcv_frame_copy(dcv_dtype(dsrc), sp, lds, dsrc.n, dsrc.t, dsrc.h * dsrc.w, c, t, dp, ldd, 1,
+                               int(accumulate), _stream()))
+
+
+def copy_cl(src, dst):
+    sp, lds, rows, c = cl_view(src)
+    dp, ldd, rows2, c2 = cl_view(dst)
+    assert rows == rows2 and c == c2
+    check(lib().dcv_copy_cl(dcv_dtype(src), sp, lds, dcv_dtype(dst), dp, ldd, rows, c, _stream()))
+
+
+# ------------------------------------------------------------------------------------ GRU, loss, Adam
+def gru_traj_fwd(h0, eps, w_ih, w_hh, b_ih, b_hh):
+    b, d = h0.shape
+    t = eps.shape[0]
+    hs = torch.empty((b, t, d), dtype=torch.float32, device=h0.device)
+    check(lib().dcv_gru_traj_fwd(h0.data_ptr(), eps.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(),
+                                 b_hh.data_ptr(), b, t, d, hs.data_ptr(), _stream()))
+    return hs
+
+
+def gru_traj_bwd(h0, eps, hs, dhs, w_ih, w_hh, b_ih, b_hh, dw_ih, dw_hh, db_ih, db_hh, accumulate=False):
+    b, d = h0.shape
+    t = eps.shape[0]
+    assert dhs.is_contiguous() and dhs.dtype == torch.float32
+    check(lib().dcv_gru_traj_bwd(h0.data_ptr(), eps.data_ptr(), hs.data_ptr(), dhs.data_ptr(), w_ih.data_ptr(),
+                                 w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), b, t, d, dw_ih.data_ptr(),
+                                 dw_hh.data_ptr(), db_ih.data_ptr(), db_hh.data_ptr(), int(accumulate), _stream()))
+
+
+def loss_fwd_bwd(y, kind, loss_out, accumulate, dy=None, grad_scale=1.0):
+    assert y.is_contiguous()
+    check(lib().dcv_loss_fwd_bwd(dcv_dtype(y), y.data_ptr(), y.numel(), kind, loss_out.data_ptr(), int(accumulate),
+                                 _p(dy), grad_scale, _stream()))
+
+
+def adam_multi(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    n = len(params)
+    arr = C.c_void_p * n
+    numel = (C.c_int64 * n)(*[p.numel() for p in params])
+    for group in (params, grads, exp_avgs, exp_avg_sqs):
+        for t in group:
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    check(lib().dcv_adam_multi(n, arr(*[p.data_ptr() for p in params]), arr(*[g.data_ptr() for g in grads]),
+                               arr(*[m.data_ptr() for m in exp_avgs]), arr(*[v.data_ptr() for v in exp_avg_sqs]), numel,
+                               lr, beta1, beta2, eps, weight_decay, step, grad_scale, _stream()))

@@ -166,6 +166,11 @@ int dcv_from_channels_last(int dtype, const void* src, int64_t ld, int N, int C,
 int dcv_copy_cl(int src_dtype, const void* src, int64_t lds, int dst_dtype, void* dst, int64_t ldd,
                 int64_t rows, int C, void* stream);
 
+/* frame t of every clip: reverse=0: dst(N,1,HW,C) = clips(N,T,HW,C)[:, t]; reverse=1: clips[:, t] (+)= dst
+ * (the image discriminator's x[:, :, t] slice, trainer.py:299,307,347, and its gradient) */
+int dcv_frame_copy(int dtype, void* clips, int64_t ldc, int N, int T, int64_t hw, int C, int t, void* frames,
+                   int64_t ldf, int reverse, int accumulate, void* stream);
+
 /* ---- GRU latent trajectory (generator.py:58,84-101) -----------------------------------------
  * h0 [B][D], eps [T][B][D] fp32; weights in nn.GRUCell layout (3D x D, gate order r,z,n).
  * hs out [B][T][D].  Backward = BPTT producing fp32 weight/bias grads ((+)= if accumulate).

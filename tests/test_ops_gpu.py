@@ -1,0 +1,365 @@
+"""Per-op parity of the CUDA kernels (called through the C ABI) against plain PyTorch fp32 on CPU.
+
+fp32 kernels: 1e-4 norm-relative.  bf16 / tcgen05 kernels: inputs are rounded to bf16 on both sides,
+the reference is then computed in fp32, tolerance 1e-2 norm-relative (bf16 output rounding ~4e-3).
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from helpers import bf16_round, cos_sim, from_act, rel_err, to_act  # noqa: E402
+
+
+def _ops():
+    import dcvgan_b200
+    dcvgan_b200.require_device()
+    from dcvgan_b200 import ops
+    return ops
+
+
+# (name, kind, cin, cout, k, s, p, N, in_spatial)
+CONV_CASES = [
+    ("conv2d_k4s2", "conv", 8, 24, (1, 4, 4), (1, 2, 2), (0, 1, 1), 3, (1, 16, 16)),
+    ("conv2d_k3s1", "conv", 2, 16, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, (1, 8, 8)),
+    ("conv2d_head", "conv", 32, 1, (1, 4, 4), (1, 2, 2), (0, 1, 1), 4, (1, 8, 8)),
+    ("conv2d_2to1", "conv", 16, 16, (1, 4, 4), (1, 2, 2), (0, 1, 1), 5, (1, 2, 2)),
+    ("conv3d_k4", "conv", 3, 8, (4, 4, 4), (1, 2, 2), (0, 1, 1), 2, (7, 8, 8)),
+    ("conv3d_k4_wide", "conv", 16, 40, (4, 4, 4), (1, 2, 2), (0, 1, 1), 2, (5, 8, 8)),
+    ("convT_k4s2", "convT", 24, 8, (1, 4, 4), (1, 2, 2), (0, 1, 1), 3, (1, 8, 8)),
+    ("convT_k4s1p0", "convT", 10, 16, (1, 4, 4), (1, 1, 1), (0, 0, 0), 6, (1, 1, 1)),
+    ("convT_k3s1", "convT", 16, 3, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, (1, 8, 8)),
+    ("convT_1to2", "convT", 12, 16, (1, 4, 4), (1, 2, 2), (0, 1, 1), 4, (1, 1, 1)),
+]
+
+TC_CASES = [
+    ("tc_conv2d_64", "conv", 64, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 4, (1, 32, 32)),
+    ("tc_conv2d_128_256", "conv", 128, 256, (1, 4, 4), (1, 2, 2), (0, 1, 1), 8, (1, 8, 8)),
+    ("tc_conv2d_small", "conv", 64, 128, (1, 4, 4), (1, 2, 2), (0, 1, 1), 16, (1, 2, 2)),
+    ("tc_conv2d_c32", "conv", 32, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 4, (1, 16, 16)),
+    ("tc_conv2d_c16_n24", "conv", 16, 24, (1, 4, 4), (1, 2, 2), (0, 1, 1), 4, (1, 16, 16)),
+    ("tc_conv3d_64_128", "conv", 64, 128, (4, 4, 4), (1, 2, 2), (0, 1, 1), 2, (13, 32, 32)),
+    ("tc_conv3d_128_256", "conv", 128, 256, (4, 4, 4), (1, 2, 2), (0, 1, 1), 3, (10, 16, 16)),
+    ("tc_convT_128_64", "convT", 128, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 4, (1, 16, 16)),
+    ("tc_convT_512_256", "convT", 512, 256, (1, 4, 4), (1, 2, 2), (0, 1, 1), 8, (1, 4, 4)),
+    ("tc_convT_k3_n3", "convT", 128, 3, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, (1, 32, 32)),
+    ("tc_convT_64_1", "convT", 64, 1, (1, 4, 4), (1, 2, 2), (0, 1, 1), 2, (1, 32, 32)),
+]
+
+
+def _torch_fwd(kind, x, w, s, p, three_d):
+    if kind == "conv":
+        return F.conv3d(x, w, stride=s, padding=p) if three_d else F.conv2d(x[:, :, 0], w[:, :, 0], stride=s[1:], padding=p[1:]).unsqueeze(2)
+    return F.conv_transpose2d(x[:, :, 0], w[:, :, 0], stride=s[1:], padding=p[1:]).unsqueeze(2)
+
+
+def _run_case(ops, case, dtype, impl_tc, tol):
+    name, kind, cin, cout, k, s, p, n, sp = case
+    torch.manual_seed(sum(map(ord, name)) % 1000)
+    three_d = k[0] > 1
+    spec = ops.ConvSpec(kind, cin, cout, k, s, p)
+    x = torch.randn(n, cin, *sp)
+    w = torch.randn((cout, cin, *k) if kind == "conv" else (cin, cout, *k)) * 0.1
+    if dtype == torch.bfloat16:
+        x, w = bf16_round(x), bf16_round(w)
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    y_ref = _torch_fwd(kind, x, w, s, p, three_d)
+    dy = torch.randn_like(y_ref)
+    if dtype == torch.bfloat16:
+        dy = bf16_round(dy)
+    y_ref.backward(dy)
+
+    from dcvgan_b200._lib import IMPL_SIMT, IMPL_TC
+    g = spec.geom(n, sp)
+    xa = to_act(x.detach(), dtype)
+    out_sp = spec.out_spatial(sp)
+    ya = ops.Act.empty(n, *out_sp, cout, dtype)
+    wdev = (w.detach().squeeze(2) if (kind == "convT" or not three_d) else w.detach()).contiguous().cuda()
+    impl = IMPL_TC if impl_tc else IMPL_SIMT
+    if impl_tc:
+        assert ops.lib().dcv_conv_tc_supported(C.byref(g), spec.fwd_dir), "case should be tcgen05-eligible"
+    # forward
+    wp = ops.pack_weight(spec, g, spec.fwd_dir, impl, wdev)
+    ops.conv(g, spec.fwd_dir, impl, xa, wp, ya)
+    e_fwd = rel_err(from_act(ya), y_ref.detach())
+    # data gradient
+    dya = to_act(dy, dtype)
+    dxa = ops.Act.empty(n, *sp, cin, dtype)
+    impl_b = impl
+    if impl_tc and not ops.lib().dcv_conv_tc_supported(C.byref(g), spec.bwd_dir):
+        impl_b = IMPL_SIMT
+    wpb = ops.pack_weight(spec, g, spec.bwd_dir, impl_b, wdev)
+    ops.conv(g, spec.bwd_dir, impl_b, dya, wpb, dxa)
+    e_dx = rel_err(from_act(dxa), x.grad)
+    # weight gradient
+    dw = torch.full_like(wdev, 7.0)
+    xl, xs = (xa, dya) if kind == "conv" else (dya, xa)
+    wimpl = IMPL_TC if (impl_tc and ops.lib().dcv_wgrad_tc_supported(C.byref(g))) else IMPL_SIMT
+    ops.wgrad(spec, g, xl, xs, dw, accumulate=False, impl=wimpl)
+    torch.cuda.synchronize()
+    wg = w.grad.squeeze(2) if (kind == "convT" or not three_d) else w.grad
+    e_dw = rel_err(dw.cpu(), wg)
+    # accumulate=True adds on top
+    ops.wgrad(spec, g, xl, xs, dw, accumulate=True, impl=wimpl)
+    torch.cuda.synchronize()
+    e_dw2 = rel_err(dw.cpu(), 2 * wg)
+    print(f"{name}: fwd {e_fwd:.2e} dx {e_dx:.2e} dw {e_dw:.2e} dw2 {e_dw2:.2e} impl_b={impl_b} wimpl={wimpl}")
+    assert e_fwd < tol and e_dx < tol and e_dw < tol and e_dw2 < tol, (name, e_fwd, e_dx, e_dw, e_dw2)
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_simt_fp32(case):
+    _run_case(_ops(), case, torch.float32, False, 1e-4)
+
+
+@pytest.mark.parametrize("case", CONV_CASES + TC_CASES[:3], ids=[c[0] for c in CONV_CASES + TC_CASES[:3]])
+def test_conv_simt_bf16(case):
+    _run_case(_ops(), case, torch.bfloat16, False, 1e-2)
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv_tcgen05(case):
+    _run_case(_ops(), case, torch.bfloat16, True, 1e-2)
+
+
+def test_conv_channel_slices():
+    """input read from / output written into channel slices of wider buffers (concat elimination)"""
+    ops = _ops()
+    from dcvgan_b200._lib import IMPL_SIMT, IMPL_TC
+    for dtype, impl in ((torch.float32, IMPL_SIMT), (torch.bfloat16, IMPL_TC)):
+        torch.manual_seed(3)
+        spec = ops.ConvSpec("conv", 64, 32, (1, 4, 4), (1, 2, 2), (0, 1, 1))
+        x = bf16_round(torch.randn(2, 64, 16, 16))
+        w = bf16_round(torch.randn(32, 64, 4, 4) * 0.1)
+        y_ref = F.conv2d(x, w, stride=2, padding=1)
+        wide_in = ops.Act.empty(2, 1, 16, 16, 96, dtype, zero=True)
+        ops.to_channels_last(x.cuda().unsqueeze(2), wide_in.ch(32, 96))
+        wide_out = ops.Act.empty(2, 1, 8, 8, 72, dtype, zero=True)
+        g = spec.geom(2, (1, 16, 16))
+        wp = ops.pack_weight(spec, g, spec.fwd_dir, impl, w.cuda())
+        ops.conv(g, spec.fwd_dir, impl, wide_in.ch(32, 96), wp, wide_out.ch(40, 72))
+        full = from_act(wide_out, 4)
+        assert rel_err(full[:, 40:72], y_ref) < 1e-2
+        assert float(full[:, :40].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("act", ["relu", "leaky"])
+def test_batchnorm_act_dropout(dtype, act):
+    ops = _ops()
+    from dcvgan_b200._lib import ACT_LEAKY
+    torch.manual_seed(1)
+    n, c, h, w = 6, 48, 8, 8
+    slope = 0.0 if act == "relu" else 0.2
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    z = torch.randn(n, c, h, w) * 2 + 0.5
+    if dtype == torch.bfloat16:
+        z = bf16_round(z)
+    z.requires_grad_(True)
+    gamma = (torch.randn(c) * 0.1 + 1).requires_grad_(True)
+    beta = (torch.randn(c) * 0.1).requires_grad_(True)
+    rm, rv = torch.randn(c) * 0.1, torch.rand(c) + 0.5
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    drop = (torch.rand(n, c) < 0.5).float() * 2.0
+    u = F.batch_norm(z, rm_ref, rv_ref, gamma, beta, training=True, momentum=0.1, eps=1e-5)
+    a_ref = F.leaky_relu(u * drop[:, :, None, None], slope)
+    da = torch.randn_like(a_ref)
+    a_ref.backward(da)
+
+    za = to_act(z.detach(), dtype)
+    rmd, rvd = rm.cuda(), rv.cuda()
+    mean, invstd = ops.bn_batch_stats(za, 1e-5, 0.1, rmd, rvd)
+    aa = za.like()
+    gd, bd, dd = gamma.detach().cuda(), beta.detach().cuda(), drop.cuda().contiguous()
+    ops.bn_act(za, mean, invstd, gd, bd, dd, ACT_LEAKY, slope, aa)
+    assert rel_err(from_act(aa, 4), a_ref.detach()) < tol
+    torch.cuda.synchronize()
+    assert rel_err(rmd.cpu(), rm_ref) < 1e-5 and rel_err(rvd.cpu(), rv_ref) < 1e-5
+    daa = to_act(da, dtype)
+    dza = za.like()
+    dg, db = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    ops.bn_act_bwd(daa, aa, za, mean, invstd, gd, dd, ACT_LEAKY, slope, dza, dg, db)
+    assert rel_err(from_act(dza, 4), z.grad) < tol
+    torch.cuda.synchronize()
+    assert rel_err(dg.cpu(), gamma.grad) < tol and rel_err(db.cpu(), beta.grad) < tol
+    # eval-mode statistics
+    m2, i2 = ops.bn_eval_stats(rmd, rvd, 1e-5)
+    ops.bn_act(za, m2, i2, gd, bd, None, ACT_LEAKY, slope, aa)
+    a_eval = F.leaky_relu(F.batch_norm(z.detach(), rm_ref, rv_ref, gamma.detach(), beta.detach(), training=False, eps=1e-5), slope)
+    assert rel_err(from_act(aa, 4), a_eval) < tol
+
+
+def test_batchnorm_wide_channels():
+    ops = _ops()
+    from dcvgan_b200._lib import ACT_NONE
+    torch.manual_seed(2)
+    z = torch.randn(4, 300, 2, 2)
+    za = to_act(z, torch.float32)
+    mean, invstd = ops.bn_batch_stats(za, 1e-5, 0.1, None, None)
+    torch.cuda.synchronize()
+    assert rel_err(mean.cpu(), z.mean((0, 2, 3))) < 1e-5
+    assert rel_err(invstd.cpu(), 1 / torch.sqrt(z.var((0, 2, 3), unbiased=False) + 1e-5)) < 1e-5
+
+
+def test_elementwise_misc():
+    ops = _ops()
+    from dcvgan_b200._lib import ACT_LEAKY, ACT_TANH
+    torch.manual_seed(4)
+    for dtype, tol in ((torch.float32, 1e-6), (torch.bfloat16, 1e-2)):
+        x = torch.randn(2, 5, 6, 4, 4)
+        xa = to_act(x, dtype)
+        xr = from_act(xa)
+        assert rel_err(xr, x) < tol
+        # temporal difference and its adjoint
+        d = ops.Act.empty(2, 5, 4, 4, 5, dtype)
+        ops.tdiff(xa, d)
+        assert rel_err(from_act(d), xr[:, :, 1:] - xr[:, :, :-1]) < tol
+        dy = torch.randn(2, 5, 5, 4, 4)
+        dya = to_act(dy, dtype)
+        dxa = xa.like()
+        ops.tdiff_bwd(dya, dxa, False)
+        xg = xr.clone().requires_grad_(True)
+        ((xg[:, :, 1:] - xg[:, :, :-1]) * from_act(dya)).sum().backward()
+        assert rel_err(from_act(dxa), xg.grad) < tol
+        # softmax fwd/bwd over channels
+        sa = xa.like()
+        ops.softmax(xa, sa)
+        xg = xr.clone().requires_grad_(True)
+        sm = torch.softmax(xg, 1)
+        assert rel_err(from_act(sa), sm.detach()) < tol
+        gy = torch.randn_like(sm)
+        sm.backward(gy)
+        ga = to_act(gy, dtype)
+        dz = xa.like()
+        ops.softmax_bwd(ga, sa, dz)
+        assert rel_err(from_act(dz), xg.grad) < max(tol, 2e-2 if dtype == torch.bfloat16 else 1e-5)
+        # segmentation remap
+        ra = xa.like()
+        ops.segm_remap(xa, ra)
+        ref = torch.full_like(xr, -1.0).scatter_(1, xr.argmax(1, keepdim=True), 1.0)
+        assert torch.equal(from_act(ra), ref)
+        # noise, axpy, frame extract / scatter, activation backward
+        nz = torch.randn(xa.rows * xa.c, device="cuda")
+        na = xa.like()
+        ops.add_noise(xa, nz, 0.2, na)
+        ref = xr + 0.2 * nz.cpu().view(2, 6, 4, 4, 5).permute(0, 4, 1, 2, 3)
+        assert rel_err(from_act(na), ref) < tol
+        ops.axpy(xa, na, True)
+        assert rel_err(from_act(na), ref + xr) < tol
+        fr = ops.Act.empty(2, 1, 4, 4, 5, dtype)
+        ops.frame_extract(xa, 3, fr)
+        assert torch.equal(from_act(fr)[:, :, 0], xr[:, :, 3])
+        acc = xa.like()
+        ops.copy_cl(xa, acc)
+        ops.frame_scatter(acc, 3, fr, True)
+        ref = xr.clone()
+        ref[:, :, 3] *= 2
+        assert rel_err(from_act(acc), ref) < tol
+        for act, slope, fn in ((ACT_LEAKY, 0.2, lambda v: F.leaky_relu(v, 0.2)), (ACT_TANH, 0.0, torch.tanh)):
+            xg = xr.clone().requires_grad_(True)
+            a = fn(xg)
+            a.backward(torch.ones_like(xr))
+            aa = to_act(a.detach(), dtype)
+            ones = to_act(torch.ones_like(xr), dtype)
+            dz = xa.like()
+            ops.act_bwd(ones, aa, act, slope, dz)
+            assert rel_err(from_act(dz), xg.grad) < max(tol, 2e-2 if dtype == torch.bfloat16 else 1e-5)
+
+
+def test_layout_strided_frames():
+    """to/from channels-last with the strided views the reference produces (x[:, :, t], permuted videos)"""
+    ops = _ops()
+    torch.manual_seed(5)
+    v = torch.randn(3, 2, 7, 8, 8, device="cuda")
+    frame = v[:, :, 4]
+    fa = ops.Act.empty(3, 1, 8, 8, 2, torch.float32)
+    ops.to_channels_last(frame, fa)
+    assert torch.equal(from_act(fa, 4), frame.cpu())
+    mem = torch.zeros(3, 7, 2, 8, 8, device="cuda")
+    out = mem.permute(0, 2, 1, 3, 4)  # (B,C,T,H,W) view of (B,T,C,H,W) memory, like generator.py:136-139
+    va = to_act(v, torch.float32)
+    ops.from_channels_last(va, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), v.cpu())
+    ops.from_channels_last(va, out, accumulate=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), 2 * v.cpu())
+
+
+def test_gru_trajectory():
+    ops = _ops()
+    torch.manual_seed(6)
+    b, t, d = 5, 16, 10
+    cell = torch.nn.GRUCell(d, d)
+    h0 = torch.randn(b, d)
+    eps = torch.randn(t, b, d)
+    h, hs = h0, []
+    for i in range(t):
+        h = cell(eps[i], h)
+        hs.append(h)
+    hs_ref = torch.stack(hs, 1)
+    dhs = torch.randn_like(hs_ref)
+    hs_ref.backward(dhs)
+    P = [p.detach().cuda().contiguous() for p in (cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh)]
+    hs_dev = ops.gru_traj_fwd(h0.cuda(), eps.cuda(), *P)
+    torch.cuda.synchronize()
+    assert rel_err(hs_dev.cpu(), hs_ref.detach()) < 1e-5
+    grads = [torch.empty_like(p) for p in P]
+    ops.gru_traj_bwd(h0.cuda(), eps.cuda(), hs_dev, dhs.cuda().contiguous(), *P, *grads)
+    torch.cuda.synchronize()
+    for gdev, pref in zip(grads, (cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh)):
+        assert rel_err(gdev.cpu(), pref.grad) < 1e-4
+
+
+def test_losses():
+    ops = _ops()
+    from dcvgan_b200 import _lib
+    torch.manual_seed(7)
+    y = (torch.randn(4, 4, 4, 4) * 3).requires_grad_(True)
+    bce = torch.nn.BCEWithLogitsLoss(reduction="sum")
+    refs = {
+        _lib.LOSS_BCE_ONES: lambda v: bce(v, torch.ones_like(v)) / v.numel(),
+        _lib.LOSS_BCE_ZEROS: lambda v: bce(v, torch.zeros_like(v)) / v.numel(),
+        _lib.LOSS_HINGE_REAL: lambda v: torch.mean(F.relu(1.0 - v)),
+        _lib.LOSS_HINGE_FAKE: lambda v: torch.mean(F.relu(1.0 + v)),
+        _lib.LOSS_SOFTPLUS_NEG: lambda v: torch.mean(F.softplus(-v)),
+    }
+    for kind, fn in refs.items():
+        y.grad = None
+        l_ref = fn(y)
+        l_ref.backward()
+        yd = y.detach().cuda().contiguous()
+        out = torch.zeros(1, device="cuda")
+        dy = torch.empty_like(yd)
+        ops.loss_fwd_bwd(yd, kind, out, False, dy, 1.0)
+        ops.loss_fwd_bwd(yd, kind, out, True, None, 1.0)
+        torch.cuda.synchronize()
+        assert abs(float(out) - 2 * float(l_ref)) < 1e-5 * max(1.0, abs(float(l_ref)))
+        assert rel_err(dy.cpu(), y.grad) < 1e-5
+
+
+def test_adam_matches_torch():
+    ops = _ops()
+    torch.manual_seed(8)
+    shapes = [(3, 5, 4, 4), (4097,), (10,), (64, 64, 4, 4), (1,)]
+    params = [torch.randn(s) for s in shapes]
+    ref = [p.clone().requires_grad_(True) for p in params]
+    opt = torch.optim.Adam(ref, lr=2e-4, betas=(0.5, 0.999), weight_decay=1e-5)
+    dev = [p.cuda() for p in params]
+    m = [torch.zeros_like(p) for p in dev]
+    v = [torch.zeros_like(p) for p in dev]
+    for step in range(1, 4):
+        grads = [torch.randn(s) for s in shapes]
+        for r, g in zip(ref, grads):
+            r.grad = g.clone()
+        opt.step()
+        ops.adam_multi(dev, [g.cuda() for g in grads], m, v, 2e-4, 0.5, 0.999, 1e-8, 1e-5, step)
+    torch.cuda.synchronize()
+    for d, r in zip(dev, ref):
+        assert rel_err(d.cpu(), r.detach()) < 1e-6
+    for mm, r in zip(m, ref):
+        assert rel_err(mm.cpu(), opt.state[r]["exp_avg"]) < 1e-6
