@@ -1,0 +1,392 @@
+"""Forward / backward plans of the five DCVGAN networks over the C-ABI kernels.
+
+A plan works on channels-last `Act` buffers, writes producers straight into channel slices of the
+buffers their consumers read (no torch.cat), and keeps exactly what the backward pass needs.
+The nn.Module classes in generator.py / discriminator.py own the parameters (same state_dict keys
+as the reference) and delegate here; trainer.py calls the same plans without autograd.
+
+Reference call stacks mirrored here: generator.py:84-141 (ggen), :361-435 (cgen),
+discriminator.py:106-127, :210-231, :309-333 (idis, vdis, gdis).
+"""
+import torch
+
+from . import ops
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_TANH
+from .ops import Act, ConvSpec
+
+BN_EPS, BN_MOM = 1e-5, 0.1
+
+
+# ------------------------------------------------------------------------------------------ RNG
+class Rng:
+    """Source of every random draw on the path (latents, Noise layers, Dropout2d masks).
+
+    mode 'device'     : torch's CUDA generator (production / benchmark)
+    mode 'cpu_parity' : the draw the reference would make on the CPU (torch.empty(shape).normal_() /
+                        .bernoulli_()), in the reference's order, copied to the GPU - so that a run
+                        seeded like the CPU oracle consumes bit-identical noise.
+    """
+
+    def __init__(self, mode="device"):
+        assert mode in ("device", "cpu_parity")
+        self.mode = mode
+
+    def normal(self, shape):
+        if self.mode == "cpu_parity":
+            return torch.empty(shape).normal_().cuda()
+        return torch.empty(shape, device="cuda").normal_()
+
+    def noise_for(self, a):
+        """fp32 noise laid out like `a` (dense channels-last); drawn in the reference's (N,C[,T],H,W) order"""
+        if self.mode == "cpu_parity":
+            # normal_() fills in memory order, so (N,C,H,W) and (N,C,1,H,W) draws are identical
+            ref = torch.empty((a.n, a.c, a.t, a.h, a.w)).normal_().cuda()
+            out = Act.empty(a.n, a.t, a.h, a.w, a.c, torch.float32)
+            ops.to_channels_last(ref, out)
+            return out.base
+        return torch.empty(a.rows * a.c, device="cuda").normal_()
+
+    def dropout_scale(self, n, c, p=0.5):
+        """Dropout2d: one Bernoulli(1-p) per (sample, channel), scaled by 1/(1-p)  (generator.py:246-248)"""
+        if self.mode == "cpu_parity":
+            return torch.empty((n, c, 1, 1)).bernoulli_(1 - p).div_(1 - p).view(n, c).cuda().contiguous()
+        return torch.empty((n, c), device="cuda").bernoulli_(1 - p).div_(1 - p)
+
+
+_RNG = Rng("device")
+
+
+def set_rng_mode(mode):
+    global _RNG
+    _RNG = Rng(mode)
+
+
+def rng():
+    return _RNG
+
+
+# ------------------------------------------------------------------------------------------ gradient sinks
+class GradSink:
+    """Where parameter gradients go.  `get(p)` returns (fp32 tensor shaped like p, accumulate?)."""
+
+    def __init__(self, lookup=None):
+        self.lookup = lookup          # optional dict: param -> preallocated grad tensor
+        self.grads = {}
+
+    def get(self, p):
+        if p in self.grads:
+            return self.grads[p], True
+        g = self.lookup[p] if self.lookup is not None else torch.empty_like(p, memory_format=torch.contiguous_format)
+        self.grads[p] = g
+        return g, False
+
+
+# ------------------------------------------------------------------------------------------ one layer group
+class Block:
+    """[Noise] -> conv -> [BatchNorm] -> [Dropout2d] -> activation, with its backward.
+
+    conv / bn are the owner's real nn.Conv*/nn.BatchNorm* modules (parameter containers only).
+    """
+
+    def __init__(self, spec, conv, bn=None, act=ACT_NONE, slope=0.0, dropout=False, noise=None):
+        self.spec, self.conv, self.bn = spec, conv, bn
+        self.act, self.slope, self.dropout = act, slope, dropout
+        self.noise = noise  # None or (use_noise, sigma)
+
+    def forward(self, x, out, training, rng_, save=True):
+        """x: input Act; out: Act (slice) that receives the block's output.  Returns ctx for backward."""
+        spec = self.spec
+        g = spec.geom(x.n, x.spatial)
+        w = self.conv.weight
+        x_used = x
+        if self.noise is not None and self.noise[0]:
+            x_used = x.like()
+            ops.add_noise(x, rng_.noise_for(x), float(self.noise[1]), x_used)
+        impl = ops.choose_conv_impl(g, spec.fwd_dir, x_used)
+        wp = ops.pack_weight(spec, g, spec.fwd_dir, impl, w)
+        ctx = {"g": g, "x": x_used if save else None, "a": out}
+        if self.bn is None:
+            ops.conv(g, spec.fwd_dir, impl, x_used, wp, out, self.act, self.slope)
+            return ctx
+        z = Act.empty(out.n, out.t, out.h, out.w, out.c, out.dtype)
+        ops.conv(g, spec.fwd_dir, impl, x_used, wp, z)
+        bn = self.bn
+        if training:
+            mean, invstd = ops.bn_batch_stats(z, BN_EPS, BN_MOM, bn.running_mean, bn.running_var)
+            bn.num_batches_tracked += 1
+        else:
+            mean, invstd = ops.bn_eval_stats(bn.running_mean, bn.running_var, BN_EPS)
+        drop = rng_.dropout_scale(z.n, z.c) if (self.dropout and training) else None
+        ops.bn_act(z, mean, invstd, bn.weight.detach(), bn.bias.detach(), drop, self.act, self.slope, out)
+        if save:
+            ctx.update(z=z, mean=mean, invstd=invstd, drop=drop, training=training)
+        return ctx
+
+    def backward(self, ctx, da, sink, dx_out=None, need_dw=True):
+        """da: gradient w.r.t. the block output (Act, may be a slice).  dx_out: Act receiving dL/dx or None."""
+        spec, g = self.spec, ctx["g"]
+        a = ctx["a"]
+        if self.bn is not None:
+            assert ctx.get("training", True), "BatchNorm backward is only defined for training-mode statistics here"
+            dz = ctx["z"].like()
+            if need_dw:
+                dgam, acc = sink.get(self.bn.weight)
+                dbet, _ = sink.get(self.bn.bias)
+            else:
+                dgam = dbet = None
+                acc = False
+            ops.bn_act_bwd(da, a, ctx["z"], ctx["mean"], ctx["invstd"], self.bn.weight.detach(), ctx["drop"], self.act,
+                           self.slope, dz, dgam, dbet, acc)
+        elif self.act != ACT_NONE:
+            dz = Act.empty(a.n, a.t, a.h, a.w, a.c, a.dtype)
+            ops.act_bwd(da, a, self.act, self.slope, dz)
+        else:
+            dz = da
+        if need_dw:
+            dw, acc = sink.get(self.conv.weight)
+            xl, xs = (ctx["x"], dz) if spec.kind == "conv" else (dz, ctx["x"])
+            ops.wgrad(spec, g, xl, xs, dw, accumulate=acc)
+        if dx_out is not None:
+            impl = ops.choose_conv_impl(g, spec.bwd_dir, dz)
+            wp = ops.pack_weight(spec, g, spec.bwd_dir, impl, self.conv.weight)
+            ops.conv(g, spec.bwd_dir, impl, dz, wp, dx_out)
+        return dz
+
+
+def _k2(k):
+    return (1, k, k)
+
+
+def conv2d_spec(cin, cout, k, s, p):
+    return ConvSpec("conv", cin, cout, _k2(k), _k2(s), (0, p, p))
+
+
+def convT2d_spec(cin, cout, k, s, p):
+    return ConvSpec("convT", cin, cout, _k2(k), _k2(s), (0, p, p))
+
+
+def conv3d_spec(cin, cout):
+    return ConvSpec("conv", cin, cout, (4, 4, 4), (1, 2, 2), (0, 1, 1))
+
+
+# ------------------------------------------------------------------------------------------ ggen
+class GGenPlan:
+    """GRU latent trajectory + 5 transposed convolutions (generator.py:58-80,84-141)."""
+
+    def __init__(self, mod):
+        self.mod = mod
+        m = mod.main
+        ngf, dz, C = mod.ngf, mod.dim_z, mod.channel
+        chans = [dz, ngf * 8, ngf * 4, ngf * 2, ngf, C]
+        self.blocks = []
+        for i in range(5):
+            spec = convT2d_spec(chans[i], chans[i + 1], 4, 1 if i == 0 else 2, 0 if i == 0 else 1)
+            if i < 4:
+                self.blocks.append(Block(spec, m[3 * i], m[3 * i + 1], ACT_LEAKY, 0.0))       # BN + ReLU
+            else:
+                self.blocks.append(Block(spec, m[12], None, ACT_NONE if mod.geometric_info == "segmentation" else ACT_TANH))
+        self.softmax = mod.geometric_info == "segmentation"
+
+    def forward(self, B, training, dtype, rng_, save=True):
+        mod = self.mod
+        T, dzc, dzm = mod.video_length, mod.dim_z_content, mod.dim_z_motion
+        rec = mod.recurrent
+        z_c = rng_.normal((B, dzc))                                              # draw order: generator.py:103-116
+        h0 = rng_.normal((B, dzm))
+        eps = torch.stack([rng_.normal((B, dzm)) for _ in range(T)], 0).contiguous()
+        P = [p.detach() for p in (rec.weight_ih, rec.weight_hh, rec.bias_ih, rec.bias_hh)]
+        hs = ops.gru_traj_fwd(h0, eps, *P)                                       # (B, T, dzm)
+        z = torch.empty((B, T, dzc + dzm), dtype=dtype, device="cuda")
+        z[:, :, :dzc] = z_c[:, None, :]                                          # z_content repeated over T (:103-108)
+        z[:, :, dzc:] = hs
+        x = Act(z.view(-1), 0, B * T, 1, 1, 1, dzc + dzm, dzc + dzm)
+        ctxs = []
+        sp = (1, 1, 1)
+        for blk in self.blocks:
+            sp = blk.spec.out_spatial(sp)
+            out = Act.empty(B * T, 1, sp[1], sp[2], blk.spec.cout, dtype)
+            ctxs.append(blk.forward(x, out, training, rng_, save))
+            x = out
+        if self.softmax:
+            y = x.like()
+            ops.softmax(x, y)
+            x = y
+        ctx = {"blocks": ctxs, "h0": h0, "eps": eps, "hs": hs, "out": x, "B": B} if save else None
+        return x, ctx
+
+    def backward(self, ctx, dout, sink):
+        """dout: Act (B*T,1,64,64,C) gradient w.r.t. the generated frames."""
+        mod = self.mod
+        da = dout
+        if self.softmax:
+            dz = dout.like()
+            ops.softmax_bwd(dout, ctx["out"], dz)
+            da = dz
+        for i in range(4, -1, -1):
+            blk, c = self.blocks[i], ctx["blocks"][i]
+            x = c["x"]
+            dx = Act.empty(x.n, x.t, x.h, x.w, x.c, x.dtype)
+            blk.backward(c, da, sink, dx_out=dx)
+            da = dx
+        B, T, dzc, dzm = ctx["B"], mod.video_length, mod.dim_z_content, mod.dim_z_motion
+        dhs = da.base.view(B, T, dzc + dzm)[:, :, dzc:].float().contiguous()
+        rec = mod.recurrent
+        P = [p.detach() for p in (rec.weight_ih, rec.weight_hh, rec.bias_ih, rec.bias_hh)]
+        grads = [sink.get(p) for p in (rec.weight_ih, rec.weight_hh, rec.bias_ih, rec.bias_hh)]
+        ops.gru_traj_bwd(ctx["h0"], ctx["eps"], ctx["hs"], dhs, *P, *[g for g, _ in grads], accumulate=grads[0][1])
+
+
+# ------------------------------------------------------------------------------------------ cgen
+class CGenPlan:
+    """U-Net colour generator (generator.py:158-282,323-402)."""
+
+    def __init__(self, mod):
+        self.mod = mod
+        ngf, dz, C = mod.ngf, mod.dim_z, mod.in_ch
+        self.ngf, self.dz, self.C = ngf, dz, C
+        self.inconv = Block(conv2d_spec(C, ngf, 3, 1, 1), mod.inconv.main[0], None, ACT_LEAKY, 0.01)
+        dch = [(ngf, ngf), (ngf, 2 * ngf), (2 * ngf, 4 * ngf), (4 * ngf, 4 * ngf), (4 * ngf, 4 * ngf), (4 * ngf, 4 * ngf)]
+        self.down = [Block(conv2d_spec(ci, co, 4, 2, 1), mod.down_blocks[i].main[0], mod.down_blocks[i].main[1], ACT_LEAKY, 0.2)
+                     for i, (ci, co) in enumerate(dch)]
+        uch = [(4 * ngf + dz, 4 * ngf), (8 * ngf, 4 * ngf), (8 * ngf, 4 * ngf), (8 * ngf, 2 * ngf), (4 * ngf, ngf), (2 * ngf, ngf)]
+        self.up = [Block(convT2d_spec(ci, co, 4, 2, 1), mod.up_blocks[i].main[0], mod.up_blocks[i].main[1], ACT_LEAKY, 0.0,
+                         dropout=(i < 2)) for i, (ci, co) in enumerate(uch)]
+        self.outconv = Block(convT2d_spec(2 * ngf, 3, 3, 1, 1), mod.outconv.main[0], None, ACT_TANH)
+        # concat buffers: (spatial, [upsampled channels, skip channels])
+        self.cat_layout = [(1, 4 * ngf, dz), (2, 4 * ngf, 4 * ngf), (4, 4 * ngf, 4 * ngf), (8, 4 * ngf, 4 * ngf),
+                           (16, 2 * ngf, 2 * ngf), (32, ngf, ngf), (64, ngf, ngf)]
+
+    def forward(self, x, z, training, rng_, save=True):
+        """x: Act (N,1,64,64,C) geometry frames; z: fp32 (N, dim_z) colour code per frame."""
+        mod, N, dtype = self.mod, x.n, x.dtype
+        if mod.geometric_info == "segmentation":                                 # generator.py:378-385
+            xr = x.like()
+            ops.segm_remap(x, xr)
+            x = xr
+        cats = [Act.empty(N, 1, s, s, a + b, dtype) for (s, a, b) in self.cat_layout]
+        # cats[0] = [down5 | z] @1, cats[k] = [up_{k-1} | skip] for k=1..5, cats[6] = [up5 | inconv] @64
+        first = [a for (_, a, _) in self.cat_layout]
+        ctx = {"cats": cats}
+        ctx["inconv"] = self.inconv.forward(x, cats[6].ch(first[6], cats[6].c), training, rng_, save)
+        src = cats[6].ch(first[6], cats[6].c)
+        dctx = []
+        for i in range(6):
+            dst = cats[5 - i].ch(first[5 - i], cats[5 - i].c) if i < 5 else cats[0].ch(0, first[0])
+            dctx.append(self.down[i].forward(src, dst, training, rng_, save))
+            src = dst
+        zc = cats[0].ch(first[0], cats[0].c)                                     # generator.py:393
+        zc.torch()[:, 0, 0, 0, :] = z.to(dtype)
+        uctx = []
+        for i in range(6):
+            dst = cats[i + 1].ch(0, first[i + 1])
+            uctx.append(self.up[i].forward(cats[i], dst, training, rng_, save))
+        out = Act.empty(N, 1, 64, 64, 3, dtype)
+        ctx["outconv"] = self.outconv.forward(cats[6], out, training, rng_, save)
+        ctx.update(down=dctx, up=uctx)
+        return out, (ctx if save else None)
+
+    def backward(self, ctx, dout, sink, need_dx=True):
+        cats = ctx["cats"]
+        first = [a for (_, a, _) in self.cat_layout]
+        dcats = [c.like() for c in cats]
+        self.outconv.backward(ctx["outconv"], dout, sink, dx_out=dcats[6])
+        for i in range(5, -1, -1):
+            self.up[i].backward(ctx["up"][i], dcats[i + 1].ch(0, first[i + 1]), sink, dx_out=dcats[i])
+        da = dcats[0].ch(0, first[0])
+        for i in range(5, -1, -1):
+            xin = ctx["down"][i]["x"]
+            dx = Act.empty(xin.n, xin.t, xin.h, xin.w, xin.c, xin.dtype)
+            self.down[i].backward(ctx["down"][i], da, sink, dx_out=dx)
+            k = 5 - i + 1 if i > 0 else 6                                        # concat buffer holding this skip tensor
+            ops.axpy(dcats[k].ch(first[k], dcats[k].c), dx, True)
+            da = dx
+        dx = None
+        if need_dx and self.mod.geometric_info != "segmentation":                # argmax/scatter blocks the gradient
+            xin = ctx["inconv"]["x"]
+            dx = Act.empty(xin.n, xin.t, xin.h, xin.w, xin.c, xin.dtype)
+        self.inconv.backward(ctx["inconv"], da, sink, dx_out=dx)
+        return dx
+
+
+# ------------------------------------------------------------------------------------------ discriminators
+class DisPlan:
+    """Image / video / gradient discriminator (discriminator.py:42-346)."""
+
+    def __init__(self, mod, kind):
+        self.mod, self.kind = mod, kind
+        ndf, cg, cc = mod.ndf, mod.ch1, mod.ch2
+        nz = (mod.use_noise, mod.noise_sigma)
+        m = mod.main
+        if kind == "idis":
+            mk = lambda ci, co: conv2d_spec(ci, co, 4, 2, 1)
+            self.stem_g = Block(mk(cg, ndf // 2), mod.conv_g[1], None, ACT_LEAKY, 0.2, noise=nz)
+            self.stem_c = Block(mk(cc, ndf // 2), mod.conv_c[1], None, ACT_LEAKY, 0.2, noise=nz)
+        elif kind == "vdis":
+            mk = conv3d_spec
+            self.stem_g = Block(mk(cg, ndf // 2), mod.conv_g[0], None, ACT_LEAKY, 0.2)
+            self.stem_c = Block(mk(cc, ndf // 2), mod.conv_c[0], None, ACT_LEAKY, 0.2)
+        else:
+            mk = conv3d_spec
+        if kind in ("idis", "vdis"):
+            self.main = [Block(mk(ndf, ndf * 2), m[1], m[2], ACT_LEAKY, 0.2, noise=nz),
+                         Block(mk(ndf * 2, ndf * 4), m[5], m[6], ACT_LEAKY, 0.2, noise=nz),
+                         Block(mk(ndf * 4, 1), m[9], None, ACT_NONE, noise=nz)]
+        else:
+            self.main = [Block(mk(cg, ndf), m[1], m[2], ACT_LEAKY, 0.2, noise=nz),
+                         Block(mk(ndf, ndf * 2), m[5], m[6], ACT_LEAKY, 0.2, noise=nz),
+                         Block(mk(ndf * 2, ndf * 4), m[9], m[10], ACT_LEAKY, 0.2, noise=nz),
+                         Block(mk(ndf * 4, 1), m[13], None, ACT_NONE, noise=nz)]
+
+    def forward(self, xg, xc, training, rng_, save=True):
+        """xg, xc: Acts (B,T,H,W,C) (T == 1 for idis).  Returns logits Act (B, To, 4, 4, 1)."""
+        ndf, dtype = self.mod.ndf, xg.dtype
+        ctx = {}
+        if self.kind == "gdis":
+            h = Act.empty(xg.n, xg.t - 1, xg.h, xg.w, xg.c, dtype)               # discriminator.py:330-331
+            ops.tdiff(xg, h)
+            ctx["xg_shape"] = xg.shape
+        else:
+            sp = self.stem_g.spec.out_spatial(xg.spatial)
+            h = Act.empty(xg.n, sp[0], sp[1], sp[2], ndf, dtype)
+            # Noise draw order: geometry stem first, then colour (discriminator.py:121-122); cat = [hc, hg] (:124)
+            ctx["stem_g"] = self.stem_g.forward(xg, h.ch(ndf // 2, ndf), training, rng_, save)
+            ctx["stem_c"] = self.stem_c.forward(xc, h.ch(0, ndf // 2), training, rng_, save)
+        mctx = []
+        for blk in self.main:
+            sp = blk.spec.out_spatial(h.spatial)
+            out = Act.empty(h.n, sp[0], sp[1], sp[2], blk.spec.cout, dtype)
+            mctx.append(blk.forward(h, out, training, rng_, save))
+            h = out
+        ctx["main"] = mctx
+        return h, (ctx if save else None)
+
+    def backward(self, ctx, dlogits, sink, need_dx=False, need_dw=True):
+        """Returns (dxg, dxc) Acts or (None, None).  dxc is None for gdis (it ignores xc)."""
+        da = dlogits
+        n_main = len(self.main)
+        for i in range(n_main - 1, -1, -1):
+            x = ctx["main"][i]["x"]
+            first = i == 0
+            if first and self.kind == "gdis" and not need_dx:
+                dx = None
+            else:
+                dx = Act.empty(x.n, x.t, x.h, x.w, x.c, x.dtype)
+            self.main[i].backward(ctx["main"][i], da, sink, dx_out=dx, need_dw=need_dw)
+            da = dx
+        if self.kind == "gdis":
+            if not need_dx:
+                return None, None
+            n, t, h, w, c = ctx["xg_shape"]
+            dxg = Act.empty(n, t, h, w, c, da.dtype)
+            ops.tdiff_bwd(da, dxg, False)
+            return dxg, None
+        ndf = self.mod.ndf
+        dxg = dxc = None
+        if need_dx:
+            xg, xc = ctx["stem_g"]["x"], ctx["stem_c"]["x"]
+            dxg = Act.empty(xg.n, xg.t, xg.h, xg.w, xg.c, xg.dtype)
+            dxc = Act.empty(xc.n, xc.t, xc.h, xc.w, xc.c, xc.dtype)
+        if need_dx or need_dw:
+            self.stem_g.backward(ctx["stem_g"], da.ch(ndf // 2, ndf), sink, dx_out=dxg, need_dw=need_dw)
+            self.stem_c.backward(ctx["stem_c"], da.ch(0, ndf // 2), sink, dx_out=dxc, need_dw=need_dw)
+        return dxg, dxc

@@ -176,7 +176,8 @@ def ggen_sample_z(P, B, cfg):
     hs = []
     for _ in range(T):
         e = torch.empty((B, g["dim_z_motion"])).normal_()         # generator.py:87-88
-        h = gru_cell(e, h, P["recurrent.weight_ih"], P["recurrent.weight_hh"], P["recurrent.bias_ih"], P["recurrent.bias_hh"])
+        # nn.GRUCell.forward == torch.gru_cell; `gru_cell` below restates its equations (tests/test_oracle.py checks both agree)
+        h = torch.gru_cell(e, h, P["recurrent.weight_ih"], P["recurrent.weight_hh"], P["recurrent.bias_ih"], P["recurrent.bias_hh"])
         hs.append(h)
     z_m = torch.stack(hs, 1).view(B * T, -1)                      # generator.py:96-99
     return torch.cat([z_c, z_m], 1)                               # generator.py:114
@@ -375,7 +376,8 @@ class OracleTrainer:
             for n in ("idis", "vdis", "gdis"):
                 if n in self.opt:
                     self.opt[n].step()
-        out = {"loss_idis": float(loss_i), "loss_vdis": float(loss_v), "loss_gdis": float(loss_g) if loss_g is not None else None}
+        out = {"loss_idis": float(loss_i.detach()), "loss_vdis": float(loss_v.detach()),
+               "loss_gdis": float(loss_g.detach()) if loss_g is not None else None}
         # ---- generator phase (trainer.py:338-368)
         self.gen_training = True
         self._zero(("ggen", "cgen"))
@@ -388,7 +390,7 @@ class OracleTrainer:
             self.opt["ggen"].step()
             self.opt["cgen"].step()
             self.opt["ggen"].step()                                               # trainer.py:357-359 (twice)
-        out["loss_gen"] = float(loss_gen)
+        out["loss_gen"] = float(loss_gen.detach())
         out["t_rand"] = int(t_rand)
         return out
 
