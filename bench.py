@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the DCVGAN training step (BASELINE.json metric: train iters/sec, 16x64x64 clips, batch 32/GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config mug-depth]
+
+One "step" = one full iteration of the reference's trainer.py:271-363 body (D-phase + G-phase, both updating)
+on one batch of 32 synthetic clips per GPU.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+# one visible device per rank so that the reference's hard-coded cuda:0 (util.py:25-26) stays valid
+if "LOCAL_RANK" in os.environ and "DCV_KEEP_VISIBLE" not in os.environ:
+    os.environ["CUDA_VISIBLE_DEVICES"] = os.environ["LOCAL_RANK"]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+O = {"lr": 0.0002, "decay": 0.00001}
+CONFIGS = {
+    # config/mug-depth.yml normalised: C=1, ngf 64/64, ndf 64/64, adversarial loss, no noise, no gdis
+    "mug-depth": {"geometric_info": {"name": "depth", "channel": 1}, "loss": "adversarial-loss", "seed": 0,
+                  "ggen": {"dim_z_content": 40, "dim_z_motion": 10, "ngf": 64, "optimizer": O},
+                  "cgen": {"dim_z_color": 10, "ngf": 64, "optimizer": O},
+                  "idis": {"use_noise": False, "noise_sigma": 0.1, "ndf": 64, "optimizer": O},
+                  "vdis": {"use_noise": False, "noise_sigma": 0.1, "ndf": 64, "optimizer": O},
+                  "gdis": {"use_noise": False, "noise_sigma": 0.2, "ndf": 32, "optimizer": O, "enabled": False}},
+    # config/isogd-flow.yml: C=2, hinge loss, Noise 0.2 on idis/vdis, gdis ndf 32 without noise
+    "isogd-flow": {"geometric_info": {"name": "optical-flow", "channel": 2}, "loss": "hinge-loss", "seed": 15,
+                   "ggen": {"dim_z_content": 40, "dim_z_motion": 10, "ngf": 64, "optimizer": O},
+                   "cgen": {"dim_z_color": 10, "ngf": 64, "optimizer": O},
+                   "idis": {"use_noise": True, "noise_sigma": 0.2, "ndf": 64, "optimizer": O},
+                   "vdis": {"use_noise": True, "noise_sigma": 0.2, "ndf": 64, "optimizer": O},
+                   "gdis": {"use_noise": False, "noise_sigma": 0.2, "ndf": 32, "optimizer": O, "enabled": True}},
+}
+
+
+def make_cfg(name, batch):
+    cfg = json.loads(json.dumps(CONFIGS[name]))
+    cfg.update({"batchsize": batch, "video_length": 16, "image_size": 64, "num_gen_update": 1, "num_dis_update": 1,
+                "n_epochs": 1, "log_interval": 10 ** 9, "snapshot_interval": 10 ** 9, "log_samples_interval": 10 ** 9,
+                "evaluation_interval": 10 ** 9, "evaluation": {"batchsize": 50, "num_samples": 0, "metrics": []},
+                "config_path": ""})
+    return cfg
+
+
+def step_flops(cfg, B):
+    """Useful FLOPs of one iteration = 4 F_G + 8 F_D with F = sum of forward 2*M*N*K."""
+    C, T = cfg["geometric_info"]["channel"], 16
+    n = B * T
+    g, c = cfg["ggen"]["ngf"], cfg["cgen"]["ngf"]
+
+    def conv(m, nn_, k):
+        return 2.0 * m * nn_ * k
+    fg = conv(n, 16 * 8 * g, 50)
+    for ci, co, hin in ((8 * g, 4 * g, 4), (4 * g, 2 * g, 8), (2 * g, g, 16), (g, C, 32)):
+        fg += conv(n * hin * hin * 4, co, 4 * ci)
+    fg += conv(n * 64 * 64, c, 9 * C)
+    for ci, co, hout in ((c, c, 32), (c, 2 * c, 16), (2 * c, 4 * c, 8), (4 * c, 4 * c, 4), (4 * c, 4 * c, 2), (4 * c, 4 * c, 1)):
+        fg += conv(n * hout * hout, co, 16 * ci)
+    for ci, co, hin in ((4 * c + 10, 4 * c, 1), (8 * c, 4 * c, 2), (8 * c, 4 * c, 4), (8 * c, 2 * c, 8), (4 * c, c, 16), (2 * c, c, 32)):
+        fg += conv(n * hin * hin * 4, co, 4 * ci)
+    fg += conv(n * 64 * 64, 3, 9 * 2 * c)
+    fd = 0.0
+    d = cfg["idis"]["ndf"]
+    fd += conv(B * 32 * 32, d // 2, 16 * C) + conv(B * 32 * 32, d // 2, 48) + conv(B * 256, 2 * d, 16 * d) + conv(B * 64, 4 * d, 32 * d) + conv(B * 16, 1, 64 * d)
+    d = cfg["vdis"]["ndf"]
+    fd += conv(B * 13 * 1024, d // 2, 64 * C) + conv(B * 13 * 1024, d // 2, 192) + conv(B * 10 * 256, 2 * d, 64 * d) + conv(B * 7 * 64, 4 * d, 128 * d) + conv(B * 4 * 16, 1, 256 * d)
+    if cfg["gdis"].get("enabled", True):
+        d = cfg["gdis"]["ndf"]
+        fd += conv(B * 12 * 1024, d, 64 * C) + conv(B * 9 * 256, 2 * d, 64 * d) + conv(B * 6 * 64, 4 * d, 128 * d) + conv(B * 3 * 16, 1, 256 * d)
+    return 4 * fg + 8 * fd, fg, fd
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.stop_flag = threading.Event()
+        self.rows = []
+        self.index = index
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None),
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["bf16_tflops"], d["bf16_tflops_sustained"], d["hbm_gbs"], "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args, cfg_name):
+    """The reference's CPU implementation of the step = the pinned oracle port, all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import dcvgan_oracle as orc
+    torch.set_num_threads(os.cpu_count())
+    Bs = args.ref_batch
+    cfg = make_cfg(cfg_name, Bs)
+    tr = orc.OracleTrainer(cfg, orc.init_all(cfg, cfg["seed"]))
+    torch.manual_seed(cfg["seed"])
+    np.random.seed(cfg["seed"])
+    xc, xg = orc.synthetic_batch(cfg, Bs, 1000)
+    for _ in range(args.warmup):
+        tr.step(xc, xg)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tr.step(xc, xg)
+    dt = (time.perf_counter() - t0) / args.steps
+    # one batch-32 iteration costs 32/Bs sampled iterations (conv cost is linear in the batch)
+    value = 1.0 / (dt * 32.0 / Bs)
+    sample = f"{args.steps} timed iteration(s) of the full step at batch {Bs} (scaled x{32 // Bs} to batch 32), fp32, {torch.get_num_threads()} threads"
+    line = {"impl": "reference", "metric": "train iters/sec (16x64x64 clips, batch 32)", "value": value, "unit": "iters/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 32.0 / Bs * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"config/{cfg_name}.yml (normalised) training step, batch 32, 16x64x64"},
+            "cpu_baseline": {"value": value, "unit": "iters/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- CUDA arm
+def build_trainer(cfg, precision):
+    import dcvgan_b200
+    from dcvgan_b200 import discriminator, engine, generator, loss, trainer, util
+    dcvgan_b200.require_device()
+    dcvgan_b200.set_precision(precision)
+    engine.set_rng_mode("device")
+    C, gname = cfg["geometric_info"]["channel"], cfg["geometric_info"]["name"]
+    torch.manual_seed(cfg["seed"])
+    models = {"ggen": generator.GeometricVideoGenerator(40, 10, C, gname, cfg["ggen"]["ngf"], 16),
+              "cgen": generator.ColorVideoGenerator(C, 10, gname, cfg["cgen"]["ngf"], 16),
+              "idis": discriminator.ImageDiscriminator(C, 3, cfg["idis"]["use_noise"], cfg["idis"]["noise_sigma"], cfg["idis"]["ndf"]),
+              "vdis": discriminator.VideoDiscriminator(C, 3, cfg["vdis"]["use_noise"], cfg["vdis"]["noise_sigma"], cfg["vdis"]["ndf"])}
+    if cfg["gdis"].get("enabled", True):
+        models["gdis"] = discriminator.GradientDiscriminator(C, 3, cfg["gdis"]["use_noise"], cfg["gdis"]["noise_sigma"], cfg["gdis"]["ndf"])
+    for m in models.values():
+        m.apply(util.init_weights)
+        m.cuda()
+    opts = {k: torch.optim.Adam(m.parameters(), lr=cfg[k]["optimizer"]["lr"], betas=(0.5, 0.999),
+                                weight_decay=cfg[k]["optimizer"]["decay"]) for k, m in models.items()}
+    L = loss.AdversarialLoss() if cfg["loss"] == "adversarial-loss" else loss.HingeLoss()
+
+    class _Log:
+        path = "/tmp/dcv_bench_rank%s" % os.environ.get("RANK", "0")
+
+        def __getattr__(self, n):
+            return lambda *a, **k: None
+    os.makedirs(_Log.path, exist_ok=True)
+    trainer.Trainer.save_classobj = lambda self: None
+    return trainer.Trainer(None, _Log(), models, opts, L, cfg)
+
+
+def dominant_kernel_probe(cfg, B, iters=20):
+    """vdis main.1 Conv3d 64->128 forward at batch B (the 60%-of-peak target layer, 85.9 GF at B=32): CUDA-event time
+    of the tcgen05 kernel alone, L2 flushed between launches."""
+    import ctypes as C
+    from dcvgan_b200 import ops
+    from dcvgan_b200._lib import IMPL_TC
+    d = cfg["vdis"]["ndf"]
+    spec = ops.ConvSpec("conv", d, 2 * d, (4, 4, 4), (1, 2, 2), (0, 1, 1))
+    g = spec.geom(B, (13, 32, 32))
+    if not ops.lib().dcv_conv_tc_supported(C.byref(g), spec.fwd_dir):
+        return None
+    x = ops.Act.empty(B, 13, 32, 32, d, torch.bfloat16)
+    x.base.normal_()
+    y = ops.Act.empty(B, 10, 16, 16, 2 * d, torch.bfloat16)
+    w = torch.randn(2 * d, d, 4, 4, 4, device="cuda") * 0.02
+    wp = ops.pack_weight(spec, g, spec.fwd_dir, IMPL_TC, w)
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        ops.conv(g, spec.fwd_dir, IMPL_TC, x, wp, y)
+    times = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv(g, spec.fwd_dir, IMPL_TC, x, wp, y)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    flops = 2.0 * (B * 10 * 16 * 16) * (2 * d) * (64 * d)
+    return {"kernel": "conv_tc_kernel (vdis main.1 Conv3d fwd)", "ms": ms, "tflops": flops / ms / 1e9, "flops": flops}
+
+
+def cpu_baseline(cfg_name, budget_s=25.0):
+    """Oracle port timed on this box's host cores on a bounded sample of the same workload (rank 0, N=1 only)."""
+    from oracle import dcvgan_oracle as orc
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    Bs = 4
+    cfg = make_cfg(cfg_name, Bs)
+    tr = orc.OracleTrainer(cfg, orc.init_all(cfg, cfg["seed"]))
+    xc, xg = orc.synthetic_batch(cfg, Bs, 1000)
+    t0 = time.perf_counter()
+    tr.step(xc, xg)
+    warm = time.perf_counter() - t0
+    n = max(1, min(3, int(budget_s / max(warm, 1e-3)) - 1))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        tr.step(xc, xg)
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 1.0 / (dt * 32.0 / Bs), "unit": "iters/s", "cores": threads, "kind": "port",
+            "sample": f"{n} iteration(s) of the full step at batch {Bs} after 1 warm-up, scaled x{32 // Bs} to batch 32, fp32"}
+
+
+def run_cuda(args, cfg_name):
+    import torch.distributed as dist
+    from dcvgan_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(0)
+        dist.init_process_group("nccl", device_id=torch.device("cuda:0"))
+    B = 32
+    cfg = make_cfg(cfg_name, B)
+    cfg["seed"] = cfg["seed"]
+    tr = build_trainer(cfg, args.precision)
+    torch.manual_seed(cfg["seed"] + rank)
+    np.random.seed(cfg["seed"] + rank)
+    C = cfg["geometric_info"]["channel"]
+    gen = torch.Generator().manual_seed(cfg["seed"] + 1000 * rank)
+    nbuf = 4
+    host = [(torch.rand((B, 3, 16, 64, 64), generator=gen).mul_(2).sub_(1).pin_memory(),
+             torch.rand((B, C, 16, 64, 64), generator=gen).mul_(2).sub_(1).pin_memory()) for _ in range(nbuf)]
+    dev = [(a.cuda(), b.cuda()) for a, b in host]
+    h2d = sum(t.numel() * 4 for t in host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    def resident_step(i):
+        tr.iteration += 1
+        xc, xg = dev[i % nbuf]
+        tr.train_step(xc, xg)
+
+    loss_host = torch.empty(4).pin_memory()
+
+    def e2e_step(i):
+        tr.iteration += 1
+        xc, xg = host[i % nbuf]
+        l = tr.train_step(xc.cuda(non_blocking=True), xg.cuda(non_blocking=True))
+        loss_host.copy_(l, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the user reads the losses each step (trainer.py:326-328,363)
+
+    for i in range(max(args.warmup, 3)):
+        resident_step(i)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")) if "DCV_KEEP_VISIBLE" in os.environ else 0)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.lib().dcv_launch_count()
+    ms = timed(resident_step, args.steps)
+    launches = _lib.lib().dcv_launch_count() - l0
+    ms_e2e = timed(e2e_step, args.steps)
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+    flops, fg, fd = step_flops(cfg, B)
+    burst, sustained, hbm, src = peaks()
+    line = {"metric": "train iters/sec (16x64x64 clips, batch 32)", "value": world * 1e3 / ms, "unit": "iters/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"config/{cfg_name}.yml (normalised) training step, batch 32 per GPU, 16x64x64, D and G both update every iteration",
+                       "l2": f"{nbuf} rotating input batches; per-step activation traffic >> 126 MB L2",
+                       "parallelism": f"dp{world}", "useful_tflop_per_step": flops / 1e12,
+                       "step_tflops": flops / ms / 1e9, "step_frac_of_sustained_peak": flops / ms / 1e9 / sustained},
+            "e2e": {"value": world * 1e3 / ms_e2e, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary() if rank == 0 else None}
+    if rank == 0:
+        probe = dominant_kernel_probe(cfg, B) if args.precision == "bf16" else None
+        if probe:
+            line["roofline"] = {"bound": "tensor", "achieved": probe["tflops"], "peak": burst, "unit": "TFLOP/s",
+                                "frac": probe["tflops"] / burst, "traffic": None, "kernel": probe["kernel"],
+                                "ms_per_launch": probe["ms"], "peak_source": f"{src} burst (kernel timed alone)"}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(cfg_name)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--config", default="mug-depth", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--ref-batch", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 3:
+            args.steps = 3      # bounded sample: a batch-32 CPU iteration takes ~10-20 s
+        args.warmup = min(args.warmup, 1)
+        run_reference(args, args.config)
+    else:
+        run_cuda(args, args.config)
+
+
+if __name__ == "__main__":
+    main()

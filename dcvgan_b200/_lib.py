@@ -37,6 +37,7 @@ SIGNATURES = {
     "dcv_abi_version": (_i, []),
     "dcv_last_error": (C.c_char_p, []),
     "dcv_device_ok": (_i, []),
+    "dcv_launch_count": (C.c_longlong, []),
     "dcv_packed_weight_bytes": (_i64, [_G, _i, _i]),
     "dcv_pack_weight": (_i, [_G, _i, _i, _vp, _i64, _i64, _i64, _vp, _vp]),
     "dcv_conv_tc_supported": (_i, [_G, _i]),

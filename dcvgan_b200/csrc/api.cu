@@ -14,7 +14,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launches = 0;
+
 int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -58,6 +61,8 @@ extern "C" {
 
 int dcv_abi_version(void) { return DCV_ABI_VERSION; }
 const char* dcv_last_error(void) { return g_err; }
+
+long long dcv_launch_count(void) { return g_launches; }
 
 int dcv_device_ok(void) {
   int dev = 0;

@@ -53,8 +53,8 @@ class _DisFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, kind, xg, xc, *params):
         plan = engine.DisPlan(mod, kind)
-        need_dx = torch.is_grad_enabled() and (xg.requires_grad or xc.requires_grad)
-        save = need_dx or _needs_grad(params)
+        need_dx = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        save = any(ctx.needs_input_grad)
         dtype = ops.torch_dtype(mod.precision)
 
         def to_act(x):

@@ -38,7 +38,7 @@ class _GGenFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, batchsize, *params):
         plan = engine.GGenPlan(mod)
-        save = _needs_grad(params)
+        save = any(ctx.needs_input_grad)      # grad mode is off inside Function.forward; this is the autograd-aware flag
         dtype = ops.torch_dtype(mod.precision)
         out, pctx = plan.forward(batchsize, mod.training, dtype, engine.rng(), save)
         B, T, C = batchsize, mod.video_length, mod.channel
@@ -144,8 +144,8 @@ class _CGenFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, x, z, *params):
         plan = engine.CGenPlan(mod)
-        need_dx = torch.is_grad_enabled() and x.requires_grad
-        save = need_dx or _needs_grad(params)
+        need_dx = ctx.needs_input_grad[1]
+        save = any(ctx.needs_input_grad)
         dtype = ops.torch_dtype(mod.precision)
         N, C, H, W = x.shape
         xa = Act.empty(N, 1, H, W, C, dtype)

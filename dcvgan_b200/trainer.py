@@ -1,0 +1,351 @@
+"""Drop-in replacement for the reference's src/trainer.py `Trainer` (same constructor, `.train()`,
+`.iteration`, `.epoch`, snapshot files), with the per-iteration body of trainer.py:271-363 executed as
+one fused schedule over the libdcvgan_b200 kernels instead of PyTorch autograd:
+
+  * every forward pass and every RNG draw happens in the reference's order (real idis/vdis/gdis, ggen,
+    cgen, fake idis/vdis/gdis; then the G-phase), so seeds and BatchNorm running statistics evolve
+    identically - including the D-phase fakes being generated in whatever train/eval mode the generators
+    were left in (trainer.py:126-127 quirk), D BatchNorm always in training mode, the swapped update
+    gates (:318,:355) and opt_ggen stepping twice (:357,:359);
+  * the provably dead work is skipped: no generator backward in the D-phase, no
+    discriminator weight gradients in the G-phase;
+  * parameters, gradients and Adam moments of each network live in flat fp32 buffers: one Adam launch per
+    optimizer step and one NCCL all-reduce per network per phase when torch.distributed is initialised
+    (data-parallel replicas, per-replica BatchNorm statistics);
+  * losses stay on the device and reach `logger.update()` in order when the log interval fires, instead of
+    four host syncs per iteration (trainer.py:326-328,363).
+"""
+import copy
+import shutil
+from pathlib import Path
+from typing import Any, Dict
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import _lib, engine, ops
+from .generator import current_device
+from .ops import Act
+
+try:  # the reference's logger module when train.py of the reference drives us
+    from logger import MetricType  # type: ignore
+except Exception:  # pragma: no cover - standalone use
+    import enum
+
+    class MetricType(enum.Enum):
+        Loss = 1
+        Float = 2
+
+
+class _FlatNet:
+    """Flat fp32 storage for one network's parameters, gradients and Adam moments."""
+
+    def __init__(self, model, opt):
+        self.model, self.opt = model, opt
+        self.params = [p for p in model.parameters()]
+        n = sum(p.numel() for p in self.params)
+        # 4-element alignment per tensor keeps every view 16-byte aligned for the vectorised Adam path
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        dev = self.params[0].device
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad_of = {}
+        self.numel = n
+        for p, o in zip(self.params, offs):
+            k = p.numel()
+            self.flat_p[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[o:o + k].view(p.shape)
+            g = self.flat_g[o:o + k].view(p.shape)
+            p.grad = g
+            self.grad_of[p] = g
+            st = opt.state[p]
+            if "exp_avg" in st:  # resume from an optimizer that already stepped
+                self.flat_m[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                self.flat_v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+            st["exp_avg"] = self.flat_m[o:o + k].view(p.shape)
+            st["exp_avg_sq"] = self.flat_v[o:o + k].view(p.shape)
+            if "step" not in st:
+                st["step"] = torch.tensor(0.0)
+        self.step_count = int(float(opt.state[self.params[0]]["step"]))
+
+    def adam_step(self, grad_scale=1.0):
+        """torch.optim.Adam.step() on the flat buffers (train.py:170-176 hyper-parameters)."""
+        g = self.opt.param_groups[0]
+        self.step_count += 1
+        b1, b2 = g["betas"]
+        _lib.check(_lib.lib().dcv_adam_flat(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+                                            self.flat_v.data_ptr(), self.flat_p.numel(), g["lr"], b1, b2, g["eps"],
+                                            g["weight_decay"], self.step_count, grad_scale,
+                                            torch.cuda.current_stream().cuda_stream))
+        for p in self.params:
+            self.opt.state[p]["step"] = torch.tensor(float(self.step_count))
+
+
+class Trainer(object):
+    def __init__(self, dataloader, logger, models: Dict[str, nn.Module], optimizers: Dict[str, Any], loss,
+                 configs: Dict[str, Any]):
+        self.dataloader = dataloader
+        self.logger = logger
+        self.models = models
+        self.optimizers = optimizers
+        self.loss = loss
+        self.configs = configs
+        self.device = current_device()
+        self.geometric_info = configs["geometric_info"]["name"]
+        self.num_log, self.rows_log, self.cols_log = 25, 5, 5
+        self.eval_batchsize = configs["evaluation"]["batchsize"]
+        self.eval_num_samples = configs["evaluation"]["num_samples"]
+        self.eval_metrics = configs["evaluation"]["metrics"]
+        self.use_gdis = "gdis" in models and models["gdis"] is not None and configs.get("gdis", {}).get("enabled", True)
+        if not hasattr(loss, "KIND_REAL"):
+            raise TypeError("dcvgan_b200.trainer.Trainer needs a dcvgan_b200.loss.AdversarialLoss / HingeLoss instance")
+
+        self.model_snapshots_path = Path(self.logger.path) / "models"
+        self.model_snapshots_path.mkdir(parents=True, exist_ok=True)
+        if configs.get("config_path") and Path(configs["config_path"]).exists():
+            shutil.copy(configs["config_path"], str(Path(self.logger.path) / "config.yml"))
+
+        self.iteration: int = 0
+        self.epoch: int = 0
+        self._flat = None
+        self._pending = []          # device-side loss records waiting for the next log flush
+        self.on_log_samples = None  # optional hooks for the (out-of-scope) visual logging / IS-FID evaluation
+        self.on_evaluate = None
+        self.save_classobj()
+
+    # ------------------------------------------------------------------ periodic side work (trainer.py:70-224)
+    def save_classobj(self):
+        """whole-module pickles, `<log>/models/{name}_model.pth` (trainer.py:70-76)"""
+        for name, _model in self.models.items():
+            model = copy.deepcopy(_model).cpu()
+            torch.save(model, self.model_snapshots_path / f"{name}_model.pth")
+
+    def save_params(self):
+        """state_dict snapshots `{name}_params_{iteration:05d}.pth` (trainer.py:78-86)"""
+        if dist.is_initialized() and dist.get_rank() != 0:
+            return
+        for name, model in self.models.items():
+            sd = {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
+            torch.save(sd, self.model_snapshots_path / f"{name}_params_{self.iteration:05d}.pth")
+
+    def log_hparams(self):
+        def flat(item, key):
+            if type(item) != dict:
+                return {key: str(item)}
+            out = {}
+            for k, v in item.items():
+                out.update(flat(v, k if key == "" else key + "/" + k))
+            return out
+        fn = getattr(self.logger, "tf_log_hparams", None)
+        if fn is not None:
+            fn(flat(self.configs, ""))
+
+    def log_samples(self, ggen, cgen, iteration):
+        """Visual logging is outside the hot path; what matters to the step is that the generators are left in
+        eval mode afterwards (trainer.py:126-127), which the next D-phase then observes."""
+        ggen.eval()
+        cgen.eval()
+        if self.on_log_samples is not None:
+            self.on_log_samples(self, ggen, cgen, iteration)
+
+    def evaluate(self, ggen, cgen):
+        if self.on_evaluate is not None:
+            ggen.eval()
+            cgen.eval()
+            self.on_evaluate(self, ggen, cgen)
+
+    # ------------------------------------------------------------------ fused step
+    def _prepare(self):
+        if self._flat is not None:
+            return
+        _lib.require_device()
+        names = ["ggen", "cgen", "idis", "vdis"] + (["gdis"] if self.use_gdis else [])
+        for n in names:
+            self.models[n].to(self.device)
+        self._flat = {n: _FlatNet(self.models[n], self.optimizers[n]) for n in names}
+        self._plans = {"ggen": engine.GGenPlan(self.models["ggen"]), "cgen": engine.CGenPlan(self.models["cgen"])}
+        for n in names[2:]:
+            self._plans[n] = engine.DisPlan(self.models[n], n)
+        self._dnames = names[2:]
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.dtype = ops.torch_dtype(self.models["ggen"].precision)
+
+    def _allreduce(self, names):
+        if self.world > 1:
+            for n in names:
+                dist.all_reduce(self._flat[n].flat_g)
+
+    def _to_clip(self, x):
+        """(B,C,T,H,W) fp32 torch tensor -> channels-last Act (B,T,H,W,C)"""
+        b, c, t, h, w = x.shape
+        a = Act.empty(b, t, h, w, c, self.dtype)
+        ops.to_channels_last(x.float(), a)
+        return a
+
+    def _frame(self, clip, t):
+        f = Act.empty(clip.n, 1, clip.h, clip.w, clip.c, clip.dtype)
+        ops.frame_extract(clip, t, f)
+        return f
+
+    def _dis_forward(self, xg, xc, t_rand, save):
+        """idis on frame t_rand, vdis and gdis on the clips, in the reference's order (trainer.py:299-301)."""
+        r = engine.rng()
+        out = {}
+        out["idis"] = self._plans["idis"].forward(self._frame(xg, t_rand), self._frame(xc, t_rand), True, r, save)
+        out["vdis"] = self._plans["vdis"].forward(xg, xc, True, r, save)
+        if self.use_gdis:
+            out["gdis"] = self._plans["gdis"].forward(xg, None, True, r, save)
+        return out
+
+    def _generate(self, B, ggen_training, cgen_training, save):
+        """ggen.sample_videos + cgen.forward_videos (trainer.py:304-305,344-345) on channels-last buffers."""
+        r = engine.rng()
+        ggen, cgen = self.models["ggen"], self.models["cgen"]
+        T = ggen.video_length
+        xg, gctx = self._plans["ggen"].forward(B, ggen_training, self.dtype, r, save)          # (B*T,1,64,64,C)
+        z = r.normal((B, cgen.dim_z))                                                           # generator.py:355-359
+        zs = z.unsqueeze(1).repeat(1, T, 1).view(B * T, -1)
+        xc, cctx = self._plans["cgen"].forward(xg, zs, cgen_training, r, save)                  # (B*T,1,64,64,3)
+        return xg, xc, gctx, cctx
+
+    def _loss_terms(self, logits, kind, slot, losses, accumulate, want_grad):
+        dy = None
+        y = logits
+        if want_grad:
+            dy = Act.empty(y.n, y.t, y.h, y.w, y.c, y.dtype)
+        _lib.check(_lib.lib().dcv_loss_fwd_bwd(ops.dcv_dtype(y), y.ptr, y.rows * y.c, kind, losses[slot:slot + 1].data_ptr(),
+                                               int(accumulate), None if dy is None else dy.ptr, 1.0,
+                                               torch.cuda.current_stream().cuda_stream))
+        return dy
+
+    def train_step(self, xc_real, xg_real, t_rand=None):
+        """One iteration of trainer.py:279-363.  xc_real (B,3,T,64,64), xg_real (B,C,T,64,64) on the device.
+        Returns a device tensor [loss_idis, loss_vdis, loss_gdis, loss_gen]."""
+        self._prepare()
+        cfg = self.configs
+        B = cfg["batchsize"]
+        ggen, cgen = self.models["ggen"], self.models["cgen"]
+        T = ggen.video_length
+        if t_rand is None:
+            t_rand = np.random.randint(T)                                                       # trainer.py:279
+        losses = torch.zeros(4, dtype=torch.float32, device=self.device)
+        slot = {"idis": 0, "vdis": 1, "gdis": 2}
+        L = self.loss
+
+        # ---------------- discriminator phase (trainer.py:285-333)
+        for n in self._dnames:
+            self.models[n].train()
+        upd_d = self.iteration % cfg["num_gen_update"] == 0                                     # sic, trainer.py:318
+        xc_r, xg_r = self._to_clip(xc_real), self._to_clip(xg_real)
+        real = self._dis_forward(xg_r, xc_r, t_rand, upd_d)
+        xg_f, xc_f, _, _ = self._generate(B, ggen.training, cgen.training, save=False)
+        fake = self._dis_forward(xg_f.reshape_nt(B, T), xc_f.reshape_nt(B, T), t_rand, upd_d)
+        grads = {}
+        for n in self._dnames:
+            dr = self._loss_terms(real[n][0], L.KIND_REAL, slot[n], losses, False, upd_d)
+            df = self._loss_terms(fake[n][0], L.KIND_FAKE, slot[n], losses, True, upd_d)
+            grads[n] = (dr, df)
+        if upd_d:
+            for n in self._dnames:
+                sink = engine.GradSink(self._flat[n].grad_of)
+                self._plans[n].backward(real[n][1], grads[n][0], sink, need_dx=False)
+                self._plans[n].backward(fake[n][1], grads[n][1], sink, need_dx=False)
+            self._allreduce(self._dnames)
+            for n in self._dnames:
+                self._flat[n].adam_step(1.0 / self.world)
+        del real, fake, grads
+
+        # ---------------- generator phase (trainer.py:338-368)
+        ggen.train()
+        cgen.train()
+        upd_g = self.iteration % cfg["num_dis_update"] == 0                                     # sic, trainer.py:355
+        xg_f, xc_f, gctx, cctx = self._generate(B, True, True, save=upd_g)
+        xg_clip, xc_clip = xg_f.reshape_nt(B, T), xc_f.reshape_nt(B, T)
+        fake = self._dis_forward(xg_clip, xc_clip, t_rand, upd_g)
+        gen_terms = ["idis", "vdis"] + (["gdis"] if (self.use_gdis and L.gen_uses_gdis) else [])
+        dls = {}
+        for i, n in enumerate(gen_terms):
+            dls[n] = self._loss_terms(fake[n][0], L.KIND_GEN, 3, losses, i > 0, upd_g)
+        if upd_g:
+            none = engine.GradSink()
+            dxg = Act.empty(B, T, 64, 64, xg_clip.c, self.dtype)
+            dxc = Act.empty(B, T, 64, 64, 3, self.dtype)
+            g_v, c_v = self._plans["vdis"].backward(fake["vdis"][1], dls["vdis"], none, need_dx=True, need_dw=False)
+            ops.copy_cl(g_v, dxg)
+            ops.copy_cl(c_v, dxc)
+            g_i, c_i = self._plans["idis"].backward(fake["idis"][1], dls["idis"], none, need_dx=True, need_dw=False)
+            ops.frame_scatter(dxg, t_rand, g_i, True)
+            ops.frame_scatter(dxc, t_rand, c_i, True)
+            if "gdis" in dls:
+                g_g, _ = self._plans["gdis"].backward(fake["gdis"][1], dls["gdis"], none, need_dx=True, need_dw=False)
+                ops.axpy(g_g, dxg, True)
+            sink_c = engine.GradSink(self._flat["cgen"].grad_of)
+            dxg_c = self._plans["cgen"].backward(cctx, dxc.reshape_nt(B * T, 1), sink_c, need_dx=True)
+            if dxg_c is not None:
+                ops.axpy(dxg_c.reshape_nt(B, T), dxg, True)
+            sink_g = engine.GradSink(self._flat["ggen"].grad_of)
+            self._plans["ggen"].backward(gctx, dxg.reshape_nt(B * T, 1), sink_g)
+            self._allreduce(["ggen", "cgen"])
+            self._flat["ggen"].adam_step(1.0 / self.world)
+            self._flat["cgen"].adam_step(1.0 / self.world)
+            self._flat["ggen"].adam_step(1.0 / self.world)                                      # trainer.py:357-359
+        return losses
+
+    # ------------------------------------------------------------------ logging of device-side losses
+    def _flush_losses(self):
+        if not self._pending:
+            return
+        vals = torch.stack([l for _, _, l in self._pending]).cpu().tolist()
+        for (it, ep, _), v in zip(self._pending, vals):
+            self.logger.update("iteration", it)
+            self.logger.update("epoch", ep)
+            self.logger.update("loss_idis", v[0])
+            self.logger.update("loss_vdis", v[1])
+            if self.use_gdis:
+                self.logger.update("loss_gdis", v[2])
+            self.logger.update("loss_gen", v[3])
+        self._pending = []
+
+    def train(self):
+        """Start training (trainer.py:226-392)."""
+        self._prepare()
+        ggen, cgen = self.models["ggen"], self.models["cgen"]
+        for name in ("loss_gen", "loss_idis", "loss_vdis", "loss_gdis"):
+            self.logger.define(name, MetricType.Loss)
+        for m in self.configs["evaluation"]["metrics"]:
+            self.logger.define(m, MetricType.Float)
+        self.log_hparams()
+        self.log_samples(ggen, cgen, 0)
+        self.evaluate(ggen, cgen)
+        if hasattr(self.logger, "print_header"):
+            self.logger.print_header()
+        cfg = self.configs
+        for _ in range(cfg["n_epochs"]):
+            self.epoch += 1
+            for batch in iter(self.dataloader):
+                self.iteration += 1
+                xc_real = batch["color"].to(self.device, non_blocking=True)
+                xg_real = batch[self.geometric_info].to(self.device, non_blocking=True)
+                losses = self.train_step(xc_real, xg_real)
+                self._pending.append((self.iteration, self.epoch, losses))
+                if self.iteration % cfg["snapshot_interval"] == 0:
+                    self.save_params()
+                if self.iteration % cfg["log_samples_interval"] == 0:
+                    self.log_samples(ggen, cgen, self.iteration)
+                if self.iteration % cfg["evaluation_interval"] == 0:
+                    self._flush_losses()
+                    self.evaluate(ggen, cgen)
+                if self.iteration % cfg["log_interval"] == 0:
+                    self._flush_losses()
+                    self.logger.log()
+                    self.logger.clear()
+        self._flush_losses()
+        self.save_params()
+        self.log_samples(ggen, cgen, self.iteration)

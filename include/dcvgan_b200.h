@@ -68,6 +68,8 @@ int dcv_abi_version(void);
 const char* dcv_last_error(void);
 /* 1 if the device behind the current context is sm_100 (B200); the host side refuses to run otherwise */
 int dcv_device_ok(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
+long long dcv_launch_count(void);
 
 /* ---- weight packing -------------------------------------------------------------------------
  * Re-lays a PyTorch fp32 master weight for one direction of a layer.  `w` is addressed as

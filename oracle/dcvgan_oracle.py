@@ -339,6 +339,8 @@ class OracleTrainer:
             plist = [v for k, v in self.P[name].items() if is_param(k)]
             self.opt[name] = torch.optim.Adam(plist, lr=o["lr"], betas=(0.5, 0.999), weight_decay=o["decay"])
         self.iteration = 0
+        self.capture_grads = False
+        self.d_grads = self.g_grads = None
         self.gen_training = True   # log_samples()/evaluate() leave the generators in eval mode (trainer.py:126-127)
 
     def _zero(self, names):
@@ -373,6 +375,9 @@ class OracleTrainer:
             loss_dis = loss_dis + loss_g
         if self.iteration % cfg["num_gen_update"] == 0:                           # trainer.py:318 (names swapped)
             loss_dis.backward()
+            if self.capture_grads:   # test hook: the useful D gradients, before the G-phase adds its dead ones
+                self.d_grads = {n: {k: v.grad.clone() for k, v in self.P[n].items() if is_param(k)}
+                                for n in ("idis", "vdis", "gdis") if n in self.opt}
             for n in ("idis", "vdis", "gdis"):
                 if n in self.opt:
                     self.opt[n].step()
@@ -387,6 +392,8 @@ class OracleTrainer:
         loss_gen = gen_loss(kind, yf_i, yf_v, yf_g)
         if self.iteration % cfg["num_dis_update"] == 0:                           # trainer.py:355
             loss_gen.backward()
+            if self.capture_grads:
+                self.g_grads = {n: {k: v.grad.clone() for k, v in self.P[n].items() if is_param(k)} for n in ("ggen", "cgen")}
             self.opt["ggen"].step()
             self.opt["cgen"].step()
             self.opt["ggen"].step()                                               # trainer.py:357-359 (twice)

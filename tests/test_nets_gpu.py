@@ -1,0 +1,285 @@
+"""Network-level and step-level parity of the CUDA path against the (pinned) CPU oracle, plus the
+reference's own shape tests (src/test/test_generator.py, test_discriminator.py, test_util.py) replayed
+against the drop-in modules.
+
+fp32 mode gates (north_star): forward outputs <= 1e-3 norm-relative, gradient cosine >= 0.999.
+bf16 mode: forward <= 3e-2 norm-relative, gradient cosine >= 0.99 (single pass; curves in test_curves_gpu.py).
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from golden_util import CASES, check_digest, expected_losses, load_case  # noqa: E402
+from helpers import cos_sim, rel_err  # noqa: E402
+from oracle import dcvgan_oracle as orc  # noqa: E402
+
+
+def _mods():
+    import dcvgan_b200
+    dcvgan_b200.require_device()
+    from dcvgan_b200 import discriminator, engine, generator, loss, trainer, util
+    return dcvgan_b200, generator, discriminator, loss, trainer, util, engine
+
+
+def build_models(cfg, init, precision):
+    dcv, generator, discriminator, _, _, _, _ = _mods()
+    dcv.set_precision(precision)
+    C, gname = cfg["geometric_info"]["channel"], cfg["geometric_info"]["name"]
+    m = {
+        "ggen": generator.GeometricVideoGenerator(cfg["ggen"]["dim_z_content"], cfg["ggen"]["dim_z_motion"], C, gname,
+                                                  cfg["ggen"]["ngf"], cfg["video_length"]),
+        "cgen": generator.ColorVideoGenerator(C, cfg["cgen"]["dim_z_color"], gname, cfg["cgen"]["ngf"], cfg["video_length"]),
+        "idis": discriminator.ImageDiscriminator(C, 3, cfg["idis"]["use_noise"], cfg["idis"]["noise_sigma"], cfg["idis"]["ndf"]),
+        "vdis": discriminator.VideoDiscriminator(C, 3, cfg["vdis"]["use_noise"], cfg["vdis"]["noise_sigma"], cfg["vdis"]["ndf"]),
+    }
+    if cfg["gdis"].get("enabled", True):
+        m["gdis"] = discriminator.GradientDiscriminator(C, 3, cfg["gdis"]["use_noise"], cfg["gdis"]["noise_sigma"], cfg["gdis"]["ndf"])
+    for k, mod in m.items():
+        mod.load_state_dict({a: b.clone() for a, b in init[k].items()})
+        mod.cuda()
+    return m
+
+
+def small_cfg(name="optical-flow", C=2, loss="hinge-loss", noise=True, ngf=6, ndf=8, gdis=True):
+    o = {"lr": 0.0002, "decay": 0.00001}
+    return {"batchsize": 2, "video_length": 16, "geometric_info": {"name": name, "channel": C}, "loss": loss,
+            "num_gen_update": 1, "num_dis_update": 1,
+            "ggen": {"dim_z_content": 40, "dim_z_motion": 10, "ngf": ngf, "optimizer": o},
+            "cgen": {"dim_z_color": 10, "ngf": ngf, "optimizer": o},
+            "idis": {"use_noise": noise, "noise_sigma": 0.2, "ndf": ndf, "optimizer": o},
+            "vdis": {"use_noise": noise, "noise_sigma": 0.2, "ndf": ndf, "optimizer": o},
+            "gdis": {"use_noise": noise, "noise_sigma": 0.2, "ndf": ndf, "optimizer": o, "enabled": gdis},
+            "evaluation": {"batchsize": 2, "num_samples": 0, "metrics": []}, "n_epochs": 1, "log_interval": 1,
+            "snapshot_interval": 10 ** 9, "log_samples_interval": 10 ** 9, "evaluation_interval": 10 ** 9}
+
+
+def _grad_report(mine, ref_grads, tag):
+    worst = 1.0
+    for k, g in ref_grads.items():
+        c = cos_sim(mine[k].cpu(), g)
+        worst = min(worst, c)
+    return worst
+
+
+@pytest.mark.parametrize("precision,ftol,ctol", [("fp32", 1e-3, 0.999), ("bf16", 3e-2, 0.97)])
+@pytest.mark.parametrize("geo", [("depth", 1), ("optical-flow", 2), ("segmentation", 25)])
+def test_generators_match_oracle(precision, ftol, ctol, geo):
+    dcv, generator, _, _, _, _, engine = _mods()
+    cfg = small_cfg(geo[0], geo[1], ngf=8)
+    P = orc.init_all(cfg, 3)
+    models = build_models(cfg, P, precision)
+    engine.set_rng_mode("cpu_parity")
+    Pr = {k: orc.require_grad({a: b.clone() for a, b in v.items()}) for k, v in P.items()}
+    B = 2
+    # oracle
+    torch.manual_seed(11)
+    xg_ref = orc.ggen_sample_videos(Pr["ggen"], B, cfg, True)
+    xc_ref = orc.cgen_forward_videos(Pr["cgen"], xg_ref, cfg, True)
+    gen = torch.Generator().manual_seed(5)
+    d_xc, d_xg = torch.randn(xc_ref.shape, generator=gen), torch.randn(xg_ref.shape, generator=gen)
+    ((xc_ref * d_xc).sum() + (xg_ref * d_xg).sum()).backward()
+    # CUDA path
+    torch.manual_seed(11)
+    xg = models["ggen"].sample_videos(B)
+    xc = models["cgen"].forward_videos(xg)
+    assert xg.shape == xg_ref.shape and xc.shape == xc_ref.shape and xg.stride() == xg_ref.stride()
+    e_g, e_c = rel_err(xg.detach().cpu(), xg_ref.detach()), rel_err(xc.detach().cpu(), xc_ref.detach())
+    ((xc * d_xc.cuda()).sum() + (xg * d_xg.cuda()).sum()).backward()
+    worst = 1.0
+    for net in ("ggen", "cgen"):
+        for k, p in models[net].named_parameters():
+            worst = min(worst, cos_sim(p.grad.cpu(), Pr[net][k].grad))
+    print(f"generators[{precision},{geo[0]}]: xg {e_g:.2e} xc {e_c:.2e} worst grad cos {worst:.5f}")
+    assert e_g < ftol and e_c < ftol, (e_g, e_c)
+    assert worst > ctol, worst
+    # BatchNorm running statistics moved identically
+    for net in ("ggen", "cgen"):
+        sd = models[net].state_dict()
+        for k, v in Pr[net].items():
+            if k.endswith("running_var") or k.endswith("running_mean"):
+                assert rel_err(sd[k].cpu(), v) < max(ftol, 1e-3), (net, k)
+            if k.endswith("num_batches_tracked"):
+                assert int(sd[k]) == int(v)
+
+
+@pytest.mark.parametrize("precision,ftol,ctol", [("fp32", 1e-3, 0.999), ("bf16", 3e-2, 0.97)])
+@pytest.mark.parametrize("kind", ["idis", "vdis", "gdis"])
+@pytest.mark.parametrize("noise", [False, True])
+def test_discriminators_match_oracle(precision, ftol, ctol, kind, noise):
+    dcv, _, _, _, _, _, engine = _mods()
+    cfg = small_cfg("optical-flow", 2, noise=noise, ndf=16)
+    P = orc.init_all(cfg, 4)
+    models = build_models(cfg, P, precision)
+    engine.set_rng_mode("cpu_parity")
+    Pr = orc.require_grad({a: b.clone() for a, b in P[kind].items()})
+    gen = torch.Generator().manual_seed(6)
+    B = 3
+    xg = torch.randn((B, 2, 16, 64, 64), generator=gen).requires_grad_(True)
+    xc = torch.randn((B, 3, 16, 64, 64), generator=gen).requires_grad_(True)
+    xg_d, xc_d = xg.detach().cuda().requires_grad_(True), xc.detach().cuda().requires_grad_(True)
+    sl = (lambda v: v[:, :, 5]) if kind == "idis" else (lambda v: v)
+    torch.manual_seed(12)
+    y_ref = orc.DIS_FORWARD[kind](Pr, sl(xg), sl(xc), cfg, True)
+    dy = torch.randn(y_ref.shape, generator=gen)
+    (y_ref * dy).sum().backward()
+    torch.manual_seed(12)
+    y = models[kind](sl(xg_d), sl(xc_d))
+    assert y.shape == y_ref.shape
+    e = rel_err(y.detach().cpu(), y_ref.detach())
+    (y * dy.cuda()).sum().backward()
+    worst = 1.0
+    for k, p in models[kind].named_parameters():
+        worst = min(worst, cos_sim(p.grad.cpu(), Pr[k].grad))
+    c_xg = cos_sim(xg_d.grad.cpu(), xg.grad)
+    c_xc = cos_sim(xc_d.grad.cpu(), xc.grad) if kind != "gdis" else 1.0
+    print(f"{kind}[{precision},noise={noise}]: y {e:.2e} worst param-grad cos {worst:.5f} dxg {c_xg:.5f} dxc {c_xc:.5f}")
+    assert e < ftol and worst > ctol and c_xg > ctol and c_xc > ctol
+
+
+# ---- the reference's own acceptance tests, replayed on the drop-in modules -------------------------------------
+def test_reference_shape_tests():
+    dcv, generator, discriminator, _, _, util, engine = _mods()
+    engine.set_rng_mode("device")
+    dcv.set_precision("bf16")
+    for inputs in ({"dim_z_content": 30, "dim_z_motion": 10, "channel": 1, "geometric_info": "depth", "video_length": 16},
+                   {"dim_z_content": 30, "dim_z_motion": 10, "channel": 2, "geometric_info": "optical-flow", "video_length": 16}):
+        ggen = generator.GeometricVideoGenerator(**inputs).cuda()          # test_generator.py:19-38
+        assert tuple(ggen.sample_videos(2).shape) == (2, inputs["channel"], 16, 64, 64)
+    cgen = generator.ColorVideoGenerator(in_ch=1, dim_z=10, geometric_info="depth").cuda()   # test_generator.py:40-51
+    z = cgen.make_hidden(2)
+    x = torch.empty(2, 1, 64, 64, device="cuda").normal_()
+    assert tuple(cgen(x, z).shape) == (2, 3, 64, 64) and tuple(z.shape) == (2, 10, 1, 1)
+    kw = {"ch1": 1, "ch2": 3, "use_noise": True, "noise_sigma": 0.2}
+    xi = (torch.empty(2, 1, 64, 64, device="cuda").normal_(), torch.empty(2, 3, 64, 64, device="cuda").normal_())
+    xv = (torch.empty(2, 1, 16, 64, 64, device="cuda").normal_(), torch.empty(2, 3, 16, 64, 64, device="cuda").normal_())
+    assert tuple(discriminator.ImageDiscriminator(**kw).cuda()(*xi).shape) == (2, 4, 4)          # test_discriminator.py:18-36
+    assert tuple(discriminator.VideoDiscriminator(**kw).cuda()(*xv).shape) == (2, 4, 4, 4)       # :38-56
+    assert tuple(discriminator.GradientDiscriminator(**kw).cuda()(*xv).shape) == (2, 3, 4, 4)    # :58-76
+    ggen = generator.GeometricVideoGenerator(30, 10, 1, "depth", 64, 16).cuda()
+    for num, bs in ((3, 1), (3, 2), (3, 4)):                                                     # test_util.py:22-58
+        xg, xc = util.generate_samples(ggen, cgen, num, bs)
+        assert xc.dtype == np.uint8 and xc.shape == (num, 3, 16, 64, 64) and xg.shape == (num, 1, 16, 64, 64)
+
+
+def test_modules_pickle_and_init_weights():
+    """torch.save(model) whole-object pickles and util.init_weights keep working (trainer.py:70-76, train.py:164-165)"""
+    import io
+    dcv, generator, discriminator, _, _, util, _ = _mods()
+    m = discriminator.VideoDiscriminator(2, 3, True, 0.2, 16)
+    g = generator.ColorVideoGenerator(2, 10, "optical-flow", 8)
+    g.apply(util.init_weights)
+    assert abs(float(g.down_blocks[0].main[1].weight.mean()) - 1.0) < 0.05
+    for mod in (m, g):
+        buf = io.BytesIO()
+        torch.save(copy.deepcopy(mod).cpu(), buf)
+        buf.seek(0)
+        back = torch.load(buf, weights_only=False)
+        assert list(back.state_dict()) == list(mod.state_dict())
+
+
+class _Logger:
+    def __init__(self, path):
+        self.path, self.rec = path, []
+
+    def update(self, k, v):
+        self.rec.append((k, v))
+
+    def __getattr__(self, n):
+        return lambda *a, **k: None
+
+
+def _run_side_by_side(cfg, init, iters, precision, tmp_path, batch_seeds, step_seed):
+    """oracle trainer and CUDA trainer from the same state, same seeds, same noise"""
+    dcv, _, _, loss_mod, trainer_mod, _, engine = _mods()
+    models = build_models(cfg, init, precision)
+    engine.set_rng_mode("cpu_parity")
+    opts = {k: torch.optim.Adam(m.parameters(), lr=cfg[k]["optimizer"]["lr"], betas=(0.5, 0.999),
+                                weight_decay=cfg[k]["optimizer"]["decay"]) for k, m in models.items()}
+    L = loss_mod.AdversarialLoss() if cfg["loss"] == "adversarial-loss" else loss_mod.HingeLoss()
+    tr = trainer_mod.Trainer(None, _Logger(tmp_path), models, opts, L, dict(cfg, config_path=""))
+    o = orc.OracleTrainer(cfg, {k: {a: b.clone() for a, b in v.items()} for k, v in init.items()})
+    o.capture_grads = True
+    out = []
+    torch.manual_seed(step_seed)
+    np.random.seed(step_seed)
+    ref_losses, ts = [], []
+    for it in range(iters):
+        xc, xg = orc.synthetic_batch(cfg, cfg["batchsize"], batch_seeds[it])
+        ref_losses.append(o.step(xc, xg))
+        ts.append(ref_losses[-1]["t_rand"])
+        out.append({"d_grads": copy.deepcopy(o.d_grads), "g_grads": copy.deepcopy(o.g_grads)})
+    torch.manual_seed(step_seed)
+    np.random.seed(step_seed)
+    my_losses, my_grads = [], []
+    for it in range(iters):
+        xc, xg = orc.synthetic_batch(cfg, cfg["batchsize"], batch_seeds[it])
+        tr.iteration += 1
+        l = tr.train_step(xc.cuda(), xg.cuda(), t_rand=ts[it])
+        my_losses.append(l.cpu().tolist())
+        my_grads.append({n: {k: p.grad.detach().cpu().clone() for k, p in models[n].named_parameters()} for n in models})
+    return o, tr, models, ref_losses, my_losses, out, my_grads
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_step_matches_golden_fp32(name, tmp_path):
+    """The fused CUDA step replays the golden runs recorded from the reference's Trainer.train()."""
+    meta, init = load_case(name)
+    cfg = meta["cfg"]
+    seeds = [b["seed"] for b in meta["batches"]]
+    o, tr, models, ref_l, my_l, ref_g, my_g = _run_side_by_side(cfg, init, meta["iters"], "fp32", tmp_path, seeds, meta["step_seed"])
+    for it in range(meta["iters"]):
+        exp = expected_losses(meta, it)
+        got = dict(zip(("loss_idis", "loss_vdis", "loss_gdis", "loss_gen"), my_l[it]))
+        for k, v in exp.items():
+            assert abs(got[k] - v) <= 1e-3 * max(1.0, abs(v)), (name, it, k, got[k], v)
+    # gradients of the last iteration against the oracle's (cosine >= 0.999 per parameter tensor)
+    last = meta["iters"] - 1
+    upd_d = (last + 1) % cfg["num_gen_update"] == 0
+    worst = 1.0
+    for net, grads in list((ref_g[last]["g_grads"] or {}).items()) + (list(ref_g[last]["d_grads"].items()) if upd_d else []):
+        for k, g in grads.items():
+            c = cos_sim(my_g[last][net][k], g)
+            worst = min(worst, c)
+            assert c > 0.999, (name, net, k, c)
+    print(f"{name}: losses ok, worst grad cosine {worst:.6f}")
+    # state after training: BatchNorm buffers to 1e-3, parameters within a fraction of one Adam step
+    for net, dig in meta["final"].items():
+        steps = meta["iters"] * (2 if net == "ggen" else 1)
+        check_digest(models[net].state_dict(), dig, rtol=2e-3, atol=1e-4, what=f"{name}/{net}/", lr_steps=2e-4 * steps)
+
+
+def _net_cosines(my, ref):
+    """cosine of the concatenated gradient of each network"""
+    out = {}
+    for net, grads in ref.items():
+        a = torch.cat([my[net][k].flatten().double() for k in grads])
+        b = torch.cat([g.flatten().double() for g in grads.values()])
+        out[net] = float((a @ b) / (a.norm() * b.norm()))
+    return out
+
+
+@pytest.mark.parametrize("precision,ltol,ctol,ntol", [("fp32", 1e-3, 0.999, 0.9999), ("bf16", 5e-2, 0.85, 0.99)])
+def test_train_step_full_width(precision, ltol, ctol, ntol, tmp_path):
+    """One iteration at the real layer widths (ngf = ndf = 64, gdis ndf 32, isogd-flow shapes), batch 2."""
+    cfg = small_cfg("optical-flow", 2, "hinge-loss", noise=True, ngf=64, ndf=64)
+    cfg["gdis"]["ndf"] = 32
+    cfg["gdis"]["use_noise"] = False
+    init = orc.init_all(cfg, 21)
+    o, tr, models, ref_l, my_l, ref_g, my_g = _run_side_by_side(cfg, init, 1, precision, tmp_path, [77], 31)
+    got = dict(zip(("loss_idis", "loss_vdis", "loss_gdis", "loss_gen"), my_l[0]))
+    for k in got:
+        assert abs(got[k] - ref_l[0][k]) <= ltol * max(1.0, abs(ref_l[0][k])), (k, got[k], ref_l[0][k])
+    worst, worst_k = 1.0, None
+    for net, grads in list(ref_g[0]["g_grads"].items()) + list(ref_g[0]["d_grads"].items()):
+        for k, g in grads.items():
+            c = cos_sim(my_g[0][net][k], g)
+            if c < worst:
+                worst, worst_k = c, (net, k)
+    nets = _net_cosines(my_g[0], dict(ref_g[0]["g_grads"], **ref_g[0]["d_grads"]))
+    print(f"full width [{precision}]: losses {got} worst per-tensor grad cosine {worst:.5f} at {worst_k}; per-network {nets}")
+    assert worst > ctol, (worst, worst_k)
+    assert min(nets.values()) > ntol, nets
