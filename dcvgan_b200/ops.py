@@ -6,6 +6,7 @@ torch.cat calls of the reference disappear); `ld` is then the pixel stride of th
 PyTorch only provides memory and streams here - every arithmetic op is a libdcvgan_b200 kernel.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -152,8 +153,11 @@ def _tc_ok(t):
     return t.dtype == torch.bfloat16 and ptr % 16 == 0 and ld % 8 == 0
 
 
+_FORCE_SIMT = bool(int(os.environ.get("DCV_FORCE_SIMT", "0")))   # debugging aid: bf16 storage without tcgen05
+
+
 def choose_conv_impl(g, direction, x):
-    if x.dtype == torch.bfloat16 and _tc_ok(x) and lib().dcv_conv_tc_supported(C.byref(g), direction):
+    if not _FORCE_SIMT and x.dtype == torch.bfloat16 and _tc_ok(x) and lib().dcv_conv_tc_supported(C.byref(g), direction):
         return IMPL_TC
     return IMPL_SIMT
 
@@ -178,7 +182,7 @@ def conv(g, direction, impl, x, wp, y, act=ACT_NONE, slope=0.0):
 
 
 def choose_wgrad_impl(g, xl, xs):
-    if xl.dtype == torch.bfloat16 and _tc_ok(xl) and _tc_ok(xs) and lib().dcv_wgrad_tc_supported(C.byref(g)):
+    if not _FORCE_SIMT and xl.dtype == torch.bfloat16 and _tc_ok(xl) and _tc_ok(xs) and lib().dcv_wgrad_tc_supported(C.byref(g)):
         return IMPL_TC
     return IMPL_SIMT
 

@@ -273,12 +273,14 @@ def test_train_step_full_width(precision, ltol, ctol, ntol, tmp_path):
     got = dict(zip(("loss_idis", "loss_vdis", "loss_gdis", "loss_gen"), my_l[0]))
     for k in got:
         assert abs(got[k] - ref_l[0][k]) <= ltol * max(1.0, abs(ref_l[0][k])), (k, got[k], ref_l[0][k])
-    worst, worst_k = 1.0, None
+    worst, worst_k, allc = 1.0, None, []
     for net, grads in list(ref_g[0]["g_grads"].items()) + list(ref_g[0]["d_grads"].items()):
         for k, g in grads.items():
             c = cos_sim(my_g[0][net][k], g)
+            allc.append((round(c, 5), net, k))
             if c < worst:
                 worst, worst_k = c, (net, k)
+    print("lowest per-tensor cosines:", sorted(allc)[:12])
     nets = _net_cosines(my_g[0], dict(ref_g[0]["g_grads"], **ref_g[0]["d_grads"]))
     print(f"full width [{precision}]: losses {got} worst per-tensor grad cosine {worst:.5f} at {worst_k}; per-network {nets}")
     assert worst > ctol, (worst, worst_k)
