@@ -23,7 +23,7 @@ class Geom(C.Structure):
 
     _fields_ = [(n, C.c_int32) for n in (
         "N", "Tl", "Hl", "Wl", "Cl", "Ts", "Hs", "Ws", "Cs",
-        "kt", "kh", "kw", "st", "sh", "sw", "pt", "ph", "pw")]
+        "kt", "kh", "kw", "st", "sh", "sw", "pt", "ph", "pw", "wCl", "wCs")]
 
     def key(self):
         return tuple(getattr(self, n) for n, _ in self._fields_)
@@ -68,7 +68,7 @@ SIGNATURES = {
     "dcv_frame_copy": (_i, [_i, _vp, _i64, _i, _i, _i64, _i, _i, _vp, _i64, _i, _i, _vp]),
     "dcv_gru_traj_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "dcv_gru_traj_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
-    "dcv_loss_fwd_bwd": (_i, [_i, _vp, _i64, _i, _vp, _i, _vp, _f, _vp]),
+    "dcv_loss_fwd_bwd": (_i, [_i, _vp, _i64, _i64, _i, _vp, _i, _vp, _i64, _f, _vp]),
     "dcv_adam_multi": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64),
                             _f, _f, _f, _f, _f, _i64, _f, _vp]),
     "dcv_adam_flat": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i64, _f, _vp]),
@@ -94,7 +94,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.dcv_abi_version() != 1:
+        if handle.dcv_abi_version() != 2:
             raise DcvError("libdcvgan_b200.so ABI version mismatch")
         _lib = handle
     return _lib

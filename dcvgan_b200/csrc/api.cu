@@ -45,6 +45,7 @@ int wgrad_tc(const dcv_geom*, const void*, int64_t, const void*, int64_t, float*
 static int check_geom(const dcv_geom* g) {
   DCV_REQUIRE(g, "null geometry");
   DCV_REQUIRE(g->N >= 0 && g->Cl > 0 && g->Cs > 0, "bad geometry: N=%d Cl=%d Cs=%d", g->N, g->Cl, g->Cs);
+  DCV_REQUIRE(g->wCl >= 0 && g->wCl <= g->Cl && g->wCs >= 0 && g->wCs <= g->Cs, "bad weight channel counts wCl=%d wCs=%d", g->wCl, g->wCs);
   DCV_REQUIRE(g->kt > 0 && g->kh > 0 && g->kw > 0 && g->st > 0 && g->sh > 0 && g->sw > 0, "bad kernel/stride");
   DCV_REQUIRE(g->Tl > 0 && g->Hl > 0 && g->Wl > 0 && g->Ts > 0 && g->Hs > 0 && g->Ws > 0, "bad extents");
   // S extent must be what a convolution of L produces: floor((L + 2p - k)/s) + 1

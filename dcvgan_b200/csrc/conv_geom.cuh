@@ -11,7 +11,8 @@ struct ConvP {
   int kt, kh, kw;
   int st, sh, sw;
   int pt, ph, pw;
-  int Kc, Nc;         // reduction channels, produced channels
+  int Kc, Nc;         // reduction channels, produced channels (incl. zero padding)
+  int wK, wN;         // of which present in the master weight
   int scatter;
 };
 
@@ -66,9 +67,11 @@ static inline ConvP make_convp(const dcv_geom* g, int dir) {
   if (!p.scatter) {
     p.It = g->Tl; p.Ih = g->Hl; p.Iw = g->Wl; p.Ot = g->Ts; p.Oh = g->Hs; p.Ow = g->Ws;
     p.Kc = g->Cl; p.Nc = g->Cs;
+    p.wK = g->wCl > 0 ? g->wCl : g->Cl; p.wN = g->wCs > 0 ? g->wCs : g->Cs;
   } else {
     p.It = g->Ts; p.Ih = g->Hs; p.Iw = g->Ws; p.Ot = g->Tl; p.Oh = g->Hl; p.Ow = g->Wl;
     p.Kc = g->Cs; p.Nc = g->Cl;
+    p.wK = g->wCs > 0 ? g->wCs : g->Cs; p.wN = g->wCl > 0 ? g->wCl : g->Cl;
   }
   return p;
 }

@@ -2,6 +2,7 @@
 // Dropout2d scaling, Noise, softmax, layout conversion, temporal difference.
 // Everything is channels-last with an explicit pixel stride, fp32 math, fp32 or bf16 storage.
 #include "common.cuh"
+#include <initializer_list>
 
 namespace dcv {
 
@@ -56,13 +57,23 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ z, 
   });
 }
 
+// one warp per channel: lanes stride over the partial blocks, double accumulation, fixed shuffle tree
+__device__ __forceinline__ void warp_sum_partials(const float* __restrict__ partials, int nblk, int C, int c, double& s0, double& s1) {
+  const int lane = threadIdx.x % 32;
+  s0 = 0.0; s1 = 0.0;
+  for (int b = lane; b < nblk; b += 32) { s0 += partials[(int64_t)b * 2 * C + c]; s1 += partials[(int64_t)b * 2 * C + C + c]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+}
+
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblk, int C, double count, float eps,
                                    float momentum, float* running_mean, float* running_var,
                                    float* __restrict__ mean, float* __restrict__ invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
   if (c >= C) return;
-  double s0 = 0.0, s1 = 0.0;
-  for (int b = 0; b < nblk; ++b) { s0 += partials[(int64_t)b * 2 * C + c]; s1 += partials[(int64_t)b * 2 * C + C + c]; }
+  double s0, s1;
+  warp_sum_partials(partials, nblk, C, c, s0, s1);
+  if (threadIdx.x % 32 != 0) return;
   const double m = s0 / count;
   double var = s1 / count - m * m;
   if (var < 0.0) var = 0.0;
@@ -117,10 +128,11 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ da, int64_t ldda, const T* __rest
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int C, float* __restrict__ sums,
                                        float* dgamma, float* dbeta, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
   if (c >= C) return;
-  double s0 = 0.0, s1 = 0.0;
-  for (int b = 0; b < nblk; ++b) { s0 += partials[(int64_t)b * 2 * C + c]; s1 += partials[(int64_t)b * 2 * C + C + c]; }
+  double s0, s1;
+  warp_sum_partials(partials, nblk, C, c, s0, s1);
+  if (threadIdx.x % 32 != 0) return;
   sums[c] = (float)s0; sums[C + c] = (float)s1;
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s0 : (float)s0;
   if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)s1 : (float)s1;
@@ -309,6 +321,250 @@ frame_copy_kernel(T* __restrict__ clips, int64_t ldc, int N, int Tn, int64_t hw,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// 16-byte vectorised variants (8 bf16 / 4 fp32 channels per thread).  Thread -> (channel group cg, row lane);
+// a block walks its rows with the per-channel constants held in registers, so every global access is a
+// coalesced 16-byte load/store.  Used when C and every pixel stride are multiples of the vector width and all
+// pointers are 16-byte aligned; the scalar kernels above remain the general case.
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct VecIO<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+struct VecMap {           // thread -> (cg, lane) mapping shared by the vector kernels
+  int cg, lane, lanes; bool active;
+  int64_t rb, re;
+};
+template <int N>
+__device__ __forceinline__ VecMap vec_map(int64_t rows, int C) {
+  VecMap m;
+  const int CG = C / N;
+  m.lanes = 256 / CG;
+  m.cg = threadIdx.x % CG; m.lane = threadIdx.x / CG;
+  m.active = m.lane < m.lanes;
+  const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
+  m.rb = (int64_t)blockIdx.x * rpb;
+  m.re = m.rb + rpb; if (m.re > rows) m.re = rows;
+  return m;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_vec_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
+                  const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  const float* __restrict__ drop, int64_t rows_per_n, int act, float slope, T* __restrict__ a, int64_t lda) {
+  constexpr int N = VecIO<T>::N;
+  const VecMap m = vec_map<N>(rows, C);
+  if (!m.active) return;
+  const int c0 = m.cg * N;
+  float sc[N], sh[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    sc[j] = 1.f; sh[j] = 0.f;
+    if (mean) {
+      const float is = invstd[c0 + j];
+      const float g = gamma ? gamma[c0 + j] : 1.f;
+      sc[j] = is * g; sh[j] = (gamma ? beta[c0 + j] : 0.f) - mean[c0 + j] * is * g;
+    }
+  }
+  for (int64_t row = m.rb + m.lane; row < m.re; row += m.lanes) {
+    float v[N];
+    VecIO<T>::load(z + row * ldz + c0, v);
+    const float* dr = drop ? drop + (row / rows_per_n) * C + c0 : nullptr;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      float t = mean ? ((v[j] - mean[c0 + j]) * invstd[c0 + j]) : v[j];   // same operation order as the scalar kernel
+      if (mean && gamma) t = t * gamma[c0 + j] + beta[c0 + j];
+      if (dr) t *= dr[j];
+      v[j] = apply_act(t, act, slope);
+    }
+    VecIO<T>::store(a + row * lda + c0, v);
+  }
+  (void)sc; (void)sh;
+}
+
+// partials[b][0][c] = sum f0, partials[b][1][c] = sum f1 over the block's rows; F fills two N-vectors per row
+template <typename T, typename F>
+__device__ __forceinline__ void channel_reduce2_vec(int64_t rows, int C, float* __restrict__ partials, F f) {
+  constexpr int N = VecIO<T>::N;
+  __shared__ float red[2][256][N + 1];
+  const VecMap m = vec_map<N>(rows, C);
+  float a0[N], a1[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+  if (m.active) {
+    for (int64_t row = m.rb + m.lane; row < m.re; row += m.lanes) {
+      float v0[N], v1[N];
+      f(row, m.cg * N, v0, v1);
+#pragma unroll
+      for (int j = 0; j < N; ++j) { a0[j] += v0[j]; a1[j] += v1[j]; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) { red[0][threadIdx.x][j] = a0[j]; red[1][threadIdx.x][j] = a1[j]; }
+  __syncthreads();
+  const int CG = C / N;
+  if (m.active && m.lane == 0) {
+    float* out = partials + (int64_t)blockIdx.x * 2 * C;
+    for (int l = 1; l < m.lanes; ++l) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) { a0[j] += red[0][l * CG + m.cg][j]; a1[j] += red[1][l * CG + m.cg][j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) { out[m.cg * N + j] = a0[j]; out[C + m.cg * N + j] = a1[j]; }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_vec_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C,
+                                                            float* __restrict__ partials) {
+  constexpr int N = VecIO<T>::N;
+  channel_reduce2_vec<T>(rows, C, partials, [&](int64_t row, int c0, float (&v0)[N], float (&v1)[N]) {
+    VecIO<T>::load(z + row * ldz + c0, v0);
+#pragma unroll
+    for (int j = 0; j < N; ++j) v1[j] = v0[j] * v0[j];
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, int64_t lda,
+                             const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
+                             const float* __restrict__ invstd, const float* __restrict__ drop, int64_t rows_per_n,
+                             int act, float slope, float* __restrict__ partials) {
+  constexpr int N = VecIO<T>::N;
+  channel_reduce2_vec<T>(rows, C, partials, [&](int64_t row, int c0, float (&v0)[N], float (&v1)[N]) {
+    float g[N], o[N], zz[N];
+    VecIO<T>::load(da + row * ldda + c0, g);
+    VecIO<T>::load(a + row * lda + c0, o);
+    VecIO<T>::load(z + row * ldz + c0, zz);
+    const float* dr = drop ? drop + (row / rows_per_n) * C + c0 : nullptr;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      float du = g[j] * act_grad_from_out(o[j], act, slope);
+      if (dr) du *= dr[j];
+      v0[j] = du; v1[j] = du * ((zz[j] - mean[c0 + j]) * invstd[c0 + j]);
+    }
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, int64_t lda,
+                            const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
+                            const float* __restrict__ invstd, const float* __restrict__ gamma,
+                            const float* __restrict__ drop, int64_t rows_per_n, int act, float slope,
+                            const float* __restrict__ sums, float inv_count, T* __restrict__ dz, int64_t lddz) {
+  constexpr int N = VecIO<T>::N;
+  const VecMap m = vec_map<N>(rows, C);
+  if (!m.active) return;
+  const int c0 = m.cg * N;
+  float mu[N], is[N], gi[N], k0[N], k1[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j];
+    gi[j] = (gamma ? gamma[c0 + j] : 1.f) * is[j];
+    k0[j] = sums[c0 + j] * inv_count; k1[j] = sums[C + c0 + j] * inv_count;
+  }
+  for (int64_t row = m.rb + m.lane; row < m.re; row += m.lanes) {
+    float g[N], o[N], zz[N];
+    VecIO<T>::load(da + row * ldda + c0, g);
+    VecIO<T>::load(a + row * lda + c0, o);
+    VecIO<T>::load(z + row * ldz + c0, zz);
+    const float* dr = drop ? drop + (row / rows_per_n) * C + c0 : nullptr;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      float du = g[j] * act_grad_from_out(o[j], act, slope);
+      if (dr) du *= dr[j];
+      const float xhat = (zz[j] - mu[j]) * is[j];
+      g[j] = gi[j] * (du - k0[j] - xhat * k1[j]);
+    }
+    VecIO<T>::store(dz + row * lddz + c0, g);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_bwd_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, int64_t lda, int64_t rows, int C,
+                   int act, float slope, T* __restrict__ dz, int64_t lddz) {
+  constexpr int N = VecIO<T>::N;
+  const VecMap m = vec_map<N>(rows, C);
+  if (!m.active) return;
+  const int c0 = m.cg * N;
+  for (int64_t row = m.rb + m.lane; row < m.re; row += m.lanes) {
+    float g[N], o[N];
+    VecIO<T>::load(da + row * ldda + c0, g);
+    VecIO<T>::load(a + row * lda + c0, o);
+#pragma unroll
+    for (int j = 0; j < N; ++j) g[j] *= act_grad_from_out(o[j], act, slope);
+    VecIO<T>::store(dz + row * lddz + c0, g);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+axpy_vec_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __restrict__ out, int64_t ldo, int accumulate) {
+  constexpr int N = VecIO<T>::N;
+  const VecMap m = vec_map<N>(rows, C);
+  if (!m.active) return;
+  const int c0 = m.cg * N;
+  for (int64_t row = m.rb + m.lane; row < m.re; row += m.lanes) {
+    float v[N], o[N];
+    VecIO<T>::load(x + row * ldx + c0, v);
+    if (accumulate) {
+      VecIO<T>::load(out + row * ldo + c0, o);
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] += o[j];
+    }
+    VecIO<T>::store(out + row * ldo + c0, v);
+  }
+}
+
+static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+template <typename T>
+static inline bool vec_ok(int C, std::initializer_list<const void*> ptrs, std::initializer_list<int64_t> lds) {
+  constexpr int N = 16 / (int)sizeof(T);
+  if (C % N != 0 || C / N > 256) return false;
+  for (const void* p : ptrs) if (!al16(p)) return false;
+  for (int64_t l : lds) if (l % N != 0) return false;
+  return true;
+}
+static inline int vec_blocks(int64_t rows, int C, int N) {
+  const int lanes = 256 / (C / N);
+  int64_t b = (rows + (int64_t)lanes * 8 - 1) / ((int64_t)lanes * 8);   // ~8 rows per thread
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
 }  // namespace dcv
 
 using namespace dcv;
@@ -331,13 +587,16 @@ int dcv_bn_stats_blocks(int64_t rows, int C) {
 
 int dcv_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float* partials, void* stream) {
   const int nblk = dcv_bn_stats_blocks(rows, C);
-  DISPATCH_T(dtype, bn_stats_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials));
+  DISPATCH_T(dtype, {
+    if (vec_ok<T>(C, {z}, {ldz})) bn_stats_vec_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials);
+    else bn_stats_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials);
+  });
   return check_launch("bn_stats");
 }
 
 int dcv_bn_finalize(const float* partials, int nblk, int C, int64_t count, float eps, float momentum,
                     float* running_mean, float* running_var, float* mean, float* invstd, void* stream) {
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partials, nblk, C, (double)count, eps, momentum,
+  bn_finalize_kernel<<<ceil_div(C, 8), 256, 0, as_stream(stream)>>>(partials, nblk, C, (double)count, eps, momentum,
                                                                     running_mean, running_var, mean, invstd);
   return check_launch("bn_finalize");
 }
@@ -352,8 +611,14 @@ int dcv_bn_act(int dtype, const void* z, int64_t ldz, int64_t rows, int C, const
                const float* gamma, const float* beta, const float* drop, int64_t rows_per_n, int act, float slope,
                void* a, int64_t lda, void* stream) {
   if (rows * C == 0) return 0;
-  DISPATCH_T(dtype, bn_act_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
-                        (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope, (T*)a, lda));
+  DISPATCH_T(dtype, {
+    if (vec_ok<T>(C, {z, a}, {ldz, lda}))
+      bn_act_vec_kernel<T><<<vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream)>>>(
+          (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope, (T*)a, lda);
+    else
+      bn_act_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
+          (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope, (T*)a, lda);
+  });
   return check_launch("bn_act");
 }
 
@@ -361,15 +626,20 @@ int dcv_bn_act_bwd_reduce(int dtype, const void* da, int64_t ldda, const void* a
                           int64_t ldz, int64_t rows, int C, const float* mean, const float* invstd, const float* drop,
                           int64_t rows_per_n, int act, float slope, float* partials, void* stream) {
   const int nblk = dcv_bn_stats_blocks(rows, C);
-  DISPATCH_T(dtype, bn_act_bwd_reduce_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>(
-                        (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, drop, rows_per_n,
-                        act, slope, partials));
+  DISPATCH_T(dtype, {
+    if (vec_ok<T>(C, {da, a, z}, {ldda, lda, ldz}))
+      bn_act_bwd_reduce_vec_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>(
+          (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, drop, rows_per_n, act, slope, partials);
+    else
+      bn_act_bwd_reduce_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>(
+          (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, drop, rows_per_n, act, slope, partials);
+  });
   return check_launch("bn_act_bwd_reduce");
 }
 
 int dcv_bn_bwd_finalize(const float* partials, int nblk, int C, float* sums, float* dgamma, float* dbeta,
                         int accumulate, void* stream) {
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partials, nblk, C, sums, dgamma, dbeta, accumulate);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, as_stream(stream)>>>(partials, nblk, C, sums, dgamma, dbeta, accumulate);
   return check_launch("bn_bwd_finalize");
 }
 
@@ -378,17 +648,30 @@ int dcv_bn_act_bwd_apply(int dtype, const void* da, int64_t ldda, const void* a,
                          const float* drop, int64_t rows_per_n, int act, float slope, const float* sums, int64_t count,
                          void* dz, int64_t lddz, void* stream) {
   if (rows * C == 0) return 0;
-  DISPATCH_T(dtype, bn_act_bwd_apply_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
-                        (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, gamma, drop,
-                        rows_per_n, act, slope, sums, 1.0f / (float)count, (T*)dz, lddz));
+  DISPATCH_T(dtype, {
+    if (vec_ok<T>(C, {da, a, z, dz}, {ldda, lda, ldz, lddz}))
+      bn_act_bwd_apply_vec_kernel<T><<<vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream)>>>(
+          (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, gamma, drop, rows_per_n, act, slope,
+          sums, 1.0f / (float)count, (T*)dz, lddz);
+    else
+      bn_act_bwd_apply_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
+          (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, gamma, drop, rows_per_n, act, slope,
+          sums, 1.0f / (float)count, (T*)dz, lddz);
+  });
   return check_launch("bn_act_bwd_apply");
 }
 
 int dcv_act_bwd(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, int64_t rows, int C, int act,
                 float slope, void* dz, int64_t lddz, void* stream) {
   if (rows * C == 0) return 0;
-  DISPATCH_T(dtype, act_bwd_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
-                        (const T*)da, ldda, (const T*)a, lda, rows, C, act, slope, (T*)dz, lddz));
+  DISPATCH_T(dtype, {
+    if (vec_ok<T>(C, {da, a, dz}, {ldda, lda, lddz}))
+      act_bwd_vec_kernel<T><<<vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream)>>>(
+          (const T*)da, ldda, (const T*)a, lda, rows, C, act, slope, (T*)dz, lddz);
+    else
+      act_bwd_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>((const T*)da, ldda, (const T*)a, lda, rows, C, act,
+                                                                               slope, (T*)dz, lddz);
+  });
   return check_launch("act_bwd");
 }
 
@@ -403,8 +686,13 @@ int dcv_add_noise(int dtype, const void* x, int64_t ldx, const float* noise, flo
 int dcv_axpy(int dtype, const void* x, int64_t ldx, int64_t rows, int C, void* out, int64_t ldo, int accumulate,
              void* stream) {
   if (rows * C == 0) return 0;
-  DISPATCH_T(dtype, axpy_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>((const T*)x, ldx, rows, C,
-                                                                                          (T*)out, ldo, accumulate));
+  DISPATCH_T(dtype, {
+    if (vec_ok<T>(C, {x, out}, {ldx, ldo}))
+      axpy_vec_kernel<T><<<vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream)>>>((const T*)x, ldx, rows, C, (T*)out,
+                                                                                                  ldo, accumulate);
+    else
+      axpy_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>((const T*)x, ldx, rows, C, (T*)out, ldo, accumulate);
+  });
   return check_launch("axpy");
 }
 

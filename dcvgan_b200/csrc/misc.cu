@@ -122,13 +122,13 @@ __global__ void gru_bwd_kernel(const float* __restrict__ h0, const float* __rest
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-loss_kernel(const T* __restrict__ y, int64_t n, int kind, float* __restrict__ loss_out, int accumulate,
-            T* __restrict__ dy, float grad_scale) {
+loss_kernel(const T* __restrict__ y, int64_t ldy, int64_t n, int kind, float* __restrict__ loss_out, int accumulate,
+            T* __restrict__ dy, int64_t lddy, float grad_scale) {
   __shared__ float red[256];
   float acc = 0.f;
   const float inv_n = 1.f / (float)n;
   for (int64_t i = threadIdx.x; i < n; i += 256) {
-    const float v = ldf(y + i);
+    const float v = ldf(y + i * ldy);
     float l, g;
     switch (kind) {
       case DCV_LOSS_BCE_ONES:
@@ -138,7 +138,7 @@ loss_kernel(const T* __restrict__ y, int64_t n, int kind, float* __restrict__ lo
       default: l = fmaxf(1.f + v, 0.f); g = (1.f + v > 0.f) ? 1.f : 0.f; break;
     }
     acc += l;
-    if (dy) stf(dy + i, g * inv_n * grad_scale);
+    if (dy) stf(dy + i * lddy, g * inv_n * grad_scale);
   }
   red[threadIdx.x] = acc;
   __syncthreads();
@@ -240,15 +240,15 @@ int dcv_gru_traj_bwd(const float* h0, const float* eps, const float* hs, const f
   return check_launch("gru_bwd");
 }
 
-int dcv_loss_fwd_bwd(int dtype, const void* y, int64_t n, int kind, float* loss_out, int accumulate, void* dy,
-                     float grad_scale, void* stream) {
+int dcv_loss_fwd_bwd(int dtype, const void* y, int64_t ldy, int64_t n, int kind, float* loss_out, int accumulate, void* dy,
+                     int64_t lddy, float grad_scale, void* stream) {
   DCV_REQUIRE(n > 0, "loss: empty logits");
   DCV_REQUIRE(kind >= 0 && kind <= 4, "loss: unknown kind %d", kind);
   if (dtype == DCV_F32)
-    loss_kernel<float><<<1, 256, 0, as_stream(stream)>>>((const float*)y, n, kind, loss_out, accumulate, (float*)dy, grad_scale);
+    loss_kernel<float><<<1, 256, 0, as_stream(stream)>>>((const float*)y, ldy, n, kind, loss_out, accumulate, (float*)dy, lddy, grad_scale);
   else
-    loss_kernel<__nv_bfloat16><<<1, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)y, n, kind, loss_out, accumulate,
-                                                                 (__nv_bfloat16*)dy, grad_scale);
+    loss_kernel<__nv_bfloat16><<<1, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)y, ldy, n, kind, loss_out, accumulate,
+                                                                 (__nv_bfloat16*)dy, lddy, grad_scale);
   return check_launch("loss");
 }
 

@@ -222,27 +222,28 @@ wgrad_simt_kernel(WgradP p, const T* __restrict__ xl, int64_t ldl, const T* __re
 }
 
 // dw[cl*s_l + cs*s_s + tap*s_tap] (+)= sum_z partial[z][tap][cl][cs]   (fixed order => deterministic)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs,
-                                    float* __restrict__ dw, int64_t s_l, int64_t s_s, int64_t s_tap,
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, int wCl,
+                                    int wCs, float* __restrict__ dw, int64_t s_l, int64_t s_s, int64_t s_tap,
                                     int accumulate) {
   const int64_t total = (int64_t)taps * Cl * Cs;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
+    if (cl >= wCl || cs >= wCs) continue;   // zero-padding channels have no master weight
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * total + i];
-    const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
     float* d = dw + cl * s_l + cs * s_s + tap * s_tap;
     *d = accumulate ? (*d + s) : s;
   }
 }
 
 __global__ void pack_weight_simt_kernel(const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap,
-                                        int Cl, int Cs, int taps, int scatter, float* __restrict__ out) {
+                                        int Cl, int Cs, int wCl, int wCs, int taps, int scatter, float* __restrict__ out) {
   const int64_t total = (int64_t)taps * Cl * Cs;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int tap, cl, cs;
     if (!scatter) { cs = (int)(i % Cs); cl = (int)((i / Cs) % Cl); tap = (int)(i / ((int64_t)Cs * Cl)); }
     else          { cl = (int)(i % Cl); cs = (int)((i / Cl) % Cs); tap = (int)(i / ((int64_t)Cs * Cl)); }
-    out[i] = w[cl * s_l + cs * s_s + tap * s_tap];
+    out[i] = (cl < wCl && cs < wCs) ? w[cl * s_l + cs * s_s + tap * s_tap] : 0.f;
   }
 }
 
@@ -276,7 +277,8 @@ int wgrad_reduce(const float* partial, int splits, const dcv_geom* g, float* dw,
   const int taps = g->kt * g->kh * g->kw;
   const int64_t total = (int64_t)taps * g->Cl * g->Cs;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, dw, s_l, s_s, s_tap, accumulate);
+  wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, g->wCl > 0 ? g->wCl : g->Cl,
+                                             g->wCs > 0 ? g->wCs : g->Cs, dw, s_l, s_s, s_tap, accumulate);
   return check_launch("wgrad_reduce");
 }
 
@@ -285,6 +287,8 @@ int wgrad_simt_splits(const dcv_geom* g) {
   int tilesA, tilesB;
   if (g->Cl <= 8) { tilesA = ceil_div(g->Cl, 4); tilesB = ceil_div(g->Cs, 64); }
   else if (g->Cs <= 8) { tilesA = ceil_div(g->Cl, 64); tilesB = ceil_div(g->Cs, 4); }
+  else if (g->Cl <= 16) { tilesA = 1; tilesB = ceil_div(g->Cs, 64); }
+  else if (g->Cs <= 16) { tilesA = ceil_div(g->Cl, 64); tilesB = 1; }
   else { tilesA = ceil_div(g->Cl, 64); tilesB = ceil_div(g->Cs, 64); }
   const int64_t M = (int64_t)g->N * g->Ts * g->Hs * g->Ws;
   int64_t base = (int64_t)tilesA * tilesB * taps;
@@ -316,6 +320,14 @@ static int launch_wgrad_simt(const dcv_geom* g, const void* xl, int64_t ldl, con
     p.tilesB = ceil_div(g->Cs, 4);
     dim3 grid(ceil_div(g->Cl, 64) * p.tilesB, taps, splits);
     wgrad_simt_kernel<T, 64, 4, 1, 1><<<grid, 256, 0, s>>>(p, (const T*)xl, ldl, (const T*)xs, lds, partial);
+  } else if (g->Cl <= 16) {
+    p.tilesB = ceil_div(g->Cs, 64);
+    dim3 grid(p.tilesB, taps, splits);
+    wgrad_simt_kernel<T, 16, 64, 2, 2><<<grid, 256, 0, s>>>(p, (const T*)xl, ldl, (const T*)xs, lds, partial);
+  } else if (g->Cs <= 16) {
+    p.tilesB = 1;
+    dim3 grid(ceil_div(g->Cl, 64), taps, splits);
+    wgrad_simt_kernel<T, 64, 16, 2, 2><<<grid, 256, 0, s>>>(p, (const T*)xl, ldl, (const T*)xs, lds, partial);
   } else {
     p.tilesB = ceil_div(g->Cs, 64);
     dim3 grid(ceil_div(g->Cl, 64) * p.tilesB, taps, splits);
@@ -341,7 +353,8 @@ int pack_weight_simt(const dcv_geom* g, int dir, const float* w, int64_t s_l, in
   const int taps = g->kt * g->kh * g->kw;
   const int64_t total = (int64_t)taps * g->Cl * g->Cs;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weight_simt_kernel<<<blocks, 256, 0, s>>>(w, s_l, s_s, s_tap, g->Cl, g->Cs, taps, dir == DCV_DIR_SCATTER, out);
+  pack_weight_simt_kernel<<<blocks, 256, 0, s>>>(w, s_l, s_s, s_tap, g->Cl, g->Cs, g->wCl > 0 ? g->wCl : g->Cl,
+                                                 g->wCs > 0 ? g->wCs : g->Cs, taps, dir == DCV_DIR_SCATTER, out);
   return check_launch("pack_weight_simt");
 }
 

@@ -264,13 +264,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------ wgrad_tc
+// D[128 rows = (128/cbA) gathered L blocks of cbA channels, Ns columns = S channels] += A^T B over pixel blocks.
+// A block = (tap, channel chunk of cbA) of the gathered L tensor, B = S tile; both MN-major (channels contiguous),
+// swizzle chosen by the block width (64 ch -> 128B, 32 -> 64B, 16 -> 32B).  G accumulators of Ns columns share one
+// S tile per stage.
 struct TcWgradP {
   dcv_geom g;
   int pix;                               // pixels (GEMM K) per stage
   int bw, bh, bt, bn;
   int tiles_w, tiles_h, tiles_t, tiles_n;
   int64_t ptiles_total, ptiles_per_split;
-  int G, Ns, clchunks, pairs_total, stages, tmem_cols;
+  int cbA, nA, clchunks, blocksA_total;  // A: block width, blocks per 128-row tile, channel chunks per tap, taps*clchunks
+  int cbB, nbB, blocksB_total;           // B: block width, blocks per CTA tile, total blocks
+  int G, Ns, stages, tmem_cols;
+  int layA, layB;                        // UMMA layout codes
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -284,16 +291,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
 
   const dcv_geom& g = p.g;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int pair0 = blockIdx.x * p.G;
-  int Gcur = p.pairs_total - pair0; if (Gcur > p.G) Gcur = p.G;
-  const int cs0 = blockIdx.y * p.Ns;
+  const int tile0 = blockIdx.x * p.G;                       // first 128-row tile of this CTA
+  const int tiles_total = (p.blocksA_total + p.nA - 1) / p.nA;
+  int Gcur = tiles_total - tile0; if (Gcur > p.G) Gcur = p.G;
+  const int bB0 = blockIdx.y * p.nbB;                       // first S block of this CTA
+  int nbB = p.blocksB_total - bB0; if (nbB > p.nbB) nbB = p.nbB;
   const int64_t pt_begin = (int64_t)blockIdx.z * p.ptiles_per_split;
   int64_t pt_end = pt_begin + p.ptiles_per_split; if (pt_end > p.ptiles_total) pt_end = p.ptiles_total;
 
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int blk_bytes = p.pix * 128;                       // one 64-channel block of `pix` pixels
-  const int nsb = p.Ns / 64;                               // S blocks
-  const int stage_bytes = blk_bytes * (nsb + 2 * p.G);
+  const int blkA_bytes = p.pix * p.cbA * 2;
+  const int blkB_bytes = p.pix * p.cbB * 2;
+  const int stage_bytes = blkB_bytes * p.nbB + blkA_bytes * p.nA * p.G;
+  int blocksA_here = p.blocksA_total - tile0 * p.nA;        // valid A blocks of this CTA
+  if (blocksA_here > Gcur * p.nA) blocksA_here = Gcur * p.nA;
 
   if (warp == 0 && lane == 0) { tmap_prefetch(&mapL); tmap_prefetch(&mapS); }
   if (warp == 1) {
@@ -319,16 +330,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
         const int h0 = (int)(q % p.tiles_h) * p.bh; q /= p.tiles_h;
         const int t0 = (int)(q % p.tiles_t) * p.bt; const int n0 = (int)(q / p.tiles_t) * p.bn;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], (uint32_t)(blk_bytes * (nsb + 2 * Gcur)));
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(blkB_bytes * nbB + blkA_bytes * blocksA_here));
         const uint32_t s_dst = sbase + stage * stage_bytes;
-        for (int b = 0; b < nsb; ++b)
-          tma_load_5d(s_dst + b * blk_bytes, &mapS, &full_bar[stage], cs0 + 64 * b, w0, h0, t0, n0);
-        const uint32_t a_dst = s_dst + nsb * blk_bytes;
-        for (int b = 0; b < 2 * Gcur; ++b) {
-          const int blk = pair0 * 2 + b;
+        for (int b = 0; b < nbB; ++b)
+          tma_load_5d(s_dst + b * blkB_bytes, &mapS, &full_bar[stage], (bB0 + b) * p.cbB, w0, h0, t0, n0);
+        const uint32_t a_dst = s_dst + p.nbB * blkB_bytes;
+        for (int b = 0; b < blocksA_here; ++b) {
+          const int blk = tile0 * p.nA + b;
           const int tap = blk / p.clchunks, clc = blk % p.clchunks;
           const int tc = tap % g.kw, tb = (tap / g.kw) % g.kh, ta = tap / (g.kw * g.kh);
-          tma_load_5d(a_dst + b * blk_bytes, &mapL, &full_bar[stage], clc * 64, w0 * g.sw - g.pw + tc,
+          tma_load_5d(a_dst + b * blkA_bytes, &mapL, &full_bar[stage], clc * p.cbA, w0 * g.sw - g.pw + tc,
                       h0 * g.sh - g.ph + tb, t0 * g.st - g.pt + ta, n0);
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -338,17 +349,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, p.Ns, 1, 1);
+      const uint32_t kstepA = 16u * (uint32_t)p.cbA * 2u, kstepB = 16u * (uint32_t)p.cbB * 2u;   // bytes per 16 pixels
+      const uint32_t sboA = 8u * (uint32_t)p.cbA * 2u, sboB = 8u * (uint32_t)p.cbB * 2u;
       int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
       for (int64_t pt = pt_begin; pt < pt_end; ++pt) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t s_src = sbase + stage * stage_bytes;
-        const uint32_t a_src = s_src + nsb * blk_bytes;
+        const uint32_t a_src = s_src + p.nbB * blkB_bytes;
         for (int gi = 0; gi < Gcur; ++gi) {
           uint32_t acc = accum;
           for (int k = 0; k < p.pix / 16; ++k) {
-            const uint64_t ad = make_sdesc(a_src + (2 * gi) * blk_bytes + k * 2048, (uint32_t)blk_bytes, 1024, 2);
-            const uint64_t bd = make_sdesc(s_src + k * 2048, (uint32_t)blk_bytes, 1024, 2);
+            const uint64_t ad = make_sdesc(a_src + gi * p.nA * blkA_bytes + k * kstepA, (uint32_t)blkA_bytes, sboA, p.layA);
+            const uint64_t bd = make_sdesc(s_src + k * kstepB, (uint32_t)blkB_bytes, sboB, p.layB);
             umma_bf16(tmem_base + gi * p.Ns, ad, bd, idesc, acc);
             acc = 1;
           }
@@ -367,14 +380,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     const bool has_work = pt_end > pt_begin;
+    const int cs0 = bB0 * p.cbB;
+    const int ncols = nbB * p.cbB;                           // valid columns of this CTA
     for (int gi = 0; gi < Gcur; ++gi) {
-      const int blk = (pair0 + gi) * 2 + row / 64;
-      const int tap = blk / p.clchunks, clc = blk % p.clchunks;
-      const int cl = clc * 64 + row % 64;
+      const int blk = (tile0 + gi) * p.nA + row / p.cbA;
+      const bool row_ok = blk < p.blocksA_total;
+      const int tap = row_ok ? blk / p.clchunks : 0, clc = row_ok ? blk % p.clchunks : 0;
+      const int cl = clc * p.cbA + row % p.cbA;
       float* out = partial + (((int64_t)blockIdx.z * taps + tap) * g.Cl + cl) * g.Cs + cs0;
       for (int cb = 0; cb < p.Ns; cb += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(gi * p.Ns + cb), v);
+        if (!row_ok || cb >= ncols) continue;
         float4* dst = reinterpret_cast<float4*>(out + cb);
         if (has_work) {
           dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
@@ -407,7 +424,7 @@ __global__ void pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int6
       const int jw = j % f.nw, jh = (j / f.nw) % f.nh, jt = j / (f.nw * f.nh);
       const int tap = ((f.a0t + f.ast * jt) * c.kh + (f.a0h + f.ash * jh)) * c.kw + (f.a0w + f.asw * jw);
       float v = 0.f;
-      if (n < c.Nc) {
+      if (n < c.wN && k < c.wK) {
         // gather: reduction channel k is an L channel, produced channel n is an S channel; scatter: swapped
         const int cl = c.scatter ? n : k, cs = c.scatter ? k : n;
         v = w[cl * s_l + cs * s_s + tap * s_tap];
@@ -567,35 +584,43 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
 }
 
 // ---- wgrad
+static int block_width(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16); }
+static int layout_code(int cb) { return cb == 64 ? 2 : (cb == 32 ? 4 : 6); }
+static CUtensorMapSwizzle swizzle_of(int cb) {
+  return cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
 int wgrad_tc_supported(const dcv_geom* g) {
-  if (g->Cl % 64 || g->Cs % 64) return 0;
-  const int taps = g->kt * g->kh * g->kw;
-  if ((taps * (g->Cl / 64)) % 2) return 0;
+  if (g->Cl % 16 || g->Cs % 16) return 0;
   if (g->st > 8 || g->sh > 8 || g->sw > 8) return 0;
   return 1;
 }
 
 static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   p->g = *g;
-  p->Ns = g->Cs % 256 == 0 ? 256 : (g->Cs % 192 == 0 ? 192 : (g->Cs % 128 == 0 ? 128 : 64));
-  p->clchunks = g->Cl / 64;
   const int taps = g->kt * g->kh * g->kw;
-  p->pairs_total = taps * p->clchunks / 2;
-  p->G = 512 / pow2_ceil(p->Ns);
+  p->cbA = block_width(g->Cl); p->nA = 128 / p->cbA; p->clchunks = g->Cl / p->cbA;
+  p->blocksA_total = taps * p->clchunks;
+  p->cbB = block_width(g->Cs); p->blocksB_total = g->Cs / p->cbB;
+  p->nbB = 256 / p->cbB; if (p->nbB > p->blocksB_total) p->nbB = p->blocksB_total;
+  p->Ns = p->nbB * p->cbB;
+  p->layA = layout_code(p->cbA); p->layB = layout_code(p->cbB);
+  const int tiles_total = ceil_div(p->blocksA_total, p->nA);
+  p->G = 512 / pow2_ceil(p->Ns < 32 ? 32 : p->Ns);
   if (p->G > 4) p->G = 4;
-  if (p->G > p->pairs_total) p->G = p->pairs_total;
+  if (p->G > tiles_total) p->G = tiles_total;
   p->tmem_cols = pow2_ceil(p->G * p->Ns < 32 ? 32 : p->G * p->Ns);
   p->pix = 32;
   choose_box(p->pix, g->Ws, g->Hs, g->Ts, g->N, &p->bw, &p->bh, &p->bt, &p->bn);
   p->tiles_w = ceil_div(g->Ws, p->bw); p->tiles_h = ceil_div(g->Hs, p->bh); p->tiles_t = ceil_div(g->Ts, p->bt);
   p->tiles_n = ceil_div(g->N, p->bn);
   p->ptiles_total = (int64_t)p->tiles_w * p->tiles_h * p->tiles_t * p->tiles_n;
-  const int stage_bytes = p->pix * 128 * (p->Ns / 64 + 2 * p->G);
+  const int stage_bytes = p->pix * 2 * (p->Ns + 128 * p->G);
   int stages = (200 * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 1) stages = 1;
   p->stages = stages;
-  const int64_t tiles = (int64_t)ceil_div(p->pairs_total, p->G) * (g->Cs / p->Ns);
+  const int64_t tiles = (int64_t)ceil_div(tiles_total, p->G) * ceil_div(p->blocksB_total, p->nbB);
   int64_t sp = (148 * 2 + tiles - 1) / tiles;
   const int64_t maxs = (p->ptiles_total + 7) / 8;
   if (sp > maxs) sp = maxs;
@@ -621,19 +646,19 @@ int wgrad_tc(const dcv_geom* g, const void* xl, int64_t ldl, const void* xs, int
   wgrad_tc_plan(g, &p, &splits);
   DCV_REQUIRE(ws_bytes >= wgrad_tc_ws_bytes(g), "wgrad_tc workspace too small");
   CUtensorMap mapL, mapS;
-  int rc = make_act_map(&mapL, xl, g->Cl, g->Wl, g->Hl, g->Tl, g->N, ldl, 64, p.bw, p.bh, p.bt, p.bn, g->sw, g->sh, g->st,
-                        CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = make_act_map(&mapL, xl, g->Cl, g->Wl, g->Hl, g->Tl, g->N, ldl, p.cbA, p.bw, p.bh, p.bt, p.bn, g->sw, g->sh, g->st,
+                        swizzle_of(p.cbA));
   if (rc) return rc;
-  rc = make_act_map(&mapS, xs, g->Cs, g->Ws, g->Hs, g->Ts, g->N, lds, 64, p.bw, p.bh, p.bt, p.bn, 1, 1, 1,
-                    CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = make_act_map(&mapS, xs, g->Cs, g->Ws, g->Hs, g->Ts, g->N, lds, p.cbB, p.bw, p.bh, p.bt, p.bn, 1, 1, 1,
+                    swizzle_of(p.cbB));
   if (rc) return rc;
-  const int smem = p.stages * p.pix * 128 * (p.Ns / 64 + 2 * p.G) + 1024;
+  const int smem = p.stages * p.pix * 2 * (p.Ns + 128 * p.G) + 1024;
   static int smem_set = 0;
   if (smem > smem_set) {
     DCV_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_set = smem;
   }
-  dim3 grid(ceil_div(p.pairs_total, p.G), g->Cs / p.Ns, splits);
+  dim3 grid(ceil_div(ceil_div(p.blocksA_total, p.nA), p.G), ceil_div(p.blocksB_total, p.nbB), splits);
   wgrad_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mapL, mapS, p, (float*)ws);
   rc = check_launch("wgrad_tc");
   if (rc) return rc;

@@ -96,20 +96,22 @@ class Block:
     def forward(self, x, out, training, rng_, save=True):
         """x: input Act; out: Act (slice) that receives the block's output.  Returns ctx for backward."""
         spec = self.spec
-        g = spec.geom(x.n, x.spatial)
         w = self.conv.weight
         x_used = x
         if self.noise is not None and self.noise[0]:
             x_used = x.like()
             ops.add_noise(x, rng_.noise_for(x), float(self.noise[1]), x_used)
+        z = out if self.bn is None else Act.empty(out.n, out.t, out.h, out.w, out.c, out.dtype)
+        # geometry over the zero-padded channel counts of both buffers (dcv_geom.wCl/wCs carry the real ones)
+        cin_p, cout_p = x_used.cp, z.cp
+        g = spec.geom(x.n, x.spatial, cin_p, cout_p)
         impl = ops.choose_conv_impl(g, spec.fwd_dir, x_used)
         wp = ops.pack_weight(spec, g, spec.fwd_dir, impl, w)
-        ctx = {"g": g, "x": x_used if save else None, "a": out}
+        ctx = {"g": g, "x": x_used if save else None, "a": out, "cin_p": cin_p, "cout_p": cout_p}
         if self.bn is None:
-            ops.conv(g, spec.fwd_dir, impl, x_used, wp, out, self.act, self.slope)
+            ops.conv(g, spec.fwd_dir, impl, x_used.padded_to(cin_p), wp, out.padded_to(cout_p), self.act, self.slope)
             return ctx
-        z = Act.empty(out.n, out.t, out.h, out.w, out.c, out.dtype)
-        ops.conv(g, spec.fwd_dir, impl, x_used, wp, z)
+        ops.conv(g, spec.fwd_dir, impl, x_used.padded_to(cin_p), wp, z.padded_to(cout_p))
         bn = self.bn
         if training:
             mean, invstd = ops.bn_batch_stats(z, BN_EPS, BN_MOM, bn.running_mean, bn.running_var)
@@ -142,14 +144,18 @@ class Block:
             ops.act_bwd(da, a, self.act, self.slope, dz)
         else:
             dz = da
+        # dz / dx_out are viewed with the same zero-padded widths the forward geometry was built with
+        cin_p, cout_p = ctx["cin_p"], ctx["cout_p"]
+        dzp = dz.padded_to(cout_p)
         if need_dw:
             dw, acc = sink.get(self.conv.weight)
-            xl, xs = (ctx["x"], dz) if spec.kind == "conv" else (dz, ctx["x"])
+            xp = ctx["x"].padded_to(cin_p)
+            xl, xs = (xp, dzp) if spec.kind == "conv" else (dzp, xp)
             ops.wgrad(spec, g, xl, xs, dw, accumulate=acc)
         if dx_out is not None:
-            impl = ops.choose_conv_impl(g, spec.bwd_dir, dz)
+            impl = ops.choose_conv_impl(g, spec.bwd_dir, dzp)
             wp = ops.pack_weight(spec, g, spec.bwd_dir, impl, self.conv.weight)
-            ops.conv(g, spec.bwd_dir, impl, dz, wp, dx_out)
+            ops.conv(g, spec.bwd_dir, impl, dzp, wp, dx_out.padded_to(cin_p))
         return dz
 
 
@@ -196,10 +202,10 @@ class GGenPlan:
         eps = torch.stack([rng_.normal((B, dzm)) for _ in range(T)], 0).contiguous()
         P = [p.detach() for p in (rec.weight_ih, rec.weight_hh, rec.bias_ih, rec.bias_hh)]
         hs = ops.gru_traj_fwd(h0, eps, *P)                                       # (B, T, dzm)
-        z = torch.empty((B, T, dzc + dzm), dtype=dtype, device="cuda")
+        x = Act.empty(B * T, 1, 1, 1, dzc + dzm, dtype)
+        z = x.rows2d().view(B, T, dzc + dzm) if x.ld == dzc + dzm else x.base.as_strided((B, T, dzc + dzm), (T * x.ld, x.ld, 1))
         z[:, :, :dzc] = z_c[:, None, :]                                          # z_content repeated over T (:103-108)
         z[:, :, dzc:] = hs
-        x = Act(z.view(-1), 0, B * T, 1, 1, 1, dzc + dzm, dzc + dzm)
         ctxs = []
         sp = (1, 1, 1)
         for blk in self.blocks:
@@ -229,7 +235,7 @@ class GGenPlan:
             blk.backward(c, da, sink, dx_out=dx)
             da = dx
         B, T, dzc, dzm = ctx["B"], mod.video_length, mod.dim_z_content, mod.dim_z_motion
-        dhs = da.base.view(B, T, dzc + dzm)[:, :, dzc:].float().contiguous()
+        dhs = da.base.as_strided((B, T, dzc + dzm), (T * da.ld, da.ld, 1))[:, :, dzc:].float().contiguous()
         rec = mod.recurrent
         P = [p.detach() for p in (rec.weight_ih, rec.weight_hh, rec.bias_ih, rec.bias_hh)]
         grads = [sink.get(p) for p in (rec.weight_ih, rec.weight_hh, rec.bias_ih, rec.bias_hh)]
@@ -275,7 +281,7 @@ class CGenPlan:
             dctx.append(self.down[i].forward(src, dst, training, rng_, save))
             src = dst
         zc = cats[0].ch(first[0], cats[0].c)                                     # generator.py:393
-        zc.torch()[:, 0, 0, 0, :] = z.to(dtype)
+        zc.rows2d().copy_(z)
         uctx = []
         for i in range(6):
             dst = cats[i + 1].ch(0, first[i + 1])

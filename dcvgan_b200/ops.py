@@ -40,17 +40,35 @@ class Act:
     pixel 0.  `ch(c0, c1)` gives a channel slice that shares the parent's memory and stride.
     """
 
-    __slots__ = ("base", "off", "n", "t", "h", "w", "c", "ld")
+    __slots__ = ("base", "off", "n", "t", "h", "w", "c", "ld", "cp")
 
-    def __init__(self, base, off, n, t, h, w, c, ld):
+    def __init__(self, base, off, n, t, h, w, c, ld, cp=None):
         self.base, self.off, self.n, self.t, self.h, self.w, self.c, self.ld = base, off, n, t, h, w, c, ld
+        self.cp = c if cp is None else cp   # channels that may be read: c real ones + zero padding up to cp
 
     @staticmethod
     def empty(n, t, h, w, c, dtype, ld=None, zero=False):
-        ld = c if ld is None else ld
+        """Dense buffer.  A channel count that is not a multiple of 16 (image-like tensors: 1, 2, 3, 25, 50, 266
+        channels) gets zero-filled padding channels up to the next multiple of 16; nothing ever writes them, so the
+        tensor-core kernels can read the padded width (see dcv_geom.wCl / wCs)."""
+        cp = c
+        if ld is None:
+            ld = c
+            if c % 16 != 0 and dtype == torch.bfloat16:   # the fp32 (CUDA-core) path gains nothing from padding
+                ld = cp = (c + 15) // 16 * 16
+                zero = True
         numel = max(n * t * h * w * ld, 1)
         base = (torch.zeros if zero else torch.empty)(numel, dtype=dtype, device="cuda")
-        return Act(base, 0, n, t, h, w, c, ld)
+        return Act(base, 0, n, t, h, w, c, ld, cp)
+
+    def padded_to(self, k):
+        """view whose channel count is k: the c real channels plus k - c of the zero padding channels"""
+        assert self.c <= k <= self.cp, (self.c, k, self.cp)
+        return self if k == self.c else Act(self.base, self.off, self.n, self.t, self.h, self.w, k, self.ld, self.cp)
+
+    def rows2d(self):
+        """torch view (rows, c) over the real channels (strided by ld); plumbing only"""
+        return self.base.as_strided((self.rows, self.c), (self.ld, 1), self.off)
 
     @staticmethod
     def from_dense(x):
@@ -61,7 +79,7 @@ class Act:
 
     def ch(self, c0, c1):
         assert 0 <= c0 < c1 <= self.c
-        return Act(self.base, self.off + c0, self.n, self.t, self.h, self.w, c1 - c0, self.ld)
+        return Act(self.base, self.off + c0, self.n, self.t, self.h, self.w, c1 - c0, self.ld)   # slices see no padding
 
     @property
     def ptr(self):
@@ -90,7 +108,7 @@ class Act:
     def reshape_nt(self, n, t):
         """reinterpret (N*T, 1, H, W) frames as (N, T, H, W) clips or back (same memory)"""
         assert n * t == self.n * self.t
-        return Act(self.base, self.off, n, t, self.h, self.w, self.c, self.ld)
+        return Act(self.base, self.off, n, t, self.h, self.w, self.c, self.ld, self.cp)
 
     def torch(self):
         """strided torch view (N,T,H,W,C) of the same memory (tests / debugging)"""
@@ -125,13 +143,16 @@ class ConvSpec:
             return tuple((i + 2 * p - k) // s + 1 for i, k, s, p in zip(in_spatial, self.k, self.s, self.p))
         return tuple((i - 1) * s - 2 * p + k for i, k, s, p in zip(in_spatial, self.k, self.s, self.p))
 
-    def geom(self, n, in_spatial):
+    def geom(self, n, in_spatial, cin_p=None, cout_p=None):
+        """cin_p / cout_p: channel counts of the activations including zero padding (default: no padding)"""
         out = self.out_spatial(in_spatial)
+        cin_p = self.cin if cin_p is None else cin_p
+        cout_p = self.cout if cout_p is None else cout_p
         if self.kind == "conv":
-            l, s_, cl, cs = in_spatial, out, self.cin, self.cout
+            l, s_, cl, cs, wl, ws = in_spatial, out, cin_p, cout_p, self.cin, self.cout
         else:
-            l, s_, cl, cs = out, in_spatial, self.cout, self.cin
-        return Geom(n, l[0], l[1], l[2], cl, s_[0], s_[1], s_[2], cs, *self.k, *self.s, *self.p)
+            l, s_, cl, cs, wl, ws = out, in_spatial, cout_p, cin_p, self.cout, self.cin
+        return Geom(n, l[0], l[1], l[2], cl, s_[0], s_[1], s_[2], cs, *self.k, *self.s, *self.p, wl, ws)
 
     # element strides of the PyTorch master weight seen as w[cl, cs, tap]
     def weight_strides(self):
@@ -372,9 +393,17 @@ def gru_traj_bwd(h0, eps, hs, dhs, w_ih, w_hh, b_ih, b_hh, dw_ih, dw_hh, db_ih, 
 
 
 def loss_fwd_bwd(y, kind, loss_out, accumulate, dy=None, grad_scale=1.0):
+    """dense torch logits (module API)"""
     assert y.is_contiguous()
-    check(lib().dcv_loss_fwd_bwd(dcv_dtype(y), y.data_ptr(), y.numel(), kind, loss_out.data_ptr(), int(accumulate),
-                                 _p(dy), grad_scale, _stream()))
+    check(lib().dcv_loss_fwd_bwd(dcv_dtype(y), y.data_ptr(), 1, y.numel(), kind, loss_out.data_ptr(), int(accumulate),
+                                 _p(dy), 1, grad_scale, _stream()))
+
+
+def loss_fwd_bwd_act(y, kind, loss_out, accumulate, dy=None, grad_scale=1.0):
+    """single-channel logits Act (possibly with padding channels) - the fused trainer path"""
+    assert y.c == 1 and (dy is None or dy.c == 1)
+    check(lib().dcv_loss_fwd_bwd(dcv_dtype(y), y.ptr, y.ld, y.rows, kind, loss_out.data_ptr(), int(accumulate),
+                                 None if dy is None else dy.ptr, 1 if dy is None else dy.ld, grad_scale, _stream()))
 
 
 def adam_multi(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):

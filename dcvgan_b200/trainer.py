@@ -220,9 +220,7 @@ class Trainer(object):
         y = logits
         if want_grad:
             dy = Act.empty(y.n, y.t, y.h, y.w, y.c, y.dtype)
-        _lib.check(_lib.lib().dcv_loss_fwd_bwd(ops.dcv_dtype(y), y.ptr, y.rows * y.c, kind, losses[slot:slot + 1].data_ptr(),
-                                               int(accumulate), None if dy is None else dy.ptr, 1.0,
-                                               torch.cuda.current_stream().cuda_stream))
+        ops.loss_fwd_bwd_act(y, kind, losses[slot:slot + 1], accumulate, dy, 1.0)
         return dy
 
     def train_step(self, xc_real, xg_real, t_rand=None):

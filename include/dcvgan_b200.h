@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DCV_ABI_VERSION 1
+#define DCV_ABI_VERSION 2
 
 enum { DCV_F32 = 0, DCV_BF16 = 1 };
 /* activation selectors (generator.py:63,76,78,175,206,243,276; discriminator.py:82-99) */
@@ -62,6 +62,10 @@ typedef struct dcv_geom {
   int32_t kt, kh, kw;
   int32_t st, sh, sw;
   int32_t pt, ph, pw;
+  /* Channels present in the master weight (0 = same as Cl / Cs).  Cl / Cs may be larger: the activation then
+   * carries zero-filled padding channels (up to a multiple of 16) so that tiny channel counts (1, 2, 3, 25, 50,
+   * 266 ...) still run on the tensor cores.  Packing zero-fills the padding rows; wgrad never writes them. */
+  int32_t wCl, wCs;
 } dcv_geom;
 
 int dcv_abi_version(void);
@@ -185,9 +189,10 @@ int dcv_gru_traj_bwd(const float* h0, const float* eps, const float* hs, const f
                      int accumulate, void* stream);
 
 /* ---- losses (loss.py) ------------------------------------------------------------------------
- * loss_out[0] (+)= mean_i l(y_i); dy_i = grad_scale * dl/dy_i / n   (y dense, `dtype`) */
-int dcv_loss_fwd_bwd(int dtype, const void* y, int64_t n, int kind, float* loss_out, int accumulate,
-                     void* dy, float grad_scale, void* stream);
+ * loss_out[0] (+)= mean_i l(y_i); dy_i = grad_scale * dl/dy_i / n.  y / dy hold n logits of `dtype`, one every
+ * ldy / lddy elements (1 = dense; 16 for a single-channel activation with zero padding channels) */
+int dcv_loss_fwd_bwd(int dtype, const void* y, int64_t ldy, int64_t n, int kind, float* loss_out, int accumulate,
+                     void* dy, int64_t lddy, float grad_scale, void* stream);
 
 /* ---- Adam (train.py:167-176, trainer.py:320-322,357-359) ---------------------------------------
  * One launch over `ntensors` tensors.  ptrs are HOST arrays of device pointers; numel host array.

@@ -126,6 +126,63 @@ def test_conv_tcgen05(case):
     _run_case(_ops(), case, torch.bfloat16, True, 1e-2)
 
 
+PADDED_CASES = [
+    ("pad_conv3d_3_32", "conv", 3, 32, (4, 4, 4), (1, 2, 2), (0, 1, 1), 2, (7, 16, 16)),
+    ("pad_conv3d_1_32", "conv", 1, 32, (4, 4, 4), (1, 2, 2), (0, 1, 1), 3, (6, 16, 16)),
+    ("pad_conv2d_k3_25_64", "conv", 25, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, (1, 16, 16)),
+    ("pad_convT_64_2", "convT", 64, 2, (1, 4, 4), (1, 2, 2), (0, 1, 1), 3, (1, 16, 16)),
+    ("pad_convT_k3_128_3", "convT", 128, 3, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, (1, 16, 16)),
+    ("pad_convT_50_512_1x1", "convT", 50, 512, (1, 4, 4), (1, 1, 1), (0, 0, 0), 32, (1, 1, 1)),
+    ("pad_convT_266_256_1x1", "convT", 266, 256, (1, 4, 4), (1, 2, 2), (0, 1, 1), 32, (1, 1, 1)),
+    ("pad_conv3d_head_256_1", "conv", 256, 1, (4, 4, 4), (1, 2, 2), (0, 1, 1), 3, (7, 8, 8)),
+    ("pad_conv3d_32_64", "conv", 32, 64, (4, 4, 4), (1, 2, 2), (0, 1, 1), 2, (12, 32, 32)),
+    ("pad_conv2d_96_192", "conv", 96, 192, (1, 4, 4), (1, 2, 2), (0, 1, 1), 4, (1, 16, 16)),
+]
+
+
+@pytest.mark.parametrize("case", PADDED_CASES, ids=[c[0] for c in PADDED_CASES])
+def test_conv_tcgen05_padded_channels(case):
+    """Tiny / odd channel counts run on the tensor cores through zero-padded activation channels
+    (dcv_geom.wCl / wCs): forward, data gradient and weight gradient, all three via tcgen05."""
+    ops = _ops()
+    from dcvgan_b200._lib import IMPL_TC
+    name, kind, cin, cout, k, s, p, n, sp = case
+    torch.manual_seed(sum(map(ord, name)) % 1000)
+    three_d = k[0] > 1
+    spec = ops.ConvSpec(kind, cin, cout, k, s, p)
+    x = bf16_round(torch.randn(n, cin, *sp)).requires_grad_(True)
+    w = bf16_round(torch.randn((cout, cin, *k) if kind == "conv" else (cin, cout, *k)) * 0.1).requires_grad_(True)
+    y_ref = _torch_fwd(kind, x, w, s, p, three_d)
+    dy = bf16_round(torch.randn_like(y_ref))
+    y_ref.backward(dy)
+    xa = to_act(x.detach(), torch.bfloat16)              # Act.empty pads the channel count to a multiple of 16
+    out_sp = spec.out_spatial(sp)
+    ya = ops.Act.empty(n, *out_sp, cout, torch.bfloat16)
+    g = spec.geom(n, sp, xa.cp, ya.cp)
+    assert g.Cl % 16 == 0 and g.Cs % 16 == 0
+    assert ops.lib().dcv_conv_tc_supported(C.byref(g), spec.fwd_dir) and ops.lib().dcv_conv_tc_supported(C.byref(g), spec.bwd_dir)
+    assert ops.lib().dcv_wgrad_tc_supported(C.byref(g))
+    wdev = (w.detach().squeeze(2) if (kind == "convT" or not three_d) else w.detach()).contiguous().cuda()
+    wp = ops.pack_weight(spec, g, spec.fwd_dir, IMPL_TC, wdev)
+    ops.conv(g, spec.fwd_dir, IMPL_TC, xa.padded_to(xa.cp), wp, ya.padded_to(ya.cp))
+    e_fwd = rel_err(from_act(ya), y_ref.detach())
+    pad = ya.padded_to(ya.cp).torch()[..., ya.c:]
+    assert pad.numel() == 0 or float(pad.float().abs().max()) == 0.0      # padding channels stay zero
+    dya = to_act(dy, torch.bfloat16)
+    dxa = ops.Act.empty(n, *sp, cin, torch.bfloat16)
+    wpb = ops.pack_weight(spec, g, spec.bwd_dir, IMPL_TC, wdev)
+    ops.conv(g, spec.bwd_dir, IMPL_TC, dya.padded_to(dya.cp), wpb, dxa.padded_to(dxa.cp))
+    e_dx = rel_err(from_act(dxa), x.grad)
+    dw = torch.full_like(wdev, 7.0)
+    xl, xs = (xa, dya) if kind == "conv" else (dya, xa)
+    ops.wgrad(spec, g, xl.padded_to(xl.cp), xs.padded_to(xs.cp), dw, accumulate=False, impl=IMPL_TC)
+    torch.cuda.synchronize()
+    wg = w.grad.squeeze(2) if (kind == "convT" or not three_d) else w.grad
+    e_dw = rel_err(dw.cpu(), wg)
+    print(f"{name}: fwd {e_fwd:.2e} dx {e_dx:.2e} dw {e_dw:.2e}  geom Cl={g.Cl} Cs={g.Cs} wCl={g.wCl} wCs={g.wCs}")
+    assert e_fwd < 1e-2 and e_dx < 1e-2 and e_dw < 1e-2
+
+
 def test_conv_channel_slices():
     """input read from / output written into channel slices of wider buffers (concat elimination)"""
     ops = _ops()
