@@ -107,6 +107,7 @@ constexpr int MAX_STAGES = 8;
 struct TcConvP {
   ConvP c;
   int bw, bh, bt, bn;                    // box of 128 output index positions
+  int mt;                                // 128-row M tiles per CTA, stacked along the batch dimension (one TMA box)
   int tiles_w, tiles_h, tiles_t, tiles_n;
   int cblk, kchunks, bnt, stages;
   int swz_layout;                        // UMMA layout code (2 = SW128, 4 = SW64, 6 = SW32)
@@ -133,7 +134,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int tw = tile % p.tiles_w; tile /= p.tiles_w;
   const int th = tile % p.tiles_h; tile /= p.tiles_h;
   const int tt = tile % p.tiles_t; const int tn = tile / p.tiles_t;
-  const int w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt, n0 = tn * p.bn;
+  const int w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt, n0 = tn * p.bn * p.mt;
   if (w0 >= f.Qw || h0 >= f.Qh || t0 >= f.Qt) return;  // tile outside this phase (uniform per CTA)
 
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -186,6 +187,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
       const uint32_t sbo = 8u * (uint32_t)p.cblk * 2u;
+      const uint32_t a_tile_bytes = 128u * (uint32_t)p.cblk * 2u;
       int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0; uint32_t accum = 0;
       for (int jt = 0; jt < f.nt; ++jt) {
         const int ct = t0 * f.mult + f.offt + f.sgn * jt;
@@ -203,9 +205,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               const uint32_t a_src = sbase + stage * stage_bytes;
               const uint32_t b_src = a_src + p.a_bytes;
               for (int k = 0; k < p.cblk / 16; ++k) {
-                const uint64_t ad = make_sdesc(a_src + k * 32, 16, sbo, p.swz_layout);
                 const uint64_t bd = make_sdesc(b_src + k * 32, 16, sbo, p.swz_layout);
-                umma_bf16(tmem_base, ad, bd, idesc, accum);
+                for (int m = 0; m < p.mt; ++m) {
+                  const uint64_t ad = make_sdesc(a_src + m * a_tile_bytes + k * 32, 16, sbo, p.swz_layout);
+                  umma_bf16(tmem_base + m * p.bnt, ad, bd, idesc, accum);
+                }
                 accum = 1;
               }
               umma_commit(&empty_bar[stage]);
@@ -226,35 +230,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int dw = r % p.bw; r /= p.bw;
     const int dh = r % p.bh; r /= p.bh;
     const int dt = r % p.bt; const int dn = r / p.bt;
-    const int qw = w0 + dw, qh = h0 + dh, qt = t0 + dt, n = n0 + dn;
-    const bool valid = qw < f.Qw && qh < f.Qh && qt < f.Qt && n < p.c.N;
-    const int64_t pos = (((int64_t)n * p.c.Ot + (qt * f.ost + f.rt)) * p.c.Oh + (qh * f.osh + f.rh)) * p.c.Ow + (qw * f.osw + f.rw);
-    __nv_bfloat16* yrow = y + pos * p.ldy;
+    const int qw = w0 + dw, qh = h0 + dh, qt = t0 + dt;
     const int nbase = blockIdx.y * p.bnt;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
-    for (int cb = 0; cb < p.bnt; cb += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb, v);
-      if (!valid) continue;
-      const int c0 = nbase + cb;
-      if (c0 >= p.c.Nc) continue;
-      if (p.vec_ok && c0 + 16 <= p.c.Nc) {
-        uint32_t pk[8];
+    for (int m = 0; m < p.mt; ++m) {
+      const int n = n0 + m * p.bn + dn;
+      const bool valid = qw < f.Qw && qh < f.Qh && qt < f.Qt && n < p.c.N;
+      const int64_t pos = (((int64_t)n * p.c.Ot + (qt * f.ost + f.rt)) * p.c.Oh + (qh * f.osh + f.rh)) * p.c.Ow + (qw * f.osw + f.rw);
+      __nv_bfloat16* yrow = y + pos * p.ldy;
+      for (int cb = 0; cb < p.bnt; cb += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * p.bnt + cb), v);
+        if (!valid) continue;
+        const int c0 = nbase + cb;
+        if (c0 >= p.c.Nc) continue;
+        if (p.vec_ok && c0 + 16 <= p.c.Nc) {
+          uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a = apply_act(__uint_as_float(v[2 * i]), p.act, p.slope);
-          const float b = apply_act(__uint_as_float(v[2 * i + 1]), p.act, p.slope);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-          pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+          for (int i = 0; i < 8; ++i) {
+            const float a = apply_act(__uint_as_float(v[2 * i]), p.act, p.slope);
+            const float b = apply_act(__uint_as_float(v[2 * i + 1]), p.act, p.slope);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < p.c.Nc) yrow[c0 + i] = __float2bfloat16_rn(apply_act(__uint_as_float(v[i]), p.act, p.slope));
         }
-        uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
-        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c0 + i < p.c.Nc) yrow[c0 + i] = __float2bfloat16_rn(apply_act(__uint_as_float(v[i]), p.act, p.slope));
       }
     }
   }
@@ -322,28 +329,35 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int64_t pt = pt_begin; pt < pt_end; ++pt) {
-        int64_t q = pt;
-        const int w0 = (int)(q % p.tiles_w) * p.bw; q /= p.tiles_w;
-        const int h0 = (int)(q % p.tiles_h) * p.bh; q /= p.tiles_h;
-        const int t0 = (int)(q % p.tiles_t) * p.bt; const int n0 = (int)(q / p.tiles_t) * p.bn;
+    // TMA producer.  A stage is many small boxes (one per (tap, channel chunk) block); the 32 lanes issue them
+    // in parallel after lane 0 has armed the barrier, otherwise the per-instruction TMA latency serialises.
+    int stage = 0; uint32_t phase = 0;
+    const int nloads = nbB + blocksA_here;
+    for (int64_t pt = pt_begin; pt < pt_end; ++pt) {
+      int64_t q = pt;
+      const int w0 = (int)(q % p.tiles_w) * p.bw; q /= p.tiles_w;
+      const int h0 = (int)(q % p.tiles_h) * p.bh; q /= p.tiles_h;
+      const int t0 = (int)(q % p.tiles_t) * p.bt; const int n0 = (int)(q / p.tiles_t) * p.bn;
+      if (lane == 0) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         mbar_expect_tx(&full_bar[stage], (uint32_t)(blkB_bytes * nbB + blkA_bytes * blocksA_here));
-        const uint32_t s_dst = sbase + stage * stage_bytes;
-        for (int b = 0; b < nbB; ++b)
-          tma_load_5d(s_dst + b * blkB_bytes, &mapS, &full_bar[stage], (bB0 + b) * p.cbB, w0, h0, t0, n0);
-        const uint32_t a_dst = s_dst + p.nbB * blkB_bytes;
-        for (int b = 0; b < blocksA_here; ++b) {
+      }
+      __syncwarp();
+      const uint32_t s_dst = sbase + stage * stage_bytes;
+      const uint32_t a_dst = s_dst + p.nbB * blkB_bytes;
+      for (int i = lane; i < nloads; i += 32) {
+        if (i < nbB) {
+          tma_load_5d(s_dst + i * blkB_bytes, &mapS, &full_bar[stage], (bB0 + i) * p.cbB, w0, h0, t0, n0);
+        } else {
+          const int b = i - nbB;
           const int blk = tile0 * p.nA + b;
           const int tap = blk / p.clchunks, clc = blk % p.clchunks;
           const int tc = tap % g.kw, tb = (tap / g.kw) % g.kh, ta = tap / (g.kw * g.kh);
           tma_load_5d(a_dst + b * blkA_bytes, &mapL, &full_bar[stage], clc * p.cbA, w0 * g.sw - g.pw + tc,
                       h0 * g.sh - g.ph + tb, t0 * g.st - g.pt + ta, n0);
         }
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -551,24 +565,38 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   p.swz_layout = p.cblk == 64 ? 2 : (p.cblk == 32 ? 4 : 6);
   const CUtensorMapSwizzle swz = p.cblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                               : (p.cblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  p.a_bytes = 128 * p.cblk * 2;
+  // two M tiles per CTA (stacked along the batch dimension, so they share the tap-skip pattern, one TMA box and
+  // every weight tile) when the batch allows it and enough CTAs remain to fill the machine
+  p.mt = 1;
+  {
+    const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * (npad / p.bnt) * phases;
+    if (p.bnt <= 256 && p.bn * 2 <= 256 && c.N >= 2 * p.bn && ctas >= 2 * 148 * 2) p.mt = 2;
+  }
+  p.tiles_n = ceil_div(c.N, p.bn * p.mt);
+  p.a_bytes = p.mt * 128 * p.cblk * 2;
   p.b_bytes = (p.bnt * p.cblk * 2 + 1023) / 1024 * 1024;
   p.tx_bytes = p.a_bytes + p.bnt * p.cblk * 2;
-  int stages = (200 * 1024) / (p.a_bytes + p.b_bytes);
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int ntaps0 = f0.nt * f0.nh * f0.nw;
-  if (stages > ntaps0 * p.kchunks) stages = ntaps0 * p.kchunks;
+  p.tmem_cols = pow2_ceil(p.mt * p.bnt < 32 ? 32 : p.mt * p.bnt);
+  // Several CTAs per SM hide each other's prologue / epilogue (tiles with few K iterations are otherwise dominated
+  // by TMEM allocation, barrier setup and the store epilogue): split the ~216 KB of shared memory between as many
+  // CTAs as TMEM (512 columns) allows, up to 4, keeping at least 2 stages each.
+  int ctas_per_sm = 512 / p.tmem_cols; if (ctas_per_sm > 4) ctas_per_sm = 4; if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int k_iters = ntaps0 * p.kchunks;
+  int stages = ((216 * 1024) / ctas_per_sm - 2048) / (p.a_bytes + p.b_bytes);
+  while (stages < 2 && ctas_per_sm > 1) { --ctas_per_sm; stages = ((216 * 1024) / ctas_per_sm - 2048) / (p.a_bytes + p.b_bytes); }
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > k_iters) stages = k_iters;
   if (stages < 1) stages = 1;
   p.stages = stages;
   p.ldy = ldy; p.act = act; p.slope = slope;
   p.vec_ok = (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0);
-  p.tmem_cols = pow2_ceil(p.bnt < 32 ? 32 : p.bnt);
 
   CUtensorMap mapA, mapB;
-  int rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn, f0.mulw, f0.mulh,
+  int rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn * p.mt, f0.mulw, f0.mulh,
                         f0.mult, swz);
   if (rc) return rc;
-  const int64_t Kph = (int64_t)ntaps0 * c.Kc;
+  const int64_t Kph = (int64_t)ntaps0 * c.Kc;  // K extent of one phase
   rc = make_weight_map(&mapB, wp, Kph, npad, phases, p.cblk, p.bnt, swz);
   if (rc) return rc;
 
@@ -610,7 +638,9 @@ static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   if (p->G > 4) p->G = 4;
   if (p->G > tiles_total) p->G = tiles_total;
   p->tmem_cols = pow2_ceil(p->G * p->Ns < 32 ? 32 : p->G * p->Ns);
+  // pixels per stage: as many as keep >= 4 stages in ~200 KB (fewer, larger TMA boxes per byte moved)
   p->pix = 32;
+  while (p->pix < 128 && (200 * 1024) / (2 * p->pix * 2 * (p->Ns + 128 * p->G)) >= 4) p->pix *= 2;
   choose_box(p->pix, g->Ws, g->Hs, g->Ts, g->N, &p->bw, &p->bh, &p->bt, &p->bn);
   p->tiles_w = ceil_div(g->Ws, p->bw); p->tiles_h = ceil_div(g->Hs, p->bh); p->tiles_t = ceil_div(g->Ts, p->bt);
   p->tiles_n = ceil_div(g->N, p->bn);
@@ -624,7 +654,7 @@ static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   int64_t sp = (148 * 2 + tiles - 1) / tiles;
   const int64_t maxs = (p->ptiles_total + 7) / 8;
   if (sp > maxs) sp = maxs;
-  if (sp > 64) sp = 64;
+  if (sp > 296) sp = 296;
   if (sp < 1) sp = 1;
   p->ptiles_per_split = (p->ptiles_total + sp - 1) / sp;
   *splits = (int)((p->ptiles_total + p->ptiles_per_split - 1) / p->ptiles_per_split);

@@ -88,6 +88,36 @@ class _FlatNet:
             self.opt.state[p]["step"] = torch.tensor(float(self.step_count))
 
 
+def dp_world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def dp_sync_params(flat_nets):
+    """Identical replicas at start: rank 0's flat parameter buffers win."""
+    if dp_world() > 1:
+        for f in flat_nets:
+            dist.broadcast(f.flat_p, 0)
+
+
+def dp_allreduce_grads(flat_nets):
+    """One sum all-reduce per network over its flat gradient buffer (NCCL over NVLink on the GPU box; gloo in the
+    CPU tests).  The 1/world average is folded into the Adam kernel's grad_scale.  Returns that scale."""
+    world = dp_world()
+    if world > 1:
+        for f in flat_nets:
+            dist.all_reduce(f.flat_g, op=dist.ReduceOp.SUM)
+    return 1.0 / world
+
+
+def dp_seed(seed):
+    """Replica r draws its latents / Noise / Dropout from seed + r (each replica is a valid reference step on its
+    own shard); returns the seed used."""
+    r = dist.get_rank() if dp_world() > 1 else 0
+    torch.manual_seed(seed + r)
+    np.random.seed(seed + r)
+    return seed + r
+
+
 class Trainer(object):
     def __init__(self, dataloader, logger, models: Dict[str, nn.Module], optimizers: Dict[str, Any], loss,
                  configs: Dict[str, Any]):
@@ -174,13 +204,15 @@ class Trainer(object):
         for n in names[2:]:
             self._plans[n] = engine.DisPlan(self.models[n], n)
         self._dnames = names[2:]
-        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.world = dp_world()
         self.dtype = ops.torch_dtype(self.models["ggen"].precision)
+        if self.world > 1:
+            dp_sync_params(self._flat.values())
+            if "seed" in self.configs:
+                dp_seed(self.configs["seed"])
 
     def _allreduce(self, names):
-        if self.world > 1:
-            for n in names:
-                dist.all_reduce(self._flat[n].flat_g)
+        dp_allreduce_grads([self._flat[n] for n in names])
 
     def _to_clip(self, x):
         """(B,C,T,H,W) fp32 torch tensor -> channels-last Act (B,T,H,W,C)"""
