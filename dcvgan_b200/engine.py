@@ -81,6 +81,30 @@ class GradSink:
         return g, False
 
 
+# ------------------------------------------------------------------------------------------ packed-weight cache
+# The fused trainer re-uses packed (bf16, K-major) weights between the passes that see the same master weights
+# (D: real + fake in the D-phase; G: forward + backward).  WCACHE maps id(param) -> {(geom, dir, impl): packed}; the
+# trainer drops a network's entries right after its Adam step.  None (module / autograd API) = always re-pack.
+WCACHE = None
+
+
+def packed_weight(spec, g, direction, impl, weight):
+    if WCACHE is None:
+        return ops.pack_weight(spec, g, direction, impl, weight)
+    per = WCACHE.setdefault(id(weight), {})
+    key = (g.key(), direction, impl)
+    wp = per.get(key)
+    if wp is None:
+        wp = per[key] = ops.pack_weight(spec, g, direction, impl, weight)
+    return wp
+
+
+def invalidate_packed(params):
+    if WCACHE is not None:
+        for p in params:
+            WCACHE.pop(id(p), None)
+
+
 # ------------------------------------------------------------------------------------------ one layer group
 class Block:
     """[Noise] -> conv -> [BatchNorm] -> [Dropout2d] -> activation, with its backward.
@@ -106,7 +130,7 @@ class Block:
         cin_p, cout_p = x_used.cp, z.cp
         g = spec.geom(x.n, x.spatial, cin_p, cout_p)
         impl = ops.choose_conv_impl(g, spec.fwd_dir, x_used)
-        wp = ops.pack_weight(spec, g, spec.fwd_dir, impl, w)
+        wp = packed_weight(spec, g, spec.fwd_dir, impl, w)
         ctx = {"g": g, "x": x_used if save else None, "a": out, "cin_p": cin_p, "cout_p": cout_p}
         if self.bn is None:
             ops.conv(g, spec.fwd_dir, impl, x_used.padded_to(cin_p), wp, out.padded_to(cout_p), self.act, self.slope)
@@ -154,7 +178,7 @@ class Block:
             ops.wgrad(spec, g, xl, xs, dw, accumulate=acc)
         if dx_out is not None:
             impl = ops.choose_conv_impl(g, spec.bwd_dir, dzp)
-            wp = ops.pack_weight(spec, g, spec.bwd_dir, impl, self.conv.weight)
+            wp = packed_weight(spec, g, spec.bwd_dir, impl, self.conv.weight)
             ops.conv(g, spec.bwd_dir, impl, dzp, wp, dx_out.padded_to(cin_p))
         return dz
 

@@ -195,7 +195,12 @@ def pack_weight(spec, g, direction, impl, weight):
     return out
 
 
+TRACE = None   # set to a list to record every conv / wgrad call (tools/layer_bench.py)
+
+
 def conv(g, direction, impl, x, wp, y, act=ACT_NONE, slope=0.0):
+    if TRACE is not None:
+        TRACE.append(("conv", g.key(), direction, impl, x.ld, y.ld, x.c, y.c))
     xp, ldx, _, _ = cl_view(x)
     yp, ldy, _, _ = cl_view(y)
     assert x.dtype == y.dtype
@@ -210,6 +215,8 @@ def choose_wgrad_impl(g, xl, xs):
 
 def wgrad(spec, g, xl, xs, dw, accumulate=False, impl=None):
     impl = choose_wgrad_impl(g, xl, xs) if impl is None else impl
+    if TRACE is not None:
+        TRACE.append(("wgrad", g.key(), 0, impl, xl.ld, xs.ld, xl.c, xs.c))
     nbytes = lib().dcv_wgrad_workspace_bytes(C.byref(g), impl)
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=xl.device)
     lp, ldl, _, _ = cl_view(xl)

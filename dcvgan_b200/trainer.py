@@ -84,6 +84,7 @@ class _FlatNet:
                                             self.flat_v.data_ptr(), self.flat_p.numel(), g["lr"], b1, b2, g["eps"],
                                             g["weight_decay"], self.step_count, grad_scale,
                                             torch.cuda.current_stream().cuda_stream))
+        engine.invalidate_packed(self.params)
         for p in self.params:
             self.opt.state[p]["step"] = torch.tensor(float(self.step_count))
 
@@ -259,6 +260,8 @@ class Trainer(object):
         """One iteration of trainer.py:279-363.  xc_real (B,3,T,64,64), xg_real (B,C,T,64,64) on the device.
         Returns a device tensor [loss_idis, loss_vdis, loss_gdis, loss_gen]."""
         self._prepare()
+        if engine.WCACHE is None:
+            engine.WCACHE = {}
         cfg = self.configs
         B = cfg["batchsize"]
         ggen, cgen = self.models["ggen"], self.models["cgen"]
