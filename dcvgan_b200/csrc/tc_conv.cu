@@ -107,45 +107,62 @@ constexpr int MAX_STAGES = 8;
 struct TcConvP {
   ConvP c;
   int bw, bh, bt, bn;                    // box of 128 output index positions
-  int mt;                                // 128-row M tiles per CTA, stacked along the batch dimension (one TMA box)
+  int mt;                                // 128-row M tiles per work item, stacked along the batch dimension (one TMA box)
   int tiles_w, tiles_h, tiles_t, tiles_n;
+  int ntn, phases;                       // N tiles, sub-pixel phases
   int cblk, kchunks, bnt, stages;
   int swz_layout;                        // UMMA layout code (2 = SW128, 4 = SW64, 6 = SW32)
   int a_bytes, b_bytes, tx_bytes;
   int64_t ldy;
   int act; float slope;
   int vec_ok;
-  int tmem_cols;
+  int acc_cols, tmem_cols;               // TMEM columns of one accumulator set (mt*bnt) and of the allocation (2 sets)
 };
 
+struct TileCoord {
+  int ph, ntile, w0, h0, t0, n0;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// work item -> (phase, N tile, spatial/batch tile); spatial index fastest so that concurrently running CTAs share
+// the weight tile and neighbouring activations in L2
+__device__ __forceinline__ TileCoord decode_tile(const TcConvP& p, int item) {
+  TileCoord t;
+  int r = item;
+  const int tw = r % p.tiles_w; r /= p.tiles_w;
+  const int th = r % p.tiles_h; r /= p.tiles_h;
+  const int tt = r % p.tiles_t; r /= p.tiles_t;
+  const int tn = r % p.tiles_n; r /= p.tiles_n;
+  t.ntile = r % p.ntn; t.ph = r / p.ntn;
+  t.w0 = tw * p.bw; t.h0 = th * p.bh; t.t0 = tt * p.bt; t.n0 = tn * p.bn * p.mt;
+  return t;
+}
+
+// Persistent kernel: one CTA per SM walks the work items; the shared-memory ring runs continuously across items
+// and TMEM holds two accumulator sets, so the epilogue of item i overlaps the main loop of item i+1.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcConvP p,
                __nv_bfloat16* __restrict__ y) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[MAX_STAGES];
   __shared__ uint64_t empty_bar[MAX_STAGES];
-  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint64_t tfull_bar[2];
+  __shared__ uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const PhaseInfo f = make_phase(p.c, blockIdx.z);
-
-  int tile = blockIdx.x;
-  const int tw = tile % p.tiles_w; tile /= p.tiles_w;
-  const int th = tile % p.tiles_h; tile /= p.tiles_h;
-  const int tt = tile % p.tiles_t; const int tn = tile / p.tiles_t;
-  const int w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt, n0 = tn * p.bn * p.mt;
-  if (w0 >= f.Qw || h0 >= f.Qh || t0 >= f.Qt) return;  // tile outside this phase (uniform per CTA)
-
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  const int ntaps = f.nt * f.nh * f.nw;
+  const int items = p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * p.ntn * p.phases;
 
   if (warp == 0 && lane == 0) { tmap_prefetch(&mapA); tmap_prefetch(&mapB); }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      mbar_init(&tmem_full_bar, 1);
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -158,26 +175,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0;
-      for (int jt = 0; jt < f.nt; ++jt) {
-        const int ct = t0 * f.mult + f.offt + f.sgn * jt;
-        const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
-        for (int jh = 0; jh < f.nh; ++jh) {
-          const int ch = h0 * f.mulh + f.offh + f.sgn * jh;
-          const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
-          for (int jw = 0; jw < f.nw; ++jw, ++j) {
-            const int cw = w0 * f.mulw + f.offw + f.sgn * jw;
-            const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
-            if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-              mbar_wait(&empty_bar[stage], phase ^ 1u);
-              mbar_expect_tx(&full_bar[stage], (uint32_t)p.tx_bytes);
-              const uint32_t a_dst = sbase + stage * stage_bytes;
-              tma_load_5d(a_dst, &mapA, &full_bar[stage], kc * p.cblk, cw, ch, ct, n0);
-              tma_load_3d(a_dst + p.a_bytes, &mapB, &full_bar[stage], j * p.c.Kc + kc * p.cblk, blockIdx.y * p.bnt, blockIdx.z);
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const TileCoord tc = decode_tile(p, item);
+        const PhaseInfo f = make_phase(p.c, tc.ph);
+        if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;        // tile outside this phase
+        const int ntaps = f.nt * f.nh * f.nw;
+        int executed = 0, j = 0;
+        for (int jt = 0; jt < f.nt; ++jt) {
+          const int ct = tc.t0 * f.mult + f.offt + f.sgn * jt;
+          const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
+          for (int jh = 0; jh < f.nh; ++jh) {
+            const int ch = tc.h0 * f.mulh + f.offh + f.sgn * jh;
+            const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
+            for (int jw = 0; jw < f.nw; ++jw, ++j) {
+              const int cw = tc.w0 * f.mulw + f.offw + f.sgn * jw;
+              const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
+              if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;   // tap entirely in the padding
+              for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                mbar_expect_tx(&full_bar[stage], (uint32_t)p.tx_bytes);
+                const uint32_t a_dst = sbase + stage * stage_bytes;
+                tma_load_5d(a_dst, &mapA, &full_bar[stage], kc * p.cblk, cw, ch, ct, tc.n0);
+                tma_load_3d(a_dst + p.a_bytes, &mapB, &full_bar[stage], j * p.c.Kc + kc * p.cblk, tc.ntile * p.bnt, tc.ph);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+              }
+              ++executed;
             }
-            ++executed;
           }
         }
       }
@@ -188,38 +212,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
       const uint32_t sbo = 8u * (uint32_t)p.cblk * 2u;
       const uint32_t a_tile_bytes = 128u * (uint32_t)p.cblk * 2u;
-      int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0; uint32_t accum = 0;
-      for (int jt = 0; jt < f.nt; ++jt) {
-        const int ct = t0 * f.mult + f.offt + f.sgn * jt;
-        const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
-        for (int jh = 0; jh < f.nh; ++jh) {
-          const int ch = h0 * f.mulh + f.offh + f.sgn * jh;
-          const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
-          for (int jw = 0; jw < f.nw; ++jw, ++j) {
-            const int cw = w0 * f.mulw + f.offw + f.sgn * jw;
-            const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
-            if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-              mbar_wait(&full_bar[stage], phase);
-              tc_fence_after();
-              const uint32_t a_src = sbase + stage * stage_bytes;
-              const uint32_t b_src = a_src + p.a_bytes;
-              for (int k = 0; k < p.cblk / 16; ++k) {
-                const uint64_t bd = make_sdesc(b_src + k * 32, 16, sbo, p.swz_layout);
-                for (int m = 0; m < p.mt; ++m) {
-                  const uint64_t ad = make_sdesc(a_src + m * a_tile_bytes + k * 32, 16, sbo, p.swz_layout);
-                  umma_bf16(tmem_base + m * p.bnt, ad, bd, idesc, accum);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t tempty_phase[2] = {0u, 0u};
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const TileCoord tc = decode_tile(p, item);
+        const PhaseInfo f = make_phase(p.c, tc.ph);
+        if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;
+        const int ntaps = f.nt * f.nh * f.nw;
+        mbar_wait(&tempty_bar[acc], tempty_phase[acc] ^ 1u);                   // epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(acc * p.acc_cols);
+        int executed = 0, j = 0; uint32_t accum = 0;
+        for (int jt = 0; jt < f.nt; ++jt) {
+          const int ct = tc.t0 * f.mult + f.offt + f.sgn * jt;
+          const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
+          for (int jh = 0; jh < f.nh; ++jh) {
+            const int ch = tc.h0 * f.mulh + f.offh + f.sgn * jh;
+            const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
+            for (int jw = 0; jw < f.nw; ++jw, ++j) {
+              const int cw = tc.w0 * f.mulw + f.offw + f.sgn * jw;
+              const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
+              if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
+              for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t a_src = sbase + stage * stage_bytes;
+                const uint32_t b_src = a_src + p.a_bytes;
+                for (int k = 0; k < p.cblk / 16; ++k) {
+                  const uint64_t bd = make_sdesc(b_src + k * 32, 16, sbo, p.swz_layout);
+                  for (int m = 0; m < p.mt; ++m) {
+                    const uint64_t ad = make_sdesc(a_src + m * a_tile_bytes + k * 32, 16, sbo, p.swz_layout);
+                    umma_bf16(d_base + m * p.bnt, ad, bd, idesc, accum);
+                  }
+                  accum = 1;
                 }
-                accum = 1;
+                umma_commit(&empty_bar[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
               }
-              umma_commit(&empty_bar[stage]);
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+              ++executed;
             }
-            ++executed;
           }
         }
+        umma_commit(&tfull_bar[acc]);
+        tempty_phase[acc] ^= 1u;
+        acc ^= 1;
       }
-      umma_commit(&tmem_full_bar);
     }
     __syncwarp();
   } else {
@@ -230,39 +267,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int dw = r % p.bw; r /= p.bw;
     const int dh = r % p.bh; r /= p.bh;
     const int dt = r % p.bt; const int dn = r / p.bt;
-    const int qw = w0 + dw, qh = h0 + dh, qt = t0 + dt;
-    const int nbase = blockIdx.y * p.bnt;
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-    for (int m = 0; m < p.mt; ++m) {
-      const int n = n0 + m * p.bn + dn;
-      const bool valid = qw < f.Qw && qh < f.Qh && qt < f.Qt && n < p.c.N;
-      const int64_t pos = (((int64_t)n * p.c.Ot + (qt * f.ost + f.rt)) * p.c.Oh + (qh * f.osh + f.rh)) * p.c.Ow + (qw * f.osw + f.rw);
-      __nv_bfloat16* yrow = y + pos * p.ldy;
-      for (int cb = 0; cb < p.bnt; cb += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * p.bnt + cb), v);
-        if (!valid) continue;
-        const int c0 = nbase + cb;
-        if (c0 >= p.c.Nc) continue;
-        if (p.vec_ok && c0 + 16 <= p.c.Nc) {
-          uint32_t pk[8];
+    int acc = 0; uint32_t tfull_phase[2] = {0u, 0u};
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const TileCoord tc = decode_tile(p, item);
+      const PhaseInfo f = make_phase(p.c, tc.ph);
+      if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;
+      const int qw = tc.w0 + dw, qh = tc.h0 + dh, qt = tc.t0 + dt;
+      const int nbase = tc.ntile * p.bnt;
+      mbar_wait(&tfull_bar[acc], tfull_phase[acc]);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+      for (int m = 0; m < p.mt; ++m) {
+        const int n = tc.n0 + m * p.bn + dn;
+        const bool valid = qw < f.Qw && qh < f.Qh && qt < f.Qt && n < p.c.N;
+        const int64_t pos = (((int64_t)n * p.c.Ot + (qt * f.ost + f.rt)) * p.c.Oh + (qh * f.osh + f.rh)) * p.c.Ow + (qw * f.osw + f.rw);
+        __nv_bfloat16* yrow = y + pos * p.ldy;
+        for (int cb = 0; cb < p.bnt; cb += 16) {
+          uint32_t v[16];
+          tmem_ld16(d_base + (uint32_t)(m * p.bnt + cb), v);
+          if (!valid) continue;
+          const int c0 = nbase + cb;
+          if (c0 >= p.c.Nc) continue;
+          if (p.vec_ok && c0 + 16 <= p.c.Nc) {
+            uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a = apply_act(__uint_as_float(v[2 * i]), p.act, p.slope);
-            const float b = apply_act(__uint_as_float(v[2 * i + 1]), p.act, p.slope);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int i = 0; i < 8; ++i) {
+              const float a = apply_act(__uint_as_float(v[2 * i]), p.act, p.slope);
+              const float b = apply_act(__uint_as_float(v[2 * i + 1]), p.act, p.slope);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < p.c.Nc) yrow[c0 + i] = __float2bfloat16_rn(apply_act(__uint_as_float(v[i]), p.act, p.slope));
           }
-          uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < p.c.Nc) yrow[c0 + i] = __float2bfloat16_rn(apply_act(__uint_as_float(v[i]), p.act, p.slope));
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);                            // this warp is done reading the set
+      tfull_phase[acc] ^= 1u;
+      acc ^= 1;
     }
   }
   tc_fence_before();
@@ -565,28 +614,24 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   p.swz_layout = p.cblk == 64 ? 2 : (p.cblk == 32 ? 4 : 6);
   const CUtensorMapSwizzle swz = p.cblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                               : (p.cblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  // two M tiles per CTA (stacked along the batch dimension, so they share the tap-skip pattern, one TMA box and
-  // every weight tile) when the batch allows it and enough CTAs remain to fill the machine
+  p.phases = phases;
+  p.ntn = npad / p.bnt;
+  // two M tiles per work item (stacked along the batch dimension, so they share the tap-skip pattern, one TMA box
+  // and every weight tile) when the batch allows it, both accumulator sets fit in TMEM and enough items remain
   p.mt = 1;
   {
-    const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * (npad / p.bnt) * phases;
-    if (p.bnt <= 256 && p.bn * 2 <= 256 && c.N >= 2 * p.bn && ctas >= 2 * 148 * 2) p.mt = 2;
+    const int64_t items1 = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * p.ntn * phases;
+    if (p.bnt <= 128 && p.bn * 2 <= 256 && c.N >= 2 * p.bn && items1 >= 2 * 148) p.mt = 2;
   }
   p.tiles_n = ceil_div(c.N, p.bn * p.mt);
   p.a_bytes = p.mt * 128 * p.cblk * 2;
   p.b_bytes = (p.bnt * p.cblk * 2 + 1023) / 1024 * 1024;
   p.tx_bytes = p.a_bytes + p.bnt * p.cblk * 2;
   const int ntaps0 = f0.nt * f0.nh * f0.nw;
-  p.tmem_cols = pow2_ceil(p.mt * p.bnt < 32 ? 32 : p.mt * p.bnt);
-  // Several CTAs per SM hide each other's prologue / epilogue (tiles with few K iterations are otherwise dominated
-  // by TMEM allocation, barrier setup and the store epilogue): split the ~216 KB of shared memory between as many
-  // CTAs as TMEM (512 columns) allows, up to 4, keeping at least 2 stages each.
-  int ctas_per_sm = 512 / p.tmem_cols; if (ctas_per_sm > 4) ctas_per_sm = 4; if (ctas_per_sm < 1) ctas_per_sm = 1;
-  const int k_iters = ntaps0 * p.kchunks;
-  int stages = ((216 * 1024) / ctas_per_sm - 2048) / (p.a_bytes + p.b_bytes);
-  while (stages < 2 && ctas_per_sm > 1) { --ctas_per_sm; stages = ((216 * 1024) / ctas_per_sm - 2048) / (p.a_bytes + p.b_bytes); }
+  p.acc_cols = p.mt * p.bnt;
+  p.tmem_cols = pow2_ceil(2 * p.acc_cols < 32 ? 32 : 2 * p.acc_cols);
+  int stages = (214 * 1024) / (p.a_bytes + p.b_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > k_iters) stages = k_iters;
   if (stages < 1) stages = 1;
   p.stages = stages;
   p.ldy = ldy; p.act = act; p.slope = slope;
@@ -606,7 +651,14 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     DCV_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_set = smem;
   }
-  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n, npad / p.bnt, phases);
+  const int64_t items = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * p.ntn * phases;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    DCV_CUDA(cudaGetDevice(&dev));
+    DCV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = (int)(items < num_sms ? items : num_sms);
   conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mapA, mapB, p, (__nv_bfloat16*)y);
   return check_launch("conv_tc");
 }
