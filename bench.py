@@ -270,12 +270,16 @@ def run_cuda(args, cfg_name):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = []
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
+        host_ms.append((time.perf_counter() - t0) * 1e3 / steps)   # time the host needs to issue one step
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -316,7 +320,7 @@ def run_cuda(args, cfg_name):
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"config/{cfg_name}.yml (normalised) training step, batch 32 per GPU, 16x64x64, D and G both update every iteration",
                        "l2": f"{nbuf} rotating input batches; per-step activation traffic >> 126 MB L2",
-                       "parallelism": f"dp{world}", "useful_tflop_per_step": flops / 1e12,
+                       "parallelism": f"dp{world}", "useful_tflop_per_step": flops / 1e12, "host_issue_ms_per_step": host_ms[0],
                        "step_tflops": flops / ms / 1e9, "step_frac_of_sustained_peak": flops / ms / 1e9 / sustained},
             "e2e": {"value": world * 1e3 / ms_e2e, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
             "gpu_launches": int(launches),

@@ -222,17 +222,33 @@ wgrad_simt_kernel(WgradP p, const T* __restrict__ xl, int64_t ldl, const T* __re
 }
 
 // dw[cl*s_l + cs*s_s + tap*s_tap] (+)= sum_z partial[z][tap][cl][cs]   (fixed order => deterministic)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, int wCl,
-                                    int wCs, float* __restrict__ dw, int64_t s_l, int64_t s_s, int64_t s_tap,
-                                    int accumulate) {
+// Block = 32 consecutive elements x 8 split lanes: lane y sums splits y, y+8, ... (coalesced 128-byte rows), the
+// eight partial sums are then added in a fixed order.  Keeps small weights with hundreds of splits parallel.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, int wCl,
+                    int wCs, float* __restrict__ dw, int64_t s_l, int64_t s_s, int64_t s_tap,
+                    int accumulate) {
+  __shared__ float red[8][33];
   const int64_t total = (int64_t)taps * Cl * Cs;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
-    if (cl >= wCl || cs >= wCs) continue;   // zero-padding channels have no master weight
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+    const int64_t i = base + tx;
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * total + i];
-    float* d = dw + cl * s_l + cs * s_s + tap * s_tap;
-    *d = accumulate ? (*d + s) : s;
+    if (i < total)
+      for (int z = ty; z < splits; z += 8) s += partial[(int64_t)z * total + i];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < total) {
+      float t = red[0][tx];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) t += red[k][tx];
+      const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
+      if (cl < wCl && cs < wCs) {   // zero-padding channels have no master weight
+        float* d = dw + cl * s_l + cs * s_s + tap * s_tap;
+        *d = accumulate ? (*d + t) : t;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -276,7 +292,7 @@ int wgrad_reduce(const float* partial, int splits, const dcv_geom* g, float* dw,
                  int64_t s_tap, int accumulate, cudaStream_t s) {
   const int taps = g->kt * g->kh * g->kw;
   const int64_t total = (int64_t)taps * g->Cl * g->Cs;
-  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  int blocks = (int)((total + 31) / 32); if (blocks > 148 * 16) blocks = 148 * 16;
   wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, g->wCl > 0 ? g->wCl : g->Cl,
                                              g->wCs > 0 ? g->wCs : g->Cs, dw, s_l, s_s, s_tap, accumulate);
   return check_launch("wgrad_reduce");
