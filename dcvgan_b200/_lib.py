@@ -65,12 +65,13 @@ SIGNATURES = {
     "dcv_to_channels_last": (_i, [_i, _vp, _i64, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
     "dcv_from_channels_last": (_i, [_i, _vp, _i64, _i, _i, _i, _i, _i, _vp, _i64, _i64, _i64, _i64, _i64, _i, _vp]),
     "dcv_copy_cl": (_i, [_i, _vp, _i64, _i, _vp, _i64, _i64, _i, _vp]),
-    "dcv_frame_copy": (_i, [_i, _vp, _i64, _i, _i, _i64, _i, _i, _vp, _i64, _i, _i, _vp]),
+    "dcv_frame_copy": (_i, [_i, _vp, _i64, _i, _i, _i64, _i, _i, _vp, _vp, _i64, _i, _i, _vp]),
     "dcv_gru_traj_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "dcv_gru_traj_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "dcv_loss_fwd_bwd": (_i, [_i, _vp, _i64, _i64, _i, _vp, _i, _vp, _i64, _f, _vp]),
     "dcv_adam_multi": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64),
                             _f, _f, _f, _f, _f, _i64, _f, _vp]),
+    "dcv_adam_flat_dev": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _vp, _f, _vp]),
     "dcv_adam_flat": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i64, _f, _vp]),
 }
 

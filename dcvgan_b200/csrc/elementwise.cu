@@ -308,8 +308,9 @@ copy_cl_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst, in
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-frame_copy_kernel(T* __restrict__ clips, int64_t ldc, int N, int Tn, int64_t hw, int C, int t, T* __restrict__ frames,
-                  int64_t ldfr, int reverse, int accumulate) {
+frame_copy_kernel(T* __restrict__ clips, int64_t ldc, int N, int Tn, int64_t hw, int C, int t, const int* __restrict__ t_dev,
+                  T* __restrict__ frames, int64_t ldfr, int reverse, int accumulate) {
+  if (t_dev) t = min(max(*t_dev, 0), Tn - 1);   // frame index kept on the device (CUDA-graph replay)
   const int64_t total = (int64_t)N * hw * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C); int64_t r = i / C;
@@ -752,13 +753,13 @@ int dcv_from_channels_last(int dtype, const void* src, int64_t ld, int N, int C,
   return check_launch("from_channels_last");
 }
 
-int dcv_frame_copy(int dtype, void* clips, int64_t ldc, int N, int T_, int64_t hw, int C, int t, void* frames, int64_t ldf,
-                   int reverse, int accumulate, void* stream) {
+int dcv_frame_copy(int dtype, void* clips, int64_t ldc, int N, int T_, int64_t hw, int C, int t, const int* t_dev, void* frames,
+                   int64_t ldf, int reverse, int accumulate, void* stream) {
   const int64_t total = (int64_t)N * hw * C;
   if (total == 0) return 0;
-  DCV_REQUIRE(t >= 0 && t < T_, "frame_copy: frame %d out of range [0,%d)", t, T_);
+  DCV_REQUIRE(t_dev || (t >= 0 && t < T_), "frame_copy: frame %d out of range [0,%d)", t, T_);
   DISPATCH_T(dtype, frame_copy_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(
-                        (T*)clips, ldc, N, T_, hw, C, t, (T*)frames, ldf, reverse, accumulate));
+                        (T*)clips, ldc, N, T_, hw, C, t, t_dev, (T*)frames, ldf, reverse, accumulate));
   return check_launch("frame_copy");
 }
 

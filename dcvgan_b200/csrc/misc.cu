@@ -176,8 +176,20 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
   p = p - step_size * (m / denom);
 }
 
+// Device-side step bookkeeping (CUDA-graph friendly): state = {int64 step; float step_size; float inv_bc2_sqrt}.
+__global__ void adam_advance_kernel(long long* state, float lr, float b1, float b2) {
+  const long long step = ++state[0];
+  const double bc1 = 1.0 - pow((double)b1, (double)step);
+  const double bc2 = 1.0 - pow((double)b2, (double)step);
+  float* f = reinterpret_cast<float*>(state + 1);
+  f[0] = (float)((double)lr / bc1);
+  f[1] = (float)(1.0 / sqrt(bc2));
+}
+
 __global__ void __launch_bounds__(256)
-adam_multi_kernel(AdamArgs a, float b1, float b2, float eps, float wd, float step_size, float inv_bc2_sqrt, float gscale) {
+adam_multi_kernel(AdamArgs a, float b1, float b2, float eps, float wd, float step_size, float inv_bc2_sqrt, float gscale,
+                  const float* __restrict__ dev_scalars) {
+  if (dev_scalars) { step_size = dev_scalars[0]; inv_bc2_sqrt = dev_scalars[1]; }
   int t = 0;
   while (t + 1 < a.ntensors && (int)blockIdx.x >= a.block_start[t + 1]) ++t;
   const int64_t off = (int64_t)(blockIdx.x - a.block_start[t]) * ADAM_CHUNK;
@@ -276,11 +288,29 @@ int dcv_adam_multi(int ntensors, float* const* p, const float* const* g, float* 
     if (k == 0) break;
     a.block_start[k] = blocks;
     a.ntensors = k;
-    adam_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, grad_scale);
+    adam_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, grad_scale, nullptr);
     int rc = check_launch("adam_multi");
     if (rc) return rc;
   }
   return 0;
+}
+
+int dcv_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, void* step_state, float grad_scale, void* stream) {
+  DCV_REQUIRE(step_state && (((uintptr_t)step_state) & 7) == 0, "adam: step_state must be an 8-byte aligned 16-byte device buffer");
+  if (n <= 0) return 0;
+  adam_advance_kernel<<<1, 1, 0, as_stream(stream)>>>((long long*)step_state, lr, beta1, beta2);
+  int rc = check_launch("adam_advance");
+  if (rc) return rc;
+  AdamArgs a;
+  a.p[0] = p; a.g[0] = g; a.m[0] = m; a.v[0] = v; a.numel[0] = n;
+  a.block_start[0] = 0;
+  const int blocks = (int)((n + ADAM_CHUNK - 1) / ADAM_CHUNK);
+  a.block_start[1] = blocks;
+  a.ntensors = 1;
+  adam_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, beta1, beta2, eps, weight_decay, 0.f, 0.f, grad_scale,
+                                                           reinterpret_cast<const float*>((long long*)step_state + 1));
+  return check_launch("adam_flat_dev");
 }
 
 int dcv_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

@@ -358,18 +358,28 @@ def from_channels_last(src, dst, accumulate=False):
                                        int(accumulate), _stream()))
 
 
+def _frame_index(t):
+    """host int, or a device int32 tensor (CUDA-graph replay keeps the index on the device)"""
+    if isinstance(t, torch.Tensor):
+        assert t.dtype == torch.int32 and t.is_cuda
+        return 0, t.data_ptr()
+    return int(t), None
+
+
 def frame_extract(src, t, dst):
     """dst (N,1,H,W,C) = frame t of src (N,T,H,W,C)   (the x[:, :, t] slice at trainer.py:299,307,347)"""
     sp, lds, _, c = cl_view(src)
     dp, ldd, _, _ = cl_view(dst)
-    check(lib().dcv_frame_copy(dcv_dtype(src), sp, lds, src.n, src.t, src.h * src.w, c, t, dp, ldd, 0, 0, _stream()))
+    ti, tp = _frame_index(t)
+    check(lib().dcv_frame_copy(dcv_dtype(src), sp, lds, src.n, src.t, src.h * src.w, c, ti, tp, dp, ldd, 0, 0, _stream()))
 
 
 def frame_scatter(dsrc, t, dframe, accumulate=True):
     """adjoint of frame_extract: dsrc[:, t] (+)= dframe"""
     sp, lds, _, c = cl_view(dsrc)
     dp, ldd, _, _ = cl_view(dframe)
-    check(lib().dcv_frame_copy(dcv_dtype(dsrc), sp, lds, dsrc.n, dsrc.t, dsrc.h * dsrc.w, c, t, dp, ldd, 1,
+    ti, tp = _frame_index(t)
+    check(lib().dcv_frame_copy(dcv_dtype(dsrc), sp, lds, dsrc.n, dsrc.t, dsrc.h * dsrc.w, c, ti, tp, dp, ldd, 1,
                                int(accumulate), _stream()))
 
 

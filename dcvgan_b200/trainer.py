@@ -16,6 +16,7 @@ one fused schedule over the libdcvgan_b200 kernels instead of PyTorch autograd:
     four host syncs per iteration (trainer.py:326-328,363).
 """
 import copy
+import os
 import shutil
 from pathlib import Path
 from typing import Any, Dict
@@ -73,20 +74,27 @@ class _FlatNet:
             st["exp_avg_sq"] = self.flat_v[o:o + k].view(p.shape)
             if "step" not in st:
                 st["step"] = torch.tensor(0.0)
-        self.step_count = int(float(opt.state[self.params[0]]["step"]))
+        # {int64 step; float lr/bias_correction1; float 1/sqrt(bias_correction2)} on the parameters' device: the step
+        # counter never passes through the host, so the fused step can be replayed as a CUDA graph
+        step0 = int(float(opt.state[self.params[0]]["step"]))
+        self.step_state = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.step_state[0] = step0
 
     def adam_step(self, grad_scale=1.0):
         """torch.optim.Adam.step() on the flat buffers (train.py:170-176 hyper-parameters)."""
         g = self.opt.param_groups[0]
-        self.step_count += 1
         b1, b2 = g["betas"]
-        _lib.check(_lib.lib().dcv_adam_flat(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
-                                            self.flat_v.data_ptr(), self.flat_p.numel(), g["lr"], b1, b2, g["eps"],
-                                            g["weight_decay"], self.step_count, grad_scale,
-                                            torch.cuda.current_stream().cuda_stream))
-        engine.invalidate_packed(self.params)
+        _lib.check(_lib.lib().dcv_adam_flat_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+                                                self.flat_v.data_ptr(), self.flat_p.numel(), g["lr"], b1, b2, g["eps"],
+                                                g["weight_decay"], self.step_state.data_ptr(), grad_scale,
+                                                torch.cuda.current_stream().cuda_stream))
+        engine.invalidate_packed(self.params)   # the packed bf16 copies of these weights are now stale
+
+    def sync_optimizer_state(self):
+        """publish the device-side step count into opt.state[p]['step'] (host sync; call before saving / inspecting)"""
+        step = float(int(self.step_state[0].item()))
         for p in self.params:
-            self.opt.state[p]["step"] = torch.tensor(float(self.step_count))
+            self.opt.state[p]["step"] = torch.tensor(step)
 
 
 def dp_world():
@@ -146,6 +154,9 @@ class Trainer(object):
         self.iteration: int = 0
         self.epoch: int = 0
         self._flat = None
+        self._wcache = {}
+        self._graphs = {}           # (upd_d, upd_g, ggen.training, cgen.training) -> [eager runs so far, CUDAGraph, losses]
+        self.use_cuda_graph = os.environ.get("DCV_NO_GRAPH", "0") != "1"
         self._pending = []          # device-side loss records waiting for the next log flush
         self.on_log_samples = None  # optional hooks for the (out-of-scope) visual logging / IS-FID evaluation
         self.on_evaluate = None
@@ -258,16 +269,68 @@ class Trainer(object):
 
     def train_step(self, xc_real, xg_real, t_rand=None):
         """One iteration of trainer.py:279-363.  xc_real (B,3,T,64,64), xg_real (B,C,T,64,64) on the device.
-        Returns a device tensor [loss_idis, loss_vdis, loss_gdis, loss_gen]."""
+        Returns a device tensor [loss_idis, loss_vdis, loss_gdis, loss_gen].
+
+        With the device RNG the whole iteration (~500 kernel launches, every one of them static in shape and
+        address) is captured once per update pattern into a CUDA graph and replayed; the frame index t_rand and
+        the Adam step counters live in device memory so nothing has to be re-recorded."""
         self._prepare()
-        if engine.WCACHE is None:
-            engine.WCACHE = {}
+        if t_rand is None:
+            t_rand = np.random.randint(self.models["ggen"].video_length)                        # trainer.py:279
+        if self.use_cuda_graph and engine.rng().mode == "device":
+            return self._graph_step(xc_real, xg_real, int(t_rand))
+        return self._eager_step(xc_real, xg_real, t_rand)
+
+    def _eager_step(self, xc_real, xg_real, t_rand):
+        engine.WCACHE = self._wcache          # packed-weight cache owned by this trainer (keys are ids of its parameters)
+        try:
+            return self._train_step(xc_real, xg_real, t_rand)
+        finally:
+            engine.WCACHE = None
+
+    GRAPH_WARMUP = 2   # eager iterations per update pattern before capture (lazy module loads, smem opt-in, NCCL setup)
+
+    def _graph_step(self, xc_real, xg_real, t_rand):
+        cfg = self.configs
+        ggen, cgen = self.models["ggen"], self.models["cgen"]
+        key = (self.iteration % cfg["num_gen_update"] == 0, self.iteration % cfg["num_dis_update"] == 0,
+               ggen.training, cgen.training, tuple(xc_real.shape), tuple(xg_real.shape))
+        slot = self._graphs.setdefault(key, [0, None, None, None])
+        if slot[1] is None and slot[0] < self.GRAPH_WARMUP:
+            slot[0] += 1
+            return self._eager_step(xc_real, xg_real, t_rand)
+        if slot[3] is None:   # static inputs of this graph: the real batch and the frame index
+            slot[3] = (torch.empty(xc_real.shape, dtype=torch.float32, device=self.device),
+                       torch.empty(xg_real.shape, dtype=torch.float32, device=self.device),
+                       torch.zeros(1, dtype=torch.int32, device=self.device), torch.zeros(1, dtype=torch.int32).pin_memory())
+        gxc, gxg, t_dev, t_host = slot[3]
+        gxc.copy_(xc_real, non_blocking=True)
+        gxg.copy_(xg_real, non_blocking=True)
+        t_host[0] = t_rand
+        t_dev.copy_(t_host, non_blocking=True)
+        if slot[1] is None:
+            # Capture.  The generators' train/eval flags change inside the step (trainer.py:338-339); restore them so the
+            # recorded pattern matches `key`, then let the first replay perform the iteration.
+            modes = (ggen.training, cgen.training)
+            self._wcache.clear()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                losses = self._eager_step(gxc, gxg, t_dev)
+            ggen.train(modes[0])
+            cgen.train(modes[1])
+            self._wcache.clear()                 # packed weights created during capture live in the graph's pool
+            slot[1], slot[2] = graph, losses
+        slot[1].replay()
+        ggen.train()                             # host-side flags the replay cannot set (trainer.py:338-339)
+        cgen.train()
+        return slot[2].clone()
+
+    def _train_step(self, xc_real, xg_real, t_rand):
         cfg = self.configs
         B = cfg["batchsize"]
         ggen, cgen = self.models["ggen"], self.models["cgen"]
         T = ggen.video_length
-        if t_rand is None:
-            t_rand = np.random.randint(T)                                                       # trainer.py:279
         losses = torch.zeros(4, dtype=torch.float32, device=self.device)
         slot = {"idis": 0, "vdis": 1, "gdis": 2}
         L = self.loss
@@ -332,6 +395,11 @@ class Trainer(object):
         return losses
 
     # ------------------------------------------------------------------ logging of device-side losses
+    def sync_optimizer_state(self):
+        if self._flat:
+            for f in self._flat.values():
+                f.sync_optimizer_state()
+
     def _flush_losses(self):
         if not self._pending:
             return
@@ -380,5 +448,6 @@ class Trainer(object):
                     self.logger.log()
                     self.logger.clear()
         self._flush_losses()
+        self.sync_optimizer_state()
         self.save_params()
         self.log_samples(ggen, cgen, self.iteration)

@@ -174,8 +174,10 @@ int dcv_copy_cl(int src_dtype, const void* src, int64_t lds, int dst_dtype, void
 
 /* frame t of every clip: reverse=0: dst(N,1,HW,C) = clips(N,T,HW,C)[:, t]; reverse=1: clips[:, t] (+)= dst
  * (the image discriminator's x[:, :, t] slice, trainer.py:299,307,347, and its gradient) */
-int dcv_frame_copy(int dtype, void* clips, int64_t ldc, int N, int T, int64_t hw, int C, int t, void* frames,
-                   int64_t ldf, int reverse, int accumulate, void* stream);
+int dcv_frame_copy(int dtype, void* clips, int64_t ldc, int N, int T, int64_t hw, int C, int t, const int* t_dev,
+                   void* frames, int64_t ldf, int reverse, int accumulate, void* stream);
+/* t_dev (device pointer, may be NULL) overrides t: the frame index then lives on the device, so a captured CUDA graph
+ * of the step can be replayed with a fresh np.random.randint(T) every iteration (trainer.py:279) */
 
 /* ---- GRU latent trajectory (generator.py:58,84-101) -----------------------------------------
  * h0 [B][D], eps [T][B][D] fp32; weights in nn.GRUCell layout (3D x D, gate order r,z,n).
@@ -200,6 +202,11 @@ int dcv_loss_fwd_bwd(int dtype, const void* y, int64_t ldy, int64_t n, int kind,
 int dcv_adam_multi(int ntensors, float* const* p, const float* const* g, float* const* m, float* const* v,
                    const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay,
                    int64_t step, float grad_scale, void* stream);
+/* Flat-buffer Adam whose step counter lives on the device: step_state is 16 bytes {int64 step; float step_size;
+ * float 1/sqrt(bias_correction2)}; the call first advances it (step += 1, bias corrections in fp64), then updates.
+ * No host value changes between iterations, so the whole training step can be captured in a CUDA graph. */
+int dcv_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, void* step_state, float grad_scale, void* stream);
 /* same over one flat buffer (the data-parallel path keeps params/grads/state flat per network) */
 int dcv_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream);

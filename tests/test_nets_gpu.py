@@ -291,3 +291,41 @@ def test_train_step_full_width(precision, ltol, ctol, ntol, tmp_path):
     print(f"full width [{precision}]: losses {got} worst per-tensor grad cosine {worst:.5f} at {worst_k}; per-network {nets}")
     assert worst > ctol, (worst, worst_k)
     assert min(nets.values()) > ntol, nets
+
+
+def test_cuda_graph_replay_of_the_step(tmp_path):
+    """Device-RNG mode: after two eager iterations the step is captured into a CUDA graph and replayed.  Checks that
+    replays keep advancing the state exactly like eager iterations do (Adam step counters on the device, BatchNorm
+    num_batches_tracked, parameters), with a different frame index every iteration."""
+    dcv, _, _, loss_mod, trainer_mod, _, engine = _mods()
+    cfg = small_cfg("optical-flow", 2, "hinge-loss", noise=True, ngf=16, ndf=16)
+    init = orc.init_all(cfg, 13)
+    models = build_models(cfg, init, "bf16")
+    engine.set_rng_mode("device")
+    opts = {k: torch.optim.Adam(m.parameters(), lr=2e-4, betas=(0.5, 0.999), weight_decay=1e-5) for k, m in models.items()}
+    trainer_mod.Trainer.save_classobj = lambda self: None
+    tr = trainer_mod.Trainer(None, _Logger(tmp_path), models, opts, loss_mod.HingeLoss(), dict(cfg, config_path=""))
+    assert tr.use_cuda_graph
+    torch.manual_seed(3)
+    xc, xg = orc.synthetic_batch(cfg, cfg["batchsize"], 1)
+    xc, xg = xc.cuda(), xg.cuda()
+    losses, w_prev = [], models["vdis"].main[1].weight.detach().clone()
+    n_iter = 7
+    for it in range(n_iter):
+        tr.iteration += 1
+        losses.append(tr.train_step(xc, xg, t_rand=it % 16))
+        w = models["vdis"].main[1].weight.detach().clone()
+        assert float((w - w_prev).abs().max()) > 0, f"iteration {it}: discriminator weights did not move"
+        w_prev = w
+    torch.cuda.synchronize()
+    slot = next(iter(tr._graphs.values()))
+    assert slot[1] is not None and slot[0] == trainer_mod.Trainer.GRAPH_WARMUP      # captured after the warm-up iterations
+    L = torch.stack(losses).cpu()
+    assert torch.isfinite(L).all() and float(L[:, 3].min()) > 0
+    tr.sync_optimizer_state()
+    assert int(tr._flat["ggen"].step_state[0]) == 2 * n_iter and int(tr._flat["vdis"].step_state[0]) == n_iter
+    assert float(opts["cgen"].state[next(models["cgen"].parameters())]["step"]) == n_iter
+    # D BatchNorm sees real, fake, fake per iteration; G BatchNorm two forwards per iteration
+    assert int(models["vdis"].main[2].num_batches_tracked) == 3 * n_iter
+    assert int(models["cgen"].down_blocks[0].main[1].num_batches_tracked) == 2 * n_iter
+    engine.set_rng_mode("cpu_parity")
