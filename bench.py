@@ -306,9 +306,9 @@ def run_cuda(args, cfg_name):
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")) if "DCV_KEEP_VISIBLE" in os.environ else 0)
     if rank == 0:
         sampler.start()
-    l0 = _lib.lib().dcv_launch_count()
+    l0 = _lib.lib().dcv_launch_count() + tr.replayed_launches
     ms = timed(resident_step, args.steps)
-    launches = _lib.lib().dcv_launch_count() - l0
+    launches = _lib.lib().dcv_launch_count() + tr.replayed_launches - l0
     ms_e2e = timed(e2e_step, args.steps)
     if rank == 0:
         sampler.stop_flag.set()
@@ -320,7 +320,7 @@ def run_cuda(args, cfg_name):
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"config/{cfg_name}.yml (normalised) training step, batch 32 per GPU, 16x64x64, D and G both update every iteration",
                        "l2": f"{nbuf} rotating input batches; per-step activation traffic >> 126 MB L2",
-                       "parallelism": f"dp{world}", "useful_tflop_per_step": flops / 1e12, "host_issue_ms_per_step": host_ms[0],
+                       "parallelism": f"dp{world}", "cuda_graph": bool(tr.use_cuda_graph), "useful_tflop_per_step": flops / 1e12, "host_issue_ms_per_step": host_ms[0],
                        "step_tflops": flops / ms / 1e9, "step_frac_of_sustained_peak": flops / ms / 1e9 / sustained},
             "e2e": {"value": world * 1e3 / ms_e2e, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
             "gpu_launches": int(launches),

@@ -155,6 +155,7 @@ class Trainer(object):
         self.epoch: int = 0
         self._flat = None
         self._wcache = {}
+        self.replayed_launches = 0  # dcv kernels executed through graph replays (dcv_launch_count() only sees eager launches)
         self._graphs = {}           # (upd_d, upd_g, ggen.training, cgen.training) -> [eager runs so far, CUDAGraph, losses]
         self.use_cuda_graph = os.environ.get("DCV_NO_GRAPH", "0") != "1"
         self._pending = []          # device-side loss records waiting for the next log flush
@@ -315,13 +316,16 @@ class Trainer(object):
             self._wcache.clear()
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            l0 = _lib.lib().dcv_launch_count()
             with torch.cuda.graph(graph):
                 losses = self._eager_step(gxc, gxg, t_dev)
+            slot.append(_lib.lib().dcv_launch_count() - l0)      # kernels of this library recorded in the graph
             ggen.train(modes[0])
             cgen.train(modes[1])
             self._wcache.clear()                 # packed weights created during capture live in the graph's pool
             slot[1], slot[2] = graph, losses
         slot[1].replay()
+        self.replayed_launches += slot[4]
         ggen.train()                             # host-side flags the replay cannot set (trainer.py:338-339)
         cgen.train()
         return slot[2].clone()
