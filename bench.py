@@ -335,7 +335,15 @@ def run_cuda(args, cfg_name):
             line["cpu_baseline"] = cpu_baseline(cfg_name)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured CUDA graphs hold NCCL work; tearing the communicator down under them can block (observed: the
+        # 2-GPU run printed its line and then sat in destroy_process_group until the timeout).  Drop the graphs, agree
+        # that everyone is done, and leave without the collective teardown.
+        tr._graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -47,6 +47,11 @@ TC_CASES = [
     ("tc_convT_512_256", "convT", 512, 256, (1, 4, 4), (1, 2, 2), (0, 1, 1), 8, (1, 4, 4)),
     ("tc_convT_k3_n3", "convT", 128, 3, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, (1, 32, 32)),
     ("tc_convT_64_1", "convT", 64, 1, (1, 4, 4), (1, 2, 2), (0, 1, 1), 2, (1, 32, 32)),
+    # halo-tile kernel: odd batch (masked second tile), 128-wide N tile with 4 fused phases, 3x3 stride-1 both ways
+    ("halo_convT_128_128_odd", "convT", 128, 128, (1, 4, 4), (1, 2, 2), (0, 1, 1), 3, (1, 16, 16)),
+    ("halo_convT_256_64", "convT", 256, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 5, (1, 32, 32)),
+    ("halo_conv_k3_64_64", "conv", 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 3, (1, 32, 32)),
+    ("halo_convT_k3_64_32", "convT", 64, 32, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, (1, 16, 24)),
 ]
 
 
