@@ -328,8 +328,13 @@ def run_cuda(args, cfg_name):
     if rank == 0:
         probe = dominant_kernel_probe(cfg, B) if args.precision == "bf16" else None
         if probe:
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tpath):   # dram__bytes_read+write per launch from the committed `ncu --set full` capture of this launch
+                traffic = json.load(open(tpath)).get("prof_vdis_main1_fwd", {}).get("dram_bytes_per_launch")
             line["roofline"] = {"bound": "tensor", "achieved": probe["tflops"], "peak": burst, "unit": "TFLOP/s",
-                                "frac": probe["tflops"] / burst, "traffic": None, "kernel": probe["kernel"],
+                                "frac": probe["tflops"] / burst, "traffic": traffic, "kernel": probe["kernel"],
+                                "algorithmic_flops_per_launch": probe["flops"],
                                 "ms_per_launch": probe["ms"], "peak_source": f"{src} burst (kernel timed alone)"}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(cfg_name)

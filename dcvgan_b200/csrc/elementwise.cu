@@ -396,18 +396,34 @@ bn_act_vec_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C, con
       sc[j] = is * g; sh[j] = (gamma ? beta[c0 + j] : 0.f) - mean[c0 + j] * is * g;
     }
   }
-  for (int64_t row = m.rb + m.lane; row < m.re; row += m.lanes) {
-    float v[N];
-    VecIO<T>::load(z + row * ldz + c0, v);
-    const float* dr = drop ? drop + (row / rows_per_n) * C + c0 : nullptr;
+  float mu[N], is[N], ga[N], be[N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      float t = mean ? ((v[j] - mean[c0 + j]) * invstd[c0 + j]) : v[j];   // same operation order as the scalar kernel
-      if (mean && gamma) t = t * gamma[c0 + j] + beta[c0 + j];
-      if (dr) t *= dr[j];
-      v[j] = apply_act(t, act, slope);
+  for (int j = 0; j < N; ++j) {
+    mu[j] = mean ? mean[c0 + j] : 0.f; is[j] = mean ? invstd[c0 + j] : 1.f;
+    ga[j] = (mean && gamma) ? gamma[c0 + j] : 1.f; be[j] = (mean && gamma) ? beta[c0 + j] : 0.f;
+  }
+  constexpr int U = 4;   // rows in flight per thread (independent 16-byte loads)
+  for (int64_t row0 = m.rb + m.lane; row0 < m.re; row0 += (int64_t)m.lanes * U) {
+    float v[U][N];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row < m.re) VecIO<T>::load(z + row * ldz + c0, v[u]);
     }
-    VecIO<T>::store(a + row * lda + c0, v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row >= m.re) continue;
+      const float* dr = drop ? drop + (row / rows_per_n) * C + c0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        float t = v[u][j];
+        if (mean) { t = (t - mu[j]) * is[j]; if (gamma) t = t * ga[j] + be[j]; }   // same operation order as the scalar kernel
+        if (dr) t *= dr[j];
+        v[u][j] = apply_act(t, act, slope);
+      }
+      VecIO<T>::store(a + row * lda + c0, v[u]);
+    }
   }
   (void)sc; (void)sh;
 }
@@ -422,7 +438,17 @@ __device__ __forceinline__ void channel_reduce2_vec(int64_t rows, int C, float* 
 #pragma unroll
   for (int j = 0; j < N; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
   if (m.active) {
-    for (int64_t row = m.rb + m.lane; row < m.re; row += m.lanes) {
+    int64_t row = m.rb + m.lane;
+    for (; row + m.lanes < m.re; row += 2 * (int64_t)m.lanes) {      // two rows in flight
+      float v0[N], v1[N], u0[N], u1[N];
+      f(row, m.cg * N, v0, v1);
+      f(row + m.lanes, m.cg * N, u0, u1);
+#pragma unroll
+      for (int j = 0; j < N; ++j) { a0[j] += v0[j]; a1[j] += v1[j]; }
+#pragma unroll
+      for (int j = 0; j < N; ++j) { a0[j] += u0[j]; a1[j] += u1[j]; }
+    }
+    for (; row < m.re; row += m.lanes) {
       float v0[N], v1[N];
       f(row, m.cg * N, v0, v1);
 #pragma unroll

@@ -222,7 +222,22 @@ wgrad_simt_kernel(WgradP p, const T* __restrict__ xl, int64_t ldl, const T* __re
 }
 
 // dw[cl*s_l + cs*s_s + tap*s_tap] (+)= sum_z partial[z][tap][cl][cs]   (fixed order => deterministic)
-// Block = 32 consecutive elements x 8 split lanes: lane y sums splits y, y+8, ... (coalesced 128-byte rows), the
+// few splits (large weights): one element per thread
+__global__ void __launch_bounds__(256)
+wgrad_reduce_flat_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, int wCl, int wCs,
+                         float* __restrict__ dw, int64_t s_l, int64_t s_s, int64_t s_tap, int accumulate) {
+  const int64_t total = (int64_t)taps * Cl * Cs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
+    if (cl >= wCl || cs >= wCs) continue;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * total + i];
+    float* d = dw + cl * s_l + cs * s_s + tap * s_tap;
+    *d = accumulate ? (*d + s) : s;
+  }
+}
+
+// many splits (small weights, huge pixel counts): block = 32 consecutive elements x 8 split lanes: lane y sums splits y, y+8, ... (coalesced 128-byte rows), the
 // eight partial sums are then added in a fixed order.  Keeps small weights with hundreds of splits parallel.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, int wCl,
@@ -292,6 +307,12 @@ int wgrad_reduce(const float* partial, int splits, const dcv_geom* g, float* dw,
                  int64_t s_tap, int accumulate, cudaStream_t s) {
   const int taps = g->kt * g->kh * g->kw;
   const int64_t total = (int64_t)taps * g->Cl * g->Cs;
+  const int wl = g->wCl > 0 ? g->wCl : g->Cl, ws_ = g->wCs > 0 ? g->wCs : g->Cs;
+  if (splits <= 16) {
+    int fb = (int)((total + 255) / 256); if (fb > 148 * 8) fb = 148 * 8;
+    wgrad_reduce_flat_kernel<<<fb, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, wl, ws_, dw, s_l, s_s, s_tap, accumulate);
+    return check_launch("wgrad_reduce");
+  }
   int blocks = (int)((total + 31) / 32); if (blocks > 148 * 16) blocks = 148 * 16;
   wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, g->wCl > 0 ? g->wCl : g->Cl,
                                              g->wCs > 0 ? g->wCs : g->Cs, dw, s_l, s_s, s_tap, accumulate);

@@ -271,180 +271,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-// ------------------------------------------------------------------------------------------ conv_halo
-// 2-D correlations whose taps read the input at unit stride (transposed convolutions / data gradients of strided
-// convolutions, phase by phase; 3x3 stride-1 layers) re-read almost the same activation tile for every tap: the
-// generic kernel above fetches 16 (k4s2, 4 phases x 4 taps) or 9 (k3s1) shifted copies of it from L2, and the SM's
-// L2 port (~42 B/clk) - not the tensor pipe - sets its speed.  Here one TMA box per channel block brings the tile
-// WITH its halo (16 columns x 18 rows for an 8 x 16 output tile) and every (phase, tap) MMA reads a shifted
-// 128-row window of it: the window for offset (dh, dw) starts (1+dh)*16 + (1+dw) rows into the box, its 16 groups
-// of 8 rows are 16 rows (2048 B) apart (descriptor SBO), and the 128B-swizzle phase of the unaligned start goes
-// into the descriptor's base-offset field.  All phases of a work item accumulate side by side in TMEM, so the
-// activation traffic per FLOP drops 4-7x and the weights are the larger stream (amortised over mt tiles).
-constexpr int HALO_W = 16, HALO_H = 18, HALO_ROWS = HALO_W * HALO_H;    // box for an 8 x 16 tile, +-1 halo, padded to 16 columns
-constexpr int HALO_TW = 8, HALO_TH = 16;
-constexpr int HALO_MAX_TAPS = 9;
-
-struct HaloP {
-  ConvP c;
-  int phases, ntaps;                       // sub-pixel phases fused in one work item, taps per phase
-  int mt;                                  // tiles (images) per work item
-  int tiles_w, tiles_h, tiles_n, ntn;
-  int kchunks, bnt;
-  int a_slot_bytes, b_slot_bytes, b_tx_bytes;
-  int64_t ldy;
-  int act; float slope;
-  int vec_ok, tmem_cols;
-};
-
-__device__ __forceinline__ uint64_t make_sdesc_off(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
-  uint64_t d = make_sdesc(saddr, 16, sbo_bytes, 2);
-  d |= (uint64_t)(base_off & 7u) << 49;
-  return d;
-}
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const HaloP p,
-                 __nv_bfloat16* __restrict__ y) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t a_full[2], a_empty[2], b_full[2], b_empty[2], tmem_full_bar;
-  __shared__ uint32_t tmem_slot;
-
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  int item = blockIdx.x;
-  const int tw = item % p.tiles_w; item /= p.tiles_w;
-  const int th = item % p.tiles_h; item /= p.tiles_h;
-  const int tn = item % p.tiles_n; const int ntile = item / p.tiles_n;
-  const int w0 = tw * HALO_TW, h0 = th * HALO_TH, n0 = tn * p.mt;
-
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_base = sbase + 2u * (uint32_t)p.a_slot_bytes;
-  const int a_tile_bytes = HALO_ROWS * 128;
-
-  if (warp == 0 && lane == 0) { tmap_prefetch(&mapA); tmap_prefetch(&mapB); }
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-      mbar_init(&tmem_full_bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-
-  if (warp == 0) {
-    // producer: lane 0 arms the barriers, the lanes then issue the boxes of a slot in parallel
-    int bs = 0; uint32_t bphase = 0;
-    for (int kc = 0; kc < p.kchunks; ++kc) {
-      const int as = kc & 1; const uint32_t aphase = (uint32_t)((kc >> 1) & 1);
-      if (lane == 0) {
-        mbar_wait(&a_empty[as], aphase ^ 1u);
-        mbar_expect_tx(&a_full[as], (uint32_t)(p.mt * a_tile_bytes));
-      }
-      __syncwarp();
-      if (lane < p.mt)
-        tma_load_5d(sbase + as * p.a_slot_bytes + lane * a_tile_bytes, &mapA, &a_full[as], kc * 64, w0 - 1, h0 - 1, 0, n0 + lane);
-      for (int ph = 0; ph < p.phases; ++ph) {
-        if (lane == 0) {
-          mbar_wait(&b_empty[bs], bphase ^ 1u);
-          mbar_expect_tx(&b_full[bs], (uint32_t)p.b_tx_bytes);
-        }
-        __syncwarp();
-        if (lane < p.ntaps)
-          tma_load_3d(b_base + bs * p.b_slot_bytes + lane * (p.bnt * 128), &mapB, &b_full[bs], lane * p.c.Kc + kc * 64,
-                      ntile * p.bnt, ph);
-        if (++bs == 2) { bs = 0; bphase ^= 1u; }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
-      int bs = 0; uint32_t bphase = 0;
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        const int as = kc & 1; const uint32_t aphase = (uint32_t)((kc >> 1) & 1);
-        mbar_wait(&a_full[as], aphase);
-        tc_fence_after();
-        const uint32_t a_src = sbase + as * p.a_slot_bytes;
-        for (int ph = 0; ph < p.phases; ++ph) {
-          const PhaseInfo f = make_phase(p.c, ph);
-          mbar_wait(&b_full[bs], bphase);
-          tc_fence_after();
-          const uint32_t b_src = b_base + bs * p.b_slot_bytes;
-          int j = 0;
-          for (int jh = 0; jh < f.nh; ++jh) {
-            const int dh = f.offh + f.sgn * jh;
-            for (int jw = 0; jw < f.nw; ++jw, ++j) {
-              const int dw = f.offw + f.sgn * jw;
-              const uint32_t row0 = (uint32_t)((1 + dh) * HALO_W + (1 + dw));
-              for (int m = 0; m < p.mt; ++m) {
-                const uint32_t d = tmem_base + (uint32_t)((ph * p.mt + m) * p.bnt);
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t ad = make_sdesc_off(a_src + m * a_tile_bytes + row0 * 128u + k * 32u, HALO_W * 128u, row0);
-                  const uint64_t bd = make_sdesc(b_src + j * (p.bnt * 128) + k * 32u, 16, 1024, 2);
-                  umma_bf16(d, ad, bd, idesc, (kc > 0 || j > 0 || k > 0) ? 1u : 0u);
-                }
-              }
-            }
-          }
-          umma_commit(&b_empty[bs]);
-          if (++bs == 2) { bs = 0; bphase ^= 1u; }
-        }
-        umma_commit(&a_empty[as]);
-      }
-      umma_commit(&tmem_full_bar);
-    }
-    __syncwarp();
-  } else {
-    const int quarter = warp % 4;
-    const int row = quarter * 32 + lane;
-    const int qw = w0 + row % HALO_TW, qh = h0 + row / HALO_TW;
-    const int nbase = ntile * p.bnt;
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-    for (int ph = 0; ph < p.phases; ++ph) {
-      const PhaseInfo f = make_phase(p.c, ph);
-      for (int m = 0; m < p.mt; ++m) {
-        const int n = n0 + m;
-        const bool valid = qw < f.Qw && qh < f.Qh && n < p.c.N;
-        const int64_t pos = ((int64_t)n * p.c.Oh + (qh * f.osh + f.rh)) * p.c.Ow + (qw * f.osw + f.rw);
-        __nv_bfloat16* yrow = y + pos * p.ldy;
-        for (int cb = 0; cb < p.bnt; cb += 16) {
-          uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((ph * p.mt + m) * p.bnt + cb), v);
-          if (!valid) continue;
-          const int c0 = nbase + cb;
-          if (c0 >= p.c.Nc) continue;
-          if (p.vec_ok && c0 + 16 <= p.c.Nc) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float a = apply_act(__uint_as_float(v[2 * i]), p.act, p.slope);
-              const float b = apply_act(__uint_as_float(v[2 * i + 1]), p.act, p.slope);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
-            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < p.c.Nc) yrow[c0 + i] = __float2bfloat16_rn(apply_act(__uint_as_float(v[i]), p.act, p.slope));
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-}
-
 // ------------------------------------------------------------------------------------------ wgrad_tc
 // D[128 rows = (128/cbA) gathered L blocks of cbA channels, Ns columns = S channels] += A^T B over pixel blocks.
 // A block = (tap, channel chunk of cbA) of the gathered L tensor, B = S tile; both MN-major (channels contiguous),
@@ -601,25 +427,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
 // ------------------------------------------------------------------------------------------ packing
 // gather : out[n][tap][k]                 (n < npad, k < Kc)
 // scatter: out[phase][n][j][k]            (j = tap-in-phase index in the kernel's loop order)
-__global__ void pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap,
-                                      int npad, int phases, __nv_bfloat16* __restrict__ out) {
-  for (int ph = 0; ph < phases; ++ph) {
+__global__ void __launch_bounds__(256)
+pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap,
+                      int npad, int phases, __nv_bfloat16* __restrict__ out) {
+  // one thread per (phase, n, k): it walks the taps of its phase, so the fp32 reads of a thread fall into one or two
+  // cache lines (taps are the innermost dimension of the PyTorch layouts) and the bf16 writes of a warp are contiguous in k
+  const int64_t per_phase_nk = (int64_t)npad * c.Kc;
+  const int64_t total = per_phase_nk * phases;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ph = (int)(i / per_phase_nk);
+    const int64_t r = i - (int64_t)ph * per_phase_nk;
+    const int k = (int)(r % c.Kc); const int n = (int)(r / c.Kc);
     const PhaseInfo f = make_phase(c, ph);
     const int ntaps = f.nt * f.nh * f.nw;
-    const int64_t per_phase = (int64_t)npad * ntaps * c.Kc;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_phase; i += (int64_t)gridDim.x * blockDim.x) {
-      const int k = (int)(i % c.Kc); int64_t r = i / c.Kc;
-      const int j = (int)(r % ntaps); const int n = (int)(r / ntaps);
-      const int jw = j % f.nw, jh = (j / f.nw) % f.nh, jt = j / (f.nw * f.nh);
-      const int tap = ((f.a0t + f.ast * jt) * c.kh + (f.a0h + f.ash * jh)) * c.kw + (f.a0w + f.asw * jw);
-      float v = 0.f;
-      if (n < c.wN && k < c.wK) {
-        // gather: reduction channel k is an L channel, produced channel n is an S channel; scatter: swapped
-        const int cl = c.scatter ? n : k, cs = c.scatter ? k : n;
-        v = w[cl * s_l + cs * s_s + tap * s_tap];
-      }
-      out[ph * per_phase + i] = __float2bfloat16_rn(v);
-    }
+    const bool real = n < c.wN && k < c.wK;
+    // gather: reduction channel k is an L channel, produced channel n is an S channel; scatter: swapped
+    const int cl = c.scatter ? n : k, cs = c.scatter ? k : n;
+    const float* wb = w + cl * s_l + cs * s_s;
+    __nv_bfloat16* ob = out + ((int64_t)ph * npad + n) * ntaps * c.Kc + k;
+    int j = 0;
+    for (int jt = 0; jt < f.nt; ++jt)
+      for (int jh = 0; jh < f.nh; ++jh)
+        for (int jw = 0; jw < f.nw; ++jw, ++j) {
+          const int tap = ((f.a0t + f.ast * jt) * c.kh + (f.a0h + f.ash * jh)) * c.kw + (f.a0w + f.asw * jw);
+          ob[(int64_t)j * c.Kc] = __float2bfloat16_rn(real ? wb[tap * s_tap] : 0.f);
+        }
   }
 }
 
@@ -716,89 +548,15 @@ int pack_weight_tc(const dcv_geom* g, int dir, const float* w, int64_t s_l, int6
   DCV_REQUIRE(conv_tc_supported(g, dir), "pack_weight_tc: geometry not supported by the tcgen05 kernel");
   const ConvP c = make_convp(g, dir);
   const int phases = c.scatter ? g->st * g->sh * g->sw : 1;
-  const int64_t total = packed_weight_tc_bytes(g, dir) / 2 / phases;
+  const int64_t total = (int64_t)tc_npad(c.Nc) * c.Kc * phases;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
   pack_weight_tc_kernel<<<blocks, 256, 0, s>>>(c, w, s_l, s_s, s_tap, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
   return check_launch("pack_weight_tc");
 }
 
-// halo kernel eligibility: 2-D, unit-stride taps with offsets in [-1,1], 64-channel blocks, tiles of 8 x 16
-static bool halo_eligible(const dcv_geom* g, const ConvP& c, int phases) {
-  if (getenv("DCV_NO_HALO")) return false;
-  if (g->kt != 1 || g->Tl != 1 || g->Ts != 1 || c.Kc % 64 != 0) return false;
-  if (!(phases == 1 || phases == 4)) return false;
-  for (int ph = 0; ph < phases; ++ph) {
-    const PhaseInfo f = make_phase(c, ph);
-    if (f.mulh != 1 || f.mulw != 1) return false;
-    if (f.nh * f.nw > HALO_MAX_TAPS || f.nh * f.nw != make_phase(c, 0).nh * make_phase(c, 0).nw) return false;
-    if (f.Qw % HALO_TW != 0 || f.Qh % HALO_TH != 0) return false;
-    for (int jh = 0; jh < f.nh; ++jh) { const int dh = f.offh + f.sgn * jh; if (dh < -1 || dh > 1) return false; }
-    for (int jw = 0; jw < f.nw; ++jw) { const int dw = f.offw + f.sgn * jw; if (dw < -1 || dw > 1) return false; }
-  }
-  return true;
-}
-
-static int conv_halo(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, int act,
-                     float slope, cudaStream_t s) {
-  HaloP p;
-  p.c = make_convp(g, dir);
-  const ConvP& c = p.c;
-  p.phases = c.scatter ? g->st * g->sh * g->sw : 1;
-  const PhaseInfo f0 = make_phase(c, 0);
-  p.ntaps = f0.nh * f0.nw;
-  const int npad = tc_npad(c.Nc);
-  // all phases of a work item accumulate in TMEM: phases * mt * bnt <= 512 columns
-  int bnt = tc_bnt(npad);
-  while (p.phases * bnt > 512 || bnt > 128) {
-    int nb = 0;
-    for (int b = bnt - 16; b >= 16; b -= 16) if (npad % b == 0) { nb = b; break; }
-    if (nb == 0) break;
-    bnt = nb;
-  }
-  DCV_REQUIRE(p.phases * bnt <= 512, "conv_halo: N tile does not fit TMEM");
-  p.bnt = bnt;
-  p.ntn = npad / bnt;
-  p.kchunks = c.Kc / 64;
-  p.mt = 512 / (p.phases * pow2_ceil(bnt)); if (p.mt > 2) p.mt = 2; if (p.mt < 1) p.mt = 1;
-  if (c.N < p.mt) p.mt = 1;
-  p.a_slot_bytes = p.mt * HALO_ROWS * 128;
-  p.b_tx_bytes = p.ntaps * bnt * 128;
-  p.b_slot_bytes = (p.b_tx_bytes + 1023) / 1024 * 1024;
-  int smem = 2 * p.a_slot_bytes + 2 * p.b_slot_bytes + 1024;
-  if (smem > 226 * 1024 && p.mt == 2) {
-    p.mt = 1; p.a_slot_bytes = HALO_ROWS * 128;
-    smem = 2 * p.a_slot_bytes + 2 * p.b_slot_bytes + 1024;
-  }
-  DCV_REQUIRE(smem <= 226 * 1024, "conv_halo: shared memory budget exceeded (%d)", smem);
-  p.tiles_w = f0.Qw / HALO_TW; p.tiles_h = f0.Qh / HALO_TH; p.tiles_n = ceil_div(c.N, p.mt);
-  p.ldy = ldy; p.act = act; p.slope = slope;
-  p.vec_ok = (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0);
-  p.tmem_cols = pow2_ceil(p.phases * p.mt * bnt < 32 ? 32 : p.phases * p.mt * bnt);
-
-  CUtensorMap mapA, mapB;
-  // activation map with a box of 16 x 18 pixels x 1 image (bw=16, bh=18)
-  int rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, 64, HALO_W, HALO_H, 1, 1, 1, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
-  rc = make_weight_map(&mapB, wp, (int64_t)p.ntaps * c.Kc, npad, p.phases, 64, bnt, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    DCV_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set = smem;
-  }
-  const int grid = p.tiles_w * p.tiles_h * p.tiles_n * p.ntn;
-  conv_halo_kernel<<<grid, TC_THREADS, smem, s>>>(mapA, mapB, p, (__nv_bfloat16*)y);
-  return check_launch("conv_halo");
-}
-
 int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, int act,
             float slope, cudaStream_t s) {
   DCV_REQUIRE(conv_tc_supported(g, dir), "conv_tc: geometry not supported by the tcgen05 kernel");
-  {
-    const ConvP c0 = make_convp(g, dir);
-    const int ph0 = c0.scatter ? g->st * g->sh * g->sw : 1;
-    if (halo_eligible(g, c0, ph0)) return conv_halo(g, dir, x, ldx, wp, y, ldy, act, slope, s);
-  }
   TcConvP p;
   p.c = make_convp(g, dir);
   const ConvP& c = p.c;
