@@ -237,26 +237,29 @@ wgrad_reduce_flat_kernel(const float* __restrict__ partial, int splits, int taps
   }
 }
 
-// many splits (small weights, huge pixel counts): block = 32 consecutive elements x 8 split lanes: lane y sums splits y, y+8, ... (coalesced 128-byte rows), the
-// eight partial sums are then added in a fixed order.  Keeps small weights with hundreds of splits parallel.
+// many splits (small weights, huge pixel counts): block = 8 consecutive elements x 32 split lanes; lane y sums splits
+// y, y+32, ... (32-byte sectors), the 32 partial sums are then added in a fixed order.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, int wCl,
                     int wCs, float* __restrict__ dw, int64_t s_l, int64_t s_s, int64_t s_tap,
                     int accumulate) {
-  __shared__ float red[8][33];
+  __shared__ float red[32][9];
   const int64_t total = (int64_t)taps * Cl * Cs;
-  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-  for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+  const int tx = threadIdx.x % 8, ty = threadIdx.x / 8;
+  for (int64_t base = (int64_t)blockIdx.x * 8; base < total; base += (int64_t)gridDim.x * 8) {
     const int64_t i = base + tx;
-    float s = 0.f;
-    if (i < total)
-      for (int z = ty; z < splits; z += 8) s += partial[(int64_t)z * total + i];
-    red[ty][tx] = s;
+    float s0 = 0.f, s1 = 0.f;
+    if (i < total) {
+      int z = ty;
+      for (; z + 32 < splits; z += 64) { s0 += partial[(int64_t)z * total + i]; s1 += partial[(int64_t)(z + 32) * total + i]; }
+      if (z < splits) s0 += partial[(int64_t)z * total + i];
+    }
+    red[ty][tx] = s0 + s1;
     __syncthreads();
     if (ty == 0 && i < total) {
-      float t = red[0][tx];
+      float t = 0.f;
 #pragma unroll
-      for (int k = 1; k < 8; ++k) t += red[k][tx];
+      for (int k = 0; k < 32; ++k) t += red[k][tx];
       const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
       if (cl < wCl && cs < wCs) {   // zero-padding channels have no master weight
         float* d = dw + cl * s_l + cs * s_s + tap * s_tap;
@@ -313,7 +316,7 @@ int wgrad_reduce(const float* partial, int splits, const dcv_geom* g, float* dw,
     wgrad_reduce_flat_kernel<<<fb, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, wl, ws_, dw, s_l, s_s, s_tap, accumulate);
     return check_launch("wgrad_reduce");
   }
-  int blocks = (int)((total + 31) / 32); if (blocks > 148 * 16) blocks = 148 * 16;
+  int blocks = (int)((total + 7) / 8); if (blocks > 148 * 16) blocks = 148 * 16;
   wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, g->wCl > 0 ? g->wCl : g->Cl,
                                              g->wCs > 0 ? g->wCs : g->Cs, dw, s_l, s_s, s_tap, accumulate);
   return check_launch("wgrad_reduce");

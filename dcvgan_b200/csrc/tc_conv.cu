@@ -29,6 +29,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
@@ -246,6 +249,178 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (!valid) continue;
         const int c0 = nbase + cb;
         if (c0 >= p.c.Nc) continue;
+        if (p.vec_ok && c0 + 16 <= p.c.Nc) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a = apply_act(__uint_as_float(v[2 * i]), p.act, p.slope);
+            const float b = apply_act(__uint_as_float(v[2 * i + 1]), p.act, p.slope);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < p.c.Nc) yrow[c0 + i] = __float2bfloat16_rn(apply_act(__uint_as_float(v[i]), p.act, p.slope));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ conv_tc, grouped taps
+// Image-like operands (16 padded channels: D stems, inconv, outconv / main.12 data gradients) make one tap = one
+// 16-wide K step.  In the generic kernel above that is one pipeline stage per tap - two tiny TMA boxes and a barrier
+// round trip for ~32 cycles of MMA - so those layers were bound by TMA issue and barrier latency.  Here a stage
+// carries FOUR taps: four A boxes (32-byte rows, 32B swizzle, issued in parallel by four lanes) and ONE B box of
+// 4 taps x 16 channels = 64 K-elements per output channel (128-byte rows, 128B swizzle - the packed weight layout
+// [n][tap][k] makes consecutive taps contiguous), consumed by up to 4*mt MMAs whose A and B descriptors simply use
+// different swizzle modes.
+constexpr int TAPG = 4;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_g4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcConvP p,
+                  __nv_bfloat16* __restrict__ y) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[MAX_STAGES];
+  __shared__ uint64_t empty_bar[MAX_STAGES];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t empty_tile_flag;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const PhaseInfo f = make_phase(p.c, blockIdx.z);
+  int tile = blockIdx.x;
+  const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+  const int th = tile % p.tiles_h; tile /= p.tiles_h;
+  const int tt = tile % p.tiles_t; const int tn = tile / p.tiles_t;
+  const int w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt, n0 = tn * p.bn * p.mt;
+  if (w0 >= f.Qw || h0 >= f.Qh || t0 >= f.Qt) return;
+
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int a_tap_bytes = p.mt * 128 * 32;                  // one tap: mt*128 rows of 16 bf16
+  const int stage_bytes = TAPG * a_tap_bytes + p.b_bytes;   // b_bytes = bnt rows * 128 B
+  const int ntaps = f.nt * f.nh * f.nw;
+  const int ngroups = (ntaps + TAPG - 1) / TAPG;
+
+  if (warp == 0 && lane == 0) { tmap_prefetch(&mapA); tmap_prefetch(&mapB); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      mbar_init(&tmem_full_bar, 1);
+      empty_tile_flag = 0u;
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  // per-lane view of "its" tap inside a group (lanes 0..3): coordinates and whether the whole box is padding
+  auto tap_coords = [&](int j, int& ct, int& ch, int& cw) -> bool {
+    const int jw = j % f.nw, jh = (j / f.nw) % f.nh, jt = j / (f.nw * f.nh);
+    ct = t0 * f.mult + f.offt + f.sgn * jt;
+    ch = h0 * f.mulh + f.offh + f.sgn * jh;
+    cw = w0 * f.mulw + f.offw + f.sgn * jw;
+    const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
+    const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
+    const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
+    return !(skt || skh || skw);      // true = has in-bounds pixels
+  };
+
+  if (warp == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int gq = 0; gq < ngroups; ++gq) {
+      const int j = gq * TAPG + lane;
+      int ct = 0, ch = 0, cw = 0;
+      const bool live = lane < TAPG && j < ntaps && tap_coords(j, ct, ch, cw);
+      const uint32_t mask = __ballot_sync(0xffffffffu, live) & 0xFu;
+      if (mask == 0u) continue;                 // every tap of this group lies in the padding (same test in the MMA warp)
+      const int nlive = __popc(mask);
+      if (lane == 0) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(nlive * a_tap_bytes + p.bnt * 128));
+      }
+      __syncwarp();
+      const uint32_t a_dst = sbase + stage * stage_bytes;
+      if (live) tma_load_5d(a_dst + lane * a_tap_bytes, &mapA, &full_bar[stage], 0, cw, ch, ct, n0);
+      if (lane == TAPG) tma_load_3d(a_dst + TAPG * a_tap_bytes, &mapB, &full_bar[stage], gq * TAPG * 16, blockIdx.y * p.bnt, blockIdx.z);
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
+    int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
+    for (int gq = 0; gq < ngroups; ++gq) {
+      const int j = gq * TAPG + lane;
+      int ct = 0, ch = 0, cw = 0;
+      const bool live = lane < TAPG && j < ntaps && tap_coords(j, ct, ch, cw);
+      const uint32_t mask = __ballot_sync(0xffffffffu, live) & 0xFu;
+      if (mask == 0u) continue;
+      if (lane == 0) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_src = sbase + stage * stage_bytes;
+        const uint32_t b_src = a_src + TAPG * a_tap_bytes;
+        for (int jj = 0; jj < TAPG; ++jj) {
+          if (!((mask >> jj) & 1u)) continue;
+          const uint64_t bd = make_sdesc(b_src + jj * 32, 16, 1024, 2);
+          for (int m = 0; m < p.mt; ++m) {
+            const uint64_t ad = make_sdesc(a_src + jj * a_tap_bytes + m * (128 * 32), 16, 256, 6);
+            umma_bf16(tmem_base + m * p.bnt, ad, bd, idesc, accum);
+          }
+          accum = 1;
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+    if (lane == 0) {
+      if (accum == 0) {                 // no tap touched real pixels: the tile is all zeros, nothing was accumulated
+        empty_tile_flag = 1u;
+        mbar_arrive(&tmem_full_bar);    // plain arrive (release) so that the flag is visible to the epilogue
+      } else {
+        umma_commit(&tmem_full_bar);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp % 4;
+    const int row = quarter * 32 + lane;
+    int r = row;
+    const int dw = r % p.bw; r /= p.bw;
+    const int dh = r % p.bh; r /= p.bh;
+    const int dt = r % p.bt; const int dn = r / p.bt;
+    const int qw = w0 + dw, qh = h0 + dh, qt = t0 + dt;
+    const int nbase = blockIdx.y * p.bnt;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const bool empty_tile = *((volatile uint32_t*)&empty_tile_flag) != 0u;
+    for (int m = 0; m < p.mt; ++m) {
+      const int n = n0 + m * p.bn + dn;
+      const bool valid = qw < f.Qw && qh < f.Qh && qt < f.Qt && n < p.c.N;
+      const int64_t pos = (((int64_t)n * p.c.Ot + (qt * f.ost + f.rt)) * p.c.Oh + (qh * f.osh + f.rh)) * p.c.Ow + (qw * f.osw + f.rw);
+      __nv_bfloat16* yrow = y + pos * p.ldy;
+      for (int cb = 0; cb < p.bnt; cb += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * p.bnt + cb), v);
+        if (!valid) continue;
+        const int c0 = nbase + cb;
+        if (c0 >= p.c.Nc) continue;
+        if (empty_tile) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
+        }
         if (p.vec_ok && c0 + 16 <= p.c.Nc) {
           uint32_t pk[8];
 #pragma unroll
@@ -608,6 +783,33 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   int rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn * p.mt, f0.mulw, f0.mulh,
                         f0.mult, swz);
   if (rc) return rc;
+  if (c.Kc == 16 && ntaps0 >= 4 && !getenv("DCV_NO_TAPGROUP")) {
+    // grouped-tap variant for 16-channel (image-like) operands: 4 taps per stage
+    p.b_bytes = p.bnt * 128;
+    const int a_tap = p.mt * 128 * 32;
+    const int stage_b = TAPG * a_tap + p.b_bytes;
+    int cps = 512 / p.tmem_cols; if (cps > 4) cps = 4; if (cps < 1) cps = 1;
+    const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * (npad / p.bnt) * phases;
+    const int need = (int)((ctas + 147) / 148);
+    if (cps > need) cps = need < 1 ? 1 : need;
+    int st = ((216 * 1024) / cps - 2048) / stage_b;
+    const int ngroups = (ntaps0 + TAPG - 1) / TAPG;
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    if (st > ngroups) st = ngroups;
+    if (st < 1) st = 1;
+    p.stages = st;
+    rc = make_weight_map(&mapB, wp, (int64_t)ntaps0 * c.Kc, npad, phases, 64, p.bnt, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const int smem_g = st * stage_b + 1024;
+    static int smem_set_g = 0;
+    if (smem_g > smem_set_g) {
+      DCV_CUDA(cudaFuncSetAttribute(conv_tc_g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
+      smem_set_g = smem_g;
+    }
+    dim3 grid_g(p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n, npad / p.bnt, phases);
+    conv_tc_g4_kernel<<<grid_g, TC_THREADS, smem_g, s>>>(mapA, mapB, p, (__nv_bfloat16*)y);
+    return check_launch("conv_tc_g4");
+  }
   const int64_t Kph = (int64_t)ntaps0 * c.Kc;  // K extent of one phase
   rc = make_weight_map(&mapB, wp, Kph, npad, phases, p.cblk, p.bnt, swz);
   if (rc) return rc;
@@ -649,10 +851,18 @@ static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   p->G = 512 / pow2_ceil(p->Ns < 32 ? 32 : p->Ns);
   if (p->G > 4) p->G = 4;
   if (p->G > tiles_total) p->G = tiles_total;
-  p->tmem_cols = pow2_ceil(p->G * p->Ns < 32 ? 32 : p->G * p->Ns);
-  // pixels per stage: as many as keep >= 4 stages in ~200 KB (fewer, larger TMA boxes per byte moved)
+  // pixels per stage.  Every (tap, channel chunk) block is its own TMA box, so with narrow blocks (16 or 32
+  // channels: image-like tensors) a 32-pixel stage is dozens of 1-2 KB boxes and the kernel becomes bound by the TMA
+  // issue rate, not by bytes: take 128-pixel stages there and fewer accumulator tiles per CTA instead.
   p->pix = 32;
-  while (p->pix < 128 && (200 * 1024) / (2 * p->pix * 2 * (p->Ns + 128 * p->G)) >= 4) p->pix *= 2;
+  if (p->cbA <= 32) {
+    p->pix = 128;
+    while (p->G > 1 && (200 * 1024) / (p->pix * 2 * (p->Ns + 128 * p->G)) < 4) --p->G;
+    while (p->pix > 32 && (200 * 1024) / (p->pix * 2 * (p->Ns + 128 * p->G)) < 3) p->pix /= 2;
+  } else {
+    while (p->pix < 128 && (200 * 1024) / (2 * p->pix * 2 * (p->Ns + 128 * p->G)) >= 4) p->pix *= 2;
+  }
+  p->tmem_cols = pow2_ceil(p->G * p->Ns < 32 ? 32 : p->G * p->Ns);
   choose_box(p->pix, g->Ws, g->Hs, g->Ts, g->N, &p->bw, &p->bh, &p->bt, &p->bn);
   p->tiles_w = ceil_div(g->Ws, p->bw); p->tiles_h = ceil_div(g->Hs, p->bh); p->tiles_t = ceil_div(g->Ts, p->bt);
   p->tiles_n = ceil_div(g->N, p->bn);
