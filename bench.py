@@ -297,7 +297,7 @@ def run_cuda(args, cfg_name):
     def e2e_step(i):
         tr.iteration += 1
         xc, xg = host[i % nbuf]
-        l = tr.train_step(xc.cuda(non_blocking=True), xg.cuda(non_blocking=True))
+        l = tr.train_step(xc, xg)      # pinned host batch: the H2D copy (straight into the graph's static input) is inside the timed region
         loss_host.copy_(l, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the user reads the losses each step (trainer.py:326-328,363)
 

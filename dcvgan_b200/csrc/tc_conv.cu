@@ -446,6 +446,52 @@ conv_tc_g4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------ single-channel heads
+// The discriminators end in a convolution with ONE output channel (discriminator.py:101,206,305): a GEMV, HBM-bound
+// (every input element is used once per overlapping window).  As a 128 x 16 MMA tile it ran 16 CTAs with 256 serial
+// K iterations (175 us for 0.07 GFLOP); here one warp owns one logit, lanes stride over the channels with 16-byte
+// loads and the bf16 weight row (row 0 of the tensor-core packing [n][tap][k]) is read through the same index.
+__global__ void __launch_bounds__(256)
+head_gemv_kernel(ConvP c, const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
+                 __nv_bfloat16* __restrict__ y, int64_t ldy, int act, float slope) {
+  const int lane = threadIdx.x % 32;
+  const int64_t M = (int64_t)c.N * c.Ot * c.Oh * c.Ow;
+  int64_t m = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (m >= M) return;
+  const int64_t pos = m;
+  const int ow = (int)(m % c.Ow); m /= c.Ow;
+  const int oh = (int)(m % c.Oh); m /= c.Oh;
+  const int ot = (int)(m % c.Ot); const int n = (int)(m / c.Ot);
+  float acc = 0.f;
+  for (int a = 0; a < c.kt; ++a) {
+    const int it = ot * c.st - c.pt + a;
+    if (it < 0 || it >= c.It) continue;
+    for (int b = 0; b < c.kh; ++b) {
+      const int ih = oh * c.sh - c.ph + b;
+      if (ih < 0 || ih >= c.Ih) continue;
+      for (int d = 0; d < c.kw; ++d) {
+        const int iw = ow * c.sw - c.pw + d;
+        if (iw < 0 || iw >= c.Iw) continue;
+        const __nv_bfloat16* xp = x + ((((int64_t)n * c.It + it) * c.Ih + ih) * c.Iw + iw) * ldx;
+        const __nv_bfloat16* wt = w + (int64_t)((a * c.kh + b) * c.kw + d) * c.Kc;
+        for (int k = lane * 8; k < c.Kc; k += 256) {
+          const uint4 xv = *reinterpret_cast<const uint4*>(xp + k);
+          const uint4 wv = *reinterpret_cast<const uint4*>(wt + k);
+          const uint32_t xa[4] = {xv.x, xv.y, xv.z, xv.w}, wa[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc = fmaf(__uint_as_float(xa[i] << 16), __uint_as_float(wa[i] << 16), acc);
+            acc = fmaf(__uint_as_float(xa[i] & 0xFFFF0000u), __uint_as_float(wa[i] & 0xFFFF0000u), acc);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[pos * ldy] = __float2bfloat16_rn(apply_act(acc, act, slope));
+}
+
 // ------------------------------------------------------------------------------------------ wgrad_tc
 // D[128 rows = (128/cbA) gathered L blocks of cbA channels, Ns columns = S channels] += A^T B over pixel blocks.
 // A block = (tap, channel chunk of cbA) of the gathered L tensor, B = S tile; both MN-major (channels contiguous),
@@ -735,6 +781,12 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   TcConvP p;
   p.c = make_convp(g, dir);
   const ConvP& c = p.c;
+  if (!c.scatter && c.wN == 1 && c.Kc % 8 == 0 && (ldx % 8) == 0 && (((uintptr_t)x) & 15) == 0 && !getenv("DCV_NO_GEMV")) {
+    const int64_t M = (int64_t)c.N * c.Ot * c.Oh * c.Ow;          // one warp per logit
+    head_gemv_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(c, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)wp,
+                                                           (__nv_bfloat16*)y, ldy, act, slope);
+    return check_launch("head_gemv");
+  }
   const int phases = c.scatter ? g->st * g->sh * g->sw : 1;
   const PhaseInfo f0 = make_phase(c, 0);
   choose_box(128, f0.Qw, f0.Qh, f0.Qt, c.N, &p.bw, &p.bh, &p.bt, &p.bn);

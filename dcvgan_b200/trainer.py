@@ -283,6 +283,9 @@ class Trainer(object):
         return self._eager_step(xc_real, xg_real, t_rand)
 
     def _eager_step(self, xc_real, xg_real, t_rand):
+        if not xc_real.is_cuda:      # host (pinned) batch: H2D copy as at trainer.py:293-297
+            xc_real = xc_real.to(self.device, non_blocking=True)
+            xg_real = xg_real.to(self.device, non_blocking=True)
         engine.WCACHE = self._wcache          # packed-weight cache owned by this trainer (keys are ids of its parameters)
         try:
             return self._train_step(xc_real, xg_real, t_rand)
