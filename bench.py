@@ -40,6 +40,21 @@ CONFIGS = {
                    "idis": {"use_noise": True, "noise_sigma": 0.2, "ndf": 64, "optimizer": O},
                    "vdis": {"use_noise": True, "noise_sigma": 0.2, "ndf": 64, "optimizer": O},
                    "gdis": {"use_noise": False, "noise_sigma": 0.2, "ndf": 32, "optimizer": O, "enabled": True}},
+    # config/surreal-depth1.yml: C=1, ggen.ngf 96, hinge loss, no noise, no gdis (num_gen_update 2 in the YAML; the bench
+    # updates D and G every iteration)
+    "surreal-depth1": {"geometric_info": {"name": "depth", "channel": 1}, "loss": "hinge-loss", "seed": 15,
+                       "ggen": {"dim_z_content": 40, "dim_z_motion": 10, "ngf": 96, "optimizer": O},
+                       "cgen": {"dim_z_color": 10, "ngf": 64, "optimizer": O},
+                       "idis": {"use_noise": False, "noise_sigma": 0.2, "ndf": 64, "optimizer": O},
+                       "vdis": {"use_noise": False, "noise_sigma": 0.2, "ndf": 64, "optimizer": O},
+                       "gdis": {"use_noise": False, "noise_sigma": 0.2, "ndf": 32, "optimizer": O, "enabled": False}},
+    # config/surreal-segm.yml: 25-channel segmentation (softmax geometry, argmax remap), ggen.ngf 96, vdis.ndf 48, Noise 0.2
+    "surreal-segm": {"geometric_info": {"name": "segmentation", "channel": 25}, "loss": "adversarial-loss", "seed": 15,
+                     "ggen": {"dim_z_content": 40, "dim_z_motion": 10, "ngf": 96, "optimizer": O},
+                     "cgen": {"dim_z_color": 10, "ngf": 64, "optimizer": O},
+                     "idis": {"use_noise": True, "noise_sigma": 0.2, "ndf": 64, "optimizer": O},
+                     "vdis": {"use_noise": True, "noise_sigma": 0.2, "ndf": 48, "optimizer": O},
+                     "gdis": {"use_noise": False, "noise_sigma": 0.2, "ndf": 32, "optimizer": O, "enabled": False}},
 }
 
 

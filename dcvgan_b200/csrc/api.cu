@@ -32,10 +32,14 @@ int conv_simt(const dcv_geom*, int, int, const void*, int64_t, const void*, void
 int wgrad_simt(const dcv_geom*, int, const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int64_t, int,
                void*, int64_t, cudaStream_t);
 int64_t wgrad_simt_ws_bytes(const dcv_geom*);
-int pack_weight_simt(const dcv_geom*, int, const float*, int64_t, int64_t, int64_t, float*, cudaStream_t);
+int pack_weight_simt(const dcv_geom*, int, const float*, int64_t, int64_t, int64_t, WeightWin, float*, cudaStream_t);
+int wgrad_simt_partial(const dcv_geom*, int, const void*, int64_t, const void*, int64_t, void*, int64_t, cudaStream_t);
+int wgrad_simt_splits(const dcv_geom*);
+int wgrad_tc_splits(const dcv_geom*);
+int wgrad_reduce_win(const float*, int, const dcv_geom*, WeightWin, float*, int64_t, int64_t, int64_t, int, cudaStream_t);
 int conv_tc_supported(const dcv_geom*, int);
 int64_t packed_weight_tc_bytes(const dcv_geom*, int);
-int pack_weight_tc(const dcv_geom*, int, const float*, int64_t, int64_t, int64_t, void*, cudaStream_t);
+int pack_weight_tc(const dcv_geom*, int, const float*, int64_t, int64_t, int64_t, WeightWin, void*, cudaStream_t);
 int conv_tc(const dcv_geom*, int, const void*, int64_t, const void*, void*, int64_t, int, float, cudaStream_t);
 int wgrad_tc_supported(const dcv_geom*);
 int64_t wgrad_tc_ws_bytes(const dcv_geom*);
@@ -84,8 +88,24 @@ int dcv_pack_weight(const dcv_geom* g, int dir, int impl, const float* w, int64_
                     void* out, void* stream) {
   if (int rc = check_geom(g)) return rc;
   DCV_REQUIRE(w && out, "pack_weight: null pointer");
-  if (impl == DCV_IMPL_TC) return pack_weight_tc(g, dir, w, s_l, s_s, s_tap, out, as_stream(stream));
-  return pack_weight_simt(g, dir, w, s_l, s_s, s_tap, (float*)out, as_stream(stream));
+  if (impl == DCV_IMPL_TC) return pack_weight_tc(g, dir, w, s_l, s_s, s_tap, full_window(g), out, as_stream(stream));
+  return pack_weight_simt(g, dir, w, s_l, s_s, s_tap, full_window(g), (float*)out, as_stream(stream));
+}
+
+static int check_window(const dcv_geom* g, int cl_off, int cl_cnt, int cs_off, int cs_cnt) {
+  DCV_REQUIRE(cl_off >= 0 && cl_cnt > 0 && cl_off + cl_cnt <= g->Cl && cs_off >= 0 && cs_cnt > 0 && cs_off + cs_cnt <= g->Cs,
+              "weight window [%d,+%d) x [%d,+%d) outside %d x %d", cl_off, cl_cnt, cs_off, cs_cnt, g->Cl, g->Cs);
+  return 0;
+}
+
+int dcv_pack_weight_sub(const dcv_geom* g, int dir, int impl, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
+                        int cl_off, int cl_cnt, int cs_off, int cs_cnt, int fill_outside, void* out, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  if (int rc = check_window(g, cl_off, cl_cnt, cs_off, cs_cnt)) return rc;
+  DCV_REQUIRE(w && out, "pack_weight_sub: null pointer");
+  WeightWin win; win.cl_off = cl_off; win.cl_cnt = cl_cnt; win.cs_off = cs_off; win.cs_cnt = cs_cnt; win.fill = fill_outside;
+  if (impl == DCV_IMPL_TC) return pack_weight_tc(g, dir, w, s_l, s_s, s_tap, win, out, as_stream(stream));
+  return pack_weight_simt(g, dir, w, s_l, s_s, s_tap, win, (float*)out, as_stream(stream));
 }
 
 int dcv_conv_tc_supported(const dcv_geom* g, int dir) {
@@ -114,6 +134,28 @@ int64_t dcv_wgrad_workspace_bytes(const dcv_geom* g, int impl) {
 int dcv_wgrad_tc_supported(const dcv_geom* g) {
   if (check_geom(g)) return 0;
   return wgrad_tc_supported(g);
+}
+
+int dcv_wgrad_partial(const dcv_geom* g, int impl, int dtype, const void* xl, int64_t ldl, const void* xs, int64_t lds,
+                      void* ws, int64_t ws_bytes, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DCV_REQUIRE(xl && xs && ws, "wgrad_partial: null pointer");
+  DCV_REQUIRE(g->N > 0, "wgrad_partial: empty batch");
+  if (impl == DCV_IMPL_TC) {
+    DCV_REQUIRE(dtype == DCV_BF16, "wgrad: the tcgen05 kernel computes in bf16");
+    return wgrad_tc(g, xl, ldl, xs, lds, nullptr, 0, 0, 0, 0, ws, ws_bytes, as_stream(stream));
+  }
+  return wgrad_simt_partial(g, dtype, xl, ldl, xs, lds, ws, ws_bytes, as_stream(stream));
+}
+
+int dcv_wgrad_reduce_sub(const dcv_geom* g, int impl, const void* ws, float* dw, int64_t s_l, int64_t s_s, int64_t s_tap,
+                         int cl_off, int cl_cnt, int cs_off, int cs_cnt, int accumulate, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  if (int rc = check_window(g, cl_off, cl_cnt, cs_off, cs_cnt)) return rc;
+  DCV_REQUIRE(ws && dw, "wgrad_reduce_sub: null pointer");
+  WeightWin win; win.cl_off = cl_off; win.cl_cnt = cl_cnt; win.cs_off = cs_off; win.cs_cnt = cs_cnt; win.fill = 0;
+  const int splits = impl == DCV_IMPL_TC ? wgrad_tc_splits(g) : wgrad_simt_splits(g);
+  return wgrad_reduce_win((const float*)ws, splits, g, win, dw, s_l, s_s, s_tap, accumulate, as_stream(stream));
 }
 
 int dcv_wgrad(const dcv_geom* g, int impl, int dtype, const void* xl, int64_t ldl, const void* xs, int64_t lds, float* dw,

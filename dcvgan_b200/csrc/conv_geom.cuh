@@ -16,6 +16,22 @@ struct ConvP {
   int scatter;
 };
 
+// Window of a (possibly zero-padded, possibly merged) weight matrix that one master weight tensor occupies:
+// activation channels cl in [cl_off, cl_off+cl_cnt) x cs in [cs_off, cs_off+cs_cnt).  fill: packers write zeros outside.
+struct WeightWin {
+  int cl_off, cl_cnt, cs_off, cs_cnt, fill;
+  __host__ __device__ bool has(int cl, int cs) const {
+    return cl >= cl_off && cl < cl_off + cl_cnt && cs >= cs_off && cs < cs_off + cs_cnt;
+  }
+};
+static inline WeightWin full_window(const dcv_geom* g) {
+  WeightWin w;
+  w.cl_off = 0; w.cl_cnt = g->wCl > 0 ? g->wCl : g->Cl;
+  w.cs_off = 0; w.cs_cnt = g->wCs > 0 ? g->wCs : g->Cs;
+  w.fill = 1;
+  return w;
+}
+
 struct PhaseInfo {
   int Qt, Qh, Qw;       // index-space extents of this phase
   int nt, nh, nw;       // tap counts

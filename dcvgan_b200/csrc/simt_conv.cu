@@ -224,15 +224,15 @@ wgrad_simt_kernel(WgradP p, const T* __restrict__ xl, int64_t ldl, const T* __re
 // dw[cl*s_l + cs*s_s + tap*s_tap] (+)= sum_z partial[z][tap][cl][cs]   (fixed order => deterministic)
 // few splits (large weights): one element per thread
 __global__ void __launch_bounds__(256)
-wgrad_reduce_flat_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, int wCl, int wCs,
+wgrad_reduce_flat_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, WeightWin win,
                          float* __restrict__ dw, int64_t s_l, int64_t s_s, int64_t s_tap, int accumulate) {
   const int64_t total = (int64_t)taps * Cl * Cs;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
-    if (cl >= wCl || cs >= wCs) continue;
+    if (!win.has(cl, cs)) continue;    // zero-padding channels / other sub-weights have no entry in this master weight
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * total + i];
-    float* d = dw + cl * s_l + cs * s_s + tap * s_tap;
+    float* d = dw + (cl - win.cl_off) * s_l + (cs - win.cs_off) * s_s + tap * s_tap;
     *d = accumulate ? (*d + s) : s;
   }
 }
@@ -240,9 +240,8 @@ wgrad_reduce_flat_kernel(const float* __restrict__ partial, int splits, int taps
 // many splits (small weights, huge pixel counts): block = 8 consecutive elements x 32 split lanes; lane y sums splits
 // y, y+32, ... (32-byte sectors), the 32 partial sums are then added in a fixed order.
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, int wCl,
-                    int wCs, float* __restrict__ dw, int64_t s_l, int64_t s_s, int64_t s_tap,
-                    int accumulate) {
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, WeightWin win,
+                    float* __restrict__ dw, int64_t s_l, int64_t s_s, int64_t s_tap, int accumulate) {
   __shared__ float red[32][9];
   const int64_t total = (int64_t)taps * Cl * Cs;
   const int tx = threadIdx.x % 8, ty = threadIdx.x / 8;
@@ -261,8 +260,8 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int
 #pragma unroll
       for (int k = 0; k < 32; ++k) t += red[k][tx];
       const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
-      if (cl < wCl && cs < wCs) {   // zero-padding channels have no master weight
-        float* d = dw + cl * s_l + cs * s_s + tap * s_tap;
+      if (win.has(cl, cs)) {
+        float* d = dw + (cl - win.cl_off) * s_l + (cs - win.cs_off) * s_s + tap * s_tap;
         *d = accumulate ? (*d + t) : t;
       }
     }
@@ -271,13 +270,14 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int
 }
 
 __global__ void pack_weight_simt_kernel(const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap,
-                                        int Cl, int Cs, int wCl, int wCs, int taps, int scatter, float* __restrict__ out) {
+                                        int Cl, int Cs, WeightWin win, int taps, int scatter, float* __restrict__ out) {
   const int64_t total = (int64_t)taps * Cl * Cs;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int tap, cl, cs;
     if (!scatter) { cs = (int)(i % Cs); cl = (int)((i / Cs) % Cl); tap = (int)(i / ((int64_t)Cs * Cl)); }
     else          { cl = (int)(i % Cl); cs = (int)((i / Cl) % Cs); tap = (int)(i / ((int64_t)Cs * Cl)); }
-    out[i] = (cl < wCl && cs < wCs) ? w[cl * s_l + cs * s_s + tap * s_tap] : 0.f;
+    if (win.has(cl, cs)) out[i] = w[(cl - win.cl_off) * s_l + (cs - win.cs_off) * s_s + tap * s_tap];
+    else if (win.fill) out[i] = 0.f;
   }
 }
 
@@ -306,20 +306,23 @@ int conv_simt(const dcv_geom* g, int dir, int dtype, const void* x, int64_t ldx,
   return launch_conv_simt<__nv_bfloat16>(g, dir, x, ldx, wp, y, ldy, act, slope, s);
 }
 
-int wgrad_reduce(const float* partial, int splits, const dcv_geom* g, float* dw, int64_t s_l, int64_t s_s,
-                 int64_t s_tap, int accumulate, cudaStream_t s) {
+int wgrad_reduce_win(const float* partial, int splits, const dcv_geom* g, WeightWin win, float* dw, int64_t s_l,
+                     int64_t s_s, int64_t s_tap, int accumulate, cudaStream_t s) {
   const int taps = g->kt * g->kh * g->kw;
   const int64_t total = (int64_t)taps * g->Cl * g->Cs;
-  const int wl = g->wCl > 0 ? g->wCl : g->Cl, ws_ = g->wCs > 0 ? g->wCs : g->Cs;
   if (splits <= 16) {
     int fb = (int)((total + 255) / 256); if (fb > 148 * 8) fb = 148 * 8;
-    wgrad_reduce_flat_kernel<<<fb, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, wl, ws_, dw, s_l, s_s, s_tap, accumulate);
+    wgrad_reduce_flat_kernel<<<fb, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, win, dw, s_l, s_s, s_tap, accumulate);
     return check_launch("wgrad_reduce");
   }
   int blocks = (int)((total + 7) / 8); if (blocks > 148 * 16) blocks = 148 * 16;
-  wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, g->wCl > 0 ? g->wCl : g->Cl,
-                                             g->wCs > 0 ? g->wCs : g->Cs, dw, s_l, s_s, s_tap, accumulate);
+  wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, win, dw, s_l, s_s, s_tap, accumulate);
   return check_launch("wgrad_reduce");
+}
+
+int wgrad_reduce(const float* partial, int splits, const dcv_geom* g, float* dw, int64_t s_l, int64_t s_s,
+                 int64_t s_tap, int accumulate, cudaStream_t s) {
+  return wgrad_reduce_win(partial, splits, g, full_window(g), dw, s_l, s_s, s_tap, accumulate, s);
 }
 
 int wgrad_simt_splits(const dcv_geom* g) {
@@ -376,6 +379,15 @@ static int launch_wgrad_simt(const dcv_geom* g, const void* xl, int64_t ldl, con
   return check_launch("wgrad_simt");
 }
 
+int wgrad_simt_partial(const dcv_geom* g, int dtype, const void* xl, int64_t ldl, const void* xs, int64_t lds, void* ws,
+                       int64_t ws_bytes, cudaStream_t s) {
+  const int splits = wgrad_simt_splits(g);
+  DCV_REQUIRE(ws_bytes >= wgrad_simt_ws_bytes(g), "wgrad workspace too small: %lld < %lld",
+              (long long)ws_bytes, (long long)wgrad_simt_ws_bytes(g));
+  return dtype == DCV_F32 ? launch_wgrad_simt<float>(g, xl, ldl, xs, lds, (float*)ws, splits, s)
+                          : launch_wgrad_simt<__nv_bfloat16>(g, xl, ldl, xs, lds, (float*)ws, splits, s);
+}
+
 int wgrad_simt(const dcv_geom* g, int dtype, const void* xl, int64_t ldl, const void* xs, int64_t lds,
                float* dw, int64_t s_l, int64_t s_s, int64_t s_tap, int accumulate, void* ws,
                int64_t ws_bytes, cudaStream_t s) {
@@ -389,12 +401,11 @@ int wgrad_simt(const dcv_geom* g, int dtype, const void* xl, int64_t ldl, const 
 }
 
 int pack_weight_simt(const dcv_geom* g, int dir, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
-                     float* out, cudaStream_t s) {
+                     WeightWin win, float* out, cudaStream_t s) {
   const int taps = g->kt * g->kh * g->kw;
   const int64_t total = (int64_t)taps * g->Cl * g->Cs;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weight_simt_kernel<<<blocks, 256, 0, s>>>(w, s_l, s_s, s_tap, g->Cl, g->Cs, g->wCl > 0 ? g->wCl : g->Cl,
-                                                 g->wCs > 0 ? g->wCs : g->Cs, taps, dir == DCV_DIR_SCATTER, out);
+  pack_weight_simt_kernel<<<blocks, 256, 0, s>>>(w, s_l, s_s, s_tap, g->Cl, g->Cs, win, taps, dir == DCV_DIR_SCATTER, out);
   return check_launch("pack_weight_simt");
 }
 

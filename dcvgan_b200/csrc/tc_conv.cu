@@ -120,6 +120,7 @@ struct TcConvP {
   int act; float slope;
   int vec_ok;
   int tmem_cols;
+  int dbg;                               // DCV_TC_DBG (timing experiments only): 1 = stop loading A, 2 = stop loading B after the first ring fill
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -162,7 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0;
+      int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0; int issued = 0;
       for (int jt = 0; jt < f.nt; ++jt) {
         const int ct = t0 * f.mult + f.offt + f.sgn * jt;
         const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
@@ -175,10 +176,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
             for (int kc = 0; kc < p.kchunks; ++kc) {
               mbar_wait(&empty_bar[stage], phase ^ 1u);
-              mbar_expect_tx(&full_bar[stage], (uint32_t)p.tx_bytes);
+              const bool ldA = !(p.dbg & 1) || issued < p.stages, ldB = !(p.dbg & 2) || issued < p.stages;
+              ++issued;
+              mbar_expect_tx(&full_bar[stage], (uint32_t)((ldA ? p.a_bytes : 0) + (ldB ? p.tx_bytes - p.a_bytes : 0)));
               const uint32_t a_dst = sbase + stage * stage_bytes;
-              tma_load_5d(a_dst, &mapA, &full_bar[stage], kc * p.cblk, cw, ch, ct, n0);
-              tma_load_3d(a_dst + p.a_bytes, &mapB, &full_bar[stage], j * p.c.Kc + kc * p.cblk, blockIdx.y * p.bnt, blockIdx.z);
+              if (ldA) tma_load_5d(a_dst, &mapA, &full_bar[stage], kc * p.cblk, cw, ch, ct, n0);
+              if (ldB) tma_load_3d(a_dst + p.a_bytes, &mapB, &full_bar[stage], j * p.c.Kc + kc * p.cblk, blockIdx.y * p.bnt, blockIdx.z);
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
             ++executed;
@@ -649,7 +652,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
 // gather : out[n][tap][k]                 (n < npad, k < Kc)
 // scatter: out[phase][n][j][k]            (j = tap-in-phase index in the kernel's loop order)
 __global__ void __launch_bounds__(256)
-pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap,
+pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap, WeightWin win,
                       int npad, int phases, __nv_bfloat16* __restrict__ out) {
   // one thread per (phase, n, k): it walks the taps of its phase, so the fp32 reads of a thread fall into one or two
   // cache lines (taps are the innermost dimension of the PyTorch layouts) and the bf16 writes of a warp are contiguous in k
@@ -661,10 +664,11 @@ pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int64_t s_l, int64_t
     const int k = (int)(r % c.Kc); const int n = (int)(r / c.Kc);
     const PhaseInfo f = make_phase(c, ph);
     const int ntaps = f.nt * f.nh * f.nw;
-    const bool real = n < c.wN && k < c.wK;
     // gather: reduction channel k is an L channel, produced channel n is an S channel; scatter: swapped
     const int cl = c.scatter ? n : k, cs = c.scatter ? k : n;
-    const float* wb = w + cl * s_l + cs * s_s;
+    const bool real = win.has(cl, cs);
+    if (!real && !win.fill) continue;
+    const float* wb = w + (cl - win.cl_off) * s_l + (cs - win.cs_off) * s_s;
     __nv_bfloat16* ob = out + ((int64_t)ph * npad + n) * ntaps * c.Kc + k;
     int j = 0;
     for (int jt = 0; jt < f.nt; ++jt)
@@ -764,14 +768,14 @@ int64_t packed_weight_tc_bytes(const dcv_geom* g, int dir) {
   return (int64_t)tc_npad(c.Nc) * taps * c.Kc * 2;
 }
 
-int pack_weight_tc(const dcv_geom* g, int dir, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, void* out,
-                   cudaStream_t s) {
+int pack_weight_tc(const dcv_geom* g, int dir, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, WeightWin win,
+                   void* out, cudaStream_t s) {
   DCV_REQUIRE(conv_tc_supported(g, dir), "pack_weight_tc: geometry not supported by the tcgen05 kernel");
   const ConvP c = make_convp(g, dir);
   const int phases = c.scatter ? g->st * g->sh * g->sw : 1;
   const int64_t total = (int64_t)tc_npad(c.Nc) * c.Kc * phases;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weight_tc_kernel<<<blocks, 256, 0, s>>>(c, w, s_l, s_s, s_tap, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
+  pack_weight_tc_kernel<<<blocks, 256, 0, s>>>(c, w, s_l, s_s, s_tap, win, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
   return check_launch("pack_weight_tc");
 }
 
@@ -805,6 +809,7 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   {
     const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * (npad / p.bnt) * phases;
     if (p.bnt <= 256 && p.bn * 2 <= 256 && c.N >= 2 * p.bn && ctas >= 2 * 148 * 2) p.mt = 2;
+    if (getenv("DCV_TC_MT1")) p.mt = 1;
   }
   p.tiles_n = ceil_div(c.N, p.bn * p.mt);
   p.a_bytes = p.mt * 128 * p.cblk * 2;
@@ -816,6 +821,8 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   // by TMEM allocation, barrier setup and the store epilogue): split the ~216 KB of shared memory between as many
   // CTAs as TMEM (512 columns) allows, up to 4, keeping at least 2 stages each.
   int ctas_per_sm = 512 / p.tmem_cols; if (ctas_per_sm > 4) ctas_per_sm = 4; if (ctas_per_sm < 1) ctas_per_sm = 1;
+  { const char* e = getenv("DCV_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  if (const char* e = getenv("DCV_TC_CPS")) { const int v = atoi(e); if (v >= 1 && v < ctas_per_sm) ctas_per_sm = v; }
   {
     const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * (npad / p.bnt) * phases;
     const int need = (int)((ctas + 147) / 148);          // CTAs that can actually share an SM
@@ -943,6 +950,12 @@ int64_t wgrad_tc_ws_bytes(const dcv_geom* g) {
 int wgrad_reduce(const float* partial, int splits, const dcv_geom* g, float* dw, int64_t s_l, int64_t s_s,
                  int64_t s_tap, int accumulate, cudaStream_t s);
 
+int wgrad_tc_splits(const dcv_geom* g) {
+  TcWgradP p; int splits;
+  wgrad_tc_plan(g, &p, &splits);
+  return splits;
+}
+
 int wgrad_tc(const dcv_geom* g, const void* xl, int64_t ldl, const void* xs, int64_t lds, float* dw, int64_t s_l,
              int64_t s_s, int64_t s_tap, int accumulate, void* ws, int64_t ws_bytes, cudaStream_t s) {
   DCV_REQUIRE(wgrad_tc_supported(g), "wgrad_tc: geometry not supported by the tcgen05 kernel");
@@ -966,6 +979,7 @@ int wgrad_tc(const dcv_geom* g, const void* xl, int64_t ldl, const void* xs, int
   wgrad_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mapL, mapS, p, (float*)ws);
   rc = check_launch("wgrad_tc");
   if (rc) return rc;
+  if (!dw) return 0;   // partial sums only; the caller reduces them (dcv_wgrad_reduce_sub)
   return wgrad_reduce((const float*)ws, splits, g, dw, s_l, s_s, s_tap, accumulate, s);
 }
 

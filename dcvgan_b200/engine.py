@@ -183,6 +183,71 @@ class Block:
         return dz
 
 
+class MergedStem:
+    """The two stem convolutions of idis / vdis (conv_g on the geometry channels, conv_c on the colour channels, both
+    + LeakyReLU(0.2), outputs concatenated as [hc | hg]: discriminator.py:79-90,121-124,180-193,225-228) run as ONE
+    convolution over the concatenated input [xg | xc] with a block-structured weight - conv_g occupies input channels
+    [0,cg) x output channels [ndf/2, ndf), conv_c input channels [cg, cg+cc) x output channels [0, ndf/2), zeros
+    elsewhere.  Same arithmetic (the zero blocks contribute exact zeros to the fp32 accumulators); one 16/32-channel
+    operand instead of two zero-padded ones, a 2x wider N tile, and channel halves that need not be multiples of 16
+    (vdis.ndf 48 in config/surreal-segm.yml).  bf16 / tcgen05 path only."""
+
+    def __init__(self, mk, cg, cc, ndf, conv_g, conv_c, noise=None):
+        self.cg, self.cc, self.ndf = cg, cc, ndf
+        self.conv_g, self.conv_c, self.noise = conv_g, conv_c, noise
+        self.spec = mk(cg + cc, ndf)
+        half = ndf // 2
+        self.windows = [(conv_g, 0, half), (conv_c, cg, 0)]      # (module, cl_off, cs_off)
+
+    def _packed(self, g, direction, impl):
+        parts = [(m.weight, cl, cs) for m, cl, cs in self.windows]
+        if WCACHE is None:
+            return ops.pack_weight_merged(g, direction, impl, parts)
+        per = WCACHE.setdefault(id(self.conv_g.weight), {})
+        key = ("merged", g.key(), direction, impl)
+        wp = per.get(key)
+        if wp is None:
+            wp = per[key] = ops.pack_weight_merged(g, direction, impl, parts)
+        return wp
+
+    def forward(self, xg, xc, out, training, rng_, save=True):
+        cg, cin = self.cg, self.cg + self.cc
+        cat = Act.empty(xg.n, xg.t, xg.h, xg.w, cin, xg.dtype)
+        if self.noise is not None and self.noise[0]:                             # draw order: geometry, then colour
+            ops.add_noise(xg, rng_.noise_for(xg), float(self.noise[1]), cat.ch(0, cg))
+            ops.add_noise(xc, rng_.noise_for(xc), float(self.noise[1]), cat.ch(cg, cin))
+        else:
+            ops.copy_cl(xg, cat.ch(0, cg))
+            ops.copy_cl(xc, cat.ch(cg, cin))
+        g = self.spec.geom(cat.n, cat.spatial, cat.cp, out.cp)
+        impl = ops.choose_conv_impl(g, self.spec.fwd_dir, cat)
+        ops.conv(g, self.spec.fwd_dir, impl, cat.padded_to(cat.cp), self._packed(g, self.spec.fwd_dir, impl),
+                 out.padded_to(out.cp), ACT_LEAKY, 0.2)
+        return {"g": g, "x": cat if save else None, "a": out}
+
+    def backward(self, ctx, da, sink, need_dx, need_dw):
+        """Returns (dxg, dxc): channel slices of one buffer, or (None, None)."""
+        g, a, cat = ctx["g"], ctx["a"], ctx["x"]
+        dz = Act.empty(a.n, a.t, a.h, a.w, a.c, a.dtype)
+        ops.act_bwd(da, a, ACT_LEAKY, 0.2, dz)
+        dzp = dz.padded_to(dz.cp)
+        if need_dw:
+            parts = []
+            for m, cl, cs in self.windows:
+                dw, acc = sink.get(m.weight)
+                parts.append((dw, cl, cs, acc))
+            ops.wgrad_merged(g, cat.padded_to(cat.cp), dzp, parts)
+        if not need_dx:
+            return None, None
+        dcat = Act.empty(cat.n, cat.t, cat.h, cat.w, cat.c, cat.dtype)
+        impl = ops.choose_conv_impl(g, self.spec.bwd_dir, dzp)
+        ops.conv(g, self.spec.bwd_dir, impl, dzp, self._packed(g, self.spec.bwd_dir, impl), dcat.padded_to(dcat.cp))
+        return dcat.ch(0, self.cg), dcat.ch(self.cg, self.cg + self.cc)
+
+
+MERGE_STEMS = True   # bf16 path; tests flip it to compare against the two-convolution form
+
+
 def _k2(k):
     return (1, k, k)
 
@@ -357,6 +422,9 @@ class DisPlan:
             self.stem_c = Block(mk(cc, ndf // 2), mod.conv_c[0], None, ACT_LEAKY, 0.2)
         else:
             mk = conv3d_spec
+        self.merged = None
+        if kind in ("idis", "vdis"):
+            self.merged = MergedStem(mk, cg, cc, ndf, self.stem_g.conv, self.stem_c.conv, self.stem_g.noise)
         if kind in ("idis", "vdis"):
             self.main = [Block(mk(ndf, ndf * 2), m[1], m[2], ACT_LEAKY, 0.2, noise=nz),
                          Block(mk(ndf * 2, ndf * 4), m[5], m[6], ACT_LEAKY, 0.2, noise=nz),
@@ -379,8 +447,11 @@ class DisPlan:
             sp = self.stem_g.spec.out_spatial(xg.spatial)
             h = Act.empty(xg.n, sp[0], sp[1], sp[2], ndf, dtype)
             # Noise draw order: geometry stem first, then colour (discriminator.py:121-122); cat = [hc, hg] (:124)
-            ctx["stem_g"] = self.stem_g.forward(xg, h.ch(ndf // 2, ndf), training, rng_, save)
-            ctx["stem_c"] = self.stem_c.forward(xc, h.ch(0, ndf // 2), training, rng_, save)
+            if MERGE_STEMS and dtype == torch.bfloat16:
+                ctx["stem"] = self.merged.forward(xg, xc, h, training, rng_, save)
+            else:
+                ctx["stem_g"] = self.stem_g.forward(xg, h.ch(ndf // 2, ndf), training, rng_, save)
+                ctx["stem_c"] = self.stem_c.forward(xc, h.ch(0, ndf // 2), training, rng_, save)
         mctx = []
         for blk in self.main:
             sp = blk.spec.out_spatial(h.spatial)
@@ -411,6 +482,10 @@ class DisPlan:
             ops.tdiff_bwd(da, dxg, False)
             return dxg, None
         ndf = self.mod.ndf
+        if "stem" in ctx:
+            if need_dx or need_dw:
+                return self.merged.backward(ctx["stem"], da, sink, need_dx, need_dw)
+            return None, None
         dxg = dxc = None
         if need_dx:
             xg, xc = ctx["stem_g"]["x"], ctx["stem_c"]["x"]

@@ -195,6 +195,43 @@ def pack_weight(spec, g, direction, impl, weight):
     return out
 
 
+def pack_weight_merged(g, direction, impl, parts):
+    """One packed matrix out of several master weights that each own a window of it (the two stem convolutions of a
+    discriminator run as ONE convolution over [xg | xc] -> [hc | hg], discriminator.py:79-90,121-124,180-193,225-228).
+    parts: [(conv weight (cs_cnt, cl_cnt, *k), cl_off, cs_off)]; everything outside the windows is zero."""
+    nbytes = lib().dcv_packed_weight_bytes(C.byref(g), direction, impl)
+    if nbytes < 0:
+        check(-1)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=parts[0][0].device)
+    taps = g.kt * g.kh * g.kw
+    for i, (weight, cl_off, cs_off) in enumerate(parts):
+        w = weight.detach()
+        assert w.is_contiguous() and w.dtype == torch.float32
+        cs_cnt, cl_cnt = w.shape[0], w.shape[1]
+        check(lib().dcv_pack_weight_sub(C.byref(g), direction, impl, w.data_ptr(), taps, cl_cnt * taps, 1, cl_off, cl_cnt,
+                                        cs_off, cs_cnt, int(i == 0), out.data_ptr(), _stream()))
+    return out
+
+
+def wgrad_merged(g, xl, xs, parts, impl=None):
+    """Weight gradient of a merged convolution: one pass over the activations leaves the split partial sums in the
+    workspace, then every master weight reduces its own window.  parts: [(dw (cs_cnt, cl_cnt, *k), cl_off, cs_off, accumulate)]"""
+    impl = choose_wgrad_impl(g, xl, xs) if impl is None else impl
+    if TRACE is not None:
+        TRACE.append(("wgrad", g.key(), 0, impl, xl.ld, xs.ld, xl.c, xs.c))
+    nbytes = lib().dcv_wgrad_workspace_bytes(C.byref(g), impl)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=xl.device)
+    lp, ldl, _, _ = cl_view(xl)
+    sp, lds, _, _ = cl_view(xs)
+    check(lib().dcv_wgrad_partial(C.byref(g), impl, dcv_dtype(xl), lp, ldl, sp, lds, ws.data_ptr(), nbytes, _stream()))
+    taps = g.kt * g.kh * g.kw
+    for dw, cl_off, cs_off, acc in parts:
+        assert dw.is_contiguous() and dw.dtype == torch.float32
+        cs_cnt, cl_cnt = dw.shape[0], dw.shape[1]
+        check(lib().dcv_wgrad_reduce_sub(C.byref(g), impl, ws.data_ptr(), dw.data_ptr(), taps, cl_cnt * taps, 1, cl_off,
+                                         cl_cnt, cs_off, cs_cnt, int(acc), _stream()))
+
+
 TRACE = None   # set to a list to record every conv / wgrad call (tools/layer_bench.py)
 
 

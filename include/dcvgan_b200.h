@@ -88,6 +88,14 @@ int64_t dcv_packed_weight_bytes(const dcv_geom* g, int dir, int impl);
 int dcv_pack_weight(const dcv_geom* g, int dir, int impl, const float* w, int64_t s_l, int64_t s_s,
                     int64_t s_tap, void* out, void* stream);
 
+/* Same, for ONE master weight that occupies only a window of the packed matrix - activation channels
+ * [cl_off, cl_off+cl_cnt) x [cs_off, cs_off+cs_cnt) - as when the two stem convolutions of a discriminator
+ * (conv_g on the geometry channels, conv_c on the colour channels, discriminator.py:79-90,180-193) are run as a single
+ * convolution over the concatenated input [xg | xc] producing [hc | hg].  `w` is indexed with window-local channels.
+ * fill_outside != 0 zero-fills everything outside the window (first call), 0 leaves it untouched (further calls). */
+int dcv_pack_weight_sub(const dcv_geom* g, int dir, int impl, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
+                        int cl_off, int cl_cnt, int cs_off, int cs_cnt, int fill_outside, void* out, void* stream);
+
 /* ---- convolution family ---------------------------------------------------------------------
  * dcv_conv: y = act(correlate(x, wp)); replaces every nn.Conv2d / nn.ConvTranspose2d / nn.Conv3d
  * forward on the path (generator.py:61-73,174,204,240,274; discriminator.py:81-101,182-206,288-305)
@@ -105,6 +113,13 @@ int dcv_wgrad_tc_supported(const dcv_geom* g);
 int dcv_wgrad(const dcv_geom* g, int impl, int dtype, const void* xl, int64_t ldl, const void* xs,
               int64_t lds, float* dw, int64_t s_l, int64_t s_s, int64_t s_tap, int accumulate,
               void* ws, int64_t ws_bytes, void* stream);
+
+/* Two-step form of dcv_wgrad for merged layers: dcv_wgrad_partial leaves the split partial sums in `ws`;
+ * dcv_wgrad_reduce_sub reduces the window of one master weight out of them (call once per master weight). */
+int dcv_wgrad_partial(const dcv_geom* g, int impl, int dtype, const void* xl, int64_t ldl, const void* xs, int64_t lds,
+                      void* ws, int64_t ws_bytes, void* stream);
+int dcv_wgrad_reduce_sub(const dcv_geom* g, int impl, const void* ws, float* dw, int64_t s_l, int64_t s_s, int64_t s_tap,
+                         int cl_off, int cl_cnt, int cs_off, int cs_cnt, int accumulate, void* stream);
 
 /* ---- BatchNorm (training + eval), activation, dropout, noise --------------------------------
  * Replaces nn.BatchNorm2d/3d (+ReLU/LeakyReLU, +Dropout2d between them, +Noise before the next

@@ -7,7 +7,8 @@ CPU oracle.  GAN trajectories are chaotic point-wise: an fp32 run whose initial 
 (relative) drifts from the unperturbed fp32 run by up to ~0.46 in the running mean of loss_vdis within 200 steps
 (measured, profiles/r1_curves.md).  Stated tolerance, on running means over 20 iterations:
   * first 30 windows (before the trajectories decorrelate): |bf16 - fp32| <= max(5 % of the fp32 value, 0.05);
-  * all 181 windows: |bf16 - fp32| <= max(2 x the drift of the 1e-6-perturbed fp32 control run, 0.05) per curve.
+  * all 181 windows: |bf16 - fp32| <= max(2 x the largest drift among three perturbed fp32 control runs (initial
+    weights scaled by 1+1e-6, 1+1e-3, 1-1e-3), 0.05) per curve.
 """
 import numpy as np
 import pytest
@@ -58,11 +59,15 @@ def test_bf16_loss_curves_track_fp32(tmp_path):
     print("max |mean20(bf16) - mean20(fp32)| per curve:", {n: float(dev[:, i].max()) for i, n in enumerate(names)})
     for lo, hi in ((0, 30), (30, 80), (80, STEPS - WINDOW + 1)):
         print(f"  window starts {lo}..{hi}: max dev", [float(f"{x:.3f}") for x in dev[lo:hi].max(axis=0)], "fp32 mean", [float(f"{x:.3f}") for x in mr[lo:hi].mean(axis=0)])
-    # control: fp32 against fp32 with the initial weights perturbed by 1e-6 relative (the chaotic spread of the GAN itself)
-    init2 = {k: {a: (b * (1 + 1e-6) if b.dtype == torch.float32 else b.clone()) for a, b in v.items()} for k, v in init.items()}
-    ctl = _running_mean(_run(cfg, init2, "fp32", STEPS, tmp_path), WINDOW)
-    cdev = np.abs(ctl - mr)
-    print("control (fp32 vs 1e-6-perturbed fp32) max dev per curve:", [float(f"{x:.3f}") for x in cdev.max(axis=0)])
+    # controls: fp32 against fp32 with the initial weights perturbed - by 1e-6 relative (the chaotic spread of the GAN
+    # itself) and by +-1e-3 relative (a perturbation of the size bf16 storage applies, half an ulp = 2e-3); the envelope
+    # of their drifts is what any bf16 run has to be compared with once the trajectories have decorrelated
+    cdevs = []
+    for eps in (1e-6, 1e-3, -1e-3):
+        init2 = {k: {a: (b * (1 + eps) if b.dtype == torch.float32 else b.clone()) for a, b in v.items()} for k, v in init.items()}
+        cdevs.append(np.abs(_running_mean(_run(cfg, init2, "fp32", STEPS, tmp_path), WINDOW) - mr))
+        print(f"control (fp32 vs {eps:+.0e}-perturbed fp32) max dev per curve:", [float(f"{x:.3f}") for x in cdevs[-1].max(axis=0)])
+    cdev = np.maximum.reduce(cdevs)
     print("final means fp32:", mr[-1].tolist(), "bf16:", mg[-1].tolist())
     print("first-step losses fp32:", ref[0].tolist(), "bf16:", got[0].tolist())
     early_tol = np.maximum(0.05 * np.abs(mr[:30]), 0.05)
