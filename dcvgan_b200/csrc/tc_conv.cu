@@ -87,6 +87,52 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- lean MMA issue ------------------------------------------------------------------------------
+// Measured with tools/mma_probe.cu (profiles/r1h_mma_probe.md): a tcgen05.mma stream issued from inside `if (lane == 0)`
+// with 64-bit descriptors rebuilt per instruction costs ~100-270 cycles of the issuing thread per MMA (R2UR moves and a
+// compiler-generated "for each distinct lane value" loop around every UTCHMMA) - 25-40 % of the tensor pipe - while the
+// same stream issued from warp-uniform code (every lane runs the loop, one elected lane issues, descriptors kept as
+// 32-bit halves in uniform registers, K steps unrolled) retires back to back: 2160 TFLOP/s from one warp at N = 128.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// descriptor halves: lo = start>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version 1 (bit 46) | layout (bits 61..63)
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint32_t sdesc_hi(uint32_t sbo_bytes, uint32_t layout) { return (sbo_bytes >> 4) | (1u << 14) | (layout << 29); }
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// one pipeline stage of conv_tc: KS K-steps of 16 channels (32 bytes = +2 in descriptor units) for MT stacked M tiles
+template <int KS>
+__device__ __forceinline__ void conv_issue_stage(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                                 uint32_t accum, int mt, uint32_t a_tile16, uint32_t bnt) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    umma_lohi(tmem_d, alo + 2 * k, hi, blo + 2 * k, hi, idesc, k == 0 ? accum : 1u);
+    if (mt == 2) umma_lohi(tmem_d + bnt, alo + a_tile16 + 2 * k, hi, blo + 2 * k, hi, idesc, k == 0 ? accum : 1u);
+  }
+}
+
+// one pixel stage of wgrad_tc for one accumulator tile: KS steps of 16 pixels
+template <int KS>
+__device__ __forceinline__ void wgrad_issue(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                            uint32_t kstepA16, uint32_t kstepB16, uint32_t idesc, uint32_t accum) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k)
+    umma_lohi(tmem_d, alo + k * kstepA16, ahi, blo + k * kstepB16, bhi, idesc, k == 0 ? accum : 1u);
+}
+
 // shared-memory matrix descriptor (sm_100 "version 1"); see DESIGN.md for the field map
 //   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle mode
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -132,7 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __shared__ uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_slot;
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0), lane = threadIdx.x % 32;   // warp-uniform for the compiler
   const PhaseInfo f = make_phase(p.c, blockIdx.z);
 
   int tile = blockIdx.x;
@@ -162,72 +208,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0; int issued = 0;
-      for (int jt = 0; jt < f.nt; ++jt) {
-        const int ct = t0 * f.mult + f.offt + f.sgn * jt;
-        const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
-        for (int jh = 0; jh < f.nh; ++jh) {
-          const int ch = h0 * f.mulh + f.offh + f.sgn * jh;
-          const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
-          for (int jw = 0; jw < f.nw; ++jw, ++j) {
-            const int cw = w0 * f.mulw + f.offw + f.sgn * jw;
-            const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
-            if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-              mbar_wait(&empty_bar[stage], phase ^ 1u);
-              const bool ldA = !(p.dbg & 1) || issued < p.stages, ldB = !(p.dbg & 2) || issued < p.stages;
-              ++issued;
+    // TMA producer.  Warp-uniform loop (all lanes wait on the barrier), one elected lane issues.
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0; int issued = 0;
+    for (int jt = 0; jt < f.nt; ++jt) {
+      const int ct = t0 * f.mult + f.offt + f.sgn * jt;
+      const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
+      for (int jh = 0; jh < f.nh; ++jh) {
+        const int ch = h0 * f.mulh + f.offh + f.sgn * jh;
+        const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
+        for (int jw = 0; jw < f.nw; ++jw, ++j) {
+          const int cw = w0 * f.mulw + f.offw + f.sgn * jw;
+          const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
+          if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            const bool ldA = !(p.dbg & 1) || issued < p.stages, ldB = !(p.dbg & 2) || issued < p.stages;
+            ++issued;
+            if (leader) {
               mbar_expect_tx(&full_bar[stage], (uint32_t)((ldA ? p.a_bytes : 0) + (ldB ? p.tx_bytes - p.a_bytes : 0)));
               const uint32_t a_dst = sbase + stage * stage_bytes;
               if (ldA) tma_load_5d(a_dst, &mapA, &full_bar[stage], kc * p.cblk, cw, ch, ct, n0);
               if (ldB) tma_load_3d(a_dst + p.a_bytes, &mapB, &full_bar[stage], j * p.c.Kc + kc * p.cblk, blockIdx.y * p.bnt, blockIdx.z);
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            ++executed;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
+          ++executed;
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
-      const uint32_t sbo = 8u * (uint32_t)p.cblk * 2u;
-      const uint32_t a_tile_bytes = 128u * (uint32_t)p.cblk * 2u;
-      int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0; uint32_t accum = 0;
-      for (int jt = 0; jt < f.nt; ++jt) {
-        const int ct = t0 * f.mult + f.offt + f.sgn * jt;
-        const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
-        for (int jh = 0; jh < f.nh; ++jh) {
-          const int ch = h0 * f.mulh + f.offh + f.sgn * jh;
-          const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
-          for (int jw = 0; jw < f.nw; ++jw, ++j) {
-            const int cw = w0 * f.mulw + f.offw + f.sgn * jw;
-            const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
-            if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-              mbar_wait(&full_bar[stage], phase);
-              tc_fence_after();
-              const uint32_t a_src = sbase + stage * stage_bytes;
-              const uint32_t b_src = a_src + p.a_bytes;
-              for (int k = 0; k < p.cblk / 16; ++k) {
-                const uint64_t bd = make_sdesc(b_src + k * 32, 16, sbo, p.swz_layout);
-                for (int m = 0; m < p.mt; ++m) {
-                  const uint64_t ad = make_sdesc(a_src + m * a_tile_bytes + k * 32, 16, sbo, p.swz_layout);
-                  umma_bf16(tmem_base + m * p.bnt, ad, bd, idesc, accum);
-                }
-                accum = 1;
-              }
+    // MMA issuer (see "lean MMA issue" above): uniform control flow, elected lane issues and commits
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
+    const uint32_t dhi = sdesc_hi(8u * (uint32_t)p.cblk * 2u, (uint32_t)p.swz_layout);
+    const uint32_t a_tile16 = (128u * (uint32_t)p.cblk * 2u) >> 4;
+    int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0; uint32_t accum = 0;
+    for (int jt = 0; jt < f.nt; ++jt) {
+      const int ct = t0 * f.mult + f.offt + f.sgn * jt;
+      const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
+      for (int jh = 0; jh < f.nh; ++jh) {
+        const int ch = h0 * f.mulh + f.offh + f.sgn * jh;
+        const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
+        for (int jw = 0; jw < f.nw; ++jw, ++j) {
+          const int cw = w0 * f.mulw + f.offw + f.sgn * jw;
+          const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
+          if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_src = sbase + stage * stage_bytes;
+            const uint32_t alo = sdesc_lo(a_src, 16), blo = sdesc_lo(a_src + p.a_bytes, 16);
+            if (leader) {
+              if (p.cblk == 64) conv_issue_stage<4>(tmem_base, alo, blo, dhi, idesc, accum, p.mt, a_tile16, (uint32_t)p.bnt);
+              else if (p.cblk == 32) conv_issue_stage<2>(tmem_base, alo, blo, dhi, idesc, accum, p.mt, a_tile16, (uint32_t)p.bnt);
+              else conv_issue_stage<1>(tmem_base, alo, blo, dhi, idesc, accum, p.mt, a_tile16, (uint32_t)p.bnt);
               umma_commit(&empty_bar[stage]);
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            ++executed;
+            accum = 1;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
+          ++executed;
         }
       }
-      umma_commit(&tmem_full_bar);
     }
+    if (leader) umma_commit(&tmem_full_bar);
     __syncwarp();
   } else {
     // epilogue: TMEM lane quarter = warp % 4 (hardware restriction), row = quarter*32 + lane
@@ -297,7 +343,7 @@ conv_tc_g4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t empty_tile_flag;
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0), lane = threadIdx.x % 32;   // warp-uniform for the compiler
   const PhaseInfo f = make_phase(p.c, blockIdx.z);
   int tile = blockIdx.x;
   const int tw = tile % p.tiles_w; tile /= p.tiles_w;
@@ -349,10 +395,8 @@ conv_tc_g4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const uint32_t mask = __ballot_sync(0xffffffffu, live) & 0xFu;
       if (mask == 0u) continue;                 // every tap of this group lies in the padding (same test in the MMA warp)
       const int nlive = __popc(mask);
-      if (lane == 0) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], (uint32_t)(nlive * a_tap_bytes + p.bnt * 128));
-      }
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (lane == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(nlive * a_tap_bytes + p.bnt * 128));
       __syncwarp();
       const uint32_t a_dst = sbase + stage * stage_bytes;
       if (live) tma_load_5d(a_dst + lane * a_tap_bytes, &mapA, &full_bar[stage], 0, cw, ch, ct, n0);
@@ -362,6 +406,8 @@ conv_tc_g4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
+    const bool leader = elect_one();
+    const uint32_t ahi = sdesc_hi(256, 6), bhi = sdesc_hi(1024, 2);   // A: 32-byte rows / 32B swizzle, B: 128-byte rows / 128B swizzle
     int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
     for (int gq = 0; gq < ngroups; ++gq) {
       const int j = gq * TAPG + lane;
@@ -369,26 +415,24 @@ conv_tc_g4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const bool live = lane < TAPG && j < ntaps && tap_coords(j, ct, ch, cw);
       const uint32_t mask = __ballot_sync(0xffffffffu, live) & 0xFu;
       if (mask == 0u) continue;
-      if (lane == 0) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t a_src = sbase + stage * stage_bytes;
-        const uint32_t b_src = a_src + TAPG * a_tap_bytes;
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t a_src = sbase + stage * stage_bytes;
+      const uint32_t alo = sdesc_lo(a_src, 16), blo = sdesc_lo(a_src + TAPG * a_tap_bytes, 16);
+      if (leader) {
+#pragma unroll
         for (int jj = 0; jj < TAPG; ++jj) {
           if (!((mask >> jj) & 1u)) continue;
-          const uint64_t bd = make_sdesc(b_src + jj * 32, 16, 1024, 2);
-          for (int m = 0; m < p.mt; ++m) {
-            const uint64_t ad = make_sdesc(a_src + jj * a_tap_bytes + m * (128 * 32), 16, 256, 6);
-            umma_bf16(tmem_base + m * p.bnt, ad, bd, idesc, accum);
-          }
+          umma_lohi(tmem_base, alo + jj * (a_tap_bytes >> 4), ahi, blo + 2 * jj, bhi, idesc, accum);
+          if (p.mt == 2) umma_lohi(tmem_base + p.bnt, alo + jj * (a_tap_bytes >> 4) + ((128 * 32) >> 4), ahi, blo + 2 * jj, bhi, idesc, accum);
           accum = 1;
         }
         umma_commit(&empty_bar[stage]);
       }
-      __syncwarp();
+      accum = 1;
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
-    if (lane == 0) {
+    if (leader) {
       if (accum == 0) {                 // no tap touched real pixels: the tile is all zeros, nothing was accumulated
         empty_tile_flag = 1u;
         mbar_arrive(&tmem_full_bar);    // plain arrive (release) so that the flag is visible to the epilogue
@@ -522,7 +566,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
   __shared__ uint32_t tmem_slot;
 
   const dcv_geom& g = p.g;
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0), lane = threadIdx.x % 32;   // warp-uniform for the compiler
   const int tile0 = blockIdx.x * p.G;                       // first 128-row tile of this CTA
   const int tiles_total = (p.blocksA_total + p.nA - 1) / p.nA;
   int Gcur = tiles_total - tile0; if (Gcur > p.G) Gcur = p.G;
@@ -563,10 +607,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
       const int w0 = (int)(q % p.tiles_w) * p.bw; q /= p.tiles_w;
       const int h0 = (int)(q % p.tiles_h) * p.bh; q /= p.tiles_h;
       const int t0 = (int)(q % p.tiles_t) * p.bt; const int n0 = (int)(q / p.tiles_t) * p.bn;
-      if (lane == 0) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], (uint32_t)(blkB_bytes * nbB + blkA_bytes * blocksA_here));
-      }
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (lane == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(blkB_bytes * nbB + blkA_bytes * blocksA_here));
       __syncwarp();
       const uint32_t s_dst = sbase + stage * stage_bytes;
       const uint32_t a_dst = s_dst + p.nbB * blkB_bytes;
@@ -586,31 +628,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.Ns, 1, 1);
-      const uint32_t kstepA = 16u * (uint32_t)p.cbA * 2u, kstepB = 16u * (uint32_t)p.cbB * 2u;   // bytes per 16 pixels
-      const uint32_t sboA = 8u * (uint32_t)p.cbA * 2u, sboB = 8u * (uint32_t)p.cbB * 2u;
-      int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
-      for (int64_t pt = pt_begin; pt < pt_end; ++pt) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t s_src = sbase + stage * stage_bytes;
-        const uint32_t a_src = s_src + p.nbB * blkB_bytes;
+    // MMA issuer: uniform control flow, elected lane issues (see "lean MMA issue")
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc(128, p.Ns, 1, 1);
+    const uint32_t kstepA16 = (16u * (uint32_t)p.cbA * 2u) >> 4, kstepB16 = (16u * (uint32_t)p.cbB * 2u) >> 4;   // 16 pixels, in 16-byte units
+    const uint32_t ahi = sdesc_hi(8u * (uint32_t)p.cbA * 2u, (uint32_t)p.layA), bhi = sdesc_hi(8u * (uint32_t)p.cbB * 2u, (uint32_t)p.layB);
+    const uint32_t tileA16 = (uint32_t)(p.nA * blkA_bytes) >> 4;
+    int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
+    for (int64_t pt = pt_begin; pt < pt_end; ++pt) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t s_src = sbase + stage * stage_bytes;
+      const uint32_t blo = sdesc_lo(s_src, (uint32_t)blkB_bytes), alo = sdesc_lo(s_src + p.nbB * blkB_bytes, (uint32_t)blkA_bytes);
+      if (leader) {
         for (int gi = 0; gi < Gcur; ++gi) {
-          uint32_t acc = accum;
-          for (int k = 0; k < p.pix / 16; ++k) {
-            const uint64_t ad = make_sdesc(a_src + gi * p.nA * blkA_bytes + k * kstepA, (uint32_t)blkA_bytes, sboA, p.layA);
-            const uint64_t bd = make_sdesc(s_src + k * kstepB, (uint32_t)blkB_bytes, sboB, p.layB);
-            umma_bf16(tmem_base + gi * p.Ns, ad, bd, idesc, acc);
-            acc = 1;
-          }
+          const uint32_t d = tmem_base + gi * p.Ns, a0 = alo + gi * tileA16;
+          if (p.pix == 128) wgrad_issue<8>(d, a0, ahi, blo, bhi, kstepA16, kstepB16, idesc, accum);
+          else if (p.pix == 64) wgrad_issue<4>(d, a0, ahi, blo, bhi, kstepA16, kstepB16, idesc, accum);
+          else wgrad_issue<2>(d, a0, ahi, blo, bhi, kstepA16, kstepB16, idesc, accum);
         }
-        accum = 1;
         umma_commit(&empty_bar[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(&tmem_full_bar);
+      accum = 1;
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
+    if (leader) umma_commit(&tmem_full_bar);
     __syncwarp();
   } else {
     const int quarter = warp % 4;
