@@ -55,6 +55,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 __device__ __forceinline__ void tmap_prefetch(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -166,6 +176,8 @@ struct TcConvP {
   int act; float slope;
   int vec_ok;
   int tmem_cols;
+  int ntn, items, acc_cols;              // persistent kernel: N tiles, work items, TMEM columns of one accumulator set
+  int tma_store;                         // persistent kernel: epilogue through shared memory + TMA store
   int dbg;                               // DCV_TC_DBG (timing experiments only): 1 = stop loading A, 2 = stop loading B after the first ring fill
 };
 
@@ -321,6 +333,295 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ conv_tc, persistent
+// One CTA per SM walks the work items (tile = blockIdx.x + i * gridDim.x); the shared-memory ring runs continuously
+// across items and TMEM holds two accumulator sets, so the store epilogue of item i overlaps the main loop of item i+1
+// and TMEM allocation / barrier set-up happen once per SM instead of once per tile.  With the lean issue path a single
+// MMA warp saturates the tensor pipe, which the first attempt at this kernel (profiles/experiments, r1d) could not.
+struct TileCoord { int ph, ntile, w0, h0, t0, n0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const TcConvP& p, int item) {
+  TileCoord t;
+  int r = item;
+  const int tw = r % p.tiles_w; r /= p.tiles_w;
+  const int th = r % p.tiles_h; r /= p.tiles_h;
+  const int tt = r % p.tiles_t; r /= p.tiles_t;
+  const int tn = r % p.tiles_n; r /= p.tiles_n;
+  t.ntile = r % p.ntn; t.ph = r / p.ntn;
+  t.w0 = tw * p.bw; t.h0 = th * p.bh; t.t0 = tt * p.bt; t.n0 = tn * p.bn * p.mt;
+  return t;
+}
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16 consecutive output channels of one row: activation, bf16, two 16-byte stores (or guarded scalar stores)
+__device__ __forceinline__ void store_row16(const uint32_t* v, __nv_bfloat16* yrow, int c0, int Nc, int vec_ok, int act, float slope) {
+  if (c0 >= Nc) return;
+  if (vec_ok && c0 + 16 <= Nc) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = apply_act(__uint_as_float(v[2 * i]), act, slope);
+      const float b = apply_act(__uint_as_float(v[2 * i + 1]), act, slope);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+      pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
+    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (c0 + i < Nc) yrow[c0 + i] = __float2bfloat16_rn(apply_act(__uint_as_float(v[i]), act, slope));
+  }
+}
+
+// number of taps of a tile that touch real pixels (the skip test is separable per dimension); >= 1 by convention
+// (a tile whose every tap lies in the padding still runs its last tap on an all-zero box so that TMEM is written)
+__device__ __forceinline__ int live_taps(const TcConvP& p, const PhaseInfo& f, const TileCoord& tc) {
+  int lt = 0, lh = 0, lw = 0;
+  for (int jt = 0; jt < f.nt; ++jt) { const int c = tc.t0 * f.mult + f.offt + f.sgn * jt; lt += !((c + (p.bt - 1) * f.mult < 0) || (c >= p.c.It)); }
+  for (int jh = 0; jh < f.nh; ++jh) { const int c = tc.h0 * f.mulh + f.offh + f.sgn * jh; lh += !((c + (p.bh - 1) * f.mulh < 0) || (c >= p.c.Ih)); }
+  for (int jw = 0; jw < f.nw; ++jw) { const int c = tc.w0 * f.mulw + f.offw + f.sgn * jw; lw += !((c + (p.bw - 1) * f.mulw < 0) || (c >= p.c.Iw)); }
+  const int n = lt * lh * lw;
+  return n > 0 ? n : 1;
+}
+
+// KS = K steps of 16 channels per stage (cblk / 16), MT = 128-row M tiles per work item
+template <int KS, int MT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const __grid_constant__ CUtensorMap mapY, const TcConvP p, __nv_bfloat16* __restrict__ y) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[MAX_STAGES];
+  __shared__ uint64_t empty_bar[MAX_STAGES];
+  __shared__ uint64_t tfull_bar[2];
+  __shared__ uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0), lane = threadIdx.x % 32;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  const int items = p.items;
+
+  if (warp == 0 && lane == 0) { tmap_prefetch(&mapA); tmap_prefetch(&mapB); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0; int issued = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const TileCoord tc = decode_tile(p, item);
+      const PhaseInfo f = make_phase(p.c, tc.ph);
+      if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;        // tile outside this phase
+      const int ntaps = f.nt * f.nh * f.nw;
+      const int bcol = tc.ntile * p.bnt;
+      int executed = 0, j = 0;
+      for (int jt = 0; jt < f.nt; ++jt) {
+        const int ct = tc.t0 * f.mult + f.offt + f.sgn * jt;
+        const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
+        for (int jh = 0; jh < f.nh; ++jh) {
+          const int ch = tc.h0 * f.mulh + f.offh + f.sgn * jh;
+          const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
+          for (int jw = 0; jw < f.nw; ++jw, ++j) {
+            const int cw = tc.w0 * f.mulw + f.offw + f.sgn * jw;
+            const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
+            if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;   // tap entirely in the padding
+            const int kb = j * p.c.Kc;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              const bool ldA = !(p.dbg & 1) || issued < p.stages, ldB = !(p.dbg & 2) || issued < p.stages;
+              ++issued;
+              if (leader) {
+                mbar_expect_tx(&full_bar[stage], (uint32_t)((ldA ? p.a_bytes : 0) + (ldB ? p.tx_bytes - p.a_bytes : 0)));
+                const uint32_t a_dst = sbase + stage * stage_bytes;
+                if (ldA) tma_load_5d(a_dst, &mapA, &full_bar[stage], kc * p.cblk, cw, ch, ct, tc.n0);
+                if (ldB) tma_load_3d(a_dst + p.a_bytes, &mapB, &full_bar[stage], kb + kc * p.cblk, bcol, tc.ph);
+              }
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            ++executed;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // MMA issuer.  The geometry is reduced to "how many stages does this item have" before its flat issue loop:
+    // a single warp executes the loop control serially (~5 cycles per dependent instruction), so everything that is
+    // not wait / issue / commit has to stay out of it (profiles/r1h_mma_probe.md: ~250 cycles of control per stage
+    // already cost 30 % at 4 MMAs per stage).
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
+    const uint32_t dhi = sdesc_hi(8u * (uint32_t)(KS * 16) * 2u, (uint32_t)p.swz_layout);
+    constexpr uint32_t a_tile16 = (128u * (uint32_t)(KS * 16) * 2u) >> 4;
+    const uint32_t stage16 = (uint32_t)stage_bytes >> 4, b_off16 = (uint32_t)p.a_bytes >> 4;
+    const uint32_t lo0 = sdesc_lo(sbase, 16), lo_end = lo0 + (uint32_t)p.stages * stage16;
+    const uint32_t bnt = (uint32_t)p.bnt;
+    uint32_t alo = lo0; int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t tempty_phase0 = 0u, tempty_phase1 = 0u;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const TileCoord tc = decode_tile(p, item);
+      const PhaseInfo f = make_phase(p.c, tc.ph);
+      if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;
+      const int nst = live_taps(p, f, tc) * p.kchunks;
+      mbar_wait(&tempty_bar[acc], (acc ? tempty_phase1 : tempty_phase0) ^ 1u);      // epilogue has drained this accumulator set
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)(acc * p.acc_cols);
+      uint32_t accum = 0;
+      for (int it = 0; it < nst; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t blo = alo + b_off16;
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              umma_lohi(d_base + m * bnt, alo + m * a_tile16 + 2 * k, dhi, blo + 2 * k, dhi, idesc, k == 0 ? accum : 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        accum = 1;
+        alo += stage16;
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; alo = lo0; }
+      }
+      (void)lo_end;
+      if (leader) umma_commit(&tfull_bar[acc]);
+      if (acc) tempty_phase1 ^= 1u; else tempty_phase0 ^= 1u;
+      acc ^= 1;
+    }
+    __syncwarp();
+  } else {
+    // epilogue: TMEM lane quarter = warp % 4 (hardware restriction), row = quarter*32 + lane
+    const int quarter = warp % 4;
+    const int row = quarter * 32 + lane;
+    int r = row;
+    const int dw = r % p.bw; r /= p.bw;
+    const int dh = r % p.bh; r /= p.bh;
+    const int dt = r % p.bt; const int dn = r / p.bt;
+    int acc = 0; uint32_t tfull_phase0 = 0u, tfull_phase1 = 0u;
+    const uint32_t stg_base = sbase + (uint32_t)(p.stages * stage_bytes);      // 2 x 16 KB staging buffers (TMA-store path)
+    int nstore = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const TileCoord tc = decode_tile(p, item);
+      const PhaseInfo f = make_phase(p.c, tc.ph);
+      if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;
+      const int qw = tc.w0 + dw, qh = tc.h0 + dh, qt = tc.t0 + dt;
+      const int nbase = tc.ntile * p.bnt;
+      mbar_wait(&tfull_bar[acc], acc ? tfull_phase1 : tfull_phase0);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+      if (p.tma_store) {
+        // Coalesced path (bnt % 64 == 0): 64-channel chunks of a tile are staged in shared memory (128-byte rows, 128B
+        // swizzle -> conflict-free 16-byte writes) and written by one TMA store each; the tensor map does the sub-pixel
+        // scatter and clips rows / channels outside the tensor.  Direct 32-byte row stores from the TMEM registers ran
+        // at ~1.6 TB/s and cost half of the kernel time on the 64x64-pixel layers (profiles/r1h_summary.md).
+        const uint32_t swz_row = (uint32_t)row * 128u, swz_x = (uint32_t)(row & 7);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          for (int cb = 0; cb < p.bnt; cb += 64) {
+            const uint32_t buf = stg_base + (uint32_t)(nstore & 1) * 16384u;
+            if (warp == 2 && lane == 0) tma_store_wait_read<1>();      // the store that last used this buffer has read it
+            epi_bar_sync();
+            uint32_t v[32], w[32];
+            tmem_ld32_nowait(d_base + (uint32_t)(m * p.bnt + cb), v);
+            tmem_ld32_nowait(d_base + (uint32_t)(m * p.bnt + cb + 32), w);
+            tmem_ld_wait();
+            if (!(p.dbg & 4)) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint32_t* src = c < 4 ? v + 8 * c : w + 8 * (c - 4);
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float a = apply_act(__uint_as_float(src[2 * i]), p.act, p.slope);
+                  const float b = apply_act(__uint_as_float(src[2 * i + 1]), p.act, p.slope);
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                  pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + swz_row + (((uint32_t)c ^ swz_x) << 4)),
+                             "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+              }
+            }
+            fence_async_smem();
+            epi_bar_sync();
+            if (warp == 2 && lane == 0 && !(p.dbg & 4)) {
+              tma_store_5d(&mapY, buf, nbase + cb, tc.w0 * f.osw + f.rw, tc.h0 * f.osh + f.rh, tc.t0 * f.ost + f.rt, tc.n0 + m * p.bn);
+              tma_store_commit();
+            }
+            ++nstore;
+          }
+        }
+      } else
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int n = tc.n0 + m * p.bn + dn;
+        const bool valid = qw < f.Qw && qh < f.Qh && qt < f.Qt && n < p.c.N;
+        const int64_t pos = (((int64_t)n * p.c.Ot + (qt * f.ost + f.rt)) * p.c.Oh + (qh * f.osh + f.rh)) * p.c.Ow + (qw * f.osw + f.rw);
+        __nv_bfloat16* yrow = y + pos * p.ldy;
+        int cb = 0;
+        if (p.dbg & 8) continue;                                // timing experiment: no TMEM reads, no stores
+        for (; cb + 32 <= p.bnt; cb += 32) {                    // 32 columns per TMEM round trip
+          uint32_t v[32];
+          tmem_ld32_nowait(d_base + (uint32_t)(m * p.bnt + cb), v);
+          tmem_ld_wait();
+          if (!valid || (p.dbg & 4)) continue;
+          store_row16(v, yrow, nbase + cb, p.c.Nc, p.vec_ok, p.act, p.slope);
+          store_row16(v + 16, yrow, nbase + cb + 16, p.c.Nc, p.vec_ok, p.act, p.slope);
+        }
+        for (; cb < p.bnt; cb += 16) {
+          uint32_t v[16];
+          tmem_ld16(d_base + (uint32_t)(m * p.bnt + cb), v);
+          if (!valid || (p.dbg & 4)) continue;
+          store_row16(v, yrow, nbase + cb, p.c.Nc, p.vec_ok, p.act, p.slope);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);                            // this warp is done reading the set
+      if (acc) tfull_phase1 ^= 1u; else tfull_phase0 ^= 1u;
+      acc ^= 1;
+    }
+    if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_all();            // bulk stores must complete before the CTA exits
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+typedef void (*ConvPersFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcConvP, __nv_bfloat16*);
+static ConvPersFn conv_pers_variant(int ks, int mt) {
+  switch (ks * 10 + mt) {
+    case 41: return conv_tc_pers_kernel<4, 1>; case 42: return conv_tc_pers_kernel<4, 2>; case 44: return conv_tc_pers_kernel<4, 4>;
+    case 21: return conv_tc_pers_kernel<2, 1>; case 22: return conv_tc_pers_kernel<2, 2>; case 24: return conv_tc_pers_kernel<2, 4>;
+    case 11: return conv_tc_pers_kernel<1, 1>; case 12: return conv_tc_pers_kernel<1, 2>; case 14: return conv_tc_pers_kernel<1, 4>;
+  }
+  return nullptr;
 }
 
 // ------------------------------------------------------------------------------------------ conv_tc, grouped taps
@@ -554,6 +855,7 @@ struct TcWgradP {
   int cbB, nbB, blocksB_total;           // B: block width, blocks per CTA tile, total blocks
   int G, Ns, stages, tmem_cols;
   int layA, layB;                        // UMMA layout codes
+  int dbg;                               // DCV_TC_DBG & 3: stop issuing TMA loads after the first ring fill (timing experiments)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -608,11 +910,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
       const int h0 = (int)(q % p.tiles_h) * p.bh; q /= p.tiles_h;
       const int t0 = (int)(q % p.tiles_t) * p.bt; const int n0 = (int)(q / p.tiles_t) * p.bn;
       mbar_wait(&empty_bar[stage], phase ^ 1u);
-      if (lane == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(blkB_bytes * nbB + blkA_bytes * blocksA_here));
+      const bool skip = (p.dbg & 3) && (pt - pt_begin) >= p.stages;
+      if (lane == 0) mbar_expect_tx(&full_bar[stage], skip ? 0u : (uint32_t)(blkB_bytes * nbB + blkA_bytes * blocksA_here));
       __syncwarp();
       const uint32_t s_dst = sbase + stage * stage_bytes;
       const uint32_t a_dst = s_dst + p.nbB * blkB_bytes;
-      for (int i = lane; i < nloads; i += 32) {
+      for (int i = lane; i < (skip ? 0 : nloads); i += 32) {
         if (i < nbB) {
           tma_load_5d(s_dst + i * blkB_bytes, &mapS, &full_bar[stage], (bB0 + i) * p.cbB, w0, h0, t0, n0);
         } else {
@@ -669,10 +972,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
       const int tap = row_ok ? blk / p.clchunks : 0, clc = row_ok ? blk % p.clchunks : 0;
       const int cl = clc * p.cbA + row % p.cbA;
       float* out = partial + (((int64_t)blockIdx.z * taps + tap) * g.Cl + cl) * g.Cs + cs0;
-      for (int cb = 0; cb < p.Ns; cb += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(gi * p.Ns + cb), v);
-        if (!row_ok || cb >= ncols) continue;
+      auto store16 = [&](const uint32_t* v, int cb) {
+        if (!row_ok || cb >= ncols) return;
         float4* dst = reinterpret_cast<float4*>(out + cb);
         if (has_work) {
           dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
@@ -682,6 +983,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
         } else {
           dst[0] = dst[1] = dst[2] = dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      };
+      int cb = 0;
+      for (; cb + 32 <= p.Ns; cb += 32) {                       // 32 columns per TMEM round trip
+        uint32_t v[32];
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(gi * p.Ns + cb), v);
+        tmem_ld_wait();
+        store16(v, cb);
+        store16(v + 16, cb + 16);
+      }
+      for (; cb < p.Ns; cb += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(gi * p.Ns + cb), v);
+        store16(v, cb);
       }
     }
   }
@@ -915,6 +1229,69 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   rc = make_weight_map(&mapB, wp, Kph, npad, phases, p.cblk, p.bnt, swz);
   if (rc) return rc;
 
+  if (!getenv("DCV_TC_NOPERSIST")) {
+    // persistent variant: one CTA per SM, two accumulator sets in TMEM.  mt = 2 (two M tiles share every weight tile)
+    // unless that costs more in load balance over the 148 SMs than it saves in operand traffic.
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      DCV_CUDA(cudaGetDevice(&dev));
+      DCV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int tiles_n1 = ceil_div(c.N, p.bn);
+    p.ntn = npad / p.bnt;
+    const int64_t sp_tiles = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.ntn * phases;
+    auto balance = [&](int mt) {
+      const int64_t items = sp_tiles * ceil_div(c.N, p.bn * mt);
+      return (double)items / ((double)num_sms * (double)((items + num_sms - 1) / num_sms));
+    };
+    // M tiles per work item: more tiles share every weight tile and amortise the per-stage barrier handshake over more
+    // MMAs (>= 512 tensor cycles per stage wanted: mt * bnt >= 256), as long as two accumulator sets fit in TMEM, the
+    // TMA box stays <= 256 samples and the load balance over the SMs does not suffer
+    p.mt = 1;
+    for (int mt = 2; mt <= 4; mt *= 2) {
+      if (2 * mt * p.bnt > 512 || p.bn * mt > 256 || c.N < mt * p.bn) break;
+      if (mt * p.bnt > 256 && p.mt * p.bnt >= 256) break;
+      if (balance(mt) < 0.9 * balance(p.mt)) break;
+      p.mt = mt;
+    }
+    if (getenv("DCV_TC_MT1")) p.mt = 1;
+    p.tiles_n = ceil_div(c.N, p.bn * p.mt);
+    p.items = (int)(sp_tiles * p.tiles_n);
+    p.a_bytes = p.mt * 128 * p.cblk * 2;
+    p.tx_bytes = p.a_bytes + p.bnt * p.cblk * 2;
+    p.acc_cols = p.mt * p.bnt;
+    p.tmem_cols = pow2_ceil(2 * p.acc_cols < 32 ? 32 : 2 * p.acc_cols);
+    p.tma_store = (p.bnt % 64 == 0) && (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0) && !getenv("DCV_TC_NO_TMA_STORE");
+    const int stg_bytes = p.tma_store ? 2 * 16384 : 0;
+    int st = (222 * 1024 - stg_bytes) / (p.a_bytes + p.b_bytes);
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    if (st < 1) st = 1;
+    p.stages = st;
+    rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz);
+    if (rc) return rc;
+    CUtensorMap mapY = mapA;
+    if (p.tma_store) {
+      // output map: {Nc channels, Ow, Oh, Ot, N}; box = one M tile x 64 channels; the traversal strides are the sub-pixel
+      // phase strides of a transposed convolution / strided data gradient (1 for plain convolutions)
+      rc = make_act_map(&mapY, y, c.Nc, c.Ow, c.Oh, c.Ot, c.N, ldy, 64, p.bw, p.bh, p.bt, p.bn, f0.osw, f0.osh, f0.ost,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    const int smem_p = st * (p.a_bytes + p.b_bytes) + stg_bytes + 1024;
+    ConvPersFn fn = conv_pers_variant(p.cblk / 16, p.mt);
+    DCV_REQUIRE(fn != nullptr, "conv_tc: no persistent kernel variant for cblk %d mt %d", p.cblk, p.mt);
+    static int smem_set_p[64] = {0};
+    int& set = smem_set_p[(p.cblk / 16) * 8 + p.mt];
+    if (smem_p > set) {
+      DCV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+      set = smem_p;
+    }
+    const int grid_p = p.items < num_sms ? p.items : num_sms;
+    fn<<<grid_p, TC_THREADS, smem_p, s>>>(mapA, mapB, mapY, p, (__nv_bfloat16*)y);
+    return check_launch("conv_tc_pers");
+  }
+
   const int smem = stages * (p.a_bytes + p.b_bytes) + 1024;
   static int smem_set = 0;
   if (smem > smem_set) {
@@ -941,6 +1318,7 @@ int wgrad_tc_supported(const dcv_geom* g) {
 
 static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   p->g = *g;
+  { const char* e = getenv("DCV_TC_DBG"); p->dbg = e ? atoi(e) : 0; }
   const int taps = g->kt * g->kh * g->kw;
   p->cbA = block_width(g->Cl); p->nA = 128 / p->cbA; p->clchunks = g->Cl / p->cbA;
   p->blocksA_total = taps * p->clchunks;
@@ -974,7 +1352,10 @@ static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   if (stages < 1) stages = 1;
   p->stages = stages;
   const int64_t tiles = (int64_t)ceil_div(tiles_total, p->G) * ceil_div(p->blocksB_total, p->nbB);
-  int64_t sp = (148 * 2 + tiles - 1) / tiles;
+  // the ring takes the whole shared memory, so exactly one CTA is resident per SM: aim for ONE wave of <= 148 CTAs
+  // (a second wave only adds a second non-overlapped epilogue and doubles the partial sums that have to be reduced)
+  int64_t sp = tiles >= 148 ? 1 : 148 / tiles;
+  if (const char* e = getenv("DCV_WGRAD_WAVES")) sp *= atoi(e) > 0 ? atoi(e) : 1;
   const int64_t maxs = (p->ptiles_total + 7) / 8;
   if (sp > maxs) sp = maxs;
   if (sp > 296) sp = 296;

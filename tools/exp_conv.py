@@ -5,7 +5,7 @@ For every probe layer the same launch is timed with the debug knobs of csrc/tc_c
   base            - the production configuration
   noA / noB / noAB- DCV_TC_DBG=1/2/3: the producer stops issuing A / B / both TMA loads after the first ring fill
                     (wrong numbers, right MMA count) -> how much of the time is operand delivery
-  cps1            - one CTA per SM;  mt1 - one M tile per CTA
+  mt1             - one M tile per work item;  nopersist - the multi-CTA (non-persistent) kernel
 """
 import os
 import sys
@@ -27,7 +27,8 @@ LAYERS.update({
     "up5_dgrad": ("convT", 128, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 32, 32), "dgrad"),
 })
 VARIANTS = [("base", {}), ("noA", {"DCV_TC_DBG": "1"}), ("noB", {"DCV_TC_DBG": "2"}), ("noAB", {"DCV_TC_DBG": "3"}),
-            ("cps1", {"DCV_TC_CPS": "1"}), ("mt1", {"DCV_TC_MT1": "1"})]
+            ("mt1", {"DCV_TC_MT1": "1"}), ("nopersist", {"DCV_TC_NOPERSIST": "1"}), ("nostore", {"DCV_TC_DBG": "4"}),
+            ("noepi", {"DCV_TC_DBG": "8"}), ("noepi+noAB", {"DCV_TC_DBG": "11"})]
 
 
 def build(name):
@@ -75,11 +76,11 @@ def main():
         fn, flops = build(name)
         cells = []
         for tag, env in VARIANTS:
-            for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1"):
+            for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1", "DCV_TC_NOPERSIST"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             cells.append(timeit(fn, flush))
-        for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1"):
+        for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1", "DCV_TC_NOPERSIST"):
             os.environ.pop(k, None)
         print(f"| {name} | {flops / 1e9:.1f} | " + " | ".join(f"{c:.3f}" for c in cells) + f" | {flops / cells[0] / 1e9:.0f} TF/s", flush=True)
 

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256, 1) probe(const P p) {
   if (warp == 0) {
     if (lane == 0) {
       for (int s = 0; s < 8; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      mbar_init(&done_bar, p.mode >= 3 ? p.MT : 1);
+      mbar_init(&done_bar, (p.mode >= 3 && p.mode <= 5) ? p.MT : 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -113,7 +113,67 @@ __global__ void __launch_bounds__(256, 1) probe(const P p) {
   const uint32_t idesc = make_idesc(CG == 2 ? 256 : 128, p.N);
   const int ksteps = p.kblk / 16;
 
-  if (p.mode == 4) {
+  if (p.mode == 6) {
+    // lean issue + the conv_tc ring handshake: warp 2 = "producer" (all lanes wait empty, elected lane arrives full),
+    // warp 1 = MMA warp (all lanes wait full, elected lane issues 4*MT MMAs and commits empty); other warps spin on done_bar
+    const int w = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0);
+    if (w == 1 && rank == 0) {
+      const bool leader = elect_one();
+      const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
+      for (int it = 0; it < p.iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_src = sbase + stage * stage_bytes, b_src = a_src + a_bytes;
+        const uint32_t alo = ((a_src >> 4) & 0x3FFFu) | (1u << 16), blo = ((b_src >> 4) & 0x3FFFu) | (1u << 16);
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_lohi(tmem_base, alo + 2 * k, blo + 2 * k, hi, idesc, k == 0 ? accum : 1u);
+            if (p.MT == 2) umma_lohi(tmem_base + p.N, alo + 1024 + 2 * k, blo + 2 * k, hi, idesc, k == 0 ? accum : 1u);
+          }
+          commit<1>(&empty_bar[stage]);
+        }
+        accum = 1;
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      if (leader) commit<1>(&done_bar);
+      __syncwarp();
+    } else if (w == 2 && rank == 0) {
+      const bool leader = elect_one();
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < p.iters; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (leader) mbar_arrive(&full_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      __syncwarp();
+    }
+  } else if (p.mode == 5) {
+    // as mode 4 but both operands MN-major (wgrad_tc): 128 rows = 2 blocks of 64 channels, K = pixels, 32-pixel stage
+    const int w = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0);
+    if (w < p.MT && rank == 0) {
+      const uint32_t blk = 32 * 128;                                // one 64-channel block of 32 pixels
+      const uint32_t a_src = sbase + w * (2 * blk), b_src = sbase + 8 * blk;
+      const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t alo = ((a_src >> 4) & 0x3FFFu) | ((blk >> 4) << 16), blo = ((b_src >> 4) & 0x3FFFu) | ((blk >> 4) << 16);
+      const uint32_t d = tmem_base + w * p.N;
+      const uint32_t idesc_mn = idesc | (1u << 15) | (1u << 16);
+      const bool leader = elect_one();
+      if (leader) {
+        umma_lohi(d, alo, blo, hi, idesc_mn, 0u);
+        umma_lohi(d, alo + 128, blo + 128, hi, idesc_mn, 1u);
+      }
+      for (int it = 1; it < 2 * p.iters; ++it) {
+        if (leader) {
+          umma_lohi(d, alo, blo, hi, idesc_mn, 1u);
+          umma_lohi(d, alo + 128, blo + 128, hi, idesc_mn, 1u);
+        }
+      }
+      if (leader) commit<1>(&done_bar);
+      __syncwarp();
+    }
+  } else if (p.mode == 4) {
     // warp-uniform issue loop: every lane runs the loop, one elected lane issues; 32-bit descriptor arithmetic
     const int w = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0);
     if (w < p.MT && rank == 0) {
@@ -253,6 +313,18 @@ int main() {
       P p; p.N = N; p.MT = MT; p.iters = 2000; p.mode = 4; p.stages = 1; p.kblk = 64;
       printf("| 1 | 4 | %d | %d | 1 | 1 | %.0f | %d issuing warps, lean uniform issue\n", N, MT, run<1>(p, 1, 1), MT);
     }
+  for (int N : {128, 256})
+    for (int MT = 1; MT <= 2; MT *= 2) {
+      P p; p.N = N; p.MT = MT; p.iters = 2000; p.mode = 5; p.stages = 2; p.kblk = 64;
+      printf("| 1 | 5 | %d | %d | 1 | 1 | %.0f | %d issuing warps, lean issue, MN-major operands\n", N, MT, run<1>(p, 1, 1), MT);
+    }
+  for (int N : {128, 256})
+    for (int MT = 1; MT <= 2; MT *= 2)
+      for (int st = 1; st <= 4; ++st) {
+        if (MT * N > 512) continue;
+        P p; p.N = N; p.MT = MT; p.iters = 2000; p.mode = 6; p.stages = st; p.kblk = 64;
+        printf("| 1 | 6 | %d | %d | 1 | %d | %.0f | lean issue + ring handshake\n", N, MT, st, run<1>(p, 1, 1));
+      }
   // stage-count sensitivity of the handshake (N=128, MT=2: the vdis main.1 configuration)
   for (int st = 1; st <= 4; ++st) {
     P p; p.N = 128; p.MT = 2; p.iters = 2000; p.mode = 1; p.stages = st; p.kblk = 64;
