@@ -162,6 +162,7 @@ __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int
 
 constexpr int TC_THREADS = 192;
 constexpr int MAX_STAGES = 8;
+constexpr int TAPG = 4;     // grouped-tap mode: taps per pipeline stage
 
 // ------------------------------------------------------------------------------------------ conv_tc
 struct TcConvP {
@@ -410,6 +411,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t stage_info[MAX_STAGES];   // grouped-tap mode: bits 0..3 = taps of the stage that were loaded, bit 8 = last stage of the item
 
   const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0), lane = threadIdx.x % 32;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -440,6 +442,45 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;        // tile outside this phase
       const int ntaps = f.nt * f.nh * f.nw;
       const int bcol = tc.ntile * p.bnt;
+      if constexpr (KS == 0) {
+        // Grouped taps (16-channel, image-like operands): a stage carries FOUR taps - four A boxes of 32-byte rows issued
+        // by four lanes and one B box of 4 taps x 16 channels (128-byte rows).  Which taps were loaded travels to the MMA
+        // warp in stage_info (written before the releasing expect_tx arrive).
+        auto tap_coords = [&](int j, int& ct, int& ch, int& cw) -> bool {
+          const int jw = j % f.nw, jh = (j / f.nw) % f.nh, jt = j / (f.nw * f.nh);
+          ct = tc.t0 * f.mult + f.offt + f.sgn * jt;
+          ch = tc.h0 * f.mulh + f.offh + f.sgn * jh;
+          cw = tc.w0 * f.mulw + f.offw + f.sgn * jw;
+          const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
+          const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
+          const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
+          return !(skt || skh || skw);
+        };
+        int ct = 0, ch = 0, cw = 0;
+        uint32_t lo = __ballot_sync(0xffffffffu, lane < ntaps && tap_coords(lane, ct, ch, cw));
+        uint32_t hi = __ballot_sync(0xffffffffu, lane + 32 < ntaps && tap_coords(lane + 32, ct, ch, cw));
+        if ((lo | hi) == 0u) { if (ntaps > 32) hi = 1u << (ntaps - 33); else lo = 1u << (ntaps - 1); }   // all padding: run the last tap on zeros
+        const uint64_t live = ((uint64_t)hi << 32) | lo;
+        const int glast = (63 - __clzll((long long)live)) / TAPG;
+        const int a_tap_bytes = p.a_bytes / TAPG;
+        for (int gq = 0; gq <= glast; ++gq) {
+          const uint32_t mask = (uint32_t)(live >> (gq * TAPG)) & 0xFu;
+          if (mask == 0u) continue;
+          const bool mine = lane < TAPG && ((mask >> lane) & 1u);
+          if (mine) tap_coords(gq * TAPG + lane, ct, ch, cw);
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const uint32_t a_dst = sbase + stage * stage_bytes;
+          if (lane == 0) {
+            stage_info[stage] = mask | (gq == glast ? 0x100u : 0u);
+            mbar_expect_tx(&full_bar[stage], (uint32_t)(__popc(mask) * a_tap_bytes + p.bnt * 128));
+          }
+          __syncwarp();
+          if (mine) tma_load_5d(a_dst + lane * a_tap_bytes, &mapA, &full_bar[stage], 0, cw, ch, ct, tc.n0);
+          if (lane == TAPG) tma_load_3d(a_dst + p.a_bytes, &mapB, &full_bar[stage], gq * TAPG * 16, bcol, tc.ph);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        continue;
+      }
       int executed = 0, j = 0;
       for (int jt = 0; jt < f.nt; ++jt) {
         const int ct = tc.t0 * f.mult + f.offt + f.sgn * jt;
@@ -477,8 +518,10 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // already cost 30 % at 4 MMAs per stage).
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
-    const uint32_t dhi = sdesc_hi(8u * (uint32_t)(KS * 16) * 2u, (uint32_t)p.swz_layout);
-    constexpr uint32_t a_tile16 = (128u * (uint32_t)(KS * 16) * 2u) >> 4;
+    const uint32_t dhi = sdesc_hi(8u * (uint32_t)((KS ? KS : 1) * 16) * 2u, (uint32_t)p.swz_layout);
+    constexpr uint32_t a_tile16 = (128u * (uint32_t)((KS ? KS : 1) * 16) * 2u) >> 4;
+    const uint32_t g4_bhi = sdesc_hi(1024, 2);              // grouped taps: B rows are 128 bytes (4 taps x 16 channels), 128B swizzle
+    const uint32_t g4_tap16 = (uint32_t)(p.a_bytes / TAPG) >> 4;
     const uint32_t stage16 = (uint32_t)stage_bytes >> 4, b_off16 = (uint32_t)p.a_bytes >> 4;
     const uint32_t lo0 = sdesc_lo(sbase, 16), lo_end = lo0 + (uint32_t)p.stages * stage16;
     const uint32_t bnt = (uint32_t)p.bnt;
@@ -488,11 +531,34 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const TileCoord tc = decode_tile(p, item);
       const PhaseInfo f = make_phase(p.c, tc.ph);
       if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;
-      const int nst = live_taps(p, f, tc) * p.kchunks;
+      const int nst = KS == 0 ? 0 : live_taps(p, f, tc) * p.kchunks;
       mbar_wait(&tempty_bar[acc], (acc ? tempty_phase1 : tempty_phase0) ^ 1u);      // epilogue has drained this accumulator set
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(acc * p.acc_cols);
       uint32_t accum = 0;
+      if constexpr (KS == 0) {
+        uint32_t info;
+        do {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          info = __shfl_sync(0xffffffffu, *((volatile uint32_t*)&stage_info[stage]), 0);
+          if (leader) {
+            const uint32_t blo = alo + b_off16;
+#pragma unroll
+            for (int jj = 0; jj < TAPG; ++jj) {
+              if (!((info >> jj) & 1u)) continue;
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_lohi(d_base + m * bnt, alo + jj * g4_tap16 + m * ((128u * 32u) >> 4), dhi, blo + 2 * jj, g4_bhi, idesc, accum);
+              accum = 1;
+            }
+            umma_commit(&empty_bar[stage]);
+          }
+          accum = 1;
+          alo += stage16;
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; alo = lo0; }
+        } while (!(info & 0x100u));
+      }
       for (int it = 0; it < nst; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -620,6 +686,7 @@ static ConvPersFn conv_pers_variant(int ks, int mt) {
     case 41: return conv_tc_pers_kernel<4, 1>; case 42: return conv_tc_pers_kernel<4, 2>; case 44: return conv_tc_pers_kernel<4, 4>;
     case 21: return conv_tc_pers_kernel<2, 1>; case 22: return conv_tc_pers_kernel<2, 2>; case 24: return conv_tc_pers_kernel<2, 4>;
     case 11: return conv_tc_pers_kernel<1, 1>; case 12: return conv_tc_pers_kernel<1, 2>; case 14: return conv_tc_pers_kernel<1, 4>;
+    case 1: return conv_tc_pers_kernel<0, 1>; case 2: return conv_tc_pers_kernel<0, 2>; case 4: return conv_tc_pers_kernel<0, 4>;   // grouped taps
   }
   return nullptr;
 }
@@ -632,7 +699,6 @@ static ConvPersFn conv_pers_variant(int ks, int mt) {
 // 4 taps x 16 channels = 64 K-elements per output channel (128-byte rows, 128B swizzle - the packed weight layout
 // [n][tap][k] makes consecutive taps contiguous), consumed by up to 4*mt MMAs whose A and B descriptors simply use
 // different swizzle modes.
-constexpr int TAPG = 4;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_g4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcConvP p,
@@ -1195,10 +1261,83 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   p.vec_ok = (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0);
 
   CUtensorMap mapA, mapB;
-  int rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn * p.mt, f0.mulw, f0.mulh,
-                        f0.mult, swz);
+  int rc = 0;
+  const bool g4 = c.Kc == 16 && ntaps0 >= 4 && !getenv("DCV_NO_TAPGROUP");   // grouped-tap mode for 16-channel (image-like) operands
+  const int64_t Kph = (int64_t)ntaps0 * c.Kc;  // K extent of one phase
+
+  if (!getenv("DCV_TC_NOPERSIST")) {
+    // persistent variant: one CTA per SM, two accumulator sets in TMEM
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      DCV_CUDA(cudaGetDevice(&dev));
+      DCV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    p.ntn = npad / p.bnt;
+    const int64_t sp_tiles = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.ntn * phases;
+    auto balance = [&](int mt) {
+      const int64_t items = sp_tiles * ceil_div(c.N, p.bn * mt);
+      return (double)items / ((double)num_sms * (double)((items + num_sms - 1) / num_sms));
+    };
+    p.tma_store = (p.bnt % 64 == 0) && (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0) && !getenv("DCV_TC_NO_TMA_STORE");
+    const int stg_bytes = p.tma_store ? 2 * 16384 : 0;
+    p.b_bytes = g4 ? (p.bnt * 128 + 1023) / 1024 * 1024 : p.b_bytes;
+    auto a_bytes_of = [&](int mt) { return g4 ? TAPG * mt * 128 * 32 : mt * 128 * p.cblk * 2; };
+    auto stages_of = [&](int mt) { return (222 * 1024 - stg_bytes) / (a_bytes_of(mt) + p.b_bytes); };
+    // M tiles per work item: more tiles share every weight tile and amortise the per-stage barrier handshake over more
+    // MMAs (>= 512 tensor cycles per stage wanted: mt * bnt >= 256), as long as two accumulator sets fit in TMEM, the
+    // TMA box stays <= 256 samples, >= 3 ring stages remain and the load balance over the SMs does not suffer
+    p.mt = 1;
+    for (int mt = 2; mt <= 4; mt *= 2) {
+      if (2 * mt * p.bnt > 512 || p.bn * mt > 256 || c.N < mt * p.bn) break;
+      if (mt * p.bnt > 256 && p.mt * p.bnt >= 256) break;
+      if (stages_of(mt) < 3) break;
+      if (balance(mt) < 0.9 * balance(p.mt)) break;
+      p.mt = mt;
+    }
+    if (getenv("DCV_TC_MT1")) p.mt = 1;
+    p.tiles_n = ceil_div(c.N, p.bn * p.mt);
+    p.items = (int)(sp_tiles * p.tiles_n);
+    p.a_bytes = a_bytes_of(p.mt);
+    p.tx_bytes = p.a_bytes + p.bnt * p.cblk * 2;
+    p.acc_cols = p.mt * p.bnt;
+    p.tmem_cols = pow2_ceil(2 * p.acc_cols < 32 ? 32 : 2 * p.acc_cols);
+    int st = stages_of(p.mt);
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    if (st < 1) st = 1;
+    p.stages = st;
+    rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz);
+    if (rc) return rc;
+    rc = g4 ? make_weight_map(&mapB, wp, Kph, npad, phases, 64, p.bnt, CU_TENSOR_MAP_SWIZZLE_128B)
+            : make_weight_map(&mapB, wp, Kph, npad, phases, p.cblk, p.bnt, swz);
+    if (rc) return rc;
+    CUtensorMap mapY = mapA;
+    if (p.tma_store) {
+      // output map: {Nc channels, Ow, Oh, Ot, N}; box = one M tile x 64 channels; the traversal strides are the sub-pixel
+      // phase strides of a transposed convolution / strided data gradient (1 for plain convolutions)
+      rc = make_act_map(&mapY, y, c.Nc, c.Ow, c.Oh, c.Ot, c.N, ldy, 64, p.bw, p.bh, p.bt, p.bn, f0.osw, f0.osh, f0.ost,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    const int smem_p = st * (p.a_bytes + p.b_bytes) + stg_bytes + 1024;
+    const int ks = g4 ? 0 : p.cblk / 16;
+    ConvPersFn fn = conv_pers_variant(ks, p.mt);
+    DCV_REQUIRE(fn != nullptr, "conv_tc: no persistent kernel variant for cblk %d mt %d", p.cblk, p.mt);
+    static int smem_set_p[64] = {0};
+    int& set = smem_set_p[ks * 8 + p.mt];
+    if (smem_p > set) {
+      DCV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+      set = smem_p;
+    }
+    const int grid_p = p.items < num_sms ? p.items : num_sms;
+    fn<<<grid_p, TC_THREADS, smem_p, s>>>(mapA, mapB, mapY, p, (__nv_bfloat16*)y);
+    return check_launch("conv_tc_pers");
+  }
+
+  // ---- non-persistent kernels (DCV_TC_NOPERSIST=1: kept for A/B timing)
+  rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz);
   if (rc) return rc;
-  if (c.Kc == 16 && ntaps0 >= 4 && !getenv("DCV_NO_TAPGROUP")) {
+  if (g4) {
     // grouped-tap variant for 16-channel (image-like) operands: 4 taps per stage
     p.b_bytes = p.bnt * 128;
     const int a_tap = p.mt * 128 * 32;
@@ -1225,72 +1364,8 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     conv_tc_g4_kernel<<<grid_g, TC_THREADS, smem_g, s>>>(mapA, mapB, p, (__nv_bfloat16*)y);
     return check_launch("conv_tc_g4");
   }
-  const int64_t Kph = (int64_t)ntaps0 * c.Kc;  // K extent of one phase
   rc = make_weight_map(&mapB, wp, Kph, npad, phases, p.cblk, p.bnt, swz);
   if (rc) return rc;
-
-  if (!getenv("DCV_TC_NOPERSIST")) {
-    // persistent variant: one CTA per SM, two accumulator sets in TMEM.  mt = 2 (two M tiles share every weight tile)
-    // unless that costs more in load balance over the 148 SMs than it saves in operand traffic.
-    static int num_sms = 0;
-    if (num_sms == 0) {
-      int dev = 0;
-      DCV_CUDA(cudaGetDevice(&dev));
-      DCV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const int tiles_n1 = ceil_div(c.N, p.bn);
-    p.ntn = npad / p.bnt;
-    const int64_t sp_tiles = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.ntn * phases;
-    auto balance = [&](int mt) {
-      const int64_t items = sp_tiles * ceil_div(c.N, p.bn * mt);
-      return (double)items / ((double)num_sms * (double)((items + num_sms - 1) / num_sms));
-    };
-    // M tiles per work item: more tiles share every weight tile and amortise the per-stage barrier handshake over more
-    // MMAs (>= 512 tensor cycles per stage wanted: mt * bnt >= 256), as long as two accumulator sets fit in TMEM, the
-    // TMA box stays <= 256 samples and the load balance over the SMs does not suffer
-    p.mt = 1;
-    for (int mt = 2; mt <= 4; mt *= 2) {
-      if (2 * mt * p.bnt > 512 || p.bn * mt > 256 || c.N < mt * p.bn) break;
-      if (mt * p.bnt > 256 && p.mt * p.bnt >= 256) break;
-      if (balance(mt) < 0.9 * balance(p.mt)) break;
-      p.mt = mt;
-    }
-    if (getenv("DCV_TC_MT1")) p.mt = 1;
-    p.tiles_n = ceil_div(c.N, p.bn * p.mt);
-    p.items = (int)(sp_tiles * p.tiles_n);
-    p.a_bytes = p.mt * 128 * p.cblk * 2;
-    p.tx_bytes = p.a_bytes + p.bnt * p.cblk * 2;
-    p.acc_cols = p.mt * p.bnt;
-    p.tmem_cols = pow2_ceil(2 * p.acc_cols < 32 ? 32 : 2 * p.acc_cols);
-    p.tma_store = (p.bnt % 64 == 0) && (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0) && !getenv("DCV_TC_NO_TMA_STORE");
-    const int stg_bytes = p.tma_store ? 2 * 16384 : 0;
-    int st = (222 * 1024 - stg_bytes) / (p.a_bytes + p.b_bytes);
-    if (st > MAX_STAGES) st = MAX_STAGES;
-    if (st < 1) st = 1;
-    p.stages = st;
-    rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz);
-    if (rc) return rc;
-    CUtensorMap mapY = mapA;
-    if (p.tma_store) {
-      // output map: {Nc channels, Ow, Oh, Ot, N}; box = one M tile x 64 channels; the traversal strides are the sub-pixel
-      // phase strides of a transposed convolution / strided data gradient (1 for plain convolutions)
-      rc = make_act_map(&mapY, y, c.Nc, c.Ow, c.Oh, c.Ot, c.N, ldy, 64, p.bw, p.bh, p.bt, p.bn, f0.osw, f0.osh, f0.ost,
-                        CU_TENSOR_MAP_SWIZZLE_128B);
-      if (rc) return rc;
-    }
-    const int smem_p = st * (p.a_bytes + p.b_bytes) + stg_bytes + 1024;
-    ConvPersFn fn = conv_pers_variant(p.cblk / 16, p.mt);
-    DCV_REQUIRE(fn != nullptr, "conv_tc: no persistent kernel variant for cblk %d mt %d", p.cblk, p.mt);
-    static int smem_set_p[64] = {0};
-    int& set = smem_set_p[(p.cblk / 16) * 8 + p.mt];
-    if (smem_p > set) {
-      DCV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
-      set = smem_p;
-    }
-    const int grid_p = p.items < num_sms ? p.items : num_sms;
-    fn<<<grid_p, TC_THREADS, smem_p, s>>>(mapA, mapB, mapY, p, (__nv_bfloat16*)y);
-    return check_launch("conv_tc_pers");
-  }
 
   const int smem = stages * (p.a_bytes + p.b_bytes) + 1024;
   static int smem_set = 0;

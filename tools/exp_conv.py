@@ -25,6 +25,10 @@ LAYERS.update({
     "up3_fwd": ("convT", 512, 128, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 8, 8), "fwd"),
     "vdis_main5_fwd": ("conv", 128, 256, (4, 4, 4), (1, 2, 2), (0, 1, 1), 32, (10, 16, 16), "fwd"),
     "up5_dgrad": ("convT", 128, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 32, 32), "dgrad"),
+    "outconv_dgrad": ("convT", 128, 3, (1, 3, 3), (1, 1, 1), (0, 1, 1), 512, (1, 64, 64), "dgrad"),
+    "vdis_stem_fwd": ("conv", 4, 64, (4, 4, 4), (1, 2, 2), (0, 1, 1), 32, (16, 64, 64), "fwd"),
+    "vdis_stem_dgrad": ("conv", 4, 64, (4, 4, 4), (1, 2, 2), (0, 1, 1), 32, (16, 64, 64), "dgrad"),
+    "ggen_last_fwd": ("convT", 64, 1, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 32, 32), "fwd"),
 })
 VARIANTS = [("base", {}), ("noA", {"DCV_TC_DBG": "1"}), ("noB", {"DCV_TC_DBG": "2"}), ("noAB", {"DCV_TC_DBG": "3"}),
             ("mt1", {"DCV_TC_MT1": "1"}), ("nopersist", {"DCV_TC_NOPERSIST": "1"}), ("nostore", {"DCV_TC_DBG": "4"}),
@@ -69,7 +73,8 @@ def timeit(fn, flush):
 def main():
     require_device()
     names = sys.argv[1:] or ["vdis_main1_fwd", "vdis_main1_dgrad", "vdis_main5_fwd", "up5_fwd", "up5_dgrad", "up4_fwd", "up3_fwd",
-                             "down0_fwd", "down1_fwd", "down2_fwd", "outconv_fwd"]
+                             "down0_fwd", "down1_fwd", "down2_fwd", "outconv_fwd", "outconv_dgrad", "inconv_fwd", "vdis_stem_fwd", "vdis_stem_dgrad",
+                             "ggen_last_fwd"]
     flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device="cuda")
     print("| layer | GF | " + " | ".join(v for v, _ in VARIANTS) + " |  (ms ; TFLOP/s of base)")
     for name in names:
