@@ -231,7 +231,16 @@ wgrad_reduce_flat_kernel(const float* __restrict__ partial, int splits, int taps
     const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
     if (!win.has(cl, cs)) continue;    // zero-padding channels / other sub-weights have no entry in this master weight
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * total + i];
+    const float* pp = partial + i;
+    int z = 0;
+    for (; z + 8 <= splits; z += 8) {          // eight independent loads in flight, added in split order (deterministic)
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = pp[(int64_t)(z + u) * total];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; z < splits; ++z) s += pp[(int64_t)z * total];
     float* d = dw + (cl - win.cl_off) * s_l + (cs - win.cs_off) * s_s + tap * s_tap;
     *d = accumulate ? (*d + s) : s;
   }
@@ -310,8 +319,8 @@ int wgrad_reduce_win(const float* partial, int splits, const dcv_geom* g, Weight
                      int64_t s_s, int64_t s_tap, int accumulate, cudaStream_t s) {
   const int taps = g->kt * g->kh * g->kw;
   const int64_t total = (int64_t)taps * g->Cl * g->Cs;
-  if (splits <= 16) {
-    int fb = (int)((total + 255) / 256); if (fb > 148 * 8) fb = 148 * 8;
+  if (splits <= 16 || total >= 16384) {      // enough elements to fill the machine with one thread per element
+    int fb = (int)((total + 255) / 256); if (fb > 148 * 16) fb = 148 * 16;
     wgrad_reduce_flat_kernel<<<fb, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, win, dw, s_l, s_s, s_tap, accumulate);
     return check_launch("wgrad_reduce");
   }

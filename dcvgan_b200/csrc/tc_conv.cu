@@ -143,6 +143,26 @@ __device__ __forceinline__ void wgrad_issue(uint32_t tmem_d, uint32_t alo, uint3
     umma_lohi(tmem_d, alo + k * kstepA16, ahi, blo + k * kstepB16, bhi, idesc, k == 0 ? accum : 1u);
 }
 
+template <int KS, int G>
+__device__ __forceinline__ void wgrad_mma_loop(uint64_t* full_bar, uint64_t* empty_bar, int nst, int stages, uint32_t stage16,
+                                               uint32_t lo_a0, uint32_t lo_b0, uint32_t ahi, uint32_t bhi, uint32_t kstepA16,
+                                               uint32_t kstepB16, uint32_t tileA16, uint32_t tmem_base, uint32_t Ns, uint32_t idesc,
+                                               bool leader) {
+  int stage = 0; uint32_t phase = 0, accum = 0, alo = lo_a0, blo = lo_b0;
+  for (int it = 0; it < nst; ++it) {
+    mbar_wait(&full_bar[stage], phase);
+    tc_fence_after();
+    if (leader) {
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) wgrad_issue<KS>(tmem_base + gi * Ns, alo + gi * tileA16, ahi, blo, bhi, kstepA16, kstepB16, idesc, accum);
+      umma_commit(&empty_bar[stage]);
+    }
+    accum = 1;
+    alo += stage16; blo += stage16;
+    if (++stage == stages) { stage = 0; phase ^= 1u; alo = lo_a0; blo = lo_b0; }
+  }
+}
+
 // shared-memory matrix descriptor (sm_100 "version 1"); see DESIGN.md for the field map
 //   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle mode
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -966,33 +986,58 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    // TMA producer.  A stage is many small boxes (one per (tap, channel chunk) block); the 32 lanes issue them
-    // in parallel after lane 0 has armed the barrier, otherwise the per-instruction TMA latency serialises.
+    // TMA producer.  A stage is many small boxes (one per (tap, channel chunk) block); the 32 lanes issue them in
+    // parallel after lane 0 has armed the barrier, otherwise the per-instruction TMA latency serialises.  Everything
+    // that does not depend on the pixel tile - which box a lane loads, its channel / tap offsets, its shared-memory
+    // offset - is computed once; the pixel-tile origin advances like an odometer.  (The first version re-derived the
+    // tap coordinates with ~10 integer divisions per lane per stage: the MMA warp then waited on this warp for 58 % of
+    // the kernel, profiles/r1j_ncu_full_summary.md.)
     int stage = 0; uint32_t phase = 0;
     const int nloads = nbB + blocksA_here;
+    int l_isB[2], l_c[2], l_dw[2], l_dh[2], l_dt[2]; uint32_t l_off[2]; bool l_on[2];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const int i = lane + 32 * sl;
+      l_on[sl] = i < nloads;
+      l_isB[sl] = i < nbB;
+      l_c[sl] = 0; l_dw[sl] = l_dh[sl] = l_dt[sl] = 0; l_off[sl] = 0;
+      if (!l_on[sl]) continue;
+      if (l_isB[sl]) {
+        l_c[sl] = (bB0 + i) * p.cbB; l_off[sl] = (uint32_t)(i * blkB_bytes);
+      } else {
+        const int b = i - nbB;
+        const int blk = tile0 * p.nA + b;
+        const int tap = blk / p.clchunks, clc = blk % p.clchunks;
+        const int tc = tap % g.kw, tb = (tap / g.kw) % g.kh, ta = tap / (g.kw * g.kh);
+        l_c[sl] = clc * p.cbA; l_dw[sl] = tc - g.pw; l_dh[sl] = tb - g.ph; l_dt[sl] = ta - g.pt;
+        l_off[sl] = (uint32_t)(p.nbB * blkB_bytes + b * blkA_bytes);
+      }
+    }
+    int w0, h0, t0, n0;
+    {
+      int64_t q = pt_begin;
+      w0 = (int)(q % p.tiles_w) * p.bw; q /= p.tiles_w;
+      h0 = (int)(q % p.tiles_h) * p.bh; q /= p.tiles_h;
+      t0 = (int)(q % p.tiles_t) * p.bt; n0 = (int)(q / p.tiles_t) * p.bn;
+    }
+    const int wend = p.tiles_w * p.bw, hend = p.tiles_h * p.bh, tend = p.tiles_t * p.bt;
     for (int64_t pt = pt_begin; pt < pt_end; ++pt) {
-      int64_t q = pt;
-      const int w0 = (int)(q % p.tiles_w) * p.bw; q /= p.tiles_w;
-      const int h0 = (int)(q % p.tiles_h) * p.bh; q /= p.tiles_h;
-      const int t0 = (int)(q % p.tiles_t) * p.bt; const int n0 = (int)(q / p.tiles_t) * p.bn;
       mbar_wait(&empty_bar[stage], phase ^ 1u);
       const bool skip = (p.dbg & 3) && (pt - pt_begin) >= p.stages;
       if (lane == 0) mbar_expect_tx(&full_bar[stage], skip ? 0u : (uint32_t)(blkB_bytes * nbB + blkA_bytes * blocksA_here));
       __syncwarp();
       const uint32_t s_dst = sbase + stage * stage_bytes;
-      const uint32_t a_dst = s_dst + p.nbB * blkB_bytes;
-      for (int i = lane; i < (skip ? 0 : nloads); i += 32) {
-        if (i < nbB) {
-          tma_load_5d(s_dst + i * blkB_bytes, &mapS, &full_bar[stage], (bB0 + i) * p.cbB, w0, h0, t0, n0);
-        } else {
-          const int b = i - nbB;
-          const int blk = tile0 * p.nA + b;
-          const int tap = blk / p.clchunks, clc = blk % p.clchunks;
-          const int tc = tap % g.kw, tb = (tap / g.kw) % g.kh, ta = tap / (g.kw * g.kh);
-          tma_load_5d(a_dst + b * blkA_bytes, &mapL, &full_bar[stage], clc * p.cbA, w0 * g.sw - g.pw + tc,
-                      h0 * g.sh - g.ph + tb, t0 * g.st - g.pt + ta, n0);
+      if (!skip) {
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          if (!l_on[sl]) continue;
+          if (l_isB[sl]) tma_load_5d(s_dst + l_off[sl], &mapS, &full_bar[stage], l_c[sl], w0, h0, t0, n0);
+          else tma_load_5d(s_dst + l_off[sl], &mapL, &full_bar[stage], l_c[sl], w0 * g.sw + l_dw[sl], h0 * g.sh + l_dh[sl],
+                           t0 * g.st + l_dt[sl], n0);
         }
       }
+      w0 += p.bw;
+      if (w0 >= wend) { w0 = 0; h0 += p.bh; if (h0 >= hend) { h0 = 0; t0 += p.bt; if (t0 >= tend) { t0 = 0; n0 += p.bn; } } }
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
     __syncwarp();
@@ -1003,24 +1048,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     const uint32_t kstepA16 = (16u * (uint32_t)p.cbA * 2u) >> 4, kstepB16 = (16u * (uint32_t)p.cbB * 2u) >> 4;   // 16 pixels, in 16-byte units
     const uint32_t ahi = sdesc_hi(8u * (uint32_t)p.cbA * 2u, (uint32_t)p.layA), bhi = sdesc_hi(8u * (uint32_t)p.cbB * 2u, (uint32_t)p.layB);
     const uint32_t tileA16 = (uint32_t)(p.nA * blkA_bytes) >> 4;
-    int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
-    for (int64_t pt = pt_begin; pt < pt_end; ++pt) {
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
-      const uint32_t s_src = sbase + stage * stage_bytes;
-      const uint32_t blo = sdesc_lo(s_src, (uint32_t)blkB_bytes), alo = sdesc_lo(s_src + p.nbB * blkB_bytes, (uint32_t)blkA_bytes);
-      if (leader) {
-        for (int gi = 0; gi < Gcur; ++gi) {
-          const uint32_t d = tmem_base + gi * p.Ns, a0 = alo + gi * tileA16;
-          if (p.pix == 128) wgrad_issue<8>(d, a0, ahi, blo, bhi, kstepA16, kstepB16, idesc, accum);
-          else if (p.pix == 64) wgrad_issue<4>(d, a0, ahi, blo, bhi, kstepA16, kstepB16, idesc, accum);
-          else wgrad_issue<2>(d, a0, ahi, blo, bhi, kstepA16, kstepB16, idesc, accum);
-        }
-        umma_commit(&empty_bar[stage]);
-      }
-      accum = 1;
-      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-    }
+    const uint32_t lo_b0 = sdesc_lo(sbase, (uint32_t)blkB_bytes), lo_a0 = sdesc_lo(sbase + p.nbB * blkB_bytes, (uint32_t)blkA_bytes);
+    const int nst = (int)(pt_end - pt_begin);
+    // the hot loop is instantiated per (K steps per stage, accumulator tiles) so that a stage is straight-line code:
+    // wait, fence, G*KS MMAs, commit (a single warp pays ~5 cycles per dependent control instruction)
+#define DCV_WG_LOOP(KS_, G_)                                                                                                     \
+    wgrad_mma_loop<KS_, G_>(full_bar, empty_bar, nst, p.stages, (uint32_t)stage_bytes >> 4, lo_a0, lo_b0, ahi, bhi, kstepA16,      \
+                            kstepB16, tileA16, tmem_base, (uint32_t)p.Ns, idesc, leader)
+#define DCV_WG_KS(G_)                                                                                                            \
+    do { if (p.pix == 128) DCV_WG_LOOP(8, G_); else if (p.pix == 64) DCV_WG_LOOP(4, G_); else DCV_WG_LOOP(2, G_); } while (0)
+    if (Gcur == 4) DCV_WG_KS(4); else if (Gcur == 3) DCV_WG_KS(3); else if (Gcur == 2) DCV_WG_KS(2); else DCV_WG_KS(1);
+#undef DCV_WG_KS
+#undef DCV_WG_LOOP
     if (leader) umma_commit(&tmem_full_bar);
     __syncwarp();
   } else {

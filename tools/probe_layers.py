@@ -24,10 +24,12 @@ LAYERS = {
     "up5_fwd": ("convT", 128, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), B * 16, (1, 32, 32), "fwd"),
     "outconv_fwd": ("convT", 128, 3, (1, 3, 3), (1, 1, 1), (0, 1, 1), B * 16, (1, 64, 64), "fwd"),
     "down0_fwd": ("conv", 64, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), B * 16, (1, 64, 64), "fwd"),
+    "down0_wgrad": ("conv", 64, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), B * 16, (1, 64, 64), "wgrad"),
+    "up5_wgrad": ("convT", 128, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), B * 16, (1, 32, 32), "wgrad"),
 }
 
 
-def run(name, reps=3):
+def run(name, reps=1):
     kind, cin, cout, k, s, p, n, sp, op = LAYERS[name]
     spec = ops.ConvSpec(kind, cin, cout, k, s, p)
     dt = torch.bfloat16
