@@ -199,6 +199,7 @@ struct TcConvP {
   int tmem_cols;
   int ntn, items, acc_cols;              // persistent kernel: N tiles, work items, TMEM columns of one accumulator set
   int tma_store;                         // persistent kernel: epilogue through shared memory + TMA store
+  PhaseInfo phs[8];                      // persistent kernel: geometry of every sub-pixel phase (host-computed)
   int dbg;                               // DCV_TC_DBG (timing experiments only): 1 = stop loading A, 2 = stop loading B after the first ring fill
 };
 
@@ -363,16 +364,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // MMA warp saturates the tensor pipe, which the first attempt at this kernel (profiles/experiments, r1d) could not.
 struct TileCoord { int ph, ntile, w0, h0, t0, n0; };
 
-__device__ __forceinline__ TileCoord decode_tile(const TcConvP& p, int item) {
-  TileCoord t;
+// Work-item iterator of the persistent kernel.  item = ((((ph * ntn + ntile) * tiles_n + tn) * tiles_t + tt) * tiles_h + th)
+// * tiles_w + tw; a CTA owns a CONTIGUOUS range of items, so stepping to the next one is an odometer increment instead of
+// five integer divisions, neighbouring tiles (shared halo rows, same weight tile) follow each other in L2, and the
+// phase geometry (PhaseInfo, precomputed on the host in TcConvP::phs) only changes a few times per CTA.  ncu of the
+// first persistent version: ~35 % of all warp samples sat in the division sequences of decode_tile / make_phase, on
+// the MMA warp that is tensor-pipe idle time.
+struct TileIter { int tw, th, tt, tn, ntile, ph; };
+
+__device__ __forceinline__ TileIter tile_iter_init(const TcConvP& p, int item) {
+  TileIter t;
   int r = item;
-  const int tw = r % p.tiles_w; r /= p.tiles_w;
-  const int th = r % p.tiles_h; r /= p.tiles_h;
-  const int tt = r % p.tiles_t; r /= p.tiles_t;
-  const int tn = r % p.tiles_n; r /= p.tiles_n;
+  t.tw = r % p.tiles_w; r /= p.tiles_w;
+  t.th = r % p.tiles_h; r /= p.tiles_h;
+  t.tt = r % p.tiles_t; r /= p.tiles_t;
+  t.tn = r % p.tiles_n; r /= p.tiles_n;
   t.ntile = r % p.ntn; t.ph = r / p.ntn;
-  t.w0 = tw * p.bw; t.h0 = th * p.bh; t.t0 = tt * p.bt; t.n0 = tn * p.bn * p.mt;
   return t;
+}
+__device__ __forceinline__ void tile_iter_next(const TcConvP& p, TileIter& t) {
+  if (++t.tw < p.tiles_w) return; t.tw = 0;
+  if (++t.th < p.tiles_h) return; t.th = 0;
+  if (++t.tt < p.tiles_t) return; t.tt = 0;
+  if (++t.tn < p.tiles_n) return; t.tn = 0;
+  if (++t.ntile < p.ntn) return; t.ntile = 0;
+  ++t.ph;
+}
+__device__ __forceinline__ TileCoord tile_coord(const TcConvP& p, const TileIter& t) {
+  TileCoord c;
+  c.ph = t.ph; c.ntile = t.ntile; c.w0 = t.tw * p.bw; c.h0 = t.th * p.bh; c.t0 = t.tt * p.bt; c.n0 = t.tn * p.bn * p.mt;
+  return c;
+}
+// contiguous item range of this CTA
+__device__ __forceinline__ void cta_item_range(int items, int& first, int& count) {
+  const int per = items / (int)gridDim.x, rem = items % (int)gridDim.x, b = (int)blockIdx.x;
+  first = b * per + (b < rem ? b : rem);
+  count = per + (b < rem ? 1 : 0);
 }
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
@@ -456,9 +483,14 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (warp == 0) {
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0; int issued = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const TileCoord tc = decode_tile(p, item);
-      const PhaseInfo f = make_phase(p.c, tc.ph);
+    int item_first, item_count;
+    cta_item_range(items, item_first, item_count);
+    TileIter ti = tile_iter_init(p, item_first);
+    int cur_ph = ti.ph;
+    PhaseInfo f = p.phs[cur_ph];
+    for (int itn = 0; itn < item_count; ++itn, tile_iter_next(p, ti)) {
+      if (ti.ph != cur_ph) { cur_ph = ti.ph; f = p.phs[cur_ph]; }
+      const TileCoord tc = tile_coord(p, ti);
       if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;        // tile outside this phase
       const int ntaps = f.nt * f.nh * f.nw;
       const int bcol = tc.ntile * p.bnt;
@@ -547,9 +579,14 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const uint32_t bnt = (uint32_t)p.bnt;
     uint32_t alo = lo0; int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t tempty_phase0 = 0u, tempty_phase1 = 0u;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const TileCoord tc = decode_tile(p, item);
-      const PhaseInfo f = make_phase(p.c, tc.ph);
+    int item_first, item_count;
+    cta_item_range(items, item_first, item_count);
+    TileIter ti = tile_iter_init(p, item_first);
+    int cur_ph = ti.ph;
+    PhaseInfo f = p.phs[cur_ph];
+    for (int itn = 0; itn < item_count; ++itn, tile_iter_next(p, ti)) {
+      if (ti.ph != cur_ph) { cur_ph = ti.ph; f = p.phs[cur_ph]; }
+      const TileCoord tc = tile_coord(p, ti);
       if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;
       const int nst = KS == 0 ? 0 : live_taps(p, f, tc) * p.kchunks;
       mbar_wait(&tempty_bar[acc], (acc ? tempty_phase1 : tempty_phase0) ^ 1u);      // epilogue has drained this accumulator set
@@ -613,9 +650,14 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     int acc = 0; uint32_t tfull_phase0 = 0u, tfull_phase1 = 0u;
     const uint32_t stg_base = sbase + (uint32_t)(p.stages * stage_bytes);      // 2 x 16 KB staging buffers (TMA-store path)
     int nstore = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const TileCoord tc = decode_tile(p, item);
-      const PhaseInfo f = make_phase(p.c, tc.ph);
+    int item_first, item_count;
+    cta_item_range(items, item_first, item_count);
+    TileIter ti = tile_iter_init(p, item_first);
+    int cur_ph = ti.ph;
+    PhaseInfo f = p.phs[cur_ph];
+    for (int itn = 0; itn < item_count; ++itn, tile_iter_next(p, ti)) {
+      if (ti.ph != cur_ph) { cur_ph = ti.ph; f = p.phs[cur_ph]; }
+      const TileCoord tc = tile_coord(p, ti);
       if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;
       const int qw = tc.w0 + dw, qh = tc.h0 + dh, qt = tc.t0 + dt;
       const int nbase = tc.ntile * p.bnt;
@@ -1313,6 +1355,8 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
       DCV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     p.ntn = npad / p.bnt;
+    DCV_REQUIRE(phases <= 8, "conv_tc: %d sub-pixel phases", phases);
+    for (int ph = 0; ph < phases; ++ph) p.phs[ph] = make_phase(c, ph);
     const int64_t sp_tiles = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.ntn * phases;
     auto balance = [&](int mt) {
       const int64_t items = sp_tiles * ceil_div(c.N, p.bn * mt);
