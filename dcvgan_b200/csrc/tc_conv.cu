@@ -200,6 +200,8 @@ struct TcConvP {
   int ntn, items, acc_cols;              // persistent kernel: N tiles, work items, TMEM columns of one accumulator set
   int tma_store;                         // persistent kernel: epilogue through shared memory + TMA store
   PhaseInfo phs[8];                      // persistent kernel: geometry of every sub-pixel phase (host-computed)
+  int hg, hcls;                          // row-halo sharing: taps per h class that share one A box (1 = off), h classes (nh / hg)
+  int a_tile16;                          // M-tile stride inside the A box, in 16-byte units (rows incl. halo x row bytes)
   int dbg;                               // DCV_TC_DBG (timing experiments only): 1 = stop loading A, 2 = stop loading B after the first ring fill
 };
 
@@ -447,8 +449,25 @@ __device__ __forceinline__ int live_taps(const TcConvP& p, const PhaseInfo& f, c
   return n > 0 ? n : 1;
 }
 
+// same with row-halo sharing: an h "tap" is a class of HG taps whose common box (bh + HG - 1 rows) has to touch real pixels
+template <int HG>
+__device__ __forceinline__ int live_stages(const TcConvP& p, const PhaseInfo& f, const TileCoord& tc) {
+  if (HG == 1) return live_taps(p, f, tc);
+  int lt = 0, lh = 0, lw = 0;
+  for (int jt = 0; jt < f.nt; ++jt) { const int c = tc.t0 * f.mult + f.offt + f.sgn * jt; lt += !((c + (p.bt - 1) * f.mult < 0) || (c >= p.c.It)); }
+  for (int jh = 0; jh < p.hcls; ++jh) {
+    int c = tc.h0 * f.mulh + f.offh + f.sgn * jh;
+    if (f.sgn < 0) c -= (HG - 1) * f.mulh;
+    lh += !((c + (p.bh + HG - 2) * f.mulh < 0) || (c >= p.c.Ih));
+  }
+  for (int jw = 0; jw < f.nw; ++jw) { const int c = tc.w0 * f.mulw + f.offw + f.sgn * jw; lw += !((c + (p.bw - 1) * f.mulw < 0) || (c >= p.c.Iw)); }
+  const int n = lt * lh * lw;
+  return n > 0 ? n : 1;
+}
+
 // KS = K steps of 16 channels per stage (cblk / 16), MT = 128-row M tiles per work item
-template <int KS, int MT>
+// HG = taps of one h class that share a single A box with HG-1 halo rows (1 = every tap loads its own box)
+template <int KS, int MT, int HG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ CUtensorMap mapY, const TcConvP p, __nv_bfloat16* __restrict__ y) {
@@ -462,7 +481,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
   const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0), lane = threadIdx.x % 32;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int stage_bytes = p.a_bytes + p.b_bytes;
+  const int stage_bytes = p.a_bytes + HG * p.b_bytes;
   const int items = p.items;
 
   if (warp == 0 && lane == 0) { tmap_prefetch(&mapA); tmap_prefetch(&mapB); }
@@ -533,18 +552,23 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         continue;
       }
-      int executed = 0, j = 0;
+      int executed = 0;
+      const int nhc = HG > 1 ? p.hcls : f.nh;                 // h classes (HG taps each) or plain h taps
+      const int nlast = f.nt * nhc * f.nw - 1;
+      int jc = 0;
       for (int jt = 0; jt < f.nt; ++jt) {
         const int ct = tc.t0 * f.mult + f.offt + f.sgn * jt;
         const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
-        for (int jh = 0; jh < f.nh; ++jh) {
-          const int ch = tc.h0 * f.mulh + f.offh + f.sgn * jh;
-          const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
-          for (int jw = 0; jw < f.nw; ++jw, ++j) {
+        for (int jh = 0; jh < nhc; ++jh) {
+          // first lattice row of the box: tap jh itself, or with halo sharing the lowest row of the class' HG taps
+          // (tap i of class jh reads rows shifted by +i (gather) / -i (scatter) in units of the traversal stride)
+          int ch = tc.h0 * f.mulh + f.offh + f.sgn * jh;
+          if (HG > 1 && f.sgn < 0) ch -= (HG - 1) * f.mulh;
+          const bool skh = (ch + (p.bh + HG - 2) * f.mulh < 0) || (ch >= p.c.Ih);
+          for (int jw = 0; jw < f.nw; ++jw, ++jc) {
             const int cw = tc.w0 * f.mulw + f.offw + f.sgn * jw;
             const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
-            if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;   // tap entirely in the padding
-            const int kb = j * p.c.Kc;
+            if ((skt || skh || skw) && !(jc == nlast && executed == 0)) continue;   // box entirely in the padding
             for (int kc = 0; kc < p.kchunks; ++kc) {
               mbar_wait(&empty_bar[stage], phase ^ 1u);
               const bool ldA = !(p.dbg & 1) || issued < p.stages, ldB = !(p.dbg & 2) || issued < p.stages;
@@ -553,7 +577,14 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 mbar_expect_tx(&full_bar[stage], (uint32_t)((ldA ? p.a_bytes : 0) + (ldB ? p.tx_bytes - p.a_bytes : 0)));
                 const uint32_t a_dst = sbase + stage * stage_bytes;
                 if (ldA) tma_load_5d(a_dst, &mapA, &full_bar[stage], kc * p.cblk, cw, ch, ct, tc.n0);
-                if (ldB) tma_load_3d(a_dst + p.a_bytes, &mapB, &full_bar[stage], kb + kc * p.cblk, bcol, tc.ph);
+                if (ldB) {
+#pragma unroll
+                  for (int i = 0; i < HG; ++i) {
+                    const int jhh = HG > 1 ? jh + i * p.hcls : jh;             // h tap i of this class
+                    const int j = (jt * f.nh + jhh) * f.nw + jw;
+                    tma_load_3d(a_dst + p.a_bytes + i * p.b_bytes, &mapB, &full_bar[stage], j * p.c.Kc + kc * p.cblk, bcol, tc.ph);
+                  }
+                }
               }
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
@@ -571,7 +602,10 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
     const uint32_t dhi = sdesc_hi(8u * (uint32_t)((KS ? KS : 1) * 16) * 2u, (uint32_t)p.swz_layout);
-    constexpr uint32_t a_tile16 = (128u * (uint32_t)((KS ? KS : 1) * 16) * 2u) >> 4;
+    const uint32_t a_tile16 = HG > 1 ? (uint32_t)p.a_tile16 : ((128u * (uint32_t)((KS ? KS : 1) * 16) * 2u) >> 4);
+    const uint32_t row16 = ((uint32_t)p.bw * (uint32_t)((KS ? KS : 1) * 16) * 2u) >> 4;   // one tile row (bw pixels) in 16-byte units
+    const uint32_t bt16 = (uint32_t)p.b_bytes >> 4;
+    const bool sgn_pos = p.phs[0].sgn > 0;
     const uint32_t g4_bhi = sdesc_hi(1024, 2);              // grouped taps: B rows are 128 bytes (4 taps x 16 channels), 128B swizzle
     const uint32_t g4_tap16 = (uint32_t)(p.a_bytes / TAPG) >> 4;
     const uint32_t stage16 = (uint32_t)stage_bytes >> 4, b_off16 = (uint32_t)p.a_bytes >> 4;
@@ -588,7 +622,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (ti.ph != cur_ph) { cur_ph = ti.ph; f = p.phs[cur_ph]; }
       const TileCoord tc = tile_coord(p, ti);
       if (tc.w0 >= f.Qw || tc.h0 >= f.Qh || tc.t0 >= f.Qt) continue;
-      const int nst = KS == 0 ? 0 : live_taps(p, f, tc) * p.kchunks;
+      const int nst = KS == 0 ? 0 : live_stages<HG>(p, f, tc) * p.kchunks;
       mbar_wait(&tempty_bar[acc], (acc ? tempty_phase1 : tempty_phase0) ^ 1u);      // epilogue has drained this accumulator set
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(acc * p.acc_cols);
@@ -622,10 +656,17 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if (leader) {
           const uint32_t blo = alo + b_off16;
 #pragma unroll
-          for (int k = 0; k < KS; ++k) {
+          for (int i = 0; i < HG; ++i) {
+            // tap i of the class: A window shifted by whole tile rows inside the halo box (a multiple of the swizzle
+            // atom, so the descriptor only changes its start address), B tile i of the stage
+            const uint32_t ai = alo + (HG > 1 ? (sgn_pos ? (uint32_t)i : (uint32_t)(HG - 1 - i)) * row16 : 0u);
+            const uint32_t bi = blo + (uint32_t)i * bt16;
 #pragma unroll
-            for (int m = 0; m < MT; ++m)
-              umma_lohi(d_base + m * bnt, alo + m * a_tile16 + 2 * k, dhi, blo + 2 * k, dhi, idesc, k == 0 ? accum : 1u);
+            for (int k = 0; k < KS; ++k) {
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_lohi(d_base + m * bnt, ai + m * a_tile16 + 2 * k, dhi, bi + 2 * k, dhi, idesc, (i == 0 && k == 0) ? accum : 1u);
+            }
           }
           umma_commit(&empty_bar[stage]);
         }
@@ -743,13 +784,13 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 }
 
 typedef void (*ConvPersFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcConvP, __nv_bfloat16*);
-static ConvPersFn conv_pers_variant(int ks, int mt) {
-  switch (ks * 10 + mt) {
-    case 41: return conv_tc_pers_kernel<4, 1>; case 42: return conv_tc_pers_kernel<4, 2>; case 44: return conv_tc_pers_kernel<4, 4>;
-    case 21: return conv_tc_pers_kernel<2, 1>; case 22: return conv_tc_pers_kernel<2, 2>; case 24: return conv_tc_pers_kernel<2, 4>;
-    case 11: return conv_tc_pers_kernel<1, 1>; case 12: return conv_tc_pers_kernel<1, 2>; case 14: return conv_tc_pers_kernel<1, 4>;
-    case 1: return conv_tc_pers_kernel<0, 1>; case 2: return conv_tc_pers_kernel<0, 2>; case 4: return conv_tc_pers_kernel<0, 4>;   // grouped taps
-  }
+static ConvPersFn conv_pers_variant(int ks, int mt, int hg) {
+#define DCV_V(KS_, MT_, HG_) if (ks == KS_ && mt == MT_ && hg == HG_) return conv_tc_pers_kernel<KS_, MT_, HG_>;
+  DCV_V(4, 1, 1) DCV_V(4, 2, 1) DCV_V(4, 4, 1) DCV_V(2, 1, 1) DCV_V(2, 2, 1) DCV_V(2, 4, 1) DCV_V(1, 1, 1) DCV_V(1, 2, 1) DCV_V(1, 4, 1)
+  DCV_V(0, 1, 1) DCV_V(0, 2, 1) DCV_V(0, 4, 1)                                      // grouped taps (16-channel operands)
+  DCV_V(4, 1, 2) DCV_V(4, 2, 2) DCV_V(4, 4, 2) DCV_V(2, 1, 2) DCV_V(2, 2, 2) DCV_V(2, 4, 2)   // row-halo sharing, 2 taps per class
+  DCV_V(4, 1, 3) DCV_V(4, 2, 3) DCV_V(4, 4, 3) DCV_V(2, 1, 3) DCV_V(2, 2, 3) DCV_V(2, 4, 3)   // 3 taps per class (3x3 stride 1)
+#undef DCV_V
   return nullptr;
 }
 
@@ -1357,23 +1398,45 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     p.ntn = npad / p.bnt;
     DCV_REQUIRE(phases <= 8, "conv_tc: %d sub-pixel phases", phases);
     for (int ph = 0; ph < phases; ++ph) p.phs[ph] = make_phase(c, ph);
+    p.tma_store = (p.bnt % 64 == 0) && (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0) && !getenv("DCV_TC_NO_TMA_STORE");
+    const int stg_bytes = p.tma_store ? 2 * 16384 : 0;
+    p.b_bytes = g4 ? (p.bnt * 128 + 1023) / 1024 * 1024 : p.b_bytes;
+
+    // Row-halo sharing: the h taps that read the same strided lattice (every sh-th tap of a strided gather, all nh taps of
+    // a sub-pixel phase / stride-1 correlation) differ by whole tile rows, so ONE A box with hg-1 extra rows serves all of
+    // them - the MMA descriptors just start hg-1 .. 0 rows further down, which is a multiple of the swizzle atom when a
+    // tile row holds a multiple of 8 pixels.  L2 -> SM traffic for A drops to (bh + hg - 1) / (hg * bh) of the per-tap
+    // boxes; the tile is re-shaped to 16 x 8 so that the halo stays small.  Needs a tile that lies in one (n, t) slice.
+    p.hg = 1; p.hcls = f0.nh;
+    if (!g4 && !getenv("DCV_TC_NOHALO")) {
+      const int hg = c.scatter ? f0.nh : (g->kh % g->sh == 0 ? g->kh / g->sh : 1);
+      const int hbw = f0.Qw >= 16 ? 16 : (f0.Qw >= 8 ? 8 : 0);
+      const int hbh = hbw ? 128 / hbw : 0;
+      bool same = true;                                       // every phase has the same number of h taps
+      for (int ph = 1; ph < phases; ++ph) same = same && (make_phase(c, ph).nh == f0.nh);
+      const int bsz = hg * p.b_bytes;
+      if ((hg == 2 || hg == 3) && hbw && f0.Qh >= hbh && same && p.cblk >= 32 && bsz <= 96 * 1024) {
+        p.hg = hg; p.hcls = f0.nh / hg;
+        p.bw = hbw; p.bh = hbh; p.bt = 1; p.bn = 1;
+        p.tiles_w = ceil_div(f0.Qw, p.bw); p.tiles_h = ceil_div(f0.Qh, p.bh); p.tiles_t = f0.Qt;
+      }
+    }
+    const int box_rows = (p.bh + p.hg - 1) * p.bw * p.bt * p.bn;                       // A rows of one M tile incl. halo
+    p.a_tile16 = (box_rows * p.cblk * 2) >> 4;
     const int64_t sp_tiles = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.ntn * phases;
     auto balance = [&](int mt) {
       const int64_t items = sp_tiles * ceil_div(c.N, p.bn * mt);
       return (double)items / ((double)num_sms * (double)((items + num_sms - 1) / num_sms));
     };
-    p.tma_store = (p.bnt % 64 == 0) && (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0) && !getenv("DCV_TC_NO_TMA_STORE");
-    const int stg_bytes = p.tma_store ? 2 * 16384 : 0;
-    p.b_bytes = g4 ? (p.bnt * 128 + 1023) / 1024 * 1024 : p.b_bytes;
-    auto a_bytes_of = [&](int mt) { return g4 ? TAPG * mt * 128 * 32 : mt * 128 * p.cblk * 2; };
-    auto stages_of = [&](int mt) { return (222 * 1024 - stg_bytes) / (a_bytes_of(mt) + p.b_bytes); };
+    auto a_bytes_of = [&](int mt) { return g4 ? TAPG * mt * 128 * 32 : mt * box_rows * p.cblk * 2; };
+    auto stages_of = [&](int mt) { return (222 * 1024 - stg_bytes) / (a_bytes_of(mt) + p.hg * p.b_bytes); };
     // M tiles per work item: more tiles share every weight tile and amortise the per-stage barrier handshake over more
-    // MMAs (>= 512 tensor cycles per stage wanted: mt * bnt >= 256), as long as two accumulator sets fit in TMEM, the
+    // MMAs (>= 512 tensor cycles per stage wanted: hg * mt * bnt >= 256), as long as two accumulator sets fit in TMEM, the
     // TMA box stays <= 256 samples, >= 3 ring stages remain and the load balance over the SMs does not suffer
     p.mt = 1;
     for (int mt = 2; mt <= 4; mt *= 2) {
       if (2 * mt * p.bnt > 512 || p.bn * mt > 256 || c.N < mt * p.bn) break;
-      if (mt * p.bnt > 256 && p.mt * p.bnt >= 256) break;
+      if (p.hg * mt * p.bnt > 256 && p.hg * p.mt * p.bnt >= 256) break;
       if (stages_of(mt) < 3) break;
       if (balance(mt) < 0.9 * balance(p.mt)) break;
       p.mt = mt;
@@ -1382,14 +1445,14 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     p.tiles_n = ceil_div(c.N, p.bn * p.mt);
     p.items = (int)(sp_tiles * p.tiles_n);
     p.a_bytes = a_bytes_of(p.mt);
-    p.tx_bytes = p.a_bytes + p.bnt * p.cblk * 2;
+    p.tx_bytes = p.a_bytes + p.hg * p.bnt * p.cblk * 2;
     p.acc_cols = p.mt * p.bnt;
     p.tmem_cols = pow2_ceil(2 * p.acc_cols < 32 ? 32 : 2 * p.acc_cols);
     int st = stages_of(p.mt);
     if (st > MAX_STAGES) st = MAX_STAGES;
     if (st < 1) st = 1;
     p.stages = st;
-    rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz);
+    rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh + p.hg - 1, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz);
     if (rc) return rc;
     rc = g4 ? make_weight_map(&mapB, wp, Kph, npad, phases, 64, p.bnt, CU_TENSOR_MAP_SWIZZLE_128B)
             : make_weight_map(&mapB, wp, Kph, npad, phases, p.cblk, p.bnt, swz);
@@ -1402,12 +1465,12 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
                         CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
-    const int smem_p = st * (p.a_bytes + p.b_bytes) + stg_bytes + 1024;
+    const int smem_p = st * (p.a_bytes + p.hg * p.b_bytes) + stg_bytes + 1024;
     const int ks = g4 ? 0 : p.cblk / 16;
-    ConvPersFn fn = conv_pers_variant(ks, p.mt);
-    DCV_REQUIRE(fn != nullptr, "conv_tc: no persistent kernel variant for cblk %d mt %d", p.cblk, p.mt);
-    static int smem_set_p[64] = {0};
-    int& set = smem_set_p[ks * 8 + p.mt];
+    ConvPersFn fn = conv_pers_variant(ks, p.mt, p.hg);
+    DCV_REQUIRE(fn != nullptr, "conv_tc: no persistent kernel variant for cblk %d mt %d hg %d", p.cblk, p.mt, p.hg);
+    static int smem_set_p[256] = {0};
+    int& set = smem_set_p[(ks * 8 + p.mt) * 4 + p.hg];
     if (smem_p > set) {
       DCV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
       set = smem_p;

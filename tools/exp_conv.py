@@ -32,7 +32,7 @@ LAYERS.update({
 })
 VARIANTS = [("base", {}), ("noA", {"DCV_TC_DBG": "1"}), ("noB", {"DCV_TC_DBG": "2"}), ("noAB", {"DCV_TC_DBG": "3"}),
             ("mt1", {"DCV_TC_MT1": "1"}), ("nopersist", {"DCV_TC_NOPERSIST": "1"}), ("nostore", {"DCV_TC_DBG": "4"}),
-            ("noepi", {"DCV_TC_DBG": "8"}), ("noepi+noAB", {"DCV_TC_DBG": "11"})]
+            ("noepi+noAB", {"DCV_TC_DBG": "11"}), ("nohalo", {"DCV_TC_NOHALO": "1"})]
 
 
 def build(name):
@@ -81,11 +81,11 @@ def main():
         fn, flops = build(name)
         cells = []
         for tag, env in VARIANTS:
-            for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1", "DCV_TC_NOPERSIST"):
+            for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1", "DCV_TC_NOPERSIST", "DCV_TC_NOHALO"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             cells.append(timeit(fn, flush))
-        for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1", "DCV_TC_NOPERSIST"):
+        for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1", "DCV_TC_NOPERSIST", "DCV_TC_NOHALO"):
             os.environ.pop(k, None)
         print(f"| {name} | {flops / 1e9:.1f} | " + " | ".join(f"{c:.3f}" for c in cells) + f" | {flops / cells[0] / 1e9:.0f} TF/s", flush=True)
 
