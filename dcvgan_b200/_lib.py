@@ -50,12 +50,12 @@ SIGNATURES = {
     "dcv_wgrad_reduce_sub": (_i, [_G, _i, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _i, _vp]),
     "dcv_bn_stats_blocks": (_i, [_i64, _i]),
     "dcv_bn_stats": (_i, [_i, _vp, _i64, _i64, _i, _vp, _vp]),
-    "dcv_bn_finalize": (_i, [_vp, _i, _i, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "dcv_bn_finalize": (_i, [_vp, _i, _i, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dcv_bn_eval_stats": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp]),
     "dcv_bn_act": (_i, [_i, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp, _i64, _vp]),
-    "dcv_bn_act_bwd_reduce": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp, _i64, _i, _f, _vp, _vp]),
+    "dcv_bn_act_bwd_reduce": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp, _vp]),
     "dcv_bn_bwd_finalize": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
-    "dcv_bn_act_bwd_apply": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp,
+    "dcv_bn_act_bwd_apply": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp,
                                   _i64, _vp, _i64, _vp]),
     "dcv_act_bwd": (_i, [_i, _vp, _i64, _vp, _i64, _i64, _i, _i, _f, _vp, _i64, _vp]),
     "dcv_add_noise": (_i, [_i, _vp, _i64, _vp, _f, _i64, _i, _vp, _i64, _vp]),
@@ -98,7 +98,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.dcv_abi_version() != 2:
+        if handle.dcv_abi_version() != 3:
             raise DcvError("libdcvgan_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -67,9 +67,10 @@ __device__ __forceinline__ void warp_sum_partials(const float* __restrict__ part
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblk, int C, double count, float eps,
-                                   float momentum, float* running_mean, float* running_var,
+                                   float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
                                    float* __restrict__ mean, float* __restrict__ invstd) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;   // nn.BatchNorm's counter
   if (c >= C) return;
   double s0, s1;
   warp_sum_partials(partials, nblk, C, c, s0, s1);
@@ -485,20 +486,27 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, int64_t lda,
                              const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
-                             const float* __restrict__ invstd, const float* __restrict__ drop, int64_t rows_per_n,
+                             const float* __restrict__ invstd, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, const float* __restrict__ drop, int64_t rows_per_n,
                              int act, float slope, float* __restrict__ partials) {
   constexpr int N = VecIO<T>::N;
+  // (Leaky)ReLU: the sign of the activated output equals the sign of the pre-activation gamma * xhat + beta, which is
+  // recomputed from z with exactly the forward's arithmetic - the output tensor `a` is then not read at all (one of
+  // the three streamed tensors).  A dropped element (drop scale 0) has zero gradient whatever the sign says.
+  const bool from_z = act == DCV_ACT_LEAKY;
   channel_reduce2_vec<T>(rows, C, partials, [&](int64_t row, int c0, float (&v0)[N], float (&v1)[N]) {
     float g[N], o[N], zz[N];
     VecIO<T>::load(da + row * ldda + c0, g);
-    VecIO<T>::load(a + row * lda + c0, o);
+    if (!from_z) VecIO<T>::load(a + row * lda + c0, o);
     VecIO<T>::load(z + row * ldz + c0, zz);
     const float* dr = drop ? drop + (row / rows_per_n) * C + c0 : nullptr;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
+      const float xhat = (zz[j] - mean[c0 + j]) * invstd[c0 + j];
+      if (from_z) { float t = xhat; if (gamma) t = t * gamma[c0 + j] + beta[c0 + j]; o[j] = t; }
       float du = g[j] * act_grad_from_out(o[j], act, slope);
       if (dr) du *= dr[j];
-      v0[j] = du; v1[j] = du * ((zz[j] - mean[c0 + j]) * invstd[c0 + j]);
+      v0[j] = du; v1[j] = du * xhat;
     }
   });
 }
@@ -508,33 +516,47 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, int64_t lda,
                             const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
                             const float* __restrict__ invstd, const float* __restrict__ gamma,
-                            const float* __restrict__ drop, int64_t rows_per_n, int act, float slope,
-                            const float* __restrict__ sums, float inv_count, T* __restrict__ dz, int64_t lddz) {
+                            const float* __restrict__ beta, const float* __restrict__ drop, int64_t rows_per_n, int act,
+                            float slope, const float* __restrict__ sums, float inv_count, T* __restrict__ dz, int64_t lddz) {
   constexpr int N = VecIO<T>::N;
   const VecMap m = vec_map<N>(rows, C);
   if (!m.active) return;
   const int c0 = m.cg * N;
-  float mu[N], is[N], gi[N], k0[N], k1[N];
+  const bool from_z = act == DCV_ACT_LEAKY;       // see bn_act_bwd_reduce_vec_kernel
+  float mu[N], is[N], ga[N], be[N], gi[N], k0[N], k1[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
     mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j];
-    gi[j] = (gamma ? gamma[c0 + j] : 1.f) * is[j];
+    ga[j] = gamma ? gamma[c0 + j] : 1.f; be[j] = gamma ? beta[c0 + j] : 0.f;
+    gi[j] = ga[j] * is[j];
     k0[j] = sums[c0 + j] * inv_count; k1[j] = sums[C + c0 + j] * inv_count;
   }
-  for (int64_t row = m.rb + m.lane; row < m.re; row += m.lanes) {
-    float g[N], o[N], zz[N];
-    VecIO<T>::load(da + row * ldda + c0, g);
-    VecIO<T>::load(a + row * lda + c0, o);
-    VecIO<T>::load(z + row * ldz + c0, zz);
-    const float* dr = drop ? drop + (row / rows_per_n) * C + c0 : nullptr;
+  constexpr int U = 2;   // rows in flight per thread
+  for (int64_t row0 = m.rb + m.lane; row0 < m.re; row0 += (int64_t)m.lanes * U) {
+    float g[U][N], o[U][N], zz[U][N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      float du = g[j] * act_grad_from_out(o[j], act, slope);
-      if (dr) du *= dr[j];
-      const float xhat = (zz[j] - mu[j]) * is[j];
-      g[j] = gi[j] * (du - k0[j] - xhat * k1[j]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row >= m.re) continue;
+      VecIO<T>::load(da + row * ldda + c0, g[u]);
+      if (!from_z) VecIO<T>::load(a + row * lda + c0, o[u]);
+      VecIO<T>::load(z + row * ldz + c0, zz[u]);
     }
-    VecIO<T>::store(dz + row * lddz + c0, g);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row >= m.re) continue;
+      const float* dr = drop ? drop + (row / rows_per_n) * C + c0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float xhat = (zz[u][j] - mu[j]) * is[j];
+        if (from_z) { float t = xhat; if (gamma) t = t * ga[j] + be[j]; o[u][j] = t; }
+        float du = g[u][j] * act_grad_from_out(o[u][j], act, slope);
+        if (dr) du *= dr[j];
+        g[u][j] = gi[j] * (du - k0[j] - xhat * k1[j]);
+      }
+      VecIO<T>::store(dz + row * lddz + c0, g[u]);
+    }
   }
 }
 
@@ -573,6 +595,211 @@ axpy_vec_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __
     }
     VecIO<T>::store(out + row * ldo + c0, v);
   }
+}
+
+// ------------------------------------------------------------------------------------------ bf16 streaming variants
+// The generic vector kernels above hold every loaded row as 8 unpacked floats plus four per-channel constant vectors:
+// 95-127 registers, 2 CTAs per SM, ~32 KB of loads in flight per SM - they reached 2.8-3.0 TB/s where a plain copy
+// runs at 6.0 TB/s (tools/exp_bn.py).  These bf16 variants keep the rows in flight as RAW 16-byte vectors (4
+// registers each), unpack one row at a time, and fold the per-channel arithmetic into 2-5 fused constants:
+//   xhat = z*A + B            A = invstd, B = -mean*invstd
+//   pre  = z*P + Q            P = A*gamma, Q = B*gamma + beta      (sign of the (Leaky)ReLU argument)
+//   dz   = G*du - R - S*z     G = gamma*invstd, R = G*(k0 + k1*B), S = G*k1*A   (k = reduced sums / count)
+__device__ __forceinline__ void unpack8(const uint4& t, float (&v)[8]) {
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h); }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(256, 3)
+bn_act_bf16_kernel(const __nv_bfloat16* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
+                   const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ drop, int64_t rows_per_n, int act, float slope, __nv_bfloat16* __restrict__ a,
+                   int64_t lda) {
+  const VecMap m = vec_map<8>(rows, C);
+  if (!m.active) return;
+  const int c0 = m.cg * 8;
+  float P[8], Q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float is = mean ? invstd[c0 + j] : 1.f, mu = mean ? mean[c0 + j] : 0.f;
+    const float g = (mean && gamma) ? gamma[c0 + j] : 1.f, b = (mean && gamma) ? beta[c0 + j] : 0.f;
+    P[j] = is * g; Q[j] = b - mu * is * g;
+  }
+  constexpr int U = 8;
+  for (int64_t row0 = m.rb + m.lane; row0 < m.re; row0 += (int64_t)m.lanes * U) {
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row < m.re) raw[u] = *reinterpret_cast<const uint4*>(z + row * ldz + c0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row >= m.re) continue;
+      float v[8];
+      unpack8(raw[u], v);
+      const float* dr = drop ? drop + (row / rows_per_n) * C + c0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(v[j], P[j], Q[j]);
+        if (dr) t *= dr[j];
+        v[j] = apply_act(t, act, slope);
+      }
+      *reinterpret_cast<uint4*>(a + row * lda + c0) = pack8(v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_apply_bf16_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const __nv_bfloat16* __restrict__ z, int64_t ldz,
+                             int64_t rows, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
+                             const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ drop,
+                             int64_t rows_per_n, float slope, const float* __restrict__ sums, float inv_count,
+                             __nv_bfloat16* __restrict__ dz, int64_t lddz) {
+  const VecMap m = vec_map<8>(rows, C);
+  if (!m.active) return;
+  const int c0 = m.cg * 8;
+  float P[8], Q[8], G[8], R[8], S[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float A = invstd[c0 + j], B = -mean[c0 + j] * A;
+    const float ga = gamma ? gamma[c0 + j] : 1.f, be = gamma ? beta[c0 + j] : 0.f;
+    const float k0 = sums[c0 + j] * inv_count, k1 = sums[C + c0 + j] * inv_count;
+    P[j] = A * ga; Q[j] = B * ga + be;
+    G[j] = ga * A; R[j] = G[j] * (k0 + k1 * B); S[j] = G[j] * k1 * A;
+  }
+  constexpr int U = 4;
+  for (int64_t row0 = m.rb + m.lane; row0 < m.re; row0 += (int64_t)m.lanes * U) {
+    uint4 rg[U], rz[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row < m.re) {
+        rg[u] = *reinterpret_cast<const uint4*>(da + row * ldda + c0);
+        rz[u] = *reinterpret_cast<const uint4*>(z + row * ldz + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row >= m.re) continue;
+      float g[8], zz[8];
+      unpack8(rg[u], g); unpack8(rz[u], zz);
+      const float* dr = drop ? drop + (row / rows_per_n) * C + c0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = fmaf(zz[j], P[j], Q[j]);
+        float du = pre > 0.f ? g[j] : g[j] * slope;
+        if (dr) du *= dr[j];
+        g[j] = fmaf(G[j], du, -fmaf(S[j], zz[j], R[j]));
+      }
+      *reinterpret_cast<uint4*>(dz + row * lddz + c0) = pack8(g);
+    }
+  }
+}
+
+// block-level reduction tail shared by the two bf16 reduce kernels: partials[b][0][c], partials[b][1][c]
+__device__ __forceinline__ void reduce2_tail(const VecMap& m, int C, float (&a0)[8], float (&a1)[8], float* __restrict__ partials) {
+  __shared__ float red[2][256][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[0][threadIdx.x][j] = a0[j]; red[1][threadIdx.x][j] = a1[j]; }
+  __syncthreads();
+  const int CG = C / 8;
+  if (m.active && m.lane == 0) {
+    float* out = partials + (int64_t)blockIdx.x * 2 * C;
+    for (int l = 1; l < m.lanes; ++l) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a0[j] += red[0][l * CG + m.cg][j]; a1[j] += red[1][l * CG + m.cg][j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { out[m.cg * 8 + j] = a0[j]; out[C + m.cg * 8 + j] = a1[j]; }
+  }
+}
+
+__global__ void __launch_bounds__(256, 3)
+bn_stats_bf16_kernel(const __nv_bfloat16* __restrict__ z, int64_t ldz, int64_t rows, int C, float* __restrict__ partials) {
+  const VecMap m = vec_map<8>(rows, C);
+  float a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+  if (m.active) {
+    const int c0 = m.cg * 8;
+    constexpr int U = 8;
+    for (int64_t row0 = m.rb + m.lane; row0 < m.re; row0 += (int64_t)m.lanes * U) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t row = row0 + (int64_t)u * m.lanes;
+        raw[u] = row < m.re ? *reinterpret_cast<const uint4*>(z + row * ldz + c0) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float v[8];
+        unpack8(raw[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] += v[j]; a1[j] = fmaf(v[j], v[j], a1[j]); }
+      }
+    }
+  }
+  reduce2_tail(m, C, a0, a1, partials);
+}
+
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_reduce_bf16_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const __nv_bfloat16* __restrict__ z, int64_t ldz,
+                              int64_t rows, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ drop,
+                              int64_t rows_per_n, float slope, float* __restrict__ partials) {
+  const VecMap m = vec_map<8>(rows, C);
+  float a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+  if (m.active) {
+    const int c0 = m.cg * 8;
+    float A[8], B[8], P[8], Q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      A[j] = invstd[c0 + j]; B[j] = -mean[c0 + j] * A[j];
+      const float ga = gamma ? gamma[c0 + j] : 1.f, be = gamma ? beta[c0 + j] : 0.f;
+      P[j] = A[j] * ga; Q[j] = B[j] * ga + be;
+    }
+    constexpr int U = 4;
+    for (int64_t row0 = m.rb + m.lane; row0 < m.re; row0 += (int64_t)m.lanes * U) {
+      uint4 rg[U], rz[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t row = row0 + (int64_t)u * m.lanes;
+        if (row < m.re) {
+          rg[u] = *reinterpret_cast<const uint4*>(da + row * ldda + c0);
+          rz[u] = *reinterpret_cast<const uint4*>(z + row * ldz + c0);
+        } else {
+          rg[u] = make_uint4(0u, 0u, 0u, 0u); rz[u] = rg[u];      // zero upstream gradient: contributes nothing
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t row = row0 + (int64_t)u * m.lanes;
+        float g[8], zz[8];
+        unpack8(rg[u], g); unpack8(rz[u], zz);
+        const float* dr = (drop && row < m.re) ? drop + (row / rows_per_n) * C + c0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pre = fmaf(zz[j], P[j], Q[j]);
+          float du = pre > 0.f ? g[j] : g[j] * slope;
+          if (dr) du *= dr[j];
+          a0[j] += du; a1[j] = fmaf(du, fmaf(zz[j], A[j], B[j]), a1[j]);
+        }
+      }
+    }
+  }
+  reduce2_tail(m, C, a0, a1, partials);
 }
 
 static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
@@ -615,16 +842,20 @@ int dcv_bn_stats_blocks(int64_t rows, int C) {
 int dcv_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float* partials, void* stream) {
   const int nblk = dcv_bn_stats_blocks(rows, C);
   DISPATCH_T(dtype, {
-    if (vec_ok<T>(C, {z}, {ldz})) bn_stats_vec_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials);
+    if (sizeof(T) == 2 && vec_ok<T>(C, {z}, {ldz}))
+      bn_stats_bf16_kernel<<<nblk, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, ldz, rows, C, partials);
+    else if (vec_ok<T>(C, {z}, {ldz})) bn_stats_vec_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials);
     else bn_stats_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials);
   });
   return check_launch("bn_stats");
 }
 
 int dcv_bn_finalize(const float* partials, int nblk, int C, int64_t count, float eps, float momentum,
-                    float* running_mean, float* running_var, float* mean, float* invstd, void* stream) {
+                    float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd,
+                    void* stream) {
   bn_finalize_kernel<<<ceil_div(C, 8), 256, 0, as_stream(stream)>>>(partials, nblk, C, (double)count, eps, momentum,
-                                                                    running_mean, running_var, mean, invstd);
+                                                                    running_mean, running_var, (long long*)num_batches_tracked,
+                                                                    mean, invstd);
   return check_launch("bn_finalize");
 }
 
@@ -639,7 +870,10 @@ int dcv_bn_act(int dtype, const void* z, int64_t ldz, int64_t rows, int C, const
                void* a, int64_t lda, void* stream) {
   if (rows * C == 0) return 0;
   DISPATCH_T(dtype, {
-    if (vec_ok<T>(C, {z, a}, {ldz, lda}))
+    if (sizeof(T) == 2 && vec_ok<T>(C, {z, a}, {ldz, lda}))
+      bn_act_bf16_kernel<<<vec_blocks(rows, C, 8), 256, 0, as_stream(stream)>>>(
+          (const __nv_bfloat16*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope, (__nv_bfloat16*)a, lda);
+    else if (vec_ok<T>(C, {z, a}, {ldz, lda}))
       bn_act_vec_kernel<T><<<vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream)>>>(
           (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope, (T*)a, lda);
     else
@@ -650,13 +884,19 @@ int dcv_bn_act(int dtype, const void* z, int64_t ldz, int64_t rows, int C, const
 }
 
 int dcv_bn_act_bwd_reduce(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, const void* z,
-                          int64_t ldz, int64_t rows, int C, const float* mean, const float* invstd, const float* drop,
-                          int64_t rows_per_n, int act, float slope, float* partials, void* stream) {
+                          int64_t ldz, int64_t rows, int C, const float* mean, const float* invstd, const float* gamma,
+                          const float* beta, const float* drop, int64_t rows_per_n, int act, float slope, float* partials,
+                          void* stream) {
   const int nblk = dcv_bn_stats_blocks(rows, C);
   DISPATCH_T(dtype, {
-    if (vec_ok<T>(C, {da, a, z}, {ldda, lda, ldz}))
+    if (sizeof(T) == 2 && act == DCV_ACT_LEAKY && vec_ok<T>(C, {da, z}, {ldda, ldz}))
+      bn_act_bwd_reduce_bf16_kernel<<<nblk, 256, 0, as_stream(stream)>>>(
+          (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, slope,
+          partials);
+    else if (vec_ok<T>(C, {da, a, z}, {ldda, lda, ldz}))
       bn_act_bwd_reduce_vec_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>(
-          (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, drop, rows_per_n, act, slope, partials);
+          (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope,
+          partials);
     else
       bn_act_bwd_reduce_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>(
           (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, drop, rows_per_n, act, slope, partials);
@@ -672,13 +912,17 @@ int dcv_bn_bwd_finalize(const float* partials, int nblk, int C, float* sums, flo
 
 int dcv_bn_act_bwd_apply(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, const void* z,
                          int64_t ldz, int64_t rows, int C, const float* mean, const float* invstd, const float* gamma,
-                         const float* drop, int64_t rows_per_n, int act, float slope, const float* sums, int64_t count,
-                         void* dz, int64_t lddz, void* stream) {
+                         const float* beta, const float* drop, int64_t rows_per_n, int act, float slope, const float* sums,
+                         int64_t count, void* dz, int64_t lddz, void* stream) {
   if (rows * C == 0) return 0;
   DISPATCH_T(dtype, {
-    if (vec_ok<T>(C, {da, a, z, dz}, {ldda, lda, ldz, lddz}))
+    if (sizeof(T) == 2 && act == DCV_ACT_LEAKY && vec_ok<T>(C, {da, z, dz}, {ldda, ldz, lddz}))
+      bn_act_bwd_apply_bf16_kernel<<<vec_blocks(rows, C, 8), 256, 0, as_stream(stream)>>>(
+          (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, slope,
+          sums, 1.0f / (float)count, (__nv_bfloat16*)dz, lddz);
+    else if (vec_ok<T>(C, {da, a, z, dz}, {ldda, lda, ldz, lddz}))
       bn_act_bwd_apply_vec_kernel<T><<<vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream)>>>(
-          (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, gamma, drop, rows_per_n, act, slope,
+          (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope,
           sums, 1.0f / (float)count, (T*)dz, lddz);
     else
       bn_act_bwd_apply_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(

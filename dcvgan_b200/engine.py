@@ -138,8 +138,7 @@ class Block:
         ops.conv(g, spec.fwd_dir, impl, x_used.padded_to(cin_p), wp, z.padded_to(cout_p))
         bn = self.bn
         if training:
-            mean, invstd = ops.bn_batch_stats(z, BN_EPS, BN_MOM, bn.running_mean, bn.running_var)
-            bn.num_batches_tracked += 1
+            mean, invstd = ops.bn_batch_stats(z, BN_EPS, BN_MOM, bn.running_mean, bn.running_var, bn.num_batches_tracked)
         else:
             mean, invstd = ops.bn_eval_stats(bn.running_mean, bn.running_var, BN_EPS)
         drop = rng_.dropout_scale(z.n, z.c) if (self.dropout and training) else None
@@ -161,8 +160,8 @@ class Block:
             else:
                 dgam = dbet = None
                 acc = False
-            ops.bn_act_bwd(da, a, ctx["z"], ctx["mean"], ctx["invstd"], self.bn.weight.detach(), ctx["drop"], self.act,
-                           self.slope, dz, dgam, dbet, acc)
+            ops.bn_act_bwd(da, a, ctx["z"], ctx["mean"], ctx["invstd"], self.bn.weight.detach(), self.bn.bias.detach(), ctx["drop"],
+                           self.act, self.slope, dz, dgam, dbet, acc)
         elif self.act != ACT_NONE:
             dz = Act.empty(a.n, a.t, a.h, a.w, a.c, a.dtype)
             ops.act_bwd(da, a, self.act, self.slope, dz)

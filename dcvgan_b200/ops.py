@@ -269,15 +269,17 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def bn_batch_stats(z, eps, momentum, running_mean, running_var):
+def bn_batch_stats(z, eps, momentum, running_mean, running_var, num_batches_tracked=None):
     zp, ldz, rows, c = cl_view(z)
     nblk = lib().dcv_bn_stats_blocks(rows, c)
     partials = torch.empty((nblk, 2, c), dtype=torch.float32, device=z.device)
     mean = torch.empty(c, dtype=torch.float32, device=z.device)
     invstd = torch.empty_like(mean)
+    if num_batches_tracked is not None:
+        assert num_batches_tracked.dtype == torch.int64 and num_batches_tracked.is_cuda
     check(lib().dcv_bn_stats(dcv_dtype(z), zp, ldz, rows, c, partials.data_ptr(), _stream()))
     check(lib().dcv_bn_finalize(partials.data_ptr(), nblk, c, rows, eps, momentum, _p(running_mean), _p(running_var),
-                                mean.data_ptr(), invstd.data_ptr(), _stream()))
+                                _p(num_batches_tracked), mean.data_ptr(), invstd.data_ptr(), _stream()))
     return mean, invstd
 
 
@@ -298,7 +300,7 @@ def bn_act(z, mean, invstd, gamma, beta, drop, act, slope, out):
                            rows_per_n, act, slope, op, ldo, _stream()))
 
 
-def bn_act_bwd(da, a, z, mean, invstd, gamma, drop, act, slope, dz, dgamma, dbeta, accumulate=False):
+def bn_act_bwd(da, a, z, mean, invstd, gamma, beta, drop, act, slope, dz, dgamma, dbeta, accumulate=False):
     dap, ldda, rows, c = cl_view(da)
     ap, lda, _, _ = cl_view(a)
     zp, ldz, _, _ = cl_view(z)
@@ -309,11 +311,11 @@ def bn_act_bwd(da, a, z, mean, invstd, gamma, drop, act, slope, dz, dgamma, dbet
     sums = torch.empty((2, c), dtype=torch.float32, device=z.device)
     dt = dcv_dtype(z)
     check(lib().dcv_bn_act_bwd_reduce(dt, dap, ldda, ap, lda, zp, ldz, rows, c, mean.data_ptr(), invstd.data_ptr(),
-                                      _p(drop), rows_per_n, act, slope, partials.data_ptr(), _stream()))
+                                      _p(gamma), _p(beta), _p(drop), rows_per_n, act, slope, partials.data_ptr(), _stream()))
     check(lib().dcv_bn_bwd_finalize(partials.data_ptr(), nblk, c, sums.data_ptr(), _p(dgamma), _p(dbeta),
                                     int(accumulate), _stream()))
     check(lib().dcv_bn_act_bwd_apply(dt, dap, ldda, ap, lda, zp, ldz, rows, c, mean.data_ptr(), invstd.data_ptr(),
-                                     _p(gamma), _p(drop), rows_per_n, act, slope, sums.data_ptr(), rows, dzp, lddz,
+                                     _p(gamma), _p(beta), _p(drop), rows_per_n, act, slope, sums.data_ptr(), rows, dzp, lddz,
                                      _stream()))
 
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DCV_ABI_VERSION 2
+#define DCV_ABI_VERSION 3
 
 enum { DCV_F32 = 0, DCV_BF16 = 1 };
 /* activation selectors (generator.py:63,76,78,175,206,243,276; discriminator.py:82-99) */
@@ -128,9 +128,11 @@ int dcv_wgrad_reduce_sub(const dcv_geom* g, int impl, const void* ws, float* dw,
  */
 int dcv_bn_stats_blocks(int64_t rows, int C);
 int dcv_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float* partials, void* stream);
-/* mean/invstd from partials (biased var), running stats updated with unbiased var, momentum. */
+/* mean/invstd from partials (biased var), running stats updated with unbiased var, momentum;
+ * *num_batches_tracked += 1 on the device (nn.BatchNorm's counter) when the pointer is not NULL. */
 int dcv_bn_finalize(const float* partials, int nblk, int C, int64_t count, float eps, float momentum,
-                    float* running_mean, float* running_var, float* mean, float* invstd, void* stream);
+                    float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean,
+                    float* invstd, void* stream);
 /* eval mode: mean = running_mean, invstd = rsqrt(running_var + eps) */
 int dcv_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
                       float* mean, float* invstd, void* stream);
@@ -140,18 +142,20 @@ int dcv_bn_act(int dtype, const void* z, int64_t ldz, int64_t rows, int C, const
                const float* invstd, const float* gamma, const float* beta, const float* drop,
                int64_t rows_per_n, int act, float slope, void* a, int64_t lda, void* stream);
 /* backward: pass 1 reduces sum(du), sum(du*xhat) into partials [nblk][2][C]; pass 2 writes dz and,
- * from the reduced sums, dgamma/dbeta (fp32, (+)= if accumulate). du = da*act'(a)*drop. */
+ * from the reduced sums, dgamma/dbeta (fp32, (+)= if accumulate). du = da*act'(a)*drop.
+ * For (Leaky)ReLU the vectorised kernels take the sign of the pre-activation gamma*xhat+beta recomputed from z and
+ * do not read `a` (it must still be a valid pointer for the other activations and the scalar fallback kernels). */
 int dcv_bn_act_bwd_reduce(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda,
                           const void* z, int64_t ldz, int64_t rows, int C, const float* mean,
-                          const float* invstd, const float* drop, int64_t rows_per_n, int act,
-                          float slope, float* partials, void* stream);
+                          const float* invstd, const float* gamma, const float* beta, const float* drop,
+                          int64_t rows_per_n, int act, float slope, float* partials, void* stream);
 int dcv_bn_bwd_finalize(const float* partials, int nblk, int C, float* sums /*[2][C]*/, float* dgamma,
                         float* dbeta, int accumulate, void* stream);
 int dcv_bn_act_bwd_apply(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda,
                          const void* z, int64_t ldz, int64_t rows, int C, const float* mean,
-                         const float* invstd, const float* gamma, const float* drop, int64_t rows_per_n,
-                         int act, float slope, const float* sums, int64_t count, void* dz, int64_t lddz,
-                         void* stream);
+                         const float* invstd, const float* gamma, const float* beta, const float* drop,
+                         int64_t rows_per_n, int act, float slope, const float* sums, int64_t count, void* dz,
+                         int64_t lddz, void* stream);
 /* plain activation backward (no BN): dz = da * act'(a) ; a is the activated output */
 int dcv_act_bwd(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, int64_t rows, int C,
                 int act, float slope, void* dz, int64_t lddz, void* stream);

@@ -234,7 +234,9 @@ def test_batchnorm_act_dropout(dtype, act):
 
     za = to_act(z.detach(), dtype)
     rmd, rvd = rm.cuda(), rv.cuda()
-    mean, invstd = ops.bn_batch_stats(za, 1e-5, 0.1, rmd, rvd)
+    nbt = torch.tensor(7, dtype=torch.int64, device="cuda")
+    mean, invstd = ops.bn_batch_stats(za, 1e-5, 0.1, rmd, rvd, nbt)
+    assert int(nbt) == 8          # nn.BatchNorm's num_batches_tracked, incremented on the device
     aa = za.like()
     gd, bd, dd = gamma.detach().cuda(), beta.detach().cuda(), drop.cuda().contiguous()
     ops.bn_act(za, mean, invstd, gd, bd, dd, ACT_LEAKY, slope, aa)
@@ -244,8 +246,15 @@ def test_batchnorm_act_dropout(dtype, act):
     daa = to_act(da, dtype)
     dza = za.like()
     dg, db = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
-    ops.bn_act_bwd(daa, aa, za, mean, invstd, gd, dd, ACT_LEAKY, slope, dza, dg, db)
+    ops.bn_act_bwd(daa, aa, za, mean, invstd, gd, bd, dd, ACT_LEAKY, slope, dza, dg, db)
     assert rel_err(from_act(dza, 4), z.grad) < tol
+    # the vectorised (Leaky)ReLU kernels take the activation sign from z, never from `a`: poisoning `a` changes nothing
+    if c % 8 == 0:
+        dz2 = za.like()
+        junk = aa.like()
+        junk.base.fill_(float("nan"))
+        ops.bn_act_bwd(daa, junk, za, mean, invstd, gd, bd, dd, ACT_LEAKY, slope, dz2, dg, db)
+        assert torch.equal(dz2.base, dza.base)
     torch.cuda.synchronize()
     assert rel_err(dg.cpu(), gamma.grad) < tol and rel_err(db.cpu(), beta.grad) < tol
     # eval-mode statistics
