@@ -307,6 +307,20 @@ copy_cl_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst, in
   }
 }
 
+// narrow copies (C <= 8: image-like tensors into / out of channel slices): one thread per pixel, no per-element division
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256)
+copy_cl_rows_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst, int64_t ldd, int64_t rows, int C) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const TS* sp = src + r * lds; TD* dp = dst + r * ldd;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c < C) v[c] = ldf(sp + c);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c < C) stf(dp + c, v[c]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 frame_copy_kernel(T* __restrict__ clips, int64_t ldc, int N, int Tn, int64_t hw, int C, int t, const int* __restrict__ t_dev,
@@ -338,6 +352,9 @@ template <> struct VecIO<float> {
   __device__ static __forceinline__ void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  __device__ static __forceinline__ void unpack(const uint4& t, float (&v)[4]) {
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+  }
 };
 template <> struct VecIO<__nv_bfloat16> {
   static constexpr int N = 8;
@@ -358,6 +375,11 @@ template <> struct VecIO<__nv_bfloat16> {
       w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ static __forceinline__ void unpack(const uint4& t, float (&v)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
   }
 };
 
@@ -568,13 +590,27 @@ act_bwd_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__
   const VecMap m = vec_map<N>(rows, C);
   if (!m.active) return;
   const int c0 = m.cg * N;
-  for (int64_t row = m.rb + m.lane; row < m.re; row += m.lanes) {
-    float g[N], o[N];
-    VecIO<T>::load(da + row * ldda + c0, g);
-    VecIO<T>::load(a + row * lda + c0, o);
+  constexpr int U = 4;   // rows in flight per thread
+  for (int64_t row0 = m.rb + m.lane; row0 < m.re; row0 += (int64_t)m.lanes * U) {
+    uint4 rg[U], ro[U];
 #pragma unroll
-    for (int j = 0; j < N; ++j) g[j] *= act_grad_from_out(o[j], act, slope);
-    VecIO<T>::store(dz + row * lddz + c0, g);
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row < m.re) {
+        rg[u] = *reinterpret_cast<const uint4*>(da + row * ldda + c0);
+        ro[u] = *reinterpret_cast<const uint4*>(a + row * lda + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row >= m.re) continue;
+      float g[N], o[N];
+      VecIO<T>::unpack(rg[u], g); VecIO<T>::unpack(ro[u], o);
+#pragma unroll
+      for (int j = 0; j < N; ++j) g[j] *= act_grad_from_out(o[j], act, slope);
+      VecIO<T>::store(dz + row * lddz + c0, g);
+    }
   }
 }
 
@@ -585,15 +621,30 @@ axpy_vec_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __
   const VecMap m = vec_map<N>(rows, C);
   if (!m.active) return;
   const int c0 = m.cg * N;
-  for (int64_t row = m.rb + m.lane; row < m.re; row += m.lanes) {
-    float v[N], o[N];
-    VecIO<T>::load(x + row * ldx + c0, v);
-    if (accumulate) {
-      VecIO<T>::load(out + row * ldo + c0, o);
+  constexpr int U = 4;   // rows in flight per thread
+  for (int64_t row0 = m.rb + m.lane; row0 < m.re; row0 += (int64_t)m.lanes * U) {
+    uint4 rx[U], ro[U];
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] += o[j];
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row < m.re) {
+        rx[u] = *reinterpret_cast<const uint4*>(x + row * ldx + c0);
+        if (accumulate) ro[u] = *reinterpret_cast<const uint4*>(out + row * ldo + c0);
+      }
     }
-    VecIO<T>::store(out + row * ldo + c0, v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * m.lanes;
+      if (row >= m.re) continue;
+      float v[N], o[N];
+      VecIO<T>::unpack(rx[u], v);
+      if (accumulate) {
+        VecIO<T>::unpack(ro[u], o);
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] += o[j];
+      }
+      VecIO<T>::store(out + row * ldo + c0, v);
+    }
   }
 }
 
@@ -1045,6 +1096,9 @@ int dcv_copy_cl(int src_dtype, const void* src, int64_t lds, int dst_dtype, void
     copy_cl_kernel<float, __nv_bfloat16><<<nb, 256, 0, s>>>((const float*)src, lds, (__nv_bfloat16*)dst, ldd, rows, C);
   else if (dst_dtype == DCV_F32)
     copy_cl_kernel<__nv_bfloat16, float><<<nb, 256, 0, s>>>((const __nv_bfloat16*)src, lds, (float*)dst, ldd, rows, C);
+  else if (C <= 8)
+    copy_cl_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<ew_blocks(rows, 2), 256, 0, s>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst,
+                                                                                          ldd, rows, C);
   else
     copy_cl_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, 256, 0, s>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, rows, C);
   return check_launch("copy_cl");
