@@ -1442,6 +1442,10 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
       p.mt = mt;
     }
     if (getenv("DCV_TC_MT1")) p.mt = 1;
+    if (const char* e = getenv("DCV_TC_MT")) {      // tuning override: force 1 / 2 / 4 when legal
+      const int mt = atoi(e);
+      if ((mt == 1 || mt == 2 || mt == 4) && 2 * mt * p.bnt <= 512 && p.bn * mt <= 256 && c.N >= mt * p.bn && stages_of(mt) >= 2) p.mt = mt;
+    }
     p.tiles_n = ceil_div(c.N, p.bn * p.mt);
     p.items = (int)(sp_tiles * p.tiles_n);
     p.a_bytes = a_bytes_of(p.mt);

@@ -58,7 +58,10 @@ class Act:
                 ld = cp = (c + 15) // 16 * 16
                 zero = True
         numel = max(n * t * h * w * ld, 1)
-        base = (torch.zeros if zero else torch.empty)(numel, dtype=dtype, device="cuda")
+        if zero and ZERO_POOL is not None:
+            base = ZERO_POOL.get(numel, dtype)
+        else:
+            base = (torch.zeros if zero else torch.empty)(numel, dtype=dtype, device="cuda")
         return Act(base, 0, n, t, h, w, c, ld, cp)
 
     def padded_to(self, k):
@@ -118,6 +121,36 @@ class Act:
 
     def like(self, c=None, dtype=None):
         return Act.empty(self.n, self.t, self.h, self.w, self.c if c is None else c, self.dtype if dtype is None else dtype)
+
+
+class ZeroPool:
+    """Zero-padded scratch buffers that survive from one training iteration to the next.
+
+    A padded activation (1, 2, 3, 25 ... real channels in a 16-multiple pitch) must have zeros in its padding channels
+    and nothing on the path ever writes them: producers store the real channels only, the tensor-core epilogues store
+    exact zeros (zero weight rows).  So the 67 MB memsets of the image-sized buffers are needed once, not once per
+    iteration: the fused step asks for its padded buffers in a fixed order and gets the same, already padded, buffer
+    for the same request every iteration (and the CUDA graph of the step then contains no memset nodes for them).
+    """
+
+    def __init__(self):
+        self.bufs = {}      # (numel, dtype) -> [tensors]
+        self.cursor = {}
+
+    def begin_step(self):
+        self.cursor = {}
+
+    def get(self, numel, dtype):
+        key = (numel, dtype)
+        i = self.cursor.get(key, 0)
+        self.cursor[key] = i + 1
+        lst = self.bufs.setdefault(key, [])
+        if i == len(lst):
+            lst.append(torch.zeros(numel, dtype=dtype, device="cuda"))
+        return lst[i]
+
+
+ZERO_POOL = None   # set by the fused trainer step
 
 
 def cl_view(a):

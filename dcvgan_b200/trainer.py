@@ -159,6 +159,7 @@ class Trainer(object):
         self._graphs = {}           # (upd_d, upd_g, ggen.training, cgen.training) -> [eager runs so far, CUDAGraph, losses]
         self.use_cuda_graph = os.environ.get("DCV_NO_GRAPH", "0") != "1"
         self._pending = []          # device-side loss records waiting for the next log flush
+        self._zero_pool = ops.ZeroPool() if os.environ.get("DCV_NO_ZERO_POOL", "0") != "1" else None
         self.on_log_samples = None  # optional hooks for the (out-of-scope) visual logging / IS-FID evaluation
         self.on_evaluate = None
         self.save_classobj()
@@ -287,10 +288,14 @@ class Trainer(object):
             xc_real = xc_real.to(self.device, non_blocking=True)
             xg_real = xg_real.to(self.device, non_blocking=True)
         engine.WCACHE = self._wcache          # packed-weight cache owned by this trainer (keys are ids of its parameters)
+        if self._zero_pool is not None:
+            self._zero_pool.begin_step()
+        ops.ZERO_POOL = self._zero_pool       # zero-padded scratch buffers reused across iterations (ops.ZeroPool)
         try:
             return self._train_step(xc_real, xg_real, t_rand)
         finally:
             engine.WCACHE = None
+            ops.ZERO_POOL = None
 
     GRAPH_WARMUP = 2   # eager iterations per update pattern before capture (lazy module loads, smem opt-in, NCCL setup)
 

@@ -29,10 +29,24 @@ LAYERS.update({
     "vdis_stem_fwd": ("conv", 4, 64, (4, 4, 4), (1, 2, 2), (0, 1, 1), 32, (16, 64, 64), "fwd"),
     "vdis_stem_dgrad": ("conv", 4, 64, (4, 4, 4), (1, 2, 2), (0, 1, 1), 32, (16, 64, 64), "dgrad"),
     "ggen_last_fwd": ("convT", 64, 1, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 32, 32), "fwd"),
+    "up4_dgrad": ("convT", 256, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 16, 16), "dgrad"),
+    "up3_dgrad": ("convT", 512, 128, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 8, 8), "dgrad"),
+    "down0_dgrad": ("conv", 64, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 64, 64), "dgrad"),
+    "down1_dgrad": ("conv", 64, 128, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 32, 32), "dgrad"),
+    "vdis_main5_dgrad": ("conv", 128, 256, (4, 4, 4), (1, 2, 2), (0, 1, 1), 32, (10, 16, 16), "dgrad"),
+    "ggen_main9_fwd": ("convT", 128, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 16, 16), "fwd"),
+    "ggen_main6_fwd": ("convT", 256, 128, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 8, 8), "fwd"),
 })
-VARIANTS = [("base", {}), ("noA", {"DCV_TC_DBG": "1"}), ("noB", {"DCV_TC_DBG": "2"}), ("noAB", {"DCV_TC_DBG": "3"}),
+VARIANTS_FULL = [("base", {}), ("noA", {"DCV_TC_DBG": "1"}), ("noB", {"DCV_TC_DBG": "2"}), ("noAB", {"DCV_TC_DBG": "3"}),
             ("mt1", {"DCV_TC_MT1": "1"}), ("nopersist", {"DCV_TC_NOPERSIST": "1"}), ("nostore", {"DCV_TC_DBG": "4"}),
             ("noepi+noAB", {"DCV_TC_DBG": "11"}), ("nohalo", {"DCV_TC_NOHALO": "1"})]
+
+
+VARIANTS = [("base", {}), ("mt1", {"DCV_TC_MT": "1"}), ("mt2", {"DCV_TC_MT": "2"}), ("mt4", {"DCV_TC_MT": "4"}),
+            ("nohalo", {"DCV_TC_NOHALO": "1"}), ("nohalo,mt1", {"DCV_TC_NOHALO": "1", "DCV_TC_MT": "1"}),
+            ("nohalo,mt2", {"DCV_TC_NOHALO": "1", "DCV_TC_MT": "2"}), ("nohalo,mt4", {"DCV_TC_NOHALO": "1", "DCV_TC_MT": "4"})]
+if os.environ.get("EXP_FULL"):
+    VARIANTS = VARIANTS_FULL
 
 
 def build(name):
@@ -72,7 +86,7 @@ def timeit(fn, flush):
 
 def main():
     require_device()
-    names = sys.argv[1:] or ["vdis_main1_fwd", "vdis_main1_dgrad", "vdis_main5_fwd", "up5_fwd", "up5_dgrad", "up4_fwd", "up3_fwd",
+    names = sys.argv[1:] or ["up4_dgrad", "up3_dgrad", "down0_dgrad", "down1_dgrad", "vdis_main5_dgrad", "ggen_main9_fwd", "ggen_main6_fwd","vdis_main1_fwd", "vdis_main1_dgrad", "vdis_main5_fwd", "up5_fwd", "up5_dgrad", "up4_fwd", "up3_fwd",
                              "down0_fwd", "down1_fwd", "down2_fwd", "outconv_fwd", "outconv_dgrad", "inconv_fwd", "vdis_stem_fwd", "vdis_stem_dgrad",
                              "ggen_last_fwd"]
     flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device="cuda")
@@ -81,11 +95,11 @@ def main():
         fn, flops = build(name)
         cells = []
         for tag, env in VARIANTS:
-            for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1", "DCV_TC_NOPERSIST", "DCV_TC_NOHALO"):
+            for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1", "DCV_TC_NOPERSIST", "DCV_TC_NOHALO", "DCV_TC_MT"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             cells.append(timeit(fn, flush))
-        for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1", "DCV_TC_NOPERSIST", "DCV_TC_NOHALO"):
+        for k in ("DCV_TC_DBG", "DCV_TC_CPS", "DCV_TC_MT1", "DCV_TC_NOPERSIST", "DCV_TC_NOHALO", "DCV_TC_MT"):
             os.environ.pop(k, None)
         print(f"| {name} | {flops / 1e9:.1f} | " + " | ".join(f"{c:.3f}" for c in cells) + f" | {flops / cells[0] / 1e9:.0f} TF/s", flush=True)
 
