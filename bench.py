@@ -234,7 +234,7 @@ def dominant_kernel_probe(cfg, B, iters=20):
         times.append(e0.elapsed_time(e1))
     ms = float(np.mean(times))
     flops = 2.0 * (B * 10 * 16 * 16) * (2 * d) * (64 * d)
-    return {"kernel": "conv_tc_kernel (vdis main.1 Conv3d fwd)", "ms": ms, "tflops": flops / ms / 1e9, "flops": flops}
+    return {"kernel": "conv_tc_pers_kernel<4,1,2> (vdis main.1 Conv3d fwd)", "ms": ms, "tflops": flops / ms / 1e9, "flops": flops}
 
 
 def cpu_baseline(cfg_name, budget_s=25.0):

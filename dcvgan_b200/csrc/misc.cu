@@ -244,10 +244,18 @@ int dcv_gru_traj_bwd(const float* h0, const float* eps, const float* hs, const f
   DCV_REQUIRE(D >= 1 && D <= 64, "gru: dim_z_motion %d out of range [1,64]", D);
   const int G = 3 * D;
   const int per_warp = 3 * D + 4 * G + 2 * G * D + 2 * G;
-  int nw = 8;
-  while (nw > 1 && (size_t)nw * per_warp * sizeof(float) > 48 * 1024) nw /= 2;
-  DCV_REQUIRE((size_t)nw * per_warp * sizeof(float) <= 48 * 1024, "gru: dim_z_motion %d too large for BPTT kernel", D);
-  gru_bwd_kernel<<<1, nw * 32, nw * per_warp * sizeof(float), as_stream(stream)>>>(
+  // one warp per batch row when the per-warp accumulators fit (the time steps are serial and latency-bound: 8 warps took
+  // 170 us for B = 32, T = 16); the warps are summed in a fixed order, so the result stays deterministic
+  int nw = 32;
+  while (nw > 1 && (nw > B || (size_t)nw * per_warp * sizeof(float) > 200 * 1024)) nw /= 2;
+  DCV_REQUIRE((size_t)nw * per_warp * sizeof(float) <= 200 * 1024, "gru: dim_z_motion %d too large for BPTT kernel", D);
+  const size_t gru_smem = (size_t)nw * per_warp * sizeof(float);
+  static size_t gru_smem_set = 48 * 1024;
+  if (gru_smem > gru_smem_set) {
+    DCV_CUDA(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru_smem));
+    gru_smem_set = gru_smem;
+  }
+  gru_bwd_kernel<<<1, nw * 32, gru_smem, as_stream(stream)>>>(
       h0, eps, hs, dhs, w_ih, w_hh, b_ih, b_hh, B, T, D, dw_ih, dw_hh, db_ih, db_hh, accumulate);
   return check_launch("gru_bwd");
 }

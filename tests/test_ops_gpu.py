@@ -131,6 +131,30 @@ def test_conv_tcgen05(case):
     _run_case(_ops(), case, torch.bfloat16, True, 1e-2)
 
 
+VARIANT_ENVS = [{"DCV_TC_NOHALO": "1"}, {"DCV_TC_MT": "1"}, {"DCV_TC_MT": "4"}, {"DCV_TC_NO_TMA_STORE": "1"},
+                {"DCV_TC_NOPERSIST": "1"}, {"DCV_WGRAD_WAVES": "2"}]
+
+
+@pytest.mark.parametrize("env", VARIANT_ENVS, ids=["+".join(f"{k}={v}" for k, v in e.items()) for e in VARIANT_ENVS])
+@pytest.mark.parametrize("case", [TC_CASES[0], TC_CASES[5], TC_CASES[7], TC_CASES[9], TC_CASES[13], TC_CASES[14]],
+                         ids=lambda c: c[0])
+def test_conv_tcgen05_kernel_variants(case, env):
+    """Every tuning switch of the tcgen05 path (row-halo sharing off, forced M-tile counts, direct-store epilogue,
+    the non-persistent kernels, two split waves in wgrad) must give the same numbers as the default configuration:
+    each variant is checked against PyTorch like the default path."""
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        _run_case(_ops(), case, torch.bfloat16, True, 1e-2)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 PADDED_CASES = [
     ("pad_conv3d_3_32", "conv", 3, 32, (4, 4, 4), (1, 2, 2), (0, 1, 1), 2, (7, 16, 16)),
     ("pad_conv3d_1_32", "conv", 1, 32, (4, 4, 4), (1, 2, 2), (0, 1, 1), 3, (6, 16, 16)),
