@@ -689,8 +689,15 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int dh = r % p.bh; r /= p.bh;
     const int dt = r % p.bt; const int dn = r / p.bt;
     int acc = 0; uint32_t tfull_phase0 = 0u, tfull_phase1 = 0u;
-    const uint32_t stg_base = sbase + (uint32_t)(p.stages * stage_bytes);      // 2 x 16 KB staging buffers (TMA-store path)
+    const uint32_t stg_base = sbase + (uint32_t)(p.stages * stage_bytes);      // 4 warps x 2 x 4 KB staging buffers (TMA-store path)
     int nstore = 0;
+    int sub_w, sub_h, sub_t, sub_n;                                            // tile-local origin of this warp's 32 rows
+    {
+      int r0 = quarter * 32;
+      sub_w = r0 % p.bw; r0 /= p.bw;
+      sub_h = r0 % p.bh; r0 /= p.bh;
+      sub_t = r0 % p.bt; sub_n = r0 / p.bt;
+    }
     int item_first, item_count;
     cta_item_range(items, item_first, item_count);
     TileIter ti = tile_iter_init(p, item_first);
@@ -706,17 +713,20 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       tc_fence_after();
       const uint32_t d_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_cols);
       if (p.tma_store) {
-        // Coalesced path (bnt % 64 == 0): 64-channel chunks of a tile are staged in shared memory (128-byte rows, 128B
-        // swizzle -> conflict-free 16-byte writes) and written by one TMA store each; the tensor map does the sub-pixel
-        // scatter and clips rows / channels outside the tensor.  Direct 32-byte row stores from the TMEM registers ran
-        // at ~1.6 TB/s and cost half of the kernel time on the 64x64-pixel layers (profiles/r1h_summary.md).
-        const uint32_t swz_row = (uint32_t)row * 128u, swz_x = (uint32_t)(row & 7);
+        // Coalesced path (bnt % 64 == 0): every epilogue warp stages ITS 32 rows of a 64-channel chunk in shared memory
+        // (128-byte rows, 128B swizzle -> conflict-free 16-byte writes) and writes them with its own TMA store; the tensor
+        // map does the sub-pixel scatter and clips rows / channels outside the tensor.  No cross-warp barrier: the four
+        // warps drain TMEM independently.  (Direct 32-byte row stores from the TMEM registers ran at ~1.6 TB/s and cost
+        // half of the kernel time on the 64x64-pixel layers; one store per 128-row tile with two block barriers per
+        // chunk still limited the 1x1-like layers to 2.8 TB/s of output.)
+        const uint32_t swz_row = (uint32_t)lane * 128u, swz_x = (uint32_t)(lane & 7);
+        const uint32_t wbuf = stg_base + (uint32_t)quarter * 8192u;
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
           for (int cb = 0; cb < p.bnt; cb += 64) {
-            const uint32_t buf = stg_base + (uint32_t)(nstore & 1) * 16384u;
-            if (warp == 2 && lane == 0) tma_store_wait_read<1>();      // the store that last used this buffer has read it
-            epi_bar_sync();
+            const uint32_t buf = wbuf + (uint32_t)(nstore & 1) * 4096u;
+            if (lane == 0) tma_store_wait_read<1>();                   // this warp's store that last used the buffer has read it
+            __syncwarp();
             uint32_t v[32], w[32];
             tmem_ld32_nowait(d_base + (uint32_t)(m * p.bnt + cb), v);
             tmem_ld32_nowait(d_base + (uint32_t)(m * p.bnt + cb + 32), w);
@@ -738,9 +748,10 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               }
             }
             fence_async_smem();
-            epi_bar_sync();
-            if (warp == 2 && lane == 0 && !(p.dbg & 4)) {
-              tma_store_5d(&mapY, buf, nbase + cb, tc.w0 * f.osw + f.rw, tc.h0 * f.osh + f.rh, tc.t0 * f.ost + f.rt, tc.n0 + m * p.bn);
+            __syncwarp();
+            if (lane == 0 && !(p.dbg & 4)) {
+              tma_store_5d(&mapY, buf, nbase + cb, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
+                           (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
               tma_store_commit();
             }
             ++nstore;
@@ -776,7 +787,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (acc) tfull_phase1 ^= 1u; else tfull_phase0 ^= 1u;
       acc ^= 1;
     }
-    if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_all();            // bulk stores must complete before the CTA exits
+    if (p.tma_store && lane == 0) tma_store_wait_all();                         // every warp's bulk stores must complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -1465,7 +1476,14 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     if (p.tma_store) {
       // output map: {Nc channels, Ow, Oh, Ot, N}; box = one M tile x 64 channels; the traversal strides are the sub-pixel
       // phase strides of a transposed convolution / strided data gradient (1 for plain convolutions)
-      rc = make_act_map(&mapY, y, c.Nc, c.Ow, c.Oh, c.Ot, c.N, ldy, 64, p.bw, p.bh, p.bt, p.bn, f0.osw, f0.osh, f0.ost,
+      // box = the 32 tile rows one epilogue warp owns (tile extents are powers of two, so 32 consecutive rows are a box)
+      int rem = 32;
+      const int yw = p.bw < rem ? p.bw : rem; rem /= yw;
+      const int yh = p.bh < rem ? p.bh : rem; rem /= yh;
+      const int yt = p.bt < rem ? p.bt : rem; rem /= yt;
+      const int yn = p.bn < rem ? p.bn : rem; rem /= yn;
+      DCV_REQUIRE(rem == 1, "conv_tc: tile %dx%dx%dx%d has no 32-row sub-box", p.bw, p.bh, p.bt, p.bn);
+      rc = make_act_map(&mapY, y, c.Nc, c.Ow, c.Oh, c.Ot, c.N, ldy, 64, yw, yh, yt, yn, f0.osw, f0.osh, f0.ost,
                         CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }

@@ -36,6 +36,13 @@ LAYERS.update({
     "vdis_main5_dgrad": ("conv", 128, 256, (4, 4, 4), (1, 2, 2), (0, 1, 1), 32, (10, 16, 16), "dgrad"),
     "ggen_main9_fwd": ("convT", 128, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 16, 16), "fwd"),
     "ggen_main6_fwd": ("convT", 256, 128, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 8, 8), "fwd"),
+    # tap-folded formulations of the image-like layers (taps moved into the tiny channel dimension by a cheap pre-pass)
+    "fold_stem_fwd": ("conv", 16, 64, (4, 4, 1), (1, 2, 1), (0, 1, 0), 32, (16, 64, 32), "fwd"),
+    "fold_stem_dgrad": ("conv", 16, 64, (4, 4, 1), (1, 2, 1), (0, 1, 0), 32, (16, 64, 32), "dgrad"),
+    "fold_inconv_fwd": ("conv", 16, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), 512, (1, 64, 64), "fwd"),
+    "fold_inconv_dgrad": ("conv", 16, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), 512, (1, 64, 64), "dgrad"),
+    "fold_outconv_dgrad": ("conv", 32, 128, (1, 1, 1), (1, 1, 1), (0, 0, 0), 512, (1, 64, 64), "fwd"),
+    "fold_outconv_fwd": ("conv", 128, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0), 512, (1, 64, 64), "fwd"),
 })
 VARIANTS_FULL = [("base", {}), ("noA", {"DCV_TC_DBG": "1"}), ("noB", {"DCV_TC_DBG": "2"}), ("noAB", {"DCV_TC_DBG": "3"}),
             ("mt1", {"DCV_TC_MT1": "1"}), ("nopersist", {"DCV_TC_NOPERSIST": "1"}), ("nostore", {"DCV_TC_DBG": "4"}),

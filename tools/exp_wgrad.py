@@ -26,6 +26,9 @@ LAYERS = {
     "down1": ("conv", 64, 128, (1, 4, 4), (1, 2, 2), (0, 1, 1), 512, (1, 32, 32)),
     "outconv": ("convT", 128, 16, (1, 3, 3), (1, 1, 1), (0, 1, 1), 512, (1, 64, 64)),
     "inconv": ("conv", 16, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 512, (1, 64, 64)),
+    "fold_stem": ("conv", 16, 64, (4, 4, 1), (1, 2, 1), (0, 1, 0), B, (16, 64, 32)),
+    "fold_inconv": ("conv", 16, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), 512, (1, 64, 64)),
+    "fold_outconv": ("conv", 128, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0), 512, (1, 64, 64)),
 }
 
 
