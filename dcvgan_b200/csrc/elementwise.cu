@@ -648,6 +648,70 @@ axpy_vec_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __
   }
 }
 
+// ------------------------------------------------------------------------------------------ w-tap folding
+// Image-like stem inputs (1-5 real channels): the kw taps of a strided convolution are moved into the channel dimension
+// by a cheap pre-pass, X2[line][ow][k*cin + c] = x[line][ow*sw - pw + k][c] (zero outside the row), so that the
+// convolution proper has kw = 1, kt*kh taps and kw*cin real channels per tap instead of kt*kh*kw taps of `cin` real
+// channels in a 16-channel pitch: 4x fewer TMA boxes / MMAs for the 4x4(x4) stride-2 stems (they were bound by the
+// TMA request rate of 32-byte rows, not by bytes).  cin = cg + cc channels come from two tensors (geometry | colour);
+// the Noise layer of the image discriminator (x + sigma * N(0,1), fp32 noise dense [pixel][c]) is applied on the way.
+template <typename T>
+__global__ void __launch_bounds__(256)
+fold_w_kernel(const T* __restrict__ xg, int64_t ldg, int cg, const float* __restrict__ ng, const T* __restrict__ xc, int64_t ldc,
+              int cc, const float* __restrict__ nc, float sigma, int64_t lines, int W, int Ow, int kw, int sw, int pw,
+              T* __restrict__ out, int64_t ldo) {
+  const int cin = cg + cc;
+  const int64_t total = lines * Ow;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t line = i / Ow; const int ow = (int)(i - line * Ow);
+    T* o = out + i * ldo;
+    for (int k = 0; k < kw; ++k) {
+      const int iw = ow * sw - pw + k;
+      const bool ok = iw >= 0 && iw < W;
+      const int64_t px = line * W + iw;
+      for (int c = 0; c < cg; ++c) {
+        float v = 0.f;
+        if (ok) { v = ldf(xg + px * ldg + c); if (ng) v += sigma * ng[px * cg + c]; }
+        stf(o + k * cin + c, v);
+      }
+      for (int c = 0; c < cc; ++c) {
+        float v = 0.f;
+        if (ok) { v = ldf(xc + px * ldc + c); if (nc) v += sigma * nc[px * cc + c]; }
+        stf(o + k * cin + cg + c, v);
+      }
+    }
+  }
+}
+
+// adjoint: dx[line][w][c] = sum over (k, ow) with ow*sw - pw + k == w of dX2[line][ow][k*cin + c]
+template <typename T>
+__global__ void __launch_bounds__(256)
+unfold_w_kernel(const T* __restrict__ d2, int64_t ld2, int64_t lines, int W, int Ow, int kw, int sw, int pw, T* __restrict__ dxg,
+                int64_t ldg, int cg, T* __restrict__ dxc, int64_t ldc, int cc) {
+  const int cin = cg + cc;
+  const int64_t total = lines * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t line = i / W; const int w = (int)(i - line * W);
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (int k = 0; k < kw; ++k) {
+      const int num = w + pw - k;
+      if (num < 0 || num % sw) continue;
+      const int ow = num / sw;
+      if (ow >= Ow) continue;
+      const T* src = d2 + (line * Ow + ow) * ld2 + k * cin;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) if (c < cin) acc[c] += ldf(src + c);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c < cg) stf(dxg + i * ldg + c, acc[c]);
+      else if (c < cin) stf(dxc + i * ldc + (c - cg), acc[c]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ bf16 streaming variants
 // The generic vector kernels above hold every loaded row as 8 unpacked floats plus four per-channel constant vectors:
 // 95-127 registers, 2 CTAs per SM, ~32 KB of loads in flight per SM - they reached 2.8-3.0 TB/s where a plain copy
@@ -1082,6 +1146,30 @@ int dcv_frame_copy(int dtype, void* clips, int64_t ldc, int N, int T_, int64_t h
   DISPATCH_T(dtype, frame_copy_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(
                         (T*)clips, ldc, N, T_, hw, C, t, t_dev, (T*)frames, ldf, reverse, accumulate));
   return check_launch("frame_copy");
+}
+
+int dcv_fold_w(int dtype, const void* xg, int64_t ldg, int cg, const float* noise_g, const void* xc, int64_t ldc, int cc,
+               const float* noise_c, float sigma, int64_t lines, int W, int kw, int sw, int pw, void* out, int64_t ldo,
+               void* stream) {
+  DCV_REQUIRE(xg && xc && out, "fold_w: null pointer");
+  DCV_REQUIRE(cg >= 1 && cc >= 1 && cg + cc <= 8 && kw >= 1 && sw >= 1 && pw >= 0 && W + 2 * pw >= kw, "fold_w: bad shape (cg %d cc %d kw %d sw %d pw %d W %d)", cg, cc, kw, sw, pw, W);
+  DCV_REQUIRE(ldo >= (int64_t)kw * (cg + cc), "fold_w: output pitch %lld < %d folded channels", (long long)ldo, kw * (cg + cc));
+  const int Ow = (W + 2 * pw - kw) / sw + 1;
+  if (lines * Ow == 0) return 0;
+  DISPATCH_T(dtype, fold_w_kernel<T><<<ew_blocks(lines * Ow, 1), 256, 0, as_stream(stream)>>>(
+                        (const T*)xg, ldg, cg, noise_g, (const T*)xc, ldc, cc, noise_c, sigma, lines, W, Ow, kw, sw, pw, (T*)out, ldo));
+  return check_launch("fold_w");
+}
+
+int dcv_unfold_w(int dtype, const void* d2, int64_t ld2, int64_t lines, int W, int kw, int sw, int pw, void* dxg, int64_t ldg,
+                 int cg, void* dxc, int64_t ldc, int cc, void* stream) {
+  DCV_REQUIRE(d2 && dxg && dxc, "unfold_w: null pointer");
+  DCV_REQUIRE(cg >= 1 && cc >= 1 && cg + cc <= 8 && kw >= 1 && sw >= 1 && pw >= 0 && W + 2 * pw >= kw, "unfold_w: bad shape");
+  const int Ow = (W + 2 * pw - kw) / sw + 1;
+  if (lines * W == 0) return 0;
+  DISPATCH_T(dtype, unfold_w_kernel<T><<<ew_blocks(lines * W, 1), 256, 0, as_stream(stream)>>>(
+                        (const T*)d2, ld2, lines, W, Ow, kw, sw, pw, (T*)dxg, ldg, cg, (T*)dxc, ldc, cc));
+  return check_launch("unfold_w");
 }
 
 int dcv_copy_cl(int src_dtype, const void* src, int64_t lds, int dst_dtype, void* dst, int64_t ldd, int64_t rows, int C,

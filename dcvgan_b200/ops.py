@@ -228,27 +228,38 @@ def pack_weight(spec, g, direction, impl, weight):
     return out
 
 
+def conv_weight_part(weight, cl_off, cs_off, fold_k=None, fold_kw=1):
+    """Window description of one master conv weight (cs_cnt, cl_cnt, *k) inside a merged / folded packed matrix.
+    Plain: input channel c sits at activation channel cl_off + c, the weight's taps are the geometry's taps.
+    w-folded (fold_k = k of fold_kw taps along w moved into the channels, ops.fold_w): the geometry has kw = 1, its tap
+    index t' maps to the weight's tap t'*fold_kw + fold_k - i.e. a base offset of fold_k elements and a tap stride of
+    fold_kw."""
+    w = weight.detach() if weight.requires_grad else weight
+    assert w.is_contiguous() and w.dtype == torch.float32
+    cs_cnt, cl_cnt = w.shape[0], w.shape[1]
+    taps_full = w[0, 0].numel()
+    off = 0 if fold_k is None else fold_k
+    s_tap = 1 if fold_k is None else fold_kw
+    return (w, off, cl_off, cl_cnt, cs_off, cs_cnt, taps_full, cl_cnt * taps_full, s_tap)
+
+
 def pack_weight_merged(g, direction, impl, parts):
     """One packed matrix out of several master weights that each own a window of it (the two stem convolutions of a
     discriminator run as ONE convolution over [xg | xc] -> [hc | hg], discriminator.py:79-90,121-124,180-193,225-228).
-    parts: [(conv weight (cs_cnt, cl_cnt, *k), cl_off, cs_off)]; everything outside the windows is zero."""
+    parts: conv_weight_part(...) tuples; everything outside the windows is zero."""
     nbytes = lib().dcv_packed_weight_bytes(C.byref(g), direction, impl)
     if nbytes < 0:
         check(-1)
     out = torch.empty(nbytes, dtype=torch.uint8, device=parts[0][0].device)
-    taps = g.kt * g.kh * g.kw
-    for i, (weight, cl_off, cs_off) in enumerate(parts):
-        w = weight.detach()
-        assert w.is_contiguous() and w.dtype == torch.float32
-        cs_cnt, cl_cnt = w.shape[0], w.shape[1]
-        check(lib().dcv_pack_weight_sub(C.byref(g), direction, impl, w.data_ptr(), taps, cl_cnt * taps, 1, cl_off, cl_cnt,
+    for i, (w, off, cl_off, cl_cnt, cs_off, cs_cnt, s_l, s_s, s_tap) in enumerate(parts):
+        check(lib().dcv_pack_weight_sub(C.byref(g), direction, impl, w.data_ptr() + 4 * off, s_l, s_s, s_tap, cl_off, cl_cnt,
                                         cs_off, cs_cnt, int(i == 0), out.data_ptr(), _stream()))
     return out
 
 
 def wgrad_merged(g, xl, xs, parts, impl=None):
     """Weight gradient of a merged convolution: one pass over the activations leaves the split partial sums in the
-    workspace, then every master weight reduces its own window.  parts: [(dw (cs_cnt, cl_cnt, *k), cl_off, cs_off, accumulate)]"""
+    workspace, then every master weight reduces its own window.  parts: (conv_weight_part(dw, ...), accumulate)"""
     impl = choose_wgrad_impl(g, xl, xs) if impl is None else impl
     if TRACE is not None:
         TRACE.append(("wgrad", g.key(), 0, impl, xl.ld, xs.ld, xl.c, xs.c))
@@ -257,11 +268,8 @@ def wgrad_merged(g, xl, xs, parts, impl=None):
     lp, ldl, _, _ = cl_view(xl)
     sp, lds, _, _ = cl_view(xs)
     check(lib().dcv_wgrad_partial(C.byref(g), impl, dcv_dtype(xl), lp, ldl, sp, lds, ws.data_ptr(), nbytes, _stream()))
-    taps = g.kt * g.kh * g.kw
-    for dw, cl_off, cs_off, acc in parts:
-        assert dw.is_contiguous() and dw.dtype == torch.float32
-        cs_cnt, cl_cnt = dw.shape[0], dw.shape[1]
-        check(lib().dcv_wgrad_reduce_sub(C.byref(g), impl, ws.data_ptr(), dw.data_ptr(), taps, cl_cnt * taps, 1, cl_off,
+    for (dw, off, cl_off, cl_cnt, cs_off, cs_cnt, s_l, s_s, s_tap), acc in parts:
+        check(lib().dcv_wgrad_reduce_sub(C.byref(g), impl, ws.data_ptr(), dw.data_ptr() + 4 * off, s_l, s_s, s_tap, cl_off,
                                          cl_cnt, cs_off, cs_cnt, int(acc), _stream()))
 
 
@@ -364,6 +372,22 @@ def add_noise(x, noise, sigma, out):
     op, ldo, _, _ = cl_view(out)
     assert noise.dtype == torch.float32 and noise.is_contiguous() and noise.numel() == rows * c
     check(lib().dcv_add_noise(dcv_dtype(x), xp, ldx, noise.data_ptr(), sigma, rows, c, op, ldo, _stream()))
+
+
+def fold_w(xg, xc, out, kw, sw, pw, noise_g=None, noise_c=None, sigma=0.0):
+    """out (N,T,H,Ow, kw*(cg+cc)) <- [xg | xc] with the kw taps along w moved into the channel dimension (+ Noise)"""
+    assert xg.shape[:4] == xc.shape[:4] and out.c == kw * (xg.c + xc.c)
+    lines, w = xg.n * xg.t * xg.h, xg.w
+    assert out.rows == lines * ((w + 2 * pw - kw) // sw + 1)
+    check(lib().dcv_fold_w(dcv_dtype(xg), xg.ptr, xg.ld, xg.c, _p(noise_g), xc.ptr, xc.ld, xc.c, _p(noise_c), float(sigma), lines, w,
+                           kw, sw, pw, out.ptr, out.ld, _stream()))
+
+
+def unfold_w(d2, dxg, dxc, kw, sw, pw):
+    """adjoint of fold_w: dxg (N,T,H,W,cg), dxc (N,T,H,W,cc) <- d2 (N,T,H,Ow, kw*(cg+cc))"""
+    lines, w = dxg.n * dxg.t * dxg.h, dxg.w
+    check(lib().dcv_unfold_w(dcv_dtype(d2), d2.ptr, d2.ld, lines, w, kw, sw, pw, dxg.ptr, dxg.ld, dxg.c, dxc.ptr, dxc.ld, dxc.c,
+                             _stream()))
 
 
 def axpy(x, out, accumulate):

@@ -159,6 +159,17 @@ int dcv_bn_act_bwd_apply(int dtype, const void* da, int64_t ldda, const void* a,
 /* plain activation backward (no BN): dz = da * act'(a) ; a is the activated output */
 int dcv_act_bwd(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, int64_t rows, int C,
                 int act, float slope, void* dz, int64_t lddz, void* stream);
+/* w-tap folding for the image-like stem inputs of the discriminators (discriminator.py:79-90,180-193: conv_g on the
+ * geometry channels, conv_c on the colour channels, kernel 4, stride 2, pad 1 along w):
+ *   out[line][ow][k*(cg+cc) + c] = [xg | xc][line][ow*sw - pw + k][c]  (+ sigma*noise, the Noise layer), 0 outside the row
+ * lines = N*T*H rows of W pixels; out has Ow = (W + 2*pw - kw)/sw + 1 positions per line with pitch ldo.
+ * The stem convolution then runs with kw = 1 on kw*(cg+cc) real channels.  dcv_unfold_w is the adjoint (gradient w.r.t.
+ * xg and xc from the gradient w.r.t. the folded tensor). */
+int dcv_fold_w(int dtype, const void* xg, int64_t ldg, int cg, const float* noise_g, const void* xc, int64_t ldc, int cc,
+               const float* noise_c, float sigma, int64_t lines, int W, int kw, int sw, int pw, void* out, int64_t ldo,
+               void* stream);
+int dcv_unfold_w(int dtype, const void* d2, int64_t ld2, int64_t lines, int W, int kw, int sw, int pw, void* dxg, int64_t ldg,
+                 int cg, void* dxc, int64_t ldc, int cc, void* stream);
 /* Noise layer (discriminator.py:30-39): out = x + sigma*noise (noise fp32, dense [rows][C]) */
 int dcv_add_noise(int dtype, const void* x, int64_t ldx, const float* noise, float sigma, int64_t rows,
                   int C, void* out, int64_t ldo, void* stream);

@@ -149,8 +149,8 @@ def test_discriminators_match_oracle(precision, ftol, ctol, kind, noise):
 @pytest.mark.parametrize("kind", ["idis", "vdis"])
 @pytest.mark.parametrize("C,ndf", [(1, 64), (2, 64), (25, 48), (25, 64)])
 def test_merged_stems_equal_the_two_convolutions(kind, C, ndf):
-    """bf16 path: the stem pair run as one block-structured convolution over [xg | xc] (engine.MergedStem) against the
-    two separate stem convolutions of discriminator.py:79-90,180-193 - same logits and gradients up to bf16 rounding of
+    """bf16 path: the stem pair run as one block-structured convolution over [xg | xc] (engine.MergedStem), plain and
+    with the w taps folded into the channels (C = 1, 2: ops.fold_w), against the two separate stem convolutions of discriminator.py:79-90,180-193 - same logits and gradients up to bf16 rounding of
     identical fp32 accumulations (zero blocks add exact zeros)."""
     dcv, _, discriminator, _, _, _, engine = _mods()
     dcv.set_precision("bf16")
@@ -161,8 +161,9 @@ def test_merged_stems_equal_the_two_convolutions(kind, C, ndf):
     B = 3
     shape = (B, 16, 64, 64) if kind == "vdis" else (B, 64, 64)
     res = {}
-    for merged in (True, False):
-        engine.MERGE_STEMS = merged
+    for mode in ("folded", "merged", "separate"):
+        engine.MERGE_STEMS = mode != "separate"
+        engine.FOLD_STEMS = mode == "folded"
         try:
             gen = torch.Generator(device="cuda").manual_seed(8)
             xg = torch.randn((B, C) + shape[1:], generator=gen, device="cuda").requires_grad_(True)
@@ -171,10 +172,20 @@ def test_merged_stems_equal_the_two_convolutions(kind, C, ndf):
             y = mod(xg, xc)
             dy = torch.randn(y.shape, generator=gen, device="cuda")
             (y * dy).sum().backward()
-            res[merged] = (y.detach().clone(), xg.grad.clone(), xc.grad.clone(),
-                           {k: p.grad.clone() for k, p in mod.named_parameters()})
+            res[mode] = (y.detach().clone(), xg.grad.clone(), xc.grad.clone(),
+                         {k: p.grad.clone() for k, p in mod.named_parameters()})
         finally:
             engine.MERGE_STEMS = True
+            engine.FOLD_STEMS = True
+    (y0, g0, c0, p0) = res["separate"]
+    for mode in ("folded", "merged"):
+        (y1, g1, c1, p1) = res[mode]
+        assert rel_err(y1.cpu(), y0.cpu()) < 2e-2, (mode, rel_err(y1.cpu(), y0.cpu()))
+        assert cos_sim(g1.cpu(), g0.cpu()) > 0.995 and cos_sim(c1.cpu(), c0.cpu()) > 0.995, mode
+        worst = min(cos_sim(p1[k].cpu(), p0[k].cpu()) for k in p1)
+        print(f"{mode} stems {kind} C={C} ndf={ndf}: y {rel_err(y1.cpu(), y0.cpu()):.2e} worst param-grad cos {worst:.5f}")
+        assert worst > 0.995, (mode, worst)
+    return
     (y1, g1, c1, p1), (y0, g0, c0, p0) = res[True], res[False]
     assert rel_err(y1.cpu(), y0.cpu()) < 2e-2, rel_err(y1.cpu(), y0.cpu())
     assert cos_sim(g1.cpu(), g0.cpu()) > 0.995 and cos_sim(c1.cpu(), c0.cpu()) > 0.995
