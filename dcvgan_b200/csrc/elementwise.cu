@@ -61,7 +61,17 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ z, 
 __device__ __forceinline__ void warp_sum_partials(const float* __restrict__ partials, int nblk, int C, int c, double& s0, double& s1) {
   const int lane = threadIdx.x % 32;
   s0 = 0.0; s1 = 0.0;
-  for (int b = lane; b < nblk; b += 32) { s0 += partials[(int64_t)b * 2 * C + c]; s1 += partials[(int64_t)b * 2 * C + C + c]; }
+  // eight independent loads per round trip (the partials of one channel are 2*C floats apart: every load is its own
+  // sector, and a dependent load-add chain over up to 19 blocks per lane made these tiny kernels 5-9 us each)
+  int b = lane;
+  for (; b + 96 < nblk; b += 128) {
+    float v0[4], v1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { v0[u] = partials[(int64_t)(b + 32 * u) * 2 * C + c]; v1[u] = partials[(int64_t)(b + 32 * u) * 2 * C + C + c]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s0 += v0[u]; s1 += v1[u]; }
+  }
+  for (; b < nblk; b += 32) { s0 += partials[(int64_t)b * 2 * C + c]; s1 += partials[(int64_t)b * 2 * C + C + c]; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
 }
@@ -823,17 +833,27 @@ bn_act_bwd_apply_bf16_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda,
 
 // block-level reduction tail shared by the two bf16 reduce kernels: partials[b][0][c], partials[b][1][c]
 __device__ __forceinline__ void reduce2_tail(const VecMap& m, int C, float (&a0)[8], float (&a1)[8], float* __restrict__ partials) {
+  // tree over the row lanes of each channel group (fixed order -> deterministic); a serial loop in the lane-0 threads
+  // took ~7 us per block, the whole cost of the small layers' launches
   __shared__ float red[2][256][9];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { red[0][threadIdx.x][j] = a0[j]; red[1][threadIdx.x][j] = a1[j]; }
-  __syncthreads();
   const int CG = C / 8;
+  int span = 1;
+  while (span < m.lanes) span <<= 1;
+  for (int sft = span >> 1; sft >= 1; sft >>= 1) {
+    if (m.active && m.lane >= sft && m.lane < 2 * sft) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { red[0][threadIdx.x][j] = a0[j]; red[1][threadIdx.x][j] = a1[j]; }
+    }
+    __syncthreads();
+    if (m.active && m.lane < sft && m.lane + sft < m.lanes) {
+      const int src = (m.lane + sft) * CG + m.cg;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a0[j] += red[0][src][j]; a1[j] += red[1][src][j]; }
+    }
+    __syncthreads();
+  }
   if (m.active && m.lane == 0) {
     float* out = partials + (int64_t)blockIdx.x * 2 * C;
-    for (int l = 1; l < m.lanes; ++l) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { a0[j] += red[0][l * CG + m.cg][j]; a1[j] += red[1][l * CG + m.cg][j]; }
-    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { out[m.cg * 8 + j] = a0[j]; out[C + m.cg * 8 + j] = a1[j]; }
   }
