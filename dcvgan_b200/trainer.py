@@ -118,6 +118,47 @@ def dp_allreduce_grads(flat_nets):
     return 1.0 / world
 
 
+class GradReducer:
+    """Bucketed gradient all-reduce overlapped with the rest of the backward pass.
+
+    One bucket = one network's flat fp32 gradient buffer.  `launch(flat)` is called right after that network's last
+    weight gradient: the all-reduce is enqueued on a communication stream that first waits for an event recorded on
+    the compute stream at that point, so NCCL runs over NVLink while the compute stream continues with the next
+    network's backward (D phase: idis -> vdis -> gdis; G phase: cgen's reduction overlaps ggen's backward).  `wait()`
+    makes the compute stream wait for every outstanding bucket before the Adam kernels read the gradients.  Both
+    calls are stream/event operations only, so they are captured into the CUDA graph of the step as a fork/join.
+    On CPU tensors (gloo tests) the reduction is synchronous."""
+
+    def __init__(self):
+        self.stream = None
+        self.pending = []
+
+    def launch(self, flat):
+        if dp_world() == 1:
+            return
+        g = flat.flat_g
+        if not g.is_cuda:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            return
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.pending.append(done)
+
+    def wait(self):
+        cur = torch.cuda.current_stream() if self.pending else None
+        for ev in self.pending:
+            cur.wait_event(ev)
+        self.pending = []
+        return 1.0 / dp_world()
+
+
 def dp_seed(seed):
     """Replica r draws its latents / Noise / Dropout from seed + r (each replica is a valid reference step on its
     own shard); returns the seed used."""
@@ -160,6 +201,7 @@ class Trainer(object):
         self.use_cuda_graph = os.environ.get("DCV_NO_GRAPH", "0") != "1"
         self._pending = []          # device-side loss records waiting for the next log flush
         self._zero_pool = ops.ZeroPool() if os.environ.get("DCV_NO_ZERO_POOL", "0") != "1" else None
+        self._reducer = GradReducer()
         self.on_log_samples = None  # optional hooks for the (out-of-scope) visual logging / IS-FID evaluation
         self.on_evaluate = None
         self.save_classobj()
@@ -227,6 +269,22 @@ class Trainer(object):
 
     def _allreduce(self, names):
         dp_allreduce_grads([self._flat[n] for n in names])
+
+    def _reduce_launch(self, name):
+        """enqueue the all-reduce of one network's gradient bucket behind the kernels issued so far (overlaps what follows)"""
+        if self.world > 1:
+            # Measured on 8 B200s (profiles/r1m_bench_8gpu_*.json): 11.92 ms/step with the bucket reduced in-stream right
+            # here, 12.03 ms with the side-stream overlap - the persistent convolution kernels hold every SM (one CTA with
+            # ~220 KB of shared memory each), so NCCL's CTAs only get an SM between two of them and the "overlap" mostly
+            # delays both.  The in-stream form is therefore the default; DCV_DP_OVERLAP=1 selects the side stream.
+            if os.environ.get("DCV_DP_OVERLAP", "0") == "1":
+                self._reducer.launch(self._flat[name])
+            else:
+                self._allreduce([name])
+
+    def _reduce_wait(self):
+        if self.world > 1:
+            self._reducer.wait()
 
     def _to_clip(self, x):
         """(B,C,T,H,W) fp32 torch tensor -> channels-last Act (B,T,H,W,C)"""
@@ -365,7 +423,8 @@ class Trainer(object):
                 sink = engine.GradSink(self._flat[n].grad_of)
                 self._plans[n].backward(real[n][1], grads[n][0], sink, need_dx=False)
                 self._plans[n].backward(fake[n][1], grads[n][1], sink, need_dx=False)
-            self._allreduce(self._dnames)
+                self._reduce_launch(n)                  # this network's bucket travels while the next one's backward runs
+            self._reduce_wait()
             for n in self._dnames:
                 self._flat[n].adam_step(1.0 / self.world)
         del real, fake, grads
@@ -396,11 +455,13 @@ class Trainer(object):
                 ops.axpy(g_g, dxg, True)
             sink_c = engine.GradSink(self._flat["cgen"].grad_of)
             dxg_c = self._plans["cgen"].backward(cctx, dxc.reshape_nt(B * T, 1), sink_c, need_dx=True)
+            self._reduce_launch("cgen")                 # 10.6 M floats, reduced under ggen's backward
             if dxg_c is not None:
                 ops.axpy(dxg_c.reshape_nt(B, T), dxg, True)
             sink_g = engine.GradSink(self._flat["ggen"].grad_of)
             self._plans["ggen"].backward(gctx, dxg.reshape_nt(B * T, 1), sink_g)
-            self._allreduce(["ggen", "cgen"])
+            self._reduce_launch("ggen")
+            self._reduce_wait()
             self._flat["ggen"].adam_step(1.0 / self.world)
             self._flat["cgen"].adam_step(1.0 / self.world)
             self._flat["ggen"].adam_step(1.0 / self.world)                                      # trainer.py:357-359

@@ -36,6 +36,12 @@ def _worker(rank, world, port, out):
     for i, p in enumerate(model.parameters()):
         p.grad.fill_(float(rank + 1) * (i + 1))        # rank-specific gradient written through the views
     scale = trainer.dp_allreduce_grads([flat])
+    # the bucketed reducer of the fused step: launch per network, wait before Adam (synchronous on CPU tensors)
+    red = trainer.GradReducer()
+    flat2 = trainer._FlatNet(torch.nn.Linear(3, 2), torch.optim.Adam(torch.nn.Linear(3, 2).parameters()))
+    flat2.flat_g.fill_(float(rank + 1))
+    red.launch(flat2)
+    assert red.wait() == 0.5 and float(flat2.flat_g[0]) == 3.0
     seed = trainer.dp_seed(15)
     draw = torch.randn(3)
     out[rank] = (w0, flat.flat_g.clone(), scale, seed, draw, [float(p.grad.flatten()[0]) for p in model.parameters()])
