@@ -2,6 +2,7 @@
 // Dropout2d scaling, Noise, softmax, layout conversion, temporal difference.
 // Everything is channels-last with an explicit pixel stride, fp32 math, fp32 or bf16 storage.
 #include "common.cuh"
+#include <stdlib.h>
 #include <initializer_list>
 
 namespace dcv {
@@ -976,6 +977,10 @@ int dcv_bn_stats_blocks(int64_t rows, int C) {
 
 int dcv_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float* partials, void* stream) {
   const int nblk = dcv_bn_stats_blocks(rows, C);
+  if (getenv("DCV_EXP_SKIP_BN_STATS")) {      // timing experiment only: how much of the step is this pass?
+    cudaMemsetAsync(partials, 0, (size_t)nblk * 2 * C * sizeof(float), as_stream(stream));
+    return 0;
+  }
   DISPATCH_T(dtype, {
     if (sizeof(T) == 2 && vec_ok<T>(C, {z}, {ldz}))
       bn_stats_bf16_kernel<<<nblk, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, ldz, rows, C, partials);

@@ -200,6 +200,8 @@ struct TcConvP {
   int ntn, items, acc_cols;              // persistent kernel: N tiles, work items, TMEM columns of one accumulator set
   int tma_store;                         // persistent kernel: epilogue through shared memory + TMA store
   PhaseInfo phs[8];                      // persistent kernel: geometry of every sub-pixel phase (host-computed)
+  float* stats;                          // fused BatchNorm statistics: [4 * grid][2][npad] fp32 partial sums (NULL = off)
+  int npad;                              // padded output channels (stats row length)
   int hg, hcls;                          // row-halo sharing: taps per h class that share one A box (1 = off), h classes (nh / hg)
   int a_tile16;                          // M-tile stride inside the A box, in 16-byte units (rows incl. halo x row bytes)
   int dbg;                               // DCV_TC_DBG (timing experiments only): 1 = stop loading A, 2 = stop loading B after the first ring fill
@@ -691,6 +693,29 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     int acc = 0; uint32_t tfull_phase0 = 0u, tfull_phase1 = 0u;
     const uint32_t stg_base = sbase + (uint32_t)(p.stages * stage_bytes);      // 4 warps x 2 x 4 KB staging buffers (TMA-store path)
     int nstore = 0;
+    // fused BatchNorm batch statistics (sum, sum of squares per output channel over the bf16-rounded outputs): every warp
+    // owns one [2][npad] slot of p.stats and accumulates the channel pair (2*lane, 2*lane+1) of up to four 64-channel chunks
+    float* const st_slot = p.stats ? p.stats + (size_t)(blockIdx.x * 4 + quarter) * 2 * p.npad : nullptr;
+    float bs[4][2], bq[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { bs[i][0] = bs[i][1] = bq[i][0] = bq[i][1] = 0.f; }
+    int st_ntile = -1;
+    if (st_slot) {
+      for (int i = lane; i < 2 * p.npad; i += 32) st_slot[i] = 0.f;
+      __syncwarp();
+    }
+    auto st_flush = [&](int ntile) {
+      if (!st_slot || ntile < 0) return;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = ntile * p.bnt + i * 64 + 2 * lane;
+        if (i * 64 < p.bnt) {
+          st_slot[c] += bs[i][0]; st_slot[c + 1] += bs[i][1];
+          st_slot[p.npad + c] += bq[i][0]; st_slot[p.npad + c + 1] += bq[i][1];
+        }
+        bs[i][0] = bs[i][1] = bq[i][0] = bq[i][1] = 0.f;
+      }
+    };
     int sub_w, sub_h, sub_t, sub_n;                                            // tile-local origin of this warp's 32 rows
     {
       int r0 = quarter * 32;
@@ -721,9 +746,15 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         // chunk still limited the 1x1-like layers to 2.8 TB/s of output.)
         const uint32_t swz_row = (uint32_t)lane * 128u, swz_x = (uint32_t)(lane & 7);
         const uint32_t wbuf = stg_base + (uint32_t)quarter * 8192u;
+        if (st_slot && tc.ntile != st_ntile) { st_flush(st_ntile); st_ntile = tc.ntile; }
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-          for (int cb = 0; cb < p.bnt; cb += 64) {
+          // rows of this warp that are real output positions (TMA clips the others on store; the statistics must too)
+          const uint32_t rowmask = st_slot ? __ballot_sync(0xffffffffu, qw < f.Qw && qh < f.Qh && qt < f.Qt && tc.n0 + m * p.bn + dn < p.c.N) : 0u;
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+            const int cb = ci * 64;
+            if (cb >= p.bnt) break;
             const uint32_t buf = wbuf + (uint32_t)(nstore & 1) * 4096u;
             if (lane == 0) tma_store_wait_read<1>();                   // this warp's store that last used the buffer has read it
             __syncwarp();
@@ -749,6 +780,20 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
             fence_async_smem();
             __syncwarp();
+            if (st_slot) {
+              // column sums over this warp's 32 staged rows: lane l reads the bf16 pair (2l, 2l+1) of every row - 32
+              // distinct words per row (the swizzle only permutes 16-byte chunks inside the row), so no bank conflicts
+              const uint32_t cx = (uint32_t)(lane >> 2), co = (uint32_t)(lane & 3) * 4u;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                if (!((rowmask >> r) & 1u)) continue;
+                uint32_t wv;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(buf + (uint32_t)r * 128u + ((cx ^ (uint32_t)(r & 7)) << 4) + co));
+                const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xFFFF0000u);
+                bs[ci][0] += f0; bs[ci][1] += f1;
+                bq[ci][0] = fmaf(f0, f0, bq[ci][0]); bq[ci][1] = fmaf(f1, f1, bq[ci][1]);
+              }
+            }
             if (lane == 0 && !(p.dbg & 4)) {
               tma_store_5d(&mapY, buf, nbase + cb, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
                            (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
@@ -787,6 +832,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (acc) tfull_phase1 ^= 1u; else tfull_phase0 ^= 1u;
       acc ^= 1;
     }
+    st_flush(st_ntile);
     if (p.tma_store && lane == 0) tma_store_wait_all();                         // every warp's bulk stores must complete before the CTA exits
   }
   tc_fence_before();
@@ -1334,13 +1380,19 @@ int pack_weight_tc(const dcv_geom* g, int dir, const float* w, int64_t s_l, int6
   return check_launch("pack_weight_tc");
 }
 
+// stats != NULL: also accumulate per-channel sum / sum of squares of the outputs (fused BatchNorm statistics, persistent
+// TMA-store path only).  slots_out != NULL: planning query - store the number of [2][npad] partial-sum slots such a launch
+// writes (0 = this geometry cannot fuse the statistics) and return without launching anything.
 int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, int act,
-            float slope, cudaStream_t s) {
+            float slope, float* stats, int* slots_out, cudaStream_t s) {
+  if (slots_out) *slots_out = 0;
   DCV_REQUIRE(conv_tc_supported(g, dir), "conv_tc: geometry not supported by the tcgen05 kernel");
   TcConvP p;
   p.c = make_convp(g, dir);
   const ConvP& c = p.c;
   if (!c.scatter && c.wN == 1 && c.Kc % 8 == 0 && (ldx % 8) == 0 && (((uintptr_t)x) & 15) == 0 && !getenv("DCV_NO_GEMV")) {
+    if (slots_out) return 0;
+    DCV_REQUIRE(!stats, "conv_tc: fused statistics are not available for the single-channel head kernel");
     const int64_t M = (int64_t)c.N * c.Ot * c.Oh * c.Ow;          // one warp per logit
     head_gemv_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(c, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)wp,
                                                            (__nv_bfloat16*)y, ldy, act, slope);
@@ -1467,6 +1519,11 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     if (st > MAX_STAGES) st = MAX_STAGES;
     if (st < 1) st = 1;
     p.stages = st;
+    const int grid_p = p.items < num_sms ? p.items : num_sms;
+    const bool can_stats = p.tma_store && !getenv("DCV_TC_NO_FUSED_STATS");
+    if (slots_out) { *slots_out = can_stats ? 4 * grid_p : 0; return 0; }
+    DCV_REQUIRE(!stats || can_stats, "conv_tc: fused statistics need the TMA-store epilogue (output channels %% 64 == 0)");
+    p.stats = stats; p.npad = npad;
     rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh + p.hg - 1, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz);
     if (rc) return rc;
     rc = g4 ? make_weight_map(&mapB, wp, Kph, npad, phases, 64, p.bnt, CU_TENSOR_MAP_SWIZZLE_128B)
@@ -1497,12 +1554,14 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
       DCV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
       set = smem_p;
     }
-    const int grid_p = p.items < num_sms ? p.items : num_sms;
     fn<<<grid_p, TC_THREADS, smem_p, s>>>(mapA, mapB, mapY, p, (__nv_bfloat16*)y);
     return check_launch("conv_tc_pers");
   }
 
   // ---- non-persistent kernels (DCV_TC_NOPERSIST=1: kept for A/B timing)
+  if (slots_out) return 0;
+  DCV_REQUIRE(!stats, "conv_tc: fused statistics need the persistent kernel");
+  p.stats = nullptr; p.npad = npad;
   rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz);
   if (rc) return rc;
   if (g4) {

@@ -8,6 +8,8 @@ as the reference) and delegate here; trainer.py calls the same plans without aut
 Reference call stacks mirrored here: generator.py:84-141 (ggen), :361-435 (cgen),
 discriminator.py:106-127, :210-231, :309-333 (idis, vdis, gdis).
 """
+import os
+
 import torch
 
 from . import ops
@@ -15,6 +17,7 @@ from ._lib import ACT_LEAKY, ACT_NONE, ACT_TANH
 from .ops import Act, ConvSpec
 
 BN_EPS, BN_MOM = 1e-5, 0.1
+FUSED_BN_STATS = os.environ.get("DCV_FUSED_BN_STATS", "0") == "1"
 
 
 # ------------------------------------------------------------------------------------------ RNG
@@ -135,12 +138,22 @@ class Block:
         if self.bn is None:
             ops.conv(g, spec.fwd_dir, impl, x_used.padded_to(cin_p), wp, out.padded_to(cout_p), self.act, self.slope)
             return ctx
-        ops.conv(g, spec.fwd_dir, impl, x_used.padded_to(cin_p), wp, z.padded_to(cout_p))
         bn = self.bn
-        if training:
-            mean, invstd = ops.bn_batch_stats(z, BN_EPS, BN_MOM, bn.running_mean, bn.running_var, bn.num_batches_tracked)
+        zp = z.padded_to(cout_p)
+        # BatchNorm batch statistics accumulated in the convolution's epilogue (dcv_conv_stats): correct and tested, but
+        # measured SLOWER in the step than the separate streaming pass (11.49 vs 11.32 ms/step at batch 32): the large
+        # BatchNorm tensors belong to the small-K layers whose store epilogue is already on the critical path, and the
+        # 32-row column sums triple its instruction count.  Opt-in: FUSED_BN_STATS / DCV_FUSED_BN_STATS=1.
+        slots = ops.conv_stats_slots(g, spec.fwd_dir, x_used, zp) if (FUSED_BN_STATS and training and impl == ops.IMPL_TC and zp.c == z.c) else 0
+        if slots > 0:
+            partials = ops.conv_stats(g, spec.fwd_dir, x_used.padded_to(cin_p), wp, zp, slots)
+            mean, invstd = ops.bn_finalize(partials, z.rows, BN_EPS, BN_MOM, bn.running_mean, bn.running_var, bn.num_batches_tracked)
         else:
-            mean, invstd = ops.bn_eval_stats(bn.running_mean, bn.running_var, BN_EPS)
+            ops.conv(g, spec.fwd_dir, impl, x_used.padded_to(cin_p), wp, zp)
+            if training:
+                mean, invstd = ops.bn_batch_stats(z, BN_EPS, BN_MOM, bn.running_mean, bn.running_var, bn.num_batches_tracked)
+            else:
+                mean, invstd = ops.bn_eval_stats(bn.running_mean, bn.running_var, BN_EPS)
         drop = rng_.dropout_scale(z.n, z.c) if (self.dropout and training) else None
         ops.bn_act(z, mean, invstd, bn.weight.detach(), bn.bias.detach(), drop, self.act, self.slope, out)
         if save:

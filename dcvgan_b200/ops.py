@@ -285,6 +285,34 @@ def conv(g, direction, impl, x, wp, y, act=ACT_NONE, slope=0.0):
     check(lib().dcv_conv(C.byref(g), direction, impl, dcv_dtype(x), xp, ldx, wp.data_ptr(), yp, ldy, act, slope, _stream()))
 
 
+def conv_stats_slots(g, direction, x, y):
+    """> 0: the convolution can accumulate the BatchNorm batch statistics of its output in its epilogue (that many slots)"""
+    if _FORCE_SIMT or y.ptr % 16:
+        return 0
+    n = lib().dcv_conv_stats_slots(C.byref(g), direction, x.ld, y.ld)
+    return max(n, 0)
+
+
+def conv_stats(g, direction, x, wp, y, slots):
+    """y = correlate(x, wp) (no activation) + partial sums for dcv_bn_finalize; returns the fp32 (slots, 2, C) partials"""
+    if TRACE is not None:
+        TRACE.append(("conv", g.key(), direction, IMPL_TC, x.ld, y.ld, x.c, y.c))
+    partials = torch.empty((slots, 2, y.c), dtype=torch.float32, device=y.device)
+    check(lib().dcv_conv_stats(C.byref(g), direction, x.ptr, x.ld, wp.data_ptr(), y.ptr, y.ld, ACT_NONE, 0.0,
+                               partials.data_ptr(), slots, _stream()))
+    return partials
+
+
+def bn_finalize(partials, rows, eps, momentum, running_mean, running_var, num_batches_tracked=None):
+    """mean / invstd (+ running statistics) from (nblk, 2, C) partial sums"""
+    nblk, _, c = partials.shape
+    mean = torch.empty(c, dtype=torch.float32, device=partials.device)
+    invstd = torch.empty_like(mean)
+    check(lib().dcv_bn_finalize(partials.data_ptr(), nblk, c, rows, eps, momentum, _p(running_mean), _p(running_var),
+                                _p(num_batches_tracked), mean.data_ptr(), invstd.data_ptr(), _stream()))
+    return mean, invstd
+
+
 def choose_wgrad_impl(g, xl, xs):
     if not _FORCE_SIMT and xl.dtype == torch.bfloat16 and _tc_ok(xl) and _tc_ok(xs) and lib().dcv_wgrad_tc_supported(C.byref(g)):
         return IMPL_TC

@@ -106,6 +106,16 @@ int dcv_conv_tc_supported(const dcv_geom* g, int dir);
 int dcv_conv(const dcv_geom* g, int dir, int impl, int dtype, const void* x, int64_t ldx,
              const void* wp, void* y, int64_t ldy, int act, float slope, void* stream);
 
+/* Convolution with the BatchNorm batch statistics fused into its epilogue (Conv/ConvTranspose + BatchNorm pairs:
+ * generator.py:62-71,205-211,242-248; discriminator.py:94-99,197-204,289-302).  dcv_conv_stats_slots returns the number
+ * of fp32 [2][Cout_padded] partial-sum slots (sum, sum of squares per output channel of the bf16-rounded outputs) that
+ * dcv_conv_stats writes for this geometry and these pixel strides - 0 if the statistics cannot be fused (output channels
+ * not a multiple of 64, CUDA-core path, ...), in which case the caller runs dcv_conv + dcv_bn_stats.  The slots have the
+ * layout dcv_bn_finalize expects (nblk = slots, C = Cout_padded).  tcgen05 / bf16 only. */
+int dcv_conv_stats_slots(const dcv_geom* g, int dir, int64_t ldx, int64_t ldy);
+int dcv_conv_stats(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, int act,
+                   float slope, float* stats, int slots, void* stream);
+
 /* Weight gradient: dw[cl*s_l + cs*s_s + tap*s_tap] (+)= sum_m S[m,cs] * L[gather(m,tap),cl].
  * `ws` is scratch of dcv_wgrad_workspace_bytes(); split partial sums are reduced deterministically. */
 int64_t dcv_wgrad_workspace_bytes(const dcv_geom* g, int impl);

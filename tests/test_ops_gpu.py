@@ -458,3 +458,33 @@ def test_adam_matches_torch():
         assert rel_err(d.cpu(), r.detach()) < 1e-6
     for mm, r in zip(m, ref):
         assert rel_err(mm.cpu(), opt.state[r]["exp_avg"]) < 1e-6
+
+
+@pytest.mark.parametrize("case", [TC_CASES[0], TC_CASES[5], TC_CASES[7], TC_CASES[13], ("tc_convT_phase_edge", "convT", 64, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 3, (1, 12, 20))],
+                         ids=lambda c: c[0])
+def test_conv_fused_batchnorm_statistics(case):
+    """dcv_conv_stats: per-channel sum / sum of squares accumulated in the convolution's TMA-store epilogue equal the
+    statistics of the stored bf16 output (what dcv_bn_stats reads back), including tiles that overhang the tensor."""
+    ops = _ops()
+    from dcvgan_b200._lib import IMPL_TC
+    name, kind, cin, cout, k, s, p, n, sp = case
+    torch.manual_seed(5)
+    spec = ops.ConvSpec(kind, cin, cout, k, s, p)
+    x = bf16_round(torch.randn(n, cin, *sp))
+    w = bf16_round(torch.randn((cout, cin, *k) if kind == "conv" else (cin, cout, *k)) * 0.1)
+    g = spec.geom(n, sp)
+    xa = to_act(x, torch.bfloat16)
+    ya = ops.Act.empty(n, *spec.out_spatial(sp), cout, torch.bfloat16)
+    three_d = k[0] > 1
+    wdev = (w.squeeze(2) if (kind == "convT" or not three_d) else w).contiguous().cuda()
+    wp = ops.pack_weight(spec, g, spec.fwd_dir, IMPL_TC, wdev)
+    slots = ops.conv_stats_slots(g, spec.fwd_dir, xa, ya)
+    assert slots > 0, "64-multiple output channels must take the fused path"
+    partials = ops.conv_stats(g, spec.fwd_dir, xa, wp, ya, slots)
+    mean, invstd = ops.bn_finalize(partials, ya.rows, 1e-5, 0.1, None, None)
+    mean2, invstd2 = ops.bn_batch_stats(ya, 1e-5, 0.1, None, None)
+    y = from_act(ya)
+    y_ref = _torch_fwd(kind, x, w, s, p, three_d)
+    assert rel_err(y, y_ref) < 1e-2
+    assert rel_err(mean.cpu(), mean2.cpu()) < 1e-4 and rel_err(invstd.cpu(), invstd2.cpu()) < 1e-4, (
+        rel_err(mean.cpu(), mean2.cpu()), rel_err(invstd.cpu(), invstd2.cpu()))
