@@ -312,7 +312,9 @@ def run_cuda(args, cfg_name):
     def e2e_step(i):
         tr.iteration += 1
         xc, xg = host[i % nbuf]
-        l = tr.train_step(xc, xg)      # pinned host batch: the H2D copy (straight into the graph's static input) is inside the timed region
+        l = tr.train_step(xc, xg)      # pinned host batch: its H2D copy is inside the timed region (staged by the previous step's prefetch)
+        nxc, nxg = host[(i + 1) % nbuf]
+        tr.prefetch(nxc, nxg)          # next step's batch crosses PCIe on the copy stream while this step computes (Trainer.train does the same)
         loss_host.copy_(l, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the user reads the losses each step (trainer.py:326-328,363)
 

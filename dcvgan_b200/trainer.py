@@ -202,6 +202,7 @@ class Trainer(object):
         self._pending = []          # device-side loss records waiting for the next log flush
         self._zero_pool = ops.ZeroPool() if os.environ.get("DCV_NO_ZERO_POOL", "0") != "1" else None
         self._reducer = GradReducer()
+        self._copy_stream = None
         self.on_log_samples = None  # optional hooks for the (out-of-scope) visual logging / IS-FID evaluation
         self.on_evaluate = None
         self.save_classobj()
@@ -327,6 +328,47 @@ class Trainer(object):
         ops.loss_fwd_bwd_act(y, kind, losses[slot:slot + 1], accumulate, dy, 1.0)
         return dy
 
+    # ------------------------------------------------------------------ input prefetch
+    def prefetch(self, xc_host, xg_host):
+        """Start the host->device copy of a FUTURE batch (pinned host tensors) on a copy stream, so that it travels over
+        PCIe while the current iteration computes; `train_step` called later with the same two host tensors picks the
+        staged copy up instead of issuing a blocking H2D at its start.  The reference moves each batch with
+        `.to(device, non_blocking=True)` right before use (trainer.py:293-297), which serialises copy and compute.
+        Two staging slots are used alternately; a slot is not overwritten before the step that consumed it has read it."""
+        if xc_host.is_cuda:
+            return
+        self._prepare()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = [None, None]
+            self._stage_i = 0
+        i = self._stage_i
+        self._stage_i ^= 1
+        slot = self._stage[i]
+        if slot is None or slot["xc"].shape != xc_host.shape or slot["xg"].shape != xg_host.shape:
+            slot = self._stage[i] = {"xc": torch.empty(xc_host.shape, dtype=torch.float32, device=self.device),
+                                     "xg": torch.empty(xg_host.shape, dtype=torch.float32, device=self.device),
+                                     "ready": torch.cuda.Event(), "consumed": None}
+        if slot["consumed"] is not None:
+            self._copy_stream.wait_event(slot["consumed"])
+        with torch.cuda.stream(self._copy_stream):
+            slot["xc"].copy_(xc_host, non_blocking=True)
+            slot["xg"].copy_(xg_host, non_blocking=True)
+            slot["ready"].record(self._copy_stream)
+        slot["key"] = (xc_host.data_ptr(), xg_host.data_ptr())
+
+    def _take_prefetched(self, xc_real, xg_real):
+        """(device xc, device xg, slot) if this host batch was staged by prefetch(), else None"""
+        if xc_real.is_cuda or self._copy_stream is None:
+            return None
+        key = (xc_real.data_ptr(), xg_real.data_ptr())
+        for slot in self._stage:
+            if slot is not None and slot.get("key") == key:
+                slot["key"] = None
+                torch.cuda.current_stream().wait_event(slot["ready"])
+                return slot
+        return None
+
     def train_step(self, xc_real, xg_real, t_rand=None):
         """One iteration of trainer.py:279-363.  xc_real (B,3,T,64,64), xg_real (B,C,T,64,64) on the device.
         Returns a device tensor [loss_idis, loss_vdis, loss_gdis, loss_gen].
@@ -342,9 +384,15 @@ class Trainer(object):
         return self._eager_step(xc_real, xg_real, t_rand)
 
     def _eager_step(self, xc_real, xg_real, t_rand):
-        if not xc_real.is_cuda:      # host (pinned) batch: H2D copy as at trainer.py:293-297
-            xc_real = xc_real.to(self.device, non_blocking=True)
-            xg_real = xg_real.to(self.device, non_blocking=True)
+        if not xc_real.is_cuda:      # host (pinned) batch: H2D copy as at trainer.py:293-297 (or the copy staged by prefetch())
+            staged = self._take_prefetched(xc_real, xg_real)
+            if staged is not None:
+                xc_real, xg_real = staged["xc"].clone(), staged["xg"].clone()
+                staged["consumed"] = torch.cuda.Event()
+                staged["consumed"].record(torch.cuda.current_stream())
+            else:
+                xc_real = xc_real.to(self.device, non_blocking=True)
+                xg_real = xg_real.to(self.device, non_blocking=True)
         engine.WCACHE = self._wcache          # packed-weight cache owned by this trainer (keys are ids of its parameters)
         if self._zero_pool is not None:
             self._zero_pool.begin_step()
@@ -371,8 +419,15 @@ class Trainer(object):
                        torch.empty(xg_real.shape, dtype=torch.float32, device=self.device),
                        torch.zeros(1, dtype=torch.int32, device=self.device), torch.zeros(1, dtype=torch.int32).pin_memory())
         gxc, gxg, t_dev, t_host = slot[3]
-        gxc.copy_(xc_real, non_blocking=True)
-        gxg.copy_(xg_real, non_blocking=True)
+        staged = self._take_prefetched(xc_real, xg_real)
+        if staged is not None:            # device-to-device from the staging slot (the PCIe copy already happened)
+            gxc.copy_(staged["xc"], non_blocking=True)
+            gxg.copy_(staged["xg"], non_blocking=True)
+            staged["consumed"] = torch.cuda.Event()
+            staged["consumed"].record(torch.cuda.current_stream())
+        else:
+            gxc.copy_(xc_real, non_blocking=True)
+            gxg.copy_(xg_real, non_blocking=True)
         t_host[0] = t_rand
         t_dev.copy_(t_host, non_blocking=True)
         if slot[1] is None:
@@ -503,11 +558,15 @@ class Trainer(object):
         cfg = self.configs
         for _ in range(cfg["n_epochs"]):
             self.epoch += 1
-            for batch in iter(self.dataloader):
+            it = iter(self.dataloader)
+            batch = next(it, None)
+            while batch is not None:
                 self.iteration += 1
-                xc_real = batch["color"].to(self.device, non_blocking=True)
-                xg_real = batch[self.geometric_info].to(self.device, non_blocking=True)
+                xc_real, xg_real = batch["color"], batch[self.geometric_info]
                 losses = self.train_step(xc_real, xg_real)
+                batch = next(it, None)
+                if batch is not None and not batch["color"].is_cuda and batch["color"].is_pinned():
+                    self.prefetch(batch["color"], batch[self.geometric_info])   # next batch crosses PCIe under this iteration
                 self._pending.append((self.iteration, self.epoch, losses))
                 if self.iteration % cfg["snapshot_interval"] == 0:
                     self.save_params()
