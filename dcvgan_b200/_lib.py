@@ -40,6 +40,7 @@ SIGNATURES = {
     "dcv_launch_count": (C.c_longlong, []),
     "dcv_packed_weight_bytes": (_i64, [_G, _i, _i]),
     "dcv_pack_weight": (_i, [_G, _i, _i, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "dcv_pack_weight_batch": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dcv_pack_weight_sub": (_i, [_G, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp]),
     "dcv_conv_tc_supported": (_i, [_G, _i]),
     "dcv_conv": (_i, [_G, _i, _i, _i, _vp, _i64, _vp, _vp, _i64, _i, _f, _vp]),

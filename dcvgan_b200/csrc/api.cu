@@ -38,6 +38,8 @@ int wgrad_simt_splits(const dcv_geom*);
 int wgrad_tc_splits(const dcv_geom*);
 int wgrad_reduce_win(const float*, int, const dcv_geom*, WeightWin, float*, int64_t, int64_t, int64_t, int, cudaStream_t);
 int conv_tc_supported(const dcv_geom*, int);
+int pack_weight_tc_batch(int, const dcv_geom* const*, const int*, const float* const*, const int64_t*, const int64_t*, const int64_t*,
+                         void* const*, cudaStream_t);
 int64_t packed_weight_tc_bytes(const dcv_geom*, int);
 int pack_weight_tc(const dcv_geom*, int, const float*, int64_t, int64_t, int64_t, WeightWin, void*, cudaStream_t);
 int conv_tc(const dcv_geom*, int, const void*, int64_t, const void*, void*, int64_t, int, float, float*, int*, cudaStream_t);
@@ -106,6 +108,16 @@ int dcv_pack_weight_sub(const dcv_geom* g, int dir, int impl, const float* w, in
   WeightWin win; win.cl_off = cl_off; win.cl_cnt = cl_cnt; win.cs_off = cs_off; win.cs_cnt = cs_cnt; win.fill = fill_outside;
   if (impl == DCV_IMPL_TC) return pack_weight_tc(g, dir, w, s_l, s_s, s_tap, win, out, as_stream(stream));
   return pack_weight_simt(g, dir, w, s_l, s_s, s_tap, win, (float*)out, as_stream(stream));
+}
+
+int dcv_pack_weight_batch(int n, const dcv_geom* const* geoms, const int* dirs, const float* const* w, const int64_t* s_l,
+                          const int64_t* s_s, const int64_t* s_tap, void* const* outs, void* stream) {
+  DCV_REQUIRE(n >= 0 && (n == 0 || (geoms && dirs && w && s_l && s_s && s_tap && outs)), "pack_weight_batch: null array");
+  for (int i = 0; i < n; ++i) {
+    if (int rc = check_geom(geoms[i])) return rc;
+    DCV_REQUIRE(w[i] && outs[i], "pack_weight_batch: null pointer in job %d", i);
+  }
+  return pack_weight_tc_batch(n, geoms, dirs, w, s_l, s_s, s_tap, outs, as_stream(stream));
 }
 
 int dcv_conv_tc_supported(const dcv_geom* g, int dir) {

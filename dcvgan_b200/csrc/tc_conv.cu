@@ -1252,33 +1252,56 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
 // ------------------------------------------------------------------------------------------ packing
 // gather : out[n][tap][k]                 (n < npad, k < Kc)
 // scatter: out[phase][n][j][k]            (j = tap-in-phase index in the kernel's loop order)
-__global__ void __launch_bounds__(256)
-pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap, WeightWin win,
-                      int npad, int phases, __nv_bfloat16* __restrict__ out) {
+__device__ __forceinline__ void pack_weight_tc_elem(const ConvP& c, const float* __restrict__ w, int64_t s_l, int64_t s_s,
+                                                    int64_t s_tap, const WeightWin& win, int npad, int64_t i,
+                                                    __nv_bfloat16* __restrict__ out) {
   // one thread per (phase, n, k): it walks the taps of its phase, so the fp32 reads of a thread fall into one or two
   // cache lines (taps are the innermost dimension of the PyTorch layouts) and the bf16 writes of a warp are contiguous in k
   const int64_t per_phase_nk = (int64_t)npad * c.Kc;
-  const int64_t total = per_phase_nk * phases;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ph = (int)(i / per_phase_nk);
-    const int64_t r = i - (int64_t)ph * per_phase_nk;
-    const int k = (int)(r % c.Kc); const int n = (int)(r / c.Kc);
-    const PhaseInfo f = make_phase(c, ph);
-    const int ntaps = f.nt * f.nh * f.nw;
-    // gather: reduction channel k is an L channel, produced channel n is an S channel; scatter: swapped
-    const int cl = c.scatter ? n : k, cs = c.scatter ? k : n;
-    const bool real = win.has(cl, cs);
-    if (!real && !win.fill) continue;
-    const float* wb = w + (cl - win.cl_off) * s_l + (cs - win.cs_off) * s_s;
-    __nv_bfloat16* ob = out + ((int64_t)ph * npad + n) * ntaps * c.Kc + k;
-    int j = 0;
-    for (int jt = 0; jt < f.nt; ++jt)
-      for (int jh = 0; jh < f.nh; ++jh)
-        for (int jw = 0; jw < f.nw; ++jw, ++j) {
-          const int tap = ((f.a0t + f.ast * jt) * c.kh + (f.a0h + f.ash * jh)) * c.kw + (f.a0w + f.asw * jw);
-          ob[(int64_t)j * c.Kc] = __float2bfloat16_rn(real ? wb[tap * s_tap] : 0.f);
-        }
-  }
+  const int ph = (int)(i / per_phase_nk);
+  const int64_t r = i - (int64_t)ph * per_phase_nk;
+  const int k = (int)(r % c.Kc); const int n = (int)(r / c.Kc);
+  const PhaseInfo f = make_phase(c, ph);
+  const int ntaps = f.nt * f.nh * f.nw;
+  // gather: reduction channel k is an L channel, produced channel n is an S channel; scatter: swapped
+  const int cl = c.scatter ? n : k, cs = c.scatter ? k : n;
+  const bool real = win.has(cl, cs);
+  if (!real && !win.fill) return;
+  const float* wb = w + (cl - win.cl_off) * s_l + (cs - win.cs_off) * s_s;
+  __nv_bfloat16* ob = out + ((int64_t)ph * npad + n) * ntaps * c.Kc + k;
+  int j = 0;
+  for (int jt = 0; jt < f.nt; ++jt)
+    for (int jh = 0; jh < f.nh; ++jh)
+      for (int jw = 0; jw < f.nw; ++jw, ++j) {
+        const int tap = ((f.a0t + f.ast * jt) * c.kh + (f.a0h + f.ash * jh)) * c.kw + (f.a0w + f.asw * jw);
+        ob[(int64_t)j * c.Kc] = __float2bfloat16_rn(real ? wb[tap * s_tap] : 0.f);
+      }
+}
+
+__global__ void __launch_bounds__(256)
+pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap, WeightWin win,
+                      int npad, int phases, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)npad * c.Kc * phases;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    pack_weight_tc_elem(c, w, s_l, s_s, s_tap, win, npad, i, out);
+}
+
+// Many weights in one launch (all layers of a network after its Adam step): the jobs travel as a kernel parameter
+// (<= 4 KB), a block finds its job by scanning the block offsets.  ~90 single packs per iteration were ~90 tiny launches.
+constexpr int PACK_BATCH_MAX = 20;
+struct PackJob {
+  ConvP c; const float* w; int64_t s_l, s_s, s_tap; WeightWin win; int npad, phases; __nv_bfloat16* out; int64_t total; int block0;
+};
+struct PackBatch { int n; PackJob jobs[PACK_BATCH_MAX]; };
+
+__global__ void __launch_bounds__(256)
+pack_weight_tc_batch_kernel(const __grid_constant__ PackBatch b) {
+  int ji = 0;
+  while (ji + 1 < b.n && (int)blockIdx.x >= b.jobs[ji + 1].block0) ++ji;
+  const PackJob& j = b.jobs[ji];
+  const int nblocks = (ji + 1 < b.n ? b.jobs[ji + 1].block0 : (int)gridDim.x) - j.block0;
+  for (int64_t i = (int64_t)(blockIdx.x - j.block0) * blockDim.x + threadIdx.x; i < j.total; i += (int64_t)nblocks * blockDim.x)
+    pack_weight_tc_elem(j.c, j.w, j.s_l, j.s_s, j.s_tap, j.win, j.npad, i, j.out);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -1378,6 +1401,31 @@ int pack_weight_tc(const dcv_geom* g, int dir, const float* w, int64_t s_l, int6
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
   pack_weight_tc_kernel<<<blocks, 256, 0, s>>>(c, w, s_l, s_s, s_tap, win, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
   return check_launch("pack_weight_tc");
+}
+
+int pack_weight_tc_batch(int n, const dcv_geom* const* geoms, const int* dirs, const float* const* w, const int64_t* s_l,
+                         const int64_t* s_s, const int64_t* s_tap, void* const* outs, cudaStream_t s) {
+  int i = 0;
+  while (i < n) {
+    PackBatch b; b.n = 0;
+    int blocks = 0;
+    for (; i < n && b.n < PACK_BATCH_MAX; ++i) {
+      const dcv_geom* g = geoms[i];
+      DCV_REQUIRE(conv_tc_supported(g, dirs[i]), "pack_weight_batch: job %d not supported by the tcgen05 kernel", i);
+      PackJob& j = b.jobs[b.n++];
+      j.c = make_convp(g, dirs[i]);
+      j.w = w[i]; j.s_l = s_l[i]; j.s_s = s_s[i]; j.s_tap = s_tap[i]; j.win = full_window(g);
+      j.npad = tc_npad(j.c.Nc); j.phases = j.c.scatter ? g->st * g->sh * g->sw : 1;
+      j.out = (__nv_bfloat16*)outs[i];
+      j.total = (int64_t)j.npad * j.c.Kc * j.phases;
+      j.block0 = blocks;
+      int nb = (int)((j.total + 255) / 256); if (nb > 148 * 2) nb = 148 * 2;
+      blocks += nb;
+    }
+    pack_weight_tc_batch_kernel<<<blocks, 256, 0, s>>>(b);
+    if (int rc = check_launch("pack_weight_tc_batch")) return rc;
+  }
+  return 0;
 }
 
 // stats != NULL: also accumulate per-channel sum / sum of squares of the outputs (fused BatchNorm statistics, persistent

@@ -91,15 +91,32 @@ class GradSink:
 WCACHE = None
 
 
+# Batch packing: PACK_GROUP maps id(weight) -> the group (network) it belongs to, PACK_LOG[group] remembers every
+# (spec, geometry, direction, weight) that was ever packed for the group.  A cache miss on one weight then re-packs the
+# WHOLE group in one launch (ops.pack_weight_batch) - after a network's Adam step all its packs are stale together.
+PACK_GROUP = None
+PACK_LOG = None     # owned by the trainer like WCACHE (group -> {key: job})
+
+
 def packed_weight(spec, g, direction, impl, weight):
     if WCACHE is None:
         return ops.pack_weight(spec, g, direction, impl, weight)
     per = WCACHE.setdefault(id(weight), {})
     key = (g.key(), direction, impl)
     wp = per.get(key)
-    if wp is None:
+    if wp is not None:
+        return wp
+    group = PACK_GROUP.get(id(weight)) if (PACK_GROUP is not None and impl == ops.IMPL_TC) else None
+    if group is None:
         wp = per[key] = ops.pack_weight(spec, g, direction, impl, weight)
-    return wp
+        return wp
+    log = PACK_LOG.setdefault(group, {})
+    log.setdefault((id(weight),) + key, (spec, g, direction, weight))
+    jobs = [(k, j) for k, j in log.items() if (k[1:]) not in WCACHE.get(k[0], {})]
+    outs = ops.pack_weight_batch([j for _, j in jobs])
+    for (k, _), o in zip(jobs, outs):
+        WCACHE.setdefault(k[0], {})[k[1:]] = o
+    return per[key]
 
 
 def invalidate_packed(params):

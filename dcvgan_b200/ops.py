@@ -273,6 +273,27 @@ def wgrad_merged(g, xl, xs, parts, impl=None):
                                          cl_cnt, cs_off, cs_cnt, int(acc), _stream()))
 
 
+def pack_weight_batch(jobs):
+    """jobs: [(spec, g, direction, weight)] (tcgen05 impl, whole weights) -> [packed uint8 tensors], ONE kernel launch"""
+    n = len(jobs)
+    outs = []
+    for spec, g, direction, weight in jobs:
+        nbytes = lib().dcv_packed_weight_bytes(C.byref(g), direction, IMPL_TC)
+        if nbytes < 0:
+            check(-1)
+        outs.append(torch.empty(nbytes, dtype=torch.uint8, device=weight.device))
+    gp = (C.POINTER(Geom) * n)(*[C.pointer(j[1]) for j in jobs])
+    dirs = (C.c_int * n)(*[j[2] for j in jobs])
+    ws = (C.c_void_p * n)(*[j[3].detach().data_ptr() for j in jobs])
+    st = [j[0].weight_strides() for j in jobs]
+    sl = (C.c_int64 * n)(*[x[0] for x in st])
+    ss = (C.c_int64 * n)(*[x[1] for x in st])
+    stp = (C.c_int64 * n)(*[x[2] for x in st])
+    op = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    check(lib().dcv_pack_weight_batch(n, gp, dirs, ws, sl, ss, stp, op, _stream()))
+    return outs
+
+
 TRACE = None   # set to a list to record every conv / wgrad call (tools/layer_bench.py)
 
 

@@ -261,6 +261,10 @@ class Trainer(object):
         for n in names[2:]:
             self._plans[n] = engine.DisPlan(self.models[n], n)
         self._dnames = names[2:]
+        self._pack_group = {id(p): n for n in names for p in self.models[n].parameters()}
+        self._pack_log = {}
+        if os.environ.get("DCV_NO_BATCH_PACK", "0") == "1":
+            self._pack_group = None
         self.world = dp_world()
         self.dtype = ops.torch_dtype(self.models["ggen"].precision)
         if self.world > 1:
@@ -394,6 +398,8 @@ class Trainer(object):
                 xc_real = xc_real.to(self.device, non_blocking=True)
                 xg_real = xg_real.to(self.device, non_blocking=True)
         engine.WCACHE = self._wcache          # packed-weight cache owned by this trainer (keys are ids of its parameters)
+        engine.PACK_GROUP = self._pack_group  # a miss re-packs every logged weight of the same network in one launch
+        engine.PACK_LOG = self._pack_log
         if self._zero_pool is not None:
             self._zero_pool.begin_step()
         ops.ZERO_POOL = self._zero_pool       # zero-padded scratch buffers reused across iterations (ops.ZeroPool)
@@ -401,6 +407,8 @@ class Trainer(object):
             return self._train_step(xc_real, xg_real, t_rand)
         finally:
             engine.WCACHE = None
+            engine.PACK_GROUP = None
+            engine.PACK_LOG = None
             ops.ZERO_POOL = None
 
     GRAPH_WARMUP = 2   # eager iterations per update pattern before capture (lazy module loads, smem opt-in, NCCL setup)

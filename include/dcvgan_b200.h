@@ -88,6 +88,11 @@ int64_t dcv_packed_weight_bytes(const dcv_geom* g, int dir, int impl);
 int dcv_pack_weight(const dcv_geom* g, int dir, int impl, const float* w, int64_t s_l, int64_t s_s,
                     int64_t s_tap, void* out, void* stream);
 
+/* n tcgen05 packs (whole weights, DCV_IMPL_TC) in one kernel launch: all layers of a network after its optimizer step
+ * (train.py:167-176 builds one Adam per network).  Arrays of length n; outs[i] has dcv_packed_weight_bytes(geoms[i], dirs[i], TC) bytes. */
+int dcv_pack_weight_batch(int n, const dcv_geom* const* geoms, const int* dirs, const float* const* w, const int64_t* s_l,
+                          const int64_t* s_s, const int64_t* s_tap, void* const* outs, void* stream);
+
 /* Same, for ONE master weight that occupies only a window of the packed matrix - activation channels
  * [cl_off, cl_off+cl_cnt) x [cs_off, cs_off+cs_cnt) - as when the two stem convolutions of a discriminator
  * (conv_g on the geometry channels, conv_c on the colour channels, discriminator.py:79-90,180-193) are run as a single
