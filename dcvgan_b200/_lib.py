@@ -61,6 +61,7 @@ SIGNATURES = {
     "dcv_bn_act_bwd_apply": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp,
                                   _i64, _vp, _i64, _vp]),
     "dcv_act_bwd": (_i, [_i, _vp, _i64, _vp, _i64, _i64, _i, _i, _f, _vp, _i64, _vp]),
+    "dcv_col2im_act": (_i, [_i, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i64, _i, _i, _vp]),
     "dcv_fold_w": (_i, [_i, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp, _f, _i64, _i, _i, _i, _i, _vp, _i64, _vp]),
     "dcv_unfold_w": (_i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _i, _vp]),
     "dcv_add_noise": (_i, [_i, _vp, _i64, _vp, _f, _i64, _i, _vp, _i64, _vp]),

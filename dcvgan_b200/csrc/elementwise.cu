@@ -659,6 +659,90 @@ axpy_vec_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __
   }
 }
 
+// ------------------------------------------------------------------------------------------ tap-unrolled transposed convolution
+// Transposed convolutions with a tiny output channel count (outconv 128 -> 3, ggen main.12 64 -> C: generator.py:73,274)
+// make poor tensor-core tiles: N = 16 padded output columns, and every tap re-reads its 128x16 A slice from shared
+// memory.  They run instead as ONE 1x1 convolution x[pixels][Cin] x W[Cin][Cout*taps] -> P[pixels][(co, kh, kw)] (the
+// transposed-convolution weight (Cin, Cout, kh, kw) already is that matrix) followed by this col2im gather:
+//   y[n][oh][ow][co] = act( sum over (kh, kw) with oh = ih*s - p + kh, ow = iw*s - p + kw of P[n][ih][iw][co*taps + kh*KW + kw] )
+// Tiled version (bf16, 16-byte aligned rows): a block owns a 16x16 output tile, stages the input pixels of P it depends
+// on in shared memory with coalesced 16-byte loads (P is read from HBM exactly once; the per-pixel gather of
+// Cout*taps 2-byte values then hits shared memory), one thread per output pixel.
+template <int S>
+__global__ void __launch_bounds__(256)
+col2im_act_tiled_kernel(const __nv_bfloat16* __restrict__ P, int64_t ldp, int Ih, int Iw, int Cout, int KH, int KW, int pad,
+                        int Oh, int Ow, int rowv /*16-byte vectors per staged row*/, int RH, int RW /*staged region*/, int act,
+                        float slope, __nv_bfloat16* __restrict__ y, int64_t ldy) {
+  extern __shared__ uint4 tile[];
+  const int n = blockIdx.z, oh0 = blockIdx.y * 16, ow0 = blockIdx.x * 16;
+  // first input row / column any output pixel of the tile can see: ih = (oh + pad - kh) / S, kh = KH-1 .. 0
+  const int ih0 = max(0, (oh0 + pad - (KH - 1) + (S - 1)) / S), iw0 = max(0, (ow0 + pad - (KW - 1) + (S - 1)) / S);
+  const int nvec = RH * RW * rowv;
+  for (int i = threadIdx.x; i < nvec; i += 256) {
+    const int v = i % rowv; const int r = i / rowv;
+    const int rw = r % RW, rh = r / RW;
+    const int ih = ih0 + rh, iw = iw0 + rw;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (ih < Ih && iw < Iw) val = *reinterpret_cast<const uint4*>(P + (((int64_t)n * Ih + ih) * Iw + iw) * ldp + v * 8);
+    tile[i] = val;
+  }
+  __syncthreads();
+  const int oh = oh0 + (int)threadIdx.x / 16, ow = ow0 + (int)threadIdx.x % 16;
+  if (oh >= Oh || ow >= Ow) return;
+  const int taps = KH * KW;
+  const __nv_bfloat16* tb = reinterpret_cast<const __nv_bfloat16*>(tile);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int kh = 0; kh < KH; ++kh) {
+    const int th = oh + pad - kh;
+    if (th < 0 || th % S) continue;
+    const int ih = th / S;
+    if (ih >= Ih) continue;
+    for (int kw = 0; kw < KW; ++kw) {
+      const int tw = ow + pad - kw;
+      if (tw < 0 || tw % S) continue;
+      const int iw = tw / S;
+      if (iw >= Iw) continue;
+      const __nv_bfloat16* row = tb + ((ih - ih0) * RW + (iw - iw0)) * rowv * 8 + kh * KW + kw;
+#pragma unroll
+      for (int co = 0; co < 4; ++co) if (co < Cout) acc[co] += __bfloat162float(row[co * taps]);
+    }
+  }
+  __nv_bfloat16* yo = y + (((int64_t)n * Oh + oh) * Ow + ow) * ldy;
+#pragma unroll
+  for (int co = 0; co < 4; ++co) if (co < Cout) yo[co] = __float2bfloat16_rn(apply_act(acc[co], act, slope));
+}
+
+template <typename T, int S>      // S = stride known at compile time (1, 2) or 0 = runtime
+__global__ void __launch_bounds__(256)
+col2im_act_kernel(const T* __restrict__ P, int64_t ldp, int N, int Ih, int Iw, int Cout, int KH, int KW, int s_rt, int pad, int Oh,
+                  int Ow, int act, float slope, T* __restrict__ y, int64_t ldy) {
+  const int s = S ? S : s_rt;
+  const int taps = KH * KW;
+  const int64_t total = (int64_t)N * Oh * Ow;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % Ow); const int64_t r = i / Ow;
+    const int oh = (int)(r % Oh); const int n = (int)(r / Oh);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kh = 0; kh < KH; ++kh) {
+      const int th = oh + pad - kh;
+      if (th < 0 || th % s) continue;
+      const int ih = th / s;
+      if (ih >= Ih) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int tw = ow + pad - kw;
+        if (tw < 0 || tw % s) continue;
+        const int iw = tw / s;
+        if (iw >= Iw) continue;
+        const T* row = P + (((int64_t)n * Ih + ih) * Iw + iw) * ldp + kh * KW + kw;
+#pragma unroll
+        for (int co = 0; co < 4; ++co) if (co < Cout) acc[co] += ldf(row + co * taps);
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < 4; ++co) if (co < Cout) stf(y + i * ldy + co, apply_act(acc[co], act, slope));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ w-tap folding
 // Image-like stem inputs (1-5 real channels): the kw taps of a strided convolution are moved into the channel dimension
 // by a cheap pre-pass, X2[line][ow][k*cin + c] = x[line][ow*sw - pw + k][c] (zero outside the row), so that the
@@ -1171,6 +1255,41 @@ int dcv_frame_copy(int dtype, void* clips, int64_t ldc, int N, int T_, int64_t h
   DISPATCH_T(dtype, frame_copy_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(
                         (T*)clips, ldc, N, T_, hw, C, t, t_dev, (T*)frames, ldf, reverse, accumulate));
   return check_launch("frame_copy");
+}
+
+int dcv_col2im_act(int dtype, const void* P, int64_t ldp, int N, int Ih, int Iw, int Cout, int KH, int KW, int stride, int pad,
+                   int act, float slope, void* y, int64_t ldy, int Oh, int Ow, void* stream) {
+  DCV_REQUIRE(P && y, "col2im_act: null pointer");
+  DCV_REQUIRE(Cout >= 1 && Cout <= 4 && KH >= 1 && KW >= 1 && stride >= 1 && pad >= 0, "col2im_act: bad shape (Cout %d k %dx%d s %d p %d)", Cout, KH, KW, stride, pad);
+  DCV_REQUIRE(Oh == (Ih - 1) * stride - 2 * pad + KH && Ow == (Iw - 1) * stride - 2 * pad + KW, "col2im_act: output %dx%d does not match input %dx%d", Oh, Ow, Ih, Iw);
+  DCV_REQUIRE(ldp >= (int64_t)Cout * KH * KW, "col2im_act: pitch %lld < %d columns", (long long)ldp, Cout * KH * KW);
+  if ((int64_t)N * Oh * Ow == 0) return 0;
+  if (dtype == DCV_BF16 && (stride == 1 || stride == 2) && ldp % 8 == 0 && (((uintptr_t)P) & 15) == 0 && N <= 65535) {
+    const int rowv = (Cout * KH * KW + 7) / 8;
+    // staged region: input rows [ih0, ih_last] for 16 output rows (ih_last = (oh0 + 15 + pad) / S)
+    const int RH = (16 + KH - 2) / stride + 2, RW = (16 + KW - 2) / stride + 2;
+    const size_t smem = (size_t)RH * RW * rowv * 16;
+    if (smem <= 48 * 1024) {
+      dim3 grid(ceil_div(Ow, 16), ceil_div(Oh, 16), N);
+      if (stride == 1)
+        col2im_act_tiled_kernel<1><<<grid, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)P, ldp, Ih, Iw, Cout, KH, KW, pad, Oh, Ow,
+                                                                           rowv, RH, RW, act, slope, (__nv_bfloat16*)y, ldy);
+      else
+        col2im_act_tiled_kernel<2><<<grid, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)P, ldp, Ih, Iw, Cout, KH, KW, pad, Oh, Ow,
+                                                                           rowv, RH, RW, act, slope, (__nv_bfloat16*)y, ldy);
+      return check_launch("col2im_act_tiled");
+    }
+  }
+  const int nb = ew_blocks((int64_t)N * Oh * Ow, 1);
+  DISPATCH_T(dtype, {
+    if (stride == 1)
+      col2im_act_kernel<T, 1><<<nb, 256, 0, as_stream(stream)>>>((const T*)P, ldp, N, Ih, Iw, Cout, KH, KW, stride, pad, Oh, Ow, act, slope, (T*)y, ldy);
+    else if (stride == 2)
+      col2im_act_kernel<T, 2><<<nb, 256, 0, as_stream(stream)>>>((const T*)P, ldp, N, Ih, Iw, Cout, KH, KW, stride, pad, Oh, Ow, act, slope, (T*)y, ldy);
+    else
+      col2im_act_kernel<T, 0><<<nb, 256, 0, as_stream(stream)>>>((const T*)P, ldp, N, Ih, Iw, Cout, KH, KW, stride, pad, Oh, Ow, act, slope, (T*)y, ldy);
+  });
+  return check_launch("col2im_act");
 }
 
 int dcv_fold_w(int dtype, const void* xg, int64_t ldg, int cg, const float* noise_g, const void* xc, int64_t ldc, int cc,

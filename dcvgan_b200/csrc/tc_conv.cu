@@ -737,7 +737,49 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       mbar_wait(&tfull_bar[acc], acc ? tfull_phase1 : tfull_phase0);
       tc_fence_after();
       const uint32_t d_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_cols);
-      if (p.tma_store) {
+      if (p.tma_store == 2) {
+        // narrow outputs (bnt = 16 or 32 channels: image-like tensors, tap-unrolled partial products): same staging + TMA
+        // store with 32- / 64-byte rows (32B / 64B swizzle), one TMEM load per row chunk
+        const int cw = p.bnt;                                   // 16 or 32
+        const uint32_t rb = (uint32_t)cw * 2u;
+        const uint32_t swz_x = cw == 32 ? (uint32_t)((lane >> 1) & 3) : (uint32_t)((lane >> 2) & 1);
+        const uint32_t wbuf = stg_base + (uint32_t)quarter * 8192u;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const uint32_t buf = wbuf + (uint32_t)(nstore & 1) * 4096u;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint32_t v[32];
+          if (cw == 32) { tmem_ld32_nowait(d_base + (uint32_t)(m * p.bnt), v); tmem_ld_wait(); }
+          else { uint32_t t16[16]; tmem_ld16(d_base + (uint32_t)(m * p.bnt), t16);
+#pragma unroll
+                 for (int i = 0; i < 16; ++i) v[i] = t16[i]; }
+          if (!(p.dbg & 4)) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c * 8 >= cw) break;
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float a = apply_act(__uint_as_float(v[8 * c + 2 * i]), p.act, p.slope);
+                const float b = apply_act(__uint_as_float(v[8 * c + 2 * i + 1]), p.act, p.slope);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)lane * rb + (((uint32_t)c ^ swz_x) << 4)),
+                           "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 4)) {
+            tma_store_5d(&mapY, buf, nbase, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
+                         (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
+            tma_store_commit();
+          }
+          ++nstore;
+        }
+      } else if (p.tma_store) {
         // Coalesced path (bnt % 64 == 0): every epilogue warp stages ITS 32 rows of a 64-channel chunk in shared memory
         // (128-byte rows, 128B swizzle -> conflict-free 16-byte writes) and writes them with its own TMA store; the tensor
         // map does the sub-pixel scatter and clips rows / channels outside the tensor.  No cross-warp barrier: the four
@@ -1509,7 +1551,11 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     p.ntn = npad / p.bnt;
     DCV_REQUIRE(phases <= 8, "conv_tc: %d sub-pixel phases", phases);
     for (int ph = 0; ph < phases; ++ph) p.phs[ph] = make_phase(c, ph);
-    p.tma_store = (p.bnt % 64 == 0) && (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0) && !getenv("DCV_TC_NO_TMA_STORE");
+    p.tma_store = 0;                                         // 1: 64-channel chunks, 2: one 16- / 32-channel chunk
+    if ((((uintptr_t)y & 15) == 0) && (ldy % 8 == 0) && !getenv("DCV_TC_NO_TMA_STORE")) {
+      if (p.bnt % 64 == 0) p.tma_store = 1;
+      else if ((p.bnt == 16 || p.bnt == 32) && c.Nc >= p.bnt && !getenv("DCV_TC_NO_NARROW_TMA_STORE")) p.tma_store = 2;
+    }
     const int stg_bytes = p.tma_store ? 2 * 16384 : 0;
     p.b_bytes = g4 ? (p.bnt * 128 + 1023) / 1024 * 1024 : p.b_bytes;
 
@@ -1568,7 +1614,7 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     if (st < 1) st = 1;
     p.stages = st;
     const int grid_p = p.items < num_sms ? p.items : num_sms;
-    const bool can_stats = p.tma_store && !getenv("DCV_TC_NO_FUSED_STATS");
+    const bool can_stats = p.tma_store == 1 && !getenv("DCV_TC_NO_FUSED_STATS");
     if (slots_out) { *slots_out = can_stats ? 4 * grid_p : 0; return 0; }
     DCV_REQUIRE(!stats || can_stats, "conv_tc: fused statistics need the TMA-store epilogue (output channels %% 64 == 0)");
     p.stats = stats; p.npad = npad;
@@ -1588,8 +1634,9 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
       const int yt = p.bt < rem ? p.bt : rem; rem /= yt;
       const int yn = p.bn < rem ? p.bn : rem; rem /= yn;
       DCV_REQUIRE(rem == 1, "conv_tc: tile %dx%dx%dx%d has no 32-row sub-box", p.bw, p.bh, p.bt, p.bn);
-      rc = make_act_map(&mapY, y, c.Nc, c.Ow, c.Oh, c.Ot, c.N, ldy, 64, yw, yh, yt, yn, f0.osw, f0.osh, f0.ost,
-                        CU_TENSOR_MAP_SWIZZLE_128B);
+      const int ycw = p.tma_store == 1 ? 64 : p.bnt;
+      rc = make_act_map(&mapY, y, c.Nc, c.Ow, c.Oh, c.Ot, c.N, ldy, ycw, yw, yh, yt, yn, f0.osw, f0.osh, f0.ost,
+                        ycw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (ycw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B));
       if (rc) return rc;
     }
     const int smem_p = st * (p.a_bytes + p.hg * p.b_bytes) + stg_bytes + 1024;

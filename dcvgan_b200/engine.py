@@ -18,6 +18,7 @@ from .ops import Act, ConvSpec
 
 BN_EPS, BN_MOM = 1e-5, 0.1
 FUSED_BN_STATS = os.environ.get("DCV_FUSED_BN_STATS", "0") == "1"
+TAP_UNROLL = os.environ.get("DCV_NO_TAP_UNROLL", "0") != "1"   # tiny-Cout transposed convolutions as 1x1 GEMM + col2im
 
 
 # ------------------------------------------------------------------------------------------ RNG
@@ -153,6 +154,9 @@ class Block:
         wp = packed_weight(spec, g, spec.fwd_dir, impl, w)
         ctx = {"g": g, "x": x_used if save else None, "a": out, "cin_p": cin_p, "cout_p": cout_p}
         if self.bn is None:
+            if self._tap_unrolled(impl, x_used):
+                self._forward_tap_unrolled(x_used, out)
+                return ctx
             ops.conv(g, spec.fwd_dir, impl, x_used.padded_to(cin_p), wp, out.padded_to(cout_p), self.act, self.slope)
             return ctx
         bn = self.bn
@@ -176,6 +180,33 @@ class Block:
         if save:
             ctx.update(z=z, mean=mean, invstd=invstd, drop=drop, training=training)
         return ctx
+
+    # ---- transposed convolutions with <= 4 output channels (outconv 128 -> 3, ggen main.12 64 -> C): 1x1 GEMM + col2im
+    def _tap_unrolled(self, impl, x):
+        spec = self.spec
+        return (TAP_UNROLL and impl == ops.IMPL_TC and spec.kind == "convT" and spec.k[0] == 1 and x.t == 1 and spec.cout <= 4
+                and spec.cout * spec.taps <= 64 and spec.cin % 16 == 0 and spec.s[1] == spec.s[2] and spec.p[1] == spec.p[2])
+
+    def _forward_tap_unrolled(self, x, out):
+        """The forward of such a layer as a tensor-core tile has N = 16 padded columns and re-reads a 128x16 A slice from
+        shared memory for every tap (outconv: 0.239 ms at B = 32, bound by shared-memory operand reads).  Here the input
+        is read once by a 1x1 convolution onto Cout*taps columns (the ConvTranspose2d weight (Cin, Cout, kh, kw) already
+        is that matrix) and a col2im pass sums the taps per output pixel and applies the activation.  The backward pass
+        is unchanged (data / weight gradients of the original geometry)."""
+        spec = self.spec
+        ncol = spec.cout * spec.taps
+        spec1 = ConvSpec("conv", spec.cin, ncol, (1, 1, 1), (1, 1, 1), (0, 0, 0))
+        P = Act.empty(x.n, 1, x.h, x.w, ncol, x.dtype)
+        g1 = spec1.geom(x.n, x.spatial, x.cp, P.cp)
+        impl1 = ops.choose_conv_impl(g1, spec1.fwd_dir, x)
+        w = self.conv.weight
+        key = ("unrolled", g1.key(), impl1)
+        per = WCACHE.setdefault(id(w), {}) if WCACHE is not None else {}
+        wp = per.get(key)
+        if wp is None:    # w[ci][co][tap] seen as w[cl = ci][cs = co*taps + tap]: strides (ncol, 1), a single "tap"
+            wp = per[key] = ops.pack_weight_strided(g1, spec1.fwd_dir, impl1, w, ncol, 1, 0)
+        ops.conv(g1, spec1.fwd_dir, impl1, x.padded_to(x.cp), wp, P.padded_to(P.cp))
+        ops.col2im_act(P, out, spec.cout, spec.k[1], spec.k[2], spec.s[1], spec.p[1], self.act, self.slope)
 
     def backward(self, ctx, da, sink, dx_out=None, need_dw=True):
         """da: gradient w.r.t. the block output (Act, may be a slice).  dx_out: Act receiving dL/dx or None."""
@@ -350,7 +381,10 @@ class GGenPlan:
         rec = mod.recurrent
         z_c = rng_.normal((B, dzc))                                              # draw order: generator.py:103-116
         h0 = rng_.normal((B, dzm))
-        eps = torch.stack([rng_.normal((B, dzm)) for _ in range(T)], 0).contiguous()
+        if rng_.mode == "device":      # one draw for the whole trajectory (the per-step draws of generator.py:84-101 are i.i.d.)
+            eps = rng_.normal((T, B, dzm))
+        else:                          # CPU-parity runs consume the reference's draws one by one
+            eps = torch.stack([rng_.normal((B, dzm)) for _ in range(T)], 0).contiguous()
         P = [p.detach() for p in (rec.weight_ih, rec.weight_hh, rec.bias_ih, rec.bias_hh)]
         hs = ops.gru_traj_fwd(h0, eps, *P)                                       # (B, T, dzm)
         x = Act.empty(B * T, 1, 1, 1, dzc + dzm, dtype)

@@ -423,6 +423,25 @@ def add_noise(x, noise, sigma, out):
     check(lib().dcv_add_noise(dcv_dtype(x), xp, ldx, noise.data_ptr(), sigma, rows, c, op, ldo, _stream()))
 
 
+def pack_weight_strided(g, direction, impl, weight, s_l, s_s, s_tap):
+    """dcv_pack_weight with explicit element strides of the master weight seen as w[cl, cs, tap]"""
+    nbytes = lib().dcv_packed_weight_bytes(C.byref(g), direction, impl)
+    if nbytes < 0:
+        check(-1)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    w = weight.detach()
+    assert w.is_contiguous() and w.dtype == torch.float32
+    check(lib().dcv_pack_weight(C.byref(g), direction, impl, w.data_ptr(), s_l, s_s, s_tap, out.data_ptr(), _stream()))
+    return out
+
+
+def col2im_act(p_act, y, cout, kh, kw, stride, pad, act, slope):
+    """y (N,1,Oh,Ow,cout) = act(col2im(P)), P (N,1,Ih,Iw,cout*kh*kw) from the tap-unrolled 1x1 convolution"""
+    assert p_act.t == 1 and y.t == 1 and y.n == p_act.n
+    check(lib().dcv_col2im_act(dcv_dtype(y), p_act.ptr, p_act.ld, p_act.n, p_act.h, p_act.w, cout, kh, kw, stride, pad, act, slope,
+                               y.ptr, y.ld, y.h, y.w, _stream()))
+
+
 def fold_w(xg, xc, out, kw, sw, pw, noise_g=None, noise_c=None, sigma=0.0):
     """out (N,T,H,Ow, kw*(cg+cc)) <- [xg | xc] with the kw taps along w moved into the channel dimension (+ Noise)"""
     assert xg.shape[:4] == xc.shape[:4] and out.c == kw * (xg.c + xc.c)

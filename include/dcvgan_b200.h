@@ -174,6 +174,12 @@ int dcv_bn_act_bwd_apply(int dtype, const void* da, int64_t ldda, const void* a,
 /* plain activation backward (no BN): dz = da * act'(a) ; a is the activated output */
 int dcv_act_bwd(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, int64_t rows, int C,
                 int act, float slope, void* dz, int64_t lddz, void* stream);
+/* Tap-unrolled form of a transposed convolution with <= 4 output channels (generator.py:73 ggen main.12 ConvTranspose2d(ngf, C,
+ * 4, 2, 1) + Tanh; generator.py:274 outconv ConvTranspose2d(2*ngf, 3, 3, 1, 1) + Tanh): a 1x1 dcv_conv with the weight viewed
+ * as (Cin) x (Cout*kh*kw) produces P[n][ih][iw][co*kh*kw + tap]; dcv_col2im_act sums the taps that land on each output pixel
+ * and applies the activation.  2-D only (T == 1). */
+int dcv_col2im_act(int dtype, const void* P, int64_t ldp, int N, int Ih, int Iw, int Cout, int KH, int KW, int stride, int pad,
+                   int act, float slope, void* y, int64_t ldy, int Oh, int Ow, void* stream);
 /* w-tap folding for the image-like stem inputs of the discriminators (discriminator.py:79-90,180-193: conv_g on the
  * geometry channels, conv_c on the colour channels, kernel 4, stride 2, pad 1 along w):
  *   out[line][ow][k*(cg+cc) + c] = [xg | xc][line][ow*sw - pw + k][c]  (+ sigma*noise, the Noise layer), 0 outside the row
