@@ -673,7 +673,10 @@ __global__ void __launch_bounds__(256)
 col2im_act_tiled_kernel(const __nv_bfloat16* __restrict__ P, int64_t ldp, int Ih, int Iw, int Cout, int KH, int KW, int pad,
                         int Oh, int Ow, int rowv /*16-byte vectors per staged row*/, int RH, int RW /*staged region*/, int act,
                         float slope, __nv_bfloat16* __restrict__ y, int64_t ldy) {
-  extern __shared__ uint4 tile[];
+  extern __shared__ uint32_t tile[];
+  // staged pixel pitch = rowv*4 + 1 words: neighbouring output pixels read the same column of neighbouring staged pixels,
+  // and a 64-byte pitch put 16 of them on 2 banks (ncu: 8 shared-memory wavefronts per load)
+  const int pitch = rowv * 4 + 1;
   const int n = blockIdx.z, oh0 = blockIdx.y * 16, ow0 = blockIdx.x * 16;
   // first input row / column any output pixel of the tile can see: ih = (oh + pad - kh) / S, kh = KH-1 .. 0
   const int ih0 = max(0, (oh0 + pad - (KH - 1) + (S - 1)) / S), iw0 = max(0, (ow0 + pad - (KW - 1) + (S - 1)) / S);
@@ -684,13 +687,13 @@ col2im_act_tiled_kernel(const __nv_bfloat16* __restrict__ P, int64_t ldp, int Ih
     const int ih = ih0 + rh, iw = iw0 + rw;
     uint4 val = make_uint4(0u, 0u, 0u, 0u);
     if (ih < Ih && iw < Iw) val = *reinterpret_cast<const uint4*>(P + (((int64_t)n * Ih + ih) * Iw + iw) * ldp + v * 8);
-    tile[i] = val;
+    uint32_t* d = tile + r * pitch + v * 4;
+    d[0] = val.x; d[1] = val.y; d[2] = val.z; d[3] = val.w;
   }
   __syncthreads();
   const int oh = oh0 + (int)threadIdx.x / 16, ow = ow0 + (int)threadIdx.x % 16;
   if (oh >= Oh || ow >= Ow) return;
   const int taps = KH * KW;
-  const __nv_bfloat16* tb = reinterpret_cast<const __nv_bfloat16*>(tile);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int kh = 0; kh < KH; ++kh) {
     const int th = oh + pad - kh;
@@ -702,9 +705,16 @@ col2im_act_tiled_kernel(const __nv_bfloat16* __restrict__ P, int64_t ldp, int Ih
       if (tw < 0 || tw % S) continue;
       const int iw = tw / S;
       if (iw >= Iw) continue;
-      const __nv_bfloat16* row = tb + ((ih - ih0) * RW + (iw - iw0)) * rowv * 8 + kh * KW + kw;
+      const uint32_t* row = tile + ((ih - ih0) * RW + (iw - iw0)) * pitch;
+      const int e0 = kh * KW + kw;
 #pragma unroll
-      for (int co = 0; co < 4; ++co) if (co < Cout) acc[co] += __bfloat162float(row[co * taps]);
+      for (int co = 0; co < 4; ++co) {
+        if (co < Cout) {
+          const int e = e0 + co * taps;
+          const uint32_t wv = row[e >> 1];
+          acc[co] += __uint_as_float((e & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+        }
+      }
     }
   }
   __nv_bfloat16* yo = y + (((int64_t)n * Oh + oh) * Ow + ow) * ldy;
@@ -760,6 +770,33 @@ fold_w_kernel(const T* __restrict__ xg, int64_t ldg, int cg, const float* __rest
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t line = i / Ow; const int ow = (int)(i - line * Ow);
     T* o = out + i * ldo;
+    if (sizeof(T) == 2 && kw == 4 && cin == 4 && ldo % 8 == 0 && ((uintptr_t)out & 15) == 0) {
+      // 4 taps x 4 channels = one 32-byte row: build it in registers, two 16-byte stores (16 scalar 2-byte stores per thread
+      // made this pass 56 us for the video stem)
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int iw = ow * sw - pw + k;
+        const bool ok = iw >= 0 && iw < W;
+        const int64_t px = line * W + iw;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float t = 0.f;
+          if (ok) {
+            if (c < cg) { t = ldf(xg + px * ldg + c); if (ng) t += sigma * ng[px * cg + c]; }
+            else { t = ldf(xc + px * ldc + (c - cg)); if (nc) t += sigma * nc[px * cc + (c - cg)]; }
+          }
+          v[k * 4 + c] = t;
+        }
+      }
+      uint32_t w[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]); w[q] = *reinterpret_cast<uint32_t*>(&h); }
+      uint4* dst = reinterpret_cast<uint4*>(o);
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      continue;
+    }
     for (int k = 0; k < kw; ++k) {
       const int iw = ow * sw - pw + k;
       const bool ok = iw >= 0 && iw < W;
@@ -1268,7 +1305,7 @@ int dcv_col2im_act(int dtype, const void* P, int64_t ldp, int N, int Ih, int Iw,
     const int rowv = (Cout * KH * KW + 7) / 8;
     // staged region: input rows [ih0, ih_last] for 16 output rows (ih_last = (oh0 + 15 + pad) / S)
     const int RH = (16 + KH - 2) / stride + 2, RW = (16 + KW - 2) / stride + 2;
-    const size_t smem = (size_t)RH * RW * rowv * 16;
+    const size_t smem = (size_t)RH * RW * (rowv * 4 + 1) * 4;
     if (smem <= 48 * 1024) {
       dim3 grid(ceil_div(Ow, 16), ceil_div(Oh, 16), N);
       if (stride == 1)
