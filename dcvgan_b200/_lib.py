@@ -41,6 +41,7 @@ SIGNATURES = {
     "dcv_packed_weight_bytes": (_i64, [_G, _i, _i]),
     "dcv_pack_weight": (_i, [_G, _i, _i, _vp, _i64, _i64, _i64, _vp, _vp]),
     "dcv_pack_weight_batch": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dcv_pack_weight_multi": (_i, [_G, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dcv_pack_weight_sub": (_i, [_G, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp]),
     "dcv_conv_tc_supported": (_i, [_G, _i]),
     "dcv_conv": (_i, [_G, _i, _i, _i, _vp, _i64, _vp, _vp, _i64, _i, _f, _vp]),
@@ -51,6 +52,7 @@ SIGNATURES = {
     "dcv_wgrad": (_i, [_G, _i, _i, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i, _vp, _i64, _vp]),
     "dcv_wgrad_partial": (_i, [_G, _i, _i, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "dcv_wgrad_reduce_sub": (_i, [_G, _i, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _i, _vp]),
+    "dcv_wgrad_reduce_multi": (_i, [_G, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dcv_bn_stats_blocks": (_i, [_i64, _i]),
     "dcv_bn_stats": (_i, [_i, _vp, _i64, _i64, _i, _vp, _vp]),
     "dcv_bn_finalize": (_i, [_vp, _i, _i, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),

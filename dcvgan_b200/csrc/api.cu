@@ -37,7 +37,11 @@ int wgrad_simt_partial(const dcv_geom*, int, const void*, int64_t, const void*, 
 int wgrad_simt_splits(const dcv_geom*);
 int wgrad_tc_splits(const dcv_geom*);
 int wgrad_reduce_win(const float*, int, const dcv_geom*, WeightWin, float*, int64_t, int64_t, int64_t, int, cudaStream_t);
+int wgrad_reduce_multi(const float*, int, const dcv_geom*, int, float* const*, const int64_t*, const int64_t*, const int64_t*, const int*,
+                       const int*, const int*, const int*, const int*, cudaStream_t);
 int conv_tc_supported(const dcv_geom*, int);
+int pack_weight_tc_multi(const dcv_geom*, int, int, const float* const*, const int64_t*, const int64_t*, const int64_t*, const int*,
+                         const int*, const int*, const int*, void*, cudaStream_t);
 int pack_weight_tc_batch(int, const dcv_geom* const*, const int*, const float* const*, const int64_t*, const int64_t*, const int64_t*,
                          void* const*, cudaStream_t);
 int64_t packed_weight_tc_bytes(const dcv_geom*, int);
@@ -120,6 +124,18 @@ int dcv_pack_weight_batch(int n, const dcv_geom* const* geoms, const int* dirs, 
   return pack_weight_tc_batch(n, geoms, dirs, w, s_l, s_s, s_tap, outs, as_stream(stream));
 }
 
+int dcv_pack_weight_multi(const dcv_geom* g, int dir, int n, const float* const* w, const int64_t* s_l, const int64_t* s_s,
+                          const int64_t* s_tap, const int* cl_off, const int* cl_cnt, const int* cs_off, const int* cs_cnt,
+                          void* out, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DCV_REQUIRE(w && s_l && s_s && s_tap && cl_off && cl_cnt && cs_off && cs_cnt && out, "pack_weight_multi: null pointer");
+  for (int i = 0; i < n; ++i) {
+    if (int rc = check_window(g, cl_off[i], cl_cnt[i], cs_off[i], cs_cnt[i])) return rc;
+    DCV_REQUIRE(w[i], "pack_weight_multi: null weight pointer in part %d", i);
+  }
+  return pack_weight_tc_multi(g, dir, n, w, s_l, s_s, s_tap, cl_off, cl_cnt, cs_off, cs_cnt, out, as_stream(stream));
+}
+
 int dcv_conv_tc_supported(const dcv_geom* g, int dir) {
   if (check_geom(g)) return 0;
   return conv_tc_supported(g, dir);
@@ -188,6 +204,20 @@ int dcv_wgrad_reduce_sub(const dcv_geom* g, int impl, const void* ws, float* dw,
   WeightWin win; win.cl_off = cl_off; win.cl_cnt = cl_cnt; win.cs_off = cs_off; win.cs_cnt = cs_cnt; win.fill = 0;
   const int splits = impl == DCV_IMPL_TC ? wgrad_tc_splits(g) : wgrad_simt_splits(g);
   return wgrad_reduce_win((const float*)ws, splits, g, win, dw, s_l, s_s, s_tap, accumulate, as_stream(stream));
+}
+
+int dcv_wgrad_reduce_multi(const dcv_geom* g, int impl, const void* ws, int n, float* const* dw, const int64_t* s_l,
+                           const int64_t* s_s, const int64_t* s_tap, const int* cl_off, const int* cl_cnt, const int* cs_off,
+                           const int* cs_cnt, const int* accumulate, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DCV_REQUIRE(ws && dw && s_l && s_s && s_tap && cl_off && cl_cnt && cs_off && cs_cnt && accumulate, "wgrad_reduce_multi: null pointer");
+  for (int i = 0; i < n; ++i) {
+    if (int rc = check_window(g, cl_off[i], cl_cnt[i], cs_off[i], cs_cnt[i])) return rc;
+    DCV_REQUIRE(dw[i], "wgrad_reduce_multi: null gradient pointer in part %d", i);
+  }
+  const int splits = impl == DCV_IMPL_TC ? wgrad_tc_splits(g) : wgrad_simt_splits(g);
+  return wgrad_reduce_multi((const float*)ws, splits, g, n, dw, s_l, s_s, s_tap, cl_off, cl_cnt, cs_off, cs_cnt, accumulate,
+                            as_stream(stream));
 }
 
 int dcv_wgrad(const dcv_geom* g, int impl, int dtype, const void* xl, int64_t ldl, const void* xs, int64_t lds, float* dw,

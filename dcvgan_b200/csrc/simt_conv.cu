@@ -246,6 +246,54 @@ wgrad_reduce_flat_kernel(const float* __restrict__ partial, int splits, int taps
   }
 }
 
+// several master weights that each own a window of the partial matrix (merged / folded stems): every element is summed
+// once over the splits and routed to the weight whose window contains it (8 separate reductions re-read the partials 8x)
+constexpr int REDUCE_MULTI_MAX = 16;
+struct ReducePart { float* dw; int64_t s_l, s_s, s_tap; WeightWin win; int accumulate; };
+struct ReduceParts { int n; ReducePart p[REDUCE_MULTI_MAX]; };
+
+__global__ void __launch_bounds__(256)
+wgrad_reduce_multi_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, const __grid_constant__ ReduceParts parts) {
+  const int64_t total = (int64_t)taps * Cl * Cs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
+    int pi = -1;
+    for (int q = 0; q < parts.n; ++q) if (parts.p[q].win.has(cl, cs)) { pi = q; break; }
+    if (pi < 0) continue;
+    float s = 0.f;
+    const float* pp = partial + i;
+    int z = 0;
+    for (; z + 8 <= splits; z += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = pp[(int64_t)(z + u) * total];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; z < splits; ++z) s += pp[(int64_t)z * total];
+    const ReducePart& r = parts.p[pi];
+    float* d = r.dw + (cl - r.win.cl_off) * r.s_l + (cs - r.win.cs_off) * r.s_s + tap * r.s_tap;
+    *d = r.accumulate ? (*d + s) : s;
+  }
+}
+
+int wgrad_reduce_multi(const float* partial, int splits, const dcv_geom* g, int n, float* const* dw, const int64_t* s_l,
+                       const int64_t* s_s, const int64_t* s_tap, const int* cl_off, const int* cl_cnt, const int* cs_off,
+                       const int* cs_cnt, const int* accumulate, cudaStream_t s) {
+  DCV_REQUIRE(n >= 1 && n <= REDUCE_MULTI_MAX, "wgrad_reduce_multi: %d parts (max %d)", n, REDUCE_MULTI_MAX);
+  ReduceParts parts; parts.n = n;
+  for (int i = 0; i < n; ++i) {
+    ReducePart& r = parts.p[i];
+    r.dw = dw[i]; r.s_l = s_l[i]; r.s_s = s_s[i]; r.s_tap = s_tap[i]; r.accumulate = accumulate[i];
+    r.win.cl_off = cl_off[i]; r.win.cl_cnt = cl_cnt[i]; r.win.cs_off = cs_off[i]; r.win.cs_cnt = cs_cnt[i]; r.win.fill = 0;
+  }
+  const int taps = g->kt * g->kh * g->kw;
+  const int64_t total = (int64_t)taps * g->Cl * g->Cs;
+  int fb = (int)((total + 255) / 256); if (fb > 148 * 16) fb = 148 * 16;
+  wgrad_reduce_multi_kernel<<<fb, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, parts);
+  return check_launch("wgrad_reduce_multi");
+}
+
 // many splits (small weights, huge pixel counts): block = 8 consecutive elements x 32 split lanes; lane y sums splits
 // y, y+32, ... (32-byte sectors), the 32 partial sums are then added in a fixed order.
 __global__ void __launch_bounds__(256)

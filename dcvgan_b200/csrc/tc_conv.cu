@@ -1328,6 +1328,31 @@ pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int64_t s_l, int64_t
     pack_weight_tc_elem(c, w, s_l, s_s, s_tap, win, npad, i, out);
 }
 
+// One packed matrix assembled from several master weights that each own a window of it (merged / folded stems), one launch
+constexpr int PACK_MULTI_MAX = 16;
+struct PackPart { const float* w; int64_t s_l, s_s, s_tap; WeightWin win; };
+struct PackParts { int n; PackPart p[PACK_MULTI_MAX]; };
+
+__global__ void __launch_bounds__(256)
+pack_weight_tc_multi_kernel(ConvP c, const __grid_constant__ PackParts parts, int npad, int phases, __nv_bfloat16* __restrict__ out) {
+  const int64_t per_phase_nk = (int64_t)npad * c.Kc;
+  const int64_t total = per_phase_nk * phases;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ph = (int)(i / per_phase_nk);
+    const int64_t r = i - (int64_t)ph * per_phase_nk;
+    const int k = (int)(r % c.Kc); const int n = (int)(r / c.Kc);
+    const int cl = c.scatter ? n : k, cs = c.scatter ? k : n;
+    int pi = -1;
+    for (int q = 0; q < parts.n; ++q) if (parts.p[q].win.has(cl, cs)) { pi = q; break; }
+    WeightWin win;                                   // the owning part's window, or an empty zero-filling one
+    const float* w = nullptr; int64_t s_l = 0, s_s = 0, s_tap = 0;
+    if (pi >= 0) { win = parts.p[pi].win; w = parts.p[pi].w; s_l = parts.p[pi].s_l; s_s = parts.p[pi].s_s; s_tap = parts.p[pi].s_tap; }
+    else { win.cl_off = win.cs_off = 0; win.cl_cnt = win.cs_cnt = 0; }
+    win.fill = 1;
+    pack_weight_tc_elem(c, w, s_l, s_s, s_tap, win, npad, i, out);
+  }
+}
+
 // Many weights in one launch (all layers of a network after its Adam step): the jobs travel as a kernel parameter
 // (<= 4 KB), a block finds its job by scanning the block offsets.  ~90 single packs per iteration were ~90 tiny launches.
 constexpr int PACK_BATCH_MAX = 20;
@@ -1443,6 +1468,25 @@ int pack_weight_tc(const dcv_geom* g, int dir, const float* w, int64_t s_l, int6
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
   pack_weight_tc_kernel<<<blocks, 256, 0, s>>>(c, w, s_l, s_s, s_tap, win, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
   return check_launch("pack_weight_tc");
+}
+
+int pack_weight_tc_multi(const dcv_geom* g, int dir, int n, const float* const* w, const int64_t* s_l, const int64_t* s_s,
+                         const int64_t* s_tap, const int* cl_off, const int* cl_cnt, const int* cs_off, const int* cs_cnt, void* out,
+                         cudaStream_t s) {
+  DCV_REQUIRE(conv_tc_supported(g, dir), "pack_weight_multi: geometry not supported by the tcgen05 kernel");
+  DCV_REQUIRE(n >= 1 && n <= PACK_MULTI_MAX, "pack_weight_multi: %d parts (max %d)", n, PACK_MULTI_MAX);
+  PackParts parts; parts.n = n;
+  for (int i = 0; i < n; ++i) {
+    PackPart& q = parts.p[i];
+    q.w = w[i]; q.s_l = s_l[i]; q.s_s = s_s[i]; q.s_tap = s_tap[i];
+    q.win.cl_off = cl_off[i]; q.win.cl_cnt = cl_cnt[i]; q.win.cs_off = cs_off[i]; q.win.cs_cnt = cs_cnt[i]; q.win.fill = 1;
+  }
+  const ConvP c = make_convp(g, dir);
+  const int phases = c.scatter ? g->st * g->sh * g->sw : 1;
+  const int64_t total = (int64_t)tc_npad(c.Nc) * c.Kc * phases;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_weight_tc_multi_kernel<<<blocks, 256, 0, s>>>(c, parts, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
+  return check_launch("pack_weight_tc_multi");
 }
 
 int pack_weight_tc_batch(int n, const dcv_geom* const* geoms, const int* dirs, const float* const* w, const int64_t* s_l,

@@ -251,6 +251,14 @@ def pack_weight_merged(g, direction, impl, parts):
     if nbytes < 0:
         check(-1)
     out = torch.empty(nbytes, dtype=torch.uint8, device=parts[0][0].device)
+    n = len(parts)
+    if impl == IMPL_TC and n <= 16:      # one launch assembles the whole matrix
+        check(lib().dcv_pack_weight_multi(
+            C.byref(g), direction, n, (C.c_void_p * n)(*[p[0].data_ptr() + 4 * p[1] for p in parts]),
+            (C.c_int64 * n)(*[p[6] for p in parts]), (C.c_int64 * n)(*[p[7] for p in parts]), (C.c_int64 * n)(*[p[8] for p in parts]),
+            (C.c_int * n)(*[p[2] for p in parts]), (C.c_int * n)(*[p[3] for p in parts]), (C.c_int * n)(*[p[4] for p in parts]),
+            (C.c_int * n)(*[p[5] for p in parts]), out.data_ptr(), _stream()))
+        return out
     for i, (w, off, cl_off, cl_cnt, cs_off, cs_cnt, s_l, s_s, s_tap) in enumerate(parts):
         check(lib().dcv_pack_weight_sub(C.byref(g), direction, impl, w.data_ptr() + 4 * off, s_l, s_s, s_tap, cl_off, cl_cnt,
                                         cs_off, cs_cnt, int(i == 0), out.data_ptr(), _stream()))
@@ -268,9 +276,18 @@ def wgrad_merged(g, xl, xs, parts, impl=None):
     lp, ldl, _, _ = cl_view(xl)
     sp, lds, _, _ = cl_view(xs)
     check(lib().dcv_wgrad_partial(C.byref(g), impl, dcv_dtype(xl), lp, ldl, sp, lds, ws.data_ptr(), nbytes, _stream()))
-    for (dw, off, cl_off, cl_cnt, cs_off, cs_cnt, s_l, s_s, s_tap), acc in parts:
-        check(lib().dcv_wgrad_reduce_sub(C.byref(g), impl, ws.data_ptr(), dw.data_ptr() + 4 * off, s_l, s_s, s_tap, cl_off,
-                                         cl_cnt, cs_off, cs_cnt, int(acc), _stream()))
+    n = len(parts)
+    if n > 16:
+        for (dw, off, cl_off, cl_cnt, cs_off, cs_cnt, s_l, s_s, s_tap), acc in parts:
+            check(lib().dcv_wgrad_reduce_sub(C.byref(g), impl, ws.data_ptr(), dw.data_ptr() + 4 * off, s_l, s_s, s_tap, cl_off,
+                                             cl_cnt, cs_off, cs_cnt, int(acc), _stream()))
+        return
+    P = [p for p, _ in parts]
+    check(lib().dcv_wgrad_reduce_multi(
+        C.byref(g), impl, ws.data_ptr(), n, (C.c_void_p * n)(*[p[0].data_ptr() + 4 * p[1] for p in P]),
+        (C.c_int64 * n)(*[p[6] for p in P]), (C.c_int64 * n)(*[p[7] for p in P]), (C.c_int64 * n)(*[p[8] for p in P]),
+        (C.c_int * n)(*[p[2] for p in P]), (C.c_int * n)(*[p[3] for p in P]), (C.c_int * n)(*[p[4] for p in P]),
+        (C.c_int * n)(*[p[5] for p in P]), (C.c_int * n)(*[int(a) for _, a in parts]), _stream()))
 
 
 def pack_weight_batch(jobs):

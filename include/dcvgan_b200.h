@@ -101,6 +101,11 @@ int dcv_pack_weight_batch(int n, const dcv_geom* const* geoms, const int* dirs, 
 int dcv_pack_weight_sub(const dcv_geom* g, int dir, int impl, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
                         int cl_off, int cl_cnt, int cs_off, int cs_cnt, int fill_outside, void* out, void* stream);
 
+/* tcgen05 packing of a matrix assembled from n (<= 16) master weights with disjoint windows, zeros elsewhere, one launch */
+int dcv_pack_weight_multi(const dcv_geom* g, int dir, int n, const float* const* w, const int64_t* s_l, const int64_t* s_s,
+                          const int64_t* s_tap, const int* cl_off, const int* cl_cnt, const int* cs_off, const int* cs_cnt,
+                          void* out, void* stream);
+
 /* ---- convolution family ---------------------------------------------------------------------
  * dcv_conv: y = act(correlate(x, wp)); replaces every nn.Conv2d / nn.ConvTranspose2d / nn.Conv3d
  * forward on the path (generator.py:61-73,174,204,240,274; discriminator.py:81-101,182-206,288-305)
@@ -135,6 +140,10 @@ int dcv_wgrad_partial(const dcv_geom* g, int impl, int dtype, const void* xl, in
                       void* ws, int64_t ws_bytes, void* stream);
 int dcv_wgrad_reduce_sub(const dcv_geom* g, int impl, const void* ws, float* dw, int64_t s_l, int64_t s_s, int64_t s_tap,
                          int cl_off, int cl_cnt, int cs_off, int cs_cnt, int accumulate, void* stream);
+/* n windows (<= 16, disjoint) in one launch: every partial sum is read once and routed to the weight that owns it */
+int dcv_wgrad_reduce_multi(const dcv_geom* g, int impl, const void* ws, int n, float* const* dw, const int64_t* s_l,
+                           const int64_t* s_s, const int64_t* s_tap, const int* cl_off, const int* cl_cnt, const int* cs_off,
+                           const int* cs_cnt, const int* accumulate, void* stream);
 
 /* ---- BatchNorm (training + eval), activation, dropout, noise --------------------------------
  * Replaces nn.BatchNorm2d/3d (+ReLU/LeakyReLU, +Dropout2d between them, +Noise before the next
