@@ -59,7 +59,7 @@ class Act:
                 zero = True
         numel = max(n * t * h * w * ld, 1)
         if zero and ZERO_POOL is not None:
-            base = ZERO_POOL.get(numel, dtype)
+            base = ZERO_POOL.get(numel, dtype, c)
         else:
             base = (torch.zeros if zero else torch.empty)(numel, dtype=dtype, device="cuda")
         return Act(base, 0, n, t, h, w, c, ld, cp)
@@ -134,14 +134,16 @@ class ZeroPool:
     """
 
     def __init__(self):
-        self.bufs = {}      # (numel, dtype) -> [tensors]
+        self.bufs = {}      # (numel, dtype, real channels) -> [tensors]
         self.cursor = {}
 
     def begin_step(self):
         self.cursor = {}
 
-    def get(self, numel, dtype):
-        key = (numel, dtype)
+    def get(self, numel, dtype, c):
+        # keyed by the real channel count too: a buffer is only ever reused for tensors with the same real channels, so its
+        # padding channels stay exactly zero even when the request order differs between iterations (update gating)
+        key = (numel, dtype, c)
         i = self.cursor.get(key, 0)
         self.cursor[key] = i + 1
         lst = self.bufs.setdefault(key, [])
