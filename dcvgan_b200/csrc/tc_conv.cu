@@ -1,17 +1,24 @@
 // tcgen05 / TMEM / TMA implicit-GEMM correlation kernels for sm_100a (bf16 in, fp32 accumulate).
 //
-//   conv_tc   : forward / data-gradient of every Conv2d, ConvTranspose2d and Conv3d on the path whose
-//               reduction channel count is a multiple of 16.  A-operand tiles (128 output positions x CBLK
-//               channels) are fetched straight from the channels-last activation by one 5-D TMA box per
-//               (tap, channel block) - traversal strides implement the (1,2,2) convolution stride, out-of-
-//               bounds coordinates implement zero padding - so no im2col matrix ever exists in HBM.
-//               Transposed (scatter) correlations run as stride^d sub-pixel phases (blockIdx.z).
-//   wgrad_tc  : weight gradient.  Both operands are MN-major (channels contiguous, pixels = GEMM K), again
-//               straight from the activations by TMA; split over pixel ranges, fp32 partials reduced in a
-//               fixed order by wgrad_reduce (simt_conv.cu).
+//   conv_tc_pers_kernel<KS, MT, HG>
+//               : forward / data-gradient of every Conv2d, ConvTranspose2d and Conv3d on the path whose reduction
+//                 channel count is a multiple of 16.  Persistent (one CTA per SM, contiguous item ranges, odometer tile
+//                 iteration), double-buffered TMEM accumulators, warp-uniform lean MMA issue, TMA-store epilogue.
+//                 A-operand tiles (128 output positions x CBLK channels) are fetched straight from the channels-last
+//                 activation by one 5-D TMA box per (tap, channel block) - traversal strides implement the (1,2,2)
+//                 convolution stride, out-of-bounds coordinates implement zero padding - so no im2col matrix ever exists
+//                 in HBM.  Transposed (scatter) correlations run as stride^d sub-pixel phases.  HG > 1: the h taps of one
+//                 lattice share a box with halo rows; KS == 0: four 16-channel taps per stage (image-like operands).
+//   conv_tc_kernel / conv_tc_g4_kernel
+//               : the earlier multi-CTA kernels, kept behind DCV_TC_NOPERSIST=1 for A/B timing.
+//   wgrad_tc    : weight gradient.  Both operands are MN-major (channels contiguous, pixels = GEMM K), again
+//                 straight from the activations by TMA; one wave of CTAs split over pixel ranges, fp32 partials reduced
+//                 in a fixed order by wgrad_reduce (simt_conv.cu).
+//   pack_weight_tc_* : fp32 master weights -> bf16 K-major operand (single, windowed, multi-window, batched).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> registers -> global).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (tcgen05.ld -> registers -> swizzled smem -> TMA store).
+// What limited these kernels and in which order it was found: DESIGN.md section 5, profiles/r1_summary.md.
 #include "common.cuh"
 #include "conv_geom.cuh"
 #include <cuda.h>
