@@ -18,6 +18,7 @@ one fused schedule over the libdcvgan_b200 kernels instead of PyTorch autograd:
 import copy
 import os
 import shutil
+import weakref
 from pathlib import Path
 from typing import Any, Dict
 
@@ -359,15 +360,15 @@ class Trainer(object):
             slot["xc"].copy_(xc_host, non_blocking=True)
             slot["xg"].copy_(xg_host, non_blocking=True)
             slot["ready"].record(self._copy_stream)
-        slot["key"] = (xc_host.data_ptr(), xg_host.data_ptr())
+        slot["key"] = (weakref.ref(xc_host), weakref.ref(xg_host))      # matched by object identity, not by address
 
     def _take_prefetched(self, xc_real, xg_real):
         """(device xc, device xg, slot) if this host batch was staged by prefetch(), else None"""
         if xc_real.is_cuda or self._copy_stream is None:
             return None
-        key = (xc_real.data_ptr(), xg_real.data_ptr())
         for slot in self._stage:
-            if slot is not None and slot.get("key") == key:
+            key = slot.get("key") if slot is not None else None
+            if key is not None and key[0]() is xc_real and key[1]() is xg_real:
                 slot["key"] = None
                 torch.cuda.current_stream().wait_event(slot["ready"])
                 return slot
