@@ -17,6 +17,9 @@ import time
 # one visible device per rank so that the reference's hard-coded cuda:0 (util.py:25-26) stays valid
 if "LOCAL_RANK" in os.environ and "DCV_KEEP_VISIBLE" not in os.environ:
     os.environ["CUDA_VISIBLE_DEVICES"] = os.environ["LOCAL_RANK"]
+# the reference arm is the reference's CPU implementation: hide the GPUs so that its util.current_device() picks the CPU
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"] or "--impl=reference" in sys.argv:
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -141,34 +144,61 @@ def peaks():
 
 
 # --------------------------------------------------------------------------------------------- reference arm (CPU)
-def run_reference(args, cfg_name):
-    """The reference's CPU implementation of the step = the pinned oracle port, all host threads, bounded sample."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def synthetic_host_batches(cfg, B, n, seed):
+    """n batches of synthetic clips shaped like the dataset's (dataset.py:111-186): color U(-1,1), geometry per kind"""
     from oracle import dcvgan_oracle as orc
-    torch.set_num_threads(os.cpu_count())
-    Bs = args.ref_batch
-    cfg = make_cfg(cfg_name, Bs)
+    gname = cfg["geometric_info"]["name"]
+    out = []
+    for i in range(n):
+        xc, xg = orc.synthetic_batch(cfg, B, seed + i)
+        out.append({"color": xc, gname: xg})
+    return out
+
+
+def reference_cpu_run(cfg_name, B, warmup, steps):
+    """The reference's own CPU implementation of the step, all host threads, at the benchmarked batch size.
+
+    kind "reference": the UNMODIFIED modules and Trainer.train() loop of raahii/dcvgan staged under baseline/_ref/src
+    (tools/ref_harness.py; staged by __graft_entry__.build()).  kind "port": the pinned oracle restatement
+    (oracle/dcvgan_oracle.py) when the staged sources are absent.  Returns (iters/s, s/iter, kind, threads, note)."""
+    from tools import ref_harness as rh
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = make_cfg(cfg_name, B)
+    if rh.reference_src() is not None:
+        ref = rh.import_reference()
+        batches = synthetic_host_batches(cfg, B, 1, 1000) * (warmup + steps)
+        _, logger = rh.run_reference_trainer(ref, cfg, batches, device="cpu", seed=cfg["seed"])
+        ips, spi = rh.timed_iters_per_s(logger, warmup, steps)
+        return ips, spi, "reference", torch.get_num_threads(), "unmodified reference Trainer.train() (baseline/_ref/src)"
+    from oracle import dcvgan_oracle as orc
     tr = orc.OracleTrainer(cfg, orc.init_all(cfg, cfg["seed"]))
     torch.manual_seed(cfg["seed"])
     np.random.seed(cfg["seed"])
-    xc, xg = orc.synthetic_batch(cfg, Bs, 1000)
-    for _ in range(args.warmup):
+    xc, xg = orc.synthetic_batch(cfg, B, 1000)
+    for _ in range(warmup):
         tr.step(xc, xg)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         tr.step(xc, xg)
-    dt = (time.perf_counter() - t0) / args.steps
-    # one batch-32 iteration costs 32/Bs sampled iterations (conv cost is linear in the batch)
-    value = 1.0 / (dt * 32.0 / Bs)
-    sample = f"{args.steps} timed iteration(s) of the full step at batch {Bs} (scaled x{32 // Bs} to batch 32), fp32, {torch.get_num_threads()} threads"
-    line = {"impl": "reference", "metric": "train iters/sec (16x64x64 clips, batch 32)", "value": value, "unit": "iters/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 32.0 / Bs * 1e3,
+    spi = (time.perf_counter() - t0) / steps
+    return 1.0 / spi, spi, "port", torch.get_num_threads(), "oracle port (reference sources not staged)"
+
+
+def run_reference(args, cfg_name):
+    """`--impl reference`: rank 0 times the reference's CPU training step at batch 32 (1 warm-up + <= 3 timed iterations)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 32
+    ips, spi, kind, threads, note = reference_cpu_run(cfg_name, B, args.warmup, args.steps)
+    sample = f"{args.steps} timed iteration(s) of the full step at batch {B} after {args.warmup} warm-up, fp32, {threads} threads; {note}"
+    line = {"impl": "reference", "metric": "train iters/sec (16x64x64 clips, batch 32)", "value": ips, "unit": "iters/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spi * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"config/{cfg_name}.yml (normalised) training step, batch 32, 16x64x64"},
-            "cpu_baseline": {"value": value, "unit": "iters/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": ips, "unit": "iters/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": ips, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -204,58 +234,152 @@ def build_trainer(cfg, precision):
     return trainer.Trainer(None, _Log(), models, opts, L, cfg)
 
 
-def dominant_kernel_probe(cfg, B, iters=20):
-    """vdis main.1 Conv3d 64->128 forward at batch B (the 60%-of-peak target layer, 85.9 GF at B=32): CUDA-event time
-    of the tcgen05 kernel alone, L2 flushed between launches."""
+def layer_table(tr, cfg, B, reps=5):
+    """Every convolution-family launch of one training step, timed alone: records the conv / wgrad calls of one eager
+    step, then replays each distinct (kernel, geometry, direction) with CUDA events and an L2 flush between launches.
+    Returns rows {ms, n, kind, dir, impl, flops, key}; flops = 2*M*N*K with the real (unpadded) channel counts."""
+    import collections
     import ctypes as C
     from dcvgan_b200 import ops
-    from dcvgan_b200._lib import IMPL_TC
-    d = cfg["vdis"]["ndf"]
-    spec = ops.ConvSpec("conv", d, 2 * d, (4, 4, 4), (1, 2, 2), (0, 1, 1))
-    g = spec.geom(B, (13, 32, 32))
-    if not ops.lib().dcv_conv_tc_supported(C.byref(g), spec.fwd_dir):
-        return None
-    x = ops.Act.empty(B, 13, 32, 32, d, torch.bfloat16)
-    x.base.normal_()
-    y = ops.Act.empty(B, 10, 16, 16, 2 * d, torch.bfloat16)
-    w = torch.randn(2 * d, d, 4, 4, 4, device="cuda") * 0.02
-    wp = ops.pack_weight(spec, g, spec.fwd_dir, IMPL_TC, w)
+    from dcvgan_b200._lib import Geom
+    Cg = cfg["geometric_info"]["channel"]
+    xc = torch.rand(B, 3, 16, 64, 64, device="cuda") * 2 - 1
+    xg = torch.rand(B, Cg, 16, 64, 64, device="cuda") * 2 - 1
+    ops.TRACE = []
+    tr.iteration += 1
+    tr._eager_step(xc, xg, 3)
+    trace, ops.TRACE = ops.TRACE, None
+    torch.cuda.synchronize()
+    count = collections.Counter((t[0], t[1], t[2], t[3]) for t in trace)
     flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device="cuda")
-    for _ in range(3):
-        ops.conv(g, spec.fwd_dir, IMPL_TC, x, wp, y)
-    times = []
+    rows = []
+    for (kind, key, direction, impl), n in count.items():
+        g = Geom(*key)
+        taps = g.kt * g.kh * g.kw
+        M = g.N * g.Ts * g.Hs * g.Ws
+        wl, ws = (g.wCl or g.Cl), (g.wCs or g.Cs)
+        flops = 2.0 * M * taps * wl * ws
+        dt = torch.bfloat16
+        L = ops.Act.empty(g.N, g.Tl, g.Hl, g.Wl, g.Cl, dt)
+        S = ops.Act.empty(g.N, g.Ts, g.Hs, g.Ws, g.Cs, dt)
+        L.base.normal_()
+        S.base.normal_()
+        if kind == "conv":
+            nbytes = ops.lib().dcv_packed_weight_bytes(C.byref(g), direction, impl)
+            wp = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+            x, y = (L, S) if direction == 0 else (S, L)
+            fn = lambda: ops.conv(g, direction, impl, x, wp, y)
+        elif kind == "wgrad":
+            spec = ops.ConvSpec("conv", wl, ws, (g.kt, g.kh, g.kw), (g.st, g.sh, g.sw), (g.pt, g.ph, g.pw))
+            dw = torch.empty((ws, wl, taps), device="cuda")
+            fn = lambda: ops.wgrad(spec, g, L, S, dw, False, impl)
+        elif kind in ("img_conv_fwd", "img_conv_bwd"):
+            spec = ops.ConvSpec("conv", wl, ws, (g.kt, g.kh, g.kw), (g.st, g.sh, g.sw), (g.pt, g.ph, g.pw))
+            w = torch.randn((ws, wl, g.kh, g.kw), device="cuda") * 0.1
+            xin = ops.Act.empty(g.N, 1, g.Hl, g.Wl, wl, dt)
+            if kind == "img_conv_fwd":
+                fn = lambda: ops.img_conv_fwd(spec, g, xin, w, S, 1, 0.01)
+            else:
+                dw = torch.empty_like(w)
+                dxo = ops.Act.empty(g.N, 1, g.Hl, g.Wl, wl, dt)
+                S2 = S.like()
+                S2.base.normal_()
+                fn = lambda: ops.img_conv_bwd(spec, g, S2, S, xin, w, 1, 0.01, dw, False, dxo)
+                flops *= 2
+        else:
+            continue
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        rows.append({"ms": float(np.median(ts)), "n": n, "kind": kind, "dir": direction, "impl": impl, "flops": flops, "key": key})
+    rows.sort(key=lambda r: -r["ms"] * r["n"])
+    return rows
+
+
+def family_of(row):
+    from dcvgan_b200._lib import IMPL_TC
+    if row["kind"] == "conv":
+        return "conv_tc_pers_kernel (tcgen05 implicit-GEMM convolution: forward + data gradient, all template variants)" if row["impl"] == IMPL_TC else "conv_simt_kernel"
+    if row["kind"] == "wgrad":
+        return "wgrad_tc_kernel (tcgen05 weight gradient)" if row["impl"] == IMPL_TC else "wgrad_simt_kernel"
+    return "img_conv3x3 (direct CUDA-core kernels, HBM-bound)"
+
+
+def describe_layer(row):
+    from dcvgan_b200._lib import Geom
+    g = Geom(*row["key"])
+    op = {"conv": "gather" if row["dir"] == 0 else "scatter"}.get(row["kind"], row["kind"])
+    return f"{op} L({g.Tl},{g.Hl},{g.Wl},{g.wCl or g.Cl}) S({g.Ts},{g.Hs},{g.Ws},{g.wCs or g.Cs}) k{g.kt}x{g.kh}x{g.kw} N={g.N}"
+
+
+def hbm_probe(B, iters=10):
+    """bn_act (normalise + affine + ReLU) on the 512x64x64x64 bf16 U-Net tensor (268 MB at B=32): 2 B read + 2 B written
+    per element, timed alone with an L2 flush between launches."""
+    from dcvgan_b200 import ops
+    from dcvgan_b200._lib import ACT_LEAKY
+    n = B * 16
+    z = ops.Act.empty(n, 1, 64, 64, 64, torch.bfloat16)
+    z.base.normal_()
+    out = z.like()
+    c = 64
+    mean, invstd = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    gamma, beta = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        ops.bn_act(z, mean, invstd, gamma, beta, None, ACT_LEAKY, 0.0, out)
+    ts = []
     for _ in range(iters):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.conv(g, spec.fwd_dir, IMPL_TC, x, wp, y)
+        ops.bn_act(z, mean, invstd, gamma, beta, None, ACT_LEAKY, 0.0, out)
         e1.record()
         torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    ms = float(np.mean(times))
-    flops = 2.0 * (B * 10 * 16 * 16) * (2 * d) * (64 * d)
-    return {"kernel": "conv_tc_pers_kernel<4,1,2> (vdis main.1 Conv3d fwd)", "ms": ms, "tflops": flops / ms / 1e9, "flops": flops}
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts))
+    nbytes = 2.0 * z.rows * c * 2
+    return {"kernel": "bn_act_bf16_kernel (cgen up_blocks.5 BatchNorm + ReLU, 512x64x64x64)", "ms": ms, "bytes": nbytes, "gbs": nbytes / ms / 1e6}
 
 
-def cpu_baseline(cfg_name, budget_s=25.0):
-    """Oracle port timed on this box's host cores on a bounded sample of the same workload (rank 0, N=1 only)."""
-    from oracle import dcvgan_oracle as orc
-    threads = os.cpu_count()
-    torch.set_num_threads(threads)
-    Bs = 4
-    cfg = make_cfg(cfg_name, Bs)
-    tr = orc.OracleTrainer(cfg, orc.init_all(cfg, cfg["seed"]))
-    xc, xg = orc.synthetic_batch(cfg, Bs, 1000)
-    t0 = time.perf_counter()
-    tr.step(xc, xg)
-    warm = time.perf_counter() - t0
-    n = max(1, min(3, int(budget_s / max(warm, 1e-3)) - 1))
-    t0 = time.perf_counter()
-    for _ in range(n):
-        tr.step(xc, xg)
-    dt = (time.perf_counter() - t0) / n
-    return {"value": 1.0 / (dt * 32.0 / Bs), "unit": "iters/s", "cores": threads, "kind": "port",
-            "sample": f"{n} iteration(s) of the full step at batch {Bs} after 1 warm-up, scaled x{32 // Bs} to batch 32, fp32"}
+def cpu_baseline(cfg_name):
+    """The reference's CPU step timed on this box's host cores on a bounded sample of the same workload (rank 0, N=1):
+    1 warm-up + 2 timed iterations at batch 32 (about 15-25 s)."""
+    ips, spi, kind, threads, note = reference_cpu_run(cfg_name, 32, 1, 2)
+    return {"value": ips, "unit": "iters/s", "cores": threads, "kind": kind,
+            "sample": f"2 timed iterations of the full step at batch 32 after 1 warm-up, fp32; {note}"}
+
+
+def gpu_eager_baseline(cfg_name, B=32, warmup=5, steps=50):
+    """the UNMODIFIED reference run eagerly on this B200 ("existing Blackwell kernels": ATen /
+    cuDNN) - torch defaults (fp32 with cuDNN TF32 convolutions), and a fair fast variant (bf16 autocast + channels_last).
+    Device-synchronised host timestamps around exactly `steps` iterations after `warmup`."""
+    from tools import ref_harness as rh
+    if rh.reference_src() is None:
+        return {"unavailable": "reference sources not staged under baseline/_ref/src"}
+    ref = rh.import_reference()
+    cfg = make_cfg(cfg_name, B)
+    batches = synthetic_host_batches(cfg, B, 1, 1000)
+    dev_batches = [{k: v.cuda() for k, v in batches[0].items()}] * (warmup + steps)
+    out = {"unit": "iters/s", "batch": B, "steps": steps, "warmup": warmup, "inputs": "resident on the device",
+           "what": "unmodified reference modules + Trainer.train() on cuda:0 (PyTorch %s eager)" % torch.__version__}
+    for name, kw in (("tf32_default", {}), ("bf16_autocast_channels_last", {"autocast_dtype": torch.bfloat16, "channels_last": True})):
+        try:
+            torch.cuda.empty_cache()
+            _, logger = rh.run_reference_trainer(ref, cfg, dev_batches, device="cuda:0", seed=cfg["seed"], **kw)
+            ips, spi = rh.timed_iters_per_s(logger, warmup, steps)
+            out[name] = {"value": ips, "ms_per_step": spi * 1e3}
+        except Exception as e:  # noqa: BLE001 - a failing variant must not take the benchmark line down
+            out[name] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_cuda(args, cfg_name):
@@ -342,19 +466,49 @@ def run_cuda(args, cfg_name):
             "e2e": {"value": world * 1e3 / ms_e2e, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
             "gpu_launches": int(launches),
             "clocks": sampler.summary() if rank == 0 else None}
+    rows = None
+    if args.precision == "bf16" and not args.no_roofline:
+        # one traced eager iteration on every rank (it contains the gradient all-reduce), replays on rank 0 only
+        if rank == 0:
+            rows = layer_table(tr, cfg, B)
+        else:
+            Cg = cfg["geometric_info"]["channel"]
+            tr.iteration += 1
+            tr._eager_step(torch.rand(B, 3, 16, 64, 64, device="cuda"), torch.rand(B, Cg, 16, 64, 64, device="cuda"), 3)
     if rank == 0:
-        probe = dominant_kernel_probe(cfg, B) if args.precision == "bf16" else None
-        if probe:
+        line["roofline_step"] = {"bound": "tensor", "achieved": flops / ms / 1e9, "peak": sustained, "unit": "TFLOP/s",
+                                 "frac": flops / ms / 1e9 / sustained, "what": "useful FLOPs of the whole iteration (4 F_G + 8 F_D) / ms_per_step",
+                                 "peak_source": f"{src} sustained"}
+        if rows:
+            fams = {}
+            for r in rows:
+                f = fams.setdefault(family_of(r), {"ms": 0.0, "flops": 0.0, "n": 0})
+                f["ms"] += r["ms"] * r["n"]
+                f["flops"] += r["flops"] * r["n"]
+                f["n"] += r["n"]
+            name, top = max(fams.items(), key=lambda kv: kv[1]["ms"])          # kernel with the largest share of the step
+            big = next(r for r in rows if family_of(r) == name)                  # its most expensive layer
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-            if os.path.exists(tpath):   # dram__bytes_read+write per launch from the committed `ncu --set full` capture of this launch
-                traffic = json.load(open(tpath)).get("prof_vdis_main1_fwd", {}).get("dram_bytes_per_launch")
-            line["roofline"] = {"bound": "tensor", "achieved": probe["tflops"], "peak": burst, "unit": "TFLOP/s",
-                                "frac": probe["tflops"] / burst, "traffic": traffic, "kernel": probe["kernel"],
-                                "algorithmic_flops_per_launch": probe["flops"],
-                                "ms_per_launch": probe["ms"], "peak_source": f"{src} burst (kernel timed alone)"}
+            if os.path.exists(tpath):   # dram__bytes_read+write per launch from the committed `ncu --set full` capture of that layer
+                traffic = json.load(open(tpath)).get(describe_layer(big), {}).get("dram_bytes_per_launch")
+            line["roofline"] = {"bound": "tensor", "achieved": top["flops"] / top["ms"] / 1e9, "peak": burst, "unit": "TFLOP/s",
+                                "frac": top["flops"] / top["ms"] / 1e9 / burst, "traffic": traffic, "kernel": name,
+                                "launches_per_step": top["n"], "ms_per_step": top["ms"], "share_of_step": top["ms"] / ms,
+                                "algorithmic_flops_per_launch": top["flops"] / top["n"], "ms_per_launch": top["ms"] / top["n"],
+                                "how": "every launch of the kernel in one iteration replayed alone (CUDA events, L2 flushed between launches); achieved = sum of algorithmic FLOPs / sum of launch times",
+                                "largest_launch": {"layer": describe_layer(big), "ms": big["ms"], "n_per_step": big["n"], "tflops": big["flops"] / big["ms"] / 1e9,
+                                                   "frac": big["flops"] / big["ms"] / 1e9 / burst},
+                                "peak_source": f"{src} burst (kernels timed alone)"}
+            line["kernel_families"] = {k: {"ms_per_step": round(v["ms"], 4), "launches": v["n"], "tflops": round(v["flops"] / v["ms"] / 1e9, 1),
+                                           "share_of_step": round(v["ms"] / ms, 4)} for k, v in fams.items()}
+            hb = hbm_probe(B)
+            line["roofline_hbm"] = {"bound": "hbm", "achieved": hb["gbs"], "peak": hbm, "unit": "GB/s", "frac": hb["gbs"] / hbm, "traffic": None,
+                                    "kernel": hb["kernel"], "algorithmic_bytes_per_launch": hb["bytes"], "ms_per_launch": hb["ms"]}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(cfg_name)
+        if world == 1 and not args.no_eager:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(cfg_name)
         print(json.dumps(line), flush=True)
     if world > 1:
         # Captured CUDA graphs hold NCCL work; tearing the communicator down under them can block (observed: the
@@ -376,8 +530,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--config", default="mug-depth", choices=sorted(CONFIGS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--ref-batch", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (unmodified reference on cuda:0)")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-layer replay behind the roofline objects")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 3:

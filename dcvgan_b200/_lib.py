@@ -10,6 +10,8 @@ from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libdcvgan_b200.so"
+if os.environ.get("DCV_EXPERIMENTS_LIB", "0") == "1":      # tools/exp_*.py only: the -DDCV_EXPERIMENTS build (csrc/build.sh exp)
+    LIB_PATH = _HERE / "libdcvgan_b200_exp.so"
 
 DCV_F32, DCV_BF16 = 0, 1
 ACT_NONE, ACT_LEAKY, ACT_TANH = 0, 1, 2
@@ -29,6 +31,8 @@ class Geom(C.Structure):
         return tuple(getattr(self, n) for n, _ in self._fields_)
 
 
+ABI_VERSION = 4   # include/dcvgan_b200.h DCV_ABI_VERSION
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _G = C.POINTER(Geom)
 
@@ -38,6 +42,11 @@ SIGNATURES = {
     "dcv_last_error": (C.c_char_p, []),
     "dcv_device_ok": (_i, []),
     "dcv_launch_count": (C.c_longlong, []),
+    "dcv_set_tuning": (_i, [C.c_char_p, _i]),
+    "dcv_img_conv_supported": (_i, [_G]),
+    "dcv_img_conv_bwd_workspace_bytes": (_i64, [_G]),
+    "dcv_img_conv_fwd": (_i, [_G, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i, _f, _vp]),
+    "dcv_img_conv_bwd": (_i, [_G, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i, _f, _vp, _i, _vp, _i64, _vp, _i64, _vp]),
     "dcv_packed_weight_bytes": (_i64, [_G, _i, _i]),
     "dcv_pack_weight": (_i, [_G, _i, _i, _vp, _i64, _i64, _i64, _vp, _vp]),
     "dcv_pack_weight_batch": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -106,7 +115,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.dcv_abi_version() != 3:
+        if handle.dcv_abi_version() != ABI_VERSION:
             raise DcvError("libdcvgan_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -40,6 +40,12 @@ int wgrad_reduce_win(const float*, int, const dcv_geom*, WeightWin, float*, int6
 int wgrad_reduce_multi(const float*, int, const dcv_geom*, int, float* const*, const int64_t*, const int64_t*, const int64_t*, const int*,
                        const int*, const int*, const int*, const int*, cudaStream_t);
 int conv_tc_supported(const dcv_geom*, int);
+int set_tuning(const char*, int);
+int img_conv_supported(const dcv_geom*);
+int64_t img_conv_bwd_ws_bytes(const dcv_geom*);
+int img_conv_fwd(const dcv_geom*, const void*, int64_t, const float*, int64_t, int64_t, int64_t, void*, int64_t, int, float, cudaStream_t);
+int img_conv_bwd(const dcv_geom*, const void*, int64_t, const void*, int64_t, const void*, int64_t, const float*, int64_t, int64_t,
+                 int64_t, int, float, float*, int, void*, int64_t, void*, int64_t, cudaStream_t);
 int pack_weight_tc_multi(const dcv_geom*, int, int, const float* const*, const int64_t*, const int64_t*, const int64_t*, const int*,
                          const int*, const int*, const int*, void*, cudaStream_t);
 int pack_weight_tc_batch(int, const dcv_geom* const*, const int*, const float* const*, const int64_t*, const int64_t*, const int64_t*,
@@ -74,6 +80,25 @@ int dcv_abi_version(void) { return DCV_ABI_VERSION; }
 const char* dcv_last_error(void) { return g_err; }
 
 long long dcv_launch_count(void) { return g_launches; }
+
+int dcv_img_conv_supported(const dcv_geom* g) { return g && check_geom(g) == 0 ? img_conv_supported(g) : 0; }
+int64_t dcv_img_conv_bwd_workspace_bytes(const dcv_geom* g) { return g ? img_conv_bwd_ws_bytes(g) : -1; }
+int dcv_img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
+                     void* y, int64_t ldy, int act, float slope, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DCV_REQUIRE(x && w && y, "img_conv_fwd: null pointer");
+  return img_conv_fwd(g, x, ldx, w, s_l, s_s, s_tap, y, ldy, act, slope, as_stream(stream));
+}
+int dcv_img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x, int64_t ldx,
+                     const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, int act, float slope, float* dw, int accumulate,
+                     void* dx, int64_t lddx, void* ws, int64_t ws_bytes, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DCV_REQUIRE(da && a && x && w && ws, "img_conv_bwd: null pointer");
+  return img_conv_bwd(g, da, ldda, a, lda, x, ldx, w, s_l, s_s, s_tap, act, slope, dw, accumulate, dx, lddx, ws, ws_bytes,
+                      as_stream(stream));
+}
+
+int dcv_set_tuning(const char* key, int value) { DCV_REQUIRE(key, "dcv_set_tuning: null key"); return set_tuning(key, value); }
 
 int dcv_device_ok(void) {
   int dev = 0;

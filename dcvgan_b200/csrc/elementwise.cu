@@ -1098,10 +1098,6 @@ int dcv_bn_stats_blocks(int64_t rows, int C) {
 
 int dcv_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float* partials, void* stream) {
   const int nblk = dcv_bn_stats_blocks(rows, C);
-  if (getenv("DCV_EXP_SKIP_BN_STATS")) {      // timing experiment only: how much of the step is this pass?
-    cudaMemsetAsync(partials, 0, (size_t)nblk * 2 * C * sizeof(float), as_stream(stream));
-    return 0;
-  }
   DISPATCH_T(dtype, {
     if (sizeof(T) == 2 && vec_ok<T>(C, {z}, {ldz}))
       bn_stats_bf16_kernel<<<nblk, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, ldz, rows, C, partials);

@@ -9,8 +9,6 @@
 //                 convolution stride, out-of-bounds coordinates implement zero padding - so no im2col matrix ever exists
 //                 in HBM.  Transposed (scatter) correlations run as stride^d sub-pixel phases.  HG > 1: the h taps of one
 //                 lattice share a box with halo rows; KS == 0: four 16-channel taps per stage (image-like operands).
-//   conv_tc_kernel / conv_tc_g4_kernel
-//               : the earlier multi-CTA kernels, kept behind DCV_TC_NOPERSIST=1 for A/B timing.
 //   wgrad_tc    : weight gradient.  Both operands are MN-major (channels contiguous, pixels = GEMM K), again
 //                 straight from the activations by TMA; one wave of CTAs split over pixel ranges, fp32 partials reduced
 //                 in a fixed order by wgrad_reduce (simt_conv.cu).
@@ -24,8 +22,34 @@
 #include <cuda.h>
 #include <mutex>
 #include <stdlib.h>
+#include <string.h>
 
 namespace dcv {
+
+// Tuning / timing-experiment hooks (environment overrides, "stop loading A / B", "skip the stores") exist only in the
+// -DDCV_EXPERIMENTS build that tools/exp_*.py use (csrc/build.sh exp); the product library has none of them, so no
+// environment variable can change what a production kernel loads or stores.
+// Result-preserving tuning switches (row-halo sharing off, forced M-tile count, direct-store epilogue, extra wgrad split
+// waves ...) are explicit process state set through dcv_set_tuning(), never read from the environment; the parity tests
+// flip them to cover every code path of the kernels (tests/test_ops_gpu.py::test_conv_tcgen05_kernel_variants).
+struct Tuning { int nohalo, mt, no_tma_store, no_narrow_tma_store, wgrad_waves, no_gemv, no_tapgroup, no_fused_stats, sm_reserve; };
+static Tuning g_tune = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+int set_tuning(const char* key, int value) {
+  struct { const char* k; int* v; } tab[] = {{"nohalo", &g_tune.nohalo}, {"mt", &g_tune.mt}, {"no_tma_store", &g_tune.no_tma_store},
+      {"no_narrow_tma_store", &g_tune.no_narrow_tma_store}, {"wgrad_waves", &g_tune.wgrad_waves}, {"no_gemv", &g_tune.no_gemv},
+      {"no_tapgroup", &g_tune.no_tapgroup}, {"no_fused_stats", &g_tune.no_fused_stats}, {"sm_reserve", &g_tune.sm_reserve}};
+  for (auto& t : tab) if (!strcmp(t.k, key)) { *t.v = value; return 0; }
+  DCV_REQUIRE(false, "dcv_set_tuning: unknown key '%s'", key);
+}
+int tuning_sm_reserve() { return g_tune.sm_reserve; }
+
+#ifdef DCV_EXPERIMENTS
+static inline const char* exp_env(const char* name) { return getenv(name); }
+#define TC_DBG(p) ((p).dbg)
+#else
+static inline const char* exp_env(const char*) { return nullptr; }
+#define TC_DBG(p) 0
+#endif
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -213,160 +237,6 @@ struct TcConvP {
   int a_tile16;                          // M-tile stride inside the A box, in 16-byte units (rows incl. halo x row bytes)
   int dbg;                               // DCV_TC_DBG (timing experiments only): 1 = stop loading A, 2 = stop loading B after the first ring fill
 };
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcConvP p,
-               __nv_bfloat16* __restrict__ y) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[MAX_STAGES];
-  __shared__ uint64_t empty_bar[MAX_STAGES];
-  __shared__ uint64_t tmem_full_bar;
-  __shared__ uint32_t tmem_slot;
-
-  const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0), lane = threadIdx.x % 32;   // warp-uniform for the compiler
-  const PhaseInfo f = make_phase(p.c, blockIdx.z);
-
-  int tile = blockIdx.x;
-  const int tw = tile % p.tiles_w; tile /= p.tiles_w;
-  const int th = tile % p.tiles_h; tile /= p.tiles_h;
-  const int tt = tile % p.tiles_t; const int tn = tile / p.tiles_t;
-  const int w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt, n0 = tn * p.bn * p.mt;
-  if (w0 >= f.Qw || h0 >= f.Qh || t0 >= f.Qt) return;  // tile outside this phase (uniform per CTA)
-
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int stage_bytes = p.a_bytes + p.b_bytes;
-  const int ntaps = f.nt * f.nh * f.nw;
-
-  if (warp == 0 && lane == 0) { tmap_prefetch(&mapA); tmap_prefetch(&mapB); }
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      mbar_init(&tmem_full_bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-
-  if (warp == 0) {
-    // TMA producer.  Warp-uniform loop (all lanes wait on the barrier), one elected lane issues.
-    const bool leader = elect_one();
-    int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0; int issued = 0;
-    for (int jt = 0; jt < f.nt; ++jt) {
-      const int ct = t0 * f.mult + f.offt + f.sgn * jt;
-      const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
-      for (int jh = 0; jh < f.nh; ++jh) {
-        const int ch = h0 * f.mulh + f.offh + f.sgn * jh;
-        const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
-        for (int jw = 0; jw < f.nw; ++jw, ++j) {
-          const int cw = w0 * f.mulw + f.offw + f.sgn * jw;
-          const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
-          if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            const bool ldA = !(p.dbg & 1) || issued < p.stages, ldB = !(p.dbg & 2) || issued < p.stages;
-            ++issued;
-            if (leader) {
-              mbar_expect_tx(&full_bar[stage], (uint32_t)((ldA ? p.a_bytes : 0) + (ldB ? p.tx_bytes - p.a_bytes : 0)));
-              const uint32_t a_dst = sbase + stage * stage_bytes;
-              if (ldA) tma_load_5d(a_dst, &mapA, &full_bar[stage], kc * p.cblk, cw, ch, ct, n0);
-              if (ldB) tma_load_3d(a_dst + p.a_bytes, &mapB, &full_bar[stage], j * p.c.Kc + kc * p.cblk, blockIdx.y * p.bnt, blockIdx.z);
-            }
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-          }
-          ++executed;
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // MMA issuer (see "lean MMA issue" above): uniform control flow, elected lane issues and commits
-    const bool leader = elect_one();
-    const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
-    const uint32_t dhi = sdesc_hi(8u * (uint32_t)p.cblk * 2u, (uint32_t)p.swz_layout);
-    const uint32_t a_tile16 = (128u * (uint32_t)p.cblk * 2u) >> 4;
-    int stage = 0; uint32_t phase = 0; int executed = 0; int j = 0; uint32_t accum = 0;
-    for (int jt = 0; jt < f.nt; ++jt) {
-      const int ct = t0 * f.mult + f.offt + f.sgn * jt;
-      const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
-      for (int jh = 0; jh < f.nh; ++jh) {
-        const int ch = h0 * f.mulh + f.offh + f.sgn * jh;
-        const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
-        for (int jw = 0; jw < f.nw; ++jw, ++j) {
-          const int cw = w0 * f.mulw + f.offw + f.sgn * jw;
-          const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
-          if ((skt || skh || skw) && !(j == ntaps - 1 && executed == 0)) continue;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t a_src = sbase + stage * stage_bytes;
-            const uint32_t alo = sdesc_lo(a_src, 16), blo = sdesc_lo(a_src + p.a_bytes, 16);
-            if (leader) {
-              if (p.cblk == 64) conv_issue_stage<4>(tmem_base, alo, blo, dhi, idesc, accum, p.mt, a_tile16, (uint32_t)p.bnt);
-              else if (p.cblk == 32) conv_issue_stage<2>(tmem_base, alo, blo, dhi, idesc, accum, p.mt, a_tile16, (uint32_t)p.bnt);
-              else conv_issue_stage<1>(tmem_base, alo, blo, dhi, idesc, accum, p.mt, a_tile16, (uint32_t)p.bnt);
-              umma_commit(&empty_bar[stage]);
-            }
-            accum = 1;
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-          }
-          ++executed;
-        }
-      }
-    }
-    if (leader) umma_commit(&tmem_full_bar);
-    __syncwarp();
-  } else {
-    // epilogue: TMEM lane quarter = warp % 4 (hardware restriction), row = quarter*32 + lane
-    const int quarter = warp % 4;
-    const int row = quarter * 32 + lane;
-    int r = row;
-    const int dw = r % p.bw; r /= p.bw;
-    const int dh = r % p.bh; r /= p.bh;
-    const int dt = r % p.bt; const int dn = r / p.bt;
-    const int qw = w0 + dw, qh = h0 + dh, qt = t0 + dt;
-    const int nbase = blockIdx.y * p.bnt;
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-    for (int m = 0; m < p.mt; ++m) {
-      const int n = n0 + m * p.bn + dn;
-      const bool valid = qw < f.Qw && qh < f.Qh && qt < f.Qt && n < p.c.N;
-      const int64_t pos = (((int64_t)n * p.c.Ot + (qt * f.ost + f.rt)) * p.c.Oh + (qh * f.osh + f.rh)) * p.c.Ow + (qw * f.osw + f.rw);
-      __nv_bfloat16* yrow = y + pos * p.ldy;
-      for (int cb = 0; cb < p.bnt; cb += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * p.bnt + cb), v);
-        if (!valid) continue;
-        const int c0 = nbase + cb;
-        if (c0 >= p.c.Nc) continue;
-        if (p.vec_ok && c0 + 16 <= p.c.Nc) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a = apply_act(__uint_as_float(v[2 * i]), p.act, p.slope);
-            const float b = apply_act(__uint_as_float(v[2 * i + 1]), p.act, p.slope);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < p.c.Nc) yrow[c0 + i] = __float2bfloat16_rn(apply_act(__uint_as_float(v[i]), p.act, p.slope));
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-}
 
 // ------------------------------------------------------------------------------------------ conv_tc, persistent
 // One CTA per SM walks the work items (tile = blockIdx.x + i * gridDim.x); the shared-memory ring runs continuously
@@ -580,7 +450,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             if ((skt || skh || skw) && !(jc == nlast && executed == 0)) continue;   // box entirely in the padding
             for (int kc = 0; kc < p.kchunks; ++kc) {
               mbar_wait(&empty_bar[stage], phase ^ 1u);
-              const bool ldA = !(p.dbg & 1) || issued < p.stages, ldB = !(p.dbg & 2) || issued < p.stages;
+              const bool ldA = !(TC_DBG(p) & 1) || issued < p.stages, ldB = !(TC_DBG(p) & 2) || issued < p.stages;
               ++issued;
               if (leader) {
                 mbar_expect_tx(&full_bar[stage], (uint32_t)((ldA ? p.a_bytes : 0) + (ldB ? p.tx_bytes - p.a_bytes : 0)));
@@ -761,7 +631,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           else { uint32_t t16[16]; tmem_ld16(d_base + (uint32_t)(m * p.bnt), t16);
 #pragma unroll
                  for (int i = 0; i < 16; ++i) v[i] = t16[i]; }
-          if (!(p.dbg & 4)) {
+          if (!(TC_DBG(p) & 4)) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               if (c * 8 >= cw) break;
@@ -779,7 +649,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0 && !(p.dbg & 4)) {
+          if (lane == 0 && !(TC_DBG(p) & 4)) {
             tma_store_5d(&mapY, buf, nbase, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
                          (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
             tma_store_commit();
@@ -811,7 +681,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             tmem_ld32_nowait(d_base + (uint32_t)(m * p.bnt + cb), v);
             tmem_ld32_nowait(d_base + (uint32_t)(m * p.bnt + cb + 32), w);
             tmem_ld_wait();
-            if (!(p.dbg & 4)) {
+            if (!(TC_DBG(p) & 4)) {
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
                 const uint32_t* src = c < 4 ? v + 8 * c : w + 8 * (c - 4);
@@ -843,7 +713,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 bq[ci][0] = fmaf(f0, f0, bq[ci][0]); bq[ci][1] = fmaf(f1, f1, bq[ci][1]);
               }
             }
-            if (lane == 0 && !(p.dbg & 4)) {
+            if (lane == 0 && !(TC_DBG(p) & 4)) {
               tma_store_5d(&mapY, buf, nbase + cb, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
                            (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
               tma_store_commit();
@@ -859,19 +729,19 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const int64_t pos = (((int64_t)n * p.c.Ot + (qt * f.ost + f.rt)) * p.c.Oh + (qh * f.osh + f.rh)) * p.c.Ow + (qw * f.osw + f.rw);
         __nv_bfloat16* yrow = y + pos * p.ldy;
         int cb = 0;
-        if (p.dbg & 8) continue;                                // timing experiment: no TMEM reads, no stores
+        if (TC_DBG(p) & 8) continue;                                // timing experiment: no TMEM reads, no stores
         for (; cb + 32 <= p.bnt; cb += 32) {                    // 32 columns per TMEM round trip
           uint32_t v[32];
           tmem_ld32_nowait(d_base + (uint32_t)(m * p.bnt + cb), v);
           tmem_ld_wait();
-          if (!valid || (p.dbg & 4)) continue;
+          if (!valid || (TC_DBG(p) & 4)) continue;
           store_row16(v, yrow, nbase + cb, p.c.Nc, p.vec_ok, p.act, p.slope);
           store_row16(v + 16, yrow, nbase + cb + 16, p.c.Nc, p.vec_ok, p.act, p.slope);
         }
         for (; cb < p.bnt; cb += 16) {
           uint32_t v[16];
           tmem_ld16(d_base + (uint32_t)(m * p.bnt + cb), v);
-          if (!valid || (p.dbg & 4)) continue;
+          if (!valid || (TC_DBG(p) & 4)) continue;
           store_row16(v, yrow, nbase + cb, p.c.Nc, p.vec_ok, p.act, p.slope);
         }
       }
@@ -898,175 +768,6 @@ static ConvPersFn conv_pers_variant(int ks, int mt, int hg) {
   DCV_V(4, 1, 3) DCV_V(4, 2, 3) DCV_V(4, 4, 3) DCV_V(2, 1, 3) DCV_V(2, 2, 3) DCV_V(2, 4, 3)   // 3 taps per class (3x3 stride 1)
 #undef DCV_V
   return nullptr;
-}
-
-// ------------------------------------------------------------------------------------------ conv_tc, grouped taps
-// Image-like operands (16 padded channels: D stems, inconv, outconv / main.12 data gradients) make one tap = one
-// 16-wide K step.  In the generic kernel above that is one pipeline stage per tap - two tiny TMA boxes and a barrier
-// round trip for ~32 cycles of MMA - so those layers were bound by TMA issue and barrier latency.  Here a stage
-// carries FOUR taps: four A boxes (32-byte rows, 32B swizzle, issued in parallel by four lanes) and ONE B box of
-// 4 taps x 16 channels = 64 K-elements per output channel (128-byte rows, 128B swizzle - the packed weight layout
-// [n][tap][k] makes consecutive taps contiguous), consumed by up to 4*mt MMAs whose A and B descriptors simply use
-// different swizzle modes.
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_g4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcConvP p,
-                  __nv_bfloat16* __restrict__ y) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[MAX_STAGES];
-  __shared__ uint64_t empty_bar[MAX_STAGES];
-  __shared__ uint64_t tmem_full_bar;
-  __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t empty_tile_flag;
-
-  const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0), lane = threadIdx.x % 32;   // warp-uniform for the compiler
-  const PhaseInfo f = make_phase(p.c, blockIdx.z);
-  int tile = blockIdx.x;
-  const int tw = tile % p.tiles_w; tile /= p.tiles_w;
-  const int th = tile % p.tiles_h; tile /= p.tiles_h;
-  const int tt = tile % p.tiles_t; const int tn = tile / p.tiles_t;
-  const int w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt, n0 = tn * p.bn * p.mt;
-  if (w0 >= f.Qw || h0 >= f.Qh || t0 >= f.Qt) return;
-
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int a_tap_bytes = p.mt * 128 * 32;                  // one tap: mt*128 rows of 16 bf16
-  const int stage_bytes = TAPG * a_tap_bytes + p.b_bytes;   // b_bytes = bnt rows * 128 B
-  const int ntaps = f.nt * f.nh * f.nw;
-  const int ngroups = (ntaps + TAPG - 1) / TAPG;
-
-  if (warp == 0 && lane == 0) { tmap_prefetch(&mapA); tmap_prefetch(&mapB); }
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      mbar_init(&tmem_full_bar, 1);
-      empty_tile_flag = 0u;
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-
-  // per-lane view of "its" tap inside a group (lanes 0..3): coordinates and whether the whole box is padding
-  auto tap_coords = [&](int j, int& ct, int& ch, int& cw) -> bool {
-    const int jw = j % f.nw, jh = (j / f.nw) % f.nh, jt = j / (f.nw * f.nh);
-    ct = t0 * f.mult + f.offt + f.sgn * jt;
-    ch = h0 * f.mulh + f.offh + f.sgn * jh;
-    cw = w0 * f.mulw + f.offw + f.sgn * jw;
-    const bool skt = (ct + (p.bt - 1) * f.mult < 0) || (ct >= p.c.It);
-    const bool skh = (ch + (p.bh - 1) * f.mulh < 0) || (ch >= p.c.Ih);
-    const bool skw = (cw + (p.bw - 1) * f.mulw < 0) || (cw >= p.c.Iw);
-    return !(skt || skh || skw);      // true = has in-bounds pixels
-  };
-
-  if (warp == 0) {
-    int stage = 0; uint32_t phase = 0;
-    for (int gq = 0; gq < ngroups; ++gq) {
-      const int j = gq * TAPG + lane;
-      int ct = 0, ch = 0, cw = 0;
-      const bool live = lane < TAPG && j < ntaps && tap_coords(j, ct, ch, cw);
-      const uint32_t mask = __ballot_sync(0xffffffffu, live) & 0xFu;
-      if (mask == 0u) continue;                 // every tap of this group lies in the padding (same test in the MMA warp)
-      const int nlive = __popc(mask);
-      mbar_wait(&empty_bar[stage], phase ^ 1u);
-      if (lane == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(nlive * a_tap_bytes + p.bnt * 128));
-      __syncwarp();
-      const uint32_t a_dst = sbase + stage * stage_bytes;
-      if (live) tma_load_5d(a_dst + lane * a_tap_bytes, &mapA, &full_bar[stage], 0, cw, ch, ct, n0);
-      if (lane == TAPG) tma_load_3d(a_dst + TAPG * a_tap_bytes, &mapB, &full_bar[stage], gq * TAPG * 16, blockIdx.y * p.bnt, blockIdx.z);
-      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
-    const bool leader = elect_one();
-    const uint32_t ahi = sdesc_hi(256, 6), bhi = sdesc_hi(1024, 2);   // A: 32-byte rows / 32B swizzle, B: 128-byte rows / 128B swizzle
-    int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
-    for (int gq = 0; gq < ngroups; ++gq) {
-      const int j = gq * TAPG + lane;
-      int ct = 0, ch = 0, cw = 0;
-      const bool live = lane < TAPG && j < ntaps && tap_coords(j, ct, ch, cw);
-      const uint32_t mask = __ballot_sync(0xffffffffu, live) & 0xFu;
-      if (mask == 0u) continue;
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
-      const uint32_t a_src = sbase + stage * stage_bytes;
-      const uint32_t alo = sdesc_lo(a_src, 16), blo = sdesc_lo(a_src + TAPG * a_tap_bytes, 16);
-      if (leader) {
-#pragma unroll
-        for (int jj = 0; jj < TAPG; ++jj) {
-          if (!((mask >> jj) & 1u)) continue;
-          umma_lohi(tmem_base, alo + jj * (a_tap_bytes >> 4), ahi, blo + 2 * jj, bhi, idesc, accum);
-          if (p.mt == 2) umma_lohi(tmem_base + p.bnt, alo + jj * (a_tap_bytes >> 4) + ((128 * 32) >> 4), ahi, blo + 2 * jj, bhi, idesc, accum);
-          accum = 1;
-        }
-        umma_commit(&empty_bar[stage]);
-      }
-      accum = 1;
-      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-    }
-    if (leader) {
-      if (accum == 0) {                 // no tap touched real pixels: the tile is all zeros, nothing was accumulated
-        empty_tile_flag = 1u;
-        mbar_arrive(&tmem_full_bar);    // plain arrive (release) so that the flag is visible to the epilogue
-      } else {
-        umma_commit(&tmem_full_bar);
-      }
-    }
-    __syncwarp();
-  } else {
-    const int quarter = warp % 4;
-    const int row = quarter * 32 + lane;
-    int r = row;
-    const int dw = r % p.bw; r /= p.bw;
-    const int dh = r % p.bh; r /= p.bh;
-    const int dt = r % p.bt; const int dn = r / p.bt;
-    const int qw = w0 + dw, qh = h0 + dh, qt = t0 + dt;
-    const int nbase = blockIdx.y * p.bnt;
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-    const bool empty_tile = *((volatile uint32_t*)&empty_tile_flag) != 0u;
-    for (int m = 0; m < p.mt; ++m) {
-      const int n = n0 + m * p.bn + dn;
-      const bool valid = qw < f.Qw && qh < f.Qh && qt < f.Qt && n < p.c.N;
-      const int64_t pos = (((int64_t)n * p.c.Ot + (qt * f.ost + f.rt)) * p.c.Oh + (qh * f.osh + f.rh)) * p.c.Ow + (qw * f.osw + f.rw);
-      __nv_bfloat16* yrow = y + pos * p.ldy;
-      for (int cb = 0; cb < p.bnt; cb += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * p.bnt + cb), v);
-        if (!valid) continue;
-        const int c0 = nbase + cb;
-        if (c0 >= p.c.Nc) continue;
-        if (empty_tile) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0u;
-        }
-        if (p.vec_ok && c0 + 16 <= p.c.Nc) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a = apply_act(__uint_as_float(v[2 * i]), p.act, p.slope);
-            const float b = apply_act(__uint_as_float(v[2 * i + 1]), p.act, p.slope);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < p.c.Nc) yrow[c0 + i] = __float2bfloat16_rn(apply_act(__uint_as_float(v[i]), p.act, p.slope));
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------ single-channel heads
@@ -1212,7 +913,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     const int wend = p.tiles_w * p.bw, hend = p.tiles_h * p.bh, tend = p.tiles_t * p.bt;
     for (int64_t pt = pt_begin; pt < pt_end; ++pt) {
       mbar_wait(&empty_bar[stage], phase ^ 1u);
-      const bool skip = (p.dbg & 3) && (pt - pt_begin) >= p.stages;
+      const bool skip = (TC_DBG(p) & 3) && (pt - pt_begin) >= p.stages;
       if (lane == 0) mbar_expect_tx(&full_bar[stage], skip ? 0u : (uint32_t)(blkB_bytes * nbB + blkA_bytes * blocksA_here));
       __syncwarp();
       const uint32_t s_dst = sbase + stage * stage_bytes;
@@ -1531,7 +1232,7 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   TcConvP p;
   p.c = make_convp(g, dir);
   const ConvP& c = p.c;
-  if (!c.scatter && c.wN == 1 && c.Kc % 8 == 0 && (ldx % 8) == 0 && (((uintptr_t)x) & 15) == 0 && !getenv("DCV_NO_GEMV")) {
+  if (!c.scatter && c.wN == 1 && c.Kc % 8 == 0 && (ldx % 8) == 0 && (((uintptr_t)x) & 15) == 0 && !g_tune.no_gemv) {
     if (slots_out) return 0;
     DCV_REQUIRE(!stats, "conv_tc: fused statistics are not available for the single-channel head kernel");
     const int64_t M = (int64_t)c.N * c.Ot * c.Oh * c.Ow;          // one warp per logit
@@ -1551,48 +1252,19 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   p.swz_layout = p.cblk == 64 ? 2 : (p.cblk == 32 ? 4 : 6);
   const CUtensorMapSwizzle swz = p.cblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                               : (p.cblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  // two M tiles per CTA (stacked along the batch dimension, so they share the tap-skip pattern, one TMA box and
-  // every weight tile) when the batch allows it and enough CTAs remain to fill the machine
-  p.mt = 1;
-  {
-    const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * (npad / p.bnt) * phases;
-    if (p.bnt <= 256 && p.bn * 2 <= 256 && c.N >= 2 * p.bn && ctas >= 2 * 148 * 2) p.mt = 2;
-    if (getenv("DCV_TC_MT1")) p.mt = 1;
-  }
-  p.tiles_n = ceil_div(c.N, p.bn * p.mt);
-  p.a_bytes = p.mt * 128 * p.cblk * 2;
   p.b_bytes = (p.bnt * p.cblk * 2 + 1023) / 1024 * 1024;
-  p.tx_bytes = p.a_bytes + p.bnt * p.cblk * 2;
   const int ntaps0 = f0.nt * f0.nh * f0.nw;
-  p.tmem_cols = pow2_ceil(p.mt * p.bnt < 32 ? 32 : p.mt * p.bnt);
-  // Several CTAs per SM hide each other's prologue / epilogue (tiles with few K iterations are otherwise dominated
-  // by TMEM allocation, barrier setup and the store epilogue): split the ~216 KB of shared memory between as many
-  // CTAs as TMEM (512 columns) allows, up to 4, keeping at least 2 stages each.
-  int ctas_per_sm = 512 / p.tmem_cols; if (ctas_per_sm > 4) ctas_per_sm = 4; if (ctas_per_sm < 1) ctas_per_sm = 1;
-  { const char* e = getenv("DCV_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
-  if (const char* e = getenv("DCV_TC_CPS")) { const int v = atoi(e); if (v >= 1 && v < ctas_per_sm) ctas_per_sm = v; }
-  {
-    const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * (npad / p.bnt) * phases;
-    const int need = (int)((ctas + 147) / 148);          // CTAs that can actually share an SM
-    if (ctas_per_sm > need) ctas_per_sm = need < 1 ? 1 : need;
-  }
-  const int k_iters = ntaps0 * p.kchunks;
-  int stages = ((216 * 1024) / ctas_per_sm - 2048) / (p.a_bytes + p.b_bytes);
-  while (stages < 2 && ctas_per_sm > 1) { --ctas_per_sm; stages = ((216 * 1024) / ctas_per_sm - 2048) / (p.a_bytes + p.b_bytes); }
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > k_iters) stages = k_iters;
-  if (stages < 1) stages = 1;
-  p.stages = stages;
+  { const char* e = exp_env("DCV_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.ldy = ldy; p.act = act; p.slope = slope;
   p.vec_ok = (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0);
 
   CUtensorMap mapA, mapB;
   int rc = 0;
-  const bool g4 = c.Kc == 16 && ntaps0 >= 4 && !getenv("DCV_NO_TAPGROUP");   // grouped-tap mode for 16-channel (image-like) operands
+  const bool g4 = c.Kc == 16 && ntaps0 >= 4 && !g_tune.no_tapgroup;   // grouped-tap mode for 16-channel (image-like) operands
   const int64_t Kph = (int64_t)ntaps0 * c.Kc;  // K extent of one phase
 
-  if (!getenv("DCV_TC_NOPERSIST")) {
-    // persistent variant: one CTA per SM, two accumulator sets in TMEM
+  {
+    // persistent kernel: one CTA per SM, two accumulator sets in TMEM
     static int num_sms = 0;
     if (num_sms == 0) {
       int dev = 0;
@@ -1603,9 +1275,9 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     DCV_REQUIRE(phases <= 8, "conv_tc: %d sub-pixel phases", phases);
     for (int ph = 0; ph < phases; ++ph) p.phs[ph] = make_phase(c, ph);
     p.tma_store = 0;                                         // 1: 64-channel chunks, 2: one 16- / 32-channel chunk
-    if ((((uintptr_t)y & 15) == 0) && (ldy % 8 == 0) && !getenv("DCV_TC_NO_TMA_STORE")) {
+    if ((((uintptr_t)y & 15) == 0) && (ldy % 8 == 0) && !g_tune.no_tma_store) {
       if (p.bnt % 64 == 0) p.tma_store = 1;
-      else if ((p.bnt == 16 || p.bnt == 32) && c.Nc >= p.bnt && !getenv("DCV_TC_NO_NARROW_TMA_STORE")) p.tma_store = 2;
+      else if ((p.bnt == 16 || p.bnt == 32) && c.Nc >= p.bnt && !g_tune.no_narrow_tma_store) p.tma_store = 2;
     }
     const int stg_bytes = p.tma_store ? 2 * 16384 : 0;
     p.b_bytes = g4 ? (p.bnt * 128 + 1023) / 1024 * 1024 : p.b_bytes;
@@ -1616,7 +1288,7 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     // tile row holds a multiple of 8 pixels.  L2 -> SM traffic for A drops to (bh + hg - 1) / (hg * bh) of the per-tap
     // boxes; the tile is re-shaped to 16 x 8 so that the halo stays small.  Needs a tile that lies in one (n, t) slice.
     p.hg = 1; p.hcls = f0.nh;
-    if (!g4 && !getenv("DCV_TC_NOHALO")) {
+    if (!g4 && !g_tune.nohalo) {
       const int hg = c.scatter ? f0.nh : (g->kh % g->sh == 0 ? g->kh / g->sh : 1);
       const int hbw = f0.Qw >= 16 ? 16 : (f0.Qw >= 8 ? 8 : 0);
       const int hbh = hbw ? 128 / hbw : 0;
@@ -1649,9 +1321,8 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
       if (balance(mt) < 0.9 * balance(p.mt)) break;
       p.mt = mt;
     }
-    if (getenv("DCV_TC_MT1")) p.mt = 1;
-    if (const char* e = getenv("DCV_TC_MT")) {      // tuning override: force 1 / 2 / 4 when legal
-      const int mt = atoi(e);
+    if (g_tune.mt) {                                 // tuning override: force 1 / 2 / 4 when legal
+      const int mt = g_tune.mt;
       if ((mt == 1 || mt == 2 || mt == 4) && 2 * mt * p.bnt <= 512 && p.bn * mt <= 256 && c.N >= mt * p.bn && stages_of(mt) >= 2) p.mt = mt;
     }
     p.tiles_n = ceil_div(c.N, p.bn * p.mt);
@@ -1664,8 +1335,10 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     if (st > MAX_STAGES) st = MAX_STAGES;
     if (st < 1) st = 1;
     p.stages = st;
-    const int grid_p = p.items < num_sms ? p.items : num_sms;
-    const bool can_stats = p.tma_store == 1 && !getenv("DCV_TC_NO_FUSED_STATS");
+    // sm_reserve > 0 (data-parallel runs, while a gradient bucket is in flight): leave a few SMs to NCCL's CTAs
+    const int sms_avail = num_sms - g_tune.sm_reserve > 8 ? num_sms - g_tune.sm_reserve : 8;
+    const int grid_p = p.items < sms_avail ? p.items : sms_avail;
+    const bool can_stats = p.tma_store == 1 && !g_tune.no_fused_stats;
     if (slots_out) { *slots_out = can_stats ? 4 * grid_p : 0; return 0; }
     DCV_REQUIRE(!stats || can_stats, "conv_tc: fused statistics need the TMA-store epilogue (output channels %% 64 == 0)");
     p.stats = stats; p.npad = npad;
@@ -1704,51 +1377,7 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     return check_launch("conv_tc_pers");
   }
 
-  // ---- non-persistent kernels (DCV_TC_NOPERSIST=1: kept for A/B timing)
-  if (slots_out) return 0;
-  DCV_REQUIRE(!stats, "conv_tc: fused statistics need the persistent kernel");
-  p.stats = nullptr; p.npad = npad;
-  rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz);
-  if (rc) return rc;
-  if (g4) {
-    // grouped-tap variant for 16-channel (image-like) operands: 4 taps per stage
-    p.b_bytes = p.bnt * 128;
-    const int a_tap = p.mt * 128 * 32;
-    const int stage_b = TAPG * a_tap + p.b_bytes;
-    int cps = 512 / p.tmem_cols; if (cps > 4) cps = 4; if (cps < 1) cps = 1;
-    const int64_t ctas = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n * (npad / p.bnt) * phases;
-    const int need = (int)((ctas + 147) / 148);
-    if (cps > need) cps = need < 1 ? 1 : need;
-    int st = ((216 * 1024) / cps - 2048) / stage_b;
-    const int ngroups = (ntaps0 + TAPG - 1) / TAPG;
-    if (st > MAX_STAGES) st = MAX_STAGES;
-    if (st > ngroups) st = ngroups;
-    if (st < 1) st = 1;
-    p.stages = st;
-    rc = make_weight_map(&mapB, wp, (int64_t)ntaps0 * c.Kc, npad, phases, 64, p.bnt, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
-    const int smem_g = st * stage_b + 1024;
-    static int smem_set_g = 0;
-    if (smem_g > smem_set_g) {
-      DCV_CUDA(cudaFuncSetAttribute(conv_tc_g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
-      smem_set_g = smem_g;
-    }
-    dim3 grid_g(p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n, npad / p.bnt, phases);
-    conv_tc_g4_kernel<<<grid_g, TC_THREADS, smem_g, s>>>(mapA, mapB, p, (__nv_bfloat16*)y);
-    return check_launch("conv_tc_g4");
-  }
-  rc = make_weight_map(&mapB, wp, Kph, npad, phases, p.cblk, p.bnt, swz);
-  if (rc) return rc;
-
-  const int smem = stages * (p.a_bytes + p.b_bytes) + 1024;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    DCV_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set = smem;
-  }
-  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_t * p.tiles_n, npad / p.bnt, phases);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mapA, mapB, p, (__nv_bfloat16*)y);
-  return check_launch("conv_tc");
+  return 0;
 }
 
 // ---- wgrad
@@ -1766,7 +1395,7 @@ int wgrad_tc_supported(const dcv_geom* g) {
 
 static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   p->g = *g;
-  { const char* e = getenv("DCV_TC_DBG"); p->dbg = e ? atoi(e) : 0; }
+  { const char* e = exp_env("DCV_TC_DBG"); p->dbg = e ? atoi(e) : 0; }
   const int taps = g->kt * g->kh * g->kw;
   p->cbA = block_width(g->Cl); p->nA = 128 / p->cbA; p->clchunks = g->Cl / p->cbA;
   p->blocksA_total = taps * p->clchunks;
@@ -1803,7 +1432,7 @@ static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   // the ring takes the whole shared memory, so exactly one CTA is resident per SM: aim for ONE wave of <= 148 CTAs
   // (a second wave only adds a second non-overlapped epilogue and doubles the partial sums that have to be reduced)
   int64_t sp = tiles >= 148 ? 1 : 148 / tiles;
-  if (const char* e = getenv("DCV_WGRAD_WAVES")) sp *= atoi(e) > 0 ? atoi(e) : 1;
+  if (g_tune.wgrad_waves > 0) sp *= g_tune.wgrad_waves;
   const int64_t maxs = (p->ptiles_total + 7) / 8;
   if (sp > maxs) sp = maxs;
   if (sp > 296) sp = 296;

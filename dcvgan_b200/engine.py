@@ -29,31 +29,88 @@ class Rng:
     mode 'cpu_parity' : the draw the reference would make on the CPU (torch.empty(shape).normal_() /
                         .bernoulli_()), in the reference's order, copied to the GPU - so that a run
                         seeded like the CPU oracle consumes bit-identical noise.
+    mode 'staged'     : the same CPU draws, but delivered through STATIC device buffers that are filled before the
+                        iteration starts (`stage()`), so that the iteration itself issues no host work and can be
+                        captured into / replayed from a CUDA graph: parity tests of the graph path
+                        (tests/test_timed_path_gpu.py).  The first iteration of a draw pattern records the request list.
     """
 
     def __init__(self, mode="device"):
-        assert mode in ("device", "cpu_parity")
+        assert mode in ("device", "cpu_parity", "staged")
         self.mode = mode
+        self.plan = []        # staged: [(kind, shape, device buffer)] in request order
+        self.cursor = 0
+        self.recording = True
+
+    # ---- the reference's CPU draws
+    @staticmethod
+    def _cpu_normal(shape):
+        return torch.empty(shape).normal_()
+
+    @staticmethod
+    def _cpu_noise(a):
+        # normal_() fills in memory order, so (N,C,H,W) and (N,C,1,H,W) draws are identical
+        return torch.empty((a[0], a[4], a[1], a[2], a[3])).normal_()
+
+    @staticmethod
+    def _cpu_dropout(n, c, p):
+        return torch.empty((n, c, 1, 1)).bernoulli_(1 - p).div_(1 - p).view(n, c).contiguous()
+
+    # ---- staged mode
+    def stage(self):
+        """draw every request of the recorded pattern on the CPU (reference order) into the static device buffers"""
+        assert self.mode == "staged"
+        self.cursor = 0
+        if not self.plan:
+            self.recording = True
+            return
+        self.recording = False
+        for kind, arg, buf in self.plan:
+            if kind == "normal":
+                buf.copy_(self._cpu_normal(arg))
+            elif kind == "noise":
+                ref = self._cpu_noise(arg).cuda()
+                ops.to_channels_last(ref, Act.from_dense(buf.view(arg)))
+            else:
+                buf.copy_(self._cpu_dropout(*arg))
+        torch.cuda.synchronize()
+
+    def _staged(self, kind, arg, make):
+        if self.recording:
+            buf = make()
+            self.plan.append((kind, arg, buf))
+            return buf
+        k, a, buf = self.plan[self.cursor]
+        assert (k, a) == (kind, arg), f"staged RNG: request {self.cursor} is {(kind, arg)}, recorded {(k, a)}"
+        self.cursor += 1
+        return buf
 
     def normal(self, shape):
         if self.mode == "cpu_parity":
-            return torch.empty(shape).normal_().cuda()
+            return self._cpu_normal(shape).cuda()
+        if self.mode == "staged":
+            return self._staged("normal", tuple(shape), lambda: self._cpu_normal(shape).cuda())
         return torch.empty(shape, device="cuda").normal_()
 
     def noise_for(self, a):
         """fp32 noise laid out like `a` (dense channels-last); drawn in the reference's (N,C[,T],H,W) order"""
-        if self.mode == "cpu_parity":
-            # normal_() fills in memory order, so (N,C,H,W) and (N,C,1,H,W) draws are identical
-            ref = torch.empty((a.n, a.c, a.t, a.h, a.w)).normal_().cuda()
-            out = Act.empty(a.n, a.t, a.h, a.w, a.c, torch.float32)
-            ops.to_channels_last(ref, out)
-            return out.base
+        if self.mode in ("cpu_parity", "staged"):
+            def make():
+                ref = self._cpu_noise(a.shape).cuda()
+                out = Act.empty(a.n, a.t, a.h, a.w, a.c, torch.float32)
+                ops.to_channels_last(ref, out)
+                return out.base
+            if self.mode == "staged":
+                return self._staged("noise", tuple(a.shape), make)
+            return make()
         return torch.empty(a.rows * a.c, device="cuda").normal_()
 
     def dropout_scale(self, n, c, p=0.5):
         """Dropout2d: one Bernoulli(1-p) per (sample, channel), scaled by 1/(1-p)  (generator.py:246-248)"""
         if self.mode == "cpu_parity":
-            return torch.empty((n, c, 1, 1)).bernoulli_(1 - p).div_(1 - p).view(n, c).cuda().contiguous()
+            return self._cpu_dropout(n, c, p).cuda()
+        if self.mode == "staged":
+            return self._staged("dropout", (n, c, p), lambda: self._cpu_dropout(n, c, p).cuda())
         return torch.empty((n, c), device="cuda").bernoulli_(1 - p).div_(1 - p)
 
 
@@ -150,9 +207,13 @@ class Block:
         # geometry over the zero-padded channel counts of both buffers (dcv_geom.wCl/wCs carry the real ones)
         cin_p, cout_p = x_used.cp, z.cp
         g = spec.geom(x.n, x.spatial, cin_p, cout_p)
+        ctx = {"g": g, "x": x_used if save else None, "a": out, "cin_p": cin_p, "cout_p": cout_p}
+        if self.bn is None and self.act in (ACT_NONE, ACT_LEAKY) and ops.img_conv_ok(spec, g, x_used, out):
+            ops.img_conv_fwd(spec, g, x_used, w, out, self.act, self.slope)       # Inconv: direct HBM-bound kernel
+            ctx["img"] = True
+            return ctx
         impl = ops.choose_conv_impl(g, spec.fwd_dir, x_used)
         wp = packed_weight(spec, g, spec.fwd_dir, impl, w)
-        ctx = {"g": g, "x": x_used if save else None, "a": out, "cin_p": cin_p, "cout_p": cout_p}
         if self.bn is None:
             if self._tap_unrolled(impl, x_used):
                 self._forward_tap_unrolled(x_used, out)
@@ -212,8 +273,11 @@ class Block:
         """da: gradient w.r.t. the block output (Act, may be a slice).  dx_out: Act receiving dL/dx or None."""
         spec, g = self.spec, ctx["g"]
         a = ctx["a"]
+        if ctx.get("img"):       # activation derivative, weight gradient and data gradient in one pass over (da, a)
+            dw, acc = sink.get(self.conv.weight) if need_dw else (None, False)
+            ops.img_conv_bwd(spec, g, da, a, ctx["x"], self.conv.weight, self.act, self.slope, dw, acc, dx_out)
+            return None
         if self.bn is not None:
-            assert ctx.get("training", True), "BatchNorm backward is only defined for training-mode statistics here"
             dz = ctx["z"].like()
             if need_dw:
                 dgam, acc = sink.get(self.bn.weight)
@@ -222,7 +286,7 @@ class Block:
                 dgam = dbet = None
                 acc = False
             ops.bn_act_bwd(da, a, ctx["z"], ctx["mean"], ctx["invstd"], self.bn.weight.detach(), self.bn.bias.detach(), ctx["drop"],
-                           self.act, self.slope, dz, dgam, dbet, acc)
+                           self.act, self.slope, dz, dgam, dbet, acc, batch_stats=ctx.get("training", True))
         elif self.act != ACT_NONE:
             dz = Act.empty(a.n, a.t, a.h, a.w, a.c, a.dtype)
             ops.act_bwd(da, a, self.act, self.slope, dz)

@@ -212,9 +212,15 @@ def _tc_ok(t):
 _FORCE_SIMT = bool(int(os.environ.get("DCV_FORCE_SIMT", "0")))   # debugging aid: bf16 storage without tcgen05
 
 
+STRICT_TC = False   # set by the fused trainer at production widths: a bf16 convolution that cannot run on tcgen05 is an error
+
+
 def choose_conv_impl(g, direction, x):
     if not _FORCE_SIMT and x.dtype == torch.bfloat16 and _tc_ok(x) and lib().dcv_conv_tc_supported(C.byref(g), direction):
         return IMPL_TC
+    if STRICT_TC and x.dtype == torch.bfloat16 and not _FORCE_SIMT:
+        raise _lib.DcvError(f"bf16 convolution {g.key()} dir {direction} (ptr % 16 = {x.ptr % 16}, ld {x.ld}) is not eligible for the "
+                            "tcgen05 kernel; refusing to fall back to the CUDA-core kernel silently")
     return IMPL_SIMT
 
 
@@ -356,6 +362,8 @@ def bn_finalize(partials, rows, eps, momentum, running_mean, running_var, num_ba
 def choose_wgrad_impl(g, xl, xs):
     if not _FORCE_SIMT and xl.dtype == torch.bfloat16 and _tc_ok(xl) and _tc_ok(xs) and lib().dcv_wgrad_tc_supported(C.byref(g)):
         return IMPL_TC
+    if STRICT_TC and xl.dtype == torch.bfloat16 and not _FORCE_SIMT:
+        raise _lib.DcvError(f"bf16 weight gradient {g.key()} is not eligible for the tcgen05 kernel; refusing to fall back silently")
     return IMPL_SIMT
 
 
@@ -371,6 +379,40 @@ def wgrad(spec, g, xl, xs, dw, accumulate=False, impl=None):
     assert dw.is_contiguous() and dw.dtype == torch.float32
     check(lib().dcv_wgrad(C.byref(g), impl, dcv_dtype(xl), lp, ldl, sp, lds, dw.data_ptr(), s_l, s_s, s_tap,
                           int(accumulate), ws.data_ptr(), nbytes, _stream()))
+
+
+# ------------------------------------------------------------------------------------ direct image-side convolution
+IMG_CONV = os.environ.get("DCV_NO_IMG_CONV", "0") != "1"
+
+
+def img_conv_ok(spec, g, x, y):
+    """the Inconv layer (Conv2d(C<=2, 64, 3, 1, 1), generator.py:171-176) in bf16: direct HBM-bound kernels instead of a
+    tensor-core tile over 16 zero-padded channels"""
+    return (IMG_CONV and not _FORCE_SIMT and spec.kind == "conv" and x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
+            and y.ptr % 16 == 0 and y.ld % 8 == 0 and (spec.cin == 1 or (x.ptr % 4 == 0 and x.ld % 2 == 0))
+            and bool(lib().dcv_img_conv_supported(C.byref(g))))
+
+
+def img_conv_fwd(spec, g, x, weight, y, act, slope):
+    if TRACE is not None:
+        TRACE.append(("img_conv_fwd", g.key(), 0, -1, x.ld, y.ld, x.c, y.c))
+    s_l, s_s, s_tap = spec.weight_strides()
+    w = weight.detach()
+    assert w.is_contiguous() and w.dtype == torch.float32
+    check(lib().dcv_img_conv_fwd(C.byref(g), x.ptr, x.ld, w.data_ptr(), s_l, s_s, s_tap, y.ptr, y.ld, act, slope, _stream()))
+
+
+def img_conv_bwd(spec, g, da, a, x, weight, act, slope, dw, accumulate, dx):
+    """dw (fp32, master layout, or None) and dx (Act or None) of the Inconv layer in one pass over (da, a)"""
+    if TRACE is not None:
+        TRACE.append(("img_conv_bwd", g.key(), 0, -1, da.ld, a.ld, da.c, x.c))
+    s_l, s_s, s_tap = spec.weight_strides()
+    w = weight.detach()
+    nbytes = lib().dcv_img_conv_bwd_workspace_bytes(C.byref(g))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=w.device)
+    check(lib().dcv_img_conv_bwd(C.byref(g), da.ptr, da.ld, a.ptr, a.ld, x.ptr, x.ld, w.data_ptr(), s_l, s_s, s_tap, act, slope,
+                                 _p(dw), int(accumulate), None if dx is None else dx.ptr, 0 if dx is None else dx.ld,
+                                 ws.data_ptr(), nbytes, _stream()))
 
 
 # ------------------------------------------------------------------------------------ BatchNorm & friends
@@ -409,7 +451,9 @@ def bn_act(z, mean, invstd, gamma, beta, drop, act, slope, out):
                            rows_per_n, act, slope, op, ldo, _stream()))
 
 
-def bn_act_bwd(da, a, z, mean, invstd, gamma, beta, drop, act, slope, dz, dgamma, dbeta, accumulate=False):
+def bn_act_bwd(da, a, z, mean, invstd, gamma, beta, drop, act, slope, dz, dgamma, dbeta, accumulate=False, batch_stats=True):
+    """batch_stats=False: the forward normalised with the running statistics (eval mode), so mean / invstd are constants
+    and dz = gamma * invstd * du without the two batch-statistic terms; dgamma / dbeta keep their formulas."""
     dap, ldda, rows, c = cl_view(da)
     ap, lda, _, _ = cl_view(a)
     zp, ldz, _, _ = cl_view(z)
@@ -423,6 +467,8 @@ def bn_act_bwd(da, a, z, mean, invstd, gamma, beta, drop, act, slope, dz, dgamma
                                       _p(gamma), _p(beta), _p(drop), rows_per_n, act, slope, partials.data_ptr(), _stream()))
     check(lib().dcv_bn_bwd_finalize(partials.data_ptr(), nblk, c, sums.data_ptr(), _p(dgamma), _p(dbeta),
                                     int(accumulate), _stream()))
+    if not batch_stats:
+        sums.zero_()
     check(lib().dcv_bn_act_bwd_apply(dt, dap, ldda, ap, lda, zp, ldz, rows, c, mean.data_ptr(), invstd.data_ptr(),
                                      _p(gamma), _p(beta), _p(drop), rows_per_n, act, slope, sums.data_ptr(), rows, dzp, lddz,
                                      _stream()))

@@ -31,14 +31,16 @@ from . import _lib, engine, ops
 from .generator import current_device
 from .ops import Act
 
-try:  # the reference's logger module when train.py of the reference drives us
-    from logger import MetricType  # type: ignore
-except Exception:  # pragma: no cover - standalone use
-    import enum
+import enum
 
-    class MetricType(enum.Enum):
-        Loss = 1
-        Float = 2
+
+class MetricType(enum.IntEnum):
+    """Same members and values as the reference's logger.MetricType (logger.py:15-23, an IntEnum): the reference's Logger
+    compares metric types by integer value, so this works whether or not its `logger` module is importable."""
+    Integer = 1
+    Float = 2
+    Loss = 3
+    Time = 4
 
 
 class _FlatNet:
@@ -60,6 +62,7 @@ class _FlatNet:
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad_of = {}
         self.numel = n
+        self.offs = offs
         for p, o in zip(self.params, offs):
             k = p.numel()
             self.flat_p[o:o + k].copy_(p.data.reshape(-1))
@@ -80,6 +83,23 @@ class _FlatNet:
         step0 = int(float(opt.state[self.params[0]]["step"]))
         self.step_state = torch.zeros(2, dtype=torch.int64, device=dev)
         self.step_state[0] = step0
+
+    def still_bound(self):
+        """False when a parameter no longer aliases its slice of flat_p (model.to('cpu').to(device), load_state_dict with
+        assign=True, ...): Adam and captured graphs would then update memory the forward passes no longer read."""
+        el = self.flat_p.element_size()
+        return all(p.data_ptr() == self.flat_p.data_ptr() + o * el and p.grad is self.grad_of.get(p)
+                   for p, o in zip(self.params, self.offs))
+
+    def rebind(self):
+        """adopt the parameters' current values and make them views of the flat buffers again"""
+        for p, o in zip(self.params, self.offs):
+            k = p.numel()
+            view = self.flat_p[o:o + k].view(p.shape)
+            if p.data_ptr() != view.data_ptr():
+                view.copy_(p.data.to(view.device))
+                p.data = view
+            p.grad = self.grad_of[p]
 
     def adam_step(self, grad_scale=1.0):
         """torch.optim.Adam.step() on the flat buffers (train.py:170-176 hyper-parameters)."""
@@ -268,10 +288,24 @@ class Trainer(object):
             self._pack_group = None
         self.world = dp_world()
         self.dtype = ops.torch_dtype(self.models["ggen"].precision)
+        # production widths (every channel count a multiple of 16): the bf16 path must run on tcgen05 end to end - a layer
+        # that would drop to the CUDA-core kernels raises instead (ops.STRICT_TC).  Narrow test widths keep the fallback.
+        widths = [self.models["ggen"].ngf, self.models["cgen"].ngf] + [self.models[n].ndf for n in names[2:]]
+        self._strict_tc = self.dtype == torch.bfloat16 and all(w % 16 == 0 for w in widths)
         if self.world > 1:
             dp_sync_params(self._flat.values())
             if "seed" in self.configs:
                 dp_seed(self.configs["seed"])
+
+    def _check_bound(self):
+        """Parameters must still alias the flat buffers (a hook may have moved a model to the CPU and back, as the
+        reference's evaluate() does): re-adopt them and drop the captured graphs and packed weights if not."""
+        stale = [f for f in self._flat.values() if not f.still_bound()]
+        if stale:
+            for f in stale:
+                f.rebind()
+            self._graphs.clear()
+            self._wcache.clear()
 
     def _allreduce(self, names):
         dp_allreduce_grads([self._flat[n] for n in names])
@@ -382,9 +416,10 @@ class Trainer(object):
         address) is captured once per update pattern into a CUDA graph and replayed; the frame index t_rand and
         the Adam step counters live in device memory so nothing has to be re-recorded."""
         self._prepare()
+        self._check_bound()
         if t_rand is None:
             t_rand = np.random.randint(self.models["ggen"].video_length)                        # trainer.py:279
-        if self.use_cuda_graph and engine.rng().mode == "device":
+        if self.use_cuda_graph and engine.rng().mode in ("device", "staged"):
             return self._graph_step(xc_real, xg_real, int(t_rand))
         return self._eager_step(xc_real, xg_real, t_rand)
 
@@ -398,12 +433,17 @@ class Trainer(object):
             else:
                 xc_real = xc_real.to(self.device, non_blocking=True)
                 xg_real = xg_real.to(self.device, non_blocking=True)
-        engine.WCACHE = self._wcache          # packed-weight cache owned by this trainer (keys are ids of its parameters)
+        # packed-weight cache owned by this trainer (keys are ids of its parameters); it only lives WITHIN one iteration
+        # (D: real + fake passes, G: forward + backward) - weights may change between iterations without the cache
+        # knowing (graph replays, load_state_dict, a hook that edits parameters), so every iteration starts empty
+        self._wcache.clear()
+        engine.WCACHE = self._wcache
         engine.PACK_GROUP = self._pack_group  # a miss re-packs every logged weight of the same network in one launch
         engine.PACK_LOG = self._pack_log
         if self._zero_pool is not None:
             self._zero_pool.begin_step()
         ops.ZERO_POOL = self._zero_pool       # zero-padded scratch buffers reused across iterations (ops.ZeroPool)
+        ops.STRICT_TC = self._strict_tc
         try:
             return self._train_step(xc_real, xg_real, t_rand)
         finally:
@@ -411,6 +451,7 @@ class Trainer(object):
             engine.PACK_GROUP = None
             engine.PACK_LOG = None
             ops.ZERO_POOL = None
+            ops.STRICT_TC = False
 
     GRAPH_WARMUP = 2   # eager iterations per update pattern before capture (lazy module loads, smem opt-in, NCCL setup)
 
@@ -426,8 +467,8 @@ class Trainer(object):
         if slot[3] is None:   # static inputs of this graph: the real batch and the frame index
             slot[3] = (torch.empty(xc_real.shape, dtype=torch.float32, device=self.device),
                        torch.empty(xg_real.shape, dtype=torch.float32, device=self.device),
-                       torch.zeros(1, dtype=torch.int32, device=self.device), torch.zeros(1, dtype=torch.int32).pin_memory())
-        gxc, gxg, t_dev, t_host = slot[3]
+                       torch.zeros(1, dtype=torch.int32, device=self.device))
+        gxc, gxg, t_dev = slot[3]
         staged = self._take_prefetched(xc_real, xg_real)
         if staged is not None:            # device-to-device from the staging slot (the PCIe copy already happened)
             gxc.copy_(staged["xc"], non_blocking=True)
@@ -437,13 +478,11 @@ class Trainer(object):
         else:
             gxc.copy_(xc_real, non_blocking=True)
             gxg.copy_(xg_real, non_blocking=True)
-        t_host[0] = t_rand
-        t_dev.copy_(t_host, non_blocking=True)
+        t_dev.fill_(t_rand)     # the value travels as a kernel argument, ordered on the stream (no reused pinned scalar)
         if slot[1] is None:
             # Capture.  The generators' train/eval flags change inside the step (trainer.py:338-339); restore them so the
             # recorded pattern matches `key`, then let the first replay perform the iteration.
             modes = (ggen.training, cgen.training)
-            self._wcache.clear()
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             l0 = _lib.lib().dcv_launch_count()
@@ -456,6 +495,9 @@ class Trainer(object):
             slot[1], slot[2] = graph, losses
         slot[1].replay()
         self.replayed_launches += slot[4]
+        # The replay ran the Adam kernels on the device: every packed bf16 weight the HOST-side cache still holds (left
+        # by an eager warm-up iteration of another graph key) is stale now and must not be reused by a later eager step.
+        self._wcache.clear()
         ggen.train()                             # host-side flags the replay cannot set (trainer.py:338-339)
         cgen.train()
         return slot[2].clone()

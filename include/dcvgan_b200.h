@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DCV_ABI_VERSION 3
+#define DCV_ABI_VERSION 4
 
 enum { DCV_F32 = 0, DCV_BF16 = 1 };
 /* activation selectors (generator.py:63,76,78,175,206,243,276; discriminator.py:82-99) */
@@ -74,6 +74,11 @@ const char* dcv_last_error(void);
 int dcv_device_ok(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
 long long dcv_launch_count(void);
+/* Result-preserving tuning switches of the tcgen05 kernels (process-wide; never read from the environment):
+ * "nohalo", "mt" (0 = automatic, 1/2/4 forced M tiles per work item), "no_tma_store", "no_narrow_tma_store",
+ * "wgrad_waves", "no_gemv", "no_tapgroup", "no_fused_stats", "sm_reserve" (SMs the persistent kernels leave free,
+ * for a collective running beside them).  The parity tests flip them to cover every kernel path. */
+int dcv_set_tuning(const char* key, int value);
 
 /* ---- weight packing -------------------------------------------------------------------------
  * Re-lays a PyTorch fp32 master weight for one direction of a layer.  `w` is addressed as
@@ -189,6 +194,20 @@ int dcv_act_bwd(int dtype, const void* da, int64_t ldda, const void* a, int64_t 
  * and applies the activation.  2-D only (T == 1). */
 int dcv_col2im_act(int dtype, const void* P, int64_t ldp, int N, int Ih, int Iw, int Cout, int KH, int KW, int stride, int pad,
                    int act, float slope, void* y, int64_t ldy, int Oh, int Ow, void* stream);
+/* Direct HBM-bound kernels for the image-side 3x3 convolution of the colour generator (generator.py:158-176, `Inconv`:
+ * Conv2d(C, 64, 3, 1, 1, bias=False) + LeakyReLU(0.01)) with C = 1 or 2 real input channels, bf16 activations, fp32 MASTER
+ * weight addressed like dcv_pack_weight (no packed copy).  dcv_img_conv_supported: 1 if the geometry qualifies.
+ * dcv_img_conv_fwd:  y = act(conv(x, w)).
+ * dcv_img_conv_bwd:  one pass over da (gradient w.r.t. the activated output) and a (the activated output): applies the
+ *   activation derivative (NONE / LEAKY), writes the weight gradient to dw (accumulate: +=; dw == NULL: skipped) and the
+ *   data gradient to dx (NULL: skipped).  ws: dcv_img_conv_bwd_workspace_bytes(g) bytes of scratch. */
+int dcv_img_conv_supported(const dcv_geom* g);
+int64_t dcv_img_conv_bwd_workspace_bytes(const dcv_geom* g);
+int dcv_img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
+                     void* y, int64_t ldy, int act, float slope, void* stream);
+int dcv_img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x, int64_t ldx,
+                     const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, int act, float slope, float* dw, int accumulate,
+                     void* dx, int64_t lddx, void* ws, int64_t ws_bytes, void* stream);
 /* w-tap folding for the image-like stem inputs of the discriminators (discriminator.py:79-90,180-193: conv_g on the
  * geometry channels, conv_c on the colour channels, kernel 4, stride 2, pad 1 along w):
  *   out[line][ow][k*(cg+cc) + c] = [xg | xc][line][ow*sw - pw + k][c]  (+ sigma*noise, the Noise layer), 0 outside the row

@@ -126,6 +126,11 @@ CASES = {
     # surreal-segm-like: 25-channel softmax geometry, adversarial loss, Noise everywhere incl. gdis
     "segm_adv_noise": (base_cfg("segmentation", 25, "adversarial-loss", idis={"use_noise": True}, vdis={"use_noise": True},
                                 gdis={"use_noise": True}), 1),
+    # trainer.py:126-127 quirk: log_samples() leaves both generators in eval mode, so the D-phase fakes of the NEXT iteration
+    # are generated with running-statistics BatchNorm and without Dropout (and loss_dis.backward() runs through eval-mode
+    # generators).  Here log_samples is reduced to exactly that side effect (ggen.eval(); cgen.eval(), no RNG draw) and fires
+    # before iteration 1 and after iteration 2 (log_samples_interval 2), so iterations 1 and 3 see eval-mode fakes.
+    "depth_hinge_evalquirk": (base_cfg("depth", 1, "hinge-loss", log_samples_interval=2, eval_quirk=True, gdis={"enabled": False}), 4),
 }
 
 
@@ -171,6 +176,11 @@ def run_case(name, cfg, iters, ref):
     run_cfg = dict(cfg, config_path=str(cfg_path))
     logger = CaptureLogger(tmp)
     tr = trainer.Trainer(ListLoader(batches), logger, models, optimizers, loss, run_cfg)
+    if cfg.get("eval_quirk"):
+        def _log_samples(ggen_, cgen_, iteration):       # trainer.py:126-127, nothing else of log_samples
+            ggen_.eval()
+            cgen_.eval()
+        tr.log_samples = _log_samples
     step_seed = cfg["seed"] + 100
     torch.manual_seed(step_seed)
     np.random.seed(step_seed)
@@ -202,5 +212,8 @@ def run_case(name, cfg, iters, ref):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     ref = import_reference()
+    only = sys.argv[1:]
     for name, (cfg, iters) in CASES.items():
+        if only and name not in only:
+            continue
         run_case(name, cfg, iters, ref)

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-CASES = ["flow_hinge_noise", "depth_adv_nogdis", "segm_adv_noise"]
+CASES = ["flow_hinge_noise", "depth_adv_nogdis", "segm_adv_noise", "depth_hinge_evalquirk"]
 LOG2 = 0.6931471805599453
 
 

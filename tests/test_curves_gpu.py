@@ -1,15 +1,28 @@
-"""bf16 loss-curve gate of the north star: generator and discriminator loss curves over 200 steps at bf16 stay within
-a stated tolerance of the fp32 curves (same seeds, same host-generated noise, same synthetic batches).
+"""bf16 loss-curve gate of the north star: generator and discriminator loss curves over 200 steps at bf16 against the
+REFERENCE's curves (tests/golden/curves_flow_hinge.json, recorded by oracle/make_curves.py from the unmodified reference
+modules + Trainer.train() on CPU) for several seeds, with identical initial weights, batches and host-generated noise
+(RNG mode 'cpu_parity').
 
-The fp32 path is itself gated against the reference (test_nets_gpu.py: golden runs, losses <= 1e-3, gradient cosine
->= 0.999), so it stands in for the reference over the 200 steps; a shorter prefix is also checked directly against the
-CPU oracle.  GAN trajectories are chaotic point-wise: an fp32 run whose initial weights are perturbed by 1e-6
-(relative) drifts from the unperturbed fp32 run by up to ~0.46 in the running mean of loss_vdis within 200 steps
-(measured, profiles/r1_curves.md).  Stated tolerance, on running means over 20 iterations:
-  * first 30 windows (before the trajectories decorrelate): |bf16 - fp32| <= max(5 % of the fp32 value, 0.05);
-  * all 181 windows: |bf16 - fp32| <= max(2 x the largest drift among three perturbed fp32 control runs (initial
-    weights scaled by 1+1e-6, 1+1e-3, 1-1e-3), 0.05) per curve.
+GAN trajectories are chaotic point-wise: two fp32 runs whose initial weights differ by 1e-6 (relative) drift apart by
+up to ~0.46 in the 20-iteration running mean of loss_vdis within 200 steps (profiles/r1_curves.md).  A per-run band
+therefore has to be either vacuous or violated by the reference itself, so the gate is statistical, over S seeds, on
+the running means m(w) (window 20) of every loss curve:
+
+  1. before the trajectories decorrelate (windows starting at iterations 0..29): every seed on its own,
+     |m_bf16 - m_ref| <= max(5 % of |m_ref|, 0.05);
+  2. over all 181 windows: the SEED-MEAN deviation is unbiased -
+     |mean_s (m_bf16 - m_ref)| <= max(10 % of |mean_s m_ref|, 0.05, 3 * standard error of the per-seed deviations)
+     (the last term is the statistical one: with S seeds a bias-free deviation stays within 3 SE);
+  3. the run-to-run spread of bf16 around the reference is not larger than the reference's OWN spread between seeds:
+     rms_s(m_bf16 - m_ref) <= max(0.05, 1.0 * std_s(m_ref)) window by window for >= 90 % of the windows, and the curve-level
+     average of that ratio is below 1.
+
+The fp32 CUDA path is additionally checked against the same reference curves with the same gate (it must pass 1. with a
+ten times tighter band), and its first iterations against float rounding.
 """
+import json
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
@@ -17,12 +30,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import dcvgan_oracle as orc  # noqa: E402
-from test_nets_gpu import _Logger, _mods, build_models, small_cfg  # noqa: E402
+from test_nets_gpu import _Logger, _mods, build_models  # noqa: E402
 
-STEPS, WINDOW = 200, 20
+GOLD = Path(__file__).resolve().parent / "golden" / "curves_flow_hinge.json"
+WINDOW = 20
+NAMES = ("loss_idis", "loss_vdis", "loss_gdis", "loss_gen")
 
 
-def _run(cfg, init, precision, steps, tmp_path):
+def _run(cfg, init, precision, steps, seed, tmp_path):
     dcv, _, _, loss_mod, trainer_mod, _, engine = _mods()
     models = build_models(cfg, init, precision)
     engine.set_rng_mode("cpu_parity")
@@ -31,13 +46,14 @@ def _run(cfg, init, precision, steps, tmp_path):
     L = loss_mod.AdversarialLoss() if cfg["loss"] == "adversarial-loss" else loss_mod.HingeLoss()
     trainer_mod.Trainer.save_classobj = lambda self: None
     tr = trainer_mod.Trainer(None, _Logger(tmp_path), models, opts, L, dict(cfg, config_path=""))
-    torch.manual_seed(123)
-    np.random.seed(123)
+    pool = [tuple(t.cuda() for t in orc.synthetic_batch(cfg, cfg["batchsize"], 5000 + i)) for i in range(8)]
+    torch.manual_seed(seed)
+    np.random.seed(seed)
     out = []
     for it in range(steps):
-        xc, xg = orc.synthetic_batch(cfg, cfg["batchsize"], 5000 + it % 8)
+        xc, xg = pool[it % 8]
         tr.iteration += 1
-        out.append(tr.train_step(xc.cuda(), xg.cuda()))
+        out.append(tr.train_step(xc, xg))
     return torch.stack(out).cpu().numpy()
 
 
@@ -46,52 +62,59 @@ def _running_mean(a, w):
     return (c[w:] - c[:-w]) / w
 
 
-def test_bf16_loss_curves_track_fp32(tmp_path):
-    cfg = small_cfg("optical-flow", 2, "hinge-loss", noise=True, ngf=16, ndf=16)
-    cfg["batchsize"] = 4
-    init = orc.init_all(cfg, 9)
-    ref = _run(cfg, init, "fp32", STEPS, tmp_path)
-    got = _run(cfg, init, "bf16", STEPS, tmp_path)
-    assert np.isfinite(ref).all() and np.isfinite(got).all()
-    mr, mg = _running_mean(ref, WINDOW), _running_mean(got, WINDOW)
-    dev = np.abs(mg - mr)
-    names = ("loss_idis", "loss_vdis", "loss_gdis", "loss_gen")
-    print("max |mean20(bf16) - mean20(fp32)| per curve:", {n: float(dev[:, i].max()) for i, n in enumerate(names)})
-    for lo, hi in ((0, 30), (30, 80), (80, STEPS - WINDOW + 1)):
-        print(f"  window starts {lo}..{hi}: max dev", [float(f"{x:.3f}") for x in dev[lo:hi].max(axis=0)], "fp32 mean", [float(f"{x:.3f}") for x in mr[lo:hi].mean(axis=0)])
-    # controls: fp32 against fp32 with the initial weights perturbed - by 1e-6 relative (the chaotic spread of the GAN
-    # itself) and by +-1e-3 relative (a perturbation of the size bf16 storage applies, half an ulp = 2e-3); the envelope
-    # of their drifts is what any bf16 run has to be compared with once the trajectories have decorrelated
-    cdevs = []
-    for eps in (1e-6, 1e-3, -1e-3):
-        init2 = {k: {a: (b * (1 + eps) if b.dtype == torch.float32 else b.clone()) for a, b in v.items()} for k, v in init.items()}
-        cdevs.append(np.abs(_running_mean(_run(cfg, init2, "fp32", STEPS, tmp_path), WINDOW) - mr))
-        print(f"control (fp32 vs {eps:+.0e}-perturbed fp32) max dev per curve:", [float(f"{x:.3f}") for x in cdevs[-1].max(axis=0)])
-    cdev = np.maximum.reduce(cdevs)
-    print("final means fp32:", mr[-1].tolist(), "bf16:", mg[-1].tolist())
-    print("first-step losses fp32:", ref[0].tolist(), "bf16:", got[0].tolist())
-    early_tol = np.maximum(0.05 * np.abs(mr[:30]), 0.05)
-    assert (dev[:30] <= early_tol).all(), {n: float((dev[:30, i] / early_tol[:, i]).max()) for i, n in enumerate(names)}
-    full_tol = np.maximum(2.0 * cdev.max(axis=0), 0.05)
-    assert (dev.max(axis=0) <= full_tol).all(), dict(zip(names, (dev.max(axis=0) / full_tol).tolist()))
+def _curves(precision, tmp_path):
+    gold = json.loads(GOLD.read_text())
+    cfg, steps = gold["cfg"], gold["steps"]
+    ref, got = [], []
+    for s, curve in sorted(gold["seeds"].items(), key=lambda kv: int(kv[0])):
+        s = int(s)
+        init = orc.init_all(cfg, 100 + s)
+        ref.append(np.array(curve))
+        got.append(_run(cfg, init, precision, steps, 1000 + s, tmp_path))
+        assert np.isfinite(got[-1]).all()
+    return np.stack(ref), np.stack(got)          # (S, steps, 4)
 
 
-def test_fp32_curve_prefix_matches_oracle(tmp_path):
-    """12 consecutive iterations of the fp32 CUDA path against the CPU oracle: float-rounding agreement on the first
-    iteration (measured 3.6e-7), then the slow chaotic drift of two fp32 implementations (measured <= 0.05)."""
-    cfg = small_cfg("depth", 1, "adversarial-loss", noise=False, ngf=8, ndf=8, gdis=False)
-    init = orc.init_all(cfg, 10)
-    o = orc.OracleTrainer(cfg, {k: {a: b.clone() for a, b in v.items()} for k, v in init.items()})
-    torch.manual_seed(123)
-    np.random.seed(123)
-    ref = []
-    for it in range(12):
-        xc, xg = orc.synthetic_batch(cfg, cfg["batchsize"], 5000 + it % 8)
-        r = o.step(xc, xg)
-        ref.append([r["loss_idis"], r["loss_vdis"], 0.0, r["loss_gen"]])
-    got = _run(cfg, init, "fp32", 12, tmp_path)
-    dev = np.abs(got - np.array(ref)).max(axis=1)
-    print("per-iteration max abs loss deviation:", [float(f"{d:.2e}") for d in dev])
-    # rounding differences are amplified by the adversarial dynamics (Adam's first steps move every weight by
-    # ~lr*sign(grad)); the deviation must start at float rounding level and stay small over the prefix
-    assert dev[0] < 1e-5 and dev[1] < 2e-3 and dev.max() < 0.1
+def _gate(ref, got, early_rel, early_abs, tag):
+    S = ref.shape[0]
+    mr = np.stack([_running_mean(r, WINDOW) for r in ref])       # (S, W, 4)
+    mg = np.stack([_running_mean(g, WINDOW) for g in got])
+    d = mg - mr
+    # 1. per seed, before decorrelation
+    tol1 = np.maximum(early_rel * np.abs(mr[:, :30]), early_abs)
+    r1 = np.abs(d[:, :30]) / tol1
+    print(f"[{tag}] early windows (0..29), worst |dev| / tolerance per curve:", dict(zip(NAMES, r1.max(axis=(0, 1)).round(3).tolist())))
+    # 2. unbiased seed mean over all windows
+    mean_d, mean_r = d.mean(axis=0), mr.mean(axis=0)
+    se = d.std(axis=0, ddof=1) / np.sqrt(S)
+    tol2 = np.maximum(np.maximum(0.10 * np.abs(mean_r), 0.05), 3.0 * se)
+    r2 = np.abs(mean_d) / tol2
+    print(f"[{tag}] seed-mean deviation, worst |mean dev| / tolerance per curve:", dict(zip(NAMES, r2.max(axis=0).round(3).tolist())),
+          "| worst |mean dev|:", dict(zip(NAMES, np.abs(mean_d).max(axis=0).round(3).tolist())))
+    # 3. spread of the deviation against the reference's own seed-to-seed spread
+    rms = np.sqrt((d ** 2).mean(axis=0))
+    spread = np.maximum(mr.std(axis=0, ddof=1), 0.05)
+    r3 = rms / spread
+    frac_ok = (r3 <= 1.0).mean(axis=0)
+    print(f"[{tag}] rms deviation / reference seed spread: mean per curve", dict(zip(NAMES, r3.mean(axis=0).round(3).tolist())),
+          "| share of windows <= 1:", dict(zip(NAMES, frac_ok.round(3).tolist())))
+    assert (r1 <= 1.0).all(), (tag, "early windows", dict(zip(NAMES, r1.max(axis=(0, 1)).tolist())))
+    assert (r2 <= 1.0).all(), (tag, "seed-mean bias", dict(zip(NAMES, r2.max(axis=0).tolist())))
+    assert (frac_ok >= 0.9).all() and (r3.mean(axis=0) < 1.0).all(), (tag, "spread", frac_ok.tolist(), r3.mean(axis=0).tolist())
+    return d
+
+
+def test_bf16_loss_curves_match_reference_statistically(tmp_path):
+    ref, got = _curves("bf16", tmp_path)
+    print("first-iteration losses, seed 0: reference", ref[0, 0].tolist(), "bf16", got[0, 0].tolist())
+    _gate(ref, got, 0.05, 0.05, "bf16")
+
+
+def test_fp32_loss_curves_match_reference(tmp_path):
+    """fp32 CUDA path against the reference curves: float-rounding agreement on the first iterations, a ten times tighter
+    early band than bf16, and the same statistical gate afterwards."""
+    ref, got = _curves("fp32", tmp_path)
+    dev = np.abs(got - ref).max(axis=2)                          # (S, steps)
+    print("fp32 per-iteration max abs loss deviation, first 6 iterations per seed:", [[float(f"{x:.1e}") for x in dev[s, :6]] for s in range(dev.shape[0])])
+    assert (dev[:, 0] < 1e-5).all() and (dev[:, 1] < 2e-3).all()
+    _gate(ref, got, 0.005, 0.005, "fp32")

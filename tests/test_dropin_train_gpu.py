@@ -1,0 +1,203 @@
+"""End-to-end drop-in run: the reference's UNMODIFIED `train.py` main() (train.py:48-183) is executed with `dropin/` first
+on sys.path, so that its `from generator import ...`, `from discriminator import ...`, `from loss import ...` and
+`from trainer import Trainer` resolve to dcvgan_b200, while `util`, `logger`, `dataset` stay the reference's own modules
+(staged under baseline/_ref/src by __graft_entry__.build(); missing third-party packages are stubbed as in SURVEY.md
+Appendix A).  Only the dataset is replaced (synthetic in-memory clips, pinned, no RNG consumption).
+
+Covers what the per-step tests do not: model construction + util.init_weights through the reference's code, the
+optimizers built by the caller, `Trainer.train()` with its update gating over several iterations (num_gen_update 2),
+`prefetch()` / `_take_prefetched()` of pinned batches, `_flush_losses()` through the reference's Logger, `save_params()`
+snapshot files, and the eval-mode quirk after `log_samples()` (trainer.py:126-127).  The logged losses are compared
+with the CPU oracle run from the same initial weights, seeds and batches.
+"""
+import importlib
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+from oracle import dcvgan_oracle as orc  # noqa: E402
+
+REF_MODULES = ("util", "generator", "discriminator", "loss", "trainer", "logger", "dataset", "dataio", "train", "preprocess",
+               "preprocess.isogd", "preprocess.mug", "preprocess.surreal", "preprocess.context")
+
+
+class SyntheticDataset:
+    name = "synthetic"
+
+    def __init__(self, *a, **k):
+        self.root_path = Path("/tmp")
+
+    def __len__(self):
+        return 0
+
+
+class SyntheticLoader:
+    """stands in for dataset.VideoDataLoader (dataset.py:16-24): pinned in-memory batches, no RNG consumption"""
+    BATCHES = []
+
+    def __init__(self, dataset, batch_size=1, num_workers=0, **kw):
+        self.dataset, self.batch_size, self.num_workers = dataset, batch_size, num_workers
+
+    def __iter__(self):
+        return iter(self.BATCHES)
+
+
+@pytest.mark.parametrize("precision,ltol", [("fp32", 2e-3), ("bf16", 6e-2)])
+def test_reference_train_py_runs_on_the_dropin_modules(precision, ltol, tmp_path, monkeypatch):
+    from tools import ref_harness as rh
+    src = rh.reference_src()
+    if src is None or not (src / "train.py").exists() or not (src / "preprocess").exists():
+        pytest.skip("reference sources are not staged under baseline/_ref/src")
+    import dcvgan_b200
+    from dcvgan_b200 import engine
+    dcvgan_b200.require_device()
+    dcvgan_b200.set_precision(precision)
+    engine.set_rng_mode("cpu_parity")
+
+    iters, B = 6, 2
+    o_ = {"lr": 0.0002, "decay": 0.00001}
+    cfg = {"seed": 3, "log_dir": str(tmp_path / "log"), "experiment_name": "dropin", "tensorboard_dir": str(tmp_path / "tb"),
+           "geometric_info": {"name": "depth", "channel": 1}, "log_interval": 2, "log_samples_interval": 4, "snapshot_interval": 3,
+           "evaluation_interval": 10 ** 9, "loss": "adversarial-loss",
+           "dataset": {"name": "mug", "path": str(tmp_path / "data"), "n_workers": 0, "number_limit": -1},
+           "video_length": 16, "image_size": 64, "batchsize": B, "n_epochs": 1, "num_gen_update": 2, "num_dis_update": 1,
+           "ggen": {"dim_z_content": 40, "dim_z_motion": 10, "ngf": 16, "optimizer": o_},
+           "cgen": {"dim_z_color": 10, "ngf": 16, "optimizer": o_},
+           "idis": {"use_noise": True, "noise_sigma": 0.2, "ndf": 16, "optimizer": o_},
+           "vdis": {"use_noise": False, "noise_sigma": 0.2, "ndf": 16, "optimizer": o_},
+           "gdis": {"use_noise": False, "noise_sigma": 0.2, "ndf": 16, "optimizer": o_},
+           "evaluation": {"batchsize": 2, "num_samples": 0, "metrics": []}}
+    cfg_path = tmp_path / "cfg.yml"
+    cfg_path.write_text(yaml.safe_dump(cfg))
+    batches = []
+    for i in range(iters):
+        xc, xg = orc.synthetic_batch(cfg, B, 7000 + i)
+        batches.append({"color": xc.pin_memory(), "depth": xg.pin_memory()})
+    SyntheticLoader.BATCHES = batches
+
+    # ---- import the reference's train.py with dropin/ shadowing generator / discriminator / loss / trainer
+    saved_modules = {n: sys.modules.pop(n) for n in REF_MODULES if n in sys.modules}
+    saved_path = list(sys.path)
+    rh.import_reference.__globals__["_REF"] = None
+    try:
+        for n in ["skvideo", "skvideo.io", "evan", "colorlog", "tensorboardX", "matplotlib", "matplotlib.pyplot"]:
+            sys.modules.setdefault(n, types.ModuleType(n))
+        sys.modules["skvideo"].io = sys.modules["skvideo.io"]
+        import logging
+
+        class _SW:
+            def __init__(self, *a, **k):
+                pass
+
+            def __getattr__(self, name):
+                return lambda *a, **k: None
+        sys.modules["tensorboardX"].SummaryWriter = _SW
+        sys.modules["colorlog"].ColoredFormatter = lambda fmt, datefmt=None, **kw: logging.Formatter(fmt.replace("%(log_color)s", ""), datefmt)
+        sys.path[:0] = [str(ROOT / "dropin"), str(src)]
+        import util  # noqa: F401  reference (import-cycle: util first)
+        import dataset as ref_dataset
+        ref_dataset.VideoDataset = SyntheticDataset
+        ref_dataset.VideoDataLoader = SyntheticLoader
+        import logger as ref_logger
+        train = importlib.import_module("train")
+        assert train.Trainer.__module__ == "dcvgan_b200.trainer" and train.GeometricVideoGenerator.__module__ == "dcvgan_b200.generator"
+        assert train.ImageDiscriminator.__module__ == "dcvgan_b200.discriminator" and train.HingeLoss.__module__ == "dcvgan_b200.loss"
+        assert Path(train.__file__).resolve() == (src / "train.py").resolve() and Path(util.__file__).resolve().parent == src.resolve()
+
+        logged = []
+        real_update = ref_logger.Logger.update
+
+        def update(self, name, value):
+            logged.append((name, value))
+            return real_update(self, name, value)
+        monkeypatch.setattr(ref_logger.Logger, "update", update)
+
+        # snapshot the initial state and fix the seed right where training starts, so that the oracle can replay the run
+        from dcvgan_b200 import trainer as my_trainer
+        state = {}
+        real_train = my_trainer.Trainer.train
+        calls = {"prefetch": 0, "taken": 0, "flush": 0}
+
+        def train_wrapper(self):
+            state["init"] = {k: {a: b.detach().cpu().clone() for a, b in m.state_dict().items()} for k, m in self.models.items()}
+            state["trainer"] = self
+            torch.manual_seed(1234)
+            np.random.seed(1234)
+            return real_train(self)
+        monkeypatch.setattr(my_trainer.Trainer, "train", train_wrapper)
+        for name in ("prefetch", "_flush_losses"):
+            real = getattr(my_trainer.Trainer, name)
+
+            def counted(self, *a, _real=real, _key=name.strip("_").split("_")[0], **k):
+                calls[_key] += 1
+                return _real(self, *a, **k)
+            monkeypatch.setattr(my_trainer.Trainer, name, counted)
+        real_take = my_trainer.Trainer._take_prefetched
+
+        def take(self, *a, **k):
+            r = real_take(self, *a, **k)
+            calls["taken"] += r is not None
+            return r
+        monkeypatch.setattr(my_trainer.Trainer, "_take_prefetched", take)
+        monkeypatch.setattr(sys, "argv", ["train.py", "--config", str(cfg_path)])
+        train.main()
+        torch.cuda.synchronize()
+    finally:
+        sys.path[:] = saved_path
+        for n in REF_MODULES:
+            sys.modules.pop(n, None)
+        sys.modules.update(saved_modules)
+        rh.import_reference.__globals__["_REF"] = None
+        engine.set_rng_mode("cpu_parity")
+
+    tr = state["trainer"]
+    assert tr.iteration == iters and tr.epoch == 1
+    # ---- side effects of Trainer.train(): snapshots (trainer.py:78-86), config copy, pickled modules
+    mdir = Path(cfg["log_dir"]) / "dropin" / "models"
+    for name in ("ggen", "cgen", "idis", "vdis", "gdis"):
+        assert (mdir / f"{name}_model.pth").exists()
+        for it in (3, 6):
+            sd = torch.load(mdir / f"{name}_params_{it:05d}.pth")
+            assert list(sd) == list(tr.models[name].state_dict())
+    assert (Path(cfg["log_dir"]) / "dropin" / "config.yml").exists()
+    assert calls["prefetch"] == iters - 1 and calls["taken"] == iters - 1, calls   # every batch but the first crossed PCIe ahead of its step
+    assert calls["flush"] >= iters // cfg["log_interval"], calls
+
+    # ---- the same run on the CPU oracle
+    ocfg = dict(cfg)
+    ocfg["gdis"] = dict(cfg["gdis"], enabled=True)
+    o = orc.OracleTrainer(ocfg, state["init"])
+    torch.manual_seed(1234)
+    np.random.seed(1234)
+    o.gen_training = False                        # log_samples(ggen, cgen, 0) before the loop (trainer.py:268)
+    ref = []
+    for it in range(iters):
+        r = o.step(batches[it]["color"], batches[it]["depth"])
+        ref.append(r)
+        if (it + 1) % cfg["log_samples_interval"] == 0:
+            o.gen_training = False
+    got = [{} for _ in range(iters)]
+    cur = -1
+    order = []
+    for k, v in logged:
+        if k == "iteration":
+            cur = v - 1
+            order.append(v)
+        elif k.startswith("loss_"):
+            got[cur][k] = v
+    assert order == list(range(1, iters + 1)), order              # losses reach the logger in iteration order
+    worst = 0.0
+    for it in range(iters):
+        for k in ("loss_idis", "loss_vdis", "loss_gdis", "loss_gen"):
+            d = abs(got[it][k] - ref[it][k]) / max(1.0, abs(ref[it][k]))
+            worst = max(worst, d)
+            assert d <= ltol, (precision, it, k, got[it][k], ref[it][k])
+    print(f"train.py through dropin [{precision}]: {iters} iterations, worst relative loss deviation {worst:.2e}; calls {calls}")

@@ -131,28 +131,25 @@ def test_conv_tcgen05(case):
     _run_case(_ops(), case, torch.bfloat16, True, 1e-2)
 
 
-VARIANT_ENVS = [{"DCV_TC_NOHALO": "1"}, {"DCV_TC_MT": "1"}, {"DCV_TC_MT": "4"}, {"DCV_TC_NO_TMA_STORE": "1"},
-                {"DCV_TC_NOPERSIST": "1"}, {"DCV_WGRAD_WAVES": "2"}]
+VARIANTS = [{"nohalo": 1}, {"mt": 1}, {"mt": 4}, {"no_tma_store": 1}, {"wgrad_waves": 2}, {"no_tapgroup": 1}, {"sm_reserve": 16}]
 
 
-@pytest.mark.parametrize("env", VARIANT_ENVS, ids=["+".join(f"{k}={v}" for k, v in e.items()) for e in VARIANT_ENVS])
+@pytest.mark.parametrize("tune", VARIANTS, ids=["+".join(f"{k}={v}" for k, v in e.items()) for e in VARIANTS])
 @pytest.mark.parametrize("case", [TC_CASES[0], TC_CASES[5], TC_CASES[7], TC_CASES[9], TC_CASES[13], TC_CASES[14]],
                          ids=lambda c: c[0])
-def test_conv_tcgen05_kernel_variants(case, env):
-    """Every tuning switch of the tcgen05 path (row-halo sharing off, forced M-tile counts, direct-store epilogue,
-    the non-persistent kernels, two split waves in wgrad) must give the same numbers as the default configuration:
-    each variant is checked against PyTorch like the default path."""
-    import os
-    old = {k: os.environ.get(k) for k in env}
-    os.environ.update(env)
+def test_conv_tcgen05_kernel_variants(case, tune):
+    """Every tuning switch of the tcgen05 path (row-halo sharing off, forced M-tile counts, direct-store epilogue, two split
+    waves in wgrad, no grouped taps, a reduced persistent grid) must give the same numbers as the default configuration:
+    each variant is checked against PyTorch like the default path.  The switches are explicit library state
+    (dcv_set_tuning), not environment variables."""
+    ops = _ops()
+    for k, v in tune.items():
+        ops.check(ops.lib().dcv_set_tuning(k.encode(), v))
     try:
-        _run_case(_ops(), case, torch.bfloat16, True, 1e-2)
+        _run_case(ops, case, torch.bfloat16, True, 1e-2)
     finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
+        for k in tune:
+            ops.check(ops.lib().dcv_set_tuning(k.encode(), 0))
 
 
 PADDED_CASES = [
@@ -210,6 +207,50 @@ def test_conv_tcgen05_padded_channels(case):
     e_dw = rel_err(dw.cpu(), wg)
     print(f"{name}: fwd {e_fwd:.2e} dx {e_dx:.2e} dw {e_dw:.2e}  geom Cl={g.Cl} Cs={g.Cs} wCl={g.wCl} wCs={g.wCs}")
     assert e_fwd < 1e-2 and e_dx < 1e-2 and e_dw < 1e-2
+
+
+@pytest.mark.parametrize("cin,n,hw,slice_out", [(1, 3, (64, 64), True), (2, 2, (64, 64), False), (1, 2, (16, 32), False), (2, 5, (8, 64), True)])
+def test_img_conv_direct_kernels(cin, n, hw, slice_out):
+    """Inconv (generator.py:171-176: Conv2d(C, 64, 3, 1, 1) + LeakyReLU(0.01)) through the direct HBM-bound kernels:
+    forward, and the one-pass backward (activation derivative + weight gradient + data gradient) against PyTorch fp32 on
+    bf16-rounded operands.  slice_out: the output / its gradient live in the upper channel half of a 128-channel buffer,
+    as in the U-Net concat buffer."""
+    ops = _ops()
+    torch.manual_seed(40 + cin + n)
+    H, W = hw
+    spec = ops.ConvSpec("conv", cin, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+    x = bf16_round(torch.randn(n, cin, H, W)).requires_grad_(True)
+    w = (torch.randn(64, cin, 3, 3) * 0.2).requires_grad_(True)           # fp32 master weight, used unrounded
+    y_ref = F.leaky_relu(F.conv2d(x, w, padding=1), 0.01)
+    dy = bf16_round(torch.randn_like(y_ref))
+    y_ref.backward(dy)
+    xa = to_act(x.detach(), torch.bfloat16)
+    if slice_out:
+        buf = ops.Act.empty(n, 1, H, W, 128, torch.bfloat16)
+        ya = buf.ch(64, 128)
+    else:
+        ya = ops.Act.empty(n, 1, H, W, 64, torch.bfloat16)
+    g = spec.geom(n, (1, H, W), xa.cp, ya.cp if not slice_out else 64)
+    assert ops.img_conv_ok(spec, g, xa, ya)
+    from dcvgan_b200._lib import ACT_LEAKY
+    wdev = w.detach().cuda().contiguous()
+    ops.img_conv_fwd(spec, g, xa, wdev, ya, ACT_LEAKY, 0.01)
+    e_fwd = rel_err(from_act(ya), y_ref.detach().unsqueeze(2))
+    # backward consumes the STORED (bf16) activation for the LeakyReLU sign, like the reference consumes its own output
+    dya = to_act(dy, torch.bfloat16)
+    dxa = ops.Act.empty(n, 1, H, W, cin, torch.bfloat16)
+    dw = torch.full_like(wdev, 3.0)
+    ops.img_conv_bwd(spec, g, dya, ya, xa, wdev, ACT_LEAKY, 0.01, dw, False, dxa)
+    torch.cuda.synchronize()
+    e_dx = rel_err(from_act(dxa), x.grad.unsqueeze(2))
+    e_dw = rel_err(dw.cpu(), w.grad)
+    ops.img_conv_bwd(spec, g, dya, ya, xa, wdev, ACT_LEAKY, 0.01, dw, True, None)
+    torch.cuda.synchronize()
+    e_dw2 = rel_err(dw.cpu(), 2 * w.grad)
+    pad = dxa.padded_to(dxa.cp).torch()[..., dxa.c:]
+    assert float(pad.float().abs().max()) == 0.0                           # padding channels of dx stay zero
+    print(f"img_conv C={cin} n={n} {H}x{W}: fwd {e_fwd:.2e} dx {e_dx:.2e} dw {e_dw:.2e} dw2 {e_dw2:.2e}")
+    assert e_fwd < 5e-3 and e_dx < 5e-3 and e_dw < 5e-3 and e_dw2 < 5e-3
 
 
 def test_conv_channel_slices():

@@ -18,6 +18,9 @@ def test_oracle_reproduces_reference_training(name):
     tr = orc.OracleTrainer(cfg, init)
     torch.manual_seed(meta["step_seed"])
     np.random.seed(meta["step_seed"])
+    quirk = cfg.get("eval_quirk", False)      # log_samples() before the loop and every log_samples_interval iterations
+    if quirk:
+        tr.gen_training = False               # trainer.py:126-127 via trainer.py:268
     for it in range(meta["iters"]):
         bd = meta["batches"][it]
         xc, xg = orc.synthetic_batch(cfg, cfg["batchsize"], bd["seed"])
@@ -25,6 +28,8 @@ def test_oracle_reproduces_reference_training(name):
         out = tr.step(xc, xg)
         for k, v in expected_losses(meta, it).items():
             assert abs(out[k] - v) <= 2e-6 * max(1.0, abs(v)), (name, it, k, out[k], v)
+        if quirk and (it + 1) % cfg["log_samples_interval"] == 0:
+            tr.gen_training = False           # trainer.py:375-376
     for net, dig in meta["final"].items():
         check_digest(tr.P[net], dig, rtol=1e-5, atol=1e-7, what=f"{name}/{net}/")
 

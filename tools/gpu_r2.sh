@@ -1,0 +1,32 @@
+#!/usr/bin/env bash
+# Round-2 GPU session: tests, bench, launch list.  Usage (on the GPU box, from the repo root):  bash tools/gpu_r2.sh <tag> [stages...]
+# stages: tests bench launches layers (default: all four)
+set -u
+TAG=${1:-r2a}; shift || true
+STAGES=${*:-tests bench launches layers}
+mkdir -p gpurun_out
+for st in $STAGES; do
+  case $st in
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -x -q -s > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -5 gpurun_out/${TAG}_tests.log;;
+    quick)
+      timeout 900 python -m pytest tests -m gpu -x -q -s --deselect tests/test_curves_gpu.py > gpurun_out/${TAG}_tests.log 2>&1; echo "quick tests rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -5 gpurun_out/${TAG}_tests.log;;
+    bench)
+      timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
+    benchfast)
+      timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-eager > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
+    refarm)
+      timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_ref.err; echo "refarm rc=$?" | tee -a gpurun_out/${TAG}_rc.log; cat gpurun_out/${TAG}_bench_reference_arm.json;;
+    launches)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv \
+        python bench.py --steps 2 --warmup 3 --no-cpu --no-eager --no-roofline > gpurun_out/${TAG}_ncu.log 2>&1; echo "launches rc=$?" | tee -a gpurun_out/${TAG}_rc.log;;
+    layers)
+      timeout 600 python tools/layer_bench.py mug-depth 32 > gpurun_out/${TAG}_layers.md 2>&1; echo "layers rc=$?" | tee -a gpurun_out/${TAG}_rc.log; head -30 gpurun_out/${TAG}_layers.md;;
+    smoke)
+      timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -3 gpurun_out/${TAG}_smoke.log;;
+    configs)
+      for c in surreal-depth1 isogd-flow surreal-segm; do
+        timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-eager --no-roofline --config $c > gpurun_out/${TAG}_bench_${c}.json 2> gpurun_out/${TAG}_bench_${c}.err; echo "bench $c rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 600 gpurun_out/${TAG}_bench_${c}.json
+      done;;
+  esac
+done

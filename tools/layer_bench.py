@@ -28,59 +28,20 @@ def main():
     C_ = cfg["geometric_info"]["channel"]
     xc = torch.rand(B, 3, 16, 64, 64, device="cuda") * 2 - 1
     xg = torch.rand(B, C_, 16, 64, 64, device="cuda") * 2 - 1
+    tr.use_cuda_graph = False
     for _ in range(2):
         tr.iteration += 1
         tr.train_step(xc, xg)
-    ops.TRACE = []
-    tr.iteration += 1
-    tr.train_step(xc, xg)
-    trace, ops.TRACE = ops.TRACE, None
-    torch.cuda.synchronize()
-    count = collections.Counter((t[0], t[1], t[2], t[3]) for t in trace)
-    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device="cuda")
-    rows = []
-    for (kind, key, direction, impl), n in count.items():
-        g = Geom(*key)
-        taps = g.kt * g.kh * g.kw
-        M = g.N * g.Ts * g.Hs * g.Ws
-        wl, ws = (g.wCl or g.Cl), (g.wCs or g.Cs)
-        flops = 2.0 * M * taps * wl * ws
-        dt = torch.bfloat16
-        L = ops.Act.empty(g.N, g.Tl, g.Hl, g.Wl, g.Cl, dt)
-        S = ops.Act.empty(g.N, g.Ts, g.Hs, g.Ws, g.Cs, dt)
-        L.base.normal_()
-        S.base.normal_()
-        if kind == "conv":
-            nbytes = ops.lib().dcv_packed_weight_bytes(C.byref(g), direction, impl)
-            wp = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
-            x, y = (L, S) if direction == 0 else (S, L)
-            fn = lambda: ops.conv(g, direction, impl, x, wp, y)
-        else:
-            spec = ops.ConvSpec("conv", wl, ws, (g.kt, g.kh, g.kw), (g.st, g.sh, g.sw), (g.pt, g.ph, g.pw))
-            dw = torch.empty((ws, wl, taps), device="cuda")
-            fn = lambda: ops.wgrad(spec, g, L, S, dw, False, impl)
-        for _ in range(2):
-            fn()
-        ts = []
-        for _ in range(5):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = float(np.median(ts))
-        rows.append((ms * n, ms, n, kind, direction, impl, flops, key))
-    rows.sort(reverse=True)
-    total = sum(r[0] for r in rows)
-    print(f"{cfg_name} B={B}: conv-family total {total:.2f} ms/step over {sum(r[2] for r in rows)} launches")
+    rows = bench.layer_table(tr, cfg, B)
+    total = sum(r["ms"] * r["n"] for r in rows)
+    print(f"{cfg_name} B={B}: conv-family total {total:.2f} ms/step over {sum(r['n'] for r in rows)} launches")
     print("| ms/step | ms | n | op | impl | L (T,H,W,C) | S (T,H,W,C) | k | GF | TFLOP/s |")
     print("|---|---|---|---|---|---|---|---|---|---|")
-    for tot, ms, n, kind, direction, impl, flops, key in rows:
-        g = Geom(*key)
-        op = kind if kind == "wgrad" else ("gather" if direction == 0 else "scatter")
-        print(f"| {tot:.3f} | {ms:.3f} | {n} | {op} | {'tc' if impl == IMPL_TC else 'simt'} | {g.Tl},{g.Hl},{g.Wl},{g.wCl or g.Cl} | "
+    for r in rows:
+        g = Geom(*r["key"])
+        kind, direction, impl, flops, ms, n = r["kind"], r["dir"], r["impl"], r["flops"], r["ms"], r["n"]
+        op = kind if kind != "conv" else ("gather" if direction == 0 else "scatter")
+        print(f"| {ms * n:.3f} | {ms:.3f} | {n} | {op} | {'tc' if impl == IMPL_TC else ('direct' if impl < 0 else 'simt')} | {g.Tl},{g.Hl},{g.Wl},{g.wCl or g.Cl} | "
               f"{g.Ts},{g.Hs},{g.Ws},{g.wCs or g.Cs} | {g.kt}x{g.kh}x{g.kw} | {flops / 1e9:.1f} | {flops / ms / 1e9:.0f} |")
 
 
