@@ -43,6 +43,9 @@ SIGNATURES = {
     "dcv_device_ok": (_i, []),
     "dcv_launch_count": (C.c_longlong, []),
     "dcv_set_tuning": (_i, [C.c_char_p, _i]),
+    "dcv_ingest_u8": (_i, [_i, _vp, _i64, _i, _vp, _i64, _vp]),
+    "dcv_ingest_onehot": (_i, [_i, _vp, _i, _i64, _i, _vp, _i64, _vp]),
+    "dcv_export_u8": (_i, [_i, _vp, _i64, _i, _i, _i, _i64, _vp, _vp]),
     "dcv_img_conv_supported": (_i, [_G]),
     "dcv_img_conv_bwd_workspace_bytes": (_i64, [_G]),
     "dcv_img_conv_fwd": (_i, [_G, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i, _f, _vp]),
@@ -65,6 +68,11 @@ SIGNATURES = {
     "dcv_bn_stats_blocks": (_i, [_i64, _i]),
     "dcv_bn_stats": (_i, [_i, _vp, _i64, _i64, _i, _vp, _vp]),
     "dcv_bn_finalize": (_i, [_vp, _i, _i, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dcv_bn_tail_workspace_bytes": (_i64, [_i64, _i]),
+    "dcv_bn_tail_counters": (_i, []),
+    "dcv_bn_stats_finalize": (_i, [_i, _vp, _i64, _i64, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dcv_bn_act_bwd_reduce_finalize": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f,
+                                            _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "dcv_bn_eval_stats": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp]),
     "dcv_bn_act": (_i, [_i, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp, _i64, _vp]),
     "dcv_bn_act_bwd_reduce": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp, _vp]),

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <stdlib.h>
 #include <initializer_list>
+#include <string.h>
 
 namespace dcv {
 
@@ -12,6 +13,83 @@ static inline int ew_blocks(int64_t total, int per_thread = 1) {
   if (b > 148 * 16) b = 148 * 16;
   if (b < 1) b = 1;
   return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------
+// In-kernel finalize of a per-channel reduction ("last block done").  The reduction kernels below leave one partial
+// row [2][C] per block; turning those into mean / invstd (forward) or sum(du), sum(du*xhat), dgamma, dbeta (backward)
+// used to be a second launch of a few microseconds per BatchNorm site - 72 launches per training iteration.  With a
+// BnTail the blocks finish the job themselves, hierarchically and in a FIXED summation order (deterministic):
+//   * blocks are grouped by 16; the block of a group that arrives last (atomic ticket) adds the group's rows, in row
+//     order, into group_ws[group][2][C];
+//   * the group-finishing block that arrives last overall adds the group rows in double precision, in group order, and
+//     writes the final per-channel values (and updates the running statistics exactly like bn_finalize_kernel).
+// Tickets are reset by the block that consumes them, so the same counter buffer serves every call on a stream.
+constexpr int BN_TAIL_GROUP = 16;
+constexpr int BN_TAIL_MAX_GROUPS = 63;
+struct BnTail {
+  unsigned* counters;       // [1 + BN_TAIL_MAX_GROUPS] zero-initialised, self-resetting; NULL = no in-kernel finalize
+  float* group_ws;          // [ngroups][2][C]
+  int backward;             // 0: BatchNorm statistics, 1: BatchNorm backward sums
+  double count; float eps, momentum;
+  float* running_mean; float* running_var; long long* num_batches_tracked; float* mean; float* invstd;
+  float* sums; float* dgamma; float* dbeta; int accumulate;
+};
+static inline BnTail no_tail() { BnTail t; memset(&t, 0, sizeof(t)); return t; }
+
+__device__ __forceinline__ void bn_tail(const float* __restrict__ partials, int C, const BnTail& t) {
+  if (t.counters == nullptr) return;
+  __shared__ int s_role;
+  const int nblk = (int)gridDim.x, tid = (int)threadIdx.x;
+  const int group = (int)blockIdx.x / BN_TAIL_GROUP, ngroups = (nblk + BN_TAIL_GROUP - 1) / BN_TAIL_GROUP;
+  const int g0 = group * BN_TAIL_GROUP, gsize = nblk - g0 < BN_TAIL_GROUP ? nblk - g0 : BN_TAIL_GROUP;
+  __threadfence();                                   // this block's partial row is visible device-wide ...
+  __syncthreads();
+  if (tid == 0) s_role = atomicAdd(&t.counters[1 + group], 1u) == (unsigned)(gsize - 1);   // ... before its ticket is
+  __syncthreads();
+  if (!s_role) return;
+  __threadfence();
+  for (int i = tid; i < 2 * C; i += (int)blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < gsize; ++r) a += __ldcg(partials + (size_t)(g0 + r) * 2 * C + i);
+    t.group_ws[(size_t)group * 2 * C + i] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    t.counters[1 + group] = 0u;
+    s_role = atomicAdd(&t.counters[0], 1u) == (unsigned)(ngroups - 1);
+  }
+  __syncthreads();
+  if (!s_role) return;
+  __threadfence();
+  for (int c = tid; c < C; c += (int)blockDim.x) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int g = 0; g < ngroups; ++g) {
+      s0 += (double)__ldcg(t.group_ws + (size_t)g * 2 * C + c);
+      s1 += (double)__ldcg(t.group_ws + (size_t)g * 2 * C + C + c);
+    }
+    if (!t.backward) {
+      const double m = s0 / t.count;
+      double var = s1 / t.count - m * m;
+      if (var < 0.0) var = 0.0;
+      t.mean[c] = (float)m;
+      t.invstd[c] = (float)(1.0 / sqrt(var + (double)t.eps));
+      if (t.running_mean) {
+        const double unbiased = t.count > 1.0 ? var * t.count / (t.count - 1.0) : var;
+        t.running_mean[c] = (float)((1.0 - t.momentum) * t.running_mean[c] + t.momentum * m);
+        t.running_var[c] = (float)((1.0 - t.momentum) * t.running_var[c] + t.momentum * unbiased);
+      }
+    } else {
+      t.sums[c] = (float)s0; t.sums[C + c] = (float)s1;
+      if (t.dbeta) t.dbeta[c] = t.accumulate ? t.dbeta[c] + (float)s0 : (float)s0;
+      if (t.dgamma) t.dgamma[c] = t.accumulate ? t.dgamma[c] + (float)s1 : (float)s1;
+    }
+  }
+  if (tid == 0) {
+    t.counters[0] = 0u;
+    if (!t.backward && t.num_batches_tracked) *t.num_batches_tracked += 1;      // nn.BatchNorm's counter
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -52,10 +130,11 @@ __device__ __forceinline__ void channel_reduce2(int64_t rows, int C, float* __re
 
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C,
-                                                        float* __restrict__ partials) {
+                                                        float* __restrict__ partials, const BnTail tail) {
   channel_reduce2(rows, C, partials, [&](int64_t row, int c, float& v0, float& v1) {
     const float v = ldf(z + row * ldz + c); v0 = v; v1 = v * v;
   });
+  bn_tail(partials, C, tail);
 }
 
 // one warp per channel: lanes stride over the partial blocks, double accumulation, fixed shuffle tree
@@ -129,13 +208,14 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, int64_t lda,
                          const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const float* __restrict__ drop, int64_t rows_per_n,
-                         int act, float slope, float* __restrict__ partials) {
+                         int act, float slope, float* __restrict__ partials, const BnTail tail) {
   channel_reduce2(rows, C, partials, [&](int64_t row, int c, float& v0, float& v1) {
     float du = ldf(da + row * ldda + c) * act_grad_from_out(ldf(a + row * lda + c), act, slope);
     if (drop) du *= drop[(row / rows_per_n) * C + c];
     const float xhat = (ldf(z + row * ldz + c) - mean[c]) * invstd[c];
     v0 = du; v1 = du * xhat;
   });
+  bn_tail(partials, C, tail);
 }
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int C, float* __restrict__ sums,
@@ -506,13 +586,14 @@ __device__ __forceinline__ void channel_reduce2_vec(int64_t rows, int C, float* 
 
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_vec_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C,
-                                                            float* __restrict__ partials) {
+                                                            float* __restrict__ partials, const BnTail tail) {
   constexpr int N = VecIO<T>::N;
   channel_reduce2_vec<T>(rows, C, partials, [&](int64_t row, int c0, float (&v0)[N], float (&v1)[N]) {
     VecIO<T>::load(z + row * ldz + c0, v0);
 #pragma unroll
     for (int j = 0; j < N; ++j) v1[j] = v0[j] * v0[j];
   });
+  bn_tail(partials, C, tail);
 }
 
 template <typename T>
@@ -521,7 +602,7 @@ bn_act_bwd_reduce_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __
                              const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
                              const float* __restrict__ invstd, const float* __restrict__ gamma,
                              const float* __restrict__ beta, const float* __restrict__ drop, int64_t rows_per_n,
-                             int act, float slope, float* __restrict__ partials) {
+                             int act, float slope, float* __restrict__ partials, const BnTail tail) {
   constexpr int N = VecIO<T>::N;
   // (Leaky)ReLU: the sign of the activated output equals the sign of the pre-activation gamma * xhat + beta, which is
   // recomputed from z with exactly the forward's arithmetic - the output tensor `a` is then not read at all (one of
@@ -542,6 +623,7 @@ bn_act_bwd_reduce_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __
       v0[j] = du; v1[j] = du * xhat;
     }
   });
+  bn_tail(partials, C, tail);
 }
 
 template <typename T>
@@ -982,7 +1064,8 @@ __device__ __forceinline__ void reduce2_tail(const VecMap& m, int C, float (&a0)
 }
 
 __global__ void __launch_bounds__(256, 3)
-bn_stats_bf16_kernel(const __nv_bfloat16* __restrict__ z, int64_t ldz, int64_t rows, int C, float* __restrict__ partials) {
+bn_stats_bf16_kernel(const __nv_bfloat16* __restrict__ z, int64_t ldz, int64_t rows, int C, float* __restrict__ partials,
+                     const BnTail tail) {
   const VecMap m = vec_map<8>(rows, C);
   float a0[8], a1[8];
 #pragma unroll
@@ -1007,13 +1090,14 @@ bn_stats_bf16_kernel(const __nv_bfloat16* __restrict__ z, int64_t ldz, int64_t r
     }
   }
   reduce2_tail(m, C, a0, a1, partials);
+  bn_tail(partials, C, tail);
 }
 
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_bf16_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const __nv_bfloat16* __restrict__ z, int64_t ldz,
                               int64_t rows, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ drop,
-                              int64_t rows_per_n, float slope, float* __restrict__ partials) {
+                              int64_t rows_per_n, float slope, float* __restrict__ partials, const BnTail tail) {
   const VecMap m = vec_map<8>(rows, C);
   float a0[8], a1[8];
 #pragma unroll
@@ -1057,6 +1141,7 @@ bn_act_bwd_reduce_bf16_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda
     }
   }
   reduce2_tail(m, C, a0, a1, partials);
+  bn_tail(partials, C, tail);
 }
 
 static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
@@ -1096,15 +1181,49 @@ int dcv_bn_stats_blocks(int64_t rows, int C) {
   return (int)b;
 }
 
-int dcv_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float* partials, void* stream) {
+static int launch_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float* partials, const BnTail& tail, void* stream) {
   const int nblk = dcv_bn_stats_blocks(rows, C);
   DISPATCH_T(dtype, {
     if (sizeof(T) == 2 && vec_ok<T>(C, {z}, {ldz}))
-      bn_stats_bf16_kernel<<<nblk, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, ldz, rows, C, partials);
-    else if (vec_ok<T>(C, {z}, {ldz})) bn_stats_vec_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials);
-    else bn_stats_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials);
+      bn_stats_bf16_kernel<<<nblk, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, ldz, rows, C, partials, tail);
+    else if (vec_ok<T>(C, {z}, {ldz})) bn_stats_vec_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials, tail);
+    else bn_stats_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials, tail);
   });
   return check_launch("bn_stats");
+}
+
+int dcv_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float* partials, void* stream) {
+  return launch_bn_stats(dtype, z, ldz, rows, C, partials, no_tail(), stream);
+}
+
+int64_t dcv_bn_tail_workspace_bytes(int64_t rows, int C) {
+  const int nblk = dcv_bn_stats_blocks(rows, C);
+  const int ngroups = (nblk + BN_TAIL_GROUP - 1) / BN_TAIL_GROUP;
+  return (int64_t)(nblk + ngroups) * 2 * C * sizeof(float);
+}
+int dcv_bn_tail_counters(void) { return 1 + BN_TAIL_MAX_GROUPS; }
+
+static int tail_ws(int64_t rows, int C, float* ws, unsigned* counters, float** partials, BnTail* t) {
+  DCV_REQUIRE(ws && counters, "bn (fused finalize): null workspace / counters");
+  const int nblk = dcv_bn_stats_blocks(rows, C);
+  const int ngroups = (nblk + BN_TAIL_GROUP - 1) / BN_TAIL_GROUP;
+  DCV_REQUIRE(ngroups <= BN_TAIL_MAX_GROUPS, "bn (fused finalize): %d block groups", ngroups);
+  *partials = ws;
+  *t = no_tail();
+  t->counters = counters;
+  t->group_ws = ws + (size_t)nblk * 2 * C;
+  return 0;
+}
+
+int dcv_bn_stats_finalize(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float eps, float momentum,
+                          float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd,
+                          void* ws, void* counters, void* stream) {
+  float* partials; BnTail t;
+  if (int rc = tail_ws(rows, C, (float*)ws, (unsigned*)counters, &partials, &t)) return rc;
+  t.backward = 0; t.count = (double)rows; t.eps = eps; t.momentum = momentum;
+  t.running_mean = running_mean; t.running_var = running_var; t.num_batches_tracked = (long long*)num_batches_tracked;
+  t.mean = mean; t.invstd = invstd;
+  return launch_bn_stats(dtype, z, ldz, rows, C, partials, t, stream);
 }
 
 int dcv_bn_finalize(const float* partials, int nblk, int C, int64_t count, float eps, float momentum,
@@ -1140,25 +1259,45 @@ int dcv_bn_act(int dtype, const void* z, int64_t ldz, int64_t rows, int C, const
   return check_launch("bn_act");
 }
 
-int dcv_bn_act_bwd_reduce(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, const void* z,
-                          int64_t ldz, int64_t rows, int C, const float* mean, const float* invstd, const float* gamma,
-                          const float* beta, const float* drop, int64_t rows_per_n, int act, float slope, float* partials,
-                          void* stream) {
+static int launch_bn_bwd_reduce(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, const void* z,
+                                int64_t ldz, int64_t rows, int C, const float* mean, const float* invstd, const float* gamma,
+                                const float* beta, const float* drop, int64_t rows_per_n, int act, float slope, float* partials,
+                                const BnTail& tail, void* stream) {
   const int nblk = dcv_bn_stats_blocks(rows, C);
   DISPATCH_T(dtype, {
     if (sizeof(T) == 2 && act == DCV_ACT_LEAKY && vec_ok<T>(C, {da, z}, {ldda, ldz}))
       bn_act_bwd_reduce_bf16_kernel<<<nblk, 256, 0, as_stream(stream)>>>(
           (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, slope,
-          partials);
+          partials, tail);
     else if (vec_ok<T>(C, {da, a, z}, {ldda, lda, ldz}))
       bn_act_bwd_reduce_vec_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>(
           (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope,
-          partials);
+          partials, tail);
     else
       bn_act_bwd_reduce_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>(
-          (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, drop, rows_per_n, act, slope, partials);
+          (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, drop, rows_per_n, act, slope, partials, tail);
   });
   return check_launch("bn_act_bwd_reduce");
+}
+
+int dcv_bn_act_bwd_reduce(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, const void* z,
+                          int64_t ldz, int64_t rows, int C, const float* mean, const float* invstd, const float* gamma,
+                          const float* beta, const float* drop, int64_t rows_per_n, int act, float slope, float* partials,
+                          void* stream) {
+  return launch_bn_bwd_reduce(dtype, da, ldda, a, lda, z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope,
+                              partials, no_tail(), stream);
+}
+
+int dcv_bn_act_bwd_reduce_finalize(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda, const void* z,
+                                   int64_t ldz, int64_t rows, int C, const float* mean, const float* invstd, const float* gamma,
+                                   const float* beta, const float* drop, int64_t rows_per_n, int act, float slope, float* sums,
+                                   float* dgamma, float* dbeta, int accumulate, void* ws, void* counters, void* stream) {
+  float* partials; BnTail t;
+  if (int rc = tail_ws(rows, C, (float*)ws, (unsigned*)counters, &partials, &t)) return rc;
+  DCV_REQUIRE(sums, "bn_act_bwd_reduce_finalize: null sums");
+  t.backward = 1; t.sums = sums; t.dgamma = dgamma; t.dbeta = dbeta; t.accumulate = accumulate;
+  return launch_bn_bwd_reduce(dtype, da, ldda, a, lda, z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope,
+                              partials, t, stream);
 }
 
 int dcv_bn_bwd_finalize(const float* partials, int nblk, int C, float* sums, float* dgamma, float* dbeta,

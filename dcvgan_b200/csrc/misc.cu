@@ -226,6 +226,48 @@ adam_multi_kernel(AdamArgs a, float b1, float b2, float eps, float wd, float ste
 
 using namespace dcv;
 
+// ------------------------------------------------------------------------------------------ dataset-side conversions
+// The reference's dataset delivers float32 (C,T,H,W) clips made on the host from uint8 frames (dataset.py:128-131,
+// 157-167: `astype(float32) / 127.5 - 1.0` after a transpose to channels-first) or from class indices (:177-181:
+// `np.eye(25)[segm]`), and its sampler converts generated videos back on the host (util.py:74-79).  The frames on disk
+// are channels-LAST uint8 - exactly this library's activation layout - so the conversions run on the device instead:
+// a quarter of the PCIe bytes in, a quarter out, and no host-side transpose.
+template <typename T>
+__global__ void __launch_bounds__(256)
+ingest_u8_kernel(const uint8_t* __restrict__ src, int64_t rows, int C, T* __restrict__ dst, int64_t ld) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C; const int c = (int)(i - row * C);
+    stf(dst + row * ld + c, (float)src[i] / 127.5f - 1.0f);
+  }
+}
+
+template <typename T, typename I>
+__global__ void __launch_bounds__(256)
+ingest_onehot_kernel(const I* __restrict__ idx, int64_t rows, int C, T* __restrict__ dst, int64_t ld) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C; const int c = (int)(i - row * C);
+    stf(dst + row * ld + c, (int)idx[row] == c ? 1.0f : 0.0f);
+  }
+}
+
+// channels-last (N, T, HW, C) activations in [-1, 1] -> planar uint8 (N, C, T, HW), numpy's clip / (v + 1) / 2 * 255 / astype
+template <typename T>
+__global__ void __launch_bounds__(256)
+export_u8_kernel(const T* __restrict__ src, int64_t ld, int N, int C, int T_, int64_t hw, uint8_t* __restrict__ dst) {
+  const int64_t total = (int64_t)N * T_ * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i % hw; const int64_t nt = i / hw; const int t = (int)(nt % T_); const int64_t n = nt / T_;
+    for (int c = 0; c < C; ++c) {
+      float v = ldf(src + i * ld + c);
+      v = fminf(fmaxf(v, -1.0f), 1.0f);
+      v = (v + 1.0f) / 2.0f * 255.0f;
+      dst[((n * C + c) * T_ + t) * hw + p] = (uint8_t)v;
+    }
+  }
+}
+
 extern "C" {
 
 int dcv_gru_traj_fwd(const float* h0, const float* eps, const float* w_ih, const float* w_hh, const float* b_ih,
@@ -325,6 +367,41 @@ int dcv_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float
                   float weight_decay, int64_t step, float grad_scale, void* stream) {
   float* pp[1] = {p}; const float* gg[1] = {g}; float* mm[1] = {m}; float* vv[1] = {v}; int64_t nn[1] = {n};
   return dcv_adam_multi(1, pp, gg, mm, vv, nn, lr, beta1, beta2, eps, weight_decay, step, grad_scale, stream);
+}
+
+static inline int io_blocks(int64_t total) { int64_t b = (total + 1023) / 1024; if (b > 148 * 16) b = 148 * 16; if (b < 1) b = 1; return (int)b; }
+
+int dcv_ingest_u8(int dtype, const void* src, int64_t rows, int C, void* dst, int64_t ld, void* stream) {
+  DCV_REQUIRE(src && dst && C >= 1 && ld >= C, "ingest_u8: bad arguments");
+  if (rows * C == 0) return 0;
+  if (dtype == DCV_F32) ingest_u8_kernel<float><<<io_blocks(rows * C), 256, 0, as_stream(stream)>>>((const uint8_t*)src, rows, C, (float*)dst, ld);
+  else ingest_u8_kernel<__nv_bfloat16><<<io_blocks(rows * C), 256, 0, as_stream(stream)>>>((const uint8_t*)src, rows, C, (__nv_bfloat16*)dst, ld);
+  return check_launch("ingest_u8");
+}
+
+int dcv_ingest_onehot(int dtype, const void* idx, int idx_bytes, int64_t rows, int C, void* dst, int64_t ld, void* stream) {
+  DCV_REQUIRE(idx && dst && C >= 1 && ld >= C, "ingest_onehot: bad arguments");
+  DCV_REQUIRE(idx_bytes == 1 || idx_bytes == 8, "ingest_onehot: class indices must be uint8 or int64 (element size %d)", idx_bytes);
+  if (rows * C == 0) return 0;
+  const int nb = io_blocks(rows * C);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == DCV_F32) {
+    if (idx_bytes == 1) ingest_onehot_kernel<float, uint8_t><<<nb, 256, 0, st>>>((const uint8_t*)idx, rows, C, (float*)dst, ld);
+    else ingest_onehot_kernel<float, long long><<<nb, 256, 0, st>>>((const long long*)idx, rows, C, (float*)dst, ld);
+  } else {
+    if (idx_bytes == 1) ingest_onehot_kernel<__nv_bfloat16, uint8_t><<<nb, 256, 0, st>>>((const uint8_t*)idx, rows, C, (__nv_bfloat16*)dst, ld);
+    else ingest_onehot_kernel<__nv_bfloat16, long long><<<nb, 256, 0, st>>>((const long long*)idx, rows, C, (__nv_bfloat16*)dst, ld);
+  }
+  return check_launch("ingest_onehot");
+}
+
+int dcv_export_u8(int dtype, const void* src, int64_t ld, int N, int C, int T_, int64_t hw, void* dst, void* stream) {
+  DCV_REQUIRE(src && dst && C >= 1 && ld >= C, "export_u8: bad arguments");
+  const int64_t total = (int64_t)N * T_ * hw;
+  if (total == 0) return 0;
+  if (dtype == DCV_F32) export_u8_kernel<float><<<io_blocks(total * 2), 256, 0, as_stream(stream)>>>((const float*)src, ld, N, C, T_, hw, (uint8_t*)dst);
+  else export_u8_kernel<__nv_bfloat16><<<io_blocks(total * 2), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, ld, N, C, T_, hw, (uint8_t*)dst);
+  return check_launch("export_u8");
 }
 
 }  // extern "C"

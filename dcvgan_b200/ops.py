@@ -382,7 +382,7 @@ def wgrad(spec, g, xl, xs, dw, accumulate=False, impl=None):
 
 
 # ------------------------------------------------------------------------------------ direct image-side convolution
-IMG_CONV = os.environ.get("DCV_NO_IMG_CONV", "0") != "1"
+IMG_CONV = os.environ.get("DCV_IMG_CONV", "0") == "1"   # r2a: 0.165 ms fwd / 0.83 ms bwd at B=32 - slower than the tensor-core tiles (0.167 / 0.42): opt-in until rewritten
 
 
 def img_conv_ok(spec, g, x, y):
@@ -420,8 +420,28 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+BN_FUSED_FINALIZE = os.environ.get("DCV_NO_BN_TAIL", "0") != "1"   # statistics / backward sums finalized inside the reduction launch
+_BN_COUNTERS = {}
+
+
+def _bn_counters(device):
+    """zero-initialised, self-resetting ticket buffer of the in-kernel finalize (one per device; calls on a stream are ordered)"""
+    t = _BN_COUNTERS.get(device)
+    if t is None:
+        t = _BN_COUNTERS[device] = torch.zeros(lib().dcv_bn_tail_counters(), dtype=torch.int32, device=device)
+    return t
+
+
 def bn_batch_stats(z, eps, momentum, running_mean, running_var, num_batches_tracked=None):
     zp, ldz, rows, c = cl_view(z)
+    if BN_FUSED_FINALIZE:
+        mean = torch.empty(c, dtype=torch.float32, device=z.device)
+        invstd = torch.empty_like(mean)
+        ws = torch.empty(lib().dcv_bn_tail_workspace_bytes(rows, c), dtype=torch.uint8, device=z.device)
+        check(lib().dcv_bn_stats_finalize(dcv_dtype(z), zp, ldz, rows, c, eps, momentum, _p(running_mean), _p(running_var),
+                                          _p(num_batches_tracked), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(),
+                                          _bn_counters(z.device).data_ptr(), _stream()))
+        return mean, invstd
     nblk = lib().dcv_bn_stats_blocks(rows, c)
     partials = torch.empty((nblk, 2, c), dtype=torch.float32, device=z.device)
     mean = torch.empty(c, dtype=torch.float32, device=z.device)
@@ -460,13 +480,20 @@ def bn_act_bwd(da, a, z, mean, invstd, gamma, beta, drop, act, slope, dz, dgamma
     dzp, lddz, _, _ = cl_view(dz)
     rows_per_n = rows // z.n
     nblk = lib().dcv_bn_stats_blocks(rows, c)
-    partials = torch.empty((nblk, 2, c), dtype=torch.float32, device=z.device)
     sums = torch.empty((2, c), dtype=torch.float32, device=z.device)
     dt = dcv_dtype(z)
-    check(lib().dcv_bn_act_bwd_reduce(dt, dap, ldda, ap, lda, zp, ldz, rows, c, mean.data_ptr(), invstd.data_ptr(),
-                                      _p(gamma), _p(beta), _p(drop), rows_per_n, act, slope, partials.data_ptr(), _stream()))
-    check(lib().dcv_bn_bwd_finalize(partials.data_ptr(), nblk, c, sums.data_ptr(), _p(dgamma), _p(dbeta),
-                                    int(accumulate), _stream()))
+    if BN_FUSED_FINALIZE:
+        ws = torch.empty(lib().dcv_bn_tail_workspace_bytes(rows, c), dtype=torch.uint8, device=z.device)
+        check(lib().dcv_bn_act_bwd_reduce_finalize(dt, dap, ldda, ap, lda, zp, ldz, rows, c, mean.data_ptr(), invstd.data_ptr(),
+                                                   _p(gamma), _p(beta), _p(drop), rows_per_n, act, slope, sums.data_ptr(),
+                                                   _p(dgamma), _p(dbeta), int(accumulate), ws.data_ptr(),
+                                                   _bn_counters(z.device).data_ptr(), _stream()))
+    else:
+        partials = torch.empty((nblk, 2, c), dtype=torch.float32, device=z.device)
+        check(lib().dcv_bn_act_bwd_reduce(dt, dap, ldda, ap, lda, zp, ldz, rows, c, mean.data_ptr(), invstd.data_ptr(),
+                                          _p(gamma), _p(beta), _p(drop), rows_per_n, act, slope, partials.data_ptr(), _stream()))
+        check(lib().dcv_bn_bwd_finalize(partials.data_ptr(), nblk, c, sums.data_ptr(), _p(dgamma), _p(dbeta),
+                                        int(accumulate), _stream()))
     if not batch_stats:
         sums.zero_()
     check(lib().dcv_bn_act_bwd_apply(dt, dap, ldda, ap, lda, zp, ldz, rows, c, mean.data_ptr(), invstd.data_ptr(),
@@ -585,6 +612,24 @@ def from_channels_last(src, dst, accumulate=False):
     sn, sc, st, sh, sw = dst.stride()
     check(lib().dcv_from_channels_last(dcv_dtype(src), sp, ld, n, c, t, h, w, dst.data_ptr(), sn, sc, st, sh, sw,
                                        int(accumulate), _stream()))
+
+
+def ingest_u8(src, dst):
+    """uint8 frames (N,T,H,W,C) as stored on disk -> channels-last Act, x / 127.5 - 1 (dataset.py:128-131,157-167)"""
+    assert src.dtype == torch.uint8 and src.is_cuda and src.is_contiguous() and tuple(src.shape) == dst.shape, (src.shape, dst.shape)
+    check(lib().dcv_ingest_u8(dcv_dtype(dst), src.data_ptr(), dst.rows, dst.c, dst.ptr, dst.ld, _stream()))
+
+
+def ingest_onehot(idx, dst):
+    """class indices (N,T,H,W) uint8 / int64 -> one-hot channels-last Act (dataset.py:177-181)"""
+    assert idx.dtype in (torch.uint8, torch.int64) and idx.is_cuda and idx.is_contiguous() and tuple(idx.shape) == dst.shape[:4]
+    check(lib().dcv_ingest_onehot(dcv_dtype(dst), idx.data_ptr(), idx.element_size(), dst.rows, dst.c, dst.ptr, dst.ld, _stream()))
+
+
+def export_u8(src, dst):
+    """channels-last Act (N,T,H,W,C) in [-1,1] -> uint8 (N,C,T,H,W) like util.videos_to_numpy (util.py:74-79)"""
+    assert dst.dtype == torch.uint8 and dst.is_cuda and dst.is_contiguous() and tuple(dst.shape) == (src.n, src.c, src.t, src.h, src.w)
+    check(lib().dcv_export_u8(dcv_dtype(src), src.ptr, src.ld, src.n, src.c, src.t, src.h * src.w, dst.data_ptr(), _stream()))
 
 
 def _frame_index(t):

@@ -118,6 +118,19 @@ class _FlatNet:
             self.opt.state[p]["step"] = torch.tensor(step)
 
 
+def _cpu_state(osd):
+    """optimizer.state_dict() with every tensor detached, cloned and moved to the CPU"""
+    def conv(v):
+        if isinstance(v, torch.Tensor):
+            return v.detach().clone().cpu()
+        if isinstance(v, dict):
+            return {k: conv(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return type(v)(conv(x) for x in v)
+        return v
+    return conv(osd)
+
+
 def dp_world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
@@ -242,6 +255,25 @@ class Trainer(object):
         for name, model in self.models.items():
             sd = {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
             torch.save(sd, self.model_snapshots_path / f"{name}_params_{self.iteration:05d}.pth")
+        # Beyond the reference (which cannot resume): the Adam state of every network and the loop counters.
+        self.sync_optimizer_state()
+        optim = {name: _cpu_state(opt.state_dict()) for name, opt in self.optimizers.items() if name in self.models}
+        torch.save({"iteration": self.iteration, "epoch": self.epoch, "optimizers": optim},
+                   self.model_snapshots_path / f"optim_{self.iteration:05d}.pth")
+
+    def load_snapshot(self, iteration, path=None):
+        """Resume from the snapshot `save_params()` wrote at `iteration`: model parameters / BatchNorm buffers
+        ({name}_params_{iteration:05d}.pth, the reference's format, infer.py:14-38) plus optim_{iteration:05d}.pth."""
+        path = Path(path) if path is not None else self.model_snapshots_path
+        for name, model in self.models.items():
+            model.load_state_dict(torch.load(path / f"{name}_params_{iteration:05d}.pth", map_location="cpu"))
+        st = torch.load(path / f"optim_{iteration:05d}.pth", map_location="cpu")
+        for name, osd in st["optimizers"].items():
+            self.optimizers[name].load_state_dict(osd)
+        self.iteration, self.epoch = int(st["iteration"]), int(st["epoch"])
+        self._flat = None            # re-adopt parameters and optimizer state into fresh flat buffers at the next step
+        self._graphs.clear()
+        self._wcache.clear()
 
     def log_hparams(self):
         def flat(item, key):
@@ -326,8 +358,21 @@ class Trainer(object):
         if self.world > 1:
             self._reducer.wait()
 
-    def _to_clip(self, x):
-        """(B,C,T,H,W) fp32 torch tensor -> channels-last Act (B,T,H,W,C)"""
+    def _to_clip(self, x, channels=None):
+        """Real batch -> channels-last Act (B,T,H,W,C).  Accepted forms:
+          * (B,C,T,H,W) float32 - what the reference's dataset yields (dataset.py:128-186);
+          * (B,T,H,W,C) uint8   - raw frames as stored on disk: `/ 127.5 - 1` happens on the device (a quarter of the H2D bytes);
+          * (B,T,H,W) uint8 / int64 class indices (segmentation): one-hot expansion on the device."""
+        if x.dtype == torch.uint8 and x.dim() == 5:
+            b, t, h, w, c = x.shape
+            a = Act.empty(b, t, h, w, c, self.dtype)
+            ops.ingest_u8(x.contiguous(), a)
+            return a
+        if x.dtype in (torch.uint8, torch.int64) and x.dim() == 4:
+            b, t, h, w = x.shape
+            a = Act.empty(b, t, h, w, channels, self.dtype)
+            ops.ingest_onehot(x.contiguous(), a)
+            return a
         b, c, t, h, w = x.shape
         a = Act.empty(b, t, h, w, c, self.dtype)
         ops.to_channels_last(x.float(), a)
@@ -384,9 +429,10 @@ class Trainer(object):
         i = self._stage_i
         self._stage_i ^= 1
         slot = self._stage[i]
-        if slot is None or slot["xc"].shape != xc_host.shape or slot["xg"].shape != xg_host.shape:
-            slot = self._stage[i] = {"xc": torch.empty(xc_host.shape, dtype=torch.float32, device=self.device),
-                                     "xg": torch.empty(xg_host.shape, dtype=torch.float32, device=self.device),
+        if (slot is None or slot["xc"].shape != xc_host.shape or slot["xg"].shape != xg_host.shape
+                or slot["xc"].dtype != xc_host.dtype or slot["xg"].dtype != xg_host.dtype):
+            slot = self._stage[i] = {"xc": torch.empty(xc_host.shape, dtype=xc_host.dtype, device=self.device),
+                                     "xg": torch.empty(xg_host.shape, dtype=xg_host.dtype, device=self.device),
                                      "ready": torch.cuda.Event(), "consumed": None}
         if slot["consumed"] is not None:
             self._copy_stream.wait_event(slot["consumed"])
@@ -459,14 +505,14 @@ class Trainer(object):
         cfg = self.configs
         ggen, cgen = self.models["ggen"], self.models["cgen"]
         key = (self.iteration % cfg["num_gen_update"] == 0, self.iteration % cfg["num_dis_update"] == 0,
-               ggen.training, cgen.training, tuple(xc_real.shape), tuple(xg_real.shape))
+               ggen.training, cgen.training, tuple(xc_real.shape), tuple(xg_real.shape), xc_real.dtype, xg_real.dtype)
         slot = self._graphs.setdefault(key, [0, None, None, None])
         if slot[1] is None and slot[0] < self.GRAPH_WARMUP:
             slot[0] += 1
             return self._eager_step(xc_real, xg_real, t_rand)
         if slot[3] is None:   # static inputs of this graph: the real batch and the frame index
-            slot[3] = (torch.empty(xc_real.shape, dtype=torch.float32, device=self.device),
-                       torch.empty(xg_real.shape, dtype=torch.float32, device=self.device),
+            slot[3] = (torch.empty(xc_real.shape, dtype=xc_real.dtype, device=self.device),
+                       torch.empty(xg_real.shape, dtype=xg_real.dtype, device=self.device),
                        torch.zeros(1, dtype=torch.int32, device=self.device))
         gxc, gxg, t_dev = slot[3]
         staged = self._take_prefetched(xc_real, xg_real)
@@ -515,7 +561,7 @@ class Trainer(object):
         for n in self._dnames:
             self.models[n].train()
         upd_d = self.iteration % cfg["num_gen_update"] == 0                                     # sic, trainer.py:318
-        xc_r, xg_r = self._to_clip(xc_real), self._to_clip(xg_real)
+        xc_r, xg_r = self._to_clip(xc_real), self._to_clip(xg_real, self.models["ggen"].channel)
         real = self._dis_forward(xg_r, xc_r, t_rand, upd_d)
         xg_f, xc_f, _, _ = self._generate(B, ggen.training, cgen.training, save=False)
         fake = self._dis_forward(xg_f.reshape_nt(B, T), xc_f.reshape_nt(B, T), t_rand, upd_d)

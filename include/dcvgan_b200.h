@@ -162,6 +162,15 @@ int dcv_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, int C, flo
 int dcv_bn_finalize(const float* partials, int nblk, int C, int64_t count, float eps, float momentum,
                     float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean,
                     float* invstd, void* stream);
+/* dcv_bn_stats + dcv_bn_finalize in ONE launch: the reduction blocks finish the job themselves ("last block done",
+ * hierarchical, fixed summation order -> deterministic).  ws: dcv_bn_tail_workspace_bytes(rows, C) bytes of scratch;
+ * counters: dcv_bn_tail_counters() zero-initialised uint32 that the kernel leaves zero again (one buffer serves every
+ * call on a stream).  Same outputs as the two-launch form up to the rounding of a different summation tree. */
+int64_t dcv_bn_tail_workspace_bytes(int64_t rows, int C);
+int dcv_bn_tail_counters(void);
+int dcv_bn_stats_finalize(int dtype, const void* z, int64_t ldz, int64_t rows, int C, float eps, float momentum,
+                          float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd,
+                          void* ws, void* counters, void* stream);
 /* eval mode: mean = running_mean, invstd = rsqrt(running_var + eps) */
 int dcv_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
                       float* mean, float* invstd, void* stream);
@@ -178,6 +187,12 @@ int dcv_bn_act_bwd_reduce(int dtype, const void* da, int64_t ldda, const void* a
                           const void* z, int64_t ldz, int64_t rows, int C, const float* mean,
                           const float* invstd, const float* gamma, const float* beta, const float* drop,
                           int64_t rows_per_n, int act, float slope, float* partials, void* stream);
+/* dcv_bn_act_bwd_reduce + dcv_bn_bwd_finalize in ONE launch (same scheme as dcv_bn_stats_finalize) */
+int dcv_bn_act_bwd_reduce_finalize(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda,
+                                   const void* z, int64_t ldz, int64_t rows, int C, const float* mean,
+                                   const float* invstd, const float* gamma, const float* beta, const float* drop,
+                                   int64_t rows_per_n, int act, float slope, float* sums /*[2][C]*/, float* dgamma,
+                                   float* dbeta, int accumulate, void* ws, void* counters, void* stream);
 int dcv_bn_bwd_finalize(const float* partials, int nblk, int C, float* sums /*[2][C]*/, float* dgamma,
                         float* dbeta, int accumulate, void* stream);
 int dcv_bn_act_bwd_apply(int dtype, const void* da, int64_t ldda, const void* a, int64_t lda,
@@ -219,6 +234,16 @@ int dcv_fold_w(int dtype, const void* xg, int64_t ldg, int cg, const float* nois
                void* stream);
 int dcv_unfold_w(int dtype, const void* d2, int64_t ld2, int64_t lines, int W, int kw, int sw, int pw, void* dxg, int64_t ldg,
                  int cg, void* dxc, int64_t ldc, int cc, void* stream);
+/* Dataset-side conversions on the device.  The reference converts on the host: uint8 frames -> float32 `x / 127.5 - 1`
+ * after a transpose to channels-first (dataset.py:128-131,157-167), class indices -> one-hot `np.eye(25)[segm]`
+ * (dataset.py:177-181), generated videos -> uint8 `clip(v,-1,1); (v+1)/2*255; astype(uint8)` (util.py:74-79).  Frames on
+ * disk are channels-last uint8, i.e. already in this library's activation layout:
+ *   dcv_ingest_u8     : dst[row][c] = src[row*C + c] / 127.5 - 1       (src uint8 [rows][C] dense, dst pitch ld)
+ *   dcv_ingest_onehot : dst[row][c] = (idx[row] == c)                  (idx uint8 or int64, idx_bytes = 1 or 8)
+ *   dcv_export_u8     : channels-last (N,T,hw,C) -> planar uint8 (N,C,T,hw) with numpy's arithmetic (bit-exact in fp32) */
+int dcv_ingest_u8(int dtype, const void* src, int64_t rows, int C, void* dst, int64_t ld, void* stream);
+int dcv_ingest_onehot(int dtype, const void* idx, int idx_bytes, int64_t rows, int C, void* dst, int64_t ld, void* stream);
+int dcv_export_u8(int dtype, const void* src, int64_t ld, int N, int C, int T, int64_t hw, void* dst, void* stream);
 /* Noise layer (discriminator.py:30-39): out = x + sigma*noise (noise fp32, dense [rows][C]) */
 int dcv_add_noise(int dtype, const void* x, int64_t ldx, const float* noise, float sigma, int64_t rows,
                   int C, void* out, int64_t ldo, void* stream);

@@ -1,0 +1,178 @@
+"""what sits either side of the training step.
+
+f1  eval-mode sampling (util.generate_samples, util.py:251-322) against the oracle's eval-mode forward, including the
+    on-device clip -> uint8 conversion (util.py:74-79);
+f2  raw dataset forms as step inputs: uint8 channels-last frames (`/ 127.5 - 1` on the device, dataset.py:128-131,
+    157-167) and class-index maps (one-hot on the device, dataset.py:177-181) give the same iteration as the float32
+    tensors the reference's dataset builds on the host;
+f3  snapshots: parameter files in the reference's format plus optimizer state, and resuming from them continues the run
+    bit for bit.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import rel_err  # noqa: E402
+from oracle import dcvgan_oracle as orc  # noqa: E402
+from test_nets_gpu import _Logger, _mods, build_models, small_cfg  # noqa: E402
+
+
+def _ops():
+    _mods()
+    from dcvgan_b200 import ops
+    return ops
+
+
+def _np_videos_to_numpy(v):
+    """util.py:74-79 verbatim arithmetic"""
+    v = np.clip(v, -1, 1)
+    v = (v + 1) / 2 * 255
+    return v.astype("uint8")
+
+
+@pytest.mark.parametrize("precision,max_px,mean_px", [("fp32", 1, 0.02), ("bf16", 12, 0.6)])
+@pytest.mark.parametrize("geo", [("depth", 1), ("segmentation", 25)])
+def test_generate_samples_eval_mode_matches_oracle(precision, max_px, mean_px, geo):
+    dcv, _, _, _, _, util, engine = _mods()
+    cfg = small_cfg(geo[0], geo[1], ngf=16)
+    P = orc.init_all(cfg, 31)
+    # running statistics that differ from the initial (0, 1) so that eval-mode BatchNorm is really exercised
+    gen = torch.Generator().manual_seed(2)
+    for net in ("ggen", "cgen"):
+        for k, v in P[net].items():
+            if k.endswith("running_mean"):
+                v.copy_(torch.randn(v.shape, generator=gen) * 0.05)
+            if k.endswith("running_var"):
+                v.copy_(1.0 + torch.rand(v.shape, generator=gen) * 0.5)
+    models = build_models(cfg, P, precision)
+    engine.set_rng_mode("cpu_parity")
+    num, bs = 5, 2
+    torch.manual_seed(21)
+    xg_ref, xc_ref = [], []
+    with torch.no_grad():
+        for _ in range(0, num, bs):
+            xg = orc.ggen_sample_videos(P["ggen"], bs, cfg, False)
+            xc = orc.cgen_forward_videos(P["cgen"], xg, cfg, False)
+            xg_ref.append(np.clip(xg.numpy(), -1, 1))
+            xc_ref.append(_np_videos_to_numpy(xc.numpy()))
+    xg_ref, xc_ref = np.concatenate(xg_ref)[:num], np.concatenate(xc_ref)[:num]
+    torch.manual_seed(21)
+    xg, xc = util.generate_samples(models["ggen"], models["cgen"], num, bs)
+    assert xc.dtype == np.uint8 and xc.shape == (num, 3, 16, 64, 64) and xg.shape == (num, geo[1], 16, 64, 64)
+    assert not models["ggen"].training and not models["cgen"].training          # left in eval mode (util.py:296-297)
+    d = np.abs(xc.astype(np.int32) - xc_ref.astype(np.int32))
+    e_g = rel_err(torch.from_numpy(xg), torch.from_numpy(xg_ref))
+    print(f"generate_samples[{precision},{geo[0]}]: geometry rel err {e_g:.2e}; colour uint8 max |diff| {d.max()} mean {d.mean():.4f}")
+    assert e_g < (1e-3 if precision == "fp32" else 3e-2)
+    if geo[0] == "segmentation" and precision == "bf16":
+        return      # argmax remap of an (almost uniform) softmax flips on bf16 near-ties: colour frames are not comparable pixel-wise
+    assert d.max() <= max_px and d.mean() <= mean_px, (d.max(), d.mean())
+
+
+def test_export_u8_is_numpy_exact():
+    ops = _ops()
+    torch.manual_seed(1)
+    x = (torch.rand(3, 3, 5, 8, 8) * 2.6 - 1.3)                 # values beyond [-1, 1] exercise the clip
+    x[0, 0, 0, 0, :4] = torch.tensor([1.0, -1.0, 0.0, 0.999999])
+    from helpers import to_act
+    a = to_act(x, torch.float32)
+    out = torch.empty((3, 3, 5, 8, 8), dtype=torch.uint8, device="cuda")
+    ops.export_u8(a, out)
+    assert np.array_equal(out.cpu().numpy(), _np_videos_to_numpy(x.numpy()))
+
+
+def test_ingest_kernels_are_numpy_exact():
+    ops = _ops()
+    rng = np.random.RandomState(3)
+    frames = rng.randint(0, 256, size=(2, 4, 8, 8, 3)).astype(np.uint8)             # (B,T,H,W,C) as read from disk
+    ref = frames.astype(np.float32) / 127.5 - 1.0                                    # dataset.py:131
+    a = ops.Act.empty(2, 4, 8, 8, 3, torch.float32)
+    ops.ingest_u8(torch.from_numpy(frames).cuda(), a)
+    assert np.array_equal(a.torch().cpu().numpy(), ref)
+    segm = rng.randint(0, 25, size=(2, 4, 8, 8))
+    ref1 = np.eye(25, dtype=np.float32)[segm]                                        # dataset.py:179
+    for t in (torch.from_numpy(segm.astype(np.uint8)), torch.from_numpy(segm.astype(np.int64))):
+        b = ops.Act.empty(2, 4, 8, 8, 25, torch.bfloat16)
+        ops.ingest_onehot(t.cuda(), b)
+        assert np.array_equal(b.torch().float().cpu().numpy(), ref1)
+        assert float(b.padded_to(b.cp).torch()[..., 25:].float().abs().max()) == 0.0
+
+
+def _trainer(cfg, init, precision, tmp_path):
+    dcv, _, _, loss_mod, trainer_mod, _, engine = _mods()
+    models = build_models(cfg, init, precision)
+    engine.set_rng_mode("cpu_parity")
+    opts = {k: torch.optim.Adam(m.parameters(), lr=cfg[k]["optimizer"]["lr"], betas=(0.5, 0.999),
+                                weight_decay=cfg[k]["optimizer"]["decay"]) for k, m in models.items()}
+    L = loss_mod.AdversarialLoss() if cfg["loss"] == "adversarial-loss" else loss_mod.HingeLoss()
+    trainer_mod.Trainer.save_classobj = lambda self: None
+    return trainer_mod.Trainer(None, _Logger(tmp_path), models, opts, L, dict(cfg, config_path="")), models, opts
+
+
+@pytest.mark.parametrize("geo", [("depth", 1), ("segmentation", 25)])
+def test_raw_dataset_inputs_give_the_same_iteration(geo, tmp_path):
+    """uint8 frames / class-index maps converted on the device == the float32 tensors the reference's dataset makes on the host"""
+    cfg = small_cfg(geo[0], geo[1], "adversarial-loss", noise=False, ngf=8, ndf=8, gdis=False)
+    init = orc.init_all(cfg, 5)
+    init.pop("gdis")
+    B, T = 2, 16
+    rng = np.random.RandomState(11)
+    color_u8 = rng.randint(0, 256, size=(B, T, 64, 64, 3)).astype(np.uint8)
+    color_f = torch.from_numpy((color_u8.astype(np.float32) / 127.5 - 1.0).transpose(0, 4, 1, 2, 3).copy())      # dataset.py:130-131
+    if geo[0] == "depth":
+        geo_raw = rng.randint(0, 256, size=(B, T, 64, 64, 1)).astype(np.uint8)
+        geo_f = torch.from_numpy((geo_raw.astype(np.float32) / 127.5 - 1.0).transpose(0, 4, 1, 2, 3).copy())
+    else:
+        geo_raw = rng.randint(0, 25, size=(B, T, 64, 64)).astype(np.uint8)
+        geo_f = torch.from_numpy(np.eye(25, dtype=np.float32)[geo_raw].transpose(0, 4, 1, 2, 3).copy())          # dataset.py:179-181
+    out = []
+    for xc, xg in ((color_f, geo_f), (torch.from_numpy(color_u8), torch.from_numpy(geo_raw))):
+        tr, models, _ = _trainer(cfg, copy.deepcopy(init), "fp32", tmp_path)
+        torch.manual_seed(8)
+        tr.iteration = 1
+        out.append((tr.train_step(xc.cuda(), xg.cuda(), t_rand=4).cpu(), {k: v.detach().cpu().clone() for k, v in models["vdis"].state_dict().items()}))
+    assert torch.equal(out[0][0], out[1][0]), (out[0][0], out[1][0])
+    for k in out[0][1]:
+        assert torch.equal(out[0][1][k], out[1][1][k]), k
+
+
+def test_snapshot_and_resume_continue_bit_for_bit(tmp_path):
+    cfg = small_cfg("optical-flow", 2, "hinge-loss", noise=True, ngf=8, ndf=8)
+    init = orc.init_all(cfg, 6)
+    batches = [tuple(t.cuda() for t in orc.synthetic_batch(cfg, 2, 60 + i)) for i in range(5)]
+
+    def steps(tr, first, last, seed0):
+        out = []
+        for it in range(first, last + 1):
+            torch.manual_seed(seed0 + it)
+            tr.iteration = it
+            out.append(tr.train_step(*batches[it - 1], t_rand=it).cpu())
+        return out
+
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    tr, models, opts = _trainer(cfg, copy.deepcopy(init), "fp32", tmp_path / "a")
+    steps(tr, 1, 3, 100)
+    tr.epoch = 1
+    tr.save_params()
+    snap = tmp_path / "a" / "models"
+    assert (snap / "optim_00003.pth").exists() and (snap / "ggen_params_00003.pth").exists()
+    st = torch.load(snap / "optim_00003.pth")
+    assert st["iteration"] == 3 and float(st["optimizers"]["ggen"]["state"][0]["step"]) == 6.0       # opt_ggen steps twice per iteration
+    assert float(st["optimizers"]["vdis"]["state"][0]["step"]) == 3.0
+    cont = steps(tr, 4, 5, 100)
+    final = {n: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()} for n, m in models.items()}
+    # fresh process state: new modules / optimizers with DIFFERENT initial weights, everything comes from the snapshot
+    tr2, models2, _ = _trainer(cfg, orc.init_all(cfg, 99), "fp32", tmp_path / "b")
+    tr2.load_snapshot(3, path=snap)
+    assert tr2.iteration == 3 and tr2.epoch == 1
+    cont2 = steps(tr2, 4, 5, 100)
+    for a, b in zip(cont, cont2):
+        assert torch.equal(a, b), (a, b)
+    for n in final:
+        for k, v in final[n].items():
+            assert torch.equal(v, models2[n].state_dict()[k].cpu()), (n, k)

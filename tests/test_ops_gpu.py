@@ -231,7 +231,7 @@ def test_img_conv_direct_kernels(cin, n, hw, slice_out):
     else:
         ya = ops.Act.empty(n, 1, H, W, 64, torch.bfloat16)
     g = spec.geom(n, (1, H, W), xa.cp, ya.cp if not slice_out else 64)
-    assert ops.img_conv_ok(spec, g, xa, ya)
+    assert ops.lib().dcv_img_conv_supported(C.byref(g))
     from dcvgan_b200._lib import ACT_LEAKY
     wdev = w.detach().cuda().contiguous()
     ops.img_conv_fwd(spec, g, xa, wdev, ya, ACT_LEAKY, 0.01)

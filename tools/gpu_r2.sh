@@ -10,7 +10,9 @@ for st in $STAGES; do
     tests)
       timeout 1500 python -m pytest tests -m gpu -x -q -s > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -5 gpurun_out/${TAG}_tests.log;;
     quick)
-      timeout 900 python -m pytest tests -m gpu -x -q -s --deselect tests/test_curves_gpu.py > gpurun_out/${TAG}_tests.log 2>&1; echo "quick tests rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -5 gpurun_out/${TAG}_tests.log;;
+      timeout 1200 python -m pytest tests -m gpu -q -s --deselect tests/test_curves_gpu.py > gpurun_out/${TAG}_tests.log 2>&1; echo "quick tests rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -5 gpurun_out/${TAG}_tests.log;;
+    curves)
+      timeout 1500 python -m pytest tests/test_curves_gpu.py -m gpu -q -s > gpurun_out/${TAG}_curves.log 2>&1; echo "curves rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_curves.log | tail -30;;
     bench)
       timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
     benchfast)
