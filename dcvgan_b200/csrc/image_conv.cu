@@ -1,19 +1,25 @@
-// Direct (CUDA-core, HBM-bound) kernels for the image-side 3x3 convolution of the colour generator:
+// HBM-bound kernels for the image-side 3x3 convolution of the colour generator:
 // `Inconv` = Conv2d(C -> 64, k3, s1, p1, no bias) + LeakyReLU(0.01) with C = 1 (depth) or 2 (optical flow) input
 // channels (reference: src/generator.py:158-176).
 //
-// As an implicit GEMM this layer has K = 9*C <= 18: on the tensor cores it needs its input padded to 16 channels and
-// runs at 14 TFLOP/s (0.167 ms at batch 32) while the HBM time of its 268 MB bf16 output is 0.041 ms.  Here
-//   * forward : one thread = 4 consecutive pixels x 8 output channels; the 9*C weights rows it needs sit in shared
-//               memory as fp32 [tap][ci][co] (read straight from the fp32 master weight - no packing pass), the
-//               18*C input values in registers; output written as 16-byte vectors (128 contiguous bytes per pixel).
-//   * backward: ONE pass over (da, a) produces everything the layer's backward needs - the LeakyReLU derivative is
-//               applied on the fly (no separate act_bwd pass over the 268 MB tensor), the weight gradient is
-//               accumulated in registers per thread (8 output channels x 9*C taps) and reduced per block into fp32
-//               partials, and the data gradient is formed per block from per-pixel partial products
-//               P[pixel][tap][ci] = sum_co dz[pixel][co] * w[co][ci][tap] (8 lanes per pixel, butterfly reduction)
-//               staged in shared memory for a band of 8 rows plus one halo row on each side, then summed over the
-//               nine taps (col2im inside the block).
+// As an implicit GEMM the layer has K = 9*C <= 18.  Through the tcgen05 / TMA path it needs its input padded to 16
+// channels (nine 32-byte-row boxes per tile) and runs at 14 TFLOP/s: 0.167 ms at batch 32 where the HBM time of its
+// 268 MB bf16 output is 0.041 ms; its backward took three passes over that tensor (act_bwd, wgrad, dgrad: 0.42 ms).
+// A first CUDA-core version of these kernels was instruction-bound (0.165 / 0.83 ms, profiles/r2a_layers.md).  Here the
+// arithmetic runs on warp-level mma.sync (m16n8k16, bf16 -> fp32), whose operands are assembled IN REGISTERS from
+// plain coalesced loads - the tiny K makes TMA / shared-memory operand staging pure overhead - so the kernels are
+// bound by the bytes of the big tensor they stream:
+//   * forward : one warp = 16 consecutive pixels x 64 channels per step.  A fragments (im2col rows) are gathered from a
+//               bf16 copy of the input window in shared memory, B fragments (the 9*C x 64 weight matrix, bf16-rounded
+//               from the fp32 master weight) live in registers for the whole kernel; the result is staged through a
+//               warp-private shared-memory tile so that global stores are 16-byte vectors covering full 128-byte rows.
+//   * backward: ONE pass over (da, a).  dz = da * LeakyReLU'(a) is formed in registers directly in mma A-fragment layout
+//               (the K permutation of a per-thread 2 x 16-byte load is applied to the B operand instead), used as
+//                 - A of  P[pixel][tap,ci] = sum_co dz[pixel][co] * w[co][ci][tap]   (data-gradient partial products),
+//                 - after a movmatrix transpose, A of  dW^T[co][tap,ci] += sum_pixel dz[pixel][co] * x[pixel + tap][ci],
+//               P is staged in shared memory for a band of 8 rows + 1 halo row each side and summed over the nine taps
+//               (col2im inside the block); dW is accumulated per warp in 32 registers, reduced per block, and the
+//               per-block partials are summed in a fixed order by wgrad_reduce.
 // Algorithmic bytes: forward 2 B/output element (+ the tiny input); backward 4 B/output element (da and a read once).
 #include "common.cuh"
 #include "conv_geom.cuh"
@@ -23,227 +29,249 @@ namespace dcv {
 int wgrad_reduce(const float* partial, int splits, const dcv_geom* g, float* dw, int64_t s_l, int64_t s_s,
                  int64_t s_tap, int accumulate, cudaStream_t s);
 
-constexpr int IMG_CO = 64;          // output channels (8 lanes x 8)
-constexpr int IMG_PX = 4;           // consecutive pixels per thread
-constexpr int IMG_BAND = 8;         // rows per block in the backward kernel
+constexpr int IMG_CO = 64;          // output channels
+constexpr int IMG_BAND = 8;         // image rows per block
+constexpr int IMG_WARPS = 8;
 
-__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
-  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(u[i] << 16); f[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  uint32_t u[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]); u[i] = *reinterpret_cast<uint32_t*>(&h); }
-  return make_uint4(u[0], u[1], u[2], u[3]);
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// D(16x8, f32) += A(16x16, bf16, row) * B(16x8, bf16, col).  Fragment layout (g = lane / 4, q = lane % 4):
+//   a0 = A[g][2q,2q+1]  a1 = A[g+8][2q,2q+1]  a2 = A[g][2q+8,2q+9]  a3 = A[g+8][2q+8,2q+9]
+//   b0 = B[2q,2q+1][g]  b1 = B[2q+8,2q+9][g]      d0,d1 = D[g][2q,2q+1]  d2,d3 = D[g+8][2q,2q+1]
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// transpose of an 8x8 b16 matrix held one 32-bit register per thread (row g, columns 2q, 2q+1)
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
 }
 
-// fp32 master weight w[co*s_s + ci*s_l + tap] -> shared [tap*C + ci][co]
+// input window of one band in shared memory: rows r0-1 .. r0+BAND, columns -1 .. W, C channels, zero outside the image
 template <int C>
-__device__ __forceinline__ void load_weights(float* ws, const float* __restrict__ w, int64_t s_l, int64_t s_s) {
-  for (int i = threadIdx.x; i < 9 * C * IMG_CO; i += blockDim.x) {
-    const int co = i % IMG_CO, tc = i / IMG_CO, tap = tc / C, ci = tc % C;
-    ws[i] = w[co * s_s + ci * s_l + tap];
+__device__ __forceinline__ void stage_window(__nv_bfloat16* xs, const __nv_bfloat16* __restrict__ x, int64_t ldx, int n, int r0,
+                                             int H, int W) {
+  const int WP = W + 2;
+  for (int i = threadIdx.x; i < (IMG_BAND + 2) * WP; i += blockDim.x) {
+    const int lr = i / WP, lc = i % WP;
+    const int h = r0 - 1 + lr, w = lc - 1;
+    const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+    const __nv_bfloat16* p = x + ((int64_t)(n * H + h) * W + w) * ldx;
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) xs[i * C + ci] = ok ? p[ci] : __float2bfloat16_rn(0.f);
   }
 }
-
-// the 3 x 6 x C input window of a group of 4 pixels (zero outside the image)
+// element k = tap * C + ci of the im2col row of pixel (lr, w) (lr: band-local row, window row lr + 1 is the pixel's own row)
 template <int C>
-__device__ __forceinline__ void load_window(const __nv_bfloat16* __restrict__ x, int64_t ldx, int n, int h, int w0, int H, int W,
-                                            float (&xin)[3][IMG_PX + 2][C]) {
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int hh = h + dy - 1;
-#pragma unroll
-    for (int dx = 0; dx < IMG_PX + 2; ++dx) {
-      const int ww = w0 + dx - 1;
-      const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-      const __nv_bfloat16* p = x + ((int64_t)(n * H + hh) * W + ww) * ldx;
-      if (C == 2) {
-        uint32_t v = ok ? *reinterpret_cast<const uint32_t*>(p) : 0u;
-        xin[dy][dx][0] = __uint_as_float(v << 16);
-        xin[dy][dx][C - 1] = __uint_as_float(v & 0xFFFF0000u);
-      } else {
-#pragma unroll
-        for (int ci = 0; ci < C; ++ci) xin[dy][dx][ci] = ok ? __bfloat162float(p[ci]) : 0.f;
-      }
-    }
-  }
+__device__ __forceinline__ uint16_t im2col_at(const __nv_bfloat16* xs, int WP, int lr, int w, int k) {
+  if (k >= 9 * C) return 0;
+  const int tap = k / C, ci = k % C;
+  const int dy = tap / 3, dx = tap % 3;
+  return reinterpret_cast<const uint16_t*>(xs)[((lr + dy) * WP + (w + dx)) * C + ci];
 }
 
+// ------------------------------------------------------------------------------------------ forward
 template <int C>
 __global__ void __launch_bounds__(256)
 img_conv3x3_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t s_l, int64_t s_s,
                        int N, int H, int W, __nv_bfloat16* __restrict__ y, int64_t ldy, int act, float slope) {
-  __shared__ __align__(16) float ws[9 * C * IMG_CO];
-  load_weights<C>(ws, w, s_l, s_s);
-  __syncthreads();
-  const int cg = threadIdx.x % 8, pg = threadIdx.x / 8;
-  const int gpr = W / IMG_PX;
-  const int64_t groups = (int64_t)N * H * gpr;
-  const int64_t gid = (int64_t)blockIdx.x * 32 + pg;
-  if (gid >= groups) return;
-  const int w0 = (int)(gid % gpr) * IMG_PX;
-  const int64_t row = gid / gpr;
-  const int h = (int)(row % H), n = (int)(row / H);
-  float xin[3][IMG_PX + 2][C];
-  load_window<C>(x, ldx, n, h, w0, H, W, xin);
-  float acc[IMG_PX][8];
+  constexpr int KS = (9 * C + 15) / 16;                        // k16 steps
+  __shared__ __align__(16) __nv_bfloat16 xs[(IMG_BAND + 2) * 66 * C];
+  __shared__ __align__(16) uint32_t stg[IMG_WARPS][16][36];     // warp-private 16 x 64 bf16 tile, 144-byte row pitch
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, g = lane / 4, q = lane % 4;
+  const int bands = H / IMG_BAND;
+  const int n = blockIdx.x / bands, r0 = (blockIdx.x % bands) * IMG_BAND;
+  const int WP = W + 2;
+  stage_window<C>(xs, x, ldx, n, r0, H, W);
+  // B fragments: B[k][co] = w[co][ci][tap] (k = tap*C + ci), bf16
+  uint32_t bw[KS][8][2];
 #pragma unroll
-  for (int j = 0; j < IMG_PX; ++j)
+  for (int s = 0; s < KS; ++s)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+      for (int h = 0; h < 2; ++h) {
+        float v[2];
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-      for (int ci = 0; ci < C; ++ci) {
-        const float4* wp = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * C + ci) * IMG_CO + cg * 8);
-        const float4 wa = wp[0], wb = wp[1];
-        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-        for (int j = 0; j < IMG_PX; ++j) {
-          const float xv = xin[ky][j + kx][ci];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(xv, wv[k], acc[j][k]);
+        for (int e = 0; e < 2; ++e) {
+          const int k = 16 * s + 2 * q + 8 * h + e;
+          v[e] = k < 9 * C ? w[(8 * j + g) * s_s + (k % C) * s_l + (k / C)] : 0.f;
         }
+        bw[s][j][h] = pack_bf16x2(v[0], v[1]);
       }
+  __syncthreads();
+  const int tiles_w = W / 16, tiles = IMG_BAND * tiles_w;
+  for (int t = warp; t < tiles; t += IMG_WARPS) {
+    const int lr = t / tiles_w, w0 = (t % tiles_w) * 16;
+    float acc[8][4];
 #pragma unroll
-  for (int j = 0; j < IMG_PX; ++j) {
-    float o[8];
+    for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = apply_act(acc[j][k], act, slope);
-    *reinterpret_cast<uint4*>(y + ((int64_t)(n * H + h) * W + w0 + j) * ldy + cg * 8) = pack8(o);
+    for (int s = 0; s < KS; ++s) {
+      uint32_t a[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)              // column half (k, k + 8)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {       // row half (g, g + 8)
+          const int k = 16 * s + 2 * q + 8 * h;
+          const uint32_t lo = im2col_at<C>(xs, WP, lr, w0 + g + 8 * rr, k), hi = im2col_at<C>(xs, WP, lr, w0 + g + 8 * rr, k + 1);
+          a[2 * h + rr] = lo | (hi << 16);
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mma16816(acc[j], a[0], a[1], a[2], a[3], bw[s][j][0], bw[s][j][1]);
+    }
+    // activation, bf16, warp-private staging (conflict-free: bank = 4 * row + 4 * j + q), then 16-byte global stores
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      stg[warp][g][4 * j + q] = pack_bf16x2(apply_act(acc[j][0], act, slope), apply_act(acc[j][1], act, slope));
+      stg[warp][g + 8][4 * j + q] = pack_bf16x2(apply_act(acc[j][2], act, slope), apply_act(acc[j][3], act, slope));
+    }
+    __syncwarp();
+    const int64_t pix0 = (int64_t)(n * H + r0 + lr) * W + w0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = 4 * i + lane / 8, chunk = lane % 8;
+      const uint4 v = *reinterpret_cast<const uint4*>(&stg[warp][row][4 * chunk]);
+      *reinterpret_cast<uint4*>(y + (pix0 + row) * ldy + 8 * chunk) = v;
+    }
+    __syncwarp();
   }
 }
 
-// total over the 8 lanes of an aligned lane group: lane l (0..7) returns the group total of v[l]   (7 shuffles)
-__device__ __forceinline__ float butterfly8(const float (&v)[8], int l) {
-  float t[4], u[2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float keep = (l & 4) ? v[i + 4] : v[i], send = (l & 4) ? v[i] : v[i + 4];
-    t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float keep = (l & 2) ? t[i + 2] : t[i], send = (l & 2) ? t[i] : t[i + 2];
-    u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  const float keep = (l & 1) ? u[1] : u[0], send = (l & 1) ? u[0] : u[1];
-  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-}
-__device__ __forceinline__ float group8_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  return v;
+// ------------------------------------------------------------------------------------------ backward
+// channel that K slot sigma (0..15) of k16 step s carries: thread q loads channels 8q..8q+7 and 32+8q..32+8q+7 of a pixel
+// (two 16-byte loads, 64 contiguous bytes per row and instruction across the quad) and feeds value i = 4s + 2h + e into
+// slot 2q + 8h + e
+__device__ __forceinline__ int slot_channel(int s, int sigma) {
+  const int qq = (sigma % 8) / 2, e = sigma % 2, h = sigma / 8;
+  const int i = 4 * s + 2 * h + e;
+  return i < 8 ? 8 * qq + i : 32 + 8 * qq + (i - 8);
 }
 
-// One block = one image x one band of IMG_BAND rows (+ one halo row above and below for the data gradient).
-// da: gradient w.r.t. the activated output, a: the activated output (its sign gives the LeakyReLU derivative; act NONE:
-// dz = da), x: the layer input.  partial: [gridDim.x][9*C][64] fp32 weight-gradient partial sums.  dx: data gradient
-// (C real channels at pixel stride lddx) or NULL.
 template <int C>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256)
 img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const __nv_bfloat16* __restrict__ a, int64_t lda,
                        const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t s_l, int64_t s_s,
                        int N, int H, int W, int act, float slope, float* __restrict__ partial, __nv_bfloat16* __restrict__ dx,
                        int64_t lddx) {
-  extern __shared__ __align__(16) float sm[];
-  constexpr int NT = 9 * C;                              // (tap, ci) pairs
-  float* ws = sm;                                        // [NT][64]
-  float* P = sm + NT * IMG_CO;                           // [(BAND+2) * W][NT]   (re-used as the wgrad reduction buffer)
-  load_weights<C>(ws, w, s_l, s_s);
-  __syncthreads();
-  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
-  const int cg = threadIdx.x % 8, pg = threadIdx.x / 8;
+  constexpr int NT = 9 * C;                    // (tap, ci) pairs
+  constexpr int NJ = (NT + 7) / 8;             // n8 tiles over them
+  constexpr int NP = NJ * 8;                   // padded row length of P
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  float* Ps = reinterpret_cast<float*>(sm_raw);                                  // [(BAND+2) * W][NP]; later [8 warps][NP][64]
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(Ps + (size_t)(IMG_BAND + 2) * W * NP);
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, g = lane / 4, q = lane % 4;
   const int bands = H / IMG_BAND;
   const int n = blockIdx.x / bands, r0 = (blockIdx.x % bands) * IMG_BAND;
-  const int gpr = W / IMG_PX;
-  const int ngroups = (IMG_BAND + 2) * gpr;
-  float acc[NT][8];
+  const int WP = W + 2;
+  stage_window<C>(xs, x, ldx, n, r0, H, W);
+  // B fragments of the data-gradient GEMM: B[k slot][nn] = w[co(s, slot)][ci][tap], nn = tap*C + ci (0 beyond 9*C)
+  uint32_t bw[4][NJ][2];
 #pragma unroll
-  for (int i = 0; i < NT; ++i)
+  for (int s = 0; s < 4; ++s)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[2];
+        const int nn = 8 * j + g;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int co = slot_channel(s, 2 * q + 8 * h + e);
+          v[e] = nn < NT ? w[co * s_s + (nn % C) * s_l + (nn / C)] : 0.f;
+        }
+        bw[s][j][h] = pack_bf16x2(v[0], v[1]);
+      }
+  float acc[4][NJ][4];                         // dW^T: m tile s (16 channels), n tile j (8 (tap, ci) pairs)
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { acc[s][j][0] = acc[s][j][1] = acc[s][j][2] = acc[s][j][3] = 0.f; }
+  __syncthreads();
 
-  for (int g0 = 0; g0 < ngroups; g0 += 32) {             // warp-uniform trip count (the shuffles below need every lane)
-    const int g = g0 + pg;
-    const int prow = g / gpr;                            // row inside the P tile: 0 = halo above the band
-    const int h = r0 - 1 + prow, w0 = (g % gpr) * IMG_PX;
-    const bool live = g < ngroups && h >= 0 && h < H;
-    const bool inband = live && prow >= 1 && prow <= IMG_BAND;
-    float dz[IMG_PX][8];
+  const int tiles_w = W / 16, tiles = (IMG_BAND + 2) * tiles_w;
+  for (int t = warp; t < tiles; t += IMG_WARPS) {
+    const int prow = t / tiles_w, w0 = (t % tiles_w) * 16;       // prow 0 / BAND+1 = halo rows
+    const int h = r0 - 1 + prow;
+    const bool live = h >= 0 && h < H;                            // warp-uniform
+    const bool inband = prow >= 1 && prow <= IMG_BAND;
+    // dz in A-fragment layout: reg[s][0] rows g (slots 2q,2q+1), [s][1] rows g+8, [s][2] rows g (slots 2q+8,+9), [s][3] rows g+8
+    uint32_t dzr[4][4];
+    if (live) {
 #pragma unroll
-    for (int j = 0; j < IMG_PX; ++j) {
-      uint4 qd = make_uint4(0, 0, 0, 0), qa = make_uint4(0, 0, 0, 0);
-      if (live) {
-        const int64_t pix = (int64_t)(n * H + h) * W + w0 + j;
-        qd = *reinterpret_cast<const uint4*>(da + pix * ldda + cg * 8);
-        if (act != DCV_ACT_NONE) qa = *reinterpret_cast<const uint4*>(a + pix * lda + cg * 8);
-      }
-      float fa[8];
-      unpack8(qd, dz[j]);
-      unpack8(qa, fa);
-      if (act != DCV_ACT_NONE) {
+      for (int rr = 0; rr < 2; ++rr) {
+        const int64_t pix = (int64_t)(n * H + h) * W + w0 + g + 8 * rr;
+        uint4 d[2], o[2];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) dz[j][k] *= act_grad_from_out(fa[k], act, slope);
+        for (int half = 0; half < 2; ++half) {
+          d[half] = *reinterpret_cast<const uint4*>(da + pix * ldda + 32 * half + 8 * q);
+          if (act != DCV_ACT_NONE) o[half] = *reinterpret_cast<const uint4*>(a + pix * lda + 32 * half + 8 * q);
+        }
+        const uint32_t dw_[8] = {d[0].x, d[0].y, d[0].z, d[0].w, d[1].x, d[1].y, d[1].z, d[1].w};
+        const uint32_t ow_[8] = {o[0].x, o[0].y, o[0].z, o[0].w, o[1].x, o[1].y, o[1].z, o[1].w};
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {          // value pair i = 2p, 2p+1  ->  step s = p / 2, column half = p % 2
+          uint32_t v = dw_[p];
+          if (act != DCV_ACT_NONE) {
+            const float g0 = act_grad_from_out(bf16_lo(ow_[p]), act, slope), g1 = act_grad_from_out(bf16_hi(ow_[p]), act, slope);
+            v = pack_bf16x2(bf16_lo(v) * g0, bf16_hi(v) * g1);
+          }
+          dzr[p / 2][2 * (p % 2) + rr] = v;
+        }
       }
+    } else {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) { dzr[s][0] = dzr[s][1] = dzr[s][2] = dzr[s][3] = 0u; }
     }
-    // ---- data gradient: per-pixel partial products, reduced over the 8 lanes that share the pixel
+    // ---- data gradient partial products P[pixel][nn]
     if (dx != nullptr) {
+      float pacc[NJ][4];
 #pragma unroll
-      for (int j = 0; j < IMG_PX; ++j) {
-        float part[NT];
+      for (int j = 0; j < NJ; ++j) { pacc[j][0] = pacc[j][1] = pacc[j][2] = pacc[j][3] = 0.f; }
 #pragma unroll
-        for (int i = 0; i < NT; ++i) {
-          const float4* wp = reinterpret_cast<const float4*>(ws + i * IMG_CO + cg * 8);
-          const float4 wa = wp[0], wb = wp[1];
-          part[i] = dz[j][0] * wa.x + dz[j][1] * wa.y + dz[j][2] * wa.z + dz[j][3] * wa.w + dz[j][4] * wb.x + dz[j][5] * wb.y +
-                    dz[j][6] * wb.z + dz[j][7] * wb.w;
-        }
-        float* prow_p = P + (size_t)(prow * W + w0 + j) * NT;
+      for (int s = 0; s < 4; ++s)
 #pragma unroll
-        for (int b = 0; b + 8 <= NT; b += 8) {
-          float v8[8];
+        for (int j = 0; j < NJ; ++j) mma16816(pacc[j], dzr[s][0], dzr[s][1], dzr[s][2], dzr[s][3], bw[s][j][0], bw[s][j][1]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v8[i] = part[b + i];
-          const float tot = butterfly8(v8, cg);
-          if (g < ngroups) prow_p[b + cg] = tot;
-        }
-#pragma unroll
-        for (int i = NT / 8 * 8; i < NT; ++i) {
-          const float tot = group8_sum(part[i]);
-          if (cg == 0 && g < ngroups) prow_p[i] = tot;
-        }
+      for (int j = 0; j < NJ; ++j) {
+        *reinterpret_cast<float2*>(Ps + (size_t)(prow * W + w0 + g) * NP + 8 * j + 2 * q) = make_float2(pacc[j][0], pacc[j][1]);
+        *reinterpret_cast<float2*>(Ps + (size_t)(prow * W + w0 + g + 8) * NP + 8 * j + 2 * q) = make_float2(pacc[j][2], pacc[j][3]);
       }
     }
-    // ---- weight gradient: rows of the band only
-    if (inband) {
-      float xin[3][IMG_PX + 2][C];
-      load_window<C>(x, ldx, n, h, w0, H, W, xin);
+    // ---- weight gradient: dW^T[co][nn] += dz^T[co][pixel] * X[pixel][nn]   (K = the 16 pixels of the tile)
+    if (inband && live && partial != nullptr) {
+      uint32_t xb[NJ][2];                       // B[k = pixel 2q+e (+8)][nn = 8j + g]
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+      for (int j = 0; j < NJ; ++j)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
+        for (int hh = 0; hh < 2; ++hh) {
+          const int nn = 8 * j + g;
+          const uint32_t lo = im2col_at<C>(xs, WP, prow - 1, w0 + 2 * q + 8 * hh, nn), hi = im2col_at<C>(xs, WP, prow - 1, w0 + 2 * q + 8 * hh + 1, nn);
+          xb[j][hh] = lo | (hi << 16);
+        }
 #pragma unroll
-          for (int ci = 0; ci < C; ++ci)
+      for (int s = 0; s < 4; ++s) {
+        // transposed 8x8 blocks: [s][0] = (pixels 0-7, slots 0-7), [1] = (pixels 8-15, slots 0-7), [2] = (0-7, 8-15), [3] = (8-15, 8-15)
+        const uint32_t t0 = movmatrix_trans(dzr[s][0]), t1 = movmatrix_trans(dzr[s][1]);
+        const uint32_t t2 = movmatrix_trans(dzr[s][2]), t3 = movmatrix_trans(dzr[s][3]);
+        // A of the m tile: rows 0-7 = slots 0-7, rows 8-15 = slots 8-15; k 0-7 = pixels 0-7, k 8-15 = pixels 8-15
 #pragma unroll
-            for (int j = 0; j < IMG_PX; ++j) {
-              const float xv = xin[ky][j + kx][ci];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) acc[(ky * 3 + kx) * C + ci][k] = fmaf(xv, dz[j][k], acc[(ky * 3 + kx) * C + ci][k]);
-            }
+        for (int j = 0; j < NJ; ++j) mma16816(acc[s][j], t0, t2, t1, t3, xb[j][0], xb[j][1]);
+      }
     }
   }
   __syncthreads();
   // ---- data gradient of the band: dx[h][w][ci] = sum_taps P[h - ky + 1][w - kx + 1][tap][ci]
   if (dx != nullptr) {
     for (int p = threadIdx.x; p < IMG_BAND * W; p += blockDim.x) {
-      const int hb = p / W, wq = p % W;                  // band-local row, column
+      const int hb = p / W, wq = p % W;
       float s[C];
 #pragma unroll
       for (int ci = 0; ci < C; ++ci) s[ci] = 0.f;
@@ -251,34 +279,36 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int pr = hb + 1 - (ky - 1), pc = wq - (kx - 1);   // P row (tile-local: band row hb is P row hb + 1), column
+          const int pr = hb + 2 - ky, pc = wq + 1 - kx;          // P row (tile-local: band row hb is P row hb + 1), column
           if (pc < 0 || pc >= W) continue;
-          const float* q = P + (size_t)(pr * W + pc) * NT + (ky * 3 + kx) * C;
+          const float* qp = Ps + (size_t)(pr * W + pc) * NP + (ky * 3 + kx) * C;
 #pragma unroll
-          for (int ci = 0; ci < C; ++ci) s[ci] += q[ci];
+          for (int ci = 0; ci < C; ++ci) s[ci] += qp[ci];
         }
       __nv_bfloat16* d = dx + ((int64_t)(n * H + r0 + hb) * W + wq) * lddx;
 #pragma unroll
       for (int ci = 0; ci < C; ++ci) d[ci] = __float2bfloat16_rn(s[ci]);
     }
-    __syncthreads();
   }
-  // ---- weight gradient: sum over the 4 pixel groups of a warp (lanes l, l^8, l^16), then over the 8 warps through smem
-  float* red = P;                                        // [8 warps][NT][64]
+  if (partial == nullptr) return;
+  __syncthreads();
+  // ---- weight gradient: per-warp accumulators -> shared [warp][nn][co] -> fixed-order sum over the warps
+  float* red = Ps;
 #pragma unroll
-  for (int i = 0; i < NT; ++i)
+  for (int s = 0; s < 4; ++s)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float v = acc[i][k];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (lane < 8) red[(warp * NT + i) * IMG_CO + cg * 8 + k] = v;
-    }
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int co = slot_channel(s, g + 8 * rr);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) red[((size_t)warp * NP + 8 * j + 2 * q + e) * IMG_CO + co] = acc[s][j][2 * rr + e];
+      }
   __syncthreads();
   for (int i = threadIdx.x; i < NT * IMG_CO; i += blockDim.x) {
     float s = 0.f;
 #pragma unroll
-    for (int wq = 0; wq < 8; ++wq) s += red[wq * NT * IMG_CO + i];
+    for (int wq = 0; wq < IMG_WARPS; ++wq) s += red[(size_t)wq * NP * IMG_CO + i];
     partial[(size_t)blockIdx.x * NT * IMG_CO + i] = s;
   }
 }
@@ -290,14 +320,14 @@ int img_conv_supported(const dcv_geom* g) {
   if (g->kt != 1 || g->kh != 3 || g->kw != 3 || g->st != 1 || g->sh != 1 || g->sw != 1 || g->pt != 0 || g->ph != 1 || g->pw != 1) return 0;
   if (g->Tl != 1 || g->Ts != 1 || g->Hl != g->Hs || g->Wl != g->Ws) return 0;
   if (wcl < 1 || wcl > 2 || wcs != IMG_CO || g->Cs != IMG_CO) return 0;
-  if (g->Wl % IMG_PX || g->Hl % IMG_BAND || g->Wl > 64) return 0;
+  if (g->Wl % 16 || g->Hl % IMG_BAND || g->Wl > 64) return 0;
   return 1;
 }
 
 static int bwd_smem_bytes(int C, int W) {
-  const int nt = 9 * C;
-  int tile = (IMG_BAND + 2) * W * nt, red = 8 * nt * IMG_CO;
-  return (nt * IMG_CO + (tile > red ? tile : red)) * (int)sizeof(float);
+  const int np = (9 * C + 7) / 8 * 8;
+  int tile = (IMG_BAND + 2) * W * np, red = IMG_WARPS * np * IMG_CO;
+  return (tile > red ? tile : red) * (int)sizeof(float) + (IMG_BAND + 2) * (W + 2) * C * 2 + 16;
 }
 
 int img_conv_bwd_blocks(const dcv_geom* g) { return g->N * (g->Hl / IMG_BAND); }
@@ -313,9 +343,7 @@ int img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, 
   DCV_REQUIRE(s_tap == 1, "img_conv_fwd: taps of the master weight must be contiguous");
   DCV_REQUIRE((((uintptr_t)y) & 15) == 0 && ldy % 8 == 0, "img_conv_fwd: output must be 16-byte aligned");
   const int C = g->wCl > 0 ? g->wCl : g->Cl;
-  DCV_REQUIRE(C == 1 || ((((uintptr_t)x) & 3) == 0 && ldx % 2 == 0), "img_conv_fwd: 2-channel input must be 4-byte aligned");
-  const int64_t groups = (int64_t)g->N * g->Hl * (g->Wl / IMG_PX);
-  const unsigned blocks = (unsigned)((groups + 31) / 32);
+  const unsigned blocks = (unsigned)img_conv_bwd_blocks(g);
   if (C == 1)
     img_conv3x3_fwd_kernel<1><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, (__nv_bfloat16*)y, ldy, act, slope);
   else
@@ -329,21 +357,21 @@ int img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a,
   DCV_REQUIRE(img_conv_supported(g), "img_conv_bwd: geometry not supported");
   DCV_REQUIRE(s_tap == 1, "img_conv_bwd: taps of the master weight must be contiguous");
   DCV_REQUIRE(act == DCV_ACT_NONE || act == DCV_ACT_LEAKY, "img_conv_bwd: activation %d", act);
-  DCV_REQUIRE(ws_bytes >= img_conv_bwd_ws_bytes(g), "img_conv_bwd: workspace too small");
+  DCV_REQUIRE(!dw || ws_bytes >= img_conv_bwd_ws_bytes(g), "img_conv_bwd: workspace too small");
   DCV_REQUIRE((((uintptr_t)da) & 15) == 0 && ldda % 8 == 0 && (((uintptr_t)a) & 15) == 0 && lda % 8 == 0, "img_conv_bwd: da / a must be 16-byte aligned");
   const int C = g->wCl > 0 ? g->wCl : g->Cl;
-  DCV_REQUIRE(C == 1 || ((((uintptr_t)x) & 3) == 0 && ldx % 2 == 0), "img_conv_bwd: 2-channel input must be 4-byte aligned");
   const int blocks = img_conv_bwd_blocks(g);
   const int smem = bwd_smem_bytes(C, g->Wl);
+  float* partial = dw ? (float*)ws : nullptr;
   static int smem_set[3] = {0, 0, 0};
   if (C == 1) {
     if (smem > smem_set[1]) { DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); smem_set[1] = smem; }
     img_conv3x3_bwd_kernel<1><<<blocks, 256, smem, s>>>((const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)x, ldx,
-                                                       w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, (float*)ws, (__nv_bfloat16*)dx, lddx);
+                                                       w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx);
   } else {
     if (smem > smem_set[2]) { DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); smem_set[2] = smem; }
     img_conv3x3_bwd_kernel<2><<<blocks, 256, smem, s>>>((const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)x, ldx,
-                                                       w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, (float*)ws, (__nv_bfloat16*)dx, lddx);
+                                                       w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx);
   }
   if (int rc = check_launch("img_conv3x3_bwd")) return rc;
   if (!dw) return 0;

@@ -1431,7 +1431,8 @@ static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   const int64_t tiles = (int64_t)ceil_div(tiles_total, p->G) * ceil_div(p->blocksB_total, p->nbB);
   // the ring takes the whole shared memory, so exactly one CTA is resident per SM: aim for ONE wave of <= 148 CTAs
   // (a second wave only adds a second non-overlapped epilogue and doubles the partial sums that have to be reduced)
-  int64_t sp = tiles >= 148 ? 1 : 148 / tiles;
+  const int sms = 148 - g_tune.sm_reserve > 8 ? 148 - g_tune.sm_reserve : 8;   // sm_reserve: SMs left to a collective
+  int64_t sp = tiles >= sms ? 1 : sms / tiles;
   if (g_tune.wgrad_waves > 0) sp *= g_tune.wgrad_waves;
   const int64_t maxs = (p->ptiles_total + 7) / 8;
   if (sp > maxs) sp = maxs;

@@ -236,6 +236,7 @@ class Trainer(object):
         self._pending = []          # device-side loss records waiting for the next log flush
         self._zero_pool = ops.ZeroPool() if os.environ.get("DCV_NO_ZERO_POOL", "0") != "1" else None
         self._reducer = GradReducer()
+        self._sm_reserved = False
         self._copy_stream = None
         self.on_log_samples = None  # optional hooks for the (out-of-scope) visual logging / IS-FID evaluation
         self.on_evaluate = None
@@ -343,20 +344,30 @@ class Trainer(object):
         dp_allreduce_grads([self._flat[n] for n in names])
 
     def _reduce_launch(self, name):
-        """enqueue the all-reduce of one network's gradient bucket behind the kernels issued so far (overlaps what follows)"""
+        """enqueue the all-reduce of one network's gradient bucket behind the kernels issued so far.
+
+        Default (DCV_DP_OVERLAP unset or 1): the bucket is reduced on a communication stream while the compute stream goes
+        on with the next network's backward, and - this is what makes the overlap real - the persistent convolution and
+        weight-gradient kernels launched until the matching wait leave `DCV_DP_SM_RESERVE` SMs (default 8) free: with
+        one ~220 KB CTA per SM on all 148 SMs NCCL's CTAs only got an SM between two kernels and the side stream
+        measured SLOWER than reducing in-stream (round 1: 12.03 vs 11.92 ms on 8 GPUs, profiles/r1m_bench_8gpu_*.json).
+        DCV_DP_OVERLAP=0 selects the in-stream form."""
         if self.world > 1:
-            # Measured on 8 B200s (profiles/r1m_bench_8gpu_*.json): 11.92 ms/step with the bucket reduced in-stream right
-            # here, 12.03 ms with the side-stream overlap - the persistent convolution kernels hold every SM (one CTA with
-            # ~220 KB of shared memory each), so NCCL's CTAs only get an SM between two of them and the "overlap" mostly
-            # delays both.  The in-stream form is therefore the default; DCV_DP_OVERLAP=1 selects the side stream.
-            if os.environ.get("DCV_DP_OVERLAP", "0") == "1":
+            if os.environ.get("DCV_DP_OVERLAP", "1") == "1":
                 self._reducer.launch(self._flat[name])
+                k = int(os.environ.get("DCV_DP_SM_RESERVE", "8"))
+                if k > 0 and not self._sm_reserved:
+                    _lib.check(_lib.lib().dcv_set_tuning(b"sm_reserve", k))
+                    self._sm_reserved = True
             else:
                 self._allreduce([name])
 
     def _reduce_wait(self):
         if self.world > 1:
             self._reducer.wait()
+            if self._sm_reserved:
+                _lib.check(_lib.lib().dcv_set_tuning(b"sm_reserve", 0))
+                self._sm_reserved = False
 
     def _to_clip(self, x, channels=None):
         """Real batch -> channels-last Act (B,T,H,W,C).  Accepted forms:
@@ -576,16 +587,20 @@ class Trainer(object):
                 self._plans[n].backward(real[n][1], grads[n][0], sink, need_dx=False)
                 self._plans[n].backward(fake[n][1], grads[n][1], sink, need_dx=False)
                 self._reduce_launch(n)                  # this network's bucket travels while the next one's backward runs
-            self._reduce_wait()
-            for n in self._dnames:
-                self._flat[n].adam_step(1.0 / self.world)
         del real, fake, grads
 
         # ---------------- generator phase (trainer.py:338-368)
         ggen.train()
         cgen.train()
         upd_g = self.iteration % cfg["num_dis_update"] == 0                                     # sic, trainer.py:355
+        # The generators' forward pass does not read the discriminators: it runs BEFORE the discriminators' Adam steps so
+        # that their gradient buckets cross NVLink underneath it (data-parallel runs); the values are those of the
+        # reference's order (opt_*dis.step() consume no random numbers and do not touch the generators).
         xg_f, xc_f, gctx, cctx = self._generate(B, True, True, save=upd_g)
+        if upd_d:
+            self._reduce_wait()
+            for n in self._dnames:
+                self._flat[n].adam_step(1.0 / self.world)
         xg_clip, xc_clip = xg_f.reshape_nt(B, T), xc_f.reshape_nt(B, T)
         fake = self._dis_forward(xg_clip, xc_clip, t_rand, upd_g)
         gen_terms = ["idis", "vdis"] + (["gdis"] if (self.use_gdis and L.gen_uses_gdis) else [])

@@ -20,7 +20,7 @@ sys.path.insert(0, str(ROOT))
 from oracle import dcvgan_oracle as orc  # noqa: E402
 from tools import ref_harness as rh  # noqa: E402
 
-STEPS, SEEDS = 200, (0, 1, 2, 3)
+STEPS, SEEDS = 200, tuple(range(12))
 O = {"lr": 0.0002, "decay": 0.00001}
 CFG = {"batchsize": 4, "video_length": 16, "image_size": 64, "geometric_info": {"name": "optical-flow", "channel": 2},
        "loss": "hinge-loss", "num_gen_update": 1, "num_dis_update": 1, "n_epochs": 1, "seed": 0,
@@ -53,8 +53,15 @@ def run_seed(ref, s):
 if __name__ == "__main__":
     torch.set_num_threads(int(sys.argv[1]) if len(sys.argv) > 1 else 8)
     ref = rh.import_reference()
+    path = ROOT / "tests" / "golden" / "curves_flow_hinge.json"
     out = {"cfg": CFG, "steps": STEPS, "torch": torch.__version__, "seeds": {}}
+    if path.exists():                    # seeds are independent runs: keep the ones already recorded
+        old = json.loads(path.read_text())
+        if old["cfg"] == CFG and old["steps"] == STEPS:
+            out["seeds"] = old["seeds"]
     for s in SEEDS:
+        if str(s) in out["seeds"]:
+            continue
         out["seeds"][str(s)] = run_seed(ref, s)
         print("seed", s, "first", out["seeds"][str(s)][0], "last", out["seeds"][str(s)][-1], flush=True)
-    (ROOT / "tests" / "golden" / "curves_flow_hinge.json").write_text(json.dumps(out))
+        path.write_text(json.dumps(out))

@@ -21,6 +21,7 @@ The fp32 CUDA path is additionally checked against the same reference curves wit
 ten times tighter band), and its first iterations against float rounding.
 """
 import json
+import os
 from pathlib import Path
 
 import numpy as np
@@ -72,7 +73,11 @@ def _curves(precision, tmp_path):
         ref.append(np.array(curve))
         got.append(_run(cfg, init, precision, steps, 1000 + s, tmp_path))
         assert np.isfinite(got[-1]).all()
-    return np.stack(ref), np.stack(got)          # (S, steps, 4)
+    ref, got = np.stack(ref), np.stack(got)      # (S, steps, 4)
+    dump = os.environ.get("DCV_CURVE_DUMP")
+    if dump:
+        np.savez_compressed(f"{dump}_{precision}.npz", ref=ref, got=got)
+    return ref, got
 
 
 def _gate(ref, got, early_rel, early_abs, tag):

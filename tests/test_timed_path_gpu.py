@@ -59,6 +59,7 @@ def test_graph_replay_batch32_bf16_matches_oracle(tmp_path):
     torch.cuda.empty_cache()
 
     tr, models, _ = _trainer(cfg, copy.deepcopy(init), "bf16", tmp_path, "staged")
+    engine._RNG = rng                     # keep the request pattern recorded by the warm-up trainer
     tr.GRAPH_WARMUP = 0
     assert tr.use_cuda_graph
     # oracle (CPU, fp32): same seed -> same draws as the staged buffers below

@@ -12,7 +12,11 @@ for st in $STAGES; do
     quick)
       timeout 1200 python -m pytest tests -m gpu -q -s --deselect tests/test_curves_gpu.py > gpurun_out/${TAG}_tests.log 2>&1; echo "quick tests rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -5 gpurun_out/${TAG}_tests.log;;
     curves)
-      timeout 1500 python -m pytest tests/test_curves_gpu.py -m gpu -q -s > gpurun_out/${TAG}_curves.log 2>&1; echo "curves rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_curves.log | tail -30;;
+      DCV_CURVE_DUMP=gpurun_out/${TAG}_curves timeout 1500 python -m pytest tests/test_curves_gpu.py -m gpu -q -s > gpurun_out/${TAG}_curves.log 2>&1; echo "curves rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_curves.log | tail -30;;
+    imgtest)
+      DCV_IMG_CONV=1 timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_nets_gpu.py tests/test_timed_path_gpu.py -m gpu -q -s -k "img_conv or full_width or generators_match or graph" > gpurun_out/${TAG}_imgtest.log 2>&1; echo "imgtest rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_imgtest.log | tail -25;;
+    imglayers)
+      DCV_IMG_CONV=1 timeout 600 python tools/layer_bench.py mug-depth 32 > gpurun_out/${TAG}_layers_img.md 2>&1; echo "imglayers rc=$?" | tee -a gpurun_out/${TAG}_rc.log; head -12 gpurun_out/${TAG}_layers_img.md;;
     bench)
       timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
     benchfast)
