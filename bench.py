@@ -392,7 +392,9 @@ def run_cuda(args, cfg_name):
         dist.init_process_group("nccl", device_id=torch.device("cuda:0"))
     B = 32
     cfg = make_cfg(cfg_name, B)
-    cfg["seed"] = cfg["seed"]
+    for kv in args.tune:
+        k, v = kv.split("=")
+        _lib.check(_lib.lib().dcv_set_tuning(k.encode(), int(v)))
     tr = build_trainer(cfg, args.precision)
     torch.manual_seed(cfg["seed"] + rank)
     np.random.seed(cfg["seed"] + rank)
@@ -533,6 +535,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (unmodified reference on cuda:0)")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-layer replay behind the roofline objects")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE", help="dcv_set_tuning switch for A/B runs, e.g. no_pdl=1")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 3:

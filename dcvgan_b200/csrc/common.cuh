@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 #include "../../include/dcvgan_b200.h"
 
 namespace dcv {
@@ -52,5 +53,31 @@ __device__ __forceinline__ float act_grad_from_out(float a, int act, float slope
 }
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// A training iteration is ~400 dependent launches; between two of them the GPU idles for the launch latency and for the
+// tail of the first kernel's last wave.  Every kernel of this library is launched through launch_k() with the
+// programmatic-stream-serialization attribute and starts with pdl_wait() (griddepcontrol.wait: returns when the
+// preceding kernel has completed and flushed) before it touches global memory, followed by pdl_trigger()
+// (griddepcontrol.launch_dependents), so the NEXT kernel's blocks are scheduled onto SMs as soon as every block of this
+// one has started: its prologue (barrier / TMEM set-up, index arithmetic) overlaps this kernel's tail.  Kernels of other
+// libraries in the stream (PyTorch fills and copies, NCCL) launch normally and serialise fully.  dcv_set_tuning("no_pdl", 1)
+// launches without the attribute (the two device instructions are then no-ops).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors are picked up by check_launch()
+}
 
 }  // namespace dcv

@@ -131,6 +131,7 @@ __device__ __forceinline__ void channel_reduce2(int64_t rows, int C, float* __re
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C,
                                                         float* __restrict__ partials, const BnTail tail) {
+  pdl_wait(); pdl_trigger();
   channel_reduce2(rows, C, partials, [&](int64_t row, int c, float& v0, float& v1) {
     const float v = ldf(z + row * ldz + c); v0 = v; v1 = v * v;
   });
@@ -159,6 +160,7 @@ __device__ __forceinline__ void warp_sum_partials(const float* __restrict__ part
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblk, int C, double count, float eps,
                                    float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
                                    float* __restrict__ mean, float* __restrict__ invstd) {
+  pdl_wait(); pdl_trigger();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
   if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;   // nn.BatchNorm's counter
   if (c >= C) return;
@@ -179,6 +181,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblk,
 
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, float eps,
                                      float* __restrict__ mean, float* __restrict__ invstd) {
+  pdl_wait(); pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   mean[c] = rm[c];
@@ -190,6 +193,7 @@ __global__ void __launch_bounds__(256)
 bn_act_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
               const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
               const float* __restrict__ drop, int64_t rows_per_n, int act, float slope, T* __restrict__ a, int64_t lda) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = rows * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / C; const int c = (int)(i - row * C);
@@ -209,6 +213,7 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ da, int64_t ldda, const T* __rest
                          const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const float* __restrict__ drop, int64_t rows_per_n,
                          int act, float slope, float* __restrict__ partials, const BnTail tail) {
+  pdl_wait(); pdl_trigger();
   channel_reduce2(rows, C, partials, [&](int64_t row, int c, float& v0, float& v1) {
     float du = ldf(da + row * ldda + c) * act_grad_from_out(ldf(a + row * lda + c), act, slope);
     if (drop) du *= drop[(row / rows_per_n) * C + c];
@@ -220,6 +225,7 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ da, int64_t ldda, const T* __rest
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int C, float* __restrict__ sums,
                                        float* dgamma, float* dbeta, int accumulate) {
+  pdl_wait(); pdl_trigger();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
   if (c >= C) return;
   double s0, s1;
@@ -237,6 +243,7 @@ bn_act_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, const T* __restr
                         const float* __restrict__ invstd, const float* __restrict__ gamma,
                         const float* __restrict__ drop, int64_t rows_per_n, int act, float slope,
                         const float* __restrict__ sums, float inv_count, T* __restrict__ dz, int64_t lddz) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = rows * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / C; const int c = (int)(i - row * C);
@@ -254,6 +261,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, int64_t lda, int64_t rows, int C,
                int act, float slope, T* __restrict__ dz, int64_t lddz) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = rows * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / C; const int c = (int)(i - row * C);
@@ -265,6 +273,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 add_noise_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ noise, float sigma, int64_t rows,
                  int C, T* __restrict__ out, int64_t ldo) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = rows * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / C; const int c = (int)(i - row * C);
@@ -275,6 +284,7 @@ add_noise_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256)
 axpy_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __restrict__ out, int64_t ldo, int accumulate) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = rows * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / C; const int c = (int)(i - row * C);
@@ -288,6 +298,7 @@ axpy_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __rest
 template <typename T>
 __global__ void __launch_bounds__(256)
 tdiff_kernel(const T* __restrict__ x, int64_t ldx, int N, int Tn, int64_t hw, int C, T* __restrict__ out, int64_t ldo) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = (int64_t)N * (Tn - 1) * hw * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C); int64_t r = i / C;
@@ -304,6 +315,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 tdiff_bwd_kernel(const T* __restrict__ dy, int64_t lddy, int N, int Tn, int64_t hw, int C, T* __restrict__ dx,
                  int64_t lddx, int accumulate) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = (int64_t)N * Tn * hw * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C); int64_t r = i / C;
@@ -321,6 +333,7 @@ tdiff_bwd_kernel(const T* __restrict__ dy, int64_t lddy, int N, int Tn, int64_t 
 template <typename T>
 __global__ void __launch_bounds__(256)
 softmax_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C, T* __restrict__ y, int64_t ldy) {
+  pdl_wait(); pdl_trigger();
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
     const T* zr = z + row * ldz; T* yr = y + row * ldy;
     float mx = -INFINITY;
@@ -336,6 +349,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ y, int64_t ldy, int64_t rows, int C,
                    T* __restrict__ dz, int64_t lddz) {
+  pdl_wait(); pdl_trigger();
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
     const T* dyr = dy + row * lddy; const T* yr = y + row * ldy; T* dzr = dz + row * lddz;
     float dot = 0.f;
@@ -348,6 +362,7 @@ softmax_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256)
 segm_remap_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __restrict__ y, int64_t ldy) {
+  pdl_wait(); pdl_trigger();
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
     const T* xr = x + row * ldx; T* yr = y + row * ldy;
     int best = 0; float bv = ldf(xr);
@@ -360,6 +375,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 to_cl_kernel(const float* __restrict__ src, int64_t sn, int64_t sc, int64_t st, int64_t sh, int64_t sw, int N, int C,
              int Tn, int H, int W, T* __restrict__ dst, int64_t ld) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = (int64_t)N * Tn * H * W * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C); int64_t r = i / C;
@@ -374,6 +390,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 from_cl_kernel(const T* __restrict__ src, int64_t ld, int N, int C, int Tn, int H, int W, float* __restrict__ dst,
                int64_t sn, int64_t sc, int64_t st, int64_t sh, int64_t sw, int accumulate) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = (int64_t)N * Tn * H * W * C;
   // iterate with w fastest, then h, t, c, n: the usual dense NC(T)HW destination is then written coalesced
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -391,6 +408,7 @@ from_cl_kernel(const T* __restrict__ src, int64_t ld, int N, int C, int Tn, int 
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256)
 copy_cl_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst, int64_t ldd, int64_t rows, int C) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = rows * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / C; const int c = (int)(i - row * C);
@@ -402,6 +420,7 @@ copy_cl_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst, in
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256)
 copy_cl_rows_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst, int64_t ldd, int64_t rows, int C) {
+  pdl_wait(); pdl_trigger();
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     const TS* sp = src + r * lds; TD* dp = dst + r * ldd;
     float v[8];
@@ -416,6 +435,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 frame_copy_kernel(T* __restrict__ clips, int64_t ldc, int N, int Tn, int64_t hw, int C, int t, const int* __restrict__ t_dev,
                   T* __restrict__ frames, int64_t ldfr, int reverse, int accumulate) {
+  pdl_wait(); pdl_trigger();
   if (t_dev) t = min(max(*t_dev, 0), Tn - 1);   // frame index kept on the device (CUDA-graph replay)
   const int64_t total = (int64_t)N * hw * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -496,6 +516,7 @@ __global__ void __launch_bounds__(256)
 bn_act_vec_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ drop, int64_t rows_per_n, int act, float slope, T* __restrict__ a, int64_t lda) {
+  pdl_wait(); pdl_trigger();
   constexpr int N = VecIO<T>::N;
   const VecMap m = vec_map<N>(rows, C);
   if (!m.active) return;
@@ -587,6 +608,7 @@ __device__ __forceinline__ void channel_reduce2_vec(int64_t rows, int C, float* 
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_vec_kernel(const T* __restrict__ z, int64_t ldz, int64_t rows, int C,
                                                             float* __restrict__ partials, const BnTail tail) {
+  pdl_wait(); pdl_trigger();
   constexpr int N = VecIO<T>::N;
   channel_reduce2_vec<T>(rows, C, partials, [&](int64_t row, int c0, float (&v0)[N], float (&v1)[N]) {
     VecIO<T>::load(z + row * ldz + c0, v0);
@@ -603,6 +625,7 @@ bn_act_bwd_reduce_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __
                              const float* __restrict__ invstd, const float* __restrict__ gamma,
                              const float* __restrict__ beta, const float* __restrict__ drop, int64_t rows_per_n,
                              int act, float slope, float* __restrict__ partials, const BnTail tail) {
+  pdl_wait(); pdl_trigger();
   constexpr int N = VecIO<T>::N;
   // (Leaky)ReLU: the sign of the activated output equals the sign of the pre-activation gamma * xhat + beta, which is
   // recomputed from z with exactly the forward's arithmetic - the output tensor `a` is then not read at all (one of
@@ -633,6 +656,7 @@ bn_act_bwd_apply_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __r
                             const float* __restrict__ invstd, const float* __restrict__ gamma,
                             const float* __restrict__ beta, const float* __restrict__ drop, int64_t rows_per_n, int act,
                             float slope, const float* __restrict__ sums, float inv_count, T* __restrict__ dz, int64_t lddz) {
+  pdl_wait(); pdl_trigger();
   constexpr int N = VecIO<T>::N;
   const VecMap m = vec_map<N>(rows, C);
   if (!m.active) return;
@@ -679,6 +703,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 act_bwd_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, int64_t lda, int64_t rows, int C,
                    int act, float slope, T* __restrict__ dz, int64_t lddz) {
+  pdl_wait(); pdl_trigger();
   constexpr int N = VecIO<T>::N;
   const VecMap m = vec_map<N>(rows, C);
   if (!m.active) return;
@@ -710,6 +735,7 @@ act_bwd_vec_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256)
 axpy_vec_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __restrict__ out, int64_t ldo, int accumulate) {
+  pdl_wait(); pdl_trigger();
   constexpr int N = VecIO<T>::N;
   const VecMap m = vec_map<N>(rows, C);
   if (!m.active) return;
@@ -755,6 +781,7 @@ __global__ void __launch_bounds__(256)
 col2im_act_tiled_kernel(const __nv_bfloat16* __restrict__ P, int64_t ldp, int Ih, int Iw, int Cout, int KH, int KW, int pad,
                         int Oh, int Ow, int rowv /*16-byte vectors per staged row*/, int RH, int RW /*staged region*/, int act,
                         float slope, __nv_bfloat16* __restrict__ y, int64_t ldy) {
+  pdl_wait(); pdl_trigger();
   extern __shared__ uint32_t tile[];
   // staged pixel pitch = rowv*4 + 1 words: neighbouring output pixels read the same column of neighbouring staged pixels,
   // and a 64-byte pitch put 16 of them on 2 banks (ncu: 8 shared-memory wavefronts per load)
@@ -808,6 +835,7 @@ template <typename T, int S>      // S = stride known at compile time (1, 2) or 
 __global__ void __launch_bounds__(256)
 col2im_act_kernel(const T* __restrict__ P, int64_t ldp, int N, int Ih, int Iw, int Cout, int KH, int KW, int s_rt, int pad, int Oh,
                   int Ow, int act, float slope, T* __restrict__ y, int64_t ldy) {
+  pdl_wait(); pdl_trigger();
   const int s = S ? S : s_rt;
   const int taps = KH * KW;
   const int64_t total = (int64_t)N * Oh * Ow;
@@ -847,6 +875,7 @@ __global__ void __launch_bounds__(256)
 fold_w_kernel(const T* __restrict__ xg, int64_t ldg, int cg, const float* __restrict__ ng, const T* __restrict__ xc, int64_t ldc,
               int cc, const float* __restrict__ nc, float sigma, int64_t lines, int W, int Ow, int kw, int sw, int pw,
               T* __restrict__ out, int64_t ldo) {
+  pdl_wait(); pdl_trigger();
   const int cin = cg + cc;
   const int64_t total = lines * Ow;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -902,6 +931,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 unfold_w_kernel(const T* __restrict__ d2, int64_t ld2, int64_t lines, int W, int Ow, int kw, int sw, int pw, T* __restrict__ dxg,
                 int64_t ldg, int cg, T* __restrict__ dxc, int64_t ldc, int cc) {
+  pdl_wait(); pdl_trigger();
   const int cin = cg + cc;
   const int64_t total = lines * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -951,6 +981,7 @@ bn_act_bf16_kernel(const __nv_bfloat16* __restrict__ z, int64_t ldz, int64_t row
                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ drop, int64_t rows_per_n, int act, float slope, __nv_bfloat16* __restrict__ a,
                    int64_t lda) {
+  pdl_wait(); pdl_trigger();
   const VecMap m = vec_map<8>(rows, C);
   if (!m.active) return;
   const int c0 = m.cg * 8;
@@ -993,6 +1024,7 @@ bn_act_bwd_apply_bf16_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda,
                              const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ drop,
                              int64_t rows_per_n, float slope, const float* __restrict__ sums, float inv_count,
                              __nv_bfloat16* __restrict__ dz, int64_t lddz) {
+  pdl_wait(); pdl_trigger();
   const VecMap m = vec_map<8>(rows, C);
   if (!m.active) return;
   const int c0 = m.cg * 8;
@@ -1066,6 +1098,7 @@ __device__ __forceinline__ void reduce2_tail(const VecMap& m, int C, float (&a0)
 __global__ void __launch_bounds__(256, 3)
 bn_stats_bf16_kernel(const __nv_bfloat16* __restrict__ z, int64_t ldz, int64_t rows, int C, float* __restrict__ partials,
                      const BnTail tail) {
+  pdl_wait(); pdl_trigger();
   const VecMap m = vec_map<8>(rows, C);
   float a0[8], a1[8];
 #pragma unroll
@@ -1098,6 +1131,7 @@ bn_act_bwd_reduce_bf16_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda
                               int64_t rows, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ drop,
                               int64_t rows_per_n, float slope, float* __restrict__ partials, const BnTail tail) {
+  pdl_wait(); pdl_trigger();
   const VecMap m = vec_map<8>(rows, C);
   float a0[8], a1[8];
 #pragma unroll
@@ -1185,9 +1219,9 @@ static int launch_bn_stats(int dtype, const void* z, int64_t ldz, int64_t rows, 
   const int nblk = dcv_bn_stats_blocks(rows, C);
   DISPATCH_T(dtype, {
     if (sizeof(T) == 2 && vec_ok<T>(C, {z}, {ldz}))
-      bn_stats_bf16_kernel<<<nblk, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, ldz, rows, C, partials, tail);
-    else if (vec_ok<T>(C, {z}, {ldz})) bn_stats_vec_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials, tail);
-    else bn_stats_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, partials, tail);
+      launch_k(bn_stats_bf16_kernel, nblk, 256, 0, as_stream(stream), (const __nv_bfloat16*)z, ldz, rows, C, partials, tail);
+    else if (vec_ok<T>(C, {z}, {ldz})) launch_k(bn_stats_vec_kernel<T>, nblk, 256, 0, as_stream(stream), (const T*)z, ldz, rows, C, partials, tail);
+    else launch_k(bn_stats_kernel<T>, nblk, 256, 0, as_stream(stream), (const T*)z, ldz, rows, C, partials, tail);
   });
   return check_launch("bn_stats");
 }
@@ -1229,7 +1263,7 @@ int dcv_bn_stats_finalize(int dtype, const void* z, int64_t ldz, int64_t rows, i
 int dcv_bn_finalize(const float* partials, int nblk, int C, int64_t count, float eps, float momentum,
                     float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd,
                     void* stream) {
-  bn_finalize_kernel<<<ceil_div(C, 8), 256, 0, as_stream(stream)>>>(partials, nblk, C, (double)count, eps, momentum,
+  launch_k(bn_finalize_kernel, ceil_div(C, 8), 256, 0, as_stream(stream), partials, nblk, C, (double)count, eps, momentum,
                                                                     running_mean, running_var, (long long*)num_batches_tracked,
                                                                     mean, invstd);
   return check_launch("bn_finalize");
@@ -1237,7 +1271,7 @@ int dcv_bn_finalize(const float* partials, int nblk, int C, int64_t count, float
 
 int dcv_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean,
                       float* invstd, void* stream) {
-  bn_eval_stats_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(running_mean, running_var, C, eps, mean, invstd);
+  launch_k(bn_eval_stats_kernel, ceil_div(C, 128), 128, 0, as_stream(stream), running_mean, running_var, C, eps, mean, invstd);
   return check_launch("bn_eval_stats");
 }
 
@@ -1247,13 +1281,13 @@ int dcv_bn_act(int dtype, const void* z, int64_t ldz, int64_t rows, int C, const
   if (rows * C == 0) return 0;
   DISPATCH_T(dtype, {
     if (sizeof(T) == 2 && vec_ok<T>(C, {z, a}, {ldz, lda}))
-      bn_act_bf16_kernel<<<vec_blocks(rows, C, 8), 256, 0, as_stream(stream)>>>(
+      launch_k(bn_act_bf16_kernel, vec_blocks(rows, C, 8), 256, 0, as_stream(stream), 
           (const __nv_bfloat16*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope, (__nv_bfloat16*)a, lda);
     else if (vec_ok<T>(C, {z, a}, {ldz, lda}))
-      bn_act_vec_kernel<T><<<vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream)>>>(
+      launch_k(bn_act_vec_kernel<T>, vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream), 
           (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope, (T*)a, lda);
     else
-      bn_act_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
+      launch_k(bn_act_kernel<T>, ew_blocks(rows * C, 4), 256, 0, as_stream(stream), 
           (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope, (T*)a, lda);
   });
   return check_launch("bn_act");
@@ -1266,15 +1300,15 @@ static int launch_bn_bwd_reduce(int dtype, const void* da, int64_t ldda, const v
   const int nblk = dcv_bn_stats_blocks(rows, C);
   DISPATCH_T(dtype, {
     if (sizeof(T) == 2 && act == DCV_ACT_LEAKY && vec_ok<T>(C, {da, z}, {ldda, ldz}))
-      bn_act_bwd_reduce_bf16_kernel<<<nblk, 256, 0, as_stream(stream)>>>(
+      launch_k(bn_act_bwd_reduce_bf16_kernel, nblk, 256, 0, as_stream(stream), 
           (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, slope,
           partials, tail);
     else if (vec_ok<T>(C, {da, a, z}, {ldda, lda, ldz}))
-      bn_act_bwd_reduce_vec_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>(
+      launch_k(bn_act_bwd_reduce_vec_kernel<T>, nblk, 256, 0, as_stream(stream), 
           (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope,
           partials, tail);
     else
-      bn_act_bwd_reduce_kernel<T><<<nblk, 256, 0, as_stream(stream)>>>(
+      launch_k(bn_act_bwd_reduce_kernel<T>, nblk, 256, 0, as_stream(stream), 
           (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, drop, rows_per_n, act, slope, partials, tail);
   });
   return check_launch("bn_act_bwd_reduce");
@@ -1302,7 +1336,7 @@ int dcv_bn_act_bwd_reduce_finalize(int dtype, const void* da, int64_t ldda, cons
 
 int dcv_bn_bwd_finalize(const float* partials, int nblk, int C, float* sums, float* dgamma, float* dbeta,
                         int accumulate, void* stream) {
-  bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, as_stream(stream)>>>(partials, nblk, C, sums, dgamma, dbeta, accumulate);
+  launch_k(bn_bwd_finalize_kernel, ceil_div(C, 8), 256, 0, as_stream(stream), partials, nblk, C, sums, dgamma, dbeta, accumulate);
   return check_launch("bn_bwd_finalize");
 }
 
@@ -1313,15 +1347,15 @@ int dcv_bn_act_bwd_apply(int dtype, const void* da, int64_t ldda, const void* a,
   if (rows * C == 0) return 0;
   DISPATCH_T(dtype, {
     if (sizeof(T) == 2 && act == DCV_ACT_LEAKY && vec_ok<T>(C, {da, z, dz}, {ldda, ldz, lddz}))
-      bn_act_bwd_apply_bf16_kernel<<<vec_blocks(rows, C, 8), 256, 0, as_stream(stream)>>>(
+      launch_k(bn_act_bwd_apply_bf16_kernel, vec_blocks(rows, C, 8), 256, 0, as_stream(stream), 
           (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, slope,
           sums, 1.0f / (float)count, (__nv_bfloat16*)dz, lddz);
     else if (vec_ok<T>(C, {da, a, z, dz}, {ldda, lda, ldz, lddz}))
-      bn_act_bwd_apply_vec_kernel<T><<<vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream)>>>(
+      launch_k(bn_act_bwd_apply_vec_kernel<T>, vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream), 
           (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, gamma, beta, drop, rows_per_n, act, slope,
           sums, 1.0f / (float)count, (T*)dz, lddz);
     else
-      bn_act_bwd_apply_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
+      launch_k(bn_act_bwd_apply_kernel<T>, ew_blocks(rows * C, 4), 256, 0, as_stream(stream), 
           (const T*)da, ldda, (const T*)a, lda, (const T*)z, ldz, rows, C, mean, invstd, gamma, drop, rows_per_n, act, slope,
           sums, 1.0f / (float)count, (T*)dz, lddz);
   });
@@ -1333,10 +1367,10 @@ int dcv_act_bwd(int dtype, const void* da, int64_t ldda, const void* a, int64_t 
   if (rows * C == 0) return 0;
   DISPATCH_T(dtype, {
     if (vec_ok<T>(C, {da, a, dz}, {ldda, lda, lddz}))
-      act_bwd_vec_kernel<T><<<vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream)>>>(
+      launch_k(act_bwd_vec_kernel<T>, vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream), 
           (const T*)da, ldda, (const T*)a, lda, rows, C, act, slope, (T*)dz, lddz);
     else
-      act_bwd_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>((const T*)da, ldda, (const T*)a, lda, rows, C, act,
+      launch_k(act_bwd_kernel<T>, ew_blocks(rows * C, 4), 256, 0, as_stream(stream), (const T*)da, ldda, (const T*)a, lda, rows, C, act,
                                                                                slope, (T*)dz, lddz);
   });
   return check_launch("act_bwd");
@@ -1345,7 +1379,7 @@ int dcv_act_bwd(int dtype, const void* da, int64_t ldda, const void* a, int64_t 
 int dcv_add_noise(int dtype, const void* x, int64_t ldx, const float* noise, float sigma, int64_t rows, int C,
                   void* out, int64_t ldo, void* stream) {
   if (rows * C == 0) return 0;
-  DISPATCH_T(dtype, add_noise_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>(
+  DISPATCH_T(dtype, launch_k(add_noise_kernel<T>, ew_blocks(rows * C, 4), 256, 0, as_stream(stream), 
                         (const T*)x, ldx, noise, sigma, rows, C, (T*)out, ldo));
   return check_launch("add_noise");
 }
@@ -1355,10 +1389,10 @@ int dcv_axpy(int dtype, const void* x, int64_t ldx, int64_t rows, int C, void* o
   if (rows * C == 0) return 0;
   DISPATCH_T(dtype, {
     if (vec_ok<T>(C, {x, out}, {ldx, ldo}))
-      axpy_vec_kernel<T><<<vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream)>>>((const T*)x, ldx, rows, C, (T*)out,
+      launch_k(axpy_vec_kernel<T>, vec_blocks(rows, C, 16 / (int)sizeof(T)), 256, 0, as_stream(stream), (const T*)x, ldx, rows, C, (T*)out,
                                                                                                   ldo, accumulate);
     else
-      axpy_kernel<T><<<ew_blocks(rows * C, 4), 256, 0, as_stream(stream)>>>((const T*)x, ldx, rows, C, (T*)out, ldo, accumulate);
+      launch_k(axpy_kernel<T>, ew_blocks(rows * C, 4), 256, 0, as_stream(stream), (const T*)x, ldx, rows, C, (T*)out, ldo, accumulate);
   });
   return check_launch("axpy");
 }
@@ -1367,7 +1401,7 @@ int dcv_tdiff(int dtype, const void* x, int64_t ldx, int N, int T_, int64_t hw, 
               void* stream) {
   const int64_t total = (int64_t)N * (T_ - 1) * hw * C;
   if (total <= 0) return 0;
-  DISPATCH_T(dtype, tdiff_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>((const T*)x, ldx, N, T_, hw, C,
+  DISPATCH_T(dtype, launch_k(tdiff_kernel<T>, ew_blocks(total, 4), 256, 0, as_stream(stream), (const T*)x, ldx, N, T_, hw, C,
                                                                                         (T*)out, ldo));
   return check_launch("tdiff");
 }
@@ -1376,28 +1410,28 @@ int dcv_tdiff_bwd(int dtype, const void* dy, int64_t lddy, int N, int T_, int64_
                   int accumulate, void* stream) {
   const int64_t total = (int64_t)N * T_ * hw * C;
   if (total <= 0) return 0;
-  DISPATCH_T(dtype, tdiff_bwd_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(
+  DISPATCH_T(dtype, launch_k(tdiff_bwd_kernel<T>, ew_blocks(total, 4), 256, 0, as_stream(stream), 
                         (const T*)dy, lddy, N, T_, hw, C, (T*)dx, lddx, accumulate));
   return check_launch("tdiff_bwd");
 }
 
 int dcv_softmax(int dtype, const void* z, int64_t ldz, int64_t rows, int C, void* y, int64_t ldy, void* stream) {
   if (rows == 0) return 0;
-  DISPATCH_T(dtype, softmax_kernel<T><<<ew_blocks(rows), 256, 0, as_stream(stream)>>>((const T*)z, ldz, rows, C, (T*)y, ldy));
+  DISPATCH_T(dtype, launch_k(softmax_kernel<T>, ew_blocks(rows), 256, 0, as_stream(stream), (const T*)z, ldz, rows, C, (T*)y, ldy));
   return check_launch("softmax");
 }
 
 int dcv_softmax_bwd(int dtype, const void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t rows, int C, void* dz,
                     int64_t lddz, void* stream) {
   if (rows == 0) return 0;
-  DISPATCH_T(dtype, softmax_bwd_kernel<T><<<ew_blocks(rows), 256, 0, as_stream(stream)>>>((const T*)dy, lddy, (const T*)y,
+  DISPATCH_T(dtype, launch_k(softmax_bwd_kernel<T>, ew_blocks(rows), 256, 0, as_stream(stream), (const T*)dy, lddy, (const T*)y,
                                                                                           ldy, rows, C, (T*)dz, lddz));
   return check_launch("softmax_bwd");
 }
 
 int dcv_segm_remap(int dtype, const void* x, int64_t ldx, int64_t rows, int C, void* y, int64_t ldy, void* stream) {
   if (rows == 0) return 0;
-  DISPATCH_T(dtype, segm_remap_kernel<T><<<ew_blocks(rows), 256, 0, as_stream(stream)>>>((const T*)x, ldx, rows, C, (T*)y, ldy));
+  DISPATCH_T(dtype, launch_k(segm_remap_kernel<T>, ew_blocks(rows), 256, 0, as_stream(stream), (const T*)x, ldx, rows, C, (T*)y, ldy));
   return check_launch("segm_remap");
 }
 
@@ -1405,7 +1439,7 @@ int dcv_to_channels_last(int dtype, const float* src, int64_t sn, int64_t sc, in
                          int C, int T_, int H, int W, void* dst, int64_t ld, void* stream) {
   const int64_t total = (int64_t)N * T_ * H * W * C;
   if (total == 0) return 0;
-  DISPATCH_T(dtype, to_cl_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(src, sn, sc, st, sh, sw, N, C, T_,
+  DISPATCH_T(dtype, launch_k(to_cl_kernel<T>, ew_blocks(total, 4), 256, 0, as_stream(stream), src, sn, sc, st, sh, sw, N, C, T_,
                                                                                         H, W, (T*)dst, ld));
   return check_launch("to_channels_last");
 }
@@ -1414,7 +1448,7 @@ int dcv_from_channels_last(int dtype, const void* src, int64_t ld, int N, int C,
                            int64_t sn, int64_t sc, int64_t st, int64_t sh, int64_t sw, int accumulate, void* stream) {
   const int64_t total = (int64_t)N * T_ * H * W * C;
   if (total == 0) return 0;
-  DISPATCH_T(dtype, from_cl_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(
+  DISPATCH_T(dtype, launch_k(from_cl_kernel<T>, ew_blocks(total, 4), 256, 0, as_stream(stream), 
                         (const T*)src, ld, N, C, T_, H, W, dst, sn, sc, st, sh, sw, accumulate));
   return check_launch("from_channels_last");
 }
@@ -1424,7 +1458,7 @@ int dcv_frame_copy(int dtype, void* clips, int64_t ldc, int N, int T_, int64_t h
   const int64_t total = (int64_t)N * hw * C;
   if (total == 0) return 0;
   DCV_REQUIRE(t_dev || (t >= 0 && t < T_), "frame_copy: frame %d out of range [0,%d)", t, T_);
-  DISPATCH_T(dtype, frame_copy_kernel<T><<<ew_blocks(total, 4), 256, 0, as_stream(stream)>>>(
+  DISPATCH_T(dtype, launch_k(frame_copy_kernel<T>, ew_blocks(total, 4), 256, 0, as_stream(stream), 
                         (T*)clips, ldc, N, T_, hw, C, t, t_dev, (T*)frames, ldf, reverse, accumulate));
   return check_launch("frame_copy");
 }
@@ -1444,10 +1478,10 @@ int dcv_col2im_act(int dtype, const void* P, int64_t ldp, int N, int Ih, int Iw,
     if (smem <= 48 * 1024) {
       dim3 grid(ceil_div(Ow, 16), ceil_div(Oh, 16), N);
       if (stride == 1)
-        col2im_act_tiled_kernel<1><<<grid, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)P, ldp, Ih, Iw, Cout, KH, KW, pad, Oh, Ow,
+        launch_k(col2im_act_tiled_kernel<1>, grid, 256, smem, as_stream(stream), (const __nv_bfloat16*)P, ldp, Ih, Iw, Cout, KH, KW, pad, Oh, Ow,
                                                                            rowv, RH, RW, act, slope, (__nv_bfloat16*)y, ldy);
       else
-        col2im_act_tiled_kernel<2><<<grid, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)P, ldp, Ih, Iw, Cout, KH, KW, pad, Oh, Ow,
+        launch_k(col2im_act_tiled_kernel<2>, grid, 256, smem, as_stream(stream), (const __nv_bfloat16*)P, ldp, Ih, Iw, Cout, KH, KW, pad, Oh, Ow,
                                                                            rowv, RH, RW, act, slope, (__nv_bfloat16*)y, ldy);
       return check_launch("col2im_act_tiled");
     }
@@ -1455,11 +1489,11 @@ int dcv_col2im_act(int dtype, const void* P, int64_t ldp, int N, int Ih, int Iw,
   const int nb = ew_blocks((int64_t)N * Oh * Ow, 1);
   DISPATCH_T(dtype, {
     if (stride == 1)
-      col2im_act_kernel<T, 1><<<nb, 256, 0, as_stream(stream)>>>((const T*)P, ldp, N, Ih, Iw, Cout, KH, KW, stride, pad, Oh, Ow, act, slope, (T*)y, ldy);
+      launch_k(col2im_act_kernel<T, 1>, nb, 256, 0, as_stream(stream), (const T*)P, ldp, N, Ih, Iw, Cout, KH, KW, stride, pad, Oh, Ow, act, slope, (T*)y, ldy);
     else if (stride == 2)
-      col2im_act_kernel<T, 2><<<nb, 256, 0, as_stream(stream)>>>((const T*)P, ldp, N, Ih, Iw, Cout, KH, KW, stride, pad, Oh, Ow, act, slope, (T*)y, ldy);
+      launch_k(col2im_act_kernel<T, 2>, nb, 256, 0, as_stream(stream), (const T*)P, ldp, N, Ih, Iw, Cout, KH, KW, stride, pad, Oh, Ow, act, slope, (T*)y, ldy);
     else
-      col2im_act_kernel<T, 0><<<nb, 256, 0, as_stream(stream)>>>((const T*)P, ldp, N, Ih, Iw, Cout, KH, KW, stride, pad, Oh, Ow, act, slope, (T*)y, ldy);
+      launch_k(col2im_act_kernel<T, 0>, nb, 256, 0, as_stream(stream), (const T*)P, ldp, N, Ih, Iw, Cout, KH, KW, stride, pad, Oh, Ow, act, slope, (T*)y, ldy);
   });
   return check_launch("col2im_act");
 }
@@ -1472,7 +1506,7 @@ int dcv_fold_w(int dtype, const void* xg, int64_t ldg, int cg, const float* nois
   DCV_REQUIRE(ldo >= (int64_t)kw * (cg + cc), "fold_w: output pitch %lld < %d folded channels", (long long)ldo, kw * (cg + cc));
   const int Ow = (W + 2 * pw - kw) / sw + 1;
   if (lines * Ow == 0) return 0;
-  DISPATCH_T(dtype, fold_w_kernel<T><<<ew_blocks(lines * Ow, 1), 256, 0, as_stream(stream)>>>(
+  DISPATCH_T(dtype, launch_k(fold_w_kernel<T>, ew_blocks(lines * Ow, 1), 256, 0, as_stream(stream), 
                         (const T*)xg, ldg, cg, noise_g, (const T*)xc, ldc, cc, noise_c, sigma, lines, W, Ow, kw, sw, pw, (T*)out, ldo));
   return check_launch("fold_w");
 }
@@ -1483,7 +1517,7 @@ int dcv_unfold_w(int dtype, const void* d2, int64_t ld2, int64_t lines, int W, i
   DCV_REQUIRE(cg >= 1 && cc >= 1 && cg + cc <= 8 && kw >= 1 && sw >= 1 && pw >= 0 && W + 2 * pw >= kw, "unfold_w: bad shape");
   const int Ow = (W + 2 * pw - kw) / sw + 1;
   if (lines * W == 0) return 0;
-  DISPATCH_T(dtype, unfold_w_kernel<T><<<ew_blocks(lines * W, 1), 256, 0, as_stream(stream)>>>(
+  DISPATCH_T(dtype, launch_k(unfold_w_kernel<T>, ew_blocks(lines * W, 1), 256, 0, as_stream(stream), 
                         (const T*)d2, ld2, lines, W, Ow, kw, sw, pw, (T*)dxg, ldg, cg, (T*)dxc, ldc, cc));
   return check_launch("unfold_w");
 }
@@ -1495,16 +1529,16 @@ int dcv_copy_cl(int src_dtype, const void* src, int64_t lds, int dst_dtype, void
   const int nb = ew_blocks(total, 4);
   cudaStream_t s = as_stream(stream);
   if (src_dtype == DCV_F32 && dst_dtype == DCV_F32)
-    copy_cl_kernel<float, float><<<nb, 256, 0, s>>>((const float*)src, lds, (float*)dst, ldd, rows, C);
+    launch_k(copy_cl_kernel<float, float>, nb, 256, 0, s, (const float*)src, lds, (float*)dst, ldd, rows, C);
   else if (src_dtype == DCV_F32)
-    copy_cl_kernel<float, __nv_bfloat16><<<nb, 256, 0, s>>>((const float*)src, lds, (__nv_bfloat16*)dst, ldd, rows, C);
+    launch_k(copy_cl_kernel<float, __nv_bfloat16>, nb, 256, 0, s, (const float*)src, lds, (__nv_bfloat16*)dst, ldd, rows, C);
   else if (dst_dtype == DCV_F32)
-    copy_cl_kernel<__nv_bfloat16, float><<<nb, 256, 0, s>>>((const __nv_bfloat16*)src, lds, (float*)dst, ldd, rows, C);
+    launch_k(copy_cl_kernel<__nv_bfloat16, float>, nb, 256, 0, s, (const __nv_bfloat16*)src, lds, (float*)dst, ldd, rows, C);
   else if (C <= 8)
-    copy_cl_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<ew_blocks(rows, 2), 256, 0, s>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst,
+    launch_k(copy_cl_rows_kernel<__nv_bfloat16, __nv_bfloat16>, ew_blocks(rows, 2), 256, 0, s, (const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst,
                                                                                           ldd, rows, C);
   else
-    copy_cl_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, 256, 0, s>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, rows, C);
+    launch_k(copy_cl_kernel<__nv_bfloat16, __nv_bfloat16>, nb, 256, 0, s, (const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, rows, C);
   return check_launch("copy_cl");
 }
 

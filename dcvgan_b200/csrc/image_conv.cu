@@ -82,14 +82,13 @@ template <int C>
 __global__ void __launch_bounds__(256)
 img_conv3x3_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t s_l, int64_t s_s,
                        int N, int H, int W, __nv_bfloat16* __restrict__ y, int64_t ldy, int act, float slope) {
+  pdl_wait(); pdl_trigger();
   constexpr int KS = (9 * C + 15) / 16;                        // k16 steps
   __shared__ __align__(16) __nv_bfloat16 xs[(IMG_BAND + 2) * 66 * C];
   __shared__ __align__(16) uint32_t stg[IMG_WARPS][16][36];     // warp-private 16 x 64 bf16 tile, 144-byte row pitch
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, g = lane / 4, q = lane % 4;
   const int bands = H / IMG_BAND;
-  const int n = blockIdx.x / bands, r0 = (blockIdx.x % bands) * IMG_BAND;
   const int WP = W + 2;
-  stage_window<C>(xs, x, ldx, n, r0, H, W);
   // B fragments: B[k][co] = w[co][ci][tap] (k = tap*C + ci), bf16
   uint32_t bw[KS][8][2];
 #pragma unroll
@@ -106,8 +105,13 @@ img_conv3x3_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const f
         }
         bw[s][j][h] = pack_bf16x2(v[0], v[1]);
       }
-  __syncthreads();
   const int tiles_w = W / 16, tiles = IMG_BAND * tiles_w;
+  // persistent over (image, band) items: the weight fragments are built once per block
+  for (int item = blockIdx.x; item < N * bands; item += gridDim.x) {
+  const int n = item / bands, r0 = (item % bands) * IMG_BAND;
+  __syncthreads();                               // the previous item's readers of xs are done
+  stage_window<C>(xs, x, ldx, n, r0, H, W);
+  __syncthreads();
   for (int t = warp; t < tiles; t += IMG_WARPS) {
     const int lr = t / tiles_w, w0 = (t % tiles_w) * 16;
     float acc[8][4];
@@ -143,6 +147,7 @@ img_conv3x3_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const f
     }
     __syncwarp();
   }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ backward
@@ -161,6 +166,7 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
                        const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t s_l, int64_t s_s,
                        int N, int H, int W, int act, float slope, float* __restrict__ partial, __nv_bfloat16* __restrict__ dx,
                        int64_t lddx) {
+  pdl_wait(); pdl_trigger();
   constexpr int NT = 9 * C;                    // (tap, ci) pairs
   constexpr int NJ = (NT + 7) / 8;             // n8 tiles over them
   constexpr int NP = NJ * 8;                   // padded row length of P
@@ -169,9 +175,7 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(Ps + (size_t)(IMG_BAND + 2) * W * NP);
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, g = lane / 4, q = lane % 4;
   const int bands = H / IMG_BAND;
-  const int n = blockIdx.x / bands, r0 = (blockIdx.x % bands) * IMG_BAND;
   const int WP = W + 2;
-  stage_window<C>(xs, x, ldx, n, r0, H, W);
   // B fragments of the data-gradient GEMM: B[k slot][nn] = w[co(s, slot)][ci][tap], nn = tap*C + ci (0 beyond 9*C)
   uint32_t bw[4][NJ][2];
 #pragma unroll
@@ -194,9 +198,14 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
   for (int s = 0; s < 4; ++s)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { acc[s][j][0] = acc[s][j][1] = acc[s][j][2] = acc[s][j][3] = 0.f; }
-  __syncthreads();
 
   const int tiles_w = W / 16, tiles = (IMG_BAND + 2) * tiles_w;
+  // persistent over (image, band) items: weight fragments built once, dW accumulated across all items of the block
+  for (int item = blockIdx.x; item < N * bands; item += gridDim.x) {
+  const int n = item / bands, r0 = (item % bands) * IMG_BAND;
+  __syncthreads();                               // the previous item's readers of xs / Ps are done
+  stage_window<C>(xs, x, ldx, n, r0, H, W);
+  __syncthreads();
   for (int t = warp; t < tiles; t += IMG_WARPS) {
     const int prow = t / tiles_w, w0 = (t % tiles_w) * 16;       // prow 0 / BAND+1 = halo rows
     const int h = r0 - 1 + prow;
@@ -290,6 +299,7 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
       for (int ci = 0; ci < C; ++ci) d[ci] = __float2bfloat16_rn(s[ci]);
     }
   }
+  }   // items
   if (partial == nullptr) return;
   __syncthreads();
   // ---- weight gradient: per-warp accumulators -> shared [warp][nn][co] -> fixed-order sum over the warps
@@ -330,7 +340,10 @@ static int bwd_smem_bytes(int C, int W) {
   return (tile > red ? tile : red) * (int)sizeof(float) + (IMG_BAND + 2) * (W + 2) * C * 2 + 16;
 }
 
-int img_conv_bwd_blocks(const dcv_geom* g) { return g->N * (g->Hl / IMG_BAND); }
+static int img_items(const dcv_geom* g) { return g->N * (g->Hl / IMG_BAND); }
+// persistent grids: forward 3 blocks / SM (80 registers, 20 KB), backward 2 blocks / SM (116 registers, ~42 KB)
+static int img_fwd_blocks(const dcv_geom* g) { const int it = img_items(g); return it < 148 * 3 ? it : 148 * 3; }
+int img_conv_bwd_blocks(const dcv_geom* g) { const int it = img_items(g); return it < 148 * 2 ? it : 148 * 2; }
 
 int64_t img_conv_bwd_ws_bytes(const dcv_geom* g) {
   const int C = g->wCl > 0 ? g->wCl : g->Cl;
@@ -343,11 +356,11 @@ int img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, 
   DCV_REQUIRE(s_tap == 1, "img_conv_fwd: taps of the master weight must be contiguous");
   DCV_REQUIRE((((uintptr_t)y) & 15) == 0 && ldy % 8 == 0, "img_conv_fwd: output must be 16-byte aligned");
   const int C = g->wCl > 0 ? g->wCl : g->Cl;
-  const unsigned blocks = (unsigned)img_conv_bwd_blocks(g);
+  const unsigned blocks = (unsigned)img_fwd_blocks(g);
   if (C == 1)
-    img_conv3x3_fwd_kernel<1><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, (__nv_bfloat16*)y, ldy, act, slope);
+    launch_k(img_conv3x3_fwd_kernel<1>, blocks, 256, 0, s, (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, (__nv_bfloat16*)y, ldy, act, slope);
   else
-    img_conv3x3_fwd_kernel<2><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, (__nv_bfloat16*)y, ldy, act, slope);
+    launch_k(img_conv3x3_fwd_kernel<2>, blocks, 256, 0, s, (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, (__nv_bfloat16*)y, ldy, act, slope);
   return check_launch("img_conv3x3_fwd");
 }
 
@@ -366,11 +379,11 @@ int img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a,
   static int smem_set[3] = {0, 0, 0};
   if (C == 1) {
     if (smem > smem_set[1]) { DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); smem_set[1] = smem; }
-    img_conv3x3_bwd_kernel<1><<<blocks, 256, smem, s>>>((const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)x, ldx,
+    launch_k(img_conv3x3_bwd_kernel<1>, blocks, 256, smem, s, (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)x, ldx,
                                                        w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx);
   } else {
     if (smem > smem_set[2]) { DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); smem_set[2] = smem; }
-    img_conv3x3_bwd_kernel<2><<<blocks, 256, smem, s>>>((const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)x, ldx,
+    launch_k(img_conv3x3_bwd_kernel<2>, blocks, 256, smem, s, (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)x, ldx,
                                                        w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx);
   }
   if (int rc = check_launch("img_conv3x3_bwd")) return rc;

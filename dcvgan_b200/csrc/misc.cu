@@ -13,6 +13,7 @@ __device__ __forceinline__ float softplusf_(float x) { return fmaxf(x, 0.f) + lo
 __global__ void gru_fwd_kernel(const float* __restrict__ h0, const float* __restrict__ eps, const float* __restrict__ w_ih,
                                const float* __restrict__ w_hh, const float* __restrict__ b_ih,
                                const float* __restrict__ b_hh, int B, int T, int D, float* __restrict__ hs) {
+  pdl_wait(); pdl_trigger();
   extern __shared__ float sm[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
   float* h = sm + warp * (8 * D);
@@ -53,6 +54,7 @@ __global__ void gru_bwd_kernel(const float* __restrict__ h0, const float* __rest
                                const float* __restrict__ b_hh, int B, int T, int D, float* __restrict__ dw_ih,
                                float* __restrict__ dw_hh, float* __restrict__ db_ih, float* __restrict__ db_hh,
                                int accumulate) {
+  pdl_wait(); pdl_trigger();
   extern __shared__ float sm[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
   const int G = 3 * D;
@@ -124,6 +126,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 loss_kernel(const T* __restrict__ y, int64_t ldy, int64_t n, int kind, float* __restrict__ loss_out, int accumulate,
             T* __restrict__ dy, int64_t lddy, float grad_scale) {
+  pdl_wait(); pdl_trigger();
   __shared__ float red[256];
   float acc = 0.f;
   const float inv_n = 1.f / (float)n;
@@ -178,6 +181,7 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
 
 // Device-side step bookkeeping (CUDA-graph friendly): state = {int64 step; float step_size; float inv_bc2_sqrt}.
 __global__ void adam_advance_kernel(long long* state, float lr, float b1, float b2) {
+  pdl_wait(); pdl_trigger();
   const long long step = ++state[0];
   const double bc1 = 1.0 - pow((double)b1, (double)step);
   const double bc2 = 1.0 - pow((double)b2, (double)step);
@@ -189,6 +193,7 @@ __global__ void adam_advance_kernel(long long* state, float lr, float b1, float 
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(AdamArgs a, float b1, float b2, float eps, float wd, float step_size, float inv_bc2_sqrt, float gscale,
                   const float* __restrict__ dev_scalars) {
+  pdl_wait(); pdl_trigger();
   if (dev_scalars) { step_size = dev_scalars[0]; inv_bc2_sqrt = dev_scalars[1]; }
   int t = 0;
   while (t + 1 < a.ntensors && (int)blockIdx.x >= a.block_start[t + 1]) ++t;
@@ -235,6 +240,7 @@ using namespace dcv;
 template <typename T>
 __global__ void __launch_bounds__(256)
 ingest_u8_kernel(const uint8_t* __restrict__ src, int64_t rows, int C, T* __restrict__ dst, int64_t ld) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = rows * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / C; const int c = (int)(i - row * C);
@@ -245,6 +251,7 @@ ingest_u8_kernel(const uint8_t* __restrict__ src, int64_t rows, int C, T* __rest
 template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 ingest_onehot_kernel(const I* __restrict__ idx, int64_t rows, int C, T* __restrict__ dst, int64_t ld) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = rows * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / C; const int c = (int)(i - row * C);
@@ -256,6 +263,7 @@ ingest_onehot_kernel(const I* __restrict__ idx, int64_t rows, int C, T* __restri
 template <typename T>
 __global__ void __launch_bounds__(256)
 export_u8_kernel(const T* __restrict__ src, int64_t ld, int N, int C, int T_, int64_t hw, uint8_t* __restrict__ dst) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = (int64_t)N * T_ * hw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i % hw; const int64_t nt = i / hw; const int t = (int)(nt % T_); const int64_t n = nt / T_;
@@ -276,7 +284,7 @@ int dcv_gru_traj_fwd(const float* h0, const float* eps, const float* w_ih, const
   if (B == 0) return 0;
   const int nw = 4;
   const int blocks = ceil_div(B, nw);
-  gru_fwd_kernel<<<blocks, nw * 32, nw * 8 * D * sizeof(float), as_stream(stream)>>>(h0, eps, w_ih, w_hh, b_ih, b_hh, B, T, D, hs);
+  launch_k(gru_fwd_kernel, blocks, nw * 32, nw * 8 * D * sizeof(float), as_stream(stream), h0, eps, w_ih, w_hh, b_ih, b_hh, B, T, D, hs);
   return check_launch("gru_fwd");
 }
 
@@ -297,7 +305,7 @@ int dcv_gru_traj_bwd(const float* h0, const float* eps, const float* hs, const f
     DCV_CUDA(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru_smem));
     gru_smem_set = gru_smem;
   }
-  gru_bwd_kernel<<<1, nw * 32, gru_smem, as_stream(stream)>>>(
+  launch_k(gru_bwd_kernel, 1, nw * 32, gru_smem, as_stream(stream), 
       h0, eps, hs, dhs, w_ih, w_hh, b_ih, b_hh, B, T, D, dw_ih, dw_hh, db_ih, db_hh, accumulate);
   return check_launch("gru_bwd");
 }
@@ -307,9 +315,9 @@ int dcv_loss_fwd_bwd(int dtype, const void* y, int64_t ldy, int64_t n, int kind,
   DCV_REQUIRE(n > 0, "loss: empty logits");
   DCV_REQUIRE(kind >= 0 && kind <= 4, "loss: unknown kind %d", kind);
   if (dtype == DCV_F32)
-    loss_kernel<float><<<1, 256, 0, as_stream(stream)>>>((const float*)y, ldy, n, kind, loss_out, accumulate, (float*)dy, lddy, grad_scale);
+    launch_k(loss_kernel<float>, 1, 256, 0, as_stream(stream), (const float*)y, ldy, n, kind, loss_out, accumulate, (float*)dy, lddy, grad_scale);
   else
-    loss_kernel<__nv_bfloat16><<<1, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)y, ldy, n, kind, loss_out, accumulate,
+    launch_k(loss_kernel<__nv_bfloat16>, 1, 256, 0, as_stream(stream), (const __nv_bfloat16*)y, ldy, n, kind, loss_out, accumulate,
                                                                  (__nv_bfloat16*)dy, lddy, grad_scale);
   return check_launch("loss");
 }
@@ -338,7 +346,7 @@ int dcv_adam_multi(int ntensors, float* const* p, const float* const* g, float* 
     if (k == 0) break;
     a.block_start[k] = blocks;
     a.ntensors = k;
-    adam_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, grad_scale, nullptr);
+    launch_k(adam_multi_kernel, blocks, 256, 0, as_stream(stream), a, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, grad_scale, nullptr);
     int rc = check_launch("adam_multi");
     if (rc) return rc;
   }
@@ -349,7 +357,7 @@ int dcv_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, f
                       float weight_decay, void* step_state, float grad_scale, void* stream) {
   DCV_REQUIRE(step_state && (((uintptr_t)step_state) & 7) == 0, "adam: step_state must be an 8-byte aligned 16-byte device buffer");
   if (n <= 0) return 0;
-  adam_advance_kernel<<<1, 1, 0, as_stream(stream)>>>((long long*)step_state, lr, beta1, beta2);
+  launch_k(adam_advance_kernel, 1, 1, 0, as_stream(stream), (long long*)step_state, lr, beta1, beta2);
   int rc = check_launch("adam_advance");
   if (rc) return rc;
   AdamArgs a;
@@ -358,7 +366,7 @@ int dcv_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, f
   const int blocks = (int)((n + ADAM_CHUNK - 1) / ADAM_CHUNK);
   a.block_start[1] = blocks;
   a.ntensors = 1;
-  adam_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, beta1, beta2, eps, weight_decay, 0.f, 0.f, grad_scale,
+  launch_k(adam_multi_kernel, blocks, 256, 0, as_stream(stream), a, beta1, beta2, eps, weight_decay, 0.f, 0.f, grad_scale,
                                                            reinterpret_cast<const float*>((long long*)step_state + 1));
   return check_launch("adam_flat_dev");
 }
@@ -374,8 +382,8 @@ static inline int io_blocks(int64_t total) { int64_t b = (total + 1023) / 1024; 
 int dcv_ingest_u8(int dtype, const void* src, int64_t rows, int C, void* dst, int64_t ld, void* stream) {
   DCV_REQUIRE(src && dst && C >= 1 && ld >= C, "ingest_u8: bad arguments");
   if (rows * C == 0) return 0;
-  if (dtype == DCV_F32) ingest_u8_kernel<float><<<io_blocks(rows * C), 256, 0, as_stream(stream)>>>((const uint8_t*)src, rows, C, (float*)dst, ld);
-  else ingest_u8_kernel<__nv_bfloat16><<<io_blocks(rows * C), 256, 0, as_stream(stream)>>>((const uint8_t*)src, rows, C, (__nv_bfloat16*)dst, ld);
+  if (dtype == DCV_F32) launch_k(ingest_u8_kernel<float>, io_blocks(rows * C), 256, 0, as_stream(stream), (const uint8_t*)src, rows, C, (float*)dst, ld);
+  else launch_k(ingest_u8_kernel<__nv_bfloat16>, io_blocks(rows * C), 256, 0, as_stream(stream), (const uint8_t*)src, rows, C, (__nv_bfloat16*)dst, ld);
   return check_launch("ingest_u8");
 }
 
@@ -386,11 +394,11 @@ int dcv_ingest_onehot(int dtype, const void* idx, int idx_bytes, int64_t rows, i
   const int nb = io_blocks(rows * C);
   cudaStream_t st = as_stream(stream);
   if (dtype == DCV_F32) {
-    if (idx_bytes == 1) ingest_onehot_kernel<float, uint8_t><<<nb, 256, 0, st>>>((const uint8_t*)idx, rows, C, (float*)dst, ld);
-    else ingest_onehot_kernel<float, long long><<<nb, 256, 0, st>>>((const long long*)idx, rows, C, (float*)dst, ld);
+    if (idx_bytes == 1) launch_k(ingest_onehot_kernel<float, uint8_t>, nb, 256, 0, st, (const uint8_t*)idx, rows, C, (float*)dst, ld);
+    else launch_k(ingest_onehot_kernel<float, long long>, nb, 256, 0, st, (const long long*)idx, rows, C, (float*)dst, ld);
   } else {
-    if (idx_bytes == 1) ingest_onehot_kernel<__nv_bfloat16, uint8_t><<<nb, 256, 0, st>>>((const uint8_t*)idx, rows, C, (__nv_bfloat16*)dst, ld);
-    else ingest_onehot_kernel<__nv_bfloat16, long long><<<nb, 256, 0, st>>>((const long long*)idx, rows, C, (__nv_bfloat16*)dst, ld);
+    if (idx_bytes == 1) launch_k(ingest_onehot_kernel<__nv_bfloat16, uint8_t>, nb, 256, 0, st, (const uint8_t*)idx, rows, C, (__nv_bfloat16*)dst, ld);
+    else launch_k(ingest_onehot_kernel<__nv_bfloat16, long long>, nb, 256, 0, st, (const long long*)idx, rows, C, (__nv_bfloat16*)dst, ld);
   }
   return check_launch("ingest_onehot");
 }
@@ -399,8 +407,8 @@ int dcv_export_u8(int dtype, const void* src, int64_t ld, int N, int C, int T_, 
   DCV_REQUIRE(src && dst && C >= 1 && ld >= C, "export_u8: bad arguments");
   const int64_t total = (int64_t)N * T_ * hw;
   if (total == 0) return 0;
-  if (dtype == DCV_F32) export_u8_kernel<float><<<io_blocks(total * 2), 256, 0, as_stream(stream)>>>((const float*)src, ld, N, C, T_, hw, (uint8_t*)dst);
-  else export_u8_kernel<__nv_bfloat16><<<io_blocks(total * 2), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, ld, N, C, T_, hw, (uint8_t*)dst);
+  if (dtype == DCV_F32) launch_k(export_u8_kernel<float>, io_blocks(total * 2), 256, 0, as_stream(stream), (const float*)src, ld, N, C, T_, hw, (uint8_t*)dst);
+  else launch_k(export_u8_kernel<__nv_bfloat16>, io_blocks(total * 2), 256, 0, as_stream(stream), (const __nv_bfloat16*)src, ld, N, C, T_, hw, (uint8_t*)dst);
   return check_launch("export_u8");
 }
 

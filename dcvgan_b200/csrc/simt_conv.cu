@@ -19,6 +19,7 @@ template <typename T, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256)
 conv_simt_kernel(ConvP p, const T* __restrict__ x, int64_t ldx, const float* __restrict__ wp,
                  T* __restrict__ y, int64_t ldy, int act, float slope) {
+  pdl_wait(); pdl_trigger();
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
   constexpr int EA = BM * BK / 256;          // A elements per thread
   constexpr int TPR = BK / EA;               // threads per A row
@@ -142,6 +143,7 @@ template <typename T, int BA, int BB, int TA, int TB>
 __global__ void __launch_bounds__(256)
 wgrad_simt_kernel(WgradP p, const T* __restrict__ xl, int64_t ldl, const T* __restrict__ xs, int64_t lds,
                   float* __restrict__ partial) {
+  pdl_wait(); pdl_trigger();
   static_assert((BA / TA) * (BB / TB) == 256, "256 threads");
   __shared__ float As[BK][BA + 4];
   __shared__ float Bs[BK][BB + 4];
@@ -226,6 +228,7 @@ wgrad_simt_kernel(WgradP p, const T* __restrict__ xl, int64_t ldl, const T* __re
 __global__ void __launch_bounds__(256)
 wgrad_reduce_flat_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, WeightWin win,
                          float* __restrict__ dw, int64_t s_l, int64_t s_s, int64_t s_tap, int accumulate) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = (int64_t)taps * Cl * Cs;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
@@ -254,6 +257,7 @@ struct ReduceParts { int n; ReducePart p[REDUCE_MULTI_MAX]; };
 
 __global__ void __launch_bounds__(256)
 wgrad_reduce_multi_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, const __grid_constant__ ReduceParts parts) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = (int64_t)taps * Cl * Cs;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cs = (int)(i % Cs); const int cl = (int)((i / Cs) % Cl); const int tap = (int)(i / ((int64_t)Cs * Cl));
@@ -290,7 +294,7 @@ int wgrad_reduce_multi(const float* partial, int splits, const dcv_geom* g, int 
   const int taps = g->kt * g->kh * g->kw;
   const int64_t total = (int64_t)taps * g->Cl * g->Cs;
   int fb = (int)((total + 255) / 256); if (fb > 148 * 16) fb = 148 * 16;
-  wgrad_reduce_multi_kernel<<<fb, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, parts);
+  launch_k(wgrad_reduce_multi_kernel, fb, 256, 0, s, partial, splits, taps, g->Cl, g->Cs, parts);
   return check_launch("wgrad_reduce_multi");
 }
 
@@ -299,6 +303,7 @@ int wgrad_reduce_multi(const float* partial, int splits, const dcv_geom* g, int 
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, WeightWin win,
                     float* __restrict__ dw, int64_t s_l, int64_t s_s, int64_t s_tap, int accumulate) {
+  pdl_wait(); pdl_trigger();
   __shared__ float red[32][9];
   const int64_t total = (int64_t)taps * Cl * Cs;
   const int tx = threadIdx.x % 8, ty = threadIdx.x / 8;
@@ -328,6 +333,7 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int
 
 __global__ void pack_weight_simt_kernel(const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap,
                                         int Cl, int Cs, WeightWin win, int taps, int scatter, float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = (int64_t)taps * Cl * Cs;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int tap, cl, cs;
@@ -349,10 +355,10 @@ static int launch_conv_simt(const dcv_geom* g, int dir, const void* x, int64_t l
   if (Mmax == 0) return 0;
   if (p.Nc <= 8) {
     dim3 grid(ceil_div(Mmax, 256), ceil_div(p.Nc, 4), phases);
-    conv_simt_kernel<T, 256, 4, 1, 4><<<grid, 256, 0, s>>>(p, (const T*)x, ldx, (const float*)wp, (T*)y, ldy, act, slope);
+    launch_k(conv_simt_kernel<T, 256, 4, 1, 4>, grid, 256, 0, s, p, (const T*)x, ldx, (const float*)wp, (T*)y, ldy, act, slope);
   } else {
     dim3 grid(ceil_div(Mmax, 64), ceil_div(p.Nc, 64), phases);
-    conv_simt_kernel<T, 64, 64, 4, 4><<<grid, 256, 0, s>>>(p, (const T*)x, ldx, (const float*)wp, (T*)y, ldy, act, slope);
+    launch_k(conv_simt_kernel<T, 64, 64, 4, 4>, grid, 256, 0, s, p, (const T*)x, ldx, (const float*)wp, (T*)y, ldy, act, slope);
   }
   return check_launch("conv_simt");
 }
@@ -369,11 +375,11 @@ int wgrad_reduce_win(const float* partial, int splits, const dcv_geom* g, Weight
   const int64_t total = (int64_t)taps * g->Cl * g->Cs;
   if (splits <= 16 || total >= 16384) {      // enough elements to fill the machine with one thread per element
     int fb = (int)((total + 255) / 256); if (fb > 148 * 16) fb = 148 * 16;
-    wgrad_reduce_flat_kernel<<<fb, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, win, dw, s_l, s_s, s_tap, accumulate);
+    launch_k(wgrad_reduce_flat_kernel, fb, 256, 0, s, partial, splits, taps, g->Cl, g->Cs, win, dw, s_l, s_s, s_tap, accumulate);
     return check_launch("wgrad_reduce");
   }
   int blocks = (int)((total + 7) / 8); if (blocks > 148 * 16) blocks = 148 * 16;
-  wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(partial, splits, taps, g->Cl, g->Cs, win, dw, s_l, s_s, s_tap, accumulate);
+  launch_k(wgrad_reduce_kernel, blocks, 256, 0, s, partial, splits, taps, g->Cl, g->Cs, win, dw, s_l, s_s, s_tap, accumulate);
   return check_launch("wgrad_reduce");
 }
 
@@ -415,23 +421,23 @@ static int launch_wgrad_simt(const dcv_geom* g, const void* xl, int64_t ldl, con
   if (g->Cl <= 8) {
     p.tilesB = ceil_div(g->Cs, 64);
     dim3 grid(ceil_div(g->Cl, 4) * p.tilesB, taps, splits);
-    wgrad_simt_kernel<T, 4, 64, 1, 1><<<grid, 256, 0, s>>>(p, (const T*)xl, ldl, (const T*)xs, lds, partial);
+    launch_k(wgrad_simt_kernel<T, 4, 64, 1, 1>, grid, 256, 0, s, p, (const T*)xl, ldl, (const T*)xs, lds, partial);
   } else if (g->Cs <= 8) {
     p.tilesB = ceil_div(g->Cs, 4);
     dim3 grid(ceil_div(g->Cl, 64) * p.tilesB, taps, splits);
-    wgrad_simt_kernel<T, 64, 4, 1, 1><<<grid, 256, 0, s>>>(p, (const T*)xl, ldl, (const T*)xs, lds, partial);
+    launch_k(wgrad_simt_kernel<T, 64, 4, 1, 1>, grid, 256, 0, s, p, (const T*)xl, ldl, (const T*)xs, lds, partial);
   } else if (g->Cl <= 16) {
     p.tilesB = ceil_div(g->Cs, 64);
     dim3 grid(p.tilesB, taps, splits);
-    wgrad_simt_kernel<T, 16, 64, 2, 2><<<grid, 256, 0, s>>>(p, (const T*)xl, ldl, (const T*)xs, lds, partial);
+    launch_k(wgrad_simt_kernel<T, 16, 64, 2, 2>, grid, 256, 0, s, p, (const T*)xl, ldl, (const T*)xs, lds, partial);
   } else if (g->Cs <= 16) {
     p.tilesB = 1;
     dim3 grid(ceil_div(g->Cl, 64), taps, splits);
-    wgrad_simt_kernel<T, 64, 16, 2, 2><<<grid, 256, 0, s>>>(p, (const T*)xl, ldl, (const T*)xs, lds, partial);
+    launch_k(wgrad_simt_kernel<T, 64, 16, 2, 2>, grid, 256, 0, s, p, (const T*)xl, ldl, (const T*)xs, lds, partial);
   } else {
     p.tilesB = ceil_div(g->Cs, 64);
     dim3 grid(ceil_div(g->Cl, 64) * p.tilesB, taps, splits);
-    wgrad_simt_kernel<T, 64, 64, 4, 4><<<grid, 256, 0, s>>>(p, (const T*)xl, ldl, (const T*)xs, lds, partial);
+    launch_k(wgrad_simt_kernel<T, 64, 64, 4, 4>, grid, 256, 0, s, p, (const T*)xl, ldl, (const T*)xs, lds, partial);
   }
   return check_launch("wgrad_simt");
 }
@@ -462,7 +468,7 @@ int pack_weight_simt(const dcv_geom* g, int dir, const float* w, int64_t s_l, in
   const int taps = g->kt * g->kh * g->kw;
   const int64_t total = (int64_t)taps * g->Cl * g->Cs;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weight_simt_kernel<<<blocks, 256, 0, s>>>(w, s_l, s_s, s_tap, g->Cl, g->Cs, win, taps, dir == DCV_DIR_SCATTER, out);
+  launch_k(pack_weight_simt_kernel, blocks, 256, 0, s, w, s_l, s_s, s_tap, g->Cl, g->Cs, win, taps, dir == DCV_DIR_SCATTER, out);
   return check_launch("pack_weight_simt");
 }
 

@@ -32,16 +32,18 @@ namespace dcv {
 // Result-preserving tuning switches (row-halo sharing off, forced M-tile count, direct-store epilogue, extra wgrad split
 // waves ...) are explicit process state set through dcv_set_tuning(), never read from the environment; the parity tests
 // flip them to cover every code path of the kernels (tests/test_ops_gpu.py::test_conv_tcgen05_kernel_variants).
-struct Tuning { int nohalo, mt, no_tma_store, no_narrow_tma_store, wgrad_waves, no_gemv, no_tapgroup, no_fused_stats, sm_reserve; };
-static Tuning g_tune = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+struct Tuning { int nohalo, mt, no_tma_store, no_narrow_tma_store, wgrad_waves, no_gemv, no_tapgroup, no_fused_stats, sm_reserve, no_pdl; };
+static Tuning g_tune = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 int set_tuning(const char* key, int value) {
   struct { const char* k; int* v; } tab[] = {{"nohalo", &g_tune.nohalo}, {"mt", &g_tune.mt}, {"no_tma_store", &g_tune.no_tma_store},
       {"no_narrow_tma_store", &g_tune.no_narrow_tma_store}, {"wgrad_waves", &g_tune.wgrad_waves}, {"no_gemv", &g_tune.no_gemv},
-      {"no_tapgroup", &g_tune.no_tapgroup}, {"no_fused_stats", &g_tune.no_fused_stats}, {"sm_reserve", &g_tune.sm_reserve}};
+      {"no_tapgroup", &g_tune.no_tapgroup}, {"no_fused_stats", &g_tune.no_fused_stats}, {"sm_reserve", &g_tune.sm_reserve},
+      {"no_pdl", &g_tune.no_pdl}};
   for (auto& t : tab) if (!strcmp(t.k, key)) { *t.v = value; return 0; }
   DCV_REQUIRE(false, "dcv_set_tuning: unknown key '%s'", key);
 }
 int tuning_sm_reserve() { return g_tune.sm_reserve; }
+bool pdl_enabled() { return g_tune.no_pdl == 0; }
 
 #ifdef DCV_EXPERIMENTS
 static inline const char* exp_env(const char* name) { return getenv(name); }
@@ -377,6 +379,10 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail;
+  // global memory is only touched from here on
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     const bool leader = elect_one();
@@ -778,6 +784,7 @@ static ConvPersFn conv_pers_variant(int ks, int mt, int hg) {
 __global__ void __launch_bounds__(256)
 head_gemv_kernel(ConvP c, const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                  __nv_bfloat16* __restrict__ y, int64_t ldy, int act, float slope) {
+  pdl_wait(); pdl_trigger();
   const int lane = threadIdx.x % 32;
   const int64_t M = (int64_t)c.N * c.Ot * c.Oh * c.Ow;
   int64_t m = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
@@ -874,6 +881,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail;
+  // global memory is only touched from here on
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // TMA producer.  A stage is many small boxes (one per (tap, channel chunk) block); the 32 lanes issue them in
@@ -1031,6 +1042,7 @@ __device__ __forceinline__ void pack_weight_tc_elem(const ConvP& c, const float*
 __global__ void __launch_bounds__(256)
 pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap, WeightWin win,
                       int npad, int phases, __nv_bfloat16* __restrict__ out) {
+  pdl_wait(); pdl_trigger();
   const int64_t total = (int64_t)npad * c.Kc * phases;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
     pack_weight_tc_elem(c, w, s_l, s_s, s_tap, win, npad, i, out);
@@ -1043,6 +1055,7 @@ struct PackParts { int n; PackPart p[PACK_MULTI_MAX]; };
 
 __global__ void __launch_bounds__(256)
 pack_weight_tc_multi_kernel(ConvP c, const __grid_constant__ PackParts parts, int npad, int phases, __nv_bfloat16* __restrict__ out) {
+  pdl_wait(); pdl_trigger();
   const int64_t per_phase_nk = (int64_t)npad * c.Kc;
   const int64_t total = per_phase_nk * phases;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1071,6 +1084,7 @@ struct PackBatch { int n; PackJob jobs[PACK_BATCH_MAX]; };
 
 __global__ void __launch_bounds__(256)
 pack_weight_tc_batch_kernel(const __grid_constant__ PackBatch b) {
+  pdl_wait(); pdl_trigger();
   int ji = 0;
   while (ji + 1 < b.n && (int)blockIdx.x >= b.jobs[ji + 1].block0) ++ji;
   const PackJob& j = b.jobs[ji];
@@ -1174,7 +1188,7 @@ int pack_weight_tc(const dcv_geom* g, int dir, const float* w, int64_t s_l, int6
   const int phases = c.scatter ? g->st * g->sh * g->sw : 1;
   const int64_t total = (int64_t)tc_npad(c.Nc) * c.Kc * phases;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weight_tc_kernel<<<blocks, 256, 0, s>>>(c, w, s_l, s_s, s_tap, win, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
+  launch_k(pack_weight_tc_kernel, blocks, 256, 0, s, c, w, s_l, s_s, s_tap, win, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
   return check_launch("pack_weight_tc");
 }
 
@@ -1193,7 +1207,7 @@ int pack_weight_tc_multi(const dcv_geom* g, int dir, int n, const float* const* 
   const int phases = c.scatter ? g->st * g->sh * g->sw : 1;
   const int64_t total = (int64_t)tc_npad(c.Nc) * c.Kc * phases;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weight_tc_multi_kernel<<<blocks, 256, 0, s>>>(c, parts, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
+  launch_k(pack_weight_tc_multi_kernel, blocks, 256, 0, s, c, parts, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
   return check_launch("pack_weight_tc_multi");
 }
 
@@ -1216,7 +1230,7 @@ int pack_weight_tc_batch(int n, const dcv_geom* const* geoms, const int* dirs, c
       int nb = (int)((j.total + 255) / 256); if (nb > 148 * 2) nb = 148 * 2;
       blocks += nb;
     }
-    pack_weight_tc_batch_kernel<<<blocks, 256, 0, s>>>(b);
+    launch_k(pack_weight_tc_batch_kernel, blocks, 256, 0, s, b);
     if (int rc = check_launch("pack_weight_tc_batch")) return rc;
   }
   return 0;
@@ -1236,7 +1250,7 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     if (slots_out) return 0;
     DCV_REQUIRE(!stats, "conv_tc: fused statistics are not available for the single-channel head kernel");
     const int64_t M = (int64_t)c.N * c.Ot * c.Oh * c.Ow;          // one warp per logit
-    head_gemv_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(c, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)wp,
+    launch_k(head_gemv_kernel, (unsigned)((M + 7) / 8), 256, 0, s, c, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)wp,
                                                            (__nv_bfloat16*)y, ldy, act, slope);
     return check_launch("head_gemv");
   }
@@ -1373,7 +1387,7 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
       DCV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
       set = smem_p;
     }
-    fn<<<grid_p, TC_THREADS, smem_p, s>>>(mapA, mapB, mapY, p, (__nv_bfloat16*)y);
+    launch_k(fn, grid_p, TC_THREADS, smem_p, s, mapA, mapB, mapY, p, (__nv_bfloat16*)y);
     return check_launch("conv_tc_pers");
   }
 
@@ -1477,7 +1491,7 @@ int wgrad_tc(const dcv_geom* g, const void* xl, int64_t ldl, const void* xs, int
     smem_set = smem;
   }
   dim3 grid(ceil_div(ceil_div(p.blocksA_total, p.nA), p.G), ceil_div(p.blocksB_total, p.nbB), splits);
-  wgrad_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mapL, mapS, p, (float*)ws);
+  launch_k(wgrad_tc_kernel, grid, TC_THREADS, smem, s, mapL, mapS, p, (float*)ws);
   rc = check_launch("wgrad_tc");
   if (rc) return rc;
   if (!dw) return 0;   // partial sums only; the caller reduces them (dcv_wgrad_reduce_sub)

@@ -131,7 +131,8 @@ def test_conv_tcgen05(case):
     _run_case(_ops(), case, torch.bfloat16, True, 1e-2)
 
 
-VARIANTS = [{"nohalo": 1}, {"mt": 1}, {"mt": 4}, {"no_tma_store": 1}, {"wgrad_waves": 2}, {"no_tapgroup": 1}, {"sm_reserve": 16}]
+VARIANTS = [{"nohalo": 1}, {"mt": 1}, {"mt": 4}, {"no_tma_store": 1}, {"wgrad_waves": 2}, {"no_tapgroup": 1}, {"sm_reserve": 16},
+            {"no_pdl": 1}]
 
 
 @pytest.mark.parametrize("tune", VARIANTS, ids=["+".join(f"{k}={v}" for k, v in e.items()) for e in VARIANTS])
@@ -220,7 +221,7 @@ def test_img_conv_direct_kernels(cin, n, hw, slice_out):
     H, W = hw
     spec = ops.ConvSpec("conv", cin, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1))
     x = bf16_round(torch.randn(n, cin, H, W)).requires_grad_(True)
-    w = (torch.randn(64, cin, 3, 3) * 0.2).requires_grad_(True)           # fp32 master weight, used unrounded
+    w = bf16_round(torch.randn(64, cin, 3, 3) * 0.2).requires_grad_(True)  # the kernels round the fp32 master weight to bf16
     y_ref = F.leaky_relu(F.conv2d(x, w, padding=1), 0.01)
     dy = bf16_round(torch.randn_like(y_ref))
     y_ref.backward(dy)
@@ -236,8 +237,13 @@ def test_img_conv_direct_kernels(cin, n, hw, slice_out):
     wdev = w.detach().cuda().contiguous()
     ops.img_conv_fwd(spec, g, xa, wdev, ya, ACT_LEAKY, 0.01)
     e_fwd = rel_err(from_act(ya), y_ref.detach().unsqueeze(2))
-    # backward consumes the STORED (bf16) activation for the LeakyReLU sign, like the reference consumes its own output
+    # The backward takes the LeakyReLU sign from the stored activation.  Fed with the kernel's own bf16 output the ~0.2 % of
+    # elements whose pre-activation lies within rounding distance of zero change sign against the fp32 reference and their
+    # dz changes by a factor 100 (measured 3e-2 in dx / dw); the arithmetic is therefore checked on the reference's output
+    # rounded to bf16 (same signs), the self-consistent case only loosely.
     dya = to_act(dy, torch.bfloat16)
+    ya_own = ya
+    ya = to_act(y_ref.detach().unsqueeze(2), torch.bfloat16)
     dxa = ops.Act.empty(n, 1, H, W, cin, torch.bfloat16)
     dw = torch.full_like(wdev, 3.0)
     ops.img_conv_bwd(spec, g, dya, ya, xa, wdev, ACT_LEAKY, 0.01, dw, False, dxa)
@@ -249,8 +255,13 @@ def test_img_conv_direct_kernels(cin, n, hw, slice_out):
     e_dw2 = rel_err(dw.cpu(), 2 * w.grad)
     pad = dxa.padded_to(dxa.cp).torch()[..., dxa.c:]
     assert float(pad.float().abs().max()) == 0.0                           # padding channels of dx stay zero
-    print(f"img_conv C={cin} n={n} {H}x{W}: fwd {e_fwd:.2e} dx {e_dx:.2e} dw {e_dw:.2e} dw2 {e_dw2:.2e}")
-    assert e_fwd < 5e-3 and e_dx < 5e-3 and e_dw < 5e-3 and e_dw2 < 5e-3
+    dxo = ops.Act.empty(n, 1, H, W, cin, torch.bfloat16)
+    dwo = torch.zeros_like(wdev)
+    ops.img_conv_bwd(spec, g, dya, ya_own, xa, wdev, ACT_LEAKY, 0.01, dwo, False, dxo)
+    torch.cuda.synchronize()
+    e_own = max(rel_err(from_act(dxo), x.grad.unsqueeze(2)), rel_err(dwo.cpu(), w.grad))
+    print(f"img_conv C={cin} n={n} {H}x{W}: fwd {e_fwd:.2e} dx {e_dx:.2e} dw {e_dw:.2e} dw2 {e_dw2:.2e}; with its own stored output {e_own:.2e}")
+    assert e_fwd < 5e-3 and e_dx < 5e-3 and e_dw < 5e-3 and e_dw2 < 5e-3 and e_own < 6e-2
 
 
 def test_conv_channel_slices():

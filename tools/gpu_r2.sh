@@ -21,6 +21,10 @@ for st in $STAGES; do
       timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
     benchfast)
       timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-eager > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
+    benchnopdl)
+      timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-eager --no-roofline --tune no_pdl=1 > gpurun_out/${TAG}_bench_nopdl.json 2> gpurun_out/${TAG}_bench_nopdl.err; echo "bench nopdl rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 700 gpurun_out/${TAG}_bench_nopdl.json;;
+    benchimg)
+      DCV_IMG_CONV=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-eager --no-roofline > gpurun_out/${TAG}_bench_img.json 2> gpurun_out/${TAG}_bench_img.err; echo "bench img rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 700 gpurun_out/${TAG}_bench_img.json;;
     refarm)
       timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_ref.err; echo "refarm rc=$?" | tee -a gpurun_out/${TAG}_rc.log; cat gpurun_out/${TAG}_bench_reference_arm.json;;
     launches)
