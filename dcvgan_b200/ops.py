@@ -382,7 +382,7 @@ def wgrad(spec, g, xl, xs, dw, accumulate=False, impl=None):
 
 
 # ------------------------------------------------------------------------------------ direct image-side convolution
-IMG_CONV = os.environ.get("DCV_IMG_CONV", "0") == "1"   # r2a: 0.165 ms fwd / 0.83 ms bwd at B=32 - slower than the tensor-core tiles (0.167 / 0.42): opt-in until rewritten
+IMG_CONV = os.environ.get("DCV_NO_IMG_CONV", "0") != "1"
 
 
 def img_conv_ok(spec, g, x, y):

@@ -77,7 +77,7 @@ long long dcv_launch_count(void);
 /* Result-preserving tuning switches of the tcgen05 kernels (process-wide; never read from the environment):
  * "nohalo", "mt" (0 = automatic, 1/2/4 forced M tiles per work item), "no_tma_store", "no_narrow_tma_store",
  * "wgrad_waves", "no_gemv", "no_tapgroup", "no_fused_stats", "sm_reserve" (SMs the persistent kernels leave free,
- * for a collective running beside them), "no_pdl" (launch without programmatic dependent launch).  The parity tests flip them to cover every kernel path. */
+ * for a collective running beside them), "pdl" (1 = launch with the programmatic-dependent-launch attribute; measured slower, off by default).  The parity tests flip them to cover every kernel path. */
 int dcv_set_tuning(const char* key, int value);
 
 /* ---- weight packing -------------------------------------------------------------------------

@@ -132,7 +132,7 @@ def test_conv_tcgen05(case):
 
 
 VARIANTS = [{"nohalo": 1}, {"mt": 1}, {"mt": 4}, {"no_tma_store": 1}, {"wgrad_waves": 2}, {"no_tapgroup": 1}, {"sm_reserve": 16},
-            {"no_pdl": 1}]
+            {"pdl": 1}]
 
 
 @pytest.mark.parametrize("tune", VARIANTS, ids=["+".join(f"{k}={v}" for k, v in e.items()) for e in VARIANTS])

@@ -14,17 +14,17 @@ for st in $STAGES; do
     curves)
       DCV_CURVE_DUMP=gpurun_out/${TAG}_curves timeout 1500 python -m pytest tests/test_curves_gpu.py -m gpu -q -s > gpurun_out/${TAG}_curves.log 2>&1; echo "curves rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_curves.log | tail -30;;
     imgtest)
-      DCV_IMG_CONV=1 timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_nets_gpu.py tests/test_timed_path_gpu.py -m gpu -q -s -k "img_conv or full_width or generators_match or graph" > gpurun_out/${TAG}_imgtest.log 2>&1; echo "imgtest rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_imgtest.log | tail -25;;
+      timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_nets_gpu.py tests/test_timed_path_gpu.py -m gpu -q -s -k "img_conv or full_width or generators_match or graph" > gpurun_out/${TAG}_imgtest.log 2>&1; echo "imgtest rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_imgtest.log | tail -25;;
     imglayers)
-      DCV_IMG_CONV=1 timeout 600 python tools/layer_bench.py mug-depth 32 > gpurun_out/${TAG}_layers_img.md 2>&1; echo "imglayers rc=$?" | tee -a gpurun_out/${TAG}_rc.log; head -12 gpurun_out/${TAG}_layers_img.md;;
+      timeout 600 python tools/layer_bench.py mug-depth 32 > gpurun_out/${TAG}_layers_img.md 2>&1; echo "imglayers rc=$?" | tee -a gpurun_out/${TAG}_rc.log; head -12 gpurun_out/${TAG}_layers_img.md;;
     bench)
       timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
     benchfast)
       timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-eager > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
-    benchnopdl)
-      timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-eager --no-roofline --tune no_pdl=1 > gpurun_out/${TAG}_bench_nopdl.json 2> gpurun_out/${TAG}_bench_nopdl.err; echo "bench nopdl rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 700 gpurun_out/${TAG}_bench_nopdl.json;;
+    benchpdl)
+      timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-eager --no-roofline --tune pdl=1 > gpurun_out/${TAG}_bench_pdl.json 2> gpurun_out/${TAG}_bench_pdl.err; echo "bench pdl rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 700 gpurun_out/${TAG}_bench_pdl.json;;
     benchimg)
-      DCV_IMG_CONV=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-eager --no-roofline > gpurun_out/${TAG}_bench_img.json 2> gpurun_out/${TAG}_bench_img.err; echo "bench img rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 700 gpurun_out/${TAG}_bench_img.json;;
+      DCV_NO_IMG_CONV=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-eager --no-roofline > gpurun_out/${TAG}_bench_img.json 2> gpurun_out/${TAG}_bench_img.err; echo "bench img rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 700 gpurun_out/${TAG}_bench_img.json;;
     refarm)
       timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_ref.err; echo "refarm rc=$?" | tee -a gpurun_out/${TAG}_rc.log; cat gpurun_out/${TAG}_bench_reference_arm.json;;
     launches)
