@@ -46,7 +46,7 @@ SIGNATURES = {
     "dcv_ingest_u8": (_i, [_i, _vp, _i64, _i, _vp, _i64, _vp]),
     "dcv_ingest_onehot": (_i, [_i, _vp, _i, _i64, _i, _vp, _i64, _vp]),
     "dcv_export_u8": (_i, [_i, _vp, _i64, _i, _i, _i, _i64, _vp, _vp]),
-    "dcv_img_conv_supported": (_i, [_G]),
+    "dcv_img_conv_supported": (_i, [_G, _i]),
     "dcv_img_conv_bwd_workspace_bytes": (_i64, [_G]),
     "dcv_img_conv_fwd": (_i, [_G, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i, _f, _vp]),
     "dcv_img_conv_bwd": (_i, [_G, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i, _f, _vp, _i, _vp, _i64, _vp, _i64, _vp]),

@@ -41,7 +41,7 @@ int wgrad_reduce_multi(const float*, int, const dcv_geom*, int, float* const*, c
                        const int*, const int*, const int*, const int*, cudaStream_t);
 int conv_tc_supported(const dcv_geom*, int);
 int set_tuning(const char*, int);
-int img_conv_supported(const dcv_geom*);
+int img_conv_supported_for(const dcv_geom*, int);
 int64_t img_conv_bwd_ws_bytes(const dcv_geom*);
 int img_conv_fwd(const dcv_geom*, const void*, int64_t, const float*, int64_t, int64_t, int64_t, void*, int64_t, int, float, cudaStream_t);
 int img_conv_bwd(const dcv_geom*, const void*, int64_t, const void*, int64_t, const void*, int64_t, const float*, int64_t, int64_t,
@@ -81,7 +81,7 @@ const char* dcv_last_error(void) { return g_err; }
 
 long long dcv_launch_count(void) { return g_launches; }
 
-int dcv_img_conv_supported(const dcv_geom* g) { return g && check_geom(g) == 0 ? img_conv_supported(g) : 0; }
+int dcv_img_conv_supported(const dcv_geom* g, int what) { return g && check_geom(g) == 0 ? img_conv_supported_for(g, what) : 0; }
 int64_t dcv_img_conv_bwd_workspace_bytes(const dcv_geom* g) { return g ? img_conv_bwd_ws_bytes(g) : -1; }
 int dcv_img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
                      void* y, int64_t ldy, int act, float slope, void* stream) {

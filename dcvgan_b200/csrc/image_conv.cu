@@ -78,75 +78,85 @@ __device__ __forceinline__ uint16_t im2col_at(const __nv_bfloat16* xs, int WP, i
 }
 
 // ------------------------------------------------------------------------------------------ forward
-template <int C>
-__global__ void __launch_bounds__(256)
+// C real input channels (1..3), NCO output channels (64 or 128, processed as halves of 64)
+template <int C, int NCO>
+__global__ void __launch_bounds__(256, 2)
 img_conv3x3_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t s_l, int64_t s_s,
                        int N, int H, int W, __nv_bfloat16* __restrict__ y, int64_t ldy, int act, float slope) {
   pdl_wait(); pdl_trigger();
   constexpr int KS = (9 * C + 15) / 16;                        // k16 steps
+  constexpr int NH = NCO / 64;                                 // halves of 64 output channels
   __shared__ __align__(16) __nv_bfloat16 xs[(IMG_BAND + 2) * 66 * C];
   __shared__ __align__(16) uint32_t stg[IMG_WARPS][16][36];     // warp-private 16 x 64 bf16 tile, 144-byte row pitch
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, g = lane / 4, q = lane % 4;
   const int bands = H / IMG_BAND;
   const int WP = W + 2;
-  // B fragments: B[k][co] = w[co][ci][tap] (k = tap*C + ci), bf16
-  uint32_t bw[KS][8][2];
+  // B fragments: B[k][co] = w[co][ci][tap] (k = tap*C + ci), bf16; kept in shared memory in fragment order (one word per lane:
+  // conflict-free), 64-128 registers otherwise
+  __shared__ uint32_t bw[NH][KS][8][2][32];
 #pragma unroll
-  for (int s = 0; s < KS; ++s)
+  for (int hf = 0; hf < NH; ++hf)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int s = 0; s < KS; ++s)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[2];
+      for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int k = 16 * s + 2 * q + 8 * h + e;
-          v[e] = k < 9 * C ? w[(8 * j + g) * s_s + (k % C) * s_l + (k / C)] : 0.f;
+        for (int h = 0; h < 2; ++h) {
+          if ((((hf * KS + s) * 8 + j) * 2 + h) % IMG_WARPS != warp) continue;      // the fragments are spread over the warps
+          float v[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k = 16 * s + 2 * q + 8 * h + e;
+            v[e] = k < 9 * C ? w[(64 * hf + 8 * j + g) * s_s + (k % C) * s_l + (k / C)] : 0.f;
+          }
+          bw[hf][s][j][h][lane] = pack_bf16x2(v[0], v[1]);
         }
-        bw[s][j][h] = pack_bf16x2(v[0], v[1]);
-      }
   const int tiles_w = W / 16, tiles = IMG_BAND * tiles_w;
   // persistent over (image, band) items: the weight fragments are built once per block
   for (int item = blockIdx.x; item < N * bands; item += gridDim.x) {
-  const int n = item / bands, r0 = (item % bands) * IMG_BAND;
-  __syncthreads();                               // the previous item's readers of xs are done
-  stage_window<C>(xs, x, ldx, n, r0, H, W);
-  __syncthreads();
-  for (int t = warp; t < tiles; t += IMG_WARPS) {
-    const int lr = t / tiles_w, w0 = (t % tiles_w) * 16;
-    float acc[8][4];
+    const int n = item / bands, r0 = (item % bands) * IMG_BAND;
+    __syncthreads();                               // the previous item's readers of xs are done
+    stage_window<C>(xs, x, ldx, n, r0, H, W);
+    __syncthreads();
+    for (int t = warp; t < tiles; t += IMG_WARPS) {
+      const int lr = t / tiles_w, w0 = (t % tiles_w) * 16;
+      uint32_t a[KS][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+      for (int s = 0; s < KS; ++s)
 #pragma unroll
-    for (int s = 0; s < KS; ++s) {
-      uint32_t a[4];
+        for (int h = 0; h < 2; ++h)              // column half (k, k + 8)
 #pragma unroll
-      for (int h = 0; h < 2; ++h)              // column half (k, k + 8)
+          for (int rr = 0; rr < 2; ++rr) {       // row half (g, g + 8)
+            const int k = 16 * s + 2 * q + 8 * h;
+            const uint32_t lo = im2col_at<C>(xs, WP, lr, w0 + g + 8 * rr, k), hi = im2col_at<C>(xs, WP, lr, w0 + g + 8 * rr, k + 1);
+            a[s][2 * h + rr] = lo | (hi << 16);
+          }
+      const int64_t pix0 = (int64_t)(n * H + r0 + lr) * W + w0;
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {       // row half (g, g + 8)
-          const int k = 16 * s + 2 * q + 8 * h;
-          const uint32_t lo = im2col_at<C>(xs, WP, lr, w0 + g + 8 * rr, k), hi = im2col_at<C>(xs, WP, lr, w0 + g + 8 * rr, k + 1);
-          a[2 * h + rr] = lo | (hi << 16);
+      for (int hf = 0; hf < NH; ++hf) {
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mma16816(acc[j], a[s][0], a[s][1], a[s][2], a[s][3], bw[hf][s][j][0][lane], bw[hf][s][j][1][lane]);
+        // activation, bf16, warp-private staging (conflict-free: bank = 4 * row + 4 * j + q), then 16-byte global stores
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          stg[warp][g][4 * j + q] = pack_bf16x2(apply_act(acc[j][0], act, slope), apply_act(acc[j][1], act, slope));
+          stg[warp][g + 8][4 * j + q] = pack_bf16x2(apply_act(acc[j][2], act, slope), apply_act(acc[j][3], act, slope));
         }
+        __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) mma16816(acc[j], a[0], a[1], a[2], a[3], bw[s][j][0], bw[s][j][1]);
+        for (int i = 0; i < 4; ++i) {
+          const int row = 4 * i + lane / 8, chunk = lane % 8;
+          const uint4 v = *reinterpret_cast<const uint4*>(&stg[warp][row][4 * chunk]);
+          *reinterpret_cast<uint4*>(y + (pix0 + row) * ldy + 64 * hf + 8 * chunk) = v;
+        }
+        __syncwarp();
+      }
     }
-    // activation, bf16, warp-private staging (conflict-free: bank = 4 * row + 4 * j + q), then 16-byte global stores
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      stg[warp][g][4 * j + q] = pack_bf16x2(apply_act(acc[j][0], act, slope), apply_act(acc[j][1], act, slope));
-      stg[warp][g + 8][4 * j + q] = pack_bf16x2(apply_act(acc[j][2], act, slope), apply_act(acc[j][3], act, slope));
-    }
-    __syncwarp();
-    const int64_t pix0 = (int64_t)(n * H + r0 + lr) * W + w0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = 4 * i + lane / 8, chunk = lane % 8;
-      const uint4 v = *reinterpret_cast<const uint4*>(&stg[warp][row][4 * chunk]);
-      *reinterpret_cast<uint4*>(y + (pix0 + row) * ldy + 8 * chunk) = v;
-    }
-    __syncwarp();
-  }
   }
 }
 
@@ -160,7 +170,9 @@ __device__ __forceinline__ int slot_channel(int s, int sigma) {
   return i < 8 ? 8 * qq + i : 32 + 8 * qq + (i - 8);
 }
 
-template <int C>
+// NCO = channels of the big tensor (64; 128 = weight gradient only, the two channel halves are owned by warps 0-3 / 4-7),
+// DGRAD: also form the data gradient dx
+template <int C, int NCO, bool DGRAD>
 __global__ void __launch_bounds__(256)
 img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const __nv_bfloat16* __restrict__ a, int64_t lda,
                        const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t s_l, int64_t s_s,
@@ -173,26 +185,31 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
   extern __shared__ __align__(16) uint8_t sm_raw[];
   float* Ps = reinterpret_cast<float*>(sm_raw);                                  // [(BAND+2) * W][NP]; later [8 warps][NP][64]
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(Ps + (size_t)(IMG_BAND + 2) * W * NP);
+  static_assert(NCO == 64 || !DGRAD, "the data gradient needs all channels of a pixel in one warp");
+  constexpr int NH = NCO / 64, WPH = IMG_WARPS / NH;             // channel halves, warps per half
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, g = lane / 4, q = lane % 4;
+  const int half = warp / WPH, wsub = warp % WPH;
   const int bands = H / IMG_BAND;
   const int WP = W + 2;
   // B fragments of the data-gradient GEMM: B[k slot][nn] = w[co(s, slot)][ci][tap], nn = tap*C + ci (0 beyond 9*C)
-  uint32_t bw[4][NJ][2];
+  uint32_t bw[DGRAD ? 4 : 1][NJ][2];
+  if (DGRAD) {
 #pragma unroll
-  for (int s = 0; s < 4; ++s)
+    for (int s = 0; s < 4; ++s)
 #pragma unroll
-    for (int j = 0; j < NJ; ++j)
+      for (int j = 0; j < NJ; ++j)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[2];
-        const int nn = 8 * j + g;
+        for (int h = 0; h < 2; ++h) {
+          float v[2];
+          const int nn = 8 * j + g;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int co = slot_channel(s, 2 * q + 8 * h + e);
-          v[e] = nn < NT ? w[co * s_s + (nn % C) * s_l + (nn / C)] : 0.f;
+          for (int e = 0; e < 2; ++e) {
+            const int co = slot_channel(s, 2 * q + 8 * h + e);
+            v[e] = nn < NT ? w[co * s_s + (nn % C) * s_l + (nn / C)] : 0.f;
+          }
+          bw[DGRAD ? s : 0][j][h] = pack_bf16x2(v[0], v[1]);
         }
-        bw[s][j][h] = pack_bf16x2(v[0], v[1]);
-      }
+  }
   float acc[4][NJ][4];                         // dW^T: m tile s (16 channels), n tile j (8 (tap, ci) pairs)
 #pragma unroll
   for (int s = 0; s < 4; ++s)
@@ -206,10 +223,10 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
   __syncthreads();                               // the previous item's readers of xs / Ps are done
   stage_window<C>(xs, x, ldx, n, r0, H, W);
   __syncthreads();
-  for (int t = warp; t < tiles; t += IMG_WARPS) {
+  for (int t = wsub; t < tiles; t += WPH) {
     const int prow = t / tiles_w, w0 = (t % tiles_w) * 16;       // prow 0 / BAND+1 = halo rows
     const int h = r0 - 1 + prow;
-    const bool live = h >= 0 && h < H;                            // warp-uniform
+    const bool live = h >= 0 && h < H && (DGRAD || (prow >= 1 && prow <= IMG_BAND));   // warp-uniform; halo rows only feed the data gradient
     const bool inband = prow >= 1 && prow <= IMG_BAND;
     // dz in A-fragment layout: reg[s][0] rows g (slots 2q,2q+1), [s][1] rows g+8, [s][2] rows g (slots 2q+8,+9), [s][3] rows g+8
     uint32_t dzr[4][4];
@@ -219,9 +236,9 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
         const int64_t pix = (int64_t)(n * H + h) * W + w0 + g + 8 * rr;
         uint4 d[2], o[2];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          d[half] = *reinterpret_cast<const uint4*>(da + pix * ldda + 32 * half + 8 * q);
-          if (act != DCV_ACT_NONE) o[half] = *reinterpret_cast<const uint4*>(a + pix * lda + 32 * half + 8 * q);
+        for (int hf = 0; hf < 2; ++hf) {
+          d[hf] = *reinterpret_cast<const uint4*>(da + pix * ldda + 64 * half + 32 * hf + 8 * q);
+          if (act != DCV_ACT_NONE) o[hf] = *reinterpret_cast<const uint4*>(a + pix * lda + 64 * half + 32 * hf + 8 * q);
         }
         const uint32_t dw_[8] = {d[0].x, d[0].y, d[0].z, d[0].w, d[1].x, d[1].y, d[1].z, d[1].w};
         const uint32_t ow_[8] = {o[0].x, o[0].y, o[0].z, o[0].w, o[1].x, o[1].y, o[1].z, o[1].w};
@@ -240,14 +257,14 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
       for (int s = 0; s < 4; ++s) { dzr[s][0] = dzr[s][1] = dzr[s][2] = dzr[s][3] = 0u; }
     }
     // ---- data gradient partial products P[pixel][nn]
-    if (dx != nullptr) {
+    if (DGRAD && dx != nullptr) {
       float pacc[NJ][4];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) { pacc[j][0] = pacc[j][1] = pacc[j][2] = pacc[j][3] = 0.f; }
 #pragma unroll
       for (int s = 0; s < 4; ++s)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) mma16816(pacc[j], dzr[s][0], dzr[s][1], dzr[s][2], dzr[s][3], bw[s][j][0], bw[s][j][1]);
+        for (int j = 0; j < NJ; ++j) mma16816(pacc[j], dzr[s][0], dzr[s][1], dzr[s][2], dzr[s][3], bw[DGRAD ? s : 0][j][0], bw[DGRAD ? s : 0][j][1]);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         *reinterpret_cast<float2*>(Ps + (size_t)(prow * W + w0 + g) * NP + 8 * j + 2 * q) = make_float2(pacc[j][0], pacc[j][1]);
@@ -278,7 +295,7 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
   }
   __syncthreads();
   // ---- data gradient of the band: dx[h][w][ci] = sum_taps P[h - ky + 1][w - kx + 1][tap][ci]
-  if (dx != nullptr) {
+  if (DGRAD && dx != nullptr) {
     for (int p = threadIdx.x; p < IMG_BAND * W; p += blockDim.x) {
       const int hb = p / W, wq = p % W;
       float s[C];
@@ -315,80 +332,104 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
         for (int e = 0; e < 2; ++e) red[((size_t)warp * NP + 8 * j + 2 * q + e) * IMG_CO + co] = acc[s][j][2 * rr + e];
       }
   __syncthreads();
-  for (int i = threadIdx.x; i < NT * IMG_CO; i += blockDim.x) {
+  for (int i = threadIdx.x; i < NT * NCO; i += blockDim.x) {
+    const int nn = i / NCO, co = i % NCO;
     float s = 0.f;
 #pragma unroll
-    for (int wq = 0; wq < IMG_WARPS; ++wq) s += red[(size_t)wq * NP * IMG_CO + i];
-    partial[(size_t)blockIdx.x * NT * IMG_CO + i] = s;
+    for (int wq = 0; wq < WPH; ++wq) s += red[((size_t)((co / 64) * WPH + wq) * NP + nn) * IMG_CO + (co % 64)];
+    partial[(size_t)blockIdx.x * NT * NCO + i] = s;
   }
 }
 
 // ------------------------------------------------------------------------------------------ host side
-// geometry test: Conv2d(k3, s1, p1) with <= 2 real input channels and exactly 64 output channels, bf16
-int img_conv_supported(const dcv_geom* g) {
+// what = 0: forward-type pass (small-channel L tensor -> S tensor with 64 or 128 channels; Inconv forward, Outconv data
+//           gradient), 1: full backward of Inconv (da, a -> dW, dx; S has 64 channels),
+//           2: weight gradient only (S has 64 or 128 channels; Outconv).  k3 / s1 / p1, 2-D, bf16.
+int img_conv_supported_for(const dcv_geom* g, int what) {
   const int wcl = g->wCl > 0 ? g->wCl : g->Cl, wcs = g->wCs > 0 ? g->wCs : g->Cs;
   if (g->kt != 1 || g->kh != 3 || g->kw != 3 || g->st != 1 || g->sh != 1 || g->sw != 1 || g->pt != 0 || g->ph != 1 || g->pw != 1) return 0;
   if (g->Tl != 1 || g->Ts != 1 || g->Hl != g->Hs || g->Wl != g->Ws) return 0;
-  if (wcl < 1 || wcl > 2 || wcs != IMG_CO || g->Cs != IMG_CO) return 0;
+  if (wcs != g->Cs || (g->Cs != 64 && g->Cs != 128)) return 0;
   if (g->Wl % 16 || g->Hl % IMG_BAND || g->Wl > 64) return 0;
-  return 1;
+  if (what == 1) return wcl >= 1 && wcl <= 2 && g->Cs == 64;
+  return wcl >= 1 && wcl <= 3;
 }
+int img_conv_supported(const dcv_geom* g) { return img_conv_supported_for(g, 1); }
 
-static int bwd_smem_bytes(int C, int W) {
+static int bwd_smem_bytes(int C, int W, bool dgrad) {
   const int np = (9 * C + 7) / 8 * 8;
-  int tile = (IMG_BAND + 2) * W * np, red = IMG_WARPS * np * IMG_CO;
+  int tile = dgrad ? (IMG_BAND + 2) * W * np : 0, red = IMG_WARPS * np * IMG_CO;
   return (tile > red ? tile : red) * (int)sizeof(float) + (IMG_BAND + 2) * (W + 2) * C * 2 + 16;
 }
 
 static int img_items(const dcv_geom* g) { return g->N * (g->Hl / IMG_BAND); }
-// persistent grids: forward 3 blocks / SM (80 registers, 20 KB), backward 2 blocks / SM (116 registers, ~42 KB)
+// persistent grids: forward 2-3 blocks / SM, backward 2 blocks / SM (116 registers, ~42 KB)
 static int img_fwd_blocks(const dcv_geom* g) { const int it = img_items(g); return it < 148 * 3 ? it : 148 * 3; }
 int img_conv_bwd_blocks(const dcv_geom* g) { const int it = img_items(g); return it < 148 * 2 ? it : 148 * 2; }
 
 int64_t img_conv_bwd_ws_bytes(const dcv_geom* g) {
   const int C = g->wCl > 0 ? g->wCl : g->Cl;
-  return (int64_t)img_conv_bwd_blocks(g) * 9 * C * IMG_CO * sizeof(float);
+  return (int64_t)img_conv_bwd_blocks(g) * 9 * C * g->Cs * sizeof(float);
+}
+
+template <int C, int NCO>
+static void launch_fwd(const dcv_geom* g, unsigned blocks, const void* x, int64_t ldx, const float* w, int64_t s_l, int64_t s_s, void* y,
+                       int64_t ldy, int act, float slope, cudaStream_t s) {
+  launch_k(img_conv3x3_fwd_kernel<C, NCO>, blocks, 256, 0, s, (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, (__nv_bfloat16*)y, ldy, act, slope);
 }
 
 int img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, void* y,
                  int64_t ldy, int act, float slope, cudaStream_t s) {
-  DCV_REQUIRE(img_conv_supported(g), "img_conv_fwd: geometry not supported");
+  DCV_REQUIRE(img_conv_supported_for(g, 0), "img_conv_fwd: geometry not supported");
   DCV_REQUIRE(s_tap == 1, "img_conv_fwd: taps of the master weight must be contiguous");
   DCV_REQUIRE((((uintptr_t)y) & 15) == 0 && ldy % 8 == 0, "img_conv_fwd: output must be 16-byte aligned");
   const int C = g->wCl > 0 ? g->wCl : g->Cl;
   const unsigned blocks = (unsigned)img_fwd_blocks(g);
-  if (C == 1)
-    launch_k(img_conv3x3_fwd_kernel<1>, blocks, 256, 0, s, (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, (__nv_bfloat16*)y, ldy, act, slope);
-  else
-    launch_k(img_conv3x3_fwd_kernel<2>, blocks, 256, 0, s, (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, (__nv_bfloat16*)y, ldy, act, slope);
+#define DCV_IMG_FWD(C_, N_) if (C == C_ && g->Cs == N_) launch_fwd<C_, N_>(g, blocks, x, ldx, w, s_l, s_s, y, ldy, act, slope, s);
+  DCV_IMG_FWD(1, 64) DCV_IMG_FWD(2, 64) DCV_IMG_FWD(3, 64) DCV_IMG_FWD(1, 128) DCV_IMG_FWD(2, 128) DCV_IMG_FWD(3, 128)
+#undef DCV_IMG_FWD
   return check_launch("img_conv3x3_fwd");
+}
+
+template <int C, int NCO, bool DGRAD>
+static int launch_bwd(const dcv_geom* g, int blocks, int smem, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x,
+                      int64_t ldx, const float* w, int64_t s_l, int64_t s_s, int act, float slope, float* partial, void* dx, int64_t lddx,
+                      cudaStream_t s) {
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_bwd_kernel<C, NCO, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  launch_k(img_conv3x3_bwd_kernel<C, NCO, DGRAD>, blocks, 256, smem, s, (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda,
+           (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx);
+  return 0;
 }
 
 int img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x, int64_t ldx,
                  const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, int act, float slope, float* dw, int accumulate,
                  void* dx, int64_t lddx, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  DCV_REQUIRE(img_conv_supported(g), "img_conv_bwd: geometry not supported");
+  const bool dgrad = dx != nullptr;
+  DCV_REQUIRE(img_conv_supported_for(g, dgrad ? 1 : 2), "img_conv_bwd: geometry not supported");
   DCV_REQUIRE(s_tap == 1, "img_conv_bwd: taps of the master weight must be contiguous");
   DCV_REQUIRE(act == DCV_ACT_NONE || act == DCV_ACT_LEAKY, "img_conv_bwd: activation %d", act);
+  DCV_REQUIRE(dgrad || dw, "img_conv_bwd: nothing to compute");
   DCV_REQUIRE(!dw || ws_bytes >= img_conv_bwd_ws_bytes(g), "img_conv_bwd: workspace too small");
-  DCV_REQUIRE((((uintptr_t)da) & 15) == 0 && ldda % 8 == 0 && (((uintptr_t)a) & 15) == 0 && lda % 8 == 0, "img_conv_bwd: da / a must be 16-byte aligned");
+  DCV_REQUIRE((((uintptr_t)da) & 15) == 0 && ldda % 8 == 0, "img_conv_bwd: da must be 16-byte aligned");
+  DCV_REQUIRE(act == DCV_ACT_NONE || ((((uintptr_t)a) & 15) == 0 && lda % 8 == 0), "img_conv_bwd: a must be 16-byte aligned");
   const int C = g->wCl > 0 ? g->wCl : g->Cl;
   const int blocks = img_conv_bwd_blocks(g);
-  const int smem = bwd_smem_bytes(C, g->Wl);
+  const int smem = bwd_smem_bytes(C, g->Wl, dgrad);
   float* partial = dw ? (float*)ws : nullptr;
-  static int smem_set[3] = {0, 0, 0};
-  if (C == 1) {
-    if (smem > smem_set[1]) { DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); smem_set[1] = smem; }
-    launch_k(img_conv3x3_bwd_kernel<1>, blocks, 256, smem, s, (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)x, ldx,
-                                                       w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx);
-  } else {
-    if (smem > smem_set[2]) { DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); smem_set[2] = smem; }
-    launch_k(img_conv3x3_bwd_kernel<2>, blocks, 256, smem, s, (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)x, ldx,
-                                                       w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx);
-  }
-  if (int rc = check_launch("img_conv3x3_bwd")) return rc;
+  int rc = -1;
+#define DCV_IMG_BWD(C_, N_, D_) if (C == C_ && g->Cs == N_ && dgrad == D_) rc = launch_bwd<C_, N_, D_>(g, blocks, smem, da, ldda, a, lda, x, ldx, w, s_l, s_s, act, slope, partial, dx, lddx, s);
+  DCV_IMG_BWD(1, 64, true) DCV_IMG_BWD(2, 64, true)
+  DCV_IMG_BWD(1, 64, false) DCV_IMG_BWD(2, 64, false) DCV_IMG_BWD(3, 64, false) DCV_IMG_BWD(1, 128, false) DCV_IMG_BWD(2, 128, false) DCV_IMG_BWD(3, 128, false)
+#undef DCV_IMG_BWD
+  DCV_REQUIRE(rc != -1, "img_conv_bwd: no kernel for C %d, %d channels, dgrad %d", C, g->Cs, (int)dgrad);
+  if (rc) return rc;
+  if (int r2 = check_launch("img_conv3x3_bwd")) return r2;
   if (!dw) return 0;
-  // partial sums [blocks][9][C][64] == the split layout of wgrad_reduce for a geometry with Cl = C real channels
+  // partial sums [blocks][9][C][Cs] == the split layout of wgrad_reduce for a geometry with Cl = C real channels
   dcv_geom g2 = *g;
   g2.Cl = C; g2.wCl = C;
   return wgrad_reduce((const float*)ws, blocks, &g2, dw, s_l, s_s, s_tap, accumulate, s);

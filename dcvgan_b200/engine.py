@@ -208,8 +208,9 @@ class Block:
         cin_p, cout_p = x_used.cp, z.cp
         g = spec.geom(x.n, x.spatial, cin_p, cout_p)
         ctx = {"g": g, "x": x_used if save else None, "a": out, "cin_p": cin_p, "cout_p": cout_p}
-        if self.bn is None and self.act in (ACT_NONE, ACT_LEAKY) and ops.img_conv_ok(spec, g, x_used, out):
-            ops.img_conv_fwd(spec, g, x_used, w, out, self.act, self.slope)       # Inconv: direct HBM-bound kernel
+        if (self.bn is None and spec.kind == "conv" and self.act in (ACT_NONE, ACT_LEAKY) and ops.img_conv_ok(spec, g, ops.IMG_FWD, x_used, out)
+                and ops.img_conv_ok(spec, g, ops.IMG_BWD, x_used, out)):
+            ops.img_conv_fwd(spec, g, x_used, w, out, self.act, self.slope)       # Inconv: HBM-bound mma.sync kernel
             ctx["img"] = True
             return ctx
         impl = ops.choose_conv_impl(g, spec.fwd_dir, x_used)
@@ -295,15 +296,25 @@ class Block:
         # dz / dx_out are viewed with the same zero-padded widths the forward geometry was built with
         cin_p, cout_p = ctx["cin_p"], ctx["cout_p"]
         dzp = dz.padded_to(cout_p)
+        # Outconv (ConvTranspose2d(128, 3, 3, 1, 1), generator.py:272-277): its 3-channel side is the L tensor of the geometry -
+        # the weight gradient streams the 128-channel input once and the data gradient is a forward-type pass 3 -> 128
+        # channels, both through the image-side mma.sync kernels instead of 16-channel-padded tensor-core tiles
+        img = spec.kind == "convT" and self.bn is None
         if need_dw:
             dw, acc = sink.get(self.conv.weight)
             xp = ctx["x"].padded_to(cin_p)
             xl, xs = (xp, dzp) if spec.kind == "conv" else (dzp, xp)
-            ops.wgrad(spec, g, xl, xs, dw, accumulate=acc)
+            if img and ops.img_conv_ok(spec, g, ops.IMG_WGRAD, dz, ctx["x"]):
+                ops.img_conv_bwd(spec, g, ctx["x"], None, dz, self.conv.weight, ACT_NONE, 0.0, dw, acc, None)
+            else:
+                ops.wgrad(spec, g, xl, xs, dw, accumulate=acc)
         if dx_out is not None:
-            impl = ops.choose_conv_impl(g, spec.bwd_dir, dzp)
-            wp = packed_weight(spec, g, spec.bwd_dir, impl, self.conv.weight)
-            ops.conv(g, spec.bwd_dir, impl, dzp, wp, dx_out.padded_to(cin_p))
+            if img and ops.img_conv_ok(spec, g, ops.IMG_FWD, dz, dx_out):
+                ops.img_conv_fwd(spec, g, dz, self.conv.weight, dx_out, ACT_NONE, 0.0)
+            else:
+                impl = ops.choose_conv_impl(g, spec.bwd_dir, dzp)
+                wp = packed_weight(spec, g, spec.bwd_dir, impl, self.conv.weight)
+                ops.conv(g, spec.bwd_dir, impl, dzp, wp, dx_out.padded_to(cin_p))
         return dz
 
 

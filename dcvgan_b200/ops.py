@@ -385,15 +385,20 @@ def wgrad(spec, g, xl, xs, dw, accumulate=False, impl=None):
 IMG_CONV = os.environ.get("DCV_NO_IMG_CONV", "0") != "1"
 
 
-def img_conv_ok(spec, g, x, y):
-    """the Inconv layer (Conv2d(C<=2, 64, 3, 1, 1), generator.py:171-176) in bf16: direct HBM-bound kernels instead of a
-    tensor-core tile over 16 zero-padded channels"""
-    return (IMG_CONV and not _FORCE_SIMT and spec.kind == "conv" and x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
-            and y.ptr % 16 == 0 and y.ld % 8 == 0 and (spec.cin == 1 or (x.ptr % 4 == 0 and x.ld % 2 == 0))
-            and bool(lib().dcv_img_conv_supported(C.byref(g))))
+IMG_FWD, IMG_BWD, IMG_WGRAD = 0, 1, 2
+
+
+def img_conv_ok(spec, g, what, small, big):
+    """3x3 / stride 1 / pad 1 image-side layers whose small (L) side has <= 3 real channels (Inconv: generator.py:171-176,
+    Outconv: generator.py:272-277) in bf16: HBM-bound mma.sync kernels instead of tensor-core tiles over 16 zero-padded
+    channels.  what: IMG_FWD (L -> S pass), IMG_BWD (full Inconv backward), IMG_WGRAD (weight gradient only)."""
+    return (IMG_CONV and not _FORCE_SIMT and small.dtype == torch.bfloat16 and big.dtype == torch.bfloat16
+            and big.ptr % 16 == 0 and big.ld % 8 == 0 and spec.weight_strides()[2] == 1
+            and bool(lib().dcv_img_conv_supported(C.byref(g), what)))
 
 
 def img_conv_fwd(spec, g, x, weight, y, act, slope):
+    """y (the 64 / 128-channel S tensor) = act(correlate(x (the small L tensor), w))"""
     if TRACE is not None:
         TRACE.append(("img_conv_fwd", g.key(), 0, -1, x.ld, y.ld, x.c, y.c))
     s_l, s_s, s_tap = spec.weight_strides()
@@ -403,14 +408,16 @@ def img_conv_fwd(spec, g, x, weight, y, act, slope):
 
 
 def img_conv_bwd(spec, g, da, a, x, weight, act, slope, dw, accumulate, dx):
-    """dw (fp32, master layout, or None) and dx (Act or None) of the Inconv layer in one pass over (da, a)"""
+    """dw (fp32, master layout, or None) and dx (Act for the small L tensor, or None) in one pass over da (gradient w.r.t.
+    the activated S tensor) and a (the activated S tensor; None with ACT_NONE); x is the small L tensor"""
     if TRACE is not None:
-        TRACE.append(("img_conv_bwd", g.key(), 0, -1, da.ld, a.ld, da.c, x.c))
+        TRACE.append(("img_conv_bwd" if dx is not None else "img_conv_wgrad", g.key(), 0, -1, da.ld, x.ld, da.c, x.c))
     s_l, s_s, s_tap = spec.weight_strides()
     w = weight.detach()
     nbytes = lib().dcv_img_conv_bwd_workspace_bytes(C.byref(g))
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=w.device)
-    check(lib().dcv_img_conv_bwd(C.byref(g), da.ptr, da.ld, a.ptr, a.ld, x.ptr, x.ld, w.data_ptr(), s_l, s_s, s_tap, act, slope,
+    ap, lda = (da.ptr, da.ld) if a is None else (a.ptr, a.ld)
+    check(lib().dcv_img_conv_bwd(C.byref(g), da.ptr, da.ld, ap, lda, x.ptr, x.ld, w.data_ptr(), s_l, s_s, s_tap, act, slope,
                                  _p(dw), int(accumulate), None if dx is None else dx.ptr, 0 if dx is None else dx.ld,
                                  ws.data_ptr(), nbytes, _stream()))
 

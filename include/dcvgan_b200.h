@@ -209,14 +209,18 @@ int dcv_act_bwd(int dtype, const void* da, int64_t ldda, const void* a, int64_t 
  * and applies the activation.  2-D only (T == 1). */
 int dcv_col2im_act(int dtype, const void* P, int64_t ldp, int N, int Ih, int Iw, int Cout, int KH, int KW, int stride, int pad,
                    int act, float slope, void* y, int64_t ldy, int Oh, int Ow, void* stream);
-/* Direct HBM-bound kernels for the image-side 3x3 convolution of the colour generator (generator.py:158-176, `Inconv`:
- * Conv2d(C, 64, 3, 1, 1, bias=False) + LeakyReLU(0.01)) with C = 1 or 2 real input channels, bf16 activations, fp32 MASTER
- * weight addressed like dcv_pack_weight (no packed copy).  dcv_img_conv_supported: 1 if the geometry qualifies.
- * dcv_img_conv_fwd:  y = act(conv(x, w)).
- * dcv_img_conv_bwd:  one pass over da (gradient w.r.t. the activated output) and a (the activated output): applies the
- *   activation derivative (NONE / LEAKY), writes the weight gradient to dw (accumulate: +=; dw == NULL: skipped) and the
- *   data gradient to dx (NULL: skipped).  ws: dcv_img_conv_bwd_workspace_bytes(g) bytes of scratch. */
-int dcv_img_conv_supported(const dcv_geom* g);
+/* HBM-bound kernels (warp-level mma.sync, operands assembled in registers) for the 3x3 / stride 1 / pad 1 image-side layers
+ * of the colour generator whose small side has <= 3 real channels: `Inconv` Conv2d(C, 64, 3, 1, 1) + LeakyReLU(0.01)
+ * (generator.py:158-176) and `Outconv` ConvTranspose2d(128, 3, 3, 1, 1) (generator.py:256-282).  bf16 activations, fp32
+ * MASTER weight addressed like dcv_pack_weight (w[cl*s_l + cs*s_s + tap], no packed copy).  In dcv_geom terms the small
+ * tensor is L, the 64- or 128-channel tensor is S.
+ * dcv_img_conv_supported(g, what): what = 0 forward-type pass L -> S (Inconv forward, Outconv data gradient),
+ *   1 full Inconv backward (S has 64 channels, <= 2 real L channels), 2 weight gradient only.
+ * dcv_img_conv_fwd:  y(S) = act(correlate(x(L), w)).
+ * dcv_img_conv_bwd:  one pass over da (gradient w.r.t. the activated S tensor) and a (the activated S tensor; unused for
+ *   ACT_NONE): applies the activation derivative (NONE / LEAKY), writes the weight gradient to dw (accumulate: +=;
+ *   dw == NULL: skipped) and the data gradient w.r.t. x to dx (NULL: skipped).  ws: dcv_img_conv_bwd_workspace_bytes(g). */
+int dcv_img_conv_supported(const dcv_geom* g, int what);
 int64_t dcv_img_conv_bwd_workspace_bytes(const dcv_geom* g);
 int dcv_img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
                      void* y, int64_t ldy, int act, float slope, void* stream);

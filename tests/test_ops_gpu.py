@@ -232,7 +232,7 @@ def test_img_conv_direct_kernels(cin, n, hw, slice_out):
     else:
         ya = ops.Act.empty(n, 1, H, W, 64, torch.bfloat16)
     g = spec.geom(n, (1, H, W), xa.cp, ya.cp if not slice_out else 64)
-    assert ops.lib().dcv_img_conv_supported(C.byref(g))
+    assert ops.img_conv_ok(spec, g, ops.IMG_FWD, xa, ya) and ops.img_conv_ok(spec, g, ops.IMG_BWD, xa, ya)
     from dcvgan_b200._lib import ACT_LEAKY
     wdev = w.detach().cuda().contiguous()
     ops.img_conv_fwd(spec, g, xa, wdev, ya, ACT_LEAKY, 0.01)
@@ -262,6 +262,40 @@ def test_img_conv_direct_kernels(cin, n, hw, slice_out):
     e_own = max(rel_err(from_act(dxo), x.grad.unsqueeze(2)), rel_err(dwo.cpu(), w.grad))
     print(f"img_conv C={cin} n={n} {H}x{W}: fwd {e_fwd:.2e} dx {e_dx:.2e} dw {e_dw:.2e} dw2 {e_dw2:.2e}; with its own stored output {e_own:.2e}")
     assert e_fwd < 5e-3 and e_dx < 5e-3 and e_dw < 5e-3 and e_dw2 < 5e-3 and e_own < 6e-2
+
+
+@pytest.mark.parametrize("n,hw", [(2, (64, 64)), (3, (8, 32))])
+def test_img_conv_outconv_backward(n, hw):
+    """Outconv = ConvTranspose2d(128, 3, 3, 1, 1) (generator.py:272-277): its data gradient (3 -> 128 channels) and weight
+    gradient through the image-side mma.sync kernels against PyTorch fp32 on bf16-rounded operands; the data gradient is
+    written into a 128-channel buffer, the weight gradient also in accumulate mode."""
+    ops = _ops()
+    from dcvgan_b200._lib import ACT_NONE
+    torch.manual_seed(60 + n)
+    H, W = hw
+    spec = ops.ConvSpec("convT", 128, 3, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+    x = bf16_round(torch.randn(n, 128, H, W)).requires_grad_(True)
+    w = bf16_round(torch.randn(128, 3, 3, 3) * 0.1).requires_grad_(True)
+    y = F.conv_transpose2d(x, w, stride=1, padding=1)
+    dy = bf16_round(torch.randn_like(y))
+    y.backward(dy)
+    xa = to_act(x.detach(), torch.bfloat16)
+    dza = to_act(dy, torch.bfloat16)                     # 3 real channels in a 16-channel pitch
+    g = spec.geom(n, (1, H, W), xa.cp, dza.cp)
+    assert ops.img_conv_ok(spec, g, ops.IMG_FWD, dza, xa) and ops.img_conv_ok(spec, g, ops.IMG_WGRAD, dza, xa)
+    wdev = w.detach().cuda().contiguous()
+    dxa = ops.Act.empty(n, 1, H, W, 128, torch.bfloat16)
+    ops.img_conv_fwd(spec, g, dza, wdev, dxa, ACT_NONE, 0.0)
+    dw = torch.full_like(wdev, 2.0)
+    ops.img_conv_bwd(spec, g, xa, None, dza, wdev, ACT_NONE, 0.0, dw, False, None)
+    torch.cuda.synchronize()
+    e_dx = rel_err(from_act(dxa), x.grad.unsqueeze(2))
+    e_dw = rel_err(dw.cpu(), w.grad)
+    ops.img_conv_bwd(spec, g, xa, None, dza, wdev, ACT_NONE, 0.0, dw, True, None)
+    torch.cuda.synchronize()
+    e_dw2 = rel_err(dw.cpu(), 2 * w.grad)
+    print(f"outconv backward n={n} {H}x{W}: dx {e_dx:.2e} dw {e_dw:.2e} dw2 {e_dw2:.2e}")
+    assert e_dx < 5e-3 and e_dw < 5e-3 and e_dw2 < 5e-3
 
 
 def test_conv_channel_slices():

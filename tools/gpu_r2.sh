@@ -14,7 +14,7 @@ for st in $STAGES; do
     curves)
       DCV_CURVE_DUMP=gpurun_out/${TAG}_curves timeout 1500 python -m pytest tests/test_curves_gpu.py -m gpu -q -s > gpurun_out/${TAG}_curves.log 2>&1; echo "curves rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_curves.log | tail -30;;
     imgtest)
-      timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_nets_gpu.py tests/test_timed_path_gpu.py -m gpu -q -s -k "img_conv or full_width or generators_match or graph" > gpurun_out/${TAG}_imgtest.log 2>&1; echo "imgtest rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_imgtest.log | tail -25;;
+      timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_nets_gpu.py tests/test_timed_path_gpu.py -m gpu -q -s -k "img_conv or full_width or generators_match or graph or golden" > gpurun_out/${TAG}_imgtest.log 2>&1; echo "imgtest rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_imgtest.log | tail -25;;
     imglayers)
       timeout 600 python tools/layer_bench.py mug-depth 32 > gpurun_out/${TAG}_layers_img.md 2>&1; echo "imglayers rc=$?" | tee -a gpurun_out/${TAG}_rc.log; head -12 gpurun_out/${TAG}_layers_img.md;;
     bench)
