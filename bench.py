@@ -273,12 +273,15 @@ def layer_table(tr, cfg, B, reps=5):
             spec = ops.ConvSpec("conv", wl, ws, (g.kt, g.kh, g.kw), (g.st, g.sh, g.sw), (g.pt, g.ph, g.pw))
             dw = torch.empty((ws, wl, taps), device="cuda")
             fn = lambda: ops.wgrad(spec, g, L, S, dw, False, impl)
-        elif kind in ("img_conv_fwd", "img_conv_bwd", "img_conv_wgrad"):
+        elif kind in ("img_conv_fwd", "img_conv_bwd", "img_conv_wgrad", "img_conv_scatter"):
             spec = ops.ConvSpec("conv", wl, ws, (g.kt, g.kh, g.kw), (g.st, g.sh, g.sw), (g.pt, g.ph, g.pw))
             w = torch.randn((ws, wl, g.kh, g.kw), device="cuda") * 0.1
             xin = ops.Act.empty(g.N, 1, g.Hl, g.Wl, wl, dt)
             if kind == "img_conv_fwd":
                 fn = lambda: ops.img_conv_fwd(spec, g, xin, w, S, 1, 0.01)
+            elif kind == "img_conv_scatter":
+                yo = ops.Act.empty(g.N, 1, g.Hl, g.Wl, wl, dt)
+                fn = lambda: ops.img_conv_scatter(spec, g, S, w, yo, 2, 0.0)
             elif kind == "img_conv_wgrad":
                 dw = torch.empty_like(w)
                 fn = lambda: ops.img_conv_bwd(spec, g, S, None, xin, w, 0, 0.0, dw, False, None)

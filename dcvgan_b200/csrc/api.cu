@@ -42,6 +42,7 @@ int wgrad_reduce_multi(const float*, int, const dcv_geom*, int, float* const*, c
 int conv_tc_supported(const dcv_geom*, int);
 int set_tuning(const char*, int);
 int img_conv_supported_for(const dcv_geom*, int);
+int img_conv_scatter(const dcv_geom*, const void*, int64_t, const float*, int64_t, int64_t, int64_t, void*, int64_t, int, float, cudaStream_t);
 int64_t img_conv_bwd_ws_bytes(const dcv_geom*);
 int img_conv_fwd(const dcv_geom*, const void*, int64_t, const float*, int64_t, int64_t, int64_t, void*, int64_t, int, float, cudaStream_t);
 int img_conv_bwd(const dcv_geom*, const void*, int64_t, const void*, int64_t, const void*, int64_t, const float*, int64_t, int64_t,
@@ -88,6 +89,12 @@ int dcv_img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float*
   if (int rc = check_geom(g)) return rc;
   DCV_REQUIRE(x && w && y, "img_conv_fwd: null pointer");
   return img_conv_fwd(g, x, ldx, w, s_l, s_s, s_tap, y, ldy, act, slope, as_stream(stream));
+}
+int dcv_img_conv_scatter(const dcv_geom* g, const void* xb, int64_t ldb, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
+                         void* y, int64_t ldy, int act, float slope, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DCV_REQUIRE(xb && w && y, "img_conv_scatter: null pointer");
+  return img_conv_scatter(g, xb, ldb, w, s_l, s_s, s_tap, y, ldy, act, slope, as_stream(stream));
 }
 int dcv_img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x, int64_t ldx,
                      const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, int act, float slope, float* dw, int accumulate,

@@ -184,7 +184,9 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
   constexpr int NP = NJ * 8;                   // padded row length of P
   extern __shared__ __align__(16) uint8_t sm_raw[];
   float* Ps = reinterpret_cast<float*>(sm_raw);                                  // [(BAND+2) * W][NP]; later [8 warps][NP][64]
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(Ps + (size_t)(IMG_BAND + 2) * W * NP);
+  // region 0: the P tile (data gradient only) and, after the loop, the per-warp weight-gradient tiles; region 1: input window
+  const int tile_floats = DGRAD ? (IMG_BAND + 2) * W * NP : 0, red_floats = IMG_WARPS * NP * IMG_CO;
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(Ps + (tile_floats > red_floats ? tile_floats : red_floats));
   static_assert(NCO == 64 || !DGRAD, "the data gradient needs all channels of a pixel in one warp");
   constexpr int NH = NCO / 64, WPH = IMG_WARPS / NH;             // channel halves, warps per half
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, g = lane / 4, q = lane % 4;
@@ -341,10 +343,108 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
   }
 }
 
+// ------------------------------------------------------------------------------------------ scatter pass (Outconv forward)
+// y (the small L tensor, C real channels) = act( sum over taps of the partial products of the big S tensor ):
+//   P[pixel][tap, cl] = sum_cs S[pixel][cs] * w[cl][cs][tap]        one pass over S, A fragments straight from global loads
+//   y[h][w][cl]       = act( sum_taps P[h - ky + 1][w - kx + 1][tap][cl] )     col2im inside the block (band + halo rows)
+// This is the forward of `Outconv` = ConvTranspose2d(128, 3, 3, 1, 1) + Tanh (generator.py:272-277), which ran as a 1x1
+// tensor-core GEMM onto 27 (padded 32) columns plus a col2im pass over a 134 MB intermediate (0.204 ms at batch 32); here the
+// 537 MB input is read once and nothing but the 3-channel output is written.
+template <int C, int NCO>
+__global__ void __launch_bounds__(256, 2)
+img_conv3x3_scatter_kernel(const __nv_bfloat16* __restrict__ xb, int64_t ldb, const float* __restrict__ w, int64_t s_l, int64_t s_s,
+                           int N, int H, int W, int act, float slope, __nv_bfloat16* __restrict__ y, int64_t ldy) {
+  pdl_wait(); pdl_trigger();
+  constexpr int NT = 9 * C, NJ = (NT + 7) / 8, NP = NJ * 8, NH = NCO / 64;
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  float* Ps = reinterpret_cast<float*>(sm_raw);                                  // [(BAND+2) * W][NP]
+  uint32_t* bws = reinterpret_cast<uint32_t*>(Ps + (size_t)(IMG_BAND + 2) * W * NP);   // [NH][4][NJ][2][32] B fragments, one word per lane
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, g = lane / 4, q = lane % 4;
+  const int bands = H / IMG_BAND;
+#pragma unroll
+  for (int hf = 0; hf < NH; ++hf)
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if ((((hf * 4 + s) * NJ + j) * 2 + h) % IMG_WARPS != warp) continue;   // the fragments are spread over the warps
+          float v[2];
+          const int nn = 8 * j + g;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int co = 64 * hf + slot_channel(s, 2 * q + 8 * h + e);
+            v[e] = nn < NT ? w[co * s_s + (nn % C) * s_l + (nn / C)] : 0.f;
+          }
+          bws[((((hf * 4 + s) * NJ + j) * 2 + h) << 5) + lane] = pack_bf16x2(v[0], v[1]);
+        }
+  const int tiles_w = W / 16, tiles = (IMG_BAND + 2) * tiles_w;
+  for (int item = blockIdx.x; item < N * bands; item += gridDim.x) {
+    const int n = item / bands, r0 = (item % bands) * IMG_BAND;
+    __syncthreads();                               // B fragments written / the previous item's readers of Ps are done
+    for (int t = warp; t < tiles; t += IMG_WARPS) {
+      const int prow = t / tiles_w, w0 = (t % tiles_w) * 16;
+      const int h = r0 - 1 + prow;
+      const bool live = h >= 0 && h < H;           // warp-uniform
+      float pacc[NJ][4];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { pacc[j][0] = pacc[j][1] = pacc[j][2] = pacc[j][3] = 0.f; }
+      if (live) {
+#pragma unroll
+        for (int hf = 0; hf < NH; ++hf) {
+          uint32_t ar[4][4];                         // A fragments of the 64 channels of this half (see slot_channel)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int64_t pix = (int64_t)(n * H + h) * W + w0 + g + 8 * rr;
+            const uint4 d0 = *reinterpret_cast<const uint4*>(xb + pix * ldb + 64 * hf + 8 * q);
+            const uint4 d1 = *reinterpret_cast<const uint4*>(xb + pix * ldb + 64 * hf + 32 + 8 * q);
+            const uint32_t dw_[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+            for (int p = 0; p < 8; ++p) ar[p / 2][2 * (p % 2) + rr] = dw_[p];
+          }
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+              mma16816(pacc[j], ar[s][0], ar[s][1], ar[s][2], ar[s][3], bws[((((hf * 4 + s) * NJ + j) * 2 + 0) << 5) + lane],
+                       bws[((((hf * 4 + s) * NJ + j) * 2 + 1) << 5) + lane]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        *reinterpret_cast<float2*>(Ps + (size_t)(prow * W + w0 + g) * NP + 8 * j + 2 * q) = make_float2(pacc[j][0], pacc[j][1]);
+        *reinterpret_cast<float2*>(Ps + (size_t)(prow * W + w0 + g + 8) * NP + 8 * j + 2 * q) = make_float2(pacc[j][2], pacc[j][3]);
+      }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < IMG_BAND * W; p += blockDim.x) {
+      const int hb = p / W, wq = p % W;
+      float sacc[C];
+#pragma unroll
+      for (int ci = 0; ci < C; ++ci) sacc[ci] = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int pr = hb + 2 - ky, pc = wq + 1 - kx;          // P row (band row hb is P row hb + 1), column
+          if (pc < 0 || pc >= W) continue;
+          const float* qp = Ps + (size_t)(pr * W + pc) * NP + (ky * 3 + kx) * C;
+#pragma unroll
+          for (int ci = 0; ci < C; ++ci) sacc[ci] += qp[ci];
+        }
+      __nv_bfloat16* d = y + ((int64_t)(n * H + r0 + hb) * W + wq) * ldy;
+#pragma unroll
+      for (int ci = 0; ci < C; ++ci) d[ci] = __float2bfloat16_rn(apply_act(sacc[ci], act, slope));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 // what = 0: forward-type pass (small-channel L tensor -> S tensor with 64 or 128 channels; Inconv forward, Outconv data
 //           gradient), 1: full backward of Inconv (da, a -> dW, dx; S has 64 channels),
-//           2: weight gradient only (S has 64 or 128 channels; Outconv).  k3 / s1 / p1, 2-D, bf16.
+//           2: weight gradient only (S has 64 or 128 channels; Outconv), 3: scatter pass S -> L (Outconv forward).
+//           k3 / s1 / p1, 2-D, bf16.
 int img_conv_supported_for(const dcv_geom* g, int what) {
   const int wcl = g->wCl > 0 ? g->wCl : g->Cl, wcs = g->wCs > 0 ? g->wCs : g->Cs;
   if (g->kt != 1 || g->kh != 3 || g->kw != 3 || g->st != 1 || g->sh != 1 || g->sw != 1 || g->pt != 0 || g->ph != 1 || g->pw != 1) return 0;
@@ -403,6 +503,37 @@ static int launch_bwd(const dcv_geom* g, int blocks, int smem, const void* da, i
   launch_k(img_conv3x3_bwd_kernel<C, NCO, DGRAD>, blocks, 256, smem, s, (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda,
            (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx);
   return 0;
+}
+
+template <int C, int NCO>
+static int launch_scatter(const dcv_geom* g, int blocks, const void* xb, int64_t ldb, const float* w, int64_t s_l, int64_t s_s, int act,
+                          float slope, void* y, int64_t ldy, cudaStream_t s) {
+  const int np = (9 * C + 7) / 8 * 8, nj = np / 8;
+  const int smem = (IMG_BAND + 2) * g->Wl * np * (int)sizeof(float) + (NCO / 64) * 4 * nj * 2 * 32 * 4 + 16;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_scatter_kernel<C, NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  launch_k(img_conv3x3_scatter_kernel<C, NCO>, blocks, 256, smem, s, (const __nv_bfloat16*)xb, ldb, w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope,
+           (__nv_bfloat16*)y, ldy);
+  return 0;
+}
+
+int img_conv_scatter(const dcv_geom* g, const void* xb, int64_t ldb, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, void* y,
+                     int64_t ldy, int act, float slope, cudaStream_t s) {
+  DCV_REQUIRE(img_conv_supported_for(g, 3), "img_conv_scatter: geometry not supported");
+  DCV_REQUIRE(s_tap == 1, "img_conv_scatter: taps of the master weight must be contiguous");
+  DCV_REQUIRE((((uintptr_t)xb) & 15) == 0 && ldb % 8 == 0, "img_conv_scatter: input must be 16-byte aligned");
+  const int C = g->wCl > 0 ? g->wCl : g->Cl;
+  const int blocks = img_conv_bwd_blocks(g);
+  int rc = -1;
+#define DCV_IMG_SC(C_, N_) if (C == C_ && g->Cs == N_) rc = launch_scatter<C_, N_>(g, blocks, xb, ldb, w, s_l, s_s, act, slope, y, ldy, s);
+  DCV_IMG_SC(1, 64) DCV_IMG_SC(2, 64) DCV_IMG_SC(3, 64) DCV_IMG_SC(1, 128) DCV_IMG_SC(2, 128) DCV_IMG_SC(3, 128)
+#undef DCV_IMG_SC
+  DCV_REQUIRE(rc != -1, "img_conv_scatter: no kernel for C %d, %d channels", C, g->Cs);
+  if (rc) return rc;
+  return check_launch("img_conv3x3_scatter");
 }
 
 int img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x, int64_t ldx,

@@ -213,6 +213,9 @@ class Block:
             ops.img_conv_fwd(spec, g, x_used, w, out, self.act, self.slope)       # Inconv: HBM-bound mma.sync kernel
             ctx["img"] = True
             return ctx
+        if self.bn is None and spec.kind == "convT" and ops.img_conv_ok(spec, g, ops.IMG_SCATTER, out, x_used):
+            ops.img_conv_scatter(spec, g, x_used, w, out, self.act, self.slope)    # Outconv: one pass over the 128-channel input
+            return ctx
         impl = ops.choose_conv_impl(g, spec.fwd_dir, x_used)
         wp = packed_weight(spec, g, spec.fwd_dir, impl, w)
         if self.bn is None:

@@ -385,7 +385,7 @@ def wgrad(spec, g, xl, xs, dw, accumulate=False, impl=None):
 IMG_CONV = os.environ.get("DCV_NO_IMG_CONV", "0") != "1"
 
 
-IMG_FWD, IMG_BWD, IMG_WGRAD = 0, 1, 2
+IMG_FWD, IMG_BWD, IMG_WGRAD, IMG_SCATTER = 0, 1, 2, 3
 
 
 def img_conv_ok(spec, g, what, small, big):
@@ -405,6 +405,16 @@ def img_conv_fwd(spec, g, x, weight, y, act, slope):
     w = weight.detach()
     assert w.is_contiguous() and w.dtype == torch.float32
     check(lib().dcv_img_conv_fwd(C.byref(g), x.ptr, x.ld, w.data_ptr(), s_l, s_s, s_tap, y.ptr, y.ld, act, slope, _stream()))
+
+
+def img_conv_scatter(spec, g, xb, weight, y, act, slope):
+    """y (the small L tensor) = act(transposed correlation of xb (the 64 / 128-channel S tensor) with w): Outconv forward"""
+    if TRACE is not None:
+        TRACE.append(("img_conv_scatter", g.key(), 0, -1, xb.ld, y.ld, xb.c, y.c))
+    s_l, s_s, s_tap = spec.weight_strides()
+    w = weight.detach()
+    assert w.is_contiguous() and w.dtype == torch.float32
+    check(lib().dcv_img_conv_scatter(C.byref(g), xb.ptr, xb.ld, w.data_ptr(), s_l, s_s, s_tap, y.ptr, y.ld, act, slope, _stream()))
 
 
 def img_conv_bwd(spec, g, da, a, x, weight, act, slope, dw, accumulate, dx):

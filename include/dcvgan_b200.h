@@ -215,8 +215,11 @@ int dcv_col2im_act(int dtype, const void* P, int64_t ldp, int N, int Ih, int Iw,
  * MASTER weight addressed like dcv_pack_weight (w[cl*s_l + cs*s_s + tap], no packed copy).  In dcv_geom terms the small
  * tensor is L, the 64- or 128-channel tensor is S.
  * dcv_img_conv_supported(g, what): what = 0 forward-type pass L -> S (Inconv forward, Outconv data gradient),
- *   1 full Inconv backward (S has 64 channels, <= 2 real L channels), 2 weight gradient only.
+ *   1 full Inconv backward (S has 64 channels, <= 2 real L channels), 2 weight gradient only, 3 scatter pass S -> L
+ *   (Outconv forward).
  * dcv_img_conv_fwd:  y(S) = act(correlate(x(L), w)).
+ * dcv_img_conv_scatter: y(L) = act(transposed correlation of xb(S) with w) - the forward of a ConvTranspose2d whose OUTPUT is
+ *   the small tensor; the big tensor is read once, no intermediate.
  * dcv_img_conv_bwd:  one pass over da (gradient w.r.t. the activated S tensor) and a (the activated S tensor; unused for
  *   ACT_NONE): applies the activation derivative (NONE / LEAKY), writes the weight gradient to dw (accumulate: +=;
  *   dw == NULL: skipped) and the data gradient w.r.t. x to dx (NULL: skipped).  ws: dcv_img_conv_bwd_workspace_bytes(g). */
@@ -224,6 +227,8 @@ int dcv_img_conv_supported(const dcv_geom* g, int what);
 int64_t dcv_img_conv_bwd_workspace_bytes(const dcv_geom* g);
 int dcv_img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
                      void* y, int64_t ldy, int act, float slope, void* stream);
+int dcv_img_conv_scatter(const dcv_geom* g, const void* xb, int64_t ldb, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
+                         void* y, int64_t ldy, int act, float slope, void* stream);
 int dcv_img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x, int64_t ldx,
                      const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, int act, float slope, float* dw, int accumulate,
                      void* dx, int64_t lddx, void* ws, int64_t ws_bytes, void* stream);

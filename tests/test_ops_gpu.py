@@ -294,8 +294,15 @@ def test_img_conv_outconv_backward(n, hw):
     ops.img_conv_bwd(spec, g, xa, None, dza, wdev, ACT_NONE, 0.0, dw, True, None)
     torch.cuda.synchronize()
     e_dw2 = rel_err(dw.cpu(), 2 * w.grad)
-    print(f"outconv backward n={n} {H}x{W}: dx {e_dx:.2e} dw {e_dw:.2e} dw2 {e_dw2:.2e}")
-    assert e_dx < 5e-3 and e_dw < 5e-3 and e_dw2 < 5e-3
+    # forward: ConvTranspose2d + Tanh in one pass over the 128-channel input
+    from dcvgan_b200._lib import ACT_TANH
+    assert ops.img_conv_ok(spec, g, ops.IMG_SCATTER, dza, xa)
+    ya = ops.Act.empty(n, 1, H, W, 3, torch.bfloat16)
+    ops.img_conv_scatter(spec, g, xa, wdev, ya, ACT_TANH, 0.0)
+    e_fwd = rel_err(from_act(ya), torch.tanh(y.detach()).unsqueeze(2))
+    assert float(ya.padded_to(ya.cp).torch()[..., 3:].float().abs().max()) == 0.0
+    print(f"outconv n={n} {H}x{W}: fwd {e_fwd:.2e} dx {e_dx:.2e} dw {e_dw:.2e} dw2 {e_dw2:.2e}")
+    assert e_fwd < 5e-3 and e_dx < 5e-3 and e_dw < 5e-3 and e_dw2 < 5e-3
 
 
 def test_conv_channel_slices():
