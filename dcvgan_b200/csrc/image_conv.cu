@@ -79,10 +79,11 @@ __device__ __forceinline__ uint16_t im2col_at(const __nv_bfloat16* xs, int WP, i
 
 // ------------------------------------------------------------------------------------------ forward
 // C real input channels (1..3), NCO output channels (64 or 128, processed as halves of 64)
-template <int C, int NCO>
+template <int C, int NCO, int ACT>
 __global__ void __launch_bounds__(256, 2)
 img_conv3x3_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t s_l, int64_t s_s,
-                       int N, int H, int W, __nv_bfloat16* __restrict__ y, int64_t ldy, int act, float slope) {
+                       int N, int H, int W, __nv_bfloat16* __restrict__ y, int64_t ldy, float slope) {
+  auto actf = [&](float v) { return ACT == DCV_ACT_LEAKY ? (v > 0.f ? v : v * slope) : v; };
   pdl_wait(); pdl_trigger();
   constexpr int KS = (9 * C + 15) / 16;                        // k16 steps
   constexpr int NH = NCO / 64;                                 // halves of 64 output channels
@@ -144,8 +145,8 @@ img_conv3x3_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const f
         // activation, bf16, warp-private staging (conflict-free: bank = 4 * row + 4 * j + q), then 16-byte global stores
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          stg[warp][g][4 * j + q] = pack_bf16x2(apply_act(acc[j][0], act, slope), apply_act(acc[j][1], act, slope));
-          stg[warp][g + 8][4 * j + q] = pack_bf16x2(apply_act(acc[j][2], act, slope), apply_act(acc[j][3], act, slope));
+          stg[warp][g][4 * j + q] = pack_bf16x2(actf(acc[j][0]), actf(acc[j][1]));
+          stg[warp][g + 8][4 * j + q] = pack_bf16x2(actf(acc[j][2]), actf(acc[j][3]));
         }
         __syncwarp();
 #pragma unroll
@@ -181,7 +182,7 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
   pdl_wait(); pdl_trigger();
   constexpr int NT = 9 * C;                    // (tap, ci) pairs
   constexpr int NJ = (NT + 7) / 8;             // n8 tiles over them
-  constexpr int NP = NJ * 8;                   // padded row length of P
+  constexpr int NP = NJ * 8 + 8;               // row length of P: 8 floats of padding keep the float2 fragment stores conflict-free
   extern __shared__ __align__(16) uint8_t sm_raw[];
   float* Ps = reinterpret_cast<float*>(sm_raw);                                  // [(BAND+2) * W][NP]; later [8 warps][NP][64]
   // region 0: the P tile (data gradient only) and, after the loop, the per-warp weight-gradient tiles; region 1: input window
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(256, 2)
 img_conv3x3_scatter_kernel(const __nv_bfloat16* __restrict__ xb, int64_t ldb, const float* __restrict__ w, int64_t s_l, int64_t s_s,
                            int N, int H, int W, int act, float slope, __nv_bfloat16* __restrict__ y, int64_t ldy) {
   pdl_wait(); pdl_trigger();
-  constexpr int NT = 9 * C, NJ = (NT + 7) / 8, NP = NJ * 8, NH = NCO / 64;
+  constexpr int NT = 9 * C, NJ = (NT + 7) / 8, NP = NJ * 8 + 8, NH = NCO / 64;   // NP: P row with 8 floats of padding (conflict-free)
   extern __shared__ __align__(16) uint8_t sm_raw[];
   float* Ps = reinterpret_cast<float*>(sm_raw);                                  // [(BAND+2) * W][NP]
   uint32_t* bws = reinterpret_cast<uint32_t*>(Ps + (size_t)(IMG_BAND + 2) * W * NP);   // [NH][4][NJ][2][32] B fragments, one word per lane
@@ -383,38 +384,55 @@ img_conv3x3_scatter_kernel(const __nv_bfloat16* __restrict__ xb, int64_t ldb, co
   for (int item = blockIdx.x; item < N * bands; item += gridDim.x) {
     const int n = item / bands, r0 = (item % bands) * IMG_BAND;
     __syncthreads();                               // B fragments written / the previous item's readers of Ps are done
-    for (int t = warp; t < tiles; t += IMG_WARPS) {
-      const int prow = t / tiles_w, w0 = (t % tiles_w) * 16;
-      const int h = r0 - 1 + prow;
-      const bool live = h >= 0 && h < H;           // warp-uniform
-      float pacc[NJ][4];
+    // two tiles per warp and step: every B fragment read from shared memory feeds two MMAs
+    for (int t = warp; t < tiles; t += 2 * IMG_WARPS) {
+      int prow[2], w0[2]; bool live[2];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) { pacc[j][0] = pacc[j][1] = pacc[j][2] = pacc[j][3] = 0.f; }
-      if (live) {
+      for (int u = 0; u < 2; ++u) {
+        const int tt = t + u * IMG_WARPS;
+        prow[u] = tt / tiles_w; w0[u] = (tt % tiles_w) * 16;
+        const int h = r0 - 1 + prow[u];
+        live[u] = tt < tiles && h >= 0 && h < H;   // warp-uniform
+      }
+      float pacc[2][NJ][4];
 #pragma unroll
-        for (int hf = 0; hf < NH; ++hf) {
-          uint32_t ar[4][4];                         // A fragments of the 64 channels of this half (see slot_channel)
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { pacc[u][j][0] = pacc[u][j][1] = pacc[u][j][2] = pacc[u][j][3] = 0.f; }
+#pragma unroll
+      for (int hf = 0; hf < NH; ++hf) {
+        uint32_t ar[2][4][4];                      // A fragments of the 64 channels of this half (see slot_channel)
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
           for (int rr = 0; rr < 2; ++rr) {
-            const int64_t pix = (int64_t)(n * H + h) * W + w0 + g + 8 * rr;
-            const uint4 d0 = *reinterpret_cast<const uint4*>(xb + pix * ldb + 64 * hf + 8 * q);
-            const uint4 d1 = *reinterpret_cast<const uint4*>(xb + pix * ldb + 64 * hf + 32 + 8 * q);
+            uint4 d0 = make_uint4(0u, 0u, 0u, 0u), d1 = d0;
+            if (live[u]) {
+              const int64_t pix = (int64_t)(n * H + r0 - 1 + prow[u]) * W + w0[u] + g + 8 * rr;
+              d0 = *reinterpret_cast<const uint4*>(xb + pix * ldb + 64 * hf + 8 * q);
+              d1 = *reinterpret_cast<const uint4*>(xb + pix * ldb + 64 * hf + 32 + 8 * q);
+            }
             const uint32_t dw_[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-            for (int p = 0; p < 8; ++p) ar[p / 2][2 * (p % 2) + rr] = dw_[p];
+            for (int p = 0; p < 8; ++p) ar[u][p / 2][2 * (p % 2) + rr] = dw_[p];
           }
 #pragma unroll
-          for (int s = 0; s < 4; ++s)
+        for (int s = 0; s < 4; ++s)
 #pragma unroll
-            for (int j = 0; j < NJ; ++j)
-              mma16816(pacc[j], ar[s][0], ar[s][1], ar[s][2], ar[s][3], bws[((((hf * 4 + s) * NJ + j) * 2 + 0) << 5) + lane],
-                       bws[((((hf * 4 + s) * NJ + j) * 2 + 1) << 5) + lane]);
-        }
+          for (int j = 0; j < NJ; ++j) {
+            const uint32_t b0 = bws[((((hf * 4 + s) * NJ + j) * 2 + 0) << 5) + lane], b1 = bws[((((hf * 4 + s) * NJ + j) * 2 + 1) << 5) + lane];
+            mma16816(pacc[0][j], ar[0][s][0], ar[0][s][1], ar[0][s][2], ar[0][s][3], b0, b1);
+            mma16816(pacc[1][j], ar[1][s][0], ar[1][s][1], ar[1][s][2], ar[1][s][3], b0, b1);
+          }
       }
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        *reinterpret_cast<float2*>(Ps + (size_t)(prow * W + w0 + g) * NP + 8 * j + 2 * q) = make_float2(pacc[j][0], pacc[j][1]);
-        *reinterpret_cast<float2*>(Ps + (size_t)(prow * W + w0 + g + 8) * NP + 8 * j + 2 * q) = make_float2(pacc[j][2], pacc[j][3]);
+      for (int u = 0; u < 2; ++u) {
+        if (t + u * IMG_WARPS >= tiles) continue;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          *reinterpret_cast<float2*>(Ps + (size_t)(prow[u] * W + w0[u] + g) * NP + 8 * j + 2 * q) = make_float2(pacc[u][j][0], pacc[u][j][1]);
+          *reinterpret_cast<float2*>(Ps + (size_t)(prow[u] * W + w0[u] + g + 8) * NP + 8 * j + 2 * q) = make_float2(pacc[u][j][2], pacc[u][j][3]);
+        }
       }
     }
     __syncthreads();
@@ -457,7 +475,7 @@ int img_conv_supported_for(const dcv_geom* g, int what) {
 int img_conv_supported(const dcv_geom* g) { return img_conv_supported_for(g, 1); }
 
 static int bwd_smem_bytes(int C, int W, bool dgrad) {
-  const int np = (9 * C + 7) / 8 * 8;
+  const int np = (9 * C + 7) / 8 * 8 + 8;
   int tile = dgrad ? (IMG_BAND + 2) * W * np : 0, red = IMG_WARPS * np * IMG_CO;
   return (tile > red ? tile : red) * (int)sizeof(float) + (IMG_BAND + 2) * (W + 2) * C * 2 + 16;
 }
@@ -475,12 +493,16 @@ int64_t img_conv_bwd_ws_bytes(const dcv_geom* g) {
 template <int C, int NCO>
 static void launch_fwd(const dcv_geom* g, unsigned blocks, const void* x, int64_t ldx, const float* w, int64_t s_l, int64_t s_s, void* y,
                        int64_t ldy, int act, float slope, cudaStream_t s) {
-  launch_k(img_conv3x3_fwd_kernel<C, NCO>, blocks, 256, 0, s, (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, (__nv_bfloat16*)y, ldy, act, slope);
+  if (act == DCV_ACT_LEAKY)
+    launch_k(img_conv3x3_fwd_kernel<C, NCO, DCV_ACT_LEAKY>, blocks, 256, 0, s, (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, (__nv_bfloat16*)y, ldy, slope);
+  else
+    launch_k(img_conv3x3_fwd_kernel<C, NCO, DCV_ACT_NONE>, blocks, 256, 0, s, (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, (__nv_bfloat16*)y, ldy, slope);
 }
 
 int img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, void* y,
                  int64_t ldy, int act, float slope, cudaStream_t s) {
   DCV_REQUIRE(img_conv_supported_for(g, 0), "img_conv_fwd: geometry not supported");
+  DCV_REQUIRE(act == DCV_ACT_NONE || act == DCV_ACT_LEAKY, "img_conv_fwd: activation %d", act);
   DCV_REQUIRE(s_tap == 1, "img_conv_fwd: taps of the master weight must be contiguous");
   DCV_REQUIRE((((uintptr_t)y) & 15) == 0 && ldy % 8 == 0, "img_conv_fwd: output must be 16-byte aligned");
   const int C = g->wCl > 0 ? g->wCl : g->Cl;
@@ -508,7 +530,7 @@ static int launch_bwd(const dcv_geom* g, int blocks, int smem, const void* da, i
 template <int C, int NCO>
 static int launch_scatter(const dcv_geom* g, int blocks, const void* xb, int64_t ldb, const float* w, int64_t s_l, int64_t s_s, int act,
                           float slope, void* y, int64_t ldy, cudaStream_t s) {
-  const int np = (9 * C + 7) / 8 * 8, nj = np / 8;
+  const int nj = (9 * C + 7) / 8, np = nj * 8 + 8;
   const int smem = (IMG_BAND + 2) * g->Wl * np * (int)sizeof(float) + (NCO / 64) * 4 * nj * 2 * 32 * 4 + 16;
   static int smem_set = 0;
   if (smem > smem_set) {
