@@ -249,6 +249,48 @@ wgrad_reduce_flat_kernel(const float* __restrict__ partial, int splits, int taps
   }
 }
 
+// Transposing form of the flat reduction for master weights whose taps are contiguous (every Conv / ConvTranspose weight:
+// [cs][cl][tap] with tap innermost) - the partial sums are [split][tap][cl][cs] with cs innermost, so the flat kernel above,
+// one thread per element in partial order, writes 4-byte words Cl*taps floats apart (a 32-byte sector per word:
+// wgrad_reduce_flat was 0.49 ms per training iteration, mostly these scattered writes).  Here a block owns one cl and 32
+// consecutive cs: it reads the partials with the lanes along cs (128-byte segments), sums the splits in split order
+// (deterministic), transposes through shared memory and writes rows of `taps` contiguous floats.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_tr_kernel(const float* __restrict__ partial, int splits, int taps, int Cl, int Cs, WeightWin win,
+                       float* __restrict__ dw, int64_t s_l, int64_t s_s, int accumulate) {
+  pdl_wait(); pdl_trigger();
+  __shared__ float t[64][33];
+  const int cl = blockIdx.x % Cl, cs0 = (blockIdx.x / Cl) * 32;
+  if (cl < win.cl_off || cl >= win.cl_off + win.cl_cnt) return;          // zero-padding channel: no entry in the master weight
+  const int lane = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int cs = cs0 + lane;
+  const int64_t total = (int64_t)taps * Cl * Cs;
+  for (int tap = ty; tap < taps; tap += 8) {
+    float s = 0.f;
+    if (cs < Cs) {
+      const float* pp = partial + ((int64_t)tap * Cl + cl) * Cs + cs;
+      int z = 0;
+      for (; z + 8 <= splits; z += 8) {          // eight independent loads in flight, added in split order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = pp[(int64_t)(z + u) * total];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+      }
+      for (; z < splits; ++z) s += pp[(int64_t)z * total];
+    }
+    t[tap][lane] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * taps; i += 256) {
+    const int r = i / taps, tp = i % taps;
+    const int c = cs0 + r;
+    if (c >= Cs || c < win.cs_off || c >= win.cs_off + win.cs_cnt) continue;
+    float* d = dw + (int64_t)(cl - win.cl_off) * s_l + (int64_t)(c - win.cs_off) * s_s + tp;
+    *d = accumulate ? (*d + t[tp][r]) : t[tp][r];
+  }
+}
+
 // several master weights that each own a window of the partial matrix (merged / folded stems): every element is summed
 // once over the splits and routed to the weight whose window contains it (8 separate reductions re-read the partials 8x)
 constexpr int REDUCE_MULTI_MAX = 16;
@@ -373,6 +415,10 @@ int wgrad_reduce_win(const float* partial, int splits, const dcv_geom* g, Weight
                      int64_t s_s, int64_t s_tap, int accumulate, cudaStream_t s) {
   const int taps = g->kt * g->kh * g->kw;
   const int64_t total = (int64_t)taps * g->Cl * g->Cs;
+  if (s_tap == 1 && taps <= 64 && total >= 16384) {      // tap-contiguous master weight: transposing reduction, coalesced both ways
+    launch_k(wgrad_reduce_tr_kernel, g->Cl * ceil_div(g->Cs, 32), 256, 0, s, partial, splits, taps, g->Cl, g->Cs, win, dw, s_l, s_s, accumulate);
+    return check_launch("wgrad_reduce");
+  }
   if (splits <= 16 || total >= 16384) {      // enough elements to fill the machine with one thread per element
     int fb = (int)((total + 255) / 256); if (fb > 148 * 16) fb = 148 * 16;
     launch_k(wgrad_reduce_flat_kernel, fb, 256, 0, s, partial, splits, taps, g->Cl, g->Cs, win, dw, s_l, s_s, s_tap, accumulate);
