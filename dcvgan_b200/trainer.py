@@ -46,7 +46,7 @@ class MetricType(enum.IntEnum):
 class _FlatNet:
     """Flat fp32 storage for one network's parameters, gradients and Adam moments."""
 
-    def __init__(self, model, opt):
+    def __init__(self, model, opt, grad_storage=None):
         self.model, self.opt = model, opt
         self.params = [p for p in model.parameters()]
         n = sum(p.numel() for p in self.params)
@@ -57,7 +57,9 @@ class _FlatNet:
             total += (p.numel() + 3) // 4 * 4
         dev = self.params[0].device
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        # grad_storage: a slice of a buffer shared by the networks of one phase, so that the phase needs ONE all-reduce
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev) if grad_storage is None else grad_storage
+        assert self.flat_g.numel() == total
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad_of = {}
@@ -83,6 +85,10 @@ class _FlatNet:
         step0 = int(float(opt.state[self.params[0]]["step"]))
         self.step_state = torch.zeros(2, dtype=torch.int64, device=dev)
         self.step_state[0] = step0
+
+    @staticmethod
+    def padded_numel(model):
+        return sum((p.numel() + 3) // 4 * 4 for p in model.parameters())
 
     def still_bound(self):
         """False when a parameter no longer aliases its slice of flat_p (model.to('cpu').to(device), load_state_dict with
@@ -310,7 +316,17 @@ class Trainer(object):
         names = ["ggen", "cgen", "idis", "vdis"] + (["gdis"] if self.use_gdis else [])
         for n in names:
             self.models[n].to(self.device)
-        self._flat = {n: _FlatNet(self.models[n], self.optimizers[n]) for n in names}
+        # gradient buffers of the networks that update together share one allocation (D: idis|vdis[|gdis], G: cgen|ggen):
+        # data-parallel runs can then reduce a phase with a single collective (DCV_DP_OVERLAP=2)
+        self._flat, self._phase_grads = {}, {}
+        for phase, members in (("d", names[2:]), ("g", ["cgen", "ggen"])):
+            sizes = [_FlatNet.padded_numel(self.models[n]) for n in members]
+            buf = torch.zeros(sum(sizes), dtype=torch.float32, device=self.device)
+            self._phase_grads[phase] = buf
+            o = 0
+            for n, k in zip(members, sizes):
+                self._flat[n] = _FlatNet(self.models[n], self.optimizers[n], buf[o:o + k])
+                o += k
         self._plans = {"ggen": engine.GGenPlan(self.models["ggen"]), "cgen": engine.CGenPlan(self.models["cgen"])}
         for n in names[2:]:
             self._plans[n] = engine.DisPlan(self.models[n], n)
@@ -343,31 +359,38 @@ class Trainer(object):
     def _allreduce(self, names):
         dp_allreduce_grads([self._flat[n] for n in names])
 
+    def _dp_mode(self):
+        """DCV_DP_OVERLAP: 0 = one in-stream all-reduce per network right after its backward (default; measured equal or
+        faster than the alternatives on 2 and 8 B200s, profiles/r2k_*, r2l_*), 1 = side-stream all-reduce per network while the
+        persistent kernels leave DCV_DP_SM_RESERVE SMs free, 2 = ONE in-stream all-reduce per phase over the shared
+        gradient buffer (fewer, larger collectives)."""
+        return os.environ.get("DCV_DP_OVERLAP", "0")
+
     def _reduce_launch(self, name):
-        """enqueue the all-reduce of one network's gradient bucket behind the kernels issued so far.
+        """enqueue the all-reduce of one network's gradient bucket behind the kernels issued so far"""
+        if self.world <= 1:
+            return
+        mode = self._dp_mode()
+        if mode == "1":
+            # side stream + reserved SMs: with one ~220 KB CTA per SM on all 148 SMs NCCL's CTAs only get an SM between two
+            # kernels, so the persistent kernels launched until the matching wait use 148 - DCV_DP_SM_RESERVE CTAs
+            self._reducer.launch(self._flat[name])
+            k = int(os.environ.get("DCV_DP_SM_RESERVE", "8"))
+            if k > 0 and not self._sm_reserved:
+                _lib.check(_lib.lib().dcv_set_tuning(b"sm_reserve", k))
+                self._sm_reserved = True
+        elif mode == "0":
+            self._allreduce([name])
 
-        Default (DCV_DP_OVERLAP unset or 1): the bucket is reduced on a communication stream while the compute stream goes
-        on with the next network's backward, and - this is what makes the overlap real - the persistent convolution and
-        weight-gradient kernels launched until the matching wait leave `DCV_DP_SM_RESERVE` SMs (default 8) free: with
-        one ~220 KB CTA per SM on all 148 SMs NCCL's CTAs only got an SM between two kernels and the side stream
-        measured SLOWER than reducing in-stream (round 1: 12.03 vs 11.92 ms on 8 GPUs, profiles/r1m_bench_8gpu_*.json).
-        DCV_DP_OVERLAP=0 selects the in-stream form."""
-        if self.world > 1:
-            if os.environ.get("DCV_DP_OVERLAP", "1") == "1":
-                self._reducer.launch(self._flat[name])
-                k = int(os.environ.get("DCV_DP_SM_RESERVE", "8"))
-                if k > 0 and not self._sm_reserved:
-                    _lib.check(_lib.lib().dcv_set_tuning(b"sm_reserve", k))
-                    self._sm_reserved = True
-            else:
-                self._allreduce([name])
-
-    def _reduce_wait(self):
-        if self.world > 1:
-            self._reducer.wait()
-            if self._sm_reserved:
-                _lib.check(_lib.lib().dcv_set_tuning(b"sm_reserve", 0))
-                self._sm_reserved = False
+    def _reduce_wait(self, phase=None):
+        if self.world <= 1:
+            return
+        if self._dp_mode() == "2" and phase is not None:
+            dist.all_reduce(self._phase_grads[phase], op=dist.ReduceOp.SUM)
+        self._reducer.wait()
+        if self._sm_reserved:
+            _lib.check(_lib.lib().dcv_set_tuning(b"sm_reserve", 0))
+            self._sm_reserved = False
 
     def _to_clip(self, x, channels=None):
         """Real batch -> channels-last Act (B,T,H,W,C).  Accepted forms:
@@ -598,7 +621,7 @@ class Trainer(object):
         # reference's order (opt_*dis.step() consume no random numbers and do not touch the generators).
         xg_f, xc_f, gctx, cctx = self._generate(B, True, True, save=upd_g)
         if upd_d:
-            self._reduce_wait()
+            self._reduce_wait("d")
             for n in self._dnames:
                 self._flat[n].adam_step(1.0 / self.world)
         xg_clip, xc_clip = xg_f.reshape_nt(B, T), xc_f.reshape_nt(B, T)
@@ -628,7 +651,7 @@ class Trainer(object):
             sink_g = engine.GradSink(self._flat["ggen"].grad_of)
             self._plans["ggen"].backward(gctx, dxg.reshape_nt(B * T, 1), sink_g)
             self._reduce_launch("ggen")
-            self._reduce_wait()
+            self._reduce_wait("g")
             self._flat["ggen"].adam_step(1.0 / self.world)
             self._flat["cgen"].adam_step(1.0 / self.world)
             self._flat["ggen"].adam_step(1.0 / self.world)                                      # trainer.py:357-359

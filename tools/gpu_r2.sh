@@ -23,8 +23,13 @@ for st in $STAGES; do
     dp)
       # data-parallel A/B on the GPUs of this box: side-stream overlap with reserved SMs (default) against in-stream reduction
       NG=${NG:-2}
-      for mode in 1 0; do
+      for mode in ${MODES:-0 1 2}; do
         DCV_DP_OVERLAP=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --steps 20 --warmup 5 --no-roofline > gpurun_out/${TAG}_bench_${NG}gpu_overlap${mode}.json 2> gpurun_out/${TAG}_bench_${NG}gpu_overlap${mode}.err; echo "dp $NG overlap=$mode rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 400 gpurun_out/${TAG}_bench_${NG}gpu_overlap${mode}.json
+      done;;
+    dpconfigs)
+      NG=${NG:-8}
+      for c in surreal-depth1 isogd-flow surreal-segm; do
+        timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NG --steps 20 --warmup 5 --no-roofline --config $c > gpurun_out/${TAG}_bench_${NG}gpu_${c}.json 2> gpurun_out/${TAG}_bench_${NG}gpu_${c}.err; echo "dp $NG $c rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 300 gpurun_out/${TAG}_bench_${NG}gpu_${c}.json
       done;;
     bench)
       timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
