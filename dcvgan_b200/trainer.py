@@ -360,11 +360,12 @@ class Trainer(object):
         dp_allreduce_grads([self._flat[n] for n in names])
 
     def _dp_mode(self):
-        """DCV_DP_OVERLAP: 0 = one in-stream all-reduce per network right after its backward (default; measured equal or
-        faster than the alternatives on 2 and 8 B200s, profiles/r2k_*, r2l_*), 1 = side-stream all-reduce per network while the
-        persistent kernels leave DCV_DP_SM_RESERVE SMs free, 2 = ONE in-stream all-reduce per phase over the shared
-        gradient buffer (fewer, larger collectives)."""
-        return os.environ.get("DCV_DP_OVERLAP", "0")
+        """DCV_DP_OVERLAP: 2 (default) = ONE in-stream all-reduce per phase over the shared gradient buffer (idis|vdis[|gdis],
+        cgen|ggen: two collectives per iteration), 0 = one in-stream all-reduce per network right after its backward,
+        1 = side-stream all-reduce per network while the persistent kernels leave DCV_DP_SM_RESERVE SMs free.
+        Measured on 8 B200s, mug-depth (profiles/r2l_bench_8gpu_overlap*.json): 10.78 / 10.89 / 10.83 ms per iteration for
+        modes 2 / 0 / 1 (1 GPU: 10.37 ms); on 2 GPUs modes 0 / 1: 10.73 / 10.77 ms."""
+        return os.environ.get("DCV_DP_OVERLAP", "2")
 
     def _reduce_launch(self, name):
         """enqueue the all-reduce of one network's gradient bucket behind the kernels issued so far"""

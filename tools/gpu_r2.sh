@@ -31,6 +31,10 @@ for st in $STAGES; do
       for c in surreal-depth1 isogd-flow surreal-segm; do
         timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NG --steps 20 --warmup 5 --no-roofline --config $c > gpurun_out/${TAG}_bench_${NG}gpu_${c}.json 2> gpurun_out/${TAG}_bench_${NG}gpu_${c}.err; echo "dp $NG $c rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 300 gpurun_out/${TAG}_bench_${NG}gpu_${c}.json
       done;;
+    ncutop)
+      # one `ncu --set full` capture per dominant launch (B200_PROFILING.md recipe), after the plain run exited 0
+      python tools/probe_layers.py vdis_main1_dgrad up5_fwd vdis_main1_fwd vdis_main1_wgrad down0_wgrad > gpurun_out/${TAG}_probe_layers.log 2>&1 && \
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_pers|wgrad_tc" -c 10 -o gpurun_out/${TAG}_top python tools/probe_layers.py vdis_main1_dgrad up5_fwd vdis_main1_fwd vdis_main1_wgrad down0_wgrad > gpurun_out/${TAG}_ncutop.log 2>&1; echo "ncutop rc=$?" | tee -a gpurun_out/${TAG}_rc.log; cat gpurun_out/${TAG}_probe_layers.log;;
     bench)
       timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
     benchfast)
