@@ -13,10 +13,16 @@ _PRECISION = "bf16"
 
 
 def set_precision(p):
-    """'bf16' (tcgen05 fast path) or 'fp32' (exact CUDA-core path used for the 1e-3 parity gates)."""
+    """Precision of modules built from now on (and, for the fp32 storage modes, of every convolution launched from now on):
+    'bf16' - bf16 activations, tcgen05 kind::f16, fp32 accumulation / statistics / master weights (fast path);
+    'tf32' - fp32 activations; forward and data gradient of every convolution whose channel counts are multiples of 32 run
+             on tcgen05 kind::tf32 (fp32 accumulation), the rest and the weight gradients on the CUDA-core kernels;
+    'fp32' - fp32 activations, CUDA-core kernels only (exact mode)."""
     global _PRECISION
-    assert p in ("bf16", "fp32")
+    assert p in ("bf16", "tf32", "fp32")
     _PRECISION = p
+    from . import ops
+    ops.TF32_TC = p == "tf32"
 
 
 def get_precision():

@@ -15,7 +15,7 @@ if os.environ.get("DCV_EXPERIMENTS_LIB", "0") == "1":      # tools/exp_*.py only
 
 DCV_F32, DCV_BF16 = 0, 1
 ACT_NONE, ACT_LEAKY, ACT_TANH = 0, 1, 2
-IMPL_SIMT, IMPL_TC = 0, 1
+IMPL_SIMT, IMPL_TC, IMPL_TC_TF32 = 0, 1, 2
 DIR_GATHER, DIR_SCATTER = 0, 1
 LOSS_BCE_ONES, LOSS_BCE_ZEROS, LOSS_HINGE_REAL, LOSS_HINGE_FAKE, LOSS_SOFTPLUS_NEG = range(5)
 
@@ -57,6 +57,7 @@ SIGNATURES = {
     "dcv_pack_weight_multi": (_i, [_G, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dcv_pack_weight_sub": (_i, [_G, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp]),
     "dcv_conv_tc_supported": (_i, [_G, _i]),
+    "dcv_conv_tf32_supported": (_i, [_G, _i]),
     "dcv_conv": (_i, [_G, _i, _i, _i, _vp, _i64, _vp, _vp, _i64, _i, _f, _vp]),
     "dcv_conv_stats_slots": (_i, [_G, _i, _i64, _i64]),
     "dcv_conv_stats": (_i, [_G, _i, _vp, _i64, _vp, _vp, _i64, _i, _f, _vp, _i, _vp]),

@@ -51,9 +51,10 @@ int pack_weight_tc_multi(const dcv_geom*, int, int, const float* const*, const i
                          const int*, const int*, const int*, void*, cudaStream_t);
 int pack_weight_tc_batch(int, const dcv_geom* const*, const int*, const float* const*, const int64_t*, const int64_t*, const int64_t*,
                          void* const*, cudaStream_t);
-int64_t packed_weight_tc_bytes(const dcv_geom*, int);
-int pack_weight_tc(const dcv_geom*, int, const float*, int64_t, int64_t, int64_t, WeightWin, void*, cudaStream_t);
-int conv_tc(const dcv_geom*, int, const void*, int64_t, const void*, void*, int64_t, int, float, float*, int*, cudaStream_t);
+int64_t packed_weight_tc_bytes(const dcv_geom*, int, int);
+int conv_tf32_supported(const dcv_geom*, int);
+int pack_weight_tc(const dcv_geom*, int, const float*, int64_t, int64_t, int64_t, WeightWin, void*, cudaStream_t, int);
+int conv_tc(const dcv_geom*, int, const void*, int64_t, const void*, void*, int64_t, int, float, float*, int*, cudaStream_t, int);
 int wgrad_tc_supported(const dcv_geom*);
 int64_t wgrad_tc_ws_bytes(const dcv_geom*);
 int wgrad_tc(const dcv_geom*, const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int64_t, int, void*,
@@ -82,6 +83,7 @@ const char* dcv_last_error(void) { return g_err; }
 
 long long dcv_launch_count(void) { return g_launches; }
 
+int dcv_conv_tf32_supported(const dcv_geom* g, int dir) { return g && check_geom(g) == 0 ? conv_tf32_supported(g, dir) : 0; }
 int dcv_img_conv_supported(const dcv_geom* g, int what) { return g && check_geom(g) == 0 ? img_conv_supported_for(g, what) : 0; }
 int64_t dcv_img_conv_bwd_workspace_bytes(const dcv_geom* g) { return g ? img_conv_bwd_ws_bytes(g) : -1; }
 int dcv_img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap,
@@ -118,7 +120,7 @@ int dcv_device_ok(void) {
 
 int64_t dcv_packed_weight_bytes(const dcv_geom* g, int dir, int impl) {
   if (check_geom(g)) return -1;
-  if (impl == DCV_IMPL_TC) return packed_weight_tc_bytes(g, dir);
+  if (impl == DCV_IMPL_TC || impl == DCV_IMPL_TC_TF32) return packed_weight_tc_bytes(g, dir, impl == DCV_IMPL_TC_TF32);
   return (int64_t)g->kt * g->kh * g->kw * g->Cl * g->Cs * sizeof(float);
 }
 
@@ -126,7 +128,8 @@ int dcv_pack_weight(const dcv_geom* g, int dir, int impl, const float* w, int64_
                     void* out, void* stream) {
   if (int rc = check_geom(g)) return rc;
   DCV_REQUIRE(w && out, "pack_weight: null pointer");
-  if (impl == DCV_IMPL_TC) return pack_weight_tc(g, dir, w, s_l, s_s, s_tap, full_window(g), out, as_stream(stream));
+  if (impl == DCV_IMPL_TC || impl == DCV_IMPL_TC_TF32)
+    return pack_weight_tc(g, dir, w, s_l, s_s, s_tap, full_window(g), out, as_stream(stream), impl == DCV_IMPL_TC_TF32);
   return pack_weight_simt(g, dir, w, s_l, s_s, s_tap, full_window(g), (float*)out, as_stream(stream));
 }
 
@@ -142,7 +145,7 @@ int dcv_pack_weight_sub(const dcv_geom* g, int dir, int impl, const float* w, in
   if (int rc = check_window(g, cl_off, cl_cnt, cs_off, cs_cnt)) return rc;
   DCV_REQUIRE(w && out, "pack_weight_sub: null pointer");
   WeightWin win; win.cl_off = cl_off; win.cl_cnt = cl_cnt; win.cs_off = cs_off; win.cs_cnt = cs_cnt; win.fill = fill_outside;
-  if (impl == DCV_IMPL_TC) return pack_weight_tc(g, dir, w, s_l, s_s, s_tap, win, out, as_stream(stream));
+  if (impl == DCV_IMPL_TC) return pack_weight_tc(g, dir, w, s_l, s_s, s_tap, win, out, as_stream(stream), 0);
   return pack_weight_simt(g, dir, w, s_l, s_s, s_tap, win, (float*)out, as_stream(stream));
 }
 
@@ -180,8 +183,12 @@ int dcv_conv(const dcv_geom* g, int dir, int impl, int dtype, const void* x, int
   DCV_REQUIRE(dtype == DCV_F32 || dtype == DCV_BF16, "conv: bad dtype %d", dtype);
   if (g->N == 0) return 0;
   if (impl == DCV_IMPL_TC) {
-    DCV_REQUIRE(dtype == DCV_BF16, "conv: the tcgen05 kernel computes in bf16");
-    return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, nullptr, nullptr, as_stream(stream));
+    DCV_REQUIRE(dtype == DCV_BF16, "conv: DCV_IMPL_TC computes in bf16 (DCV_IMPL_TC_TF32 takes fp32 tensors)");
+    return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, nullptr, nullptr, as_stream(stream), 0);
+  }
+  if (impl == DCV_IMPL_TC_TF32) {
+    DCV_REQUIRE(dtype == DCV_F32, "conv: DCV_IMPL_TC_TF32 takes fp32 tensors");
+    return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, nullptr, nullptr, as_stream(stream), 1);
   }
   return conv_simt(g, dir, dtype, x, ldx, wp, y, ldy, act, slope, as_stream(stream));
 }
@@ -191,7 +198,7 @@ int dcv_conv_stats_slots(const dcv_geom* g, int dir, int64_t ldx, int64_t ldy) {
   if (g->N == 0 || !conv_tc_supported(g, dir)) return 0;
   int slots = 0;
   // planning query: aligned dummy pointers, nothing is dereferenced or launched
-  if (conv_tc(g, dir, (const void*)16, ldx, nullptr, (void*)16, ldy, 0, 0.f, nullptr, &slots, nullptr)) return -1;
+  if (conv_tc(g, dir, (const void*)16, ldx, nullptr, (void*)16, ldy, 0, 0.f, nullptr, &slots, nullptr, 0)) return -1;
   return slots;
 }
 
@@ -203,7 +210,7 @@ int dcv_conv_stats(const dcv_geom* g, int dir, const void* x, int64_t ldx, const
   DCV_REQUIRE(((uintptr_t)y & 15) == 0, "conv_stats: output must be 16-byte aligned");
   const int want = dcv_conv_stats_slots(g, dir, ldx, ldy);
   DCV_REQUIRE(want > 0 && want == slots, "conv_stats: this geometry writes %d statistic slots, caller provided %d", want, slots);
-  return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, stats, nullptr, as_stream(stream));
+  return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, stats, nullptr, as_stream(stream), 0);
 }
 
 int64_t dcv_wgrad_workspace_bytes(const dcv_geom* g, int impl) {

@@ -156,6 +156,26 @@ __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t alo, uint32_
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "}" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with kind::tf32 (fp32 operands in shared memory, 10-bit mantissa products, fp32 accumulate; K = 8 per instruction = the
+// same 32 bytes per K step, so descriptors and step arithmetic are shared with the bf16 path)
+__device__ __forceinline__ void umma_lohi_tf32(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  if (TF32) umma_lohi_tf32(tmem_d, alo, ahi, blo, bhi, idesc, accumulate);
+  else umma_lohi(tmem_d, alo, ahi, blo, bhi, idesc, accumulate);
+}
 // one pipeline stage of conv_tc: KS K-steps of 16 channels (32 bytes = +2 in descriptor units) for MT stacked M tiles
 template <int KS>
 __device__ __forceinline__ void conv_issue_stage(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
@@ -207,9 +227,10 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
   d |= (uint64_t)layout << 61;
   return d;
 }
-// instruction descriptor for kind::f16, bf16 x bf16 -> f32
-__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// instruction descriptor: D format f32 (bit 4), A / B format bf16 = 1 (kind::f16) or tf32 = 2 (kind::tf32) at bits 7 / 10
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int tf32 = 0) {
+  const uint32_t fmt = tf32 ? 2u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -348,7 +369,8 @@ __device__ __forceinline__ int live_stages(const TcConvP& p, const PhaseInfo& f,
 
 // KS = K steps of 16 channels per stage (cblk / 16), MT = 128-row M tiles per work item
 // HG = taps of one h class that share a single A box with HG-1 halo rows (1 = every tap loads its own box)
-template <int KS, int MT, int HG>
+// TF32: fp32 activations and weights, kind::tf32 MMAs, fp32 output through the TMA-store epilogue (32-channel chunks)
+template <int KS, int MT, int HG, bool TF32 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ CUtensorMap mapY, const TcConvP p, __nv_bfloat16* __restrict__ y) {
@@ -485,7 +507,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // not wait / issue / commit has to stay out of it (profiles/r1h_mma_probe.md: ~250 cycles of control per stage
     // already cost 30 % at 4 MMAs per stage).
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc(128, p.bnt, 0, 0);
+    const uint32_t idesc = make_idesc(128, p.bnt, 0, 0, TF32 ? 1 : 0);
     const uint32_t dhi = sdesc_hi(8u * (uint32_t)((KS ? KS : 1) * 16) * 2u, (uint32_t)p.swz_layout);
     const uint32_t a_tile16 = HG > 1 ? (uint32_t)p.a_tile16 : ((128u * (uint32_t)((KS ? KS : 1) * 16) * 2u) >> 4);
     const uint32_t row16 = ((uint32_t)p.bw * (uint32_t)((KS ? KS : 1) * 16) * 2u) >> 4;   // one tile row (bw pixels) in 16-byte units
@@ -550,7 +572,7 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             for (int k = 0; k < KS; ++k) {
 #pragma unroll
               for (int m = 0; m < MT; ++m)
-                umma_lohi(d_base + m * bnt, ai + m * a_tile16 + 2 * k, dhi, bi + 2 * k, dhi, idesc, (i == 0 && k == 0) ? accum : 1u);
+                umma_issue<TF32>(d_base + m * bnt, ai + m * a_tile16 + 2 * k, dhi, bi + 2 * k, dhi, idesc, (i == 0 && k == 0) ? accum : 1u);
             }
           }
           umma_commit(&empty_bar[stage]);
@@ -620,7 +642,38 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       mbar_wait(&tfull_bar[acc], acc ? tfull_phase1 : tfull_phase0);
       tc_fence_after();
       const uint32_t d_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.acc_cols);
-      if (p.tma_store == 2) {
+      if constexpr (TF32) {
+        // fp32 output: 32-channel chunks = 128-byte rows (128B swizzle), same per-warp staging + TMA store as the bf16 path
+        const uint32_t swz_row = (uint32_t)lane * 128u, swz_x = (uint32_t)(lane & 7);
+        const uint32_t wbuf = stg_base + (uint32_t)quarter * 8192u;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          for (int cb = 0; cb < p.bnt; cb += 32) {
+            const uint32_t buf = wbuf + (uint32_t)(nstore & 1) * 4096u;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            uint32_t v[32];
+            tmem_ld32_nowait(d_base + (uint32_t)(m * p.bnt + cb), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              uint32_t o[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o[i] = __float_as_uint(apply_act(__uint_as_float(v[4 * c + i]), p.act, p.slope));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + swz_row + (((uint32_t)c ^ swz_x) << 4)),
+                           "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_5d(&mapY, buf, nbase + cb, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
+                           (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
+              tma_store_commit();
+            }
+            ++nstore;
+          }
+        }
+      } else if (p.tma_store == 2) {
         // narrow outputs (bnt = 16 or 32 channels: image-like tensors, tap-unrolled partial products): same staging + TMA
         // store with 32- / 64-byte rows (32B / 64B swizzle), one TMEM load per row chunk
         const int cw = p.bnt;                                   // 16 or 32
@@ -766,6 +819,12 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 }
 
 typedef void (*ConvPersFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcConvP, __nv_bfloat16*);
+static ConvPersFn conv_pers_variant_tf32(int mt, int hg) {      // 32 fp32 channels per stage = 128-byte rows = 4 K steps
+#define DCV_V(MT_, HG_) if (mt == MT_ && hg == HG_) return conv_tc_pers_kernel<4, MT_, HG_, true>;
+  DCV_V(1, 1) DCV_V(2, 1) DCV_V(4, 1) DCV_V(1, 2) DCV_V(2, 2) DCV_V(4, 2) DCV_V(1, 3) DCV_V(2, 3) DCV_V(4, 3)
+#undef DCV_V
+  return nullptr;
+}
 static ConvPersFn conv_pers_variant(int ks, int mt, int hg) {
 #define DCV_V(KS_, MT_, HG_) if (ks == KS_ && mt == MT_ && hg == HG_) return conv_tc_pers_kernel<KS_, MT_, HG_>;
   DCV_V(4, 1, 1) DCV_V(4, 2, 1) DCV_V(4, 4, 1) DCV_V(2, 1, 1) DCV_V(2, 2, 1) DCV_V(2, 4, 1) DCV_V(1, 1, 1) DCV_V(1, 2, 1) DCV_V(1, 4, 1)
@@ -1013,9 +1072,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
 // ------------------------------------------------------------------------------------------ packing
 // gather : out[n][tap][k]                 (n < npad, k < Kc)
 // scatter: out[phase][n][j][k]            (j = tap-in-phase index in the kernel's loop order)
+template <typename OT>
 __device__ __forceinline__ void pack_weight_tc_elem(const ConvP& c, const float* __restrict__ w, int64_t s_l, int64_t s_s,
                                                     int64_t s_tap, const WeightWin& win, int npad, int64_t i,
-                                                    __nv_bfloat16* __restrict__ out) {
+                                                    OT* __restrict__ out) {
   // one thread per (phase, n, k): it walks the taps of its phase, so the fp32 reads of a thread fall into one or two
   // cache lines (taps are the innermost dimension of the PyTorch layouts) and the bf16 writes of a warp are contiguous in k
   const int64_t per_phase_nk = (int64_t)npad * c.Kc;
@@ -1029,19 +1089,20 @@ __device__ __forceinline__ void pack_weight_tc_elem(const ConvP& c, const float*
   const bool real = win.has(cl, cs);
   if (!real && !win.fill) return;
   const float* wb = w + (cl - win.cl_off) * s_l + (cs - win.cs_off) * s_s;
-  __nv_bfloat16* ob = out + ((int64_t)ph * npad + n) * ntaps * c.Kc + k;
+  OT* ob = out + ((int64_t)ph * npad + n) * ntaps * c.Kc + k;
   int j = 0;
   for (int jt = 0; jt < f.nt; ++jt)
     for (int jh = 0; jh < f.nh; ++jh)
       for (int jw = 0; jw < f.nw; ++jw, ++j) {
         const int tap = ((f.a0t + f.ast * jt) * c.kh + (f.a0h + f.ash * jh)) * c.kw + (f.a0w + f.asw * jw);
-        ob[(int64_t)j * c.Kc] = __float2bfloat16_rn(real ? wb[tap * s_tap] : 0.f);
+        stf(ob + (int64_t)j * c.Kc, real ? wb[tap * s_tap] : 0.f);
       }
 }
 
+template <typename OT>
 __global__ void __launch_bounds__(256)
 pack_weight_tc_kernel(ConvP c, const float* __restrict__ w, int64_t s_l, int64_t s_s, int64_t s_tap, WeightWin win,
-                      int npad, int phases, __nv_bfloat16* __restrict__ out) {
+                      int npad, int phases, OT* __restrict__ out) {
   pdl_wait(); pdl_trigger();
   const int64_t total = (int64_t)npad * c.Kc * phases;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
@@ -1113,31 +1174,32 @@ static EncodeTiledFn get_encode() {
 
 // activation map: dims {C, W, H, T, N}, box {cbox, bw*ew, bh*eh, bt*et, bn}, traversal strides {1, ew, eh, et, 1}
 static int make_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int N, int64_t ld, int cbox,
-                        int bw, int bh, int bt, int bn, int ew, int eh, int et, CUtensorMapSwizzle swz) {
+                        int bw, int bh, int bt, int bn, int ew, int eh, int et, CUtensorMapSwizzle swz, int esize = 2) {
   EncodeTiledFn enc = get_encode();
   DCV_REQUIRE(enc, "cuTensorMapEncodeTiled entry point unavailable");
-  DCV_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld % 8) == 0, "TMA operand must be 16-byte aligned (ptr %p, ld %lld)", ptr, (long long)ld);
+  DCV_REQUIRE(((uintptr_t)ptr & 15) == 0 && ((ld * esize) % 16) == 0, "TMA operand must be 16-byte aligned (ptr %p, ld %lld)", ptr, (long long)ld);
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)N};
-  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2, (cuuint64_t)T * H * W * ld * 2};
+  const cuuint64_t es = (cuuint64_t)esize;
+  cuuint64_t strides[4] = {(cuuint64_t)ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es, (cuuint64_t)T * H * W * ld * es};
   cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)(bw * ew), (cuuint32_t)(bh * eh), (cuuint32_t)(bt * et), (cuuint32_t)bn};
   cuuint32_t estr[5] = {1, (cuuint32_t)ew, (cuuint32_t)eh, (cuuint32_t)et, 1};
   for (int i = 0; i < 5; ++i) DCV_REQUIRE(box[i] >= 1 && box[i] <= 256, "TMA box dim %d = %u out of range", i, box[i]);
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DCV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed with %d", (int)r);
   return 0;
 }
 
 static int make_weight_map(CUtensorMap* m, const void* ptr, int64_t K, int npad, int phases, int cbox, int nbox,
-                           CUtensorMapSwizzle swz) {
+                           CUtensorMapSwizzle swz, int esize = 2) {
   EncodeTiledFn enc = get_encode();
   DCV_REQUIRE(enc, "cuTensorMapEncodeTiled entry point unavailable");
   DCV_REQUIRE(((uintptr_t)ptr & 15) == 0, "packed weight must be 16-byte aligned");
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)npad, (cuuint64_t)phases};
-  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * npad * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * esize, (cuuint64_t)K * npad * esize};
   cuuint32_t box[3] = {(cuuint32_t)cbox, (cuuint32_t)nbox, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DCV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed with %d", (int)r);
   return 0;
@@ -1175,20 +1237,21 @@ int conv_tc_supported(const dcv_geom* g, int dir) {
   return 1;
 }
 
-int64_t packed_weight_tc_bytes(const dcv_geom* g, int dir) {
+int64_t packed_weight_tc_bytes(const dcv_geom* g, int dir, int tf32) {
   const ConvP c = make_convp(g, dir);
   const int taps = g->kt * g->kh * g->kw;   // sum over phases of taps-in-phase == taps when k % s == 0
-  return (int64_t)tc_npad(c.Nc) * taps * c.Kc * 2;
+  return (int64_t)tc_npad(c.Nc) * taps * c.Kc * (tf32 ? 4 : 2);
 }
 
 int pack_weight_tc(const dcv_geom* g, int dir, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, WeightWin win,
-                   void* out, cudaStream_t s) {
+                   void* out, cudaStream_t s, int tf32) {
   DCV_REQUIRE(conv_tc_supported(g, dir), "pack_weight_tc: geometry not supported by the tcgen05 kernel");
   const ConvP c = make_convp(g, dir);
   const int phases = c.scatter ? g->st * g->sh * g->sw : 1;
   const int64_t total = (int64_t)tc_npad(c.Nc) * c.Kc * phases;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(pack_weight_tc_kernel, blocks, 256, 0, s, c, w, s_l, s_s, s_tap, win, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
+  if (tf32) launch_k(pack_weight_tc_kernel<float>, blocks, 256, 0, s, c, w, s_l, s_s, s_tap, win, tc_npad(c.Nc), phases, (float*)out);
+  else launch_k(pack_weight_tc_kernel<__nv_bfloat16>, blocks, 256, 0, s, c, w, s_l, s_s, s_tap, win, tc_npad(c.Nc), phases, (__nv_bfloat16*)out);
   return check_launch("pack_weight_tc");
 }
 
@@ -1239,14 +1302,23 @@ int pack_weight_tc_batch(int n, const dcv_geom* const* geoms, const int* dirs, c
 // stats != NULL: also accumulate per-channel sum / sum of squares of the outputs (fused BatchNorm statistics, persistent
 // TMA-store path only).  slots_out != NULL: planning query - store the number of [2][npad] partial-sum slots such a launch
 // writes (0 = this geometry cannot fuse the statistics) and return without launching anything.
+int conv_tf32_supported(const dcv_geom* g, int dir) {
+  if (!conv_tc_supported(g, dir)) return 0;
+  const ConvP c = make_convp(g, dir);
+  return c.Kc % 32 == 0 && c.Nc % 32 == 0 && c.wN > 1;
+}
+
+// tf32 != 0: fp32 activations / packed weights / output, kind::tf32 MMAs (x, wp, y are float buffers, ldx / ldy in floats)
 int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, int act,
-            float slope, float* stats, int* slots_out, cudaStream_t s) {
+            float slope, float* stats, int* slots_out, cudaStream_t s, int tf32) {
   if (slots_out) *slots_out = 0;
   DCV_REQUIRE(conv_tc_supported(g, dir), "conv_tc: geometry not supported by the tcgen05 kernel");
+  DCV_REQUIRE(!tf32 || (conv_tf32_supported(g, dir) && !stats && !slots_out), "conv_tc: geometry not supported by the tf32 variant");
+  const int esz = tf32 ? 4 : 2;
   TcConvP p;
   p.c = make_convp(g, dir);
   const ConvP& c = p.c;
-  if (!c.scatter && c.wN == 1 && c.Kc % 8 == 0 && (ldx % 8) == 0 && (((uintptr_t)x) & 15) == 0 && !g_tune.no_gemv) {
+  if (!tf32 && !c.scatter && c.wN == 1 && c.Kc % 8 == 0 && (ldx % 8) == 0 && (((uintptr_t)x) & 15) == 0 && !g_tune.no_gemv) {
     if (slots_out) return 0;
     DCV_REQUIRE(!stats, "conv_tc: fused statistics are not available for the single-channel head kernel");
     const int64_t M = (int64_t)c.N * c.Ot * c.Oh * c.Ow;          // one warp per logit
@@ -1259,22 +1331,23 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   choose_box(128, f0.Qw, f0.Qh, f0.Qt, c.N, &p.bw, &p.bh, &p.bt, &p.bn);
   p.tiles_w = ceil_div(f0.Qw, p.bw); p.tiles_h = ceil_div(f0.Qh, p.bh); p.tiles_t = ceil_div(f0.Qt, p.bt);
   p.tiles_n = ceil_div(c.N, p.bn);
-  p.cblk = c.Kc % 64 == 0 ? 64 : (c.Kc % 32 == 0 ? 32 : 16);
+  p.cblk = tf32 ? 32 : (c.Kc % 64 == 0 ? 64 : (c.Kc % 32 == 0 ? 32 : 16));   // 128-byte rows whenever the channel count allows
   p.kchunks = c.Kc / p.cblk;
   const int npad = tc_npad(c.Nc);
   p.bnt = tc_bnt(npad);
-  p.swz_layout = p.cblk == 64 ? 2 : (p.cblk == 32 ? 4 : 6);
-  const CUtensorMapSwizzle swz = p.cblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                              : (p.cblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  p.b_bytes = (p.bnt * p.cblk * 2 + 1023) / 1024 * 1024;
+  const int row_bytes = p.cblk * esz;
+  p.swz_layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                  : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  p.b_bytes = (p.bnt * p.cblk * esz + 1023) / 1024 * 1024;
   const int ntaps0 = f0.nt * f0.nh * f0.nw;
   { const char* e = exp_env("DCV_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.ldy = ldy; p.act = act; p.slope = slope;
-  p.vec_ok = (((uintptr_t)y & 15) == 0) && (ldy % 8 == 0);
+  p.vec_ok = (((uintptr_t)y & 15) == 0) && ((ldy * esz) % 16 == 0);
 
   CUtensorMap mapA, mapB;
   int rc = 0;
-  const bool g4 = c.Kc == 16 && ntaps0 >= 4 && !g_tune.no_tapgroup;   // grouped-tap mode for 16-channel (image-like) operands
+  const bool g4 = !tf32 && c.Kc == 16 && ntaps0 >= 4 && !g_tune.no_tapgroup;   // grouped-tap mode for 16-channel (image-like) operands
   const int64_t Kph = (int64_t)ntaps0 * c.Kc;  // K extent of one phase
 
   {
@@ -1289,7 +1362,10 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     DCV_REQUIRE(phases <= 8, "conv_tc: %d sub-pixel phases", phases);
     for (int ph = 0; ph < phases; ++ph) p.phs[ph] = make_phase(c, ph);
     p.tma_store = 0;                                         // 1: 64-channel chunks, 2: one 16- / 32-channel chunk
-    if ((((uintptr_t)y & 15) == 0) && (ldy % 8 == 0) && !g_tune.no_tma_store) {
+    if (tf32) {
+      DCV_REQUIRE(p.vec_ok, "conv_tc (tf32): the output must be 16-byte aligned");
+      p.tma_store = 1;
+    } else if ((((uintptr_t)y & 15) == 0) && (ldy % 8 == 0) && !g_tune.no_tma_store) {
       if (p.bnt % 64 == 0) p.tma_store = 1;
       else if ((p.bnt == 16 || p.bnt == 32) && c.Nc >= p.bnt && !g_tune.no_narrow_tma_store) p.tma_store = 2;
     }
@@ -1309,20 +1385,20 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
       bool same = true;                                       // every phase has the same number of h taps
       for (int ph = 1; ph < phases; ++ph) same = same && (make_phase(c, ph).nh == f0.nh);
       const int bsz = hg * p.b_bytes;
-      if ((hg == 2 || hg == 3) && hbw && f0.Qh >= hbh && same && p.cblk >= 32 && bsz <= 96 * 1024) {
+      if ((hg == 2 || hg == 3) && hbw && f0.Qh >= hbh && same && row_bytes >= 64 && bsz <= 96 * 1024) {
         p.hg = hg; p.hcls = f0.nh / hg;
         p.bw = hbw; p.bh = hbh; p.bt = 1; p.bn = 1;
         p.tiles_w = ceil_div(f0.Qw, p.bw); p.tiles_h = ceil_div(f0.Qh, p.bh); p.tiles_t = f0.Qt;
       }
     }
     const int box_rows = (p.bh + p.hg - 1) * p.bw * p.bt * p.bn;                       // A rows of one M tile incl. halo
-    p.a_tile16 = (box_rows * p.cblk * 2) >> 4;
+    p.a_tile16 = (box_rows * p.cblk * esz) >> 4;
     const int64_t sp_tiles = (int64_t)p.tiles_w * p.tiles_h * p.tiles_t * p.ntn * phases;
     auto balance = [&](int mt) {
       const int64_t items = sp_tiles * ceil_div(c.N, p.bn * mt);
       return (double)items / ((double)num_sms * (double)((items + num_sms - 1) / num_sms));
     };
-    auto a_bytes_of = [&](int mt) { return g4 ? TAPG * mt * 128 * 32 : mt * box_rows * p.cblk * 2; };
+    auto a_bytes_of = [&](int mt) { return g4 ? TAPG * mt * 128 * 32 : mt * box_rows * p.cblk * esz; };
     auto stages_of = [&](int mt) { return (222 * 1024 - stg_bytes) / (a_bytes_of(mt) + p.hg * p.b_bytes); };
     // M tiles per work item: more tiles share every weight tile and amortise the per-stage barrier handshake over more
     // MMAs (>= 512 tensor cycles per stage wanted: hg * mt * bnt >= 256), as long as two accumulator sets fit in TMEM, the
@@ -1342,7 +1418,7 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     p.tiles_n = ceil_div(c.N, p.bn * p.mt);
     p.items = (int)(sp_tiles * p.tiles_n);
     p.a_bytes = a_bytes_of(p.mt);
-    p.tx_bytes = p.a_bytes + p.hg * p.bnt * p.cblk * 2;
+    p.tx_bytes = p.a_bytes + p.hg * p.bnt * p.cblk * esz;
     p.acc_cols = p.mt * p.bnt;
     p.tmem_cols = pow2_ceil(2 * p.acc_cols < 32 ? 32 : 2 * p.acc_cols);
     int st = stages_of(p.mt);
@@ -1352,14 +1428,14 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     // sm_reserve > 0 (data-parallel runs, while a gradient bucket is in flight): leave a few SMs to NCCL's CTAs
     const int sms_avail = num_sms - g_tune.sm_reserve > 8 ? num_sms - g_tune.sm_reserve : 8;
     const int grid_p = p.items < sms_avail ? p.items : sms_avail;
-    const bool can_stats = p.tma_store == 1 && !g_tune.no_fused_stats;
+    const bool can_stats = !tf32 && p.tma_store == 1 && !g_tune.no_fused_stats;
     if (slots_out) { *slots_out = can_stats ? 4 * grid_p : 0; return 0; }
     DCV_REQUIRE(!stats || can_stats, "conv_tc: fused statistics need the TMA-store epilogue (output channels %% 64 == 0)");
     p.stats = stats; p.npad = npad;
-    rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh + p.hg - 1, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz);
+    rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh + p.hg - 1, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz, esz);
     if (rc) return rc;
     rc = g4 ? make_weight_map(&mapB, wp, Kph, npad, phases, 64, p.bnt, CU_TENSOR_MAP_SWIZZLE_128B)
-            : make_weight_map(&mapB, wp, Kph, npad, phases, p.cblk, p.bnt, swz);
+            : make_weight_map(&mapB, wp, Kph, npad, phases, p.cblk, p.bnt, swz, esz);
     if (rc) return rc;
     CUtensorMap mapY = mapA;
     if (p.tma_store) {
@@ -1372,17 +1448,18 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
       const int yt = p.bt < rem ? p.bt : rem; rem /= yt;
       const int yn = p.bn < rem ? p.bn : rem; rem /= yn;
       DCV_REQUIRE(rem == 1, "conv_tc: tile %dx%dx%dx%d has no 32-row sub-box", p.bw, p.bh, p.bt, p.bn);
-      const int ycw = p.tma_store == 1 ? 64 : p.bnt;
+      const int ycw = tf32 ? 32 : (p.tma_store == 1 ? 64 : p.bnt);      // 128-byte rows: 64 bf16 or 32 fp32 channels
+      const int ybytes = ycw * esz;
       rc = make_act_map(&mapY, y, c.Nc, c.Ow, c.Oh, c.Ot, c.N, ldy, ycw, yw, yh, yt, yn, f0.osw, f0.osh, f0.ost,
-                        ycw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (ycw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B));
+                        ybytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (ybytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), esz);
       if (rc) return rc;
     }
     const int smem_p = st * (p.a_bytes + p.hg * p.b_bytes) + stg_bytes + 1024;
-    const int ks = g4 ? 0 : p.cblk / 16;
-    ConvPersFn fn = conv_pers_variant(ks, p.mt, p.hg);
-    DCV_REQUIRE(fn != nullptr, "conv_tc: no persistent kernel variant for cblk %d mt %d hg %d", p.cblk, p.mt, p.hg);
-    static int smem_set_p[256] = {0};
-    int& set = smem_set_p[(ks * 8 + p.mt) * 4 + p.hg];
+    const int ks = g4 ? 0 : row_bytes / 32;                       // 32-byte K steps per stage
+    ConvPersFn fn = tf32 ? conv_pers_variant_tf32(p.mt, p.hg) : conv_pers_variant(ks, p.mt, p.hg);
+    DCV_REQUIRE(fn != nullptr, "conv_tc: no persistent kernel variant for cblk %d mt %d hg %d tf32 %d", p.cblk, p.mt, p.hg, tf32);
+    static int smem_set_p[512] = {0};
+    int& set = smem_set_p[((tf32 ? 8 : ks) * 8 + p.mt) * 4 + p.hg];
     if (smem_p > set) {
       DCV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
       set = smem_p;

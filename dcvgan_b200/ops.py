@@ -11,7 +11,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (ACT_LEAKY, ACT_NONE, ACT_TANH, DCV_BF16, DCV_F32, DIR_GATHER, DIR_SCATTER, IMPL_SIMT, IMPL_TC, Geom,
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_TANH, DCV_BF16, DCV_F32, DIR_GATHER, DIR_SCATTER, IMPL_SIMT, IMPL_TC, IMPL_TC_TF32, Geom,
                    check, lib)
 
 __all__ = ["ConvSpec", "Act"]
@@ -30,7 +30,7 @@ def dcv_dtype(t):
 
 
 def torch_dtype(precision):
-    return torch.float32 if precision == "fp32" else torch.bfloat16
+    return torch.float32 if precision in ("fp32", "tf32") else torch.bfloat16
 
 
 class Act:
@@ -212,6 +212,7 @@ def _tc_ok(t):
 _FORCE_SIMT = bool(int(os.environ.get("DCV_FORCE_SIMT", "0")))   # debugging aid: bf16 storage without tcgen05
 
 
+TF32_TC = False     # dcvgan_b200.set_precision("tf32"): fp32 convolutions with channel counts % 32 == 0 run on tcgen05 kind::tf32
 STRICT_TC = False   # set by the fused trainer at production widths: a bf16 convolution that cannot run on tcgen05 is an error
 
 
@@ -221,6 +222,9 @@ def choose_conv_impl(g, direction, x):
     if STRICT_TC and x.dtype == torch.bfloat16 and not _FORCE_SIMT:
         raise _lib.DcvError(f"bf16 convolution {g.key()} dir {direction} (ptr % 16 = {x.ptr % 16}, ld {x.ld}) is not eligible for the "
                             "tcgen05 kernel; refusing to fall back to the CUDA-core kernel silently")
+    if (TF32_TC and not _FORCE_SIMT and x.dtype == torch.float32 and x.ptr % 16 == 0 and x.ld % 4 == 0
+            and lib().dcv_conv_tf32_supported(C.byref(g), direction)):
+        return IMPL_TC_TF32
     return IMPL_SIMT
 
 

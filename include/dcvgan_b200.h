@@ -36,7 +36,9 @@ enum { DCV_F32 = 0, DCV_BF16 = 1 };
 /* activation selectors (generator.py:63,76,78,175,206,243,276; discriminator.py:82-99) */
 enum { DCV_ACT_NONE = 0, DCV_ACT_LEAKY = 1, DCV_ACT_TANH = 2 };
 /* implementation selector for the convolution entry points */
-enum { DCV_IMPL_SIMT = 0, DCV_IMPL_TC = 1 };
+/* SIMT: CUDA-core fp32 kernels (exact mode, any shape); TC: tcgen05 kind::f16 on bf16 tensors; TC_TF32: tcgen05 kind::tf32 on
+ * fp32 tensors (forward / data gradient of layers whose channel counts are multiples of 32) */
+enum { DCV_IMPL_SIMT = 0, DCV_IMPL_TC = 1, DCV_IMPL_TC_TF32 = 2 };
 /* direction of a correlation w.r.t. the geometry below */
 enum { DCV_DIR_GATHER = 0, DCV_DIR_SCATTER = 1 };
 /* loss kinds (loss.py:93-99,123-131,163-166,190-193) */
@@ -118,6 +120,8 @@ int dcv_pack_weight_multi(const dcv_geom* g, int dir, int n, const float* const*
  * dcv_conv_tc_supported tells whether the tcgen05 kernel covers (geom, dir).
  */
 int dcv_conv_tc_supported(const dcv_geom* g, int dir);
+/* same question for DCV_IMPL_TC_TF32 (fp32 activations and packed weights, tf32 products, fp32 accumulation and output) */
+int dcv_conv_tf32_supported(const dcv_geom* g, int dir);
 int dcv_conv(const dcv_geom* g, int dir, int impl, int dtype, const void* x, int64_t ldx,
              const void* wp, void* y, int64_t ldy, int act, float slope, void* stream);
 

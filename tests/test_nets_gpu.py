@@ -327,14 +327,26 @@ def _net_cosines(my, ref):
     return out
 
 
-@pytest.mark.parametrize("precision,ltol,ctol,ntol", [("fp32", 1e-3, 0.999, 0.9999), ("bf16", 5e-2, 0.85, 0.95)])
+@pytest.mark.parametrize("precision,ltol,ctol,ntol", [("fp32", 1e-3, 0.999, 0.9999), ("tf32", 1e-3, 0.999, 0.9999), ("bf16", 5e-2, 0.85, 0.95)])
 def test_train_step_full_width(precision, ltol, ctol, ntol, tmp_path):
     """One iteration at the real layer widths (ngf = ndf = 64, gdis ndf 32, isogd-flow shapes), batch 2."""
     cfg = small_cfg("optical-flow", 2, "hinge-loss", noise=True, ngf=64, ndf=64)
     cfg["gdis"]["ndf"] = 32
     cfg["gdis"]["use_noise"] = False
     init = orc.init_all(cfg, 21)
-    o, tr, models, ref_l, my_l, ref_g, my_g = _run_side_by_side(cfg, init, 1, precision, tmp_path, [77], 31)
+    from dcvgan_b200 import ops
+    ops.TRACE = []
+    try:
+        o, tr, models, ref_l, my_l, ref_g, my_g = _run_side_by_side(cfg, init, 1, precision, tmp_path, [77], 31)
+    finally:
+        trace, ops.TRACE = ops.TRACE, None
+    impls = [t[3] for t in trace if t[0] == "conv"]
+    print(f"full width [{precision}]: convolution launches by implementation (0 CUDA cores, 1 tcgen05 bf16, 2 tcgen05 tf32):",
+          {i: impls.count(i) for i in sorted(set(impls))})
+    if precision == "tf32":      # the fp32/TF32 gate runs on the tensor cores: every eligible forward / data gradient is kind::tf32
+        assert impls.count(2) >= 40 and impls.count(1) == 0, impls
+    if precision == "bf16":
+        assert impls.count(0) == 0, "bf16 mode must not fall back to the CUDA-core convolution at production widths"
     got = dict(zip(("loss_idis", "loss_vdis", "loss_gdis", "loss_gen"), my_l[0]))
     for k in got:
         assert abs(got[k] - ref_l[0][k]) <= ltol * max(1.0, abs(ref_l[0][k])), (k, got[k], ref_l[0][k])

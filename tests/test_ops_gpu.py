@@ -131,6 +131,40 @@ def test_conv_tcgen05(case):
     _run_case(_ops(), case, torch.bfloat16, True, 1e-2)
 
 
+TF32_CASES = [c for c in TC_CASES if c[2] % 32 == 0 and c[3] % 32 == 0]
+
+
+@pytest.mark.parametrize("case", TF32_CASES, ids=[c[0] for c in TF32_CASES])
+def test_conv_tcgen05_tf32(case):
+    """tcgen05 kind::tf32 variant of the persistent convolution kernel (fp32 tensors, fp32 packed weights, fp32 output
+    through the TMA-store epilogue): forward and data gradient against PyTorch fp32.  TF32 keeps 10 mantissa bits of each
+    operand (products exact, fp32 accumulation): norm-relative error ~3e-4, gate 1e-3 (the north star's fp32/TF32 bar)."""
+    ops = _ops()
+    from dcvgan_b200._lib import IMPL_TC_TF32
+    name, kind, cin, cout, k, s, p, n, sp = case
+    torch.manual_seed(sum(map(ord, name)) % 1000)
+    three_d = k[0] > 1
+    spec = ops.ConvSpec(kind, cin, cout, k, s, p)
+    x = torch.randn(n, cin, *sp, requires_grad=True)
+    w = (torch.randn((cout, cin, *k) if kind == "conv" else (cin, cout, *k)) * 0.1).requires_grad_(True)
+    y_ref = _torch_fwd(kind, x, w, s, p, three_d)
+    dy = torch.randn_like(y_ref)
+    y_ref.backward(dy)
+    g = spec.geom(n, sp)
+    assert ops.lib().dcv_conv_tf32_supported(C.byref(g), spec.fwd_dir) and ops.lib().dcv_conv_tf32_supported(C.byref(g), spec.bwd_dir)
+    xa = to_act(x.detach(), torch.float32)
+    ya = ops.Act.empty(n, *spec.out_spatial(sp), cout, torch.float32)
+    wdev = (w.detach().squeeze(2) if (kind == "convT" or not three_d) else w.detach()).contiguous().cuda()
+    ops.conv(g, spec.fwd_dir, IMPL_TC_TF32, xa, ops.pack_weight(spec, g, spec.fwd_dir, IMPL_TC_TF32, wdev), ya)
+    e_fwd = rel_err(from_act(ya), y_ref.detach())
+    dya = to_act(dy, torch.float32)
+    dxa = ops.Act.empty(n, *sp, cin, torch.float32)
+    ops.conv(g, spec.bwd_dir, IMPL_TC_TF32, dya, ops.pack_weight(spec, g, spec.bwd_dir, IMPL_TC_TF32, wdev), dxa)
+    e_dx = rel_err(from_act(dxa), x.grad)
+    print(f"{name} [tf32]: fwd {e_fwd:.2e} dx {e_dx:.2e}")
+    assert e_fwd < 1e-3 and e_dx < 1e-3, (name, e_fwd, e_dx)
+
+
 VARIANTS = [{"nohalo": 1}, {"mt": 1}, {"mt": 4}, {"no_tma_store": 1}, {"wgrad_waves": 2}, {"no_tapgroup": 1}, {"sm_reserve": 16},
             {"pdl": 1}]
 

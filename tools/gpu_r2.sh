@@ -35,6 +35,8 @@ for st in $STAGES; do
       # one `ncu --set full` capture per dominant launch (B200_PROFILING.md recipe), after the plain run exited 0
       python tools/probe_layers.py vdis_main1_dgrad up5_fwd vdis_main1_fwd vdis_main1_wgrad down0_wgrad > gpurun_out/${TAG}_probe_layers.log 2>&1 && \
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_pers|wgrad_tc" -c 10 -o gpurun_out/${TAG}_top python tools/probe_layers.py vdis_main1_dgrad up5_fwd vdis_main1_fwd vdis_main1_wgrad down0_wgrad > gpurun_out/${TAG}_ncutop.log 2>&1; echo "ncutop rc=$?" | tee -a gpurun_out/${TAG}_rc.log; cat gpurun_out/${TAG}_probe_layers.log;;
+    tf32)
+      timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_nets_gpu.py -m gpu -q -s -k "tf32 or full_width" > gpurun_out/${TAG}_tf32.log 2>&1; echo "tf32 rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_tf32.log | grep "tf32\|passed\|failed\|Error\|error" | tail -30;;
     bench)
       timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
     benchfast)
