@@ -327,7 +327,11 @@ def _net_cosines(my, ref):
     return out
 
 
-@pytest.mark.parametrize("precision,ltol,ctol,ntol", [("fp32", 1e-3, 0.999, 0.9999), ("tf32", 1e-3, 0.999, 0.9999), ("bf16", 5e-2, 0.85, 0.95)])
+# tf32: kind::tf32 TRUNCATES both operands to 10 mantissa bits (every product shrinks by up to 2^-9: a uniform -7.7e-4 on each
+# layer's output, tests/test_ops_gpu.py::test_conv_tcgen05_tf32).  Losses stay within 1e-3; through the 12-layer U-Net at
+# batch 2 the per-network gradient cosine is 0.996 (measured r2n: ggen 0.9961, cgen 0.9965, idis 0.9999, vdis 0.9999, gdis
+# 0.9995; worst single tensor 0.9917, the GRU's weight_hh), against 0.99999 in the exact fp32 mode.
+@pytest.mark.parametrize("precision,ltol,ctol,ntol", [("fp32", 1e-3, 0.999, 0.9999), ("tf32", 1e-3, 0.99, 0.995), ("bf16", 5e-2, 0.85, 0.95)])
 def test_train_step_full_width(precision, ltol, ctol, ntol, tmp_path):
     """One iteration at the real layer widths (ngf = ndf = 64, gdis ndf 32, isogd-flow shapes), batch 2."""
     cfg = small_cfg("optical-flow", 2, "hinge-loss", noise=True, ngf=64, ndf=64)
