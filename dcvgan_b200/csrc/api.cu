@@ -53,6 +53,8 @@ int pack_weight_tc_batch(int, const dcv_geom* const*, const int*, const float* c
                          void* const*, cudaStream_t);
 int64_t packed_weight_tc_bytes(const dcv_geom*, int, int);
 int conv_tf32_supported(const dcv_geom*, int);
+int head_loss_supported(const dcv_geom*, int);
+int head_loss(const dcv_geom*, int, const void*, int64_t, const void*, void*, int64_t, int, float*, int, void*, int64_t, float, unsigned*, cudaStream_t);
 int pack_weight_tc(const dcv_geom*, int, const float*, int64_t, int64_t, int64_t, WeightWin, void*, cudaStream_t, int);
 int conv_tc(const dcv_geom*, int, const void*, int64_t, const void*, void*, int64_t, int, float, float*, int*, cudaStream_t, int);
 int wgrad_tc_supported(const dcv_geom*);
@@ -83,6 +85,13 @@ const char* dcv_last_error(void) { return g_err; }
 
 long long dcv_launch_count(void) { return g_launches; }
 
+int dcv_head_loss_supported(const dcv_geom* g, int dir) { return g && check_geom(g) == 0 ? head_loss_supported(g, dir) : 0; }
+int dcv_head_loss(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, int kind, float* loss_out,
+                  int accumulate, void* dy, int64_t lddy, float grad_scale, void* counter, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DCV_REQUIRE(x && wp && y && loss_out && counter, "head_loss: null pointer");
+  return head_loss(g, dir, x, ldx, wp, y, ldy, kind, loss_out, accumulate, dy, lddy, grad_scale, (unsigned*)counter, as_stream(stream));
+}
 int dcv_conv_tf32_supported(const dcv_geom* g, int dir) { return g && check_geom(g) == 0 ? conv_tf32_supported(g, dir) : 0; }
 int dcv_img_conv_supported(const dcv_geom* g, int what) { return g && check_geom(g) == 0 ? img_conv_supported_for(g, what) : 0; }
 int64_t dcv_img_conv_bwd_workspace_bytes(const dcv_geom* g) { return g ? img_conv_bwd_ws_bytes(g) : -1; }

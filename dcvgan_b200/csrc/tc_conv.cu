@@ -882,6 +882,93 @@ head_gemv_kernel(ConvP c, const __nv_bfloat16* __restrict__ x, int64_t ldx, cons
   if (lane == 0) y[pos * ldy] = __float2bfloat16_rn(apply_act(acc, act, slope));
 }
 
+// The same GEMV with the adversarial-loss term of the head fused in (loss.py:93-99,123-131,163-166,190-193 on the logits of
+// discriminator.py:101,206,305): every block writes its logits, takes a ticket, and the block that arrives last computes
+// the mean loss over all M logits (in the summation order of loss_kernel, from the bf16-rounded logits it re-reads through
+// L2: identical numbers to the two-launch form) and dL/dlogit for the backward pass.  kind: DCV_LOSS_*.
+__device__ __forceinline__ float hl_softplus(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }   // == misc.cu softplusf_
+__device__ __forceinline__ float hl_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(256)
+head_gemv_loss_kernel(ConvP c, const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
+                      __nv_bfloat16* __restrict__ y, int64_t ldy, int kind, float* __restrict__ loss_out, int accumulate,
+                      __nv_bfloat16* __restrict__ dy, int64_t lddy, float grad_scale, unsigned* __restrict__ counter) {
+  pdl_wait(); pdl_trigger();
+  __shared__ float red[256];
+  __shared__ int s_last;
+  const int lane = threadIdx.x % 32;
+  const int64_t M = (int64_t)c.N * c.Ot * c.Oh * c.Ow;
+  int64_t m = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (m < M) {
+    const int64_t pos = m;
+    const int ow = (int)(m % c.Ow); m /= c.Ow;
+    const int oh = (int)(m % c.Oh); m /= c.Oh;
+    const int ot = (int)(m % c.Ot); const int n = (int)(m / c.Ot);
+    float acc = 0.f;
+    for (int a = 0; a < c.kt; ++a) {
+      const int it = ot * c.st - c.pt + a;
+      if (it < 0 || it >= c.It) continue;
+      for (int b = 0; b < c.kh; ++b) {
+        const int ih = oh * c.sh - c.ph + b;
+        if (ih < 0 || ih >= c.Ih) continue;
+        for (int d = 0; d < c.kw; ++d) {
+          const int iw = ow * c.sw - c.pw + d;
+          if (iw < 0 || iw >= c.Iw) continue;
+          const __nv_bfloat16* xp = x + ((((int64_t)n * c.It + it) * c.Ih + ih) * c.Iw + iw) * ldx;
+          const __nv_bfloat16* wt = w + (int64_t)((a * c.kh + b) * c.kw + d) * c.Kc;
+          for (int k = lane * 8; k < c.Kc; k += 256) {
+            const uint4 xv = *reinterpret_cast<const uint4*>(xp + k);
+            const uint4 wv = *reinterpret_cast<const uint4*>(wt + k);
+            const uint32_t xa[4] = {xv.x, xv.y, xv.z, xv.w}, wa[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc = fmaf(__uint_as_float(xa[i] << 16), __uint_as_float(wa[i] << 16), acc);
+              acc = fmaf(__uint_as_float(xa[i] & 0xFFFF0000u), __uint_as_float(wa[i] & 0xFFFF0000u), acc);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[pos * ldy] = __float2bfloat16_rn(acc);
+  }
+  // ---- last block: the loss term and its gradient over all logits
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float lacc = 0.f;
+  const float inv_n = 1.f / (float)M;
+  for (int64_t i = threadIdx.x; i < M; i += 256) {
+    const unsigned short raw = __ldcg(reinterpret_cast<const unsigned short*>(y + i * ldy));
+    const float v = __uint_as_float((uint32_t)raw << 16);
+    float l, g;
+    switch (kind) {
+      case DCV_LOSS_BCE_ONES:
+      case DCV_LOSS_SOFTPLUS_NEG: l = hl_softplus(-v); g = hl_sigmoid(v) - 1.f; break;
+      case DCV_LOSS_BCE_ZEROS: l = hl_softplus(v); g = hl_sigmoid(v); break;
+      case DCV_LOSS_HINGE_REAL: l = fmaxf(1.f - v, 0.f); g = (1.f - v > 0.f) ? -1.f : 0.f; break;
+      default: l = fmaxf(1.f + v, 0.f); g = (1.f + v > 0.f) ? 1.f : 0.f; break;
+    }
+    lacc += l;
+    if (dy) dy[i * lddy] = __float2bfloat16_rn(g * inv_n * grad_scale);
+  }
+  red[threadIdx.x] = lacc;
+  __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) {
+    if (threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float l = red[0] * inv_n;
+    loss_out[0] = accumulate ? loss_out[0] + l : l;
+    *counter = 0u;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ wgrad_tc
 // D[128 rows = (128/cbA) gathered L blocks of cbA channels, Ns columns = S channels] += A^T B over pixel blocks.
 // A block = (tap, channel chunk of cbA) of the gathered L tensor, B = S tile; both MN-major (channels contiguous),
@@ -1302,6 +1389,24 @@ int pack_weight_tc_batch(int n, const dcv_geom* const* geoms, const int* dirs, c
 // stats != NULL: also accumulate per-channel sum / sum of squares of the outputs (fused BatchNorm statistics, persistent
 // TMA-store path only).  slots_out != NULL: planning query - store the number of [2][npad] partial-sum slots such a launch
 // writes (0 = this geometry cannot fuse the statistics) and return without launching anything.
+int head_loss_supported(const dcv_geom* g, int dir) {
+  if (!conv_tc_supported(g, dir)) return 0;
+  const ConvP c = make_convp(g, dir);
+  return !c.scatter && c.wN == 1 && c.Kc % 8 == 0;
+}
+
+int head_loss(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, int kind, float* loss_out,
+              int accumulate, void* dy, int64_t lddy, float grad_scale, unsigned* counter, cudaStream_t s) {
+  DCV_REQUIRE(head_loss_supported(g, dir) && (ldx % 8) == 0 && (((uintptr_t)x) & 15) == 0, "head_loss: not a single-channel head on an aligned bf16 input");
+  DCV_REQUIRE(kind >= 0 && kind <= 4, "head_loss: unknown loss kind %d", kind);
+  const ConvP c = make_convp(g, dir);
+  const int64_t M = (int64_t)c.N * c.Ot * c.Oh * c.Ow;
+  DCV_REQUIRE(M > 0, "head_loss: empty logits");
+  launch_k(head_gemv_loss_kernel, (unsigned)((M + 7) / 8), 256, 0, s, c, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)wp,
+           (__nv_bfloat16*)y, ldy, kind, loss_out, accumulate, (__nv_bfloat16*)dy, lddy, grad_scale, counter);
+  return check_launch("head_gemv_loss");
+}
+
 int conv_tf32_supported(const dcv_geom* g, int dir) {
   if (!conv_tc_supported(g, dir)) return 0;
   const ConvP c = make_convp(g, dir);

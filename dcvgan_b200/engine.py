@@ -195,8 +195,10 @@ class Block:
         self.act, self.slope, self.dropout = act, slope, dropout
         self.noise = noise  # None or (use_noise, sigma)
 
-    def forward(self, x, out, training, rng_, save=True):
-        """x: input Act; out: Act (slice) that receives the block's output.  Returns ctx for backward."""
+    def forward(self, x, out, training, rng_, save=True, loss=None):
+        """x: input Act; out: Act (slice) that receives the block's output.  Returns ctx for backward.
+        loss (heads only): {'kind', 'out' (1-element fp32 tensor), 'accumulate', 'want_grad'} - the adversarial-loss term of
+        this head is computed in the head's own launch; ctx['dlogits'] then holds dL/dlogits (or None)."""
         spec = self.spec
         w = self.conv.weight
         x_used = x
@@ -221,6 +223,11 @@ class Block:
         if self.bn is None:
             if self._tap_unrolled(impl, x_used):
                 self._forward_tap_unrolled(x_used, out)
+                return ctx
+            if loss is not None and self.act == ACT_NONE and spec.cout == 1 and ops.head_loss_ok(g, spec.fwd_dir, impl, x_used):
+                ctx["dlogits"] = ops.head_loss(g, spec.fwd_dir, x_used.padded_to(cin_p), wp, out.padded_to(cout_p), loss["kind"],
+                                               loss["out"], loss["accumulate"], loss["want_grad"])
+                ctx["loss_fused"] = True
                 return ctx
             ops.conv(g, spec.fwd_dir, impl, x_used.padded_to(cin_p), wp, out.padded_to(cout_p), self.act, self.slope)
             return ctx
@@ -609,8 +616,9 @@ class DisPlan:
                          Block(mk(ndf * 2, ndf * 4), m[9], m[10], ACT_LEAKY, 0.2, noise=nz),
                          Block(mk(ndf * 4, 1), m[13], None, ACT_NONE, noise=nz)]
 
-    def forward(self, xg, xc, training, rng_, save=True):
-        """xg, xc: Acts (B,T,H,W,C) (T == 1 for idis).  Returns logits Act (B, To, 4, 4, 1)."""
+    def forward(self, xg, xc, training, rng_, save=True, loss=None):
+        """xg, xc: Acts (B,T,H,W,C) (T == 1 for idis).  Returns (logits Act (B, To, 4, 4, 1), ctx); with `loss` (see
+        Block.forward) the head fuses its loss term and ctx_or_info['head'] carries {'loss_fused', 'dlogits'}."""
         ndf, dtype = self.mod.ndf, xg.dtype
         ctx = {}
         if self.kind == "gdis":
@@ -630,9 +638,10 @@ class DisPlan:
         for blk in self.main:
             sp = blk.spec.out_spatial(h.spatial)
             out = Act.empty(h.n, sp[0], sp[1], sp[2], blk.spec.cout, dtype)
-            mctx.append(blk.forward(h, out, training, rng_, save))
+            mctx.append(blk.forward(h, out, training, rng_, save, loss=loss if blk is self.main[-1] else None))
             h = out
         ctx["main"] = mctx
+        self.last_head = {"loss_fused": bool(mctx[-1].get("loss_fused")), "dlogits": mctx[-1].get("dlogits")}
         return h, (ctx if save else None)
 
     def backward(self, ctx, dlogits, sink, need_dx=False, need_dw=True):

@@ -335,6 +335,28 @@ def conv(g, direction, impl, x, wp, y, act=ACT_NONE, slope=0.0):
     check(lib().dcv_conv(C.byref(g), direction, impl, dcv_dtype(x), xp, ldx, wp.data_ptr(), yp, ldy, act, slope, _stream()))
 
 
+HEAD_LOSS = os.environ.get("DCV_NO_HEAD_LOSS", "0") != "1"
+_HEAD_COUNTER = {}
+
+
+def head_loss_ok(g, direction, impl, x):
+    return (HEAD_LOSS and impl == IMPL_TC and x.dtype == torch.bfloat16 and x.ptr % 16 == 0 and x.ld % 8 == 0
+            and bool(lib().dcv_head_loss_supported(C.byref(g), direction)))
+
+
+def head_loss(g, direction, x, wp, y, kind, loss_out, accumulate, want_grad, grad_scale=1.0):
+    """discriminator head + its loss term in one launch; returns dL/dlogits (Act shaped like y) or None"""
+    if TRACE is not None:
+        TRACE.append(("conv", g.key(), direction, IMPL_TC, x.ld, y.ld, x.c, y.c))
+    cnt = _HEAD_COUNTER.get(x.device)
+    if cnt is None:
+        cnt = _HEAD_COUNTER[x.device] = torch.zeros(4, dtype=torch.int32, device=x.device)
+    dy = Act.empty(y.n, y.t, y.h, y.w, y.c, y.dtype) if want_grad else None
+    check(lib().dcv_head_loss(C.byref(g), direction, x.ptr, x.ld, wp.data_ptr(), y.ptr, y.ld, kind, loss_out.data_ptr(), int(accumulate),
+                              None if dy is None else dy.ptr, 1 if dy is None else dy.ld, grad_scale, cnt.data_ptr(), _stream()))
+    return dy
+
+
 def conv_stats_slots(g, direction, x, y):
     """> 0: the convolution can accumulate the BatchNorm batch statistics of its output in its epilogue (that many slots)"""
     if _FORCE_SIMT or y.ptr % 16:

@@ -418,14 +418,18 @@ class Trainer(object):
         ops.frame_extract(clip, t, f)
         return f
 
-    def _dis_forward(self, xg, xc, t_rand, save):
-        """idis on frame t_rand, vdis and gdis on the clips, in the reference's order (trainer.py:299-301)."""
+    def _dis_forward(self, xg, xc, t_rand, save, loss=None):
+        """idis on frame t_rand, vdis and gdis on the clips, in the reference's order (trainer.py:299-301).
+        loss: None or {name: {'kind', 'out', 'accumulate', 'want_grad'}} - the loss term of each listed discriminator is fused
+        into its head launch.  Returns {name: (logits, ctx, head info {'loss_fused', 'dlogits'})}."""
         r = engine.rng()
+        loss = loss or {}
         out = {}
-        out["idis"] = self._plans["idis"].forward(self._frame(xg, t_rand), self._frame(xc, t_rand), True, r, save)
-        out["vdis"] = self._plans["vdis"].forward(xg, xc, True, r, save)
-        if self.use_gdis:
-            out["gdis"] = self._plans["gdis"].forward(xg, None, True, r, save)
+        for n, args in (("idis", (self._frame(xg, t_rand), self._frame(xc, t_rand))), ("vdis", (xg, xc)), ("gdis", (xg, None))):
+            if n == "gdis" and not self.use_gdis:
+                continue
+            y, ctx = self._plans[n].forward(args[0], args[1], True, r, save, loss=loss.get(n))
+            out[n] = (y, ctx, self._plans[n].last_head)
         return out
 
     def _generate(self, B, ggen_training, cgen_training, save):
@@ -597,13 +601,16 @@ class Trainer(object):
             self.models[n].train()
         upd_d = self.iteration % cfg["num_gen_update"] == 0                                     # sic, trainer.py:318
         xc_r, xg_r = self._to_clip(xc_real), self._to_clip(xg_real, self.models["ggen"].channel)
-        real = self._dis_forward(xg_r, xc_r, t_rand, upd_d)
+        def spec(kind, slot_of, acc_of, want_grad, names):
+            return {n: {"kind": kind, "out": losses[slot_of(n):slot_of(n) + 1], "accumulate": acc_of(n), "want_grad": want_grad} for n in names}
+        real = self._dis_forward(xg_r, xc_r, t_rand, upd_d, spec(L.KIND_REAL, slot.get, lambda n: False, upd_d, self._dnames))
         xg_f, xc_f, _, _ = self._generate(B, ggen.training, cgen.training, save=False)
-        fake = self._dis_forward(xg_f.reshape_nt(B, T), xc_f.reshape_nt(B, T), t_rand, upd_d)
+        fake = self._dis_forward(xg_f.reshape_nt(B, T), xc_f.reshape_nt(B, T), t_rand, upd_d,
+                                 spec(L.KIND_FAKE, slot.get, lambda n: True, upd_d, self._dnames))
         grads = {}
-        for n in self._dnames:
-            dr = self._loss_terms(real[n][0], L.KIND_REAL, slot[n], losses, False, upd_d)
-            df = self._loss_terms(fake[n][0], L.KIND_FAKE, slot[n], losses, True, upd_d)
+        for n in self._dnames:     # heads that could not fuse their loss term (fp32 / CUDA-core path): the separate loss kernel
+            dr = real[n][2]["dlogits"] if real[n][2]["loss_fused"] else self._loss_terms(real[n][0], L.KIND_REAL, slot[n], losses, False, upd_d)
+            df = fake[n][2]["dlogits"] if fake[n][2]["loss_fused"] else self._loss_terms(fake[n][0], L.KIND_FAKE, slot[n], losses, True, upd_d)
             grads[n] = (dr, df)
         if upd_d:
             for n in self._dnames:
@@ -626,11 +633,11 @@ class Trainer(object):
             for n in self._dnames:
                 self._flat[n].adam_step(1.0 / self.world)
         xg_clip, xc_clip = xg_f.reshape_nt(B, T), xc_f.reshape_nt(B, T)
-        fake = self._dis_forward(xg_clip, xc_clip, t_rand, upd_g)
         gen_terms = ["idis", "vdis"] + (["gdis"] if (self.use_gdis and L.gen_uses_gdis) else [])
+        fake = self._dis_forward(xg_clip, xc_clip, t_rand, upd_g, spec(L.KIND_GEN, lambda n: 3, lambda n: n != "idis", upd_g, gen_terms))
         dls = {}
         for i, n in enumerate(gen_terms):
-            dls[n] = self._loss_terms(fake[n][0], L.KIND_GEN, 3, losses, i > 0, upd_g)
+            dls[n] = fake[n][2]["dlogits"] if fake[n][2]["loss_fused"] else self._loss_terms(fake[n][0], L.KIND_GEN, 3, losses, i > 0, upd_g)
         if upd_g:
             none = engine.GradSink()
             dxg = Act.empty(B, T, 64, 64, xg_clip.c, self.dtype)

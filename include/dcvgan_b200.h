@@ -120,6 +120,14 @@ int dcv_pack_weight_multi(const dcv_geom* g, int dir, int n, const float* const*
  * dcv_conv_tc_supported tells whether the tcgen05 kernel covers (geom, dir).
  */
 int dcv_conv_tc_supported(const dcv_geom* g, int dir);
+/* Discriminator head (Conv -> 1 channel, discriminator.py:101,206,305) with its adversarial-loss term fused in (loss.py:93-99,
+ * 123-131,163-166,190-193): y = correlate(x, wp) as dcv_conv does for a single output channel (bf16, packed DCV_IMPL_TC weight),
+ * then - in the same launch, by the block that finishes last - loss_out[0] (+)= mean loss(kind) over all logits and, if dy is
+ * not NULL, dy = grad_scale * dL/dlogit.  Same numbers as dcv_conv followed by dcv_loss_fwd_bwd.  counter: one zero-initialised
+ * uint32 the kernel leaves zero again (dcv_bn_tail_counters() buffers qualify). */
+int dcv_head_loss_supported(const dcv_geom* g, int dir);
+int dcv_head_loss(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, int kind,
+                  float* loss_out, int accumulate, void* dy, int64_t lddy, float grad_scale, void* counter, void* stream);
 /* same question for DCV_IMPL_TC_TF32 (fp32 activations and packed weights, tf32 products, fp32 accumulation and output) */
 int dcv_conv_tf32_supported(const dcv_geom* g, int dir);
 int dcv_conv(const dcv_geom* g, int dir, int impl, int dtype, const void* x, int64_t ldx,
