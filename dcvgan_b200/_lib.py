@@ -61,6 +61,7 @@ SIGNATURES = {
     "dcv_head_loss_supported": (_i, [_G, _i]),
     "dcv_head_loss": (_i, [_G, _i, _vp, _i64, _vp, _vp, _i64, _i, _vp, _i, _vp, _i64, _f, _vp, _vp]),
     "dcv_conv": (_i, [_G, _i, _i, _i, _vp, _i64, _vp, _vp, _i64, _i, _f, _vp]),
+    "dcv_conv_accumulate": (_i, [_G, _i, _vp, _i64, _vp, _vp, _i64, _vp]),
     "dcv_conv_stats_slots": (_i, [_G, _i, _i64, _i64]),
     "dcv_conv_stats": (_i, [_G, _i, _vp, _i64, _vp, _vp, _i64, _i, _f, _vp, _i, _vp]),
     "dcv_wgrad_workspace_bytes": (_i64, [_G, _i]),

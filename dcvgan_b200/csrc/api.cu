@@ -56,7 +56,7 @@ int conv_tf32_supported(const dcv_geom*, int);
 int head_loss_supported(const dcv_geom*, int);
 int head_loss(const dcv_geom*, int, const void*, int64_t, const void*, void*, int64_t, int, float*, int, void*, int64_t, float, unsigned*, cudaStream_t);
 int pack_weight_tc(const dcv_geom*, int, const float*, int64_t, int64_t, int64_t, WeightWin, void*, cudaStream_t, int);
-int conv_tc(const dcv_geom*, int, const void*, int64_t, const void*, void*, int64_t, int, float, float*, int*, cudaStream_t, int);
+int conv_tc(const dcv_geom*, int, const void*, int64_t, const void*, void*, int64_t, int, float, float*, int*, cudaStream_t, int, int);
 int wgrad_tc_supported(const dcv_geom*);
 int64_t wgrad_tc_ws_bytes(const dcv_geom*);
 int wgrad_tc(const dcv_geom*, const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int64_t, int, void*,
@@ -193,13 +193,20 @@ int dcv_conv(const dcv_geom* g, int dir, int impl, int dtype, const void* x, int
   if (g->N == 0) return 0;
   if (impl == DCV_IMPL_TC) {
     DCV_REQUIRE(dtype == DCV_BF16, "conv: DCV_IMPL_TC computes in bf16 (DCV_IMPL_TC_TF32 takes fp32 tensors)");
-    return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, nullptr, nullptr, as_stream(stream), 0);
+    return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, nullptr, nullptr, as_stream(stream), 0, 0);
   }
   if (impl == DCV_IMPL_TC_TF32) {
     DCV_REQUIRE(dtype == DCV_F32, "conv: DCV_IMPL_TC_TF32 takes fp32 tensors");
-    return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, nullptr, nullptr, as_stream(stream), 1);
+    return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, nullptr, nullptr, as_stream(stream), 1, 0);
   }
   return conv_simt(g, dir, dtype, x, ldx, wp, y, ldy, act, slope, as_stream(stream));
+}
+
+int dcv_conv_accumulate(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DCV_REQUIRE(x && wp && y, "conv_accumulate: null pointer");
+  if (g->N == 0) return 0;
+  return conv_tc(g, dir, x, ldx, wp, y, ldy, DCV_ACT_NONE, 0.f, nullptr, nullptr, as_stream(stream), 0, 1);
 }
 
 int dcv_conv_stats_slots(const dcv_geom* g, int dir, int64_t ldx, int64_t ldy) {
@@ -207,7 +214,7 @@ int dcv_conv_stats_slots(const dcv_geom* g, int dir, int64_t ldx, int64_t ldy) {
   if (g->N == 0 || !conv_tc_supported(g, dir)) return 0;
   int slots = 0;
   // planning query: aligned dummy pointers, nothing is dereferenced or launched
-  if (conv_tc(g, dir, (const void*)16, ldx, nullptr, (void*)16, ldy, 0, 0.f, nullptr, &slots, nullptr, 0)) return -1;
+  if (conv_tc(g, dir, (const void*)16, ldx, nullptr, (void*)16, ldy, 0, 0.f, nullptr, &slots, nullptr, 0, 0)) return -1;
   return slots;
 }
 
@@ -219,7 +226,7 @@ int dcv_conv_stats(const dcv_geom* g, int dir, const void* x, int64_t ldx, const
   DCV_REQUIRE(((uintptr_t)y & 15) == 0, "conv_stats: output must be 16-byte aligned");
   const int want = dcv_conv_stats_slots(g, dir, ldx, ldy);
   DCV_REQUIRE(want > 0 && want == slots, "conv_stats: this geometry writes %d statistic slots, caller provided %d", want, slots);
-  return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, stats, nullptr, as_stream(stream), 0);
+  return conv_tc(g, dir, x, ldx, wp, y, ldy, act, slope, stats, nullptr, as_stream(stream), 0, 0);
 }
 
 int64_t dcv_wgrad_workspace_bytes(const dcv_geom* g, int impl) {

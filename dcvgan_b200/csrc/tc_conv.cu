@@ -93,6 +93,12 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
       "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
       ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
+// same box, but the destination is read-modify-written: dst += src (bf16 / fp32 add performed at L2, element type from the map)
+__device__ __forceinline__ void tma_reduce_add_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -249,6 +255,7 @@ struct TcConvP {
   int a_bytes, b_bytes, tx_bytes;
   int64_t ldy;
   int act; float slope;
+  int accumulate;                        // epilogue adds into the output (TMA reduce-add) instead of overwriting it
   int vec_ok;
   int tmem_cols;
   int ntn, items, acc_cols;              // persistent kernel: N tiles, work items, TMEM columns of one accumulator set
@@ -666,8 +673,10 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_5d(&mapY, buf, nbase + cb, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
-                           (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
+              if (p.accumulate) tma_reduce_add_5d(&mapY, buf, nbase + cb, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
+                                                  (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
+              else tma_store_5d(&mapY, buf, nbase + cb, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
+                                (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
               tma_store_commit();
             }
             ++nstore;
@@ -709,8 +718,10 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           fence_async_smem();
           __syncwarp();
           if (lane == 0 && !(TC_DBG(p) & 4)) {
-            tma_store_5d(&mapY, buf, nbase, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
-                         (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
+            if (p.accumulate) tma_reduce_add_5d(&mapY, buf, nbase, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
+                                                (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
+            else tma_store_5d(&mapY, buf, nbase, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
+                              (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
             tma_store_commit();
           }
           ++nstore;
@@ -773,8 +784,10 @@ conv_tc_pers_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               }
             }
             if (lane == 0 && !(TC_DBG(p) & 4)) {
-              tma_store_5d(&mapY, buf, nbase + cb, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
-                           (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
+              if (p.accumulate) tma_reduce_add_5d(&mapY, buf, nbase + cb, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
+                                                  (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
+              else tma_store_5d(&mapY, buf, nbase + cb, (tc.w0 + sub_w) * f.osw + f.rw, (tc.h0 + sub_h) * f.osh + f.rh,
+                                (tc.t0 + sub_t) * f.ost + f.rt, tc.n0 + m * p.bn + sub_n);
               tma_store_commit();
             }
             ++nstore;
@@ -1414,8 +1427,9 @@ int conv_tf32_supported(const dcv_geom* g, int dir) {
 }
 
 // tf32 != 0: fp32 activations / packed weights / output, kind::tf32 MMAs (x, wp, y are float buffers, ldx / ldy in floats)
+// accumulate != 0: y += result (TMA reduce-add epilogue; needs the TMA-store path, fails otherwise)
 int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, int act,
-            float slope, float* stats, int* slots_out, cudaStream_t s, int tf32) {
+            float slope, float* stats, int* slots_out, cudaStream_t s, int tf32, int accumulate) {
   if (slots_out) *slots_out = 0;
   DCV_REQUIRE(conv_tc_supported(g, dir), "conv_tc: geometry not supported by the tcgen05 kernel");
   DCV_REQUIRE(!tf32 || (conv_tf32_supported(g, dir) && !stats && !slots_out), "conv_tc: geometry not supported by the tf32 variant");
@@ -1423,7 +1437,7 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   TcConvP p;
   p.c = make_convp(g, dir);
   const ConvP& c = p.c;
-  if (!tf32 && !c.scatter && c.wN == 1 && c.Kc % 8 == 0 && (ldx % 8) == 0 && (((uintptr_t)x) & 15) == 0 && !g_tune.no_gemv) {
+  if (!tf32 && !accumulate && !c.scatter && c.wN == 1 && c.Kc % 8 == 0 && (ldx % 8) == 0 && (((uintptr_t)x) & 15) == 0 && !g_tune.no_gemv) {
     if (slots_out) return 0;
     DCV_REQUIRE(!stats, "conv_tc: fused statistics are not available for the single-channel head kernel");
     const int64_t M = (int64_t)c.N * c.Ot * c.Oh * c.Ow;          // one warp per logit
@@ -1537,6 +1551,8 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     if (slots_out) { *slots_out = can_stats ? 4 * grid_p : 0; return 0; }
     DCV_REQUIRE(!stats || can_stats, "conv_tc: fused statistics need the TMA-store epilogue (output channels %% 64 == 0)");
     p.stats = stats; p.npad = npad;
+    p.accumulate = accumulate;
+    DCV_REQUIRE(!accumulate || (p.tma_store && !stats && act == DCV_ACT_NONE), "conv_tc: accumulating into the output needs the TMA-store epilogue, no activation and no fused statistics");
     rc = make_act_map(&mapA, x, c.Kc, c.Iw, c.Ih, c.It, c.N, ldx, p.cblk, p.bw, p.bh + p.hg - 1, p.bt, p.bn * p.mt, f0.mulw, f0.mulh, f0.mult, swz, esz);
     if (rc) return rc;
     rc = g4 ? make_weight_map(&mapB, wp, Kph, npad, phases, 64, p.bnt, CU_TENSOR_MAP_SWIZZLE_128B)

@@ -280,8 +280,10 @@ class Block:
         ops.conv(g1, spec1.fwd_dir, impl1, x.padded_to(x.cp), wp, P.padded_to(P.cp))
         ops.col2im_act(P, out, spec.cout, spec.k[1], spec.k[2], spec.s[1], spec.p[1], self.act, self.slope)
 
-    def backward(self, ctx, da, sink, dx_out=None, need_dw=True):
-        """da: gradient w.r.t. the block output (Act, may be a slice).  dx_out: Act receiving dL/dx or None."""
+    def backward(self, ctx, da, sink, dx_out=None, need_dw=True, dx_accumulate=False):
+        """da: gradient w.r.t. the block output (Act, may be a slice).  dx_out: Act receiving dL/dx or None.
+        dx_accumulate: dx_out already holds a gradient (a U-Net skip connection's) and dL/dx is ADDED to it - by the
+        convolution's own epilogue (TMA reduce-add) when the tcgen05 path allows, else through a temporary and an add."""
         spec, g = self.spec, ctx["g"]
         a = ctx["a"]
         if ctx.get("img"):       # activation derivative, weight gradient and data gradient in one pass over (da, a)
@@ -324,7 +326,15 @@ class Block:
             else:
                 impl = ops.choose_conv_impl(g, spec.bwd_dir, dzp)
                 wp = packed_weight(spec, g, spec.bwd_dir, impl, self.conv.weight)
-                ops.conv(g, spec.bwd_dir, impl, dzp, wp, dx_out.padded_to(cin_p))
+                dxp = dx_out.padded_to(cin_p)
+                if not dx_accumulate:
+                    ops.conv(g, spec.bwd_dir, impl, dzp, wp, dxp)
+                elif ops.conv_accumulate_ok(g, spec.bwd_dir, impl, dzp, dxp):
+                    ops.conv_accumulate(g, spec.bwd_dir, dzp, wp, dxp)
+                else:
+                    tmp = Act.empty(dx_out.n, dx_out.t, dx_out.h, dx_out.w, dx_out.c, dx_out.dtype)
+                    ops.conv(g, spec.bwd_dir, impl, dzp, wp, tmp.padded_to(cin_p))
+                    ops.axpy(tmp, dx_out, True)
         return dz
 
 
@@ -570,12 +580,13 @@ class CGenPlan:
             self.up[i].backward(ctx["up"][i], dcats[i + 1].ch(0, first[i + 1]), sink, dx_out=dcats[i])
         da = dcats[0].ch(0, first[0])
         for i in range(5, -1, -1):
-            xin = ctx["down"][i]["x"]
-            dx = Act.empty(xin.n, xin.t, xin.h, xin.w, xin.c, xin.dtype)
-            self.down[i].backward(ctx["down"][i], da, sink, dx_out=dx)
-            k = 5 - i + 1 if i > 0 else 6                                        # concat buffer holding this skip tensor
-            ops.axpy(dcats[k].ch(first[k], dcats[k].c), dx, True)
-            da = dx
+            # the input of down block i is the skip tensor in the second half of concat buffer k: its gradient from the up path
+            # is already there, and the block's data gradient is added on top of it (generator.py:398-400) - by the
+            # convolution epilogue itself (TMA reduce-add), no separate a + b pass over the tensor
+            k = 5 - i + 1 if i > 0 else 6
+            skip = dcats[k].ch(first[k], dcats[k].c)
+            self.down[i].backward(ctx["down"][i], da, sink, dx_out=skip, dx_accumulate=True)
+            da = skip
         dx = None
         if need_dx and self.mod.geometric_info != "segmentation":                # argmax/scatter blocks the gradient
             xin = ctx["inconv"]["x"]

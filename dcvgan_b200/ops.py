@@ -351,10 +351,27 @@ def head_loss(g, direction, x, wp, y, kind, loss_out, accumulate, want_grad, gra
     cnt = _HEAD_COUNTER.get(x.device)
     if cnt is None:
         cnt = _HEAD_COUNTER[x.device] = torch.zeros(4, dtype=torch.int32, device=x.device)
-    dy = Act.empty(y.n, y.t, y.h, y.w, y.c, y.dtype) if want_grad else None
+    # ONE real channel in a zero-filled 16-channel pitch: the head's backward reads the padded width
+    dy = Act.empty(y.n, y.t, y.h, y.w, 1, y.dtype) if want_grad else None
     check(lib().dcv_head_loss(C.byref(g), direction, x.ptr, x.ld, wp.data_ptr(), y.ptr, y.ld, kind, loss_out.data_ptr(), int(accumulate),
                               None if dy is None else dy.ptr, 1 if dy is None else dy.ld, grad_scale, cnt.data_ptr(), _stream()))
     return dy
+
+
+CONV_ACCUMULATE = os.environ.get("DCV_NO_CONV_ACCUMULATE", "0") != "1"
+
+
+def conv_accumulate_ok(g, direction, impl, x, y):
+    """the tcgen05 convolution can add its result into y (TMA reduce-add epilogue): bf16, aligned, >= 16 output channels"""
+    return (CONV_ACCUMULATE and impl == IMPL_TC and y.dtype == torch.bfloat16 and y.ptr % 16 == 0 and y.ld % 8 == 0 and y.c % 16 == 0
+            and x.dtype == torch.bfloat16)
+
+
+def conv_accumulate(g, direction, x, wp, y):
+    """y += correlate(x, wp)"""
+    if TRACE is not None:
+        TRACE.append(("conv", g.key(), direction, IMPL_TC, x.ld, y.ld, x.c, y.c))
+    check(lib().dcv_conv_accumulate(C.byref(g), direction, x.ptr, x.ld, wp.data_ptr(), y.ptr, y.ld, _stream()))
 
 
 def conv_stats_slots(g, direction, x, y):

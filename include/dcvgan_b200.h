@@ -139,6 +139,10 @@ int dcv_conv(const dcv_geom* g, int dir, int impl, int dtype, const void* x, int
  * dcv_conv_stats writes for this geometry and these pixel strides - 0 if the statistics cannot be fused (output channels
  * not a multiple of 64, CUDA-core path, ...), in which case the caller runs dcv_conv + dcv_bn_stats.  The slots have the
  * layout dcv_bn_finalize expects (nblk = slots, C = Cout_padded).  tcgen05 / bf16 only. */
+/* y += correlate(x, wp) for DCV_IMPL_TC / bf16: the epilogue adds into the output with TMA reduce-add instead of overwriting it
+ * (gradient fan-in of the U-Net skip connections, generator.py:398-400: the data gradient of a down block lands directly on top
+ * of the skip gradient, no separate a + b pass).  Needs a 16-byte aligned output whose channel count is a multiple of 16. */
+int dcv_conv_accumulate(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, void* stream);
 int dcv_conv_stats_slots(const dcv_geom* g, int dir, int64_t ldx, int64_t ldy);
 int dcv_conv_stats(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* wp, void* y, int64_t ldy, int act,
                    float slope, float* stats, int slots, void* stream);
