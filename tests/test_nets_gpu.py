@@ -89,11 +89,18 @@ def test_generators_match_oracle(precision, ftol, ctol, geo):
     assert xg.shape == xg_ref.shape and xc.shape == xc_ref.shape and xg.stride() == xg_ref.stride()
     e_g, e_c = rel_err(xg.detach().cpu(), xg_ref.detach()), rel_err(xc.detach().cpu(), xc_ref.detach())
     ((xc * d_xc.cuda()).sum() + (xg * d_xg.cuda()).sum()).backward()
-    worst = 1.0
+    worst, worst_k, nets = 1.0, None, {}
     for net in ("ggen", "cgen"):
+        mine, ref = [], []
         for k, p in models[net].named_parameters():
-            worst = min(worst, cos_sim(p.grad.cpu(), Pr[net][k].grad))
-    print(f"generators[{precision},{geo[0]}]: xg {e_g:.2e} xc {e_c:.2e} worst grad cos {worst:.5f}")
+            c = cos_sim(p.grad.cpu(), Pr[net][k].grad)
+            if c < worst:
+                worst, worst_k = c, (net, k)
+            mine.append(p.grad.cpu().flatten().double())
+            ref.append(Pr[net][k].grad.flatten().double())
+        a, b = torch.cat(mine), torch.cat(ref)
+        nets[net] = float((a @ b) / (a.norm() * b.norm()))
+    print(f"generators[{precision},{geo[0]}]: xg {e_g:.2e} xc {e_c:.2e} worst per-tensor grad cos {worst:.5f} at {worst_k}; per-network {nets}")
     if precision == "bf16":
         # bf16 storage at batch 2 / width 8: BatchNorm over 32 samples at the 1x1 bottleneck amplifies rounding, and the
         # segmentation argmax flips on near-ties; the bf16 gate of the north star is the loss curve (test_curves_gpu.py).

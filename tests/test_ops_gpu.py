@@ -339,6 +339,69 @@ def test_img_conv_outconv_backward(n, hw):
     assert e_fwd < 5e-3 and e_dx < 5e-3 and e_dw < 5e-3 and e_dw2 < 5e-3
 
 
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 4])
+def test_head_with_fused_loss_term(kind):
+    """dcv_head_loss (discriminator head + its adversarial-loss term + dL/dlogits in one launch) against the two-launch form
+    dcv_conv + dcv_loss_fwd_bwd: identical logits, loss and gradient (same bf16 logits, same summation order); first call
+    writes the loss, second accumulates."""
+    ops = _ops()
+    from dcvgan_b200._lib import IMPL_TC
+    torch.manual_seed(70 + kind)
+    spec = ops.ConvSpec("conv", 256, 1, (4, 4, 4), (1, 2, 2), (0, 1, 1))
+    n, sp = 6, (7, 8, 8)
+    x = to_act(bf16_round(torch.randn(n, 256, *sp)), torch.bfloat16)
+    w = (torch.randn(1, 256, 4, 4, 4) * 0.02).cuda()
+    out_sp = spec.out_spatial(sp)
+    y0 = ops.Act.empty(n, *out_sp, 1, torch.bfloat16)
+    y1 = ops.Act.empty(n, *out_sp, 1, torch.bfloat16)
+    g = spec.geom(n, sp, x.cp, y0.cp)
+    wp = ops.pack_weight(spec, g, spec.fwd_dir, IMPL_TC, w)
+    assert ops.head_loss_ok(g, spec.fwd_dir, IMPL_TC, x)
+    # reference: two launches
+    ops.conv(g, spec.fwd_dir, IMPL_TC, x, wp, y0.padded_to(y0.cp))
+    loss0 = torch.zeros(1, device="cuda")
+    dy0 = ops.Act.empty(n, *out_sp, 1, torch.bfloat16)
+    ops.loss_fwd_bwd_act(y0, kind, loss0, False, dy0, 1.0)
+    ops.loss_fwd_bwd_act(y0, kind, loss0, True, None, 1.0)
+    # fused
+    loss1 = torch.zeros(1, device="cuda")
+    dy1 = ops.head_loss(g, spec.fwd_dir, x, wp, y1.padded_to(y1.cp), kind, loss1, False, True)
+    assert ops.head_loss(g, spec.fwd_dir, x, wp, y1.padded_to(y1.cp), kind, loss1, True, False) is None
+    torch.cuda.synchronize()
+    assert torch.equal(from_act(y1), from_act(y0))
+    assert torch.equal(from_act(dy1), from_act(dy0))
+    assert float(dy1.padded_to(dy1.cp).torch()[..., 1:].float().abs().max()) == 0.0      # padding channels of dL/dlogits are zero
+    assert abs(float(loss1) - float(loss0)) <= 1e-6 * max(1.0, abs(float(loss0))), (float(loss1), float(loss0))
+
+
+def test_conv_accumulate_into_output():
+    """dcv_conv_accumulate (TMA reduce-add epilogue): y += dgrad(x) equals the separate convolution followed by an add, for a
+    strided data gradient (sub-pixel scatter) written into a channel slice of a wider buffer (the U-Net skip-gradient case)."""
+    ops = _ops()
+    from dcvgan_b200._lib import IMPL_TC
+    torch.manual_seed(81)
+    spec = ops.ConvSpec("conv", 64, 128, (1, 4, 4), (1, 2, 2), (0, 1, 1))
+    n, sp = 5, (1, 32, 32)
+    w = (torch.randn(128, 64, 4, 4) * 0.05).cuda()
+    dz = to_act(bf16_round(torch.randn(n, 128, 16, 16)), torch.bfloat16)
+    g = spec.geom(n, sp)
+    wpb = ops.pack_weight(spec, g, spec.bwd_dir, IMPL_TC, w)
+    base = bf16_round(torch.randn(n, 128, 32, 32))
+    buf0, buf1 = to_act(base, torch.bfloat16), to_act(base, torch.bfloat16)
+    skip0, skip1 = buf0.ch(64, 128), buf1.ch(64, 128)
+    tmp = ops.Act.empty(n, 1, 32, 32, 64, torch.bfloat16)
+    ops.conv(g, spec.bwd_dir, IMPL_TC, dz, wpb, tmp)
+    ops.axpy(tmp, skip0, True)
+    assert ops.conv_accumulate_ok(g, spec.bwd_dir, IMPL_TC, dz, skip1)
+    ops.conv_accumulate(g, spec.bwd_dir, dz, wpb, skip1)
+    torch.cuda.synchronize()
+    a, b = from_act(buf1), from_act(buf0)
+    assert torch.equal(a[:, :64], b[:, :64])                                        # the other half of the buffer is untouched
+    e = rel_err(a[:, 64:], b[:, 64:])
+    print(f"conv_accumulate vs conv + add: {e:.2e}")
+    assert e < 2e-3          # one bf16 rounding of the partial result before the add instead of fp32 -> bf16 after it
+
+
 def test_conv_channel_slices():
     """input read from / output written into channel slices of wider buffers (concat elimination)"""
     ops = _ops()

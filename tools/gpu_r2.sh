@@ -37,6 +37,12 @@ for st in $STAGES; do
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_pers|wgrad_tc" -c 10 -o gpurun_out/${TAG}_top python tools/probe_layers.py vdis_main1_dgrad up5_fwd vdis_main1_fwd vdis_main1_wgrad down0_wgrad > gpurun_out/${TAG}_ncutop.log 2>&1; echo "ncutop rc=$?" | tee -a gpurun_out/${TAG}_rc.log; cat gpurun_out/${TAG}_probe_layers.log;;
     tf32)
       timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_nets_gpu.py -m gpu -q -s -k "tf32 or full_width" > gpurun_out/${TAG}_tf32.log 2>&1; echo "tf32 rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -v "^DEBUG\|^INFO" gpurun_out/${TAG}_tf32.log | grep "tf32\|passed\|failed\|Error\|error" | tail -30;;
+    sanitize)
+      # memcheck + racecheck over the kernels added this round (image-side mma.sync kernels, in-kernel BatchNorm finalize, head + loss,
+      # transposing reduction, TMA reduce-add): small shapes, a few tests each
+      for tool in memcheck racecheck; do
+        timeout 1200 compute-sanitizer --tool $tool --error-exitcode 99 python -m pytest tests/test_ops_gpu.py -m gpu -q -x -k "img_conv or outconv or batchnorm or losses or head_with or accumulate or tc_conv2d_64 or tc_convT_128_64" > gpurun_out/${TAG}_sanitize_${tool}.log 2>&1; echo "sanitize $tool rc=$?" | tee -a gpurun_out/${TAG}_rc.log; grep -c "ERROR SUMMARY\|Error\|RACECHECK" gpurun_out/${TAG}_sanitize_${tool}.log; tail -4 gpurun_out/${TAG}_sanitize_${tool}.log
+      done;;
     bench)
       timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${TAG}_rc.log; tail -c 3000 gpurun_out/${TAG}_bench.json;;
     benchfast)
