@@ -32,13 +32,13 @@ namespace dcv {
 // Result-preserving tuning switches (row-halo sharing off, forced M-tile count, direct-store epilogue, extra wgrad split
 // waves ...) are explicit process state set through dcv_set_tuning(), never read from the environment; the parity tests
 // flip them to cover every code path of the kernels (tests/test_ops_gpu.py::test_conv_tcgen05_kernel_variants).
-struct Tuning { int nohalo, mt, no_tma_store, no_narrow_tma_store, wgrad_waves, no_gemv, no_tapgroup, no_fused_stats, sm_reserve, pdl; };
-static Tuning g_tune = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+struct Tuning { int nohalo, mt, no_tma_store, no_narrow_tma_store, wgrad_waves, no_gemv, no_tapgroup, no_fused_stats, sm_reserve, pdl, no_nsplit; };
+static Tuning g_tune = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 int set_tuning(const char* key, int value) {
   struct { const char* k; int* v; } tab[] = {{"nohalo", &g_tune.nohalo}, {"mt", &g_tune.mt}, {"no_tma_store", &g_tune.no_tma_store},
       {"no_narrow_tma_store", &g_tune.no_narrow_tma_store}, {"wgrad_waves", &g_tune.wgrad_waves}, {"no_gemv", &g_tune.no_gemv},
       {"no_tapgroup", &g_tune.no_tapgroup}, {"no_fused_stats", &g_tune.no_fused_stats}, {"sm_reserve", &g_tune.sm_reserve},
-      {"pdl", &g_tune.pdl}};
+      {"pdl", &g_tune.pdl}, {"no_nsplit", &g_tune.no_nsplit}};
   for (auto& t : tab) if (!strcmp(t.k, key)) { *t.v = value; return 0; }
   DCV_REQUIRE(false, "dcv_set_tuning: unknown key '%s'", key);
 }
@@ -1321,8 +1321,8 @@ static void choose_box(int target, int Qw, int Qh, int Qt, int N, int* bw, int* 
 }
 
 int tc_npad(int Nc) { return (Nc + 15) / 16 * 16; }
-static int tc_bnt(int npad) {
-  for (int b = 256; b >= 16; b -= 16) if (npad % b == 0) return b;
+static int tc_bnt(int npad, int cap = 256) {
+  for (int b = cap; b >= 16; b -= 16) if (npad % b == 0) return b;
   return 16;
 }
 
@@ -1447,13 +1447,15 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
   }
   const int phases = c.scatter ? g->st * g->sh * g->sw : 1;
   const PhaseInfo f0 = make_phase(c, 0);
+  int bnt_cap = 256;
+replan:
   choose_box(128, f0.Qw, f0.Qh, f0.Qt, c.N, &p.bw, &p.bh, &p.bt, &p.bn);
   p.tiles_w = ceil_div(f0.Qw, p.bw); p.tiles_h = ceil_div(f0.Qh, p.bh); p.tiles_t = ceil_div(f0.Qt, p.bt);
   p.tiles_n = ceil_div(c.N, p.bn);
   p.cblk = tf32 ? 32 : (c.Kc % 64 == 0 ? 64 : (c.Kc % 32 == 0 ? 32 : 16));   // 128-byte rows whenever the channel count allows
   p.kchunks = c.Kc / p.cblk;
   const int npad = tc_npad(c.Nc);
-  p.bnt = tc_bnt(npad);
+  p.bnt = tc_bnt(npad, bnt_cap);
   const int row_bytes = p.cblk * esz;
   p.swz_layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
   const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -1536,6 +1538,9 @@ int conv_tc(const dcv_geom* g, int dir, const void* x, int64_t ldx, const void* 
     }
     p.tiles_n = ceil_div(c.N, p.bn * p.mt);
     p.items = (int)(sp_tiles * p.tiles_n);
+    // Few work items (the deep 1x1 .. 4x4 layers: 4-32 items, each a K loop of 4096-8192 fed at ONE SM's L2 bandwidth): a
+    // narrower N tile spreads the same work over 2-4x as many SMs; the A tile is then fetched by more CTAs, from L2.
+    if (!g4 && !g_tune.no_nsplit && p.items * 2 <= num_sms && p.bnt % 128 == 0) { bnt_cap = p.bnt / 2; goto replan; }
     p.a_bytes = a_bytes_of(p.mt);
     p.tx_bytes = p.a_bytes + p.hg * p.bnt * p.cblk * esz;
     p.acc_cols = p.mt * p.bnt;
