@@ -32,13 +32,13 @@ namespace dcv {
 // Result-preserving tuning switches (row-halo sharing off, forced M-tile count, direct-store epilogue, extra wgrad split
 // waves ...) are explicit process state set through dcv_set_tuning(), never read from the environment; the parity tests
 // flip them to cover every code path of the kernels (tests/test_ops_gpu.py::test_conv_tcgen05_kernel_variants).
-struct Tuning { int nohalo, mt, no_tma_store, no_narrow_tma_store, wgrad_waves, no_gemv, no_tapgroup, no_fused_stats, sm_reserve, pdl, no_nsplit; };
-static Tuning g_tune = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+struct Tuning { int nohalo, mt, no_tma_store, no_narrow_tma_store, wgrad_waves, no_gemv, no_tapgroup, no_fused_stats, sm_reserve, pdl, no_nsplit, no_wgrad_halo; };
+static Tuning g_tune = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 int set_tuning(const char* key, int value) {
   struct { const char* k; int* v; } tab[] = {{"nohalo", &g_tune.nohalo}, {"mt", &g_tune.mt}, {"no_tma_store", &g_tune.no_tma_store},
       {"no_narrow_tma_store", &g_tune.no_narrow_tma_store}, {"wgrad_waves", &g_tune.wgrad_waves}, {"no_gemv", &g_tune.no_gemv},
       {"no_tapgroup", &g_tune.no_tapgroup}, {"no_fused_stats", &g_tune.no_fused_stats}, {"sm_reserve", &g_tune.sm_reserve},
-      {"pdl", &g_tune.pdl}, {"no_nsplit", &g_tune.no_nsplit}};
+      {"pdl", &g_tune.pdl}, {"no_nsplit", &g_tune.no_nsplit}, {"no_wgrad_halo", &g_tune.no_wgrad_halo}};
   for (auto& t : tab) if (!strcmp(t.k, key)) { *t.v = value; return 0; }
   DCV_REQUIRE(false, "dcv_set_tuning: unknown key '%s'", key);
 }
@@ -194,26 +194,30 @@ __device__ __forceinline__ void conv_issue_stage(uint32_t tmem_d, uint32_t alo, 
 }
 
 // one pixel stage of wgrad_tc for one accumulator tile: KS steps of 16 pixels
+// slabA16 / slab_shift: row-halo mode - the A box holds one extra tile row per (t, n) slab of slab = 1 << slab_shift pixels
 template <int KS>
 __device__ __forceinline__ void wgrad_issue(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
-                                            uint32_t kstepA16, uint32_t kstepB16, uint32_t idesc, uint32_t accum) {
+                                            uint32_t kstepA16, uint32_t kstepB16, uint32_t idesc, uint32_t accum,
+                                            uint32_t slabA16, int slab_shift) {
 #pragma unroll
   for (int k = 0; k < KS; ++k)
-    umma_lohi(tmem_d, alo + k * kstepA16, ahi, blo + k * kstepB16, bhi, idesc, k == 0 ? accum : 1u);
+    umma_lohi(tmem_d, alo + k * kstepA16 + (uint32_t)((k * 16) >> slab_shift) * slabA16, ahi, blo + k * kstepB16, bhi, idesc,
+              k == 0 ? accum : 1u);
 }
 
 template <int KS, int G>
 __device__ __forceinline__ void wgrad_mma_loop(uint64_t* full_bar, uint64_t* empty_bar, int nst, int stages, uint32_t stage16,
                                                uint32_t lo_a0, uint32_t lo_b0, uint32_t ahi, uint32_t bhi, uint32_t kstepA16,
                                                uint32_t kstepB16, uint32_t tileA16, uint32_t tmem_base, uint32_t Ns, uint32_t idesc,
-                                               bool leader) {
+                                               bool leader, uint32_t slabA16, int slab_shift) {
   int stage = 0; uint32_t phase = 0, accum = 0, alo = lo_a0, blo = lo_b0;
   for (int it = 0; it < nst; ++it) {
     mbar_wait(&full_bar[stage], phase);
     tc_fence_after();
     if (leader) {
 #pragma unroll
-      for (int gi = 0; gi < G; ++gi) wgrad_issue<KS>(tmem_base + gi * Ns, alo + gi * tileA16, ahi, blo, bhi, kstepA16, kstepB16, idesc, accum);
+      for (int gi = 0; gi < G; ++gi)
+        wgrad_issue<KS>(tmem_base + gi * Ns, alo + gi * tileA16, ahi, blo, bhi, kstepA16, kstepB16, idesc, accum, slabA16, slab_shift);
       umma_commit(&empty_bar[stage]);
     }
     accum = 1;
@@ -998,7 +1002,21 @@ struct TcWgradP {
   int G, Ns, stages, tmem_cols;
   int layA, layB;                        // UMMA layout codes
   int dbg;                               // DCV_TC_DBG & 3: stop issuing TMA loads after the first ring fill (timing experiments)
+  // Row-halo sharing (k = 4, stride 2 along h, 64-channel blocks): the taps kh and kh + 2 read the same stride-2 row lattice of
+  // L, one tile row apart.  A 128-row accumulator tile is then the PAIR (kh, kh + 2) of one (kt, kh % 2, kw, channel chunk),
+  // both halves served by ONE box with a halo row - the second half's descriptor starts bw pixels (a multiple of the 1024-byte
+  // swizzle atom) further down - so a stage carries (bh + 1) / (2 bh) of the per-tap boxes.
+  int halo;                              // 1: tiles are (kh, kh + 2) pairs over a shared halo box
+  int boxA_bytes;                        // bytes of one halo box: slabs * (bh + 1) * bw pixels * 128
+  int slab_shift;                        // log2(bw * bh): pixels of one (t, n) slab of the tile
 };
+
+// halo mode: tile index -> (kt, kh class, kw, channel chunk); the tile's row block d (0 / 1) is the tap kh = class + 2 d
+__device__ __forceinline__ void wgrad_halo_tile(const dcv_geom& g, int clchunks, int tile, int& ta, int& cls, int& tc, int& clc) {
+  clc = tile % clchunks; tile /= clchunks;
+  tc = tile % g.kw; tile /= g.kw;
+  cls = tile % 2; ta = tile / 2;
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapS, const TcWgradP p,
@@ -1022,9 +1040,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int blkA_bytes = p.pix * p.cbA * 2;
   const int blkB_bytes = p.pix * p.cbB * 2;
-  const int stage_bytes = blkB_bytes * p.nbB + blkA_bytes * p.nA * p.G;
+  const int tileA_bytes = p.halo ? p.boxA_bytes : blkA_bytes * p.nA;      // shared memory of one accumulator tile's A operand
+  const int stage_bytes = blkB_bytes * p.nbB + tileA_bytes * p.G;
   int blocksA_here = p.blocksA_total - tile0 * p.nA;        // valid A blocks of this CTA
   if (blocksA_here > Gcur * p.nA) blocksA_here = Gcur * p.nA;
+  const int loadsA = p.halo ? Gcur : blocksA_here;          // TMA boxes per stage for A
+  const int bytesA = p.halo ? Gcur * p.boxA_bytes : blkA_bytes * blocksA_here;
 
   if (warp == 0 && lane == 0) { tmap_prefetch(&mapL); tmap_prefetch(&mapS); }
   if (warp == 1) {
@@ -1053,7 +1074,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     // tap coordinates with ~10 integer divisions per lane per stage: the MMA warp then waited on this warp for 58 % of
     // the kernel, profiles/r1j_ncu_full_summary.md.)
     int stage = 0; uint32_t phase = 0;
-    const int nloads = nbB + blocksA_here;
+    const int nloads = nbB + loadsA;
     int l_isB[2], l_c[2], l_dw[2], l_dh[2], l_dt[2]; uint32_t l_off[2]; bool l_on[2];
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) {
@@ -1064,6 +1085,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
       if (!l_on[sl]) continue;
       if (l_isB[sl]) {
         l_c[sl] = (bB0 + i) * p.cbB; l_off[sl] = (uint32_t)(i * blkB_bytes);
+      } else if (p.halo) {
+        const int b = i - nbB;
+        int ta, cls, tc, clc;
+        wgrad_halo_tile(g, p.clchunks, tile0 + b, ta, cls, tc, clc);
+        l_c[sl] = clc * p.cbA; l_dw[sl] = tc - g.pw; l_dh[sl] = cls - g.ph; l_dt[sl] = ta - g.pt;
+        l_off[sl] = (uint32_t)(p.nbB * blkB_bytes + b * p.boxA_bytes);
       } else {
         const int b = i - nbB;
         const int blk = tile0 * p.nA + b;
@@ -1084,7 +1111,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     for (int64_t pt = pt_begin; pt < pt_end; ++pt) {
       mbar_wait(&empty_bar[stage], phase ^ 1u);
       const bool skip = (TC_DBG(p) & 3) && (pt - pt_begin) >= p.stages;
-      if (lane == 0) mbar_expect_tx(&full_bar[stage], skip ? 0u : (uint32_t)(blkB_bytes * nbB + blkA_bytes * blocksA_here));
+      if (lane == 0) mbar_expect_tx(&full_bar[stage], skip ? 0u : (uint32_t)(blkB_bytes * nbB + bytesA));
       __syncwarp();
       const uint32_t s_dst = sbase + stage * stage_bytes;
       if (!skip) {
@@ -1107,14 +1134,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     const uint32_t idesc = make_idesc(128, p.Ns, 1, 1);
     const uint32_t kstepA16 = (16u * (uint32_t)p.cbA * 2u) >> 4, kstepB16 = (16u * (uint32_t)p.cbB * 2u) >> 4;   // 16 pixels, in 16-byte units
     const uint32_t ahi = sdesc_hi(8u * (uint32_t)p.cbA * 2u, (uint32_t)p.layA), bhi = sdesc_hi(8u * (uint32_t)p.cbB * 2u, (uint32_t)p.layB);
-    const uint32_t tileA16 = (uint32_t)(p.nA * blkA_bytes) >> 4;
-    const uint32_t lo_b0 = sdesc_lo(sbase, (uint32_t)blkB_bytes), lo_a0 = sdesc_lo(sbase + p.nbB * blkB_bytes, (uint32_t)blkA_bytes);
+    const uint32_t tileA16 = (uint32_t)tileA_bytes >> 4;
+    // halo mode: the tile's second 64-channel block is the same box one tile row (bw pixels) further down
+    const uint32_t rowA_bytes = (uint32_t)(p.bw * p.cbA * 2);
+    const uint32_t lo_b0 = sdesc_lo(sbase, (uint32_t)blkB_bytes),
+                   lo_a0 = sdesc_lo(sbase + p.nbB * blkB_bytes, p.halo ? rowA_bytes : (uint32_t)blkA_bytes);
+    const uint32_t slabA16 = p.halo ? rowA_bytes >> 4 : 0u;      // extra offset per (t, n) slab of the tile: its halo row
     const int nst = (int)(pt_end - pt_begin);
     // the hot loop is instantiated per (K steps per stage, accumulator tiles) so that a stage is straight-line code:
     // wait, fence, G*KS MMAs, commit (a single warp pays ~5 cycles per dependent control instruction)
 #define DCV_WG_LOOP(KS_, G_)                                                                                                     \
     wgrad_mma_loop<KS_, G_>(full_bar, empty_bar, nst, p.stages, (uint32_t)stage_bytes >> 4, lo_a0, lo_b0, ahi, bhi, kstepA16,      \
-                            kstepB16, tileA16, tmem_base, (uint32_t)p.Ns, idesc, leader)
+                            kstepB16, tileA16, tmem_base, (uint32_t)p.Ns, idesc, leader, slabA16, p.slab_shift)
 #define DCV_WG_KS(G_)                                                                                                            \
     do { if (p.pix == 128) DCV_WG_LOOP(8, G_); else if (p.pix == 64) DCV_WG_LOOP(4, G_); else DCV_WG_LOOP(2, G_); } while (0)
     if (Gcur == 4) DCV_WG_KS(4); else if (Gcur == 3) DCV_WG_KS(3); else if (Gcur == 2) DCV_WG_KS(2); else DCV_WG_KS(1);
@@ -1134,7 +1165,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     for (int gi = 0; gi < Gcur; ++gi) {
       const int blk = (tile0 + gi) * p.nA + row / p.cbA;
       const bool row_ok = blk < p.blocksA_total;
-      const int tap = row_ok ? blk / p.clchunks : 0, clc = row_ok ? blk % p.clchunks : 0;
+      int tap = row_ok ? blk / p.clchunks : 0, clc = row_ok ? blk % p.clchunks : 0;
+      if (p.halo) {
+        int ta, cls, tc;
+        wgrad_halo_tile(g, p.clchunks, tile0 + gi, ta, cls, tc, clc);
+        tap = (ta * g.kh + cls + 2 * (row / p.cbA)) * g.kw + tc;
+      }
       const int cl = clc * p.cbA + row % p.cbA;
       float* out = partial + (((int64_t)blockIdx.z * taps + tap) * g.Cl + cl) * g.Cs + cs0;
       auto store16 = [&](const uint32_t* v, int cb) {
@@ -1637,10 +1673,33 @@ static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   }
   p->tmem_cols = pow2_ceil(p->G * p->Ns < 32 ? 32 : p->G * p->Ns);
   choose_box(p->pix, g->Ws, g->Hs, g->Ts, g->N, &p->bw, &p->bh, &p->bt, &p->bn);
+  int stage_bytes = p->pix * 2 * (p->Ns + 128 * p->G);
+  p->halo = 0; p->boxA_bytes = 0; p->slab_shift = 0;
+  if (!g_tune.no_wgrad_halo && p->cbA == 64 && g->kh == 4 && g->sh == 2 && g->Ws >= 8 && g->Hs >= 2) {
+    // row-halo sharing (see TcWgradP): 8-pixel-wide tiles with as many rows as fit, the largest pixel count that leaves >= 4
+    // ring stages (else >= 3)
+    auto stages_of = [&](int pix) {
+      const int bh = pow2_floor(g->Hs < pix / 8 ? g->Hs : pix / 8);
+      return (200 * 1024) / (pix * 2 * p->Ns + p->G * (pix / (8 * bh)) * (bh + 1) * 8 * 128);
+    };
+    int best = 0;
+    for (int want = 4; want >= 3 && !best; --want)
+      for (int pix = 128; pix >= 32 && !best; pix /= 2) if (stages_of(pix) >= want) best = pix;
+    if (best) {
+      p->halo = 1; p->pix = best;
+      p->bw = 8; p->bh = pow2_floor(g->Hs < best / 8 ? g->Hs : best / 8);
+      int rem = best / (8 * p->bh), t = 1;
+      while (t * 2 <= rem && g->Ts % (t * 2) == 0) t *= 2;
+      p->bt = t; p->bn = rem / t;
+      p->boxA_bytes = p->bt * p->bn * (p->bh + 1) * 8 * 128;
+      int sh = 0; while ((1 << sh) < 8 * p->bh) ++sh;
+      p->slab_shift = sh;
+      stage_bytes = p->pix * 2 * p->Ns + p->G * p->boxA_bytes;
+    }
+  }
   p->tiles_w = ceil_div(g->Ws, p->bw); p->tiles_h = ceil_div(g->Hs, p->bh); p->tiles_t = ceil_div(g->Ts, p->bt);
   p->tiles_n = ceil_div(g->N, p->bn);
   p->ptiles_total = (int64_t)p->tiles_w * p->tiles_h * p->tiles_t * p->tiles_n;
-  const int stage_bytes = p->pix * 2 * (p->Ns + 128 * p->G);
   int stages = (200 * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 1) stages = 1;
@@ -1681,13 +1740,13 @@ int wgrad_tc(const dcv_geom* g, const void* xl, int64_t ldl, const void* xs, int
   wgrad_tc_plan(g, &p, &splits);
   DCV_REQUIRE(ws_bytes >= wgrad_tc_ws_bytes(g), "wgrad_tc workspace too small");
   CUtensorMap mapL, mapS;
-  int rc = make_act_map(&mapL, xl, g->Cl, g->Wl, g->Hl, g->Tl, g->N, ldl, p.cbA, p.bw, p.bh, p.bt, p.bn, g->sw, g->sh, g->st,
+  int rc = make_act_map(&mapL, xl, g->Cl, g->Wl, g->Hl, g->Tl, g->N, ldl, p.cbA, p.bw, p.bh + p.halo, p.bt, p.bn, g->sw, g->sh, g->st,
                         swizzle_of(p.cbA));
   if (rc) return rc;
   rc = make_act_map(&mapS, xs, g->Cs, g->Ws, g->Hs, g->Ts, g->N, lds, p.cbB, p.bw, p.bh, p.bt, p.bn, 1, 1, 1,
                     swizzle_of(p.cbB));
   if (rc) return rc;
-  const int smem = p.stages * p.pix * 2 * (p.Ns + 128 * p.G) + 1024;
+  const int smem = p.stages * (p.halo ? p.pix * 2 * p.Ns + p.G * p.boxA_bytes : p.pix * 2 * (p.Ns + 128 * p.G)) + 1024;
   static int smem_set = 0;
   if (smem > smem_set) {
     DCV_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

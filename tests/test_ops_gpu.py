@@ -52,6 +52,10 @@ TC_CASES = [
     ("halo_convT_256_64", "convT", 256, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 5, (1, 32, 32)),
     ("halo_conv_k3_64_64", "conv", 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), 3, (1, 32, 32)),
     ("halo_convT_k3_64_32", "convT", 64, 32, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, (1, 16, 24)),
+    # weight gradient with row-halo sharing: ragged tiles (S 12 x 20, odd batch), two channel chunks, 3-D with odd T
+    ("wgrad_halo_ragged", "conv", 64, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 3, (1, 24, 40)),
+    ("wgrad_halo_128_64", "conv", 128, 64, (1, 4, 4), (1, 2, 2), (0, 1, 1), 5, (1, 8, 16)),
+    ("wgrad_halo_3d", "conv", 64, 32, (4, 4, 4), (1, 2, 2), (0, 1, 1), 3, (6, 8, 16)),
 ]
 
 
@@ -166,7 +170,7 @@ def test_conv_tcgen05_tf32(case):
 
 
 VARIANTS = [{"nohalo": 1}, {"mt": 1}, {"mt": 4}, {"no_tma_store": 1}, {"wgrad_waves": 2}, {"no_tapgroup": 1}, {"sm_reserve": 16},
-            {"pdl": 1}, {"no_nsplit": 1}]
+            {"pdl": 1}, {"no_nsplit": 1}, {"no_wgrad_halo": 1}]
 
 
 @pytest.mark.parametrize("tune", VARIANTS, ids=["+".join(f"{k}={v}" for k, v in e.items()) for e in VARIANTS])
