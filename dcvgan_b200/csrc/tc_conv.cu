@@ -32,13 +32,13 @@ namespace dcv {
 // Result-preserving tuning switches (row-halo sharing off, forced M-tile count, direct-store epilogue, extra wgrad split
 // waves ...) are explicit process state set through dcv_set_tuning(), never read from the environment; the parity tests
 // flip them to cover every code path of the kernels (tests/test_ops_gpu.py::test_conv_tcgen05_kernel_variants).
-struct Tuning { int nohalo, mt, no_tma_store, no_narrow_tma_store, wgrad_waves, no_gemv, no_tapgroup, no_fused_stats, sm_reserve, pdl, no_nsplit, no_wgrad_halo; };
-static Tuning g_tune = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+struct Tuning { int nohalo, mt, no_tma_store, no_narrow_tma_store, wgrad_waves, no_gemv, no_tapgroup, no_fused_stats, sm_reserve, pdl, no_nsplit, no_wgrad_halo, wgrad_halo4, no_wgrad_whalo; };
+static Tuning g_tune = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 int set_tuning(const char* key, int value) {
   struct { const char* k; int* v; } tab[] = {{"nohalo", &g_tune.nohalo}, {"mt", &g_tune.mt}, {"no_tma_store", &g_tune.no_tma_store},
       {"no_narrow_tma_store", &g_tune.no_narrow_tma_store}, {"wgrad_waves", &g_tune.wgrad_waves}, {"no_gemv", &g_tune.no_gemv},
       {"no_tapgroup", &g_tune.no_tapgroup}, {"no_fused_stats", &g_tune.no_fused_stats}, {"sm_reserve", &g_tune.sm_reserve},
-      {"pdl", &g_tune.pdl}, {"no_nsplit", &g_tune.no_nsplit}, {"no_wgrad_halo", &g_tune.no_wgrad_halo}};
+      {"pdl", &g_tune.pdl}, {"no_nsplit", &g_tune.no_nsplit}, {"no_wgrad_halo", &g_tune.no_wgrad_halo}, {"wgrad_halo4", &g_tune.wgrad_halo4}, {"no_wgrad_whalo", &g_tune.no_wgrad_whalo}};
   for (auto& t : tab) if (!strcmp(t.k, key)) { *t.v = value; return 0; }
   DCV_REQUIRE(false, "dcv_set_tuning: unknown key '%s'", key);
 }
@@ -208,8 +208,8 @@ __device__ __forceinline__ void wgrad_issue(uint32_t tmem_d, uint32_t alo, uint3
 template <int KS, int G>
 __device__ __forceinline__ void wgrad_mma_loop(uint64_t* full_bar, uint64_t* empty_bar, int nst, int stages, uint32_t stage16,
                                                uint32_t lo_a0, uint32_t lo_b0, uint32_t ahi, uint32_t bhi, uint32_t kstepA16,
-                                               uint32_t kstepB16, uint32_t tileA16, uint32_t tmem_base, uint32_t Ns, uint32_t idesc,
-                                               bool leader, uint32_t slabA16, int slab_shift) {
+                                               uint32_t kstepB16, uint32_t pairA16, uint32_t oddA16, uint32_t tmem_base, uint32_t Ns,
+                                               uint32_t idesc, bool leader, uint32_t slabA16, int slab_shift) {
   int stage = 0; uint32_t phase = 0, accum = 0, alo = lo_a0, blo = lo_b0;
   for (int it = 0; it < nst; ++it) {
     mbar_wait(&full_bar[stage], phase);
@@ -217,7 +217,8 @@ __device__ __forceinline__ void wgrad_mma_loop(uint64_t* full_bar, uint64_t* emp
     if (leader) {
 #pragma unroll
       for (int gi = 0; gi < G; ++gi)
-        wgrad_issue<KS>(tmem_base + gi * Ns, alo + gi * tileA16, ahi, blo, bhi, kstepA16, kstepB16, idesc, accum, slabA16, slab_shift);
+        wgrad_issue<KS>(tmem_base + gi * Ns, alo + (gi >> 1) * pairA16 + (gi & 1) * oddA16, ahi, blo, bhi, kstepA16, kstepB16, idesc, accum,
+                        slabA16, slab_shift);
       umma_commit(&empty_bar[stage]);
     }
     accum = 1;
@@ -1006,15 +1007,29 @@ struct TcWgradP {
   // L, one tile row apart.  A 128-row accumulator tile is then the PAIR (kh, kh + 2) of one (kt, kh % 2, kw, channel chunk),
   // both halves served by ONE box with a halo row - the second half's descriptor starts bw pixels (a multiple of the 1024-byte
   // swizzle atom) further down - so a stage carries (bh + 1) / (2 bh) of the per-tap boxes.
-  int halo;                              // 1: tiles are (kh, kh + 2) pairs over a shared halo box
-  int boxA_bytes;                        // bytes of one halo box: slabs * (bh + 1) * bw pixels * 128
+  // Mode 2 (k = 4, stride 2 along w as well, 8-pixel-wide tiles) shares along w too: the FOUR taps (kh % 2 + {0, 2},
+  // kw % 2 + {0, 2}) of a parity class read one box of (bh + 1) x (bw + 1) lattice pixels; the kw + 2 pair is the same box one
+  // PIXEL (128 bytes) further - the 128-byte swizzle is a function of the absolute shared-memory address, so a descriptor that
+  // starts inside a swizzle atom still reads what TMA wrote (checked on the GPU with the half-atom row shift of 4-pixel tiles).
+  // Two accumulator tiles per box: a stage carries (bh + 1)(bw + 1) / (4 bh bw) of the per-tap boxes.
+  int halo;                              // 0: one box per (tap, chunk); 1: row halo; 2: row + column halo
+  int boxA_bytes;                        // shared-memory pitch of one halo box: slabs * (bh + 1) * rpA pixels * 128, rounded up to 1024
+  int boxA_tx;                           // bytes TMA delivers per box (the same without the rounding)
+  int rpA;                               // pixels per box row: bw (mode 1) or bw + 1 (mode 2)
   int slab_shift;                        // log2(bw * bh): pixels of one (t, n) slab of the tile
 };
 
-// halo mode: tile index -> (kt, kh class, kw, channel chunk); the tile's row block d (0 / 1) is the tap kh = class + 2 d
-__device__ __forceinline__ void wgrad_halo_tile(const dcv_geom& g, int clchunks, int tile, int& ta, int& cls, int& tc, int& clc) {
-  clc = tile % clchunks; tile /= clchunks;
-  tc = tile % g.kw; tile /= g.kw;
+// halo modes: tile index -> (kt, kh class, kw, channel chunk); the tile's row block d (0 / 1) is the tap kh = class + 2 d.
+// Mode 2 orders the tiles (kt, kh class, kw class, chunk, dw) so that the two tiles of a box (kw = class + 2 dw) are neighbours.
+__device__ __forceinline__ void wgrad_halo_tile(const dcv_geom& g, int clchunks, int mode, int tile, int& ta, int& cls, int& tc, int& clc) {
+  if (mode == 2) {
+    const int dw = tile % 2; tile /= 2;
+    clc = tile % clchunks; tile /= clchunks;
+    tc = tile % 2 + 2 * dw; tile /= 2;
+  } else {
+    clc = tile % clchunks; tile /= clchunks;
+    tc = tile % g.kw; tile /= g.kw;
+  }
   cls = tile % 2; ta = tile / 2;
 }
 
@@ -1040,12 +1055,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int blkA_bytes = p.pix * p.cbA * 2;
   const int blkB_bytes = p.pix * p.cbB * 2;
-  const int tileA_bytes = p.halo ? p.boxA_bytes : blkA_bytes * p.nA;      // shared memory of one accumulator tile's A operand
-  const int stage_bytes = blkB_bytes * p.nbB + tileA_bytes * p.G;
+  // shared memory of the A operand of a PAIR of accumulator tiles, and where the odd tile of a pair starts
+  const int pairA_bytes = p.halo == 2 ? p.boxA_bytes : 2 * (p.halo ? p.boxA_bytes : blkA_bytes * p.nA);
+  const int oddA_bytes = p.halo == 2 ? p.cbA * 2 : pairA_bytes / 2;
+  const int stage_bytes = blkB_bytes * p.nbB + (p.halo == 2 ? (p.G / 2) * p.boxA_bytes : (pairA_bytes / 2) * p.G);
   int blocksA_here = p.blocksA_total - tile0 * p.nA;        // valid A blocks of this CTA
   if (blocksA_here > Gcur * p.nA) blocksA_here = Gcur * p.nA;
-  const int loadsA = p.halo ? Gcur : blocksA_here;          // TMA boxes per stage for A
-  const int bytesA = p.halo ? Gcur * p.boxA_bytes : blkA_bytes * blocksA_here;
+  const int loadsA = p.halo == 2 ? Gcur / 2 : (p.halo ? Gcur : blocksA_here);          // TMA boxes per stage for A
+  const int bytesA = p.halo ? loadsA * p.boxA_tx : blkA_bytes * blocksA_here;
 
   if (warp == 0 && lane == 0) { tmap_prefetch(&mapL); tmap_prefetch(&mapS); }
   if (warp == 1) {
@@ -1088,7 +1105,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
       } else if (p.halo) {
         const int b = i - nbB;
         int ta, cls, tc, clc;
-        wgrad_halo_tile(g, p.clchunks, tile0 + b, ta, cls, tc, clc);
+        wgrad_halo_tile(g, p.clchunks, p.halo, p.halo == 2 ? tile0 + 2 * b : tile0 + b, ta, cls, tc, clc);   // mode 2: box b = tiles 2b, 2b + 1
         l_c[sl] = clc * p.cbA; l_dw[sl] = tc - g.pw; l_dh[sl] = cls - g.ph; l_dt[sl] = ta - g.pt;
         l_off[sl] = (uint32_t)(p.nbB * blkB_bytes + b * p.boxA_bytes);
       } else {
@@ -1132,11 +1149,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     // MMA issuer: uniform control flow, elected lane issues (see "lean MMA issue")
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc(128, p.Ns, 1, 1);
-    const uint32_t kstepA16 = (16u * (uint32_t)p.cbA * 2u) >> 4, kstepB16 = (16u * (uint32_t)p.cbB * 2u) >> 4;   // 16 pixels, in 16-byte units
-    const uint32_t ahi = sdesc_hi(8u * (uint32_t)p.cbA * 2u, (uint32_t)p.layA), bhi = sdesc_hi(8u * (uint32_t)p.cbB * 2u, (uint32_t)p.layB);
-    const uint32_t tileA16 = (uint32_t)tileA_bytes >> 4;
-    // halo mode: the tile's second 64-channel block is the same box one tile row (bw pixels) further down
-    const uint32_t rowA_bytes = (uint32_t)(p.bw * p.cbA * 2);
+    // K step = 16 pixels, in 16-byte units; SBO = distance between consecutive 8-pixel groups.  Mode 2: a group is one 8-pixel
+    // tile row inside a 9-pixel box row, so both follow the box row pitch
+    const uint32_t kstepA16 = (p.halo == 2 ? 2u * (uint32_t)p.rpA : 16u) * (uint32_t)p.cbA * 2u >> 4, kstepB16 = (16u * (uint32_t)p.cbB * 2u) >> 4;
+    const uint32_t ahi = sdesc_hi((p.halo == 2 ? (uint32_t)p.rpA : 8u) * (uint32_t)p.cbA * 2u, (uint32_t)p.layA),
+                   bhi = sdesc_hi(8u * (uint32_t)p.cbB * 2u, (uint32_t)p.layB);
+    const uint32_t pairA16 = (uint32_t)pairA_bytes >> 4, oddA16 = (uint32_t)oddA_bytes >> 4;
+    // halo modes: the tile's second 64-channel block is the same box one box row further down
+    const uint32_t rowA_bytes = (uint32_t)(p.rpA * p.cbA * 2);
     const uint32_t lo_b0 = sdesc_lo(sbase, (uint32_t)blkB_bytes),
                    lo_a0 = sdesc_lo(sbase + p.nbB * blkB_bytes, p.halo ? rowA_bytes : (uint32_t)blkA_bytes);
     const uint32_t slabA16 = p.halo ? rowA_bytes >> 4 : 0u;      // extra offset per (t, n) slab of the tile: its halo row
@@ -1145,7 +1165,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     // wait, fence, G*KS MMAs, commit (a single warp pays ~5 cycles per dependent control instruction)
 #define DCV_WG_LOOP(KS_, G_)                                                                                                     \
     wgrad_mma_loop<KS_, G_>(full_bar, empty_bar, nst, p.stages, (uint32_t)stage_bytes >> 4, lo_a0, lo_b0, ahi, bhi, kstepA16,      \
-                            kstepB16, tileA16, tmem_base, (uint32_t)p.Ns, idesc, leader, slabA16, p.slab_shift)
+                            kstepB16, pairA16, oddA16, tmem_base, (uint32_t)p.Ns, idesc, leader, slabA16, p.slab_shift)
 #define DCV_WG_KS(G_)                                                                                                            \
     do { if (p.pix == 128) DCV_WG_LOOP(8, G_); else if (p.pix == 64) DCV_WG_LOOP(4, G_); else DCV_WG_LOOP(2, G_); } while (0)
     if (Gcur == 4) DCV_WG_KS(4); else if (Gcur == 3) DCV_WG_KS(3); else if (Gcur == 2) DCV_WG_KS(2); else DCV_WG_KS(1);
@@ -1168,7 +1188,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
       int tap = row_ok ? blk / p.clchunks : 0, clc = row_ok ? blk % p.clchunks : 0;
       if (p.halo) {
         int ta, cls, tc;
-        wgrad_halo_tile(g, p.clchunks, tile0 + gi, ta, cls, tc, clc);
+        wgrad_halo_tile(g, p.clchunks, p.halo, tile0 + gi, ta, cls, tc, clc);
         tap = (ta * g.kh + cls + 2 * (row / p.cbA)) * g.kw + tc;
       }
       const int cl = clc * p.cbA + row % p.cbA;
@@ -1674,27 +1694,53 @@ static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   p->tmem_cols = pow2_ceil(p->G * p->Ns < 32 ? 32 : p->G * p->Ns);
   choose_box(p->pix, g->Ws, g->Hs, g->Ts, g->N, &p->bw, &p->bh, &p->bt, &p->bn);
   int stage_bytes = p->pix * 2 * (p->Ns + 128 * p->G);
-  p->halo = 0; p->boxA_bytes = 0; p->slab_shift = 0;
-  if (!g_tune.no_wgrad_halo && p->cbA == 64 && g->kh == 4 && g->sh == 2 && g->Ws >= 8 && g->Hs >= 2) {
-    // row-halo sharing (see TcWgradP): 8-pixel-wide tiles with as many rows as fit, the largest pixel count that leaves >= 4
+  p->halo = 0; p->boxA_bytes = 0; p->boxA_tx = 0; p->slab_shift = 0; p->rpA = 0;
+  // tile width: 8 pixels (a tile row = one 1024-byte swizzle atom).  4-pixel-wide tiles (4x4 maps) shift the second block by
+  // HALF an atom: the swizzle is a function of the absolute shared-memory address bits, so the shifted view stays consistent.
+  const int hbw = g->Ws >= 8 ? 8 : (g->Ws >= 4 && g_tune.wgrad_halo4 ? 4 : 0);
+  if (!g_tune.no_wgrad_halo && p->cbA == 64 && g->kh == 4 && g->sh == 2 && hbw && g->Hs * hbw >= 16) {
+    // row-halo sharing (see TcWgradP): narrow tiles with as many rows as fit, the largest pixel count that leaves >= 4
     // ring stages (else >= 3)
+    auto bh_of = [&](int pix) { return pow2_floor(g->Hs < pix / hbw ? g->Hs : pix / hbw); };
     auto stages_of = [&](int pix) {
-      const int bh = pow2_floor(g->Hs < pix / 8 ? g->Hs : pix / 8);
-      return (200 * 1024) / (pix * 2 * p->Ns + p->G * (pix / (8 * bh)) * (bh + 1) * 8 * 128);
+      const int bh = bh_of(pix);
+      return (200 * 1024) / (pix * 2 * p->Ns + p->G * (pix / (hbw * bh)) * (bh + 1) * hbw * 128);
     };
     int best = 0;
     for (int want = 4; want >= 3 && !best; --want)
       for (int pix = 128; pix >= 32 && !best; pix /= 2) if (stages_of(pix) >= want) best = pix;
     if (best) {
       p->halo = 1; p->pix = best;
-      p->bw = 8; p->bh = pow2_floor(g->Hs < best / 8 ? g->Hs : best / 8);
-      int rem = best / (8 * p->bh), t = 1;
+      p->bw = hbw; p->bh = bh_of(best);
+      int rem = best / (hbw * p->bh), t = 1;
       while (t * 2 <= rem && g->Ts % (t * 2) == 0) t *= 2;
       p->bt = t; p->bn = rem / t;
-      p->boxA_bytes = p->bt * p->bn * (p->bh + 1) * 8 * 128;
-      int sh = 0; while ((1 << sh) < 8 * p->bh) ++sh;
+      p->rpA = hbw;
+      p->boxA_bytes = p->boxA_tx = p->bt * p->bn * (p->bh + 1) * hbw * 128;
+      int sh = 0; while ((1 << sh) < hbw * p->bh) ++sh;
       p->slab_shift = sh;
       stage_bytes = p->pix * 2 * p->Ns + p->G * p->boxA_bytes;
+    }
+    // column halo on top (mode 2): 8-pixel-wide tiles, kw = 4 with stride 2, an even number of tiles per CTA
+    if (best && hbw == 8 && g->kw == 4 && g->sw == 2 && p->G % 2 == 0 && tiles_total % p->G == 0 && !g_tune.no_wgrad_whalo) {
+      auto box2 = [&](int pix) { const int bh = bh_of(pix); return ((pix / (8 * bh)) * (bh + 1) * 9 * 128 + 1023) / 1024 * 1024; };
+      auto stages2 = [&](int pix) { return (200 * 1024) / (pix * 2 * p->Ns + (p->G / 2) * box2(pix)); };
+      int best2 = 0;
+      for (int want = 4; want >= 3 && !best2; --want)
+        for (int pix = 128; pix >= 32 && !best2; pix /= 2) if (stages2(pix) >= want) best2 = pix;
+      if (best2) {
+        p->halo = 2; p->pix = best2;
+        p->bh = bh_of(best2);
+        int rem = best2 / (8 * p->bh), t = 1;
+        while (t * 2 <= rem && g->Ts % (t * 2) == 0) t *= 2;
+        p->bt = t; p->bn = rem / t;
+        p->rpA = 9;
+        p->boxA_bytes = box2(best2);
+        p->boxA_tx = p->bt * p->bn * (p->bh + 1) * 9 * 128;
+        int sh = 0; while ((1 << sh) < 8 * p->bh) ++sh;
+        p->slab_shift = sh;
+        stage_bytes = p->pix * 2 * p->Ns + (p->G / 2) * p->boxA_bytes;
+      }
     }
   }
   p->tiles_w = ceil_div(g->Ws, p->bw); p->tiles_h = ceil_div(g->Hs, p->bh); p->tiles_t = ceil_div(g->Ts, p->bt);
@@ -1740,13 +1786,14 @@ int wgrad_tc(const dcv_geom* g, const void* xl, int64_t ldl, const void* xs, int
   wgrad_tc_plan(g, &p, &splits);
   DCV_REQUIRE(ws_bytes >= wgrad_tc_ws_bytes(g), "wgrad_tc workspace too small");
   CUtensorMap mapL, mapS;
-  int rc = make_act_map(&mapL, xl, g->Cl, g->Wl, g->Hl, g->Tl, g->N, ldl, p.cbA, p.bw, p.bh + p.halo, p.bt, p.bn, g->sw, g->sh, g->st,
-                        swizzle_of(p.cbA));
+  int rc = make_act_map(&mapL, xl, g->Cl, g->Wl, g->Hl, g->Tl, g->N, ldl, p.cbA, p.bw + (p.halo == 2), p.bh + (p.halo != 0), p.bt, p.bn,
+                        g->sw, g->sh, g->st, swizzle_of(p.cbA));
   if (rc) return rc;
   rc = make_act_map(&mapS, xs, g->Cs, g->Ws, g->Hs, g->Ts, g->N, lds, p.cbB, p.bw, p.bh, p.bt, p.bn, 1, 1, 1,
                     swizzle_of(p.cbB));
   if (rc) return rc;
-  const int smem = p.stages * (p.halo ? p.pix * 2 * p.Ns + p.G * p.boxA_bytes : p.pix * 2 * (p.Ns + 128 * p.G)) + 1024;
+  const int smem = p.stages * (p.halo == 2 ? p.pix * 2 * p.Ns + (p.G / 2) * p.boxA_bytes
+                                           : (p.halo ? p.pix * 2 * p.Ns + p.G * p.boxA_bytes : p.pix * 2 * (p.Ns + 128 * p.G))) + 1024;
   static int smem_set = 0;
   if (smem > smem_set) {
     DCV_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -170,11 +170,12 @@ def test_conv_tcgen05_tf32(case):
 
 
 VARIANTS = [{"nohalo": 1}, {"mt": 1}, {"mt": 4}, {"no_tma_store": 1}, {"wgrad_waves": 2}, {"no_tapgroup": 1}, {"sm_reserve": 16},
-            {"pdl": 1}, {"no_nsplit": 1}, {"no_wgrad_halo": 1}]
+            {"pdl": 1}, {"no_nsplit": 1}, {"no_wgrad_halo": 1}, {"wgrad_halo4": 1}, {"no_wgrad_whalo": 1}]
 
 
 @pytest.mark.parametrize("tune", VARIANTS, ids=["+".join(f"{k}={v}" for k, v in e.items()) for e in VARIANTS])
-@pytest.mark.parametrize("case", [TC_CASES[0], TC_CASES[1], TC_CASES[5], TC_CASES[7], TC_CASES[8], TC_CASES[9], TC_CASES[13], TC_CASES[14]],
+@pytest.mark.parametrize("case", [TC_CASES[0], TC_CASES[1], TC_CASES[5], TC_CASES[7], TC_CASES[8], TC_CASES[9], TC_CASES[13], TC_CASES[14],
+                                  TC_CASES[15], TC_CASES[17]],
                          ids=lambda c: c[0])
 def test_conv_tcgen05_kernel_variants(case, tune):
     """Every tuning switch of the tcgen05 path (row-halo sharing off, forced M-tile counts, direct-store epilogue, two split
