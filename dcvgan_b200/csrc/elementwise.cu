@@ -779,14 +779,14 @@ axpy_vec_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int C, T* __
 template <int S>
 __global__ void __launch_bounds__(256)
 col2im_act_tiled_kernel(const __nv_bfloat16* __restrict__ P, int64_t ldp, int Ih, int Iw, int Cout, int KH, int KW, int pad,
-                        int Oh, int Ow, int rowv /*16-byte vectors per staged row*/, int RH, int RW /*staged region*/, int act,
-                        float slope, __nv_bfloat16* __restrict__ y, int64_t ldy) {
+                        int Oh, int Ow, int rowv /*16-byte vectors per staged row*/, int RH, int RW /*staged region*/, int TW /*tile width*/,
+                        int act, float slope, __nv_bfloat16* __restrict__ y, int64_t ldy) {
   pdl_wait(); pdl_trigger();
   extern __shared__ uint32_t tile[];
   // staged pixel pitch = rowv*4 + 1 words: neighbouring output pixels read the same column of neighbouring staged pixels,
   // and a 64-byte pitch put 16 of them on 2 banks (ncu: 8 shared-memory wavefronts per load)
   const int pitch = rowv * 4 + 1;
-  const int n = blockIdx.z, oh0 = blockIdx.y * 16, ow0 = blockIdx.x * 16;
+  const int n = blockIdx.z, oh0 = blockIdx.y * 16, ow0 = blockIdx.x * TW;
   // first input row / column any output pixel of the tile can see: ih = (oh + pad - kh) / S, kh = KH-1 .. 0
   const int ih0 = max(0, (oh0 + pad - (KH - 1) + (S - 1)) / S), iw0 = max(0, (ow0 + pad - (KW - 1) + (S - 1)) / S);
   const int nvec = RH * RW * rowv;
@@ -800,35 +800,39 @@ col2im_act_tiled_kernel(const __nv_bfloat16* __restrict__ P, int64_t ldp, int Ih
     d[0] = val.x; d[1] = val.y; d[2] = val.z; d[3] = val.w;
   }
   __syncthreads();
-  const int oh = oh0 + (int)threadIdx.x / 16, ow = ow0 + (int)threadIdx.x % 16;
-  if (oh >= Oh || ow >= Ow) return;
   const int taps = KH * KW;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int kh = 0; kh < KH; ++kh) {
-    const int th = oh + pad - kh;
-    if (th < 0 || th % S) continue;
-    const int ih = th / S;
-    if (ih >= Ih) continue;
-    for (int kw = 0; kw < KW; ++kw) {
-      const int tw = ow + pad - kw;
-      if (tw < 0 || tw % S) continue;
-      const int iw = tw / S;
-      if (iw >= Iw) continue;
-      const uint32_t* row = tile + ((ih - ih0) * RW + (iw - iw0)) * pitch;
-      const int e0 = kh * KW + kw;
+  // a 16-row x TW-column output tile per block (TW = 64 when the staged region fits: 4x fewer, 4x longer blocks - 8192 blocks of
+  // 256 outputs each spent their time in launch / barrier latency, 58 us for the 64x64 frames of a batch of 32 clips)
+  for (int o = threadIdx.x; o < 16 * TW; o += 256) {
+    const int oh = oh0 + o / TW, ow = ow0 + o % TW;
+    if (oh >= Oh || ow >= Ow) continue;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kh = 0; kh < KH; ++kh) {
+      const int th = oh + pad - kh;
+      if (th < 0 || th % S) continue;
+      const int ih = th / S;
+      if (ih >= Ih) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int tw = ow + pad - kw;
+        if (tw < 0 || tw % S) continue;
+        const int iw = tw / S;
+        if (iw >= Iw) continue;
+        const uint32_t* row = tile + ((ih - ih0) * RW + (iw - iw0)) * pitch;
+        const int e0 = kh * KW + kw;
 #pragma unroll
-      for (int co = 0; co < 4; ++co) {
-        if (co < Cout) {
-          const int e = e0 + co * taps;
-          const uint32_t wv = row[e >> 1];
-          acc[co] += __uint_as_float((e & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+        for (int co = 0; co < 4; ++co) {
+          if (co < Cout) {
+            const int e = e0 + co * taps;
+            const uint32_t wv = row[e >> 1];
+            acc[co] += __uint_as_float((e & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+          }
         }
       }
     }
-  }
-  __nv_bfloat16* yo = y + (((int64_t)n * Oh + oh) * Ow + ow) * ldy;
+    __nv_bfloat16* yo = y + (((int64_t)n * Oh + oh) * Ow + ow) * ldy;
 #pragma unroll
-  for (int co = 0; co < 4; ++co) if (co < Cout) yo[co] = __float2bfloat16_rn(apply_act(acc[co], act, slope));
+    for (int co = 0; co < 4; ++co) if (co < Cout) yo[co] = __float2bfloat16_rn(apply_act(acc[co], act, slope));
+  }
 }
 
 template <typename T, int S>      // S = stride known at compile time (1, 2) or 0 = runtime
@@ -1473,16 +1477,18 @@ int dcv_col2im_act(int dtype, const void* P, int64_t ldp, int N, int Ih, int Iw,
   if (dtype == DCV_BF16 && (stride == 1 || stride == 2) && ldp % 8 == 0 && (((uintptr_t)P) & 15) == 0 && N <= 65535) {
     const int rowv = (Cout * KH * KW + 7) / 8;
     // staged region: input rows [ih0, ih_last] for 16 output rows (ih_last = (oh0 + 15 + pad) / S)
-    const int RH = (16 + KH - 2) / stride + 2, RW = (16 + KW - 2) / stride + 2;
+    const int RH = (16 + KH - 2) / stride + 2;
+    int TW = 64, RW = (TW + KW - 2) / stride + 2;
+    if (Ow < 64 || (size_t)RH * RW * (rowv * 4 + 1) * 4 > 48 * 1024) { TW = 16; RW = (TW + KW - 2) / stride + 2; }
     const size_t smem = (size_t)RH * RW * (rowv * 4 + 1) * 4;
     if (smem <= 48 * 1024) {
-      dim3 grid(ceil_div(Ow, 16), ceil_div(Oh, 16), N);
+      dim3 grid(ceil_div(Ow, TW), ceil_div(Oh, 16), N);
       if (stride == 1)
         launch_k(col2im_act_tiled_kernel<1>, grid, 256, smem, as_stream(stream), (const __nv_bfloat16*)P, ldp, Ih, Iw, Cout, KH, KW, pad, Oh, Ow,
-                                                                           rowv, RH, RW, act, slope, (__nv_bfloat16*)y, ldy);
+                                                                           rowv, RH, RW, TW, act, slope, (__nv_bfloat16*)y, ldy);
       else
         launch_k(col2im_act_tiled_kernel<2>, grid, 256, smem, as_stream(stream), (const __nv_bfloat16*)P, ldp, Ih, Iw, Cout, KH, KW, pad, Oh, Ow,
-                                                                           rowv, RH, RW, act, slope, (__nv_bfloat16*)y, ldy);
+                                                                           rowv, RH, RW, TW, act, slope, (__nv_bfloat16*)y, ldy);
       return check_launch("col2im_act_tiled");
     }
   }

@@ -121,6 +121,148 @@ __global__ void gru_bwd_kernel(const float* __restrict__ h0, const float* __rest
   }
 }
 
+// ---- dim_z_motion <= 10 (every shipped configuration): 3 D <= 32 gate rows, ONE per lane.  The generic kernels above re-read the
+// weights from global memory inside every time step, keep the weight-gradient accumulators in shared memory (read-modify-write
+// per step) and fetch the step's inputs with dependent global loads: 79 us for the 16-step BPTT of a batch of 32, all of it
+// latency.  Here a lane keeps its gate row of both weight matrices (and, backward, its accumulators and its column of W_hh) in
+// registers and the whole trajectory of the row (eps, h, dh) is staged in shared memory up front.  Same operations in the same
+// order as the generic kernels: bit-identical results.
+template <int D>
+__global__ void gru_fwd_small_kernel(const float* __restrict__ h0, const float* __restrict__ eps, const float* __restrict__ w_ih,
+                                     const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+                                     const float* __restrict__ b_hh, int B, int T, float* __restrict__ hs) {
+  pdl_wait(); pdl_trigger();
+  constexpr int G = 3 * D;
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  float* es = sm + warp * (T * D + D + 2 * G);          // eps of every step
+  float* h = es + T * D; float* gi = h + D; float* gh = gi + G;
+  float wi[D], wh[D], bi = 0.f, bh = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) { wi[k] = lane < G ? w_ih[lane * D + k] : 0.f; wh[k] = lane < G ? w_hh[lane * D + k] : 0.f; }
+  if (lane < G) { bi = b_ih[lane]; bh = b_hh[lane]; }
+  for (int b = blockIdx.x * nw + warp; b < B; b += gridDim.x * nw) {
+    __syncwarp();
+    for (int i = lane; i < T * D; i += 32) es[i] = eps[((int64_t)(i / D) * B + b) * D + i % D];
+    if (lane < D) h[lane] = h0[b * D + lane];
+    __syncwarp();
+    for (int t = 0; t < T; ++t) {
+      if (lane < G) {
+        float a = bi, c = bh;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { a = fmaf(wi[k], es[t * D + k], a); c = fmaf(wh[k], h[k], c); }
+        gi[lane] = a; gh[lane] = c;
+      }
+      __syncwarp();
+      float hn = 0.f;
+      if (lane < D) {
+        const float r = sigmoidf_(gi[lane] + gh[lane]);
+        const float z = sigmoidf_(gi[D + lane] + gh[D + lane]);
+        const float n = tanhf(gi[2 * D + lane] + r * gh[2 * D + lane]);
+        hn = (1.f - z) * n + z * h[lane];
+        hs[((int64_t)b * T + t) * D + lane] = hn;
+      }
+      __syncwarp();
+      if (lane < D) h[lane] = hn;
+      __syncwarp();
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(1024, 1) gru_bwd_small_kernel(const float* __restrict__ h0, const float* __restrict__ eps, const float* __restrict__ hs,
+                                     const float* __restrict__ dhs, const float* __restrict__ w_ih,
+                                     const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+                                     const float* __restrict__ b_hh, int B, int T, float* __restrict__ dw_ih,
+                                     float* __restrict__ dw_hh, float* __restrict__ db_ih, float* __restrict__ db_hh,
+                                     int accumulate) {
+  pdl_wait(); pdl_trigger();
+  constexpr int G = 3 * D, NACC = 2 * G * D + 2 * G;
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  const int per_warp = 3 * T * D + 2 * D + 4 * G + NACC;
+  float* whs = sm + nw * per_warp;                                                // W_hh, shared by the warps (read by column)
+  for (int i = threadIdx.x; i < G * D; i += blockDim.x) whs[i] = w_hh[i];
+  __syncthreads();
+  float* base = sm + warp * per_warp;
+  float* es = base; float* hp = es + T * D; float* dhs_s = hp + T * D;          // eps_t, h_{t-1}, dL/dh_t for every step
+  float* dh = dhs_s + T * D; float* pad = dh + D;
+  float* gi = pad + D; float* gh = gi + G; float* dgi = gh + G; float* dgh = dgi + G;
+  float* acc = dgh + G;                                                           // this warp's sums, dumped at the end
+  float wi[D], wh[D], aWi[D], aWh[D], bi = 0.f, bh = 0.f, abi = 0.f, abh = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    wi[k] = lane < G ? w_ih[lane * D + k] : 0.f; wh[k] = lane < G ? w_hh[lane * D + k] : 0.f;
+    aWi[k] = 0.f; aWh[k] = 0.f;
+  }
+  if (lane < G) { bi = b_ih[lane]; bh = b_hh[lane]; }
+  for (int b = warp; b < B; b += nw) {
+    __syncwarp();
+    for (int i = lane; i < T * D; i += 32) {
+      const int t = i / D, d = i % D;
+      es[i] = eps[((int64_t)t * B + b) * D + d];
+      hp[i] = t == 0 ? h0[b * D + d] : hs[((int64_t)b * T + (t - 1)) * D + d];
+      dhs_s[i] = dhs[((int64_t)b * T + t) * D + d];
+    }
+    if (lane < D) dh[lane] = 0.f;
+    __syncwarp();
+    for (int t = T - 1; t >= 0; --t) {
+      const float* e = es + t * D; const float* h = hp + t * D;
+      if (lane < D) dh[lane] += dhs_s[t * D + lane];
+      if (lane < G) {
+        float a = bi, c = bh;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { a = fmaf(wi[k], e[k], a); c = fmaf(wh[k], h[k], c); }
+        gi[lane] = a; gh[lane] = c;
+      }
+      __syncwarp();
+      if (lane < D) {
+        const int d = lane;
+        const float r = sigmoidf_(gi[d] + gh[d]);
+        const float z = sigmoidf_(gi[D + d] + gh[D + d]);
+        const float n = tanhf(gi[2 * D + d] + r * gh[2 * D + d]);
+        const float g = dh[d];
+        const float dn_pre = g * (1.f - z) * (1.f - n * n);
+        const float dz_pre = g * (h[d] - n) * z * (1.f - z);
+        const float dr_pre = dn_pre * gh[2 * D + d] * r * (1.f - r);
+        dgi[d] = dr_pre; dgi[D + d] = dz_pre; dgi[2 * D + d] = dn_pre;
+        dgh[d] = dr_pre; dgh[D + d] = dz_pre; dgh[2 * D + d] = dn_pre * r;
+        dh[d] = g * z;  // direct path to h_{t-1}
+      }
+      __syncwarp();
+      if (lane < G) {
+        const float a = dgi[lane], c = dgh[lane];
+#pragma unroll
+        for (int k = 0; k < D; ++k) { aWi[k] = fmaf(a, e[k], aWi[k]); aWh[k] = fmaf(c, h[k], aWh[k]); }
+        abi += a; abh += c;
+      }
+      if (lane < D) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < G; ++j) s = fmaf(dgh[j], whs[j * D + lane], s);
+        dh[lane] += s;
+      }
+      __syncwarp();
+    }
+  }
+  if (lane < G) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) { acc[lane * D + k] = aWi[k]; acc[G * D + lane * D + k] = aWh[k]; }
+    acc[2 * G * D + lane] = abi; acc[2 * G * D + G + lane] = abh;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NACC; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += sm[w * per_warp + (per_warp - NACC) + i];
+    float* dst;
+    if (i < G * D) dst = dw_ih + i;
+    else if (i < 2 * G * D) dst = dw_hh + (i - G * D);
+    else if (i < 2 * G * D + G) dst = db_ih + (i - 2 * G * D);
+    else dst = db_hh + (i - 2 * G * D - G);
+    *dst = accumulate ? *dst + s : s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -284,6 +426,11 @@ int dcv_gru_traj_fwd(const float* h0, const float* eps, const float* w_ih, const
   if (B == 0) return 0;
   const int nw = 4;
   const int blocks = ceil_div(B, nw);
+  if (D == 10 && (size_t)nw * (T * D + D + 6 * D) * sizeof(float) <= 48 * 1024) {
+    launch_k(gru_fwd_small_kernel<10>, blocks, nw * 32, nw * (T * D + D + 6 * D) * sizeof(float), as_stream(stream), h0, eps, w_ih, w_hh,
+             b_ih, b_hh, B, T, hs);
+    return check_launch("gru_fwd_small");
+  }
   launch_k(gru_fwd_kernel, blocks, nw * 32, nw * 8 * D * sizeof(float), as_stream(stream), h0, eps, w_ih, w_hh, b_ih, b_hh, B, T, D, hs);
   return check_launch("gru_fwd");
 }
@@ -293,6 +440,22 @@ int dcv_gru_traj_bwd(const float* h0, const float* eps, const float* hs, const f
                      float* dw_hh, float* db_ih, float* db_hh, int accumulate, void* stream) {
   DCV_REQUIRE(D >= 1 && D <= 64, "gru: dim_z_motion %d out of range [1,64]", D);
   const int G = 3 * D;
+  if (D == 10) {
+    const int pw = 3 * T * D + 2 * D + 4 * G + 2 * G * D + 2 * G;
+    int nws = 32;
+    while (nws > 1 && (nws > B || ((size_t)nws * pw + G * D) * sizeof(float) > 200 * 1024)) nws /= 2;
+    const size_t smem_s = ((size_t)nws * pw + G * D) * sizeof(float);
+    if (smem_s <= 200 * 1024) {
+      static size_t smem_s_set = 48 * 1024;
+      if (smem_s > smem_s_set) {
+        DCV_CUDA(cudaFuncSetAttribute(gru_bwd_small_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+        smem_s_set = smem_s;
+      }
+      launch_k(gru_bwd_small_kernel<10>, 1, nws * 32, smem_s, as_stream(stream), h0, eps, hs, dhs, w_ih, w_hh, b_ih, b_hh, B, T, dw_ih,
+               dw_hh, db_ih, db_hh, accumulate);
+      return check_launch("gru_bwd_small");
+    }
+  }
   const int per_warp = 3 * D + 4 * G + 2 * G * D + 2 * G;
   // one warp per batch row when the per-warp accumulators fit (the time steps are serial and latency-bound: 8 warps took
   // 170 us for B = 32, T = 16); the warps are summed in a fixed order, so the result stays deterministic

@@ -580,10 +580,12 @@ def test_layout_strided_frames():
     assert torch.equal(out.cpu(), 2 * v.cpu())
 
 
-def test_gru_trajectory():
+@pytest.mark.parametrize("b,t,d", [(5, 16, 10), (32, 16, 10), (37, 7, 10), (6, 9, 12)])
+def test_gru_trajectory(b, t, d):
+    """d = 10: register-resident kernels (one gate row per lane; 32 rows fill the 32-warp BPTT block, 37 wrap around);
+    d = 12: the generic kernels"""
     ops = _ops()
     torch.manual_seed(6)
-    b, t, d = 5, 16, 10
     cell = torch.nn.GRUCell(d, d)
     h0 = torch.randn(b, d)
     eps = torch.randn(t, b, d)
