@@ -31,7 +31,14 @@ class Geom(C.Structure):
         return tuple(getattr(self, n) for n, _ in self._fields_)
 
 
-ABI_VERSION = 4   # include/dcvgan_b200.h DCV_ABI_VERSION
+class PreBn(C.Structure):
+    """mirror of `struct dcv_prebn` (BatchNorm + (Leaky)ReLU applied on load by the image-side kernels)"""
+
+    _fields_ = [("mean", C.c_void_p), ("invstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("c0", C.c_int32), ("count", C.c_int32), ("slope", C.c_float)]
+
+
+ABI_VERSION = 5   # include/dcvgan_b200.h DCV_ABI_VERSION
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _G = C.POINTER(Geom)
@@ -49,8 +56,8 @@ SIGNATURES = {
     "dcv_img_conv_supported": (_i, [_G, _i]),
     "dcv_img_conv_bwd_workspace_bytes": (_i64, [_G]),
     "dcv_img_conv_fwd": (_i, [_G, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i, _f, _vp]),
-    "dcv_img_conv_scatter": (_i, [_G, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i, _f, _vp]),
-    "dcv_img_conv_bwd": (_i, [_G, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i, _f, _vp, _i, _vp, _i64, _vp, _i64, _vp]),
+    "dcv_img_conv_scatter": (_i, [_G, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i, _f, _vp, _vp]),
+    "dcv_img_conv_bwd": (_i, [_G, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i, _f, _vp, _i, _vp, _i64, _vp, _i64, _vp, _vp]),
     "dcv_packed_weight_bytes": (_i64, [_G, _i, _i]),
     "dcv_pack_weight": (_i, [_G, _i, _i, _vp, _i64, _i64, _i64, _vp, _vp]),
     "dcv_pack_weight_batch": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

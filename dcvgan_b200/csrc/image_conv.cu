@@ -40,6 +40,34 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
+// ---- BatchNorm + (Leaky)ReLU applied on load ("pre-BN") ------------------------------------------------------------------
+// The 128-channel input of Outconv is the concat [up_blocks.5 output | Inconv skip] (generator.py:401-402).  Its first half is
+// BatchNorm + ReLU of a convolution output z; materialising a = relu(bn(z)) costs a pass that reads and writes the 268 MB
+// tensor (bn_act, 0.09 ms at batch 32, twice per iteration).  With a PreBn the kernels below read z itself from that half of
+// the concat buffer and apply a = act(z * P + Q), P = invstd * gamma, Q = beta - mean * invstd * gamma, rounded to bf16 - the
+// arithmetic and rounding of bn_act_bf16_kernel, so the operand the MMAs see is bit-identical to the materialised tensor.
+struct PreBn {
+  const float* mean; const float* invstd; const float* gamma; const float* beta;   // [64] each; gamma / beta may be NULL
+  int half;                                                                        // 64-channel half of the input they apply to
+  float slope;                                                                     // LeakyReLU slope (0 = ReLU)
+};
+// coefficients of the 16 channels a lane touches in a half: 8q .. 8q+7 and 32+8q .. 32+8q+7
+__device__ __forceinline__ void prebn_coeffs(const PreBn& pre, int q, float (&P)[16], float (&Q)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = (i < 8 ? 8 * q + i : 32 + 8 * q + (i - 8));
+    const float is = pre.invstd[c], mu = pre.mean[c];
+    const float g = pre.gamma ? pre.gamma[c] : 1.f, b = pre.gamma ? pre.beta[c] : 0.f;
+    P[i] = is * g; Q[i] = b - mu * is * g;
+  }
+}
+// word p (0..7) of a lane's two 16-byte vectors holds the channel pair 2p, 2p+1 of those 16
+__device__ __forceinline__ uint32_t prebn_word(uint32_t v, int p, const float (&P)[16], const float (&Q)[16], float slope) {
+  float a = fmaf(bf16_lo(v), P[2 * p], Q[2 * p]), b = fmaf(bf16_hi(v), P[2 * p + 1], Q[2 * p + 1]);
+  a = a > 0.f ? a : a * slope; b = b > 0.f ? b : b * slope;
+  return pack_bf16x2(a, b);
+}
+
 // D(16x8, f32) += A(16x16, bf16, row) * B(16x8, bf16, col).  Fragment layout (g = lane / 4, q = lane % 4):
 //   a0 = A[g][2q,2q+1]  a1 = A[g+8][2q,2q+1]  a2 = A[g][2q+8,2q+9]  a3 = A[g+8][2q+8,2q+9]
 //   b0 = B[2q,2q+1][g]  b1 = B[2q+8,2q+9][g]      d0,d1 = D[g][2q,2q+1]  d2,d3 = D[g+8][2q,2q+1]
@@ -173,13 +201,14 @@ __device__ __forceinline__ int slot_channel(int s, int sigma) {
 
 // NCO = channels of the big tensor (64; 128 = weight gradient only, the two channel halves are owned by warps 0-3 / 4-7),
 // DGRAD: also form the data gradient dx
-template <int C, int NCO, bool DGRAD>
-__global__ void __launch_bounds__(256)
+template <int C, int NCO, bool DGRAD, bool PRE = false>
+__global__ void __launch_bounds__(256, 2)
 img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const __nv_bfloat16* __restrict__ a, int64_t lda,
                        const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t s_l, int64_t s_s,
                        int N, int H, int W, int act, float slope, float* __restrict__ partial, __nv_bfloat16* __restrict__ dx,
-                       int64_t lddx) {
+                       int64_t lddx, const PreBn pre) {
   pdl_wait(); pdl_trigger();
+  static_assert(!PRE || !DGRAD, "pre-BN is for the weight-gradient-only pass (the streamed tensor is the layer input)");
   constexpr int NT = 9 * C;                    // (tap, ci) pairs
   constexpr int NJ = (NT + 7) / 8;             // n8 tiles over them
   constexpr int NP = NJ * 8 + 8;               // row length of P: 8 floats of padding keep the float2 fragment stores conflict-free
@@ -194,6 +223,24 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
   const int half = warp / WPH, wsub = warp % WPH;
   const int bands = H / IMG_BAND;
   const int WP = W + 2;
+  // pre-BN coefficients live in shared memory here ((P, Q) of a channel pair per float4): 32 more registers per thread would
+  // cost this kernel its second block per SM
+  __shared__ float4 prePQ[PRE ? 32 : 1];
+  const bool pre_on = PRE && half == pre.half;
+  if constexpr (PRE) {
+    if (threadIdx.x < 32) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = 2 * (int)threadIdx.x + e;
+        const float is = pre.invstd[c], mu = pre.mean[c];
+        const float gm = pre.gamma ? pre.gamma[c] : 1.f, bt = pre.gamma ? pre.beta[c] : 0.f;
+        v[2 * e] = is * gm; v[2 * e + 1] = bt - mu * is * gm;
+      }
+      prePQ[threadIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+  }
   // B fragments of the data-gradient GEMM: B[k slot][nn] = w[co(s, slot)][ci][tap], nn = tap*C + ci (0 beyond 9*C)
   uint32_t bw[DGRAD ? 4 : 1][NJ][2];
   if (DGRAD) {
@@ -248,6 +295,14 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
 #pragma unroll
         for (int p = 0; p < 8; ++p) {          // value pair i = 2p, 2p+1  ->  step s = p / 2, column half = p % 2
           uint32_t v = dw_[p];
+          if constexpr (PRE) {
+            if (pre_on) {                        // word p = channel pair (p < 4 ? 8q + 2p : 32 + 8q + 2(p - 4)) of this half
+              const float4 c4 = prePQ[p < 4 ? 4 * q + p : 16 + 4 * q + (p - 4)];
+              float f0 = fmaf(bf16_lo(v), c4.x, c4.y), f1 = fmaf(bf16_hi(v), c4.z, c4.w);
+              f0 = f0 > 0.f ? f0 : f0 * pre.slope; f1 = f1 > 0.f ? f1 : f1 * pre.slope;
+              v = pack_bf16x2(f0, f1);
+            }
+          }
           if (act != DCV_ACT_NONE) {
             const float g0 = act_grad_from_out(bf16_lo(ow_[p]), act, slope), g1 = act_grad_from_out(bf16_hi(ow_[p]), act, slope);
             v = pack_bf16x2(bf16_lo(v) * g0, bf16_hi(v) * g1);
@@ -351,10 +406,10 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
 // This is the forward of `Outconv` = ConvTranspose2d(128, 3, 3, 1, 1) + Tanh (generator.py:272-277), which ran as a 1x1
 // tensor-core GEMM onto 27 (padded 32) columns plus a col2im pass over a 134 MB intermediate (0.204 ms at batch 32); here the
 // 537 MB input is read once and nothing but the 3-channel output is written.
-template <int C, int NCO>
+template <int C, int NCO, bool PRE = false>
 __global__ void __launch_bounds__(256, 2)
 img_conv3x3_scatter_kernel(const __nv_bfloat16* __restrict__ xb, int64_t ldb, const float* __restrict__ w, int64_t s_l, int64_t s_s,
-                           int N, int H, int W, int act, float slope, __nv_bfloat16* __restrict__ y, int64_t ldy) {
+                           int N, int H, int W, int act, float slope, __nv_bfloat16* __restrict__ y, int64_t ldy, const PreBn pre) {
   pdl_wait(); pdl_trigger();
   constexpr int NT = 9 * C, NJ = (NT + 7) / 8, NP = NJ * 8 + 8, NH = NCO / 64;   // NP: P row with 8 floats of padding (conflict-free)
   extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -381,6 +436,8 @@ img_conv3x3_scatter_kernel(const __nv_bfloat16* __restrict__ xb, int64_t ldb, co
           bws[((((hf * 4 + s) * NJ + j) * 2 + h) << 5) + lane] = pack_bf16x2(v[0], v[1]);
         }
   const int tiles_w = W / 16, tiles = (IMG_BAND + 2) * tiles_w;
+  float preP[PRE ? 16 : 1], preQ[PRE ? 16 : 1];
+  if constexpr (PRE) prebn_coeffs(pre, q, preP, preQ);
   for (int item = blockIdx.x; item < N * bands; item += gridDim.x) {
     const int n = item / bands, r0 = (item % bands) * IMG_BAND;
     __syncthreads();                               // B fragments written / the previous item's readers of Ps are done
@@ -412,7 +469,13 @@ img_conv3x3_scatter_kernel(const __nv_bfloat16* __restrict__ xb, int64_t ldb, co
               d0 = *reinterpret_cast<const uint4*>(xb + pix * ldb + 64 * hf + 8 * q);
               d1 = *reinterpret_cast<const uint4*>(xb + pix * ldb + 64 * hf + 32 + 8 * q);
             }
-            const uint32_t dw_[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            uint32_t dw_[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            if constexpr (PRE) {
+              if (hf == pre.half && live[u]) {     // padding rows stay zero AFTER the activation
+#pragma unroll
+                for (int p = 0; p < 8; ++p) dw_[p] = prebn_word(dw_[p], p, preP, preQ, pre.slope);
+              }
+            }
 #pragma unroll
             for (int p = 0; p < 8; ++p) ar[u][p / 2][2 * (p % 2) + rr] = dw_[p];
           }
@@ -513,46 +576,62 @@ int img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, 
   return check_launch("img_conv3x3_fwd");
 }
 
-template <int C, int NCO, bool DGRAD>
+template <int C, int NCO, bool DGRAD, bool PRE = false>
 static int launch_bwd(const dcv_geom* g, int blocks, int smem, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x,
                       int64_t ldx, const float* w, int64_t s_l, int64_t s_s, int act, float slope, float* partial, void* dx, int64_t lddx,
-                      cudaStream_t s) {
+                      const PreBn& pre, cudaStream_t s) {
   static int smem_set = 0;
   if (smem > smem_set) {
-    DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_bwd_kernel<C, NCO, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_bwd_kernel<C, NCO, DGRAD, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_set = smem;
   }
-  launch_k(img_conv3x3_bwd_kernel<C, NCO, DGRAD>, blocks, 256, smem, s, (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda,
-           (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx);
+  launch_k(img_conv3x3_bwd_kernel<C, NCO, DGRAD, PRE>, blocks, 256, smem, s, (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda,
+           (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx, pre);
   return 0;
 }
 
-template <int C, int NCO>
+template <int C, int NCO, bool PRE = false>
 static int launch_scatter(const dcv_geom* g, int blocks, const void* xb, int64_t ldb, const float* w, int64_t s_l, int64_t s_s, int act,
-                          float slope, void* y, int64_t ldy, cudaStream_t s) {
+                          float slope, void* y, int64_t ldy, const PreBn& pre, cudaStream_t s) {
   const int nj = (9 * C + 7) / 8, np = nj * 8 + 8;
   const int smem = (IMG_BAND + 2) * g->Wl * np * (int)sizeof(float) + (NCO / 64) * 4 * nj * 2 * 32 * 4 + 16;
   static int smem_set = 0;
   if (smem > smem_set) {
-    DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_scatter_kernel<C, NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_scatter_kernel<C, NCO, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_set = smem;
   }
-  launch_k(img_conv3x3_scatter_kernel<C, NCO>, blocks, 256, smem, s, (const __nv_bfloat16*)xb, ldb, w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope,
-           (__nv_bfloat16*)y, ldy);
+  launch_k(img_conv3x3_scatter_kernel<C, NCO, PRE>, blocks, 256, smem, s, (const __nv_bfloat16*)xb, ldb, w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope,
+           (__nv_bfloat16*)y, ldy, pre);
+  return 0;
+}
+
+static int make_prebn(const dcv_geom* g, const dcv_prebn* pre, PreBn* out) {
+  memset(out, 0, sizeof(*out));
+  out->half = -1;
+  if (!pre) return 0;
+  DCV_REQUIRE(pre->mean && pre->invstd && (!pre->gamma == !pre->beta), "pre-BN: null statistics / gamma without beta");
+  DCV_REQUIRE(pre->count == 64 && pre->c0 % 64 == 0 && pre->c0 >= 0 && pre->c0 + 64 <= g->Cs,
+              "pre-BN: channels [%d, %d) are not a 64-channel half of the %d-channel input", pre->c0, pre->c0 + pre->count, g->Cs);
+  DCV_REQUIRE(pre->slope >= 0.f, "pre-BN: negative LeakyReLU slope");
+  out->mean = pre->mean; out->invstd = pre->invstd; out->gamma = pre->gamma; out->beta = pre->beta;
+  out->half = pre->c0 / 64; out->slope = pre->slope;
   return 0;
 }
 
 int img_conv_scatter(const dcv_geom* g, const void* xb, int64_t ldb, const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, void* y,
-                     int64_t ldy, int act, float slope, cudaStream_t s) {
+                     int64_t ldy, int act, float slope, const dcv_prebn* prebn, cudaStream_t s) {
+  PreBn pre;
+  if (int prc = make_prebn(g, prebn, &pre)) return prc;
   DCV_REQUIRE(img_conv_supported_for(g, 3), "img_conv_scatter: geometry not supported");
   DCV_REQUIRE(s_tap == 1, "img_conv_scatter: taps of the master weight must be contiguous");
   DCV_REQUIRE((((uintptr_t)xb) & 15) == 0 && ldb % 8 == 0, "img_conv_scatter: input must be 16-byte aligned");
   const int C = g->wCl > 0 ? g->wCl : g->Cl;
   const int blocks = img_conv_bwd_blocks(g);
   int rc = -1;
-#define DCV_IMG_SC(C_, N_) if (C == C_ && g->Cs == N_) rc = launch_scatter<C_, N_>(g, blocks, xb, ldb, w, s_l, s_s, act, slope, y, ldy, s);
+#define DCV_IMG_SC(C_, N_) if (C == C_ && g->Cs == N_ && pre.half < 0) rc = launch_scatter<C_, N_>(g, blocks, xb, ldb, w, s_l, s_s, act, slope, y, ldy, pre, s);
   DCV_IMG_SC(1, 64) DCV_IMG_SC(2, 64) DCV_IMG_SC(3, 64) DCV_IMG_SC(1, 128) DCV_IMG_SC(2, 128) DCV_IMG_SC(3, 128)
 #undef DCV_IMG_SC
+  if (pre.half >= 0 && C == 3 && g->Cs == 128) rc = launch_scatter<3, 128, true>(g, blocks, xb, ldb, w, s_l, s_s, act, slope, y, ldy, pre, s);
   DCV_REQUIRE(rc != -1, "img_conv_scatter: no kernel for C %d, %d channels", C, g->Cs);
   if (rc) return rc;
   return check_launch("img_conv3x3_scatter");
@@ -560,8 +639,11 @@ int img_conv_scatter(const dcv_geom* g, const void* xb, int64_t ldb, const float
 
 int img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x, int64_t ldx,
                  const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, int act, float slope, float* dw, int accumulate,
-                 void* dx, int64_t lddx, void* ws, int64_t ws_bytes, cudaStream_t s) {
+                 void* dx, int64_t lddx, void* ws, int64_t ws_bytes, const dcv_prebn* prebn, cudaStream_t s) {
   const bool dgrad = dx != nullptr;
+  PreBn pre;
+  if (int prc = make_prebn(g, prebn, &pre)) return prc;
+  DCV_REQUIRE(pre.half < 0 || (!dgrad && act == DCV_ACT_NONE), "img_conv_bwd: pre-BN is for the weight-gradient-only pass without activation");
   DCV_REQUIRE(img_conv_supported_for(g, dgrad ? 1 : 2), "img_conv_bwd: geometry not supported");
   DCV_REQUIRE(s_tap == 1, "img_conv_bwd: taps of the master weight must be contiguous");
   DCV_REQUIRE(act == DCV_ACT_NONE || act == DCV_ACT_LEAKY, "img_conv_bwd: activation %d", act);
@@ -574,10 +656,12 @@ int img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a,
   const int smem = bwd_smem_bytes(C, g->Wl, dgrad);
   float* partial = dw ? (float*)ws : nullptr;
   int rc = -1;
-#define DCV_IMG_BWD(C_, N_, D_) if (C == C_ && g->Cs == N_ && dgrad == D_) rc = launch_bwd<C_, N_, D_>(g, blocks, smem, da, ldda, a, lda, x, ldx, w, s_l, s_s, act, slope, partial, dx, lddx, s);
+#define DCV_IMG_BWD(C_, N_, D_) if (C == C_ && g->Cs == N_ && dgrad == D_ && pre.half < 0) rc = launch_bwd<C_, N_, D_>(g, blocks, smem, da, ldda, a, lda, x, ldx, w, s_l, s_s, act, slope, partial, dx, lddx, pre, s);
   DCV_IMG_BWD(1, 64, true) DCV_IMG_BWD(2, 64, true)
   DCV_IMG_BWD(1, 64, false) DCV_IMG_BWD(2, 64, false) DCV_IMG_BWD(3, 64, false) DCV_IMG_BWD(1, 128, false) DCV_IMG_BWD(2, 128, false) DCV_IMG_BWD(3, 128, false)
 #undef DCV_IMG_BWD
+  if (pre.half >= 0 && C == 3 && g->Cs == 128 && !dgrad)
+    rc = launch_bwd<3, 128, false, true>(g, blocks, smem, da, ldda, a, lda, x, ldx, w, s_l, s_s, act, slope, partial, dx, lddx, pre, s);
   DCV_REQUIRE(rc != -1, "img_conv_bwd: no kernel for C %d, %d channels, dgrad %d", C, g->Cs, (int)dgrad);
   if (rc) return rc;
   if (int r2 = check_launch("img_conv3x3_bwd")) return r2;

@@ -183,6 +183,9 @@ def invalidate_packed(params):
             WCACHE.pop(id(p), None)
 
 
+DEFER_BN = os.environ.get("DCV_NO_DEFER_BN", "0") != "1"    # cgen up_blocks.5: BatchNorm + ReLU applied by Outconv's kernels on load
+
+
 # ------------------------------------------------------------------------------------------ one layer group
 class Block:
     """[Noise] -> conv -> [BatchNorm] -> [Dropout2d] -> activation, with its backward.
@@ -195,29 +198,42 @@ class Block:
         self.act, self.slope, self.dropout = act, slope, dropout
         self.noise = noise  # None or (use_noise, sigma)
 
-    def forward(self, x, out, training, rng_, save=True, loss=None):
+    def img_scatter_paths_ok(self, x, out):
+        """True when forward and weight gradient of this (BatchNorm-free, transposed) layer run on the image-side kernels, which
+        can apply a producer's deferred BatchNorm while they load x"""
+        spec = self.spec
+        if self.bn is not None or spec.kind != "convT" or (self.noise is not None and self.noise[0]):
+            return False
+        g = spec.geom(x.n, x.spatial, x.cp, out.cp)
+        return ops.img_conv_ok(spec, g, ops.IMG_SCATTER, out, x) and ops.img_conv_ok(spec, g, ops.IMG_WGRAD, out, x)
+
+    def forward(self, x, out, training, rng_, save=True, loss=None, defer_bn=False, pre=None):
         """x: input Act; out: Act (slice) that receives the block's output.  Returns ctx for backward.
         loss (heads only): {'kind', 'out' (1-element fp32 tensor), 'accumulate', 'want_grad'} - the adversarial-loss term of
-        this head is computed in the head's own launch; ctx['dlogits'] then holds dL/dlogits (or None)."""
+        this head is computed in the head's own launch; ctx['dlogits'] then holds dL/dlogits (or None).
+        defer_bn: leave the PRE-BatchNorm convolution output z in `out` and return the normalisation in ctx['pre'] - the only
+        consumer (Outconv) applies BatchNorm + ReLU while it loads the tensor, so the normalise pass over it never runs.
+        pre: such a deferred normalisation of channels [c0, c0 + 64) of x (image-side kernels only)."""
         spec = self.spec
         w = self.conv.weight
         x_used = x
         if self.noise is not None and self.noise[0]:
             x_used = x.like()
             ops.add_noise(x, rng_.noise_for(x), float(self.noise[1]), x_used)
-        z = out if self.bn is None else Act.empty(out.n, out.t, out.h, out.w, out.c, out.dtype)
+        z = out if (self.bn is None or defer_bn) else Act.empty(out.n, out.t, out.h, out.w, out.c, out.dtype)
         # geometry over the zero-padded channel counts of both buffers (dcv_geom.wCl/wCs carry the real ones)
         cin_p, cout_p = x_used.cp, z.cp
         g = spec.geom(x.n, x.spatial, cin_p, cout_p)
-        ctx = {"g": g, "x": x_used if save else None, "a": out, "cin_p": cin_p, "cout_p": cout_p}
+        ctx = {"g": g, "x": x_used if save else None, "a": out, "cin_p": cin_p, "cout_p": cout_p, "pre_in": pre}
         if (self.bn is None and spec.kind == "conv" and self.act in (ACT_NONE, ACT_LEAKY) and ops.img_conv_ok(spec, g, ops.IMG_FWD, x_used, out)
                 and ops.img_conv_ok(spec, g, ops.IMG_BWD, x_used, out)):
             ops.img_conv_fwd(spec, g, x_used, w, out, self.act, self.slope)       # Inconv: HBM-bound mma.sync kernel
             ctx["img"] = True
             return ctx
         if self.bn is None and spec.kind == "convT" and ops.img_conv_ok(spec, g, ops.IMG_SCATTER, out, x_used):
-            ops.img_conv_scatter(spec, g, x_used, w, out, self.act, self.slope)    # Outconv: one pass over the 128-channel input
+            ops.img_conv_scatter(spec, g, x_used, w, out, self.act, self.slope, pre)    # Outconv: one pass over the 128-channel input
             return ctx
+        assert pre is None, "a deferred BatchNorm needs the image-side kernels of its consumer"
         impl = ops.choose_conv_impl(g, spec.fwd_dir, x_used)
         wp = packed_weight(spec, g, spec.fwd_dir, impl, w)
         if self.bn is None:
@@ -247,6 +263,12 @@ class Block:
                 mean, invstd = ops.bn_batch_stats(z, BN_EPS, BN_MOM, bn.running_mean, bn.running_var, bn.num_batches_tracked)
             else:
                 mean, invstd = ops.bn_eval_stats(bn.running_mean, bn.running_var, BN_EPS)
+        if defer_bn:
+            assert not self.dropout and self.act == ACT_LEAKY
+            ctx["pre"] = {"mean": mean, "invstd": invstd, "gamma": bn.weight.detach(), "beta": bn.bias.detach(), "slope": self.slope}
+            if save:
+                ctx.update(z=z, mean=mean, invstd=invstd, drop=None, training=training)
+            return ctx
         drop = rng_.dropout_scale(z.n, z.c) if (self.dropout and training) else None
         ops.bn_act(z, mean, invstd, bn.weight.detach(), bn.bias.detach(), drop, self.act, self.slope, out)
         if save:
@@ -317,7 +339,9 @@ class Block:
             xp = ctx["x"].padded_to(cin_p)
             xl, xs = (xp, dzp) if spec.kind == "conv" else (dzp, xp)
             if img and ops.img_conv_ok(spec, g, ops.IMG_WGRAD, dz, ctx["x"]):
-                ops.img_conv_bwd(spec, g, ctx["x"], None, dz, self.conv.weight, ACT_NONE, 0.0, dw, acc, None)
+                ops.img_conv_bwd(spec, g, ctx["x"], None, dz, self.conv.weight, ACT_NONE, 0.0, dw, acc, None, ctx.get("pre_in"))
+            elif ctx.get("pre_in") is not None:
+                raise RuntimeError("a deferred BatchNorm needs the image-side weight-gradient kernel of its consumer")
             else:
                 ops.wgrad(spec, g, xl, xs, dw, accumulate=acc)
         if dx_out is not None:
@@ -563,11 +587,15 @@ class CGenPlan:
         zc = cats[0].ch(first[0], cats[0].c)                                     # generator.py:393
         zc.rows2d().copy_(z)
         uctx = []
+        out = Act.empty(N, 1, 64, 64, 3, dtype)
+        # up_blocks.5's BatchNorm + ReLU output is read by Outconv only: leave the convolution output in the concat buffer and let
+        # Outconv's kernels normalise on load (no bn_act pass over the 64x64x64 tensor; bit-identical operands)
+        defer = DEFER_BN and dtype == torch.bfloat16 and first[6] == 64 and self.outconv.img_scatter_paths_ok(cats[6], out)
         for i in range(6):
             dst = cats[i + 1].ch(0, first[i + 1])
-            uctx.append(self.up[i].forward(cats[i], dst, training, rng_, save))
-        out = Act.empty(N, 1, 64, 64, 3, dtype)
-        ctx["outconv"] = self.outconv.forward(cats[6], out, training, rng_, save)
+            uctx.append(self.up[i].forward(cats[i], dst, training, rng_, save, defer_bn=(defer and i == 5)))
+        pre = dict(uctx[5]["pre"], c0=0) if defer else None
+        ctx["outconv"] = self.outconv.forward(cats[6], out, training, rng_, save, pre=pre)
         ctx.update(down=dctx, up=uctx)
         return out, (ctx if save else None)
 

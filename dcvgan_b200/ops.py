@@ -450,17 +450,29 @@ def img_conv_fwd(spec, g, x, weight, y, act, slope):
     check(lib().dcv_img_conv_fwd(C.byref(g), x.ptr, x.ld, w.data_ptr(), s_l, s_s, s_tap, y.ptr, y.ld, act, slope, _stream()))
 
 
-def img_conv_scatter(spec, g, xb, weight, y, act, slope):
-    """y (the small L tensor) = act(transposed correlation of xb (the 64 / 128-channel S tensor) with w): Outconv forward"""
+def make_prebn(pre):
+    """pre: None or dict(mean, invstd, gamma, beta, c0, slope) -> (ctypes struct or None, tensors to keep alive)"""
+    if pre is None:
+        return None, ()
+    keep = (pre["mean"], pre["invstd"], pre["gamma"], pre["beta"])
+    st = _lib.PreBn(pre["mean"].data_ptr(), pre["invstd"].data_ptr(), _p(pre["gamma"]), _p(pre["beta"]), int(pre["c0"]), 64,
+                    float(pre["slope"]))
+    return C.byref(st), keep + (st,)
+
+
+def img_conv_scatter(spec, g, xb, weight, y, act, slope, pre=None):
+    """y (the small L tensor) = act(transposed correlation of xb (the 64 / 128-channel S tensor) with w): Outconv forward.
+    pre: the channels [c0, c0 + 64) of xb hold a pre-BatchNorm tensor, normalised + activated on load (dcv_prebn)"""
     if TRACE is not None:
         TRACE.append(("img_conv_scatter", g.key(), 0, -1, xb.ld, y.ld, xb.c, y.c))
     s_l, s_s, s_tap = spec.weight_strides()
     w = weight.detach()
     assert w.is_contiguous() and w.dtype == torch.float32
-    check(lib().dcv_img_conv_scatter(C.byref(g), xb.ptr, xb.ld, w.data_ptr(), s_l, s_s, s_tap, y.ptr, y.ld, act, slope, _stream()))
+    pp, _keep = make_prebn(pre)
+    check(lib().dcv_img_conv_scatter(C.byref(g), xb.ptr, xb.ld, w.data_ptr(), s_l, s_s, s_tap, y.ptr, y.ld, act, slope, pp, _stream()))
 
 
-def img_conv_bwd(spec, g, da, a, x, weight, act, slope, dw, accumulate, dx):
+def img_conv_bwd(spec, g, da, a, x, weight, act, slope, dw, accumulate, dx, pre=None):
     """dw (fp32, master layout, or None) and dx (Act for the small L tensor, or None) in one pass over da (gradient w.r.t.
     the activated S tensor) and a (the activated S tensor; None with ACT_NONE); x is the small L tensor"""
     if TRACE is not None:
@@ -470,9 +482,10 @@ def img_conv_bwd(spec, g, da, a, x, weight, act, slope, dw, accumulate, dx):
     nbytes = lib().dcv_img_conv_bwd_workspace_bytes(C.byref(g))
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=w.device)
     ap, lda = (da.ptr, da.ld) if a is None else (a.ptr, a.ld)
+    pp, _keep = make_prebn(pre)
     check(lib().dcv_img_conv_bwd(C.byref(g), da.ptr, da.ld, ap, lda, x.ptr, x.ld, w.data_ptr(), s_l, s_s, s_tap, act, slope,
                                  _p(dw), int(accumulate), None if dx is None else dx.ptr, 0 if dx is None else dx.ld,
-                                 ws.data_ptr(), nbytes, _stream()))
+                                 ws.data_ptr(), nbytes, pp, _stream()))
 
 
 # ------------------------------------------------------------------------------------ BatchNorm & friends

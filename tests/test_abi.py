@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(str(_lib.LIB_PATH))
     for n in names:
         assert getattr(handle, n) is not None
-    assert _lib.lib().dcv_abi_version() == _lib.ABI_VERSION == 4
+    assert _lib.lib().dcv_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_geom_struct_matches_header():

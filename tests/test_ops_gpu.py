@@ -344,6 +344,41 @@ def test_img_conv_outconv_backward(n, hw):
     assert e_fwd < 5e-3 and e_dx < 5e-3 and e_dw < 5e-3 and e_dw2 < 5e-3
 
 
+@pytest.mark.parametrize("n,hw,gamma", [(2, (64, 64), True), (3, (8, 32), True), (2, (16, 16), False)])
+def test_outconv_batchnorm_on_load(n, hw, gamma):
+    """dcv_prebn: Outconv's forward and weight-gradient kernels normalise + ReLU the first 64 channels of their 128-channel
+    input while loading it.  Against the materialised form (dcv_bn_act into a copy of the buffer, then the same kernels):
+    bit-identical output and weight gradient; the second half (the Inconv skip, negative values included) is untouched."""
+    ops = _ops()
+    from dcvgan_b200._lib import ACT_LEAKY, ACT_NONE, ACT_TANH
+    torch.manual_seed(90 + n)
+    H, W = hw
+    spec = ops.ConvSpec("convT", 128, 3, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+    cat = to_act(bf16_round(torch.randn(n, 128, 1, H, W) * 1.5 + 0.2), torch.bfloat16)      # [z of up_blocks.5 | skip]
+    z = cat.ch(0, 64)
+    mean, invstd = (torch.randn(64) * 0.3).cuda(), (torch.rand(64) + 0.5).cuda()
+    gd, bd = ((torch.randn(64) * 0.2 + 1).cuda(), (torch.randn(64) * 0.2).cuda()) if gamma else (None, None)
+    mat = cat.like()
+    mat.base.copy_(cat.base)
+    ops.bn_act(z, mean, invstd, gd, bd, None, ACT_LEAKY, 0.0, mat.ch(0, 64))
+    assert float(from_act(mat)[:, 64:].min()) < 0 and float(from_act(mat)[:, :64].min()) == 0.0
+    pre = {"mean": mean, "invstd": invstd, "gamma": gd, "beta": bd, "c0": 0, "slope": 0.0}
+    wdev = (torch.randn(128, 3, 3, 3) * 0.05).cuda()
+    y0, y1 = ops.Act.empty(n, 1, H, W, 3, torch.bfloat16), ops.Act.empty(n, 1, H, W, 3, torch.bfloat16)
+    g = spec.geom(n, (1, H, W), cat.cp, y0.cp)
+    assert ops.img_conv_ok(spec, g, ops.IMG_SCATTER, y0, cat) and ops.img_conv_ok(spec, g, ops.IMG_WGRAD, y0, cat)
+    ops.img_conv_scatter(spec, g, mat, wdev, y0, ACT_TANH, 0.0)
+    ops.img_conv_scatter(spec, g, cat, wdev, y1, ACT_TANH, 0.0, pre)
+    dz = to_act(bf16_round(torch.randn(n, 3, 1, H, W)), torch.bfloat16)
+    dw0, dw1 = torch.empty_like(wdev), torch.empty_like(wdev)
+    ops.img_conv_bwd(spec, g, mat, None, dz, wdev, ACT_NONE, 0.0, dw0, False, None)
+    ops.img_conv_bwd(spec, g, cat, None, dz, wdev, ACT_NONE, 0.0, dw1, False, None, pre)
+    torch.cuda.synchronize()
+    assert torch.equal(y0.base, y1.base)
+    assert torch.equal(dw0, dw1)
+    assert float(dw0.abs().max()) > 0 and float(y0.base.float().abs().max()) > 0
+
+
 @pytest.mark.parametrize("kind", [0, 1, 2, 3, 4])
 def test_head_with_fused_loss_term(kind):
     """dcv_head_loss (discriminator head + its adversarial-loss term + dL/dlogits in one launch) against the two-launch form
