@@ -57,7 +57,7 @@ SIGNATURES = {
     "dcv_img_conv_bwd_workspace_bytes": (_i64, [_G]),
     "dcv_img_conv_fwd": (_i, [_G, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i, _f, _vp]),
     "dcv_img_conv_scatter": (_i, [_G, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i, _f, _vp, _vp]),
-    "dcv_img_conv_bwd": (_i, [_G, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i, _f, _vp, _i, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "dcv_img_conv_bwd": (_i, [_G, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i, _f, _vp, _i, _vp, _i64, _vp, _i64, _vp]),
     "dcv_packed_weight_bytes": (_i64, [_G, _i, _i]),
     "dcv_pack_weight": (_i, [_G, _i, _i, _vp, _i64, _i64, _i64, _vp, _vp]),
     "dcv_pack_weight_batch": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -46,7 +46,7 @@ int img_conv_scatter(const dcv_geom*, const void*, int64_t, const float*, int64_
 int64_t img_conv_bwd_ws_bytes(const dcv_geom*);
 int img_conv_fwd(const dcv_geom*, const void*, int64_t, const float*, int64_t, int64_t, int64_t, void*, int64_t, int, float, cudaStream_t);
 int img_conv_bwd(const dcv_geom*, const void*, int64_t, const void*, int64_t, const void*, int64_t, const float*, int64_t, int64_t,
-                 int64_t, int, float, float*, int, void*, int64_t, void*, int64_t, const dcv_prebn*, cudaStream_t);
+                 int64_t, int, float, float*, int, void*, int64_t, void*, int64_t, cudaStream_t);
 int pack_weight_tc_multi(const dcv_geom*, int, int, const float* const*, const int64_t*, const int64_t*, const int64_t*, const int*,
                          const int*, const int*, const int*, void*, cudaStream_t);
 int pack_weight_tc_batch(int, const dcv_geom* const*, const int*, const float* const*, const int64_t*, const int64_t*, const int64_t*,
@@ -109,10 +109,10 @@ int dcv_img_conv_scatter(const dcv_geom* g, const void* xb, int64_t ldb, const f
 }
 int dcv_img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x, int64_t ldx,
                      const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, int act, float slope, float* dw, int accumulate,
-                     void* dx, int64_t lddx, void* ws, int64_t ws_bytes, const dcv_prebn* pre, void* stream) {
+                     void* dx, int64_t lddx, void* ws, int64_t ws_bytes, void* stream) {
   if (int rc = check_geom(g)) return rc;
   DCV_REQUIRE(da && a && x && w && ws, "img_conv_bwd: null pointer");
-  return img_conv_bwd(g, da, ldda, a, lda, x, ldx, w, s_l, s_s, s_tap, act, slope, dw, accumulate, dx, lddx, ws, ws_bytes, pre,
+  return img_conv_bwd(g, da, ldda, a, lda, x, ldx, w, s_l, s_s, s_tap, act, slope, dw, accumulate, dx, lddx, ws, ws_bytes,
                       as_stream(stream));
 }
 

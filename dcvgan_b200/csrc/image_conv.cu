@@ -43,9 +43,12 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 // ---- BatchNorm + (Leaky)ReLU applied on load ("pre-BN") ------------------------------------------------------------------
 // The 128-channel input of Outconv is the concat [up_blocks.5 output | Inconv skip] (generator.py:401-402).  Its first half is
 // BatchNorm + ReLU of a convolution output z; materialising a = relu(bn(z)) costs a pass that reads and writes the 268 MB
-// tensor (bn_act, 0.09 ms at batch 32, twice per iteration).  With a PreBn the kernels below read z itself from that half of
-// the concat buffer and apply a = act(z * P + Q), P = invstd * gamma, Q = beta - mean * invstd * gamma, rounded to bf16 - the
+// tensor (bn_act, 0.09 ms at batch 32).  With a PreBn the scatter kernel (Outconv forward) reads z itself from that half of
+// the concat buffer and applies a = act(z * P + Q), P = invstd * gamma, Q = beta - mean * invstd * gamma, rounded to bf16 - the
 // arithmetic and rounding of bn_act_bf16_kernel, so the operand the MMAs see is bit-identical to the materialised tensor.
+// Used for forward passes that are not differentiated (the fake batch of the D-phase, sampling): the weight-gradient kernel
+// with the same transform measured 0.33 ms against 0.19 + 0.09 ms for bn_act + the plain kernel, so when a backward pass
+// follows the tensor is materialised as before.
 struct PreBn {
   const float* mean; const float* invstd; const float* gamma; const float* beta;   // [64] each; gamma / beta may be NULL
   int half;                                                                        // 64-channel half of the input they apply to
@@ -201,14 +204,13 @@ __device__ __forceinline__ int slot_channel(int s, int sigma) {
 
 // NCO = channels of the big tensor (64; 128 = weight gradient only, the two channel halves are owned by warps 0-3 / 4-7),
 // DGRAD: also form the data gradient dx
-template <int C, int NCO, bool DGRAD, bool PRE = false>
+template <int C, int NCO, bool DGRAD>
 __global__ void __launch_bounds__(256, 2)
 img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const __nv_bfloat16* __restrict__ a, int64_t lda,
                        const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t s_l, int64_t s_s,
                        int N, int H, int W, int act, float slope, float* __restrict__ partial, __nv_bfloat16* __restrict__ dx,
-                       int64_t lddx, const PreBn pre) {
+                       int64_t lddx) {
   pdl_wait(); pdl_trigger();
-  static_assert(!PRE || !DGRAD, "pre-BN is for the weight-gradient-only pass (the streamed tensor is the layer input)");
   constexpr int NT = 9 * C;                    // (tap, ci) pairs
   constexpr int NJ = (NT + 7) / 8;             // n8 tiles over them
   constexpr int NP = NJ * 8 + 8;               // row length of P: 8 floats of padding keep the float2 fragment stores conflict-free
@@ -223,24 +225,6 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
   const int half = warp / WPH, wsub = warp % WPH;
   const int bands = H / IMG_BAND;
   const int WP = W + 2;
-  // pre-BN coefficients live in shared memory here ((P, Q) of a channel pair per float4): 32 more registers per thread would
-  // cost this kernel its second block per SM
-  __shared__ float4 prePQ[PRE ? 32 : 1];
-  const bool pre_on = PRE && half == pre.half;
-  if constexpr (PRE) {
-    if (threadIdx.x < 32) {
-      float v[4];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = 2 * (int)threadIdx.x + e;
-        const float is = pre.invstd[c], mu = pre.mean[c];
-        const float gm = pre.gamma ? pre.gamma[c] : 1.f, bt = pre.gamma ? pre.beta[c] : 0.f;
-        v[2 * e] = is * gm; v[2 * e + 1] = bt - mu * is * gm;
-      }
-      prePQ[threadIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
-    }
-    __syncthreads();
-  }
   // B fragments of the data-gradient GEMM: B[k slot][nn] = w[co(s, slot)][ci][tap], nn = tap*C + ci (0 beyond 9*C)
   uint32_t bw[DGRAD ? 4 : 1][NJ][2];
   if (DGRAD) {
@@ -295,14 +279,6 @@ img_conv3x3_bwd_kernel(const __nv_bfloat16* __restrict__ da, int64_t ldda, const
 #pragma unroll
         for (int p = 0; p < 8; ++p) {          // value pair i = 2p, 2p+1  ->  step s = p / 2, column half = p % 2
           uint32_t v = dw_[p];
-          if constexpr (PRE) {
-            if (pre_on) {                        // word p = channel pair (p < 4 ? 8q + 2p : 32 + 8q + 2(p - 4)) of this half
-              const float4 c4 = prePQ[p < 4 ? 4 * q + p : 16 + 4 * q + (p - 4)];
-              float f0 = fmaf(bf16_lo(v), c4.x, c4.y), f1 = fmaf(bf16_hi(v), c4.z, c4.w);
-              f0 = f0 > 0.f ? f0 : f0 * pre.slope; f1 = f1 > 0.f ? f1 : f1 * pre.slope;
-              v = pack_bf16x2(f0, f1);
-            }
-          }
           if (act != DCV_ACT_NONE) {
             const float g0 = act_grad_from_out(bf16_lo(ow_[p]), act, slope), g1 = act_grad_from_out(bf16_hi(ow_[p]), act, slope);
             v = pack_bf16x2(bf16_lo(v) * g0, bf16_hi(v) * g1);
@@ -576,17 +552,17 @@ int img_conv_fwd(const dcv_geom* g, const void* x, int64_t ldx, const float* w, 
   return check_launch("img_conv3x3_fwd");
 }
 
-template <int C, int NCO, bool DGRAD, bool PRE = false>
+template <int C, int NCO, bool DGRAD>
 static int launch_bwd(const dcv_geom* g, int blocks, int smem, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x,
                       int64_t ldx, const float* w, int64_t s_l, int64_t s_s, int act, float slope, float* partial, void* dx, int64_t lddx,
-                      const PreBn& pre, cudaStream_t s) {
+                      cudaStream_t s) {
   static int smem_set = 0;
   if (smem > smem_set) {
-    DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_bwd_kernel<C, NCO, DGRAD, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DCV_CUDA(cudaFuncSetAttribute(img_conv3x3_bwd_kernel<C, NCO, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_set = smem;
   }
-  launch_k(img_conv3x3_bwd_kernel<C, NCO, DGRAD, PRE>, blocks, 256, smem, s, (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda,
-           (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx, pre);
+  launch_k(img_conv3x3_bwd_kernel<C, NCO, DGRAD>, blocks, 256, smem, s, (const __nv_bfloat16*)da, ldda, (const __nv_bfloat16*)a, lda,
+           (const __nv_bfloat16*)x, ldx, w, s_l, s_s, g->N, g->Hl, g->Wl, act, slope, partial, (__nv_bfloat16*)dx, lddx);
   return 0;
 }
 
@@ -639,11 +615,8 @@ int img_conv_scatter(const dcv_geom* g, const void* xb, int64_t ldb, const float
 
 int img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x, int64_t ldx,
                  const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, int act, float slope, float* dw, int accumulate,
-                 void* dx, int64_t lddx, void* ws, int64_t ws_bytes, const dcv_prebn* prebn, cudaStream_t s) {
+                 void* dx, int64_t lddx, void* ws, int64_t ws_bytes, cudaStream_t s) {
   const bool dgrad = dx != nullptr;
-  PreBn pre;
-  if (int prc = make_prebn(g, prebn, &pre)) return prc;
-  DCV_REQUIRE(pre.half < 0 || (!dgrad && act == DCV_ACT_NONE), "img_conv_bwd: pre-BN is for the weight-gradient-only pass without activation");
   DCV_REQUIRE(img_conv_supported_for(g, dgrad ? 1 : 2), "img_conv_bwd: geometry not supported");
   DCV_REQUIRE(s_tap == 1, "img_conv_bwd: taps of the master weight must be contiguous");
   DCV_REQUIRE(act == DCV_ACT_NONE || act == DCV_ACT_LEAKY, "img_conv_bwd: activation %d", act);
@@ -656,12 +629,10 @@ int img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a,
   const int smem = bwd_smem_bytes(C, g->Wl, dgrad);
   float* partial = dw ? (float*)ws : nullptr;
   int rc = -1;
-#define DCV_IMG_BWD(C_, N_, D_) if (C == C_ && g->Cs == N_ && dgrad == D_ && pre.half < 0) rc = launch_bwd<C_, N_, D_>(g, blocks, smem, da, ldda, a, lda, x, ldx, w, s_l, s_s, act, slope, partial, dx, lddx, pre, s);
+#define DCV_IMG_BWD(C_, N_, D_) if (C == C_ && g->Cs == N_ && dgrad == D_) rc = launch_bwd<C_, N_, D_>(g, blocks, smem, da, ldda, a, lda, x, ldx, w, s_l, s_s, act, slope, partial, dx, lddx, s);
   DCV_IMG_BWD(1, 64, true) DCV_IMG_BWD(2, 64, true)
   DCV_IMG_BWD(1, 64, false) DCV_IMG_BWD(2, 64, false) DCV_IMG_BWD(3, 64, false) DCV_IMG_BWD(1, 128, false) DCV_IMG_BWD(2, 128, false) DCV_IMG_BWD(3, 128, false)
 #undef DCV_IMG_BWD
-  if (pre.half >= 0 && C == 3 && g->Cs == 128 && !dgrad)
-    rc = launch_bwd<3, 128, false, true>(g, blocks, smem, da, ldda, a, lda, x, ldx, w, s_l, s_s, act, slope, partial, dx, lddx, pre, s);
   DCV_REQUIRE(rc != -1, "img_conv_bwd: no kernel for C %d, %d channels, dgrad %d", C, g->Cs, (int)dgrad);
   if (rc) return rc;
   if (int r2 = check_launch("img_conv3x3_bwd")) return r2;

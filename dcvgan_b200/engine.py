@@ -183,7 +183,7 @@ def invalidate_packed(params):
             WCACHE.pop(id(p), None)
 
 
-DEFER_BN = os.environ.get("DCV_NO_DEFER_BN", "0") != "1"    # cgen up_blocks.5: BatchNorm + ReLU applied by Outconv's kernels on load
+DEFER_BN = os.environ.get("DCV_NO_DEFER_BN", "0") != "1"    # cgen up_blocks.5 without backward: BatchNorm + ReLU applied by Outconv on load
 
 
 # ------------------------------------------------------------------------------------------ one layer group
@@ -199,21 +199,21 @@ class Block:
         self.noise = noise  # None or (use_noise, sigma)
 
     def img_scatter_paths_ok(self, x, out):
-        """True when forward and weight gradient of this (BatchNorm-free, transposed) layer run on the image-side kernels, which
-        can apply a producer's deferred BatchNorm while they load x"""
+        """True when the forward of this (BatchNorm-free, transposed) layer runs on the image-side scatter kernel, which can apply
+        a producer's deferred BatchNorm while it loads x"""
         spec = self.spec
         if self.bn is not None or spec.kind != "convT" or (self.noise is not None and self.noise[0]):
             return False
         g = spec.geom(x.n, x.spatial, x.cp, out.cp)
-        return ops.img_conv_ok(spec, g, ops.IMG_SCATTER, out, x) and ops.img_conv_ok(spec, g, ops.IMG_WGRAD, out, x)
+        return ops.img_conv_ok(spec, g, ops.IMG_SCATTER, out, x)
 
     def forward(self, x, out, training, rng_, save=True, loss=None, defer_bn=False, pre=None):
         """x: input Act; out: Act (slice) that receives the block's output.  Returns ctx for backward.
         loss (heads only): {'kind', 'out' (1-element fp32 tensor), 'accumulate', 'want_grad'} - the adversarial-loss term of
         this head is computed in the head's own launch; ctx['dlogits'] then holds dL/dlogits (or None).
-        defer_bn: leave the PRE-BatchNorm convolution output z in `out` and return the normalisation in ctx['pre'] - the only
-        consumer (Outconv) applies BatchNorm + ReLU while it loads the tensor, so the normalise pass over it never runs.
-        pre: such a deferred normalisation of channels [c0, c0 + 64) of x (image-side kernels only)."""
+        defer_bn (forward passes that are not differentiated): leave the PRE-BatchNorm convolution output z in `out` and return
+        the normalisation in ctx['pre'] - the only consumer (Outconv) applies BatchNorm + ReLU while it loads the tensor, so the
+        normalise pass over it never runs.  pre: such a deferred normalisation of channels [c0, c0 + 64) of x."""
         spec = self.spec
         w = self.conv.weight
         x_used = x
@@ -224,7 +224,8 @@ class Block:
         # geometry over the zero-padded channel counts of both buffers (dcv_geom.wCl/wCs carry the real ones)
         cin_p, cout_p = x_used.cp, z.cp
         g = spec.geom(x.n, x.spatial, cin_p, cout_p)
-        ctx = {"g": g, "x": x_used if save else None, "a": out, "cin_p": cin_p, "cout_p": cout_p, "pre_in": pre}
+        ctx = {"g": g, "x": x_used if save else None, "a": out, "cin_p": cin_p, "cout_p": cout_p}
+        assert pre is None or not save, "a deferred BatchNorm is for forward passes that are not differentiated"
         if (self.bn is None and spec.kind == "conv" and self.act in (ACT_NONE, ACT_LEAKY) and ops.img_conv_ok(spec, g, ops.IMG_FWD, x_used, out)
                 and ops.img_conv_ok(spec, g, ops.IMG_BWD, x_used, out)):
             ops.img_conv_fwd(spec, g, x_used, w, out, self.act, self.slope)       # Inconv: HBM-bound mma.sync kernel
@@ -266,8 +267,6 @@ class Block:
         if defer_bn:
             assert not self.dropout and self.act == ACT_LEAKY
             ctx["pre"] = {"mean": mean, "invstd": invstd, "gamma": bn.weight.detach(), "beta": bn.bias.detach(), "slope": self.slope}
-            if save:
-                ctx.update(z=z, mean=mean, invstd=invstd, drop=None, training=training)
             return ctx
         drop = rng_.dropout_scale(z.n, z.c) if (self.dropout and training) else None
         ops.bn_act(z, mean, invstd, bn.weight.detach(), bn.bias.detach(), drop, self.act, self.slope, out)
@@ -339,9 +338,7 @@ class Block:
             xp = ctx["x"].padded_to(cin_p)
             xl, xs = (xp, dzp) if spec.kind == "conv" else (dzp, xp)
             if img and ops.img_conv_ok(spec, g, ops.IMG_WGRAD, dz, ctx["x"]):
-                ops.img_conv_bwd(spec, g, ctx["x"], None, dz, self.conv.weight, ACT_NONE, 0.0, dw, acc, None, ctx.get("pre_in"))
-            elif ctx.get("pre_in") is not None:
-                raise RuntimeError("a deferred BatchNorm needs the image-side weight-gradient kernel of its consumer")
+                ops.img_conv_bwd(spec, g, ctx["x"], None, dz, self.conv.weight, ACT_NONE, 0.0, dw, acc, None)
             else:
                 ops.wgrad(spec, g, xl, xs, dw, accumulate=acc)
         if dx_out is not None:
@@ -588,9 +585,11 @@ class CGenPlan:
         zc.rows2d().copy_(z)
         uctx = []
         out = Act.empty(N, 1, 64, 64, 3, dtype)
-        # up_blocks.5's BatchNorm + ReLU output is read by Outconv only: leave the convolution output in the concat buffer and let
-        # Outconv's kernels normalise on load (no bn_act pass over the 64x64x64 tensor; bit-identical operands)
-        defer = DEFER_BN and dtype == torch.bfloat16 and first[6] == 64 and self.outconv.img_scatter_paths_ok(cats[6], out)
+        # up_blocks.5's BatchNorm + ReLU output is read by Outconv only: when no backward pass follows (the fake batch of the
+        # D-phase, sampling) leave the convolution output in the concat buffer and let Outconv's kernel normalise on load (no
+        # bn_act pass over the 64x64x64 tensor; bit-identical operands)
+        defer = (DEFER_BN and not save and dtype == torch.bfloat16 and first[6] == 64
+                 and self.outconv.img_scatter_paths_ok(cats[6], out))
         for i in range(6):
             dst = cats[i + 1].ch(0, first[i + 1])
             uctx.append(self.up[i].forward(cats[i], dst, training, rng_, save, defer_bn=(defer and i == 5)))

@@ -472,7 +472,7 @@ def img_conv_scatter(spec, g, xb, weight, y, act, slope, pre=None):
     check(lib().dcv_img_conv_scatter(C.byref(g), xb.ptr, xb.ld, w.data_ptr(), s_l, s_s, s_tap, y.ptr, y.ld, act, slope, pp, _stream()))
 
 
-def img_conv_bwd(spec, g, da, a, x, weight, act, slope, dw, accumulate, dx, pre=None):
+def img_conv_bwd(spec, g, da, a, x, weight, act, slope, dw, accumulate, dx):
     """dw (fp32, master layout, or None) and dx (Act for the small L tensor, or None) in one pass over da (gradient w.r.t.
     the activated S tensor) and a (the activated S tensor; None with ACT_NONE); x is the small L tensor"""
     if TRACE is not None:
@@ -482,10 +482,9 @@ def img_conv_bwd(spec, g, da, a, x, weight, act, slope, dw, accumulate, dx, pre=
     nbytes = lib().dcv_img_conv_bwd_workspace_bytes(C.byref(g))
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=w.device)
     ap, lda = (da.ptr, da.ld) if a is None else (a.ptr, a.ld)
-    pp, _keep = make_prebn(pre)
     check(lib().dcv_img_conv_bwd(C.byref(g), da.ptr, da.ld, ap, lda, x.ptr, x.ld, w.data_ptr(), s_l, s_s, s_tap, act, slope,
                                  _p(dw), int(accumulate), None if dx is None else dx.ptr, 0 if dx is None else dx.ld,
-                                 ws.data_ptr(), nbytes, pp, _stream()))
+                                 ws.data_ptr(), nbytes, _stream()))
 
 
 # ------------------------------------------------------------------------------------ BatchNorm & friends

@@ -239,11 +239,12 @@ int dcv_col2im_act(int dtype, const void* P, int64_t ldp, int N, int Ih, int Iw,
  * dcv_img_conv_bwd:  one pass over da (gradient w.r.t. the activated S tensor) and a (the activated S tensor; unused for
  *   ACT_NONE): applies the activation derivative (NONE / LEAKY), writes the weight gradient to dw (accumulate: +=;
  *   dw == NULL: skipped) and the data gradient w.r.t. x to dx (NULL: skipped).  ws: dcv_img_conv_bwd_workspace_bytes(g). */
-/* BatchNorm + (Leaky)ReLU applied on load ("pre-BN", NULL = off): the 64 channels [c0, c0 + 64) of the 128-channel input of
- * dcv_img_conv_scatter (xb) / of the weight-gradient-only dcv_img_conv_bwd (da, with act = NONE and dx = NULL) hold the
- * PRE-BatchNorm convolution output z of the producing block (cgen up_blocks.5, generator.py:239-248), and the kernels use
- * a = leaky_relu(((z - mean) * invstd) * gamma + beta, slope) rounded to bf16 - exactly what dcv_bn_act would have written, minus
- * the pass over the tensor.  mean / invstd / gamma / beta: fp32 [64] (gamma and beta may both be NULL). */
+/* BatchNorm + (Leaky)ReLU applied on load ("pre-BN", NULL = off): the 64 channels [c0, c0 + 64) of the 128-channel input xb of
+ * dcv_img_conv_scatter hold the PRE-BatchNorm convolution output z of the producing block (cgen up_blocks.5,
+ * generator.py:239-248), and the kernel uses a = leaky_relu(((z - mean) * invstd) * gamma + beta, slope) rounded to bf16 -
+ * exactly what dcv_bn_act would have written, minus the pass over the tensor.  For forward passes that are not differentiated
+ * (the fake batch of the D-phase, trainer.py:303-309; sampling).  mean / invstd / gamma / beta: fp32 [64] (gamma and beta
+ * may both be NULL). */
 typedef struct dcv_prebn {
   const float* mean; const float* invstd; const float* gamma; const float* beta;
   int c0, count;      /* count must be 64, c0 a multiple of 64 */
@@ -257,7 +258,7 @@ int dcv_img_conv_scatter(const dcv_geom* g, const void* xb, int64_t ldb, const f
                          void* y, int64_t ldy, int act, float slope, const dcv_prebn* pre, void* stream);
 int dcv_img_conv_bwd(const dcv_geom* g, const void* da, int64_t ldda, const void* a, int64_t lda, const void* x, int64_t ldx,
                      const float* w, int64_t s_l, int64_t s_s, int64_t s_tap, int act, float slope, float* dw, int accumulate,
-                     void* dx, int64_t lddx, void* ws, int64_t ws_bytes, const dcv_prebn* pre, void* stream);
+                     void* dx, int64_t lddx, void* ws, int64_t ws_bytes, void* stream);
 /* w-tap folding for the image-like stem inputs of the discriminators (discriminator.py:79-90,180-193: conv_g on the
  * geometry channels, conv_c on the colour channels, kernel 4, stride 2, pad 1 along w):
  *   out[line][ow][k*(cg+cc) + c] = [xg | xc][line][ow*sw - pw + k][c]  (+ sigma*noise, the Noise layer), 0 outside the row

@@ -346,9 +346,9 @@ def test_img_conv_outconv_backward(n, hw):
 
 @pytest.mark.parametrize("n,hw,gamma", [(2, (64, 64), True), (3, (8, 32), True), (2, (16, 16), False)])
 def test_outconv_batchnorm_on_load(n, hw, gamma):
-    """dcv_prebn: Outconv's forward and weight-gradient kernels normalise + ReLU the first 64 channels of their 128-channel
-    input while loading it.  Against the materialised form (dcv_bn_act into a copy of the buffer, then the same kernels):
-    bit-identical output and weight gradient; the second half (the Inconv skip, negative values included) is untouched."""
+    """dcv_prebn: Outconv's forward kernel normalises + ReLUs the first 64 channels of its 128-channel input while loading it.
+    Against the materialised form (dcv_bn_act into a copy of the buffer, then the same kernel): bit-identical output; the
+    second half (the Inconv skip, negative values included) is untouched."""
     ops = _ops()
     from dcvgan_b200._lib import ACT_LEAKY, ACT_NONE, ACT_TANH
     torch.manual_seed(90 + n)
@@ -366,17 +366,12 @@ def test_outconv_batchnorm_on_load(n, hw, gamma):
     wdev = (torch.randn(128, 3, 3, 3) * 0.05).cuda()
     y0, y1 = ops.Act.empty(n, 1, H, W, 3, torch.bfloat16), ops.Act.empty(n, 1, H, W, 3, torch.bfloat16)
     g = spec.geom(n, (1, H, W), cat.cp, y0.cp)
-    assert ops.img_conv_ok(spec, g, ops.IMG_SCATTER, y0, cat) and ops.img_conv_ok(spec, g, ops.IMG_WGRAD, y0, cat)
+    assert ops.img_conv_ok(spec, g, ops.IMG_SCATTER, y0, cat)
     ops.img_conv_scatter(spec, g, mat, wdev, y0, ACT_TANH, 0.0)
     ops.img_conv_scatter(spec, g, cat, wdev, y1, ACT_TANH, 0.0, pre)
-    dz = to_act(bf16_round(torch.randn(n, 3, 1, H, W)), torch.bfloat16)
-    dw0, dw1 = torch.empty_like(wdev), torch.empty_like(wdev)
-    ops.img_conv_bwd(spec, g, mat, None, dz, wdev, ACT_NONE, 0.0, dw0, False, None)
-    ops.img_conv_bwd(spec, g, cat, None, dz, wdev, ACT_NONE, 0.0, dw1, False, None, pre)
     torch.cuda.synchronize()
     assert torch.equal(y0.base, y1.base)
-    assert torch.equal(dw0, dw1)
-    assert float(dw0.abs().max()) > 0 and float(y0.base.float().abs().max()) > 0
+    assert float(y0.base.float().abs().max()) > 0
 
 
 @pytest.mark.parametrize("kind", [0, 1, 2, 3, 4])
