@@ -37,3 +37,15 @@ def cos_sim(a, b):
 
 def bf16_round(x):
     return x.to(torch.bfloat16).float()
+
+
+def trainer_without_pickles(trainer_mod, *args):
+    """Trainer(*args) without the whole-module pickles of save_classobj (trainer.py:70-76: slow and irrelevant to these tests).
+    The class attribute is restored before returning, so later tests in the same process (the drop-in run of train.py checks
+    those very files) see the real method."""
+    orig = trainer_mod.Trainer.save_classobj
+    trainer_mod.Trainer.save_classobj = lambda self: None
+    try:
+        return trainer_mod.Trainer(*args)
+    finally:
+        trainer_mod.Trainer.save_classobj = orig

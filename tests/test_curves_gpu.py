@@ -33,6 +33,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import dcvgan_oracle as orc  # noqa: E402
+from helpers import trainer_without_pickles  # noqa: E402
 from test_nets_gpu import _Logger, _mods, build_models  # noqa: E402
 
 GOLD = Path(__file__).resolve().parent / "golden" / "curves_flow_hinge.json"
@@ -47,8 +48,7 @@ def _run(cfg, init, precision, steps, seed, tmp_path):
     opts = {k: torch.optim.Adam(m.parameters(), lr=cfg[k]["optimizer"]["lr"], betas=(0.5, 0.999),
                                 weight_decay=cfg[k]["optimizer"]["decay"]) for k, m in models.items()}
     L = loss_mod.AdversarialLoss() if cfg["loss"] == "adversarial-loss" else loss_mod.HingeLoss()
-    trainer_mod.Trainer.save_classobj = lambda self: None
-    tr = trainer_mod.Trainer(None, _Logger(tmp_path), models, opts, L, dict(cfg, config_path=""))
+    tr = trainer_without_pickles(trainer_mod, None, _Logger(tmp_path), models, opts, L, dict(cfg, config_path=""))
     pool = [tuple(t.cuda() for t in orc.synthetic_batch(cfg, cfg["batchsize"], 5000 + i)) for i in range(8)]
     torch.manual_seed(seed)
     np.random.seed(seed)

@@ -16,7 +16,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from helpers import rel_err  # noqa: E402
+from helpers import rel_err, trainer_without_pickles  # noqa: E402
 from oracle import dcvgan_oracle as orc  # noqa: E402
 from test_nets_gpu import _Logger, _mods, build_models, small_cfg  # noqa: E402
 
@@ -114,8 +114,7 @@ def _trainer(cfg, init, precision, tmp_path):
     opts = {k: torch.optim.Adam(m.parameters(), lr=cfg[k]["optimizer"]["lr"], betas=(0.5, 0.999),
                                 weight_decay=cfg[k]["optimizer"]["decay"]) for k, m in models.items()}
     L = loss_mod.AdversarialLoss() if cfg["loss"] == "adversarial-loss" else loss_mod.HingeLoss()
-    trainer_mod.Trainer.save_classobj = lambda self: None
-    return trainer_mod.Trainer(None, _Logger(tmp_path), models, opts, L, dict(cfg, config_path="")), models, opts
+    return trainer_without_pickles(trainer_mod, None, _Logger(tmp_path), models, opts, L, dict(cfg, config_path="")), models, opts
 
 
 @pytest.mark.parametrize("geo", [("depth", 1), ("segmentation", 25)])

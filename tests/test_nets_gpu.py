@@ -14,7 +14,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from golden_util import CASES, check_digest, expected_losses, load_case  # noqa: E402
-from helpers import cos_sim, rel_err  # noqa: E402
+from helpers import cos_sim, rel_err, trainer_without_pickles  # noqa: E402
 from oracle import dcvgan_oracle as orc  # noqa: E402
 
 
@@ -254,7 +254,7 @@ def _run_side_by_side(cfg, init, iters, precision, tmp_path, batch_seeds, step_s
     opts = {k: torch.optim.Adam(m.parameters(), lr=cfg[k]["optimizer"]["lr"], betas=(0.5, 0.999),
                                 weight_decay=cfg[k]["optimizer"]["decay"]) for k, m in models.items()}
     L = loss_mod.AdversarialLoss() if cfg["loss"] == "adversarial-loss" else loss_mod.HingeLoss()
-    tr = trainer_mod.Trainer(None, _Logger(tmp_path), models, opts, L, dict(cfg, config_path=""))
+    tr = trainer_without_pickles(trainer_mod, None, _Logger(tmp_path), models, opts, L, dict(cfg, config_path=""))
     o = orc.OracleTrainer(cfg, {k: {a: b.clone() for a, b in v.items()} for k, v in init.items()})
     o.capture_grads = True
     out = []
@@ -385,8 +385,7 @@ def test_cuda_graph_replay_of_the_step(tmp_path):
     models = build_models(cfg, init, "bf16")
     engine.set_rng_mode("device")
     opts = {k: torch.optim.Adam(m.parameters(), lr=2e-4, betas=(0.5, 0.999), weight_decay=1e-5) for k, m in models.items()}
-    trainer_mod.Trainer.save_classobj = lambda self: None
-    tr = trainer_mod.Trainer(None, _Logger(tmp_path), models, opts, loss_mod.HingeLoss(), dict(cfg, config_path=""))
+    tr = trainer_without_pickles(trainer_mod, None, _Logger(tmp_path), models, opts, loss_mod.HingeLoss(), dict(cfg, config_path=""))
     assert tr.use_cuda_graph
     torch.manual_seed(3)
     xc, xg = orc.synthetic_batch(cfg, cfg["batchsize"], 1)

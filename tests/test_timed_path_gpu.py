@@ -14,7 +14,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from helpers import cos_sim, rel_err  # noqa: E402
+from helpers import cos_sim, rel_err, trainer_without_pickles  # noqa: E402
 from oracle import dcvgan_oracle as orc  # noqa: E402
 from test_nets_gpu import _Logger, _mods, _net_cosines, build_models, small_cfg  # noqa: E402
 
@@ -34,8 +34,7 @@ def _trainer(cfg, init, precision, tmp_path, rng_mode):
     opts = {k: torch.optim.Adam(m.parameters(), lr=cfg[k]["optimizer"]["lr"], betas=(0.5, 0.999),
                                 weight_decay=cfg[k]["optimizer"]["decay"]) for k, m in models.items()}
     L = loss_mod.AdversarialLoss() if cfg["loss"] == "adversarial-loss" else loss_mod.HingeLoss()
-    trainer_mod.Trainer.save_classobj = lambda self: None
-    return trainer_mod.Trainer(None, _Logger(tmp_path), models, opts, L, dict(cfg, config_path="")), models, engine
+    return trainer_without_pickles(trainer_mod, None, _Logger(tmp_path), models, opts, L, dict(cfg, config_path="")), models, engine
 
 
 def test_graph_replay_batch32_bf16_matches_oracle(tmp_path):
