@@ -269,6 +269,25 @@ act_bwd_kernel(const T* __restrict__ da, int64_t ldda, const T* __restrict__ a, 
   }
 }
 
+// planar fp32 (N, C, T, H, W) -> channels-last bf16, one thread per pixel: the reads of a warp are contiguous in every channel plane
+__global__ void __launch_bounds__(256)
+to_cl_px_bf16_kernel(const float* __restrict__ src, int64_t sn, int64_t sc, int64_t st, int64_t sh, int64_t sw, int N, int C,
+                     int Tn, int H, int W, __nv_bfloat16* __restrict__ dst, int64_t ld) {
+  pdl_wait(); pdl_trigger();
+  const int64_t total = (int64_t)N * Tn * H * W;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(r % W); int64_t q = r / W;
+    const int h = (int)(q % H); q /= H;
+    const int t = (int)(q % Tn); const int n = (int)(q / Tn);
+    const float* p = src + n * sn + t * st + h * sh + w * sw;
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = c < C ? p[c * sc] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if (c < C) dst[r * ld + c] = __float2bfloat16_rn(v[c]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 add_noise_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ noise, float sigma, int64_t rows,
@@ -1443,6 +1462,11 @@ int dcv_to_channels_last(int dtype, const float* src, int64_t sn, int64_t sc, in
                          int C, int T_, int H, int W, void* dst, int64_t ld, void* stream) {
   const int64_t total = (int64_t)N * T_ * H * W * C;
   if (total == 0) return 0;
+  if (dtype == DCV_BF16 && C <= 4) {
+    launch_k(to_cl_px_bf16_kernel, ew_blocks(total / C, 2), 256, 0, as_stream(stream), src, sn, sc, st, sh, sw, N, C, T_, H, W,
+             (__nv_bfloat16*)dst, ld);
+    return check_launch("to_channels_last_px");
+  }
   DISPATCH_T(dtype, launch_k(to_cl_kernel<T>, ew_blocks(total, 4), 256, 0, as_stream(stream), src, sn, sc, st, sh, sw, N, C, T_,
                                                                                         H, W, (T*)dst, ld));
   return check_launch("to_channels_last");
