@@ -32,13 +32,13 @@ namespace dcv {
 // Result-preserving tuning switches (row-halo sharing off, forced M-tile count, direct-store epilogue, extra wgrad split
 // waves ...) are explicit process state set through dcv_set_tuning(), never read from the environment; the parity tests
 // flip them to cover every code path of the kernels (tests/test_ops_gpu.py::test_conv_tcgen05_kernel_variants).
-struct Tuning { int nohalo, mt, no_tma_store, no_narrow_tma_store, wgrad_waves, no_gemv, no_tapgroup, no_fused_stats, sm_reserve, pdl, no_nsplit, no_wgrad_halo, wgrad_halo4, no_wgrad_whalo; };
-static Tuning g_tune = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+struct Tuning { int nohalo, mt, no_tma_store, no_narrow_tma_store, wgrad_waves, no_gemv, no_tapgroup, no_fused_stats, sm_reserve, pdl, no_nsplit, no_wgrad_halo, wgrad_halo4, no_wgrad_whalo, wgrad_g, wgrad_ns; };
+static Tuning g_tune = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 int set_tuning(const char* key, int value) {
   struct { const char* k; int* v; } tab[] = {{"nohalo", &g_tune.nohalo}, {"mt", &g_tune.mt}, {"no_tma_store", &g_tune.no_tma_store},
       {"no_narrow_tma_store", &g_tune.no_narrow_tma_store}, {"wgrad_waves", &g_tune.wgrad_waves}, {"no_gemv", &g_tune.no_gemv},
       {"no_tapgroup", &g_tune.no_tapgroup}, {"no_fused_stats", &g_tune.no_fused_stats}, {"sm_reserve", &g_tune.sm_reserve},
-      {"pdl", &g_tune.pdl}, {"no_nsplit", &g_tune.no_nsplit}, {"no_wgrad_halo", &g_tune.no_wgrad_halo}, {"wgrad_halo4", &g_tune.wgrad_halo4}, {"no_wgrad_whalo", &g_tune.no_wgrad_whalo}};
+      {"pdl", &g_tune.pdl}, {"no_nsplit", &g_tune.no_nsplit}, {"no_wgrad_halo", &g_tune.no_wgrad_halo}, {"wgrad_halo4", &g_tune.wgrad_halo4}, {"no_wgrad_whalo", &g_tune.no_wgrad_whalo}, {"wgrad_g", &g_tune.wgrad_g}, {"wgrad_ns", &g_tune.wgrad_ns}};
   for (auto& t : tab) if (!strcmp(t.k, key)) { *t.v = value; return 0; }
   DCV_REQUIRE(false, "dcv_set_tuning: unknown key '%s'", key);
 }
@@ -1673,12 +1673,20 @@ static void wgrad_tc_plan(const dcv_geom* g, TcWgradP* p, int* splits) {
   p->cbA = block_width(g->Cl); p->nA = 128 / p->cbA; p->clchunks = g->Cl / p->cbA;
   p->blocksA_total = taps * p->clchunks;
   p->cbB = block_width(g->Cs); p->blocksB_total = g->Cs / p->cbB;
-  p->nbB = 256 / p->cbB; if (p->nbB > p->blocksB_total) p->nbB = p->blocksB_total;
+  p->nbB = (g_tune.wgrad_ns > 0 ? g_tune.wgrad_ns : 256) / p->cbB; if (p->nbB < 1) p->nbB = 1;
+  if (p->nbB > p->blocksB_total) p->nbB = p->blocksB_total;
   p->Ns = p->nbB * p->cbB;
   p->layA = layout_code(p->cbA); p->layB = layout_code(p->cbB);
   const int tiles_total = ceil_div(p->blocksA_total, p->nA);
   p->G = 512 / pow2_ceil(p->Ns < 32 ? 32 : p->Ns);
   if (p->G > 4) p->G = 4;
+  // Accumulator tiles per CTA: fewer tiles = more CTAs per pixel range = fewer pixel splits, and every split writes (and the
+  // reduction re-reads) a full fp32 copy of the weight gradient - 39 MB per launch for a 64 -> 128 channel layer with 74 splits.
+  // Measured per iteration (mug-depth, batch 32, same session): four tiles per CTA 9.70 ms, two (one column-halo box pair)
+  // 9.59 ms, ONE (row halo only) 9.47 ms; narrowing the S tile as well (128 / 64 columns) 9.47 / 9.66 ms.  One tile per CTA is
+  // the default; dcv_set_tuning("wgrad_g", 2 | 4) selects the wider plans (parity-tested, incl. the column halo).
+  const int gcap = g_tune.wgrad_g > 0 ? g_tune.wgrad_g : 1;
+  if (p->G > gcap) p->G = gcap;
   if (p->G > tiles_total) p->G = tiles_total;
   // pixels per stage.  Every (tap, channel chunk) block is its own TMA box, so with narrow blocks (16 or 32
   // channels: image-like tensors) a 32-pixel stage is dozens of 1-2 KB boxes and the kernel becomes bound by the TMA

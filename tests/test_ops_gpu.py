@@ -170,7 +170,7 @@ def test_conv_tcgen05_tf32(case):
 
 
 VARIANTS = [{"nohalo": 1}, {"mt": 1}, {"mt": 4}, {"no_tma_store": 1}, {"wgrad_waves": 2}, {"no_tapgroup": 1}, {"sm_reserve": 16},
-            {"pdl": 1}, {"no_nsplit": 1}, {"no_wgrad_halo": 1}, {"wgrad_halo4": 1}, {"no_wgrad_whalo": 1}]
+            {"pdl": 1}, {"no_nsplit": 1}, {"no_wgrad_halo": 1}, {"wgrad_halo4": 1}, {"no_wgrad_whalo": 1}, {"wgrad_g": 4}, {"wgrad_g": 2}, {"wgrad_g": 2, "no_wgrad_whalo": 1}, {"wgrad_ns": 64}]
 
 
 @pytest.mark.parametrize("tune", VARIANTS, ids=["+".join(f"{k}={v}" for k, v in e.items()) for e in VARIANTS])
