@@ -102,10 +102,41 @@ def test_generators_match_oracle(precision, ftol, ctol, geo):
         nets[net] = float((a @ b) / (a.norm() * b.norm()))
     print(f"generators[{precision},{geo[0]}]: xg {e_g:.2e} xc {e_c:.2e} worst per-tensor grad cos {worst:.5f} at {worst_k}; per-network {nets}")
     if precision == "bf16":
-        # bf16 storage at batch 2 / width 8: BatchNorm over 32 samples at the 1x1 bottleneck amplifies rounding, and the
-        # segmentation argmax flips on near-ties; the bf16 gate of the north star is the loss curve (test_curves_gpu.py).
+        # bf16 storage at batch 2 / width 8: BatchNorm over 32 samples at the 1x1 bottleneck amplifies rounding (measured worst
+        # per-tensor cosine 0.81-0.84, per network 0.93-0.96), and with segmentation the argmax of the geometry generator's
+        # bf16 output flips on near-ties, which hands the colour generator a DIFFERENT one-hot input than the oracle's.
         assert e_g < ftol and (e_c < 2 * ftol or geo[0] == "segmentation"), (e_g, e_c)
-        assert worst > (0.5 if geo[0] != "segmentation" else -1.0), worst
+        if geo[0] != "segmentation":
+            assert worst > 0.7 and min(nets.values()) > 0.9, (worst, nets)
+        else:
+            assert nets["ggen"] > 0.99, nets
+        # The colour generator ALONE on a given geometry (identical input, identical noise draws): its own bf16 error.  For
+        # depth / flow the input is the oracle's geometry; for segmentation it is that geometry sharpened to the +-1 one-hot form
+        # of real data (dataset.py:177-181) - a random-init softmax is near-uniform over its 25 classes, and the argmax of its
+        # bf16 copy differs from the fp32 one on near-ties, which is an input difference, not a kernel error.
+        xin, grads_ref, xc_cmp = xg_ref.detach(), {k: v.grad for k, v in Pr["cgen"].items() if v.grad is not None}, xc_ref.detach()
+        if geo[0] == "segmentation":
+            xin = torch.full_like(xin, -1.0).scatter_(1, xin.argmax(1, keepdim=True), 1.0)
+            Pc = orc.require_grad({a: b.clone() for a, b in P["cgen"].items()})
+            torch.manual_seed(11)
+            with torch.no_grad():
+                orc.ggen_sample_videos(P["ggen"], B, cfg, True)             # consumes the geometry generator's draws
+            xc_cmp = orc.cgen_forward_videos(Pc, xin, cfg, True)
+            (xc_cmp * d_xc).sum().backward()
+            grads_ref, xc_cmp = {k: v.grad for k, v in Pc.items() if v.grad is not None}, xc_cmp.detach()
+        for m in models.values():
+            m.zero_grad()
+        torch.manual_seed(11)
+        models["ggen"].sample_videos(B)                                   # consumes the same draws
+        xc2 = models["cgen"].forward_videos(xin.cuda())
+        e_c2 = rel_err(xc2.detach().cpu(), xc_cmp)
+        (xc2 * d_xc.cuda()).sum().backward()
+        named = [(k, p) for k, p in models["cgen"].named_parameters() if k in grads_ref]
+        mine = torch.cat([p.grad.cpu().flatten().double() for _, p in named])
+        ref = torch.cat([grads_ref[k].flatten().double() for k, _ in named])
+        c2 = float((mine @ ref) / (mine.norm() * ref.norm()))
+        print(f"  colour generator alone on a fixed geometry: xc {e_c2:.2e}, per-network grad cos {c2:.5f}")
+        assert e_c2 < ftol and c2 > 0.95, (e_c2, c2)       # measured 1.4e-2 .. 1.6e-2 and 0.963 .. 0.971 for the three geometries
         return
     assert e_g < ftol and e_c < ftol, (e_g, e_c)
     assert worst > ctol, worst
