@@ -196,7 +196,7 @@ def run_reference(args, cfg_name):
     line = {"impl": "reference", "metric": "train iters/sec (16x64x64 clips, batch 32)", "value": ips, "unit": "iters/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spi * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config/{cfg_name}.yml (normalised) training step, batch 32, 16x64x64"},
+            "config": {"workload": f"config/{cfg_name}.yml (normalised) training step, batch 32 per GPU, 16x64x64, D and G both update every iteration"},
             "cpu_baseline": {"value": ips, "unit": "iters/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": ips, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
