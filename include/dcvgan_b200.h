@@ -79,7 +79,12 @@ long long dcv_launch_count(void);
 /* Result-preserving tuning switches of the tcgen05 kernels (process-wide; never read from the environment):
  * "nohalo", "mt" (0 = automatic, 1/2/4 forced M tiles per work item), "no_tma_store", "no_narrow_tma_store",
  * "wgrad_waves", "no_gemv", "no_tapgroup", "no_fused_stats", "sm_reserve" (SMs the persistent kernels leave free,
- * for a collective running beside them), "pdl" (1 = launch with the programmatic-dependent-launch attribute; measured slower, off by default).  The parity tests flip them to cover every kernel path. */
+ * for a collective running beside them), "pdl" (1 = launch with the programmatic-dependent-launch attribute; measured slower,
+ * off by default), "no_nsplit" (1 = keep the widest N tile even when a convolution has fewer work items than half the SMs),
+ * weight-gradient plans: "wgrad_g" (accumulator tiles per CTA: 0 = default 1; 2 / 4 = the older plans), "wgrad_ns" (S-tile
+ * columns, 0 = 256), "no_wgrad_halo" (one TMA box per tap instead of a row-halo box per tap pair), "no_wgrad_whalo" (no
+ * column halo in the 2- / 4-tile plans), "wgrad_halo4" (row halo for 4-pixel-wide maps as well).  The parity tests flip
+ * them to cover every kernel path. */
 int dcv_set_tuning(const char* key, int value);
 
 /* ---- weight packing -------------------------------------------------------------------------
