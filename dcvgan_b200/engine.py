@@ -17,7 +17,13 @@ from ._lib import ACT_LEAKY, ACT_NONE, ACT_TANH
 from .ops import Act, ConvSpec
 
 BN_EPS, BN_MOM = 1e-5, 0.1
+# BatchNorm batch statistics accumulated in the convolution's own epilogue (dcv_conv_stats) for output tensors of at most this
+# many MiB (0 = never; DCV_FUSED_BN_STATS=1 = always).  Measured per iteration at the end of round 2 (mug-depth, batch 32, one
+# session): off 9.465 ms, <= 2 MiB 9.424, <= 8 9.414, <= 32 9.393, <= 70 9.362, <= 140 9.360, always 9.372 - every tensor but
+# the 268 MiB output of cgen up_blocks.5 (whose small-K convolution is bound by its store epilogue) gains: the separate
+# statistics pass costs a read of the tensor plus ~10 us of fixed latency per launch.
 FUSED_BN_STATS = os.environ.get("DCV_FUSED_BN_STATS", "0") == "1"
+FUSED_BN_STATS_MAX_MB = float(os.environ.get("DCV_FUSED_BN_STATS_MAX_MB", "140"))
 TAP_UNROLL = os.environ.get("DCV_NO_TAP_UNROLL", "0") != "1"   # tiny-Cout transposed convolutions as 1x1 GEMM + col2im
 
 
@@ -250,11 +256,9 @@ class Block:
             return ctx
         bn = self.bn
         zp = z.padded_to(cout_p)
-        # BatchNorm batch statistics accumulated in the convolution's epilogue (dcv_conv_stats): correct and tested, but
-        # measured SLOWER in the step than the separate streaming pass (11.49 vs 11.32 ms/step at batch 32): the large
-        # BatchNorm tensors belong to the small-K layers whose store epilogue is already on the critical path, and the
-        # 32-row column sums triple its instruction count.  Opt-in: FUSED_BN_STATS / DCV_FUSED_BN_STATS=1.
-        slots = ops.conv_stats_slots(g, spec.fwd_dir, x_used, zp) if (FUSED_BN_STATS and training and impl == ops.IMPL_TC and zp.c == z.c) else 0
+        # statistics in the convolution's epilogue where that pays (see FUSED_BN_STATS_MAX_MB), else the streaming pass
+        fuse_stats = FUSED_BN_STATS or z.rows * z.c * 2 <= FUSED_BN_STATS_MAX_MB * (1 << 20)
+        slots = ops.conv_stats_slots(g, spec.fwd_dir, x_used, zp) if (fuse_stats and training and impl == ops.IMPL_TC and zp.c == z.c) else 0
         if slots > 0:
             partials = ops.conv_stats(g, spec.fwd_dir, x_used.padded_to(cin_p), wp, zp, slots)
             mean, invstd = ops.bn_finalize(partials, z.rows, BN_EPS, BN_MOM, bn.running_mean, bn.running_var, bn.num_batches_tracked)
